@@ -1,0 +1,123 @@
+// TEST INFRASTRUCTURE — C-callable shims around the UNMODIFIED reference classes, so that the
+// Python tests can call the reference's own component functions (SURVEY.md §8c "component-level
+// oracle").  Built into oracle/_ref/libdftatom_ref.so by oracle/Makefile from the headers under
+// /root/reference/DFTAtom (not copied).  Nothing in the product links against this.
+#include <vector>
+#include <algorithm>
+#include <limits>
+#include <cmath>
+#include <math.h>
+#include <cstring>
+#include "Numerov.h"
+#include "AufbauPrinciple.h"
+#include "PoissonSolver.h"
+#include "Integral.h"
+#include "VWNExcCor.h"
+
+using NumerovNU = DFT::Numerov<DFT::NumerovFunctionNonUniformGrid>;
+
+extern "C" {
+
+// Numerov.h:272-349
+int ref_numerov_count_nodes(const double* V, int n_nodes, double delta, double rmax, int l, double E, int nodes_limit)
+{
+    DFT::Potential pot;
+    pot.m_potentialValues.assign(V, V + n_nodes);
+    NumerovNU num(pot, delta, rmax, n_nodes);
+    int cnt = 0;
+    num.SolveSchrodingerCountNodes(n_nodes - 1, l, E, n_nodes - 1, nodes_limit, cnt);
+    return cnt;
+}
+
+// Numerov.h:351-401
+double ref_numerov_solution_in_zero(const double* V, int n_nodes, double delta, double rmax, int l, double E)
+{
+    DFT::Potential pot;
+    pot.m_potentialValues.assign(V, V + n_nodes);
+    NumerovNU num(pot, delta, rmax, n_nodes);
+    return num.SolveSchrodingerSolutionInZero(n_nodes - 1, l, E, n_nodes - 1);
+}
+
+// batched versions (one Numerov object, many (l,E) lanes) for speed
+void ref_numerov_lanes(const double* V, int n_nodes, double delta, double rmax, int n_lanes,
+                       const int* l, const double* E, const int* nodes_limit, double* y0, int* count)
+{
+    DFT::Potential pot;
+    pot.m_potentialValues.assign(V, V + n_nodes);
+    NumerovNU num(pot, delta, rmax, n_nodes);
+    for (int k = 0; k < n_lanes; ++k) {
+        if (y0) y0[k] = num.SolveSchrodingerSolutionInZero(n_nodes - 1, l[k], E[k], n_nodes - 1);
+        if (count) {
+            int cnt = 0;
+            num.SolveSchrodingerCountNodes(n_nodes - 1, l[k], E[k], n_nodes - 1, nodes_limit[k], cnt);
+            count[k] = cnt;
+        }
+    }
+}
+
+// Numerov.h:403-504
+long ref_numerov_match(const double* V, int n_nodes, double delta, double rmax, int l, double E, double* psi)
+{
+    DFT::Potential pot;
+    pot.m_potentialValues.assign(V, V + n_nodes);
+    NumerovNU num(pot, delta, rmax, n_nodes);
+    long int matchPoint = 0;
+    std::vector<double> r = num.SolveSchrodingerMatchSolutionCompletely(n_nodes - 1, l, E, n_nodes - 1, matchPoint);
+    std::memcpy(psi, r.data(), sizeof(double) * n_nodes);
+    return matchPoint;
+}
+
+// PoissonSolver.h:51-81
+void ref_poisson_nonuniform(int levels, double delta, int Z, double rmax, const double* density, double* U)
+{
+    DFT::PoissonSolver ps(levels, delta);
+    const int n = DFT::PoissonSolver::GetNumberOfNodes(levels);
+    std::vector<double> d(density, density + n);
+    std::vector<double> u = ps.SolvePoissonNonUniform(Z, rmax, d);
+    std::memcpy(U, u.data(), sizeof(double) * n);
+}
+
+// VWNExcCor.h:73-128
+void ref_vwn_lda(const double* rho, int n, double* vexc, double* eexcdif)
+{
+    std::vector<double> d(rho, rho + n);
+    std::vector<double> v = DFT::VWNExchCor::Vexc(d);
+    std::vector<double> e = DFT::VWNExchCor::eexcDif(d);
+    std::memcpy(vexc, v.data(), sizeof(double) * n);
+    std::memcpy(eexcdif, e.data(), sizeof(double) * n);
+}
+
+// VWNExcCor.h:134-312
+void ref_vwn_lsda(const double* na, const double* nb, int n, double* va, double* vb, double* vexc, double* eexcdif)
+{
+    std::vector<double> a(na, na + n), b(nb, nb + n), xa, xb;
+    std::vector<double> v = DFT::VWNExchCor::Vexc(a, b, xa, xb);
+    std::vector<double> e = DFT::VWNExchCor::eexcDif(a, b);
+    std::memcpy(va, xa.data(), sizeof(double) * n);
+    std::memcpy(vb, xb.data(), sizeof(double) * n);
+    std::memcpy(vexc, v.data(), sizeof(double) * n);
+    std::memcpy(eexcdif, e.data(), sizeof(double) * n);
+}
+
+// Integral.h:50-73
+double ref_simpson38(double delta, const double* v, int n)
+{
+    std::vector<double> d(v, v + n);
+    return DFT::Integral::Simpson38(delta, d);
+}
+
+// AufbauPrinciple.h:36-75 + the driver's sort (DFTAtom.cpp:367); out = triples (N0, L, occ); returns count
+int ref_aufbau(int Z, int* out, int max_levels)
+{
+    std::vector<DFT::Subshell> lv = DFT::AufbauPrinciple::GetSubshells(Z);
+    std::sort(lv.begin(), lv.end());
+    int k = 0;
+    for (const auto& s : lv) {
+        if (k >= max_levels) break;
+        out[3 * k] = s.m_N; out[3 * k + 1] = s.m_L; out[3 * k + 2] = s.m_nrElectrons;
+        ++k;
+    }
+    return k;
+}
+
+}

@@ -1,0 +1,31 @@
+// TEST INFRASTRUCTURE — headless driver for the UNMODIFIED reference solver.
+// Compiled by oracle/Makefile against /root/reference/DFTAtom/{DFTAtom,PoissonSolver}.cpp where
+// they lie (never copied into this repo).  Output: oracle/_ref/dftatom_ref (git-ignored).
+// Replaces the wx worker-thread lambda of DFTAtomFrame.cpp:185-198 (the only caller of the solver).
+//
+// usage: dftatom_ref Z levels mixing rmax delta method(0=LDA,1=LSDA)
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <algorithm>
+#include <limits>
+#include <cmath>
+#include "DFTAtom.h"
+
+int main(int argc, char** argv)
+{
+    if (argc < 7) {
+        std::fprintf(stderr, "usage: %s Z levels mixing rmax delta method\n", argv[0]);
+        return 2;
+    }
+    const int Z = std::atoi(argv[1]);
+    const int levels = std::atoi(argv[2]);
+    const double mixing = std::atof(argv[3]);
+    const double rmax = std::atof(argv[4]);
+    const double delta = std::atof(argv[5]);
+    const int method = std::atoi(argv[6]);
+    if (method) DFT::DFTAtom::CalculateNonUniformLSDA(Z, levels, mixing, rmax, delta);
+    else DFT::DFTAtom::CalculateNonUniformLDA(Z, levels, mixing, rmax, delta);
+    std::printf("\n");
+    return 0;
+}

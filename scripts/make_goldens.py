@@ -1,0 +1,81 @@
+#!/usr/bin/env python
+"""Generate golden fixtures by RUNNING THE UNMODIFIED REFERENCE (oracle/_ref/dftatom_ref_hp, built by
+oracle/Makefile from /root/reference) and parsing its stdout.  Test infrastructure only.
+
+usage: python scripts/make_goldens.py NAME [--jobs J]
+  NAME in: small, argon, radon, sweep, lsda_batch
+Writes tests/golden/<NAME>.json.  Each atom record holds every SCF step the reference printed
+(eigenvalues + five energies, 17 significant digits) unless --final-only semantics apply (sweep,
+lsda_batch keep per-step Etotal and eigenvalues of the last step only, to keep fixtures small).
+"""
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from dftatom_b200.report import parse_report  # noqa: E402
+
+REF_HP = os.path.join(ROOT, "oracle", "_ref", "dftatom_ref_hp")
+
+C1 = dict(levels=14, mixing=0.5, rmax=25.0, delta=0.0005, method=0)
+CONFIGS = {
+    # small cases the CPU test-suite can re-run in seconds
+    "small": [dict(Z=z, levels=10, mixing=0.5, rmax=15.0, delta=0.004, method=m)
+              for z, m in [(1, 0), (2, 0), (3, 1), (10, 0), (7, 1), (26, 0), (64, 1), (92, 0)]]
+             + [dict(Z=2, levels=12, mixing=0.5, rmax=15.0, delta=0.001, method=0),
+                dict(Z=3, levels=12, mixing=0.5, rmax=15.0, delta=0.001, method=1)],
+    "argon": [dict(Z=18, **C1)],
+    "radon": [dict(Z=86, levels=17, mixing=0.5, rmax=50.0, delta=0.0001, method=1)],
+    "sweep": [dict(Z=z, **C1) for z in range(1, 93)],
+    "lsda_batch": [dict(Z=z, levels=16, mixing=0.5, rmax=50.0, delta=0.0002, method=1)
+                   for z in list(range(21, 31)) + list(range(57, 72))],
+}
+FINAL_ONLY = {"sweep", "lsda_batch"}
+
+
+def run_one(cfg):
+    t0 = time.time()
+    out = subprocess.run([REF_HP, str(cfg["Z"]), str(cfg["levels"]), repr(cfg["mixing"]), repr(cfg["rmax"]),
+                          repr(cfg["delta"]), str(cfg["method"])], capture_output=True, text=True, check=True).stdout
+    rec = parse_report(out)
+    rec["options"] = cfg
+    rec["ref_seconds"] = round(time.time() - t0, 2)
+    return rec
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("name", choices=sorted(CONFIGS))
+    ap.add_argument("--jobs", type=int, default=max(1, (os.cpu_count() or 2) - 2))
+    a = ap.parse_args()
+    cfgs = CONFIGS[a.name]
+    # longest first
+    order = sorted(range(len(cfgs)), key=lambda i: -cfgs[i]["Z"])
+    res = [None] * len(cfgs)
+    with ThreadPoolExecutor(a.jobs) as ex:
+        futs = {i: ex.submit(run_one, cfgs[i]) for i in order}
+        for i, f in futs.items():
+            res[i] = f.result()
+            print(f"Z={cfgs[i]['Z']} steps={len(res[i]['steps'])} finished={res[i]['finished']} t={res[i]['ref_seconds']}s", flush=True)
+    if a.name in FINAL_ONLY:
+        for r in res:
+            r["etotal_per_step"] = [s["Etotal"] for s in r["steps"]]
+            r["steps_kept"] = "last"
+            r["n_steps"] = len(r["steps"])
+            r["steps"] = r["steps"][-1:]
+    meta = dict(generator="scripts/make_goldens.py", source="oracle/_ref/dftatom_ref_hp (unmodified reference, g++ -O2, glibc)",
+                name=a.name)
+    path = os.path.join(ROOT, "tests", "golden", a.name + ".json")
+    with open(path, "w") as f:
+        json.dump(dict(meta=meta, atoms=res), f, separators=(",", ":"))
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()
