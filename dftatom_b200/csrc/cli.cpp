@@ -1,0 +1,143 @@
+// dftatom — headless replacement of the reference's wxWidgets shell (DFTAtomApp / DFTAtomFrame / OptionsFrame).
+// Flags carry the reference's Options fields with the same defaults (Options.cpp:6) and dialog ranges
+// (OptionsFrame.cpp:46,152-173); the output is the text the reference's worker thread prints (DFTAtomFrame.cpp:185-198
+// -> DFTAtom.cpp:358-490 / :857-1021).  All computation goes through the C ABI of include/dftatom_b200.h.
+//
+//   dftatom [--Z 18 | --Z 1-92 | --Z 21,22,57] [--levels 14] [--delta 0.0005] [--mixing 0.5] [--rmax 25]
+//           [--method 0|1|lda|lsda] [--precision 6] [--json] [--quiet-steps] [--device 0] [--ini DFTAtom.ini]
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <string>
+#include <vector>
+#include "../../include/dftatom_b200.h"
+
+static const char kOrb[] = "spdf";
+
+static std::vector<int> parse_z(const std::string& s)
+{
+    std::vector<int> out;
+    size_t pos = 0;
+    while (pos < s.size()) {
+        size_t comma = s.find(',', pos);
+        std::string tok = s.substr(pos, comma == std::string::npos ? std::string::npos : comma - pos);
+        size_t dash = tok.find('-', 1);
+        if (dash != std::string::npos) {
+            int a = std::atoi(tok.substr(0, dash).c_str()), b = std::atoi(tok.substr(dash + 1).c_str());
+            for (int z = a; z <= b; ++z) out.push_back(z);
+        } else if (!tok.empty()) out.push_back(std::atoi(tok.c_str()));
+        if (comma == std::string::npos) break;
+        pos = comma + 1;
+    }
+    return out;
+}
+
+// reads the keys the reference persists with wxFileConfig (Options.cpp:42-49): Z, MultigridLevels, MaxR, deltaGrid, alpha, Method
+static void read_ini(const char* path, dftatom_options& o)
+{
+    std::ifstream f(path);
+    std::string line;
+    while (std::getline(f, line)) {
+        size_t eq = line.find('=');
+        if (eq == std::string::npos) continue;
+        std::string k = line.substr(0, eq), v = line.substr(eq + 1);
+        while (!k.empty() && (k.back() == ' ' || k.back() == '\t')) k.pop_back();
+        while (!k.empty() && (k[0] == '/' || k[0] == ' ')) k.erase(0, 1);
+        if (k == "Z") o.Z = std::atoi(v.c_str());
+        else if (k == "MultigridLevels") o.levels = std::atoi(v.c_str());
+        else if (k == "MaxR") o.max_r = std::atof(v.c_str());
+        else if (k == "deltaGrid") o.delta = std::atof(v.c_str());
+        else if (k == "alpha") o.mixing = std::atof(v.c_str());
+        else if (k == "Method") o.method = std::atoi(v.c_str());
+    }
+}
+
+static void print_conf(const dftatom_level* lv, int n)
+{
+    for (int k = 0; k < n; ++k) std::printf("%d%c%d ", lv[k].n, kOrb[lv[k].l], lv[k].occ);
+}
+
+int main(int argc, char** argv)
+{
+    dftatom_options base = { 36, 12, 10.0, 0.001, 0.5, 0 };     // Options.cpp:6
+    std::vector<int> zs;
+    int precision = 6, device = 0;
+    bool json = false, quiet = false;
+    for (int i = 1; i < argc; ++i) {
+        std::string a = argv[i];
+        auto next = [&]() -> const char* { if (i + 1 >= argc) { std::fprintf(stderr, "missing value for %s\n", a.c_str()); std::exit(2); } return argv[++i]; };
+        if (a == "--Z") zs = parse_z(next());
+        else if (a == "--levels") base.levels = std::atoi(next());
+        else if (a == "--delta") base.delta = std::atof(next());
+        else if (a == "--mixing" || a == "--alpha") base.mixing = std::atof(next());
+        else if (a == "--rmax") base.max_r = std::atof(next());
+        else if (a == "--method") { std::string m = next(); base.method = (m == "1" || m == "lsda" || m == "LSDA") ? 1 : 0; }
+        else if (a == "--precision") precision = std::atoi(next());
+        else if (a == "--device") device = std::atoi(next());
+        else if (a == "--ini") read_ini(next(), base);
+        else if (a == "--json") json = true;
+        else if (a == "--quiet-steps") quiet = true;
+        else if (a == "--help" || a == "-h") {
+            std::printf("usage: dftatom [--Z 18|1-92|a,b,c] [--levels L] [--delta d] [--mixing a] [--rmax R] [--method 0|1] "
+                        "[--precision p] [--json] [--quiet-steps] [--device k] [--ini file]\n");
+            return 0;
+        } else { std::fprintf(stderr, "unknown flag %s\n", a.c_str()); return 2; }
+    }
+    if (zs.empty()) zs.push_back(base.Z);
+    const int n = (int)zs.size();
+    std::vector<dftatom_options> opts(n, base);
+    for (int k = 0; k < n; ++k) opts[k].Z = zs[k];
+
+    dftatom_ctx* ctx = nullptr;
+    if (dftatom_create(&ctx, device) != DFTATOM_OK) { std::fprintf(stderr, "dftatom: %s\n", dftatom_last_error()); return 1; }
+    const int stride = DFTATOM_MAX_STEPS_LSDA;
+    std::vector<dftatom_result> res(n);
+    std::vector<dftatom_step> steps((size_t)n * stride);
+    if (dftatom_solve_batch(ctx, opts.data(), n, res.data(), steps.data(), stride) != DFTATOM_OK) {
+        std::fprintf(stderr, "dftatom: %s\n", dftatom_last_error());
+        dftatom_destroy(ctx);
+        return 1;
+    }
+    double ms = 0; long long launches = 0;
+    dftatom_last_timing(ctx, &ms, &launches);
+
+    if (json) std::printf("[");
+    for (int a = 0; a < n; ++a) {
+        const dftatom_result& R = res[a];
+        if (json) {
+            std::printf("%s{\"Z\":%d,\"method\":%d,\"status\":%d,\"n_steps\":%d,\"Etotal\":%.17g,\"Ekin\":%.17g,\"Ecoul\":%.17g,\"Eenuc\":%.17g,\"Exc\":%.17g,\"levels\":[",
+                        a ? "," : "", opts[a].Z, opts[a].method, R.status, R.n_steps, R.Etotal, R.Ekin, R.Ecoul, R.Eenuc, R.Exc);
+            bool first = true;
+            for (int s = 0; s < R.n_spin; ++s)
+                for (int k = 0; k < R.n_levels[s]; ++k) {
+                    const dftatom_level& L = R.levels[s][k];
+                    std::printf("%s{\"spin\":%d,\"n\":%d,\"l\":%d,\"occ\":%d,\"nodes\":%d,\"E\":%.17g}", first ? "" : ",", s, L.n, L.l, L.occ, L.nodes, L.E);
+                    first = false;
+                }
+            std::printf("]}");
+            continue;
+        }
+        std::printf("Computing atom with Z=%d using %s with non-uniform grid\n", opts[a].Z, opts[a].method ? "LSDA" : "LSD");   // DFTAtom.cpp:358,857
+        for (int sp = quiet ? R.n_steps - 1 : 0; sp < R.n_steps; ++sp) {
+            const dftatom_step& S = steps[(size_t)a * stride + sp];
+            std::printf("Step: %d\n", sp);
+            for (int s = 0; s < R.n_spin; ++s)
+                for (int k = 0; k < R.n_levels[s]; ++k)
+                    std::printf("Energy %d%c: %.*f Num nodes: %d\n", R.levels[s][k].n, kOrb[R.levels[s][k].l], precision, S.E[s][k], R.levels[s][k].nodes);
+            std::printf("Etotal = %.*f Ekin = %.*f Ecoul = %.*f Eenuc = %.*f Exc = %.*f\n", precision, S.Etotal, precision, S.Ekin, precision, S.Ecoul,
+                        precision, S.Eenuc, precision, S.Exc);
+            if (sp == R.n_steps - 1 && R.status == DFTATOM_CONVERGED) std::printf("\nFinished!\n\n");
+            else std::printf("********************************************************************************\n");
+        }
+        if (opts[a].method) {
+            std::printf("Alpha: "); print_conf(R.sorted[0], R.n_levels[0]);
+            std::printf("\nBeta: "); print_conf(R.sorted[1], R.n_levels[1]);
+        } else print_conf(R.sorted[0], R.n_levels[0]);
+        std::printf("\n");
+    }
+    if (json) std::printf("]\n");
+    std::fprintf(stderr, "dftatom: %d atom(s), device time %.2f ms, %lld kernel launches\n", n, ms, launches);
+    dftatom_destroy(ctx);
+    return 0;
+}

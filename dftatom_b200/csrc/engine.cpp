@@ -1,0 +1,633 @@
+// Host side of libdftatom_b200.so: context, grid tables, device buffers, the SCF launch sequence and the C ABI
+// declared in include/dftatom_b200.h.  The host only enqueues kernels; densities, potentials, the energy search
+// state, mixing and the stop test live on the device (north_star: no per-step host round trip).
+#include "internal.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+
+namespace dft {
+
+static thread_local std::string g_err;
+void set_error(const std::string& s) { g_err = s; }
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) { set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e)); return DFTATOM_E_CUDA; }
+        cap = bytes;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() { return static_cast<T*>(p); }
+};
+
+struct GridKey {
+    int L; double delta, max_r;
+    bool operator<(const GridKey& o) const { return std::tie(L, delta, max_r) < std::tie(o.L, o.delta, o.max_r); }
+};
+
+struct GridEntry { GridDev dev; DevBuf mem; };
+
+}  // namespace dft
+
+using namespace dft;
+
+struct dftatom_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::map<GridKey, GridEntry> grids;
+    // options
+    int max_vcycles = 100;
+    int floor_stop = 1;
+    int r_segments = 0;
+    int profile = 0;
+    dftatom_kernel_profile prof[DFTATOM_K_COUNT] = {};
+    // reusable buffers
+    DevBuf atoms, astate, orbs, ss, rho, rhot, vpot, atab, psi, match_pt, phi, src, zbc, tab_of, steps, n_active;
+    DevBuf scratch[8];
+    int* h_active = nullptr;       // pinned
+    // timing of the last solve
+    double last_ms = 0.;
+    long long last_launches = 0;
+};
+
+namespace dft {
+
+static int get_grid(dftatom_ctx* c, int L, double delta, double max_r, GridDev** out)
+{
+    const GridKey key{ L, delta, max_r };
+    auto it = c->grids.find(key);
+    if (it != c->grids.end()) { *out = &it->second.dev; return 0; }
+    const int N = (1 << L) + 1;
+    // host tables with the same libm the CPU reference uses (exp), uploaded once per grid
+    const int n_tab = 9;
+    std::vector<double> h((size_t)n_tab * N);
+    double* r = &h[0]; double* ex = &h[(size_t)N]; double* sqex = &h[(size_t)2 * N]; double* b12 = &h[(size_t)3 * N];
+    double* c6 = &h[(size_t)4 * N]; double* k2 = &h[(size_t)5 * N]; double* wjac = &h[(size_t)6 * N];
+    double* psrc = &h[(size_t)7 * N]; double* inv4pr2 = &h[(size_t)8 * N];
+    const double rp = max_r / (std::exp((double)(N - 1) * delta) - 1.);      // DFTAtom.cpp:356
+    const double rp2d2 = rp * rp * (delta * delta);
+    for (int i = 0; i < N; ++i) {
+        ex[i] = std::exp((double)i * delta);
+        r[i] = rp * (ex[i] - 1.);                                            // Numerov.h:181-184
+        sqex[i] = std::exp((double)i * delta * 0.5);                         // DFTAtom.cpp:42
+        const double K = rp2d2 * std::exp((double)i * (2. * delta));        // Numerov.h:100
+        b12[i] = i ? K / (12. * r[i] * r[i]) : 0.;
+        c6[i] = K / 6.;
+        k2[i] = 2. * K;
+        const double w = (i == 0 || i == N - 1) ? 1. : ((i % 3 == 0) ? 2. : 3.);   // Integral.h:50-73
+        wjac[i] = 0.375 * w * (rp * delta * ex[i]);                          // jacobian DFTAtom.cpp:47,442
+        psrc[i] = (i == 0 || i == N - 1) ? 0. : r[i] * (kFourPi * K);        // PoissonSolver.h:55-74
+        inv4pr2[i] = i ? 1. / (kFourPi * r[i] * r[i]) : 0.;                  // DFTAtom.cpp:340
+    }
+    GridEntry& e = c->grids[key];
+    int rc = e.mem.ensure(h.size() * sizeof(double));
+    if (rc) { c->grids.erase(key); return rc; }
+    DFT_CHECK(cudaMemcpyAsync(e.mem.p, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    DFT_CHECK(cudaStreamSynchronize(c->stream));
+    double* d = e.mem.as<double>();
+    e.dev.N = N; e.dev.L = L; e.dev.delta = delta; e.dev.rp = rp; e.dev.max_r = max_r;
+    e.dev.r = d; e.dev.ex = d + (size_t)N; e.dev.sqex = d + (size_t)2 * N; e.dev.b12 = d + (size_t)3 * N;
+    e.dev.c6 = d + (size_t)4 * N; e.dev.k2 = d + (size_t)5 * N; e.dev.wjac = d + (size_t)6 * N;
+    e.dev.psrc = d + (size_t)7 * N; e.dev.inv4pr2 = d + (size_t)8 * N;
+    *out = &e.dev;
+    return 0;
+}
+
+static int validate(const dftatom_options& o)
+{   // ranges of the reference's dialog validators, OptionsFrame.cpp:46,152-173 (levels: the class itself accepts any >= 1)
+    if (o.Z < 1 || o.Z > 118) { set_error("Z must be in 1..118"); return DFTATOM_E_BAD_OPTION; }
+    if (o.levels < 4 || o.levels > 20) { set_error("levels must be in 4..20"); return DFTATOM_E_BAD_OPTION; }
+    if (!(o.max_r >= 1. && o.max_r <= 90.)) { set_error("max_r must be in 1..90"); return DFTATOM_E_BAD_OPTION; }
+    if (!(o.delta > 0. && o.delta <= 1.)) { set_error("delta must be in (0,1]"); return DFTATOM_E_BAD_OPTION; }
+    if (!(o.mixing >= 0. && o.mixing <= 1.)) { set_error("mixing must be in [0,1]"); return DFTATOM_E_BAD_OPTION; }
+    if (o.method != 0 && o.method != 1) { set_error("method must be 0 (LDA) or 1 (LSDA)"); return DFTATOM_E_BAD_OPTION; }
+    return 0;
+}
+
+template <class T> static int upload(dftatom_ctx* c, DevBuf& b, const std::vector<T>& h)
+{
+    int rc = b.ensure(std::max<size_t>(h.size(), 1) * sizeof(T));
+    if (rc) return rc;
+    if (!h.empty()) DFT_CHECK(cudaMemcpyAsync(b.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
+}  // namespace dft
+
+extern "C" {
+
+const char* dftatom_last_error(void) { return g_err.c_str(); }
+const char* dftatom_version(void) { return "dftatom_b200 0.1 (sm_100a)"; }
+
+int dftatom_create(dftatom_ctx** out, int device)
+{
+    if (!out) return DFTATOM_E_ARG;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        set_error("no CUDA device: dftatom_b200 has no CPU fallback");
+        return DFTATOM_E_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) { set_error("bad device index"); return DFTATOM_E_ARG; }
+    DFT_CHECK(cudaSetDevice(device));
+    dftatom_ctx* c = new dftatom_ctx;
+    c->device = device;
+    DFT_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    DFT_CHECK(cudaMallocHost((void**)&c->h_active, sizeof(int) * 256));
+    *out = c;
+    return 0;
+}
+
+void dftatom_destroy(dftatom_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto& kv : c->grids) kv.second.mem.release();
+    DevBuf* all[] = { &c->atoms, &c->astate, &c->orbs, &c->ss, &c->rho, &c->rhot, &c->vpot, &c->atab, &c->psi, &c->match_pt,
+                      &c->phi, &c->src, &c->zbc, &c->tab_of, &c->steps, &c->n_active };
+    for (DevBuf* b : all) b->release();
+    for (DevBuf& b : c->scratch) b.release();
+    if (c->h_active) cudaFreeHost(c->h_active);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int dftatom_set_option(dftatom_ctx* c, const char* key, double value)
+{
+    if (!c || !key) return DFTATOM_E_ARG;
+    const std::string k(key);
+    if (k == "max_vcycles") c->max_vcycles = std::max(1, (int)value);
+    else if (k == "vcycle_floor_stop") c->floor_stop = value != 0.;
+    else if (k == "r_segments") c->r_segments = (int)value;
+    else if (k == "profile") c->profile = value != 0.;
+    else { set_error("unknown option " + k); return DFTATOM_E_ARG; }
+    return 0;
+}
+
+int dftatom_aufbau(int Z, dftatom_level* out, int max_out) { return dft::aufbau(Z, out, max_out); }
+int dftatom_split_spin(int Z, dftatom_level* a, int* na, dftatom_level* b, int* nb, int* ea, int* eb)
+{
+    return dft::split_spin(Z, a, na, b, nb, ea, eb);
+}
+int dftatom_n_nodes(int levels) { return (1 << levels) + 1; }
+
+int dftatom_last_timing(dftatom_ctx* c, double* ms, long long* launches)
+{
+    if (!c) return DFTATOM_E_ARG;
+    if (ms) *ms = c->last_ms;
+    if (launches) *launches = c->last_launches;
+    return 0;
+}
+
+int dftatom_last_profile(dftatom_ctx* c, dftatom_kernel_profile* out)
+{
+    if (!c || !out) return DFTATOM_E_ARG;
+    for (int k = 0; k < DFTATOM_K_COUNT; ++k) out[k] = c->prof[k];
+    return 0;
+}
+
+int dftatom_measure_fp64_peak(dftatom_ctx* c, double* tflops)
+{
+    if (!c || !tflops) return DFTATOM_E_ARG;
+    DFT_CHECK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const int blocks = 148 * 8, threads = 256, iters = 1 << 15;
+    int rc = c->scratch[0].ensure(sizeof(double) * (size_t)blocks * threads);
+    if (rc) return rc;
+    cudaEvent_t a, b;
+    DFT_CHECK(cudaEventCreate(&a)); DFT_CHECK(cudaEventCreate(&b));
+    double best = 0.;
+    for (int rep = 0; rep < 6; ++rep) {
+        DFT_CHECK(cudaEventRecord(a, st));
+        launch_dfma_peak(c->scratch[0].as<double>(), blocks, threads, iters, st);
+        DFT_CHECK(cudaEventRecord(b, st));
+        DFT_CHECK(cudaEventSynchronize(b));
+        float ms = 0.f;
+        DFT_CHECK(cudaEventElapsedTime(&ms, a, b));
+        const double fl = 2. * 8. * (double)iters * blocks * threads;
+        if (rep >= 1) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    *tflops = best;
+    return 0;
+}
+
+int dftatom_solve_batch(dftatom_ctx* c, const dftatom_options* opts, int n_atoms, dftatom_result* out, dftatom_step* steps,
+                        int steps_stride)
+{
+    if (!c || !opts || !out || n_atoms <= 0) { set_error("bad argument"); return DFTATOM_E_ARG; }
+    DFT_CHECK(cudaSetDevice(c->device));
+    for (int a = 0; a < n_atoms; ++a) {
+        int rc = validate(opts[a]);
+        if (rc) return rc;
+        if (opts[a].levels != opts[0].levels || opts[a].delta != opts[0].delta || opts[a].max_r != opts[0].max_r) {
+            set_error("all atoms of one batch must share (levels, delta, max_r)");
+            return DFTATOM_E_MIXED_GRID;
+        }
+    }
+    GridDev* gp = nullptr;
+    int rc = get_grid(c, opts[0].levels, opts[0].delta, opts[0].max_r, &gp);
+    if (rc) return rc;
+    const GridDev g = *gp;
+    const int N = g.N;
+    const PoissonLevels lv = make_levels(g.L);
+    cudaStream_t st = c->stream;
+
+    // ---- host-side rules: levels per atom / spin ----
+    std::vector<AtomDev> atoms(n_atoms);
+    std::vector<AtomState> astate(n_atoms);
+    std::vector<OrbitalDev> orbs;
+    std::vector<int> tab_of(2 * (size_t)n_atoms, -1), zbc(n_atoms);
+    std::vector<std::vector<dftatom_level>> lev_a(n_atoms), lev_b(n_atoms);
+    int n_tabs = 0, max_steps = 0, zmax = 1;
+    for (int a = 0; a < n_atoms; ++a) {
+        AtomDev& at = atoms[a];
+        at.Z = opts[a].Z; at.method = opts[a].method; at.n_spin = opts[a].method ? 2 : 1;
+        at.n_steps_max = opts[a].method ? DFTATOM_MAX_STEPS_LSDA : DFTATOM_MAX_STEPS_LDA;
+        at.mixing = opts[a].mixing;
+        max_steps = std::max(max_steps, at.n_steps_max);
+        zmax = std::max(zmax, at.Z);
+        zbc[a] = at.Z;
+        dftatom_level la[DFTATOM_MAX_LEVELS], lb[DFTATOM_MAX_LEVELS];
+        int na = 0, nb = 0, ea = at.Z, eb = 0;
+        if (at.method) { rc = split_spin(at.Z, la, &na, lb, &nb, &ea, &eb); if (rc) return rc; }
+        else { na = aufbau(at.Z, la, DFTATOM_MAX_LEVELS); if (na < 0) return na; }
+        lev_a[a].assign(la, la + na); lev_b[a].assign(lb, lb + nb);
+        at.n_el[0] = ea; at.n_el[1] = eb;
+        for (int s = 0; s < at.n_spin; ++s) {
+            tab_of[2 * a + s] = n_tabs;
+            at.orb_begin[s] = (int)orbs.size();
+            const auto& L = s ? lev_b[a] : lev_a[a];
+            at.orb_count[s] = (int)L.size();
+            for (const auto& x : L) {
+                OrbitalDev o; o.atom = a; o.spin = s; o.n0 = x.n - 1; o.l = x.l; o.occ = x.occ; o.want = x.nodes; o.tab = n_tabs;
+                orbs.push_back(o);
+            }
+            ++n_tabs;
+        }
+        if (at.n_spin == 1) { at.orb_begin[1] = 0; at.orb_count[1] = 0; }
+        astate[a] = AtomState{ 0., 0, 0, 0, DFTATOM_MAX_STEPS };
+    }
+    const int n_orbs = (int)orbs.size();
+    const int stride = max_steps;
+
+    // ---- device buffers ----
+    if ((rc = upload(c, c->atoms, atoms))) return rc;
+    if ((rc = upload(c, c->astate, astate))) return rc;
+    if ((rc = upload(c, c->orbs, orbs))) return rc;
+    if ((rc = upload(c, c->tab_of, tab_of))) return rc;
+    if ((rc = upload(c, c->zbc, zbc))) return rc;
+    if ((rc = c->ss.ensure(sizeof(SearchState) * (size_t)n_orbs))) return rc;
+    if ((rc = c->rho.ensure(sizeof(double) * (size_t)n_tabs * N))) return rc;
+    if ((rc = c->rhot.ensure(sizeof(double) * (size_t)n_atoms * N))) return rc;
+    if ((rc = c->vpot.ensure(sizeof(double) * (size_t)n_tabs * N))) return rc;
+    if ((rc = c->atab.ensure(sizeof(double) * (size_t)n_tabs * N))) return rc;
+    if ((rc = c->psi.ensure(sizeof(double) * (size_t)n_orbs * N))) return rc;
+    if ((rc = c->match_pt.ensure(sizeof(int) * (size_t)n_orbs))) return rc;
+    if ((rc = c->phi.ensure(sizeof(double) * (size_t)n_atoms * lv.total))) return rc;
+    if ((rc = c->src.ensure(sizeof(double) * (size_t)n_atoms * lv.total))) return rc;
+    if ((rc = c->steps.ensure(sizeof(dftatom_step) * (size_t)n_atoms * stride))) return rc;
+    if ((rc = c->n_active.ensure(sizeof(int)))) return rc;
+    DFT_CHECK(cudaMemsetAsync(c->steps.p, 0, sizeof(dftatom_step) * (size_t)n_atoms * stride, st));
+    DFT_CHECK(cudaMemcpyAsync(c->n_active.p, &n_atoms, sizeof(int), cudaMemcpyHostToDevice, st));
+
+    ScfBuffers b{};
+    b.n_atoms = n_atoms; b.n_orbs = n_orbs; b.n_tabs = n_tabs; b.N = N;
+    b.atoms = c->atoms.as<AtomDev>(); b.astate = c->astate.as<AtomState>(); b.orbs = c->orbs.as<OrbitalDev>();
+    b.ss = c->ss.as<SearchState>(); b.rho = c->rho.as<double>(); b.rhot = c->rhot.as<double>(); b.vpot = c->vpot.as<double>();
+    b.atab = c->atab.as<double>(); b.psi = c->psi.as<double>(); b.match_pt = c->match_pt.as<int>();
+    b.phi = c->phi.as<double>(); b.src = c->src.as<double>(); b.Zbc = c->zbc.as<int>(); b.tab_of = c->tab_of.as<int>();
+    b.steps = c->steps.as<dftatom_step>(); b.steps_stride = stride; b.n_active = c->n_active.as<int>();
+
+    PoissonArgs pa{};
+    pa.n_dens = n_atoms; pa.rho = b.rhot; pa.Zbc = b.Zbc; pa.phi = b.phi; pa.src = b.src;
+    pa.skip = &b.astate[0].done; pa.skip_stride_bytes = (int)sizeof(AtomState);
+    pa.max_vcycles = c->max_vcycles; pa.floor_stop = c->floor_stop;
+
+    cudaEvent_t ev0, ev1;
+    DFT_CHECK(cudaEventCreate(&ev0));
+    DFT_CHECK(cudaEventCreate(&ev1));
+    std::vector<cudaEvent_t> step_ev(max_steps);
+    for (auto& e : step_ev) DFT_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    if (max_steps > 256) { set_error("internal: step cap"); return DFTATOM_E_ARG; }
+
+    long long launches = 0;
+    // optional per-class kernel timing: one event pair per launch group, resolved after the final sync
+    struct Span { int cls; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    const bool prof = c->profile != 0;
+    unsigned long long* d_work = nullptr;
+    if ((rc = c->scratch[7].ensure(sizeof(unsigned long long) * 8))) return rc;
+    d_work = c->scratch[7].as<unsigned long long>();
+    DFT_CHECK(cudaMemsetAsync(d_work, 0, sizeof(unsigned long long) * 8, st));
+    pa.work = d_work + DFTATOM_K_POISSON;
+    auto begin_span = [&](int cls) { if (prof) { Span s{ cls, nullptr, nullptr }; cudaEventCreate(&s.a); cudaEventCreate(&s.b); cudaEventRecord(s.a, st); spans.push_back(s); } };
+    auto end_span = [&]() { if (prof) cudaEventRecord(spans.back().b, st); };
+    DFT_CHECK(cudaEventRecord(ev0, st));
+    // initial guess -> U -> V   (DFTAtom.cpp:371-392)
+    launch_initial_density(g, b, st); ++launches;
+    launch_poisson_full(g, lv, pa, st); ++launches;
+    launch_potential_energy(g, lv, b, 1, st); ++launches;
+
+    const int rounds = search_rounds_needed(zmax);
+    int steps_enqueued = 0;
+    const int lag = 2;
+    for (int sp = 0; sp < max_steps; ++sp) {
+        begin_span(DFTATOM_K_SEARCH);
+        launch_search_init(g, b.atoms, b.astate, b.orbs, b.ss, n_orbs, st); ++launches;
+        for (int r = 0; r < rounds; ++r) { launch_search_round(g, b.atab, b.orbs, b.astate, b.ss, n_orbs, d_work + DFTATOM_K_SEARCH, st); ++launches; }
+        end_span();
+        begin_span(DFTATOM_K_MATCH);
+        launch_match(g, b.atab, b.orbs, b.astate, b.ss, b.psi, b.match_pt, n_orbs, st); ++launches;
+        end_span();
+        begin_span(DFTATOM_K_DENSITY);
+        launch_density_update(g, b, st); ++launches;
+        end_span();
+        begin_span(DFTATOM_K_POISSON);
+        launch_poisson_full(g, lv, pa, st); ++launches;
+        end_span();
+        begin_span(DFTATOM_K_POTENTIAL);
+        launch_potential_energy(g, lv, b, 0, st); ++launches;
+        end_span();
+        DFT_CHECK(cudaMemcpyAsync(&c->h_active[sp], b.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+        DFT_CHECK(cudaEventRecord(step_ev[sp], st));
+        ++steps_enqueued;
+        if (sp >= lag) {
+            // the host stays `lag` steps ahead of the device: it never idles the GPU, it only stops enqueueing
+            DFT_CHECK(cudaEventSynchronize(step_ev[sp - lag]));
+            if (c->h_active[sp - lag] == 0) break;
+        }
+    }
+    DFT_CHECK(cudaEventRecord(ev1, st));
+    DFT_CHECK(cudaStreamSynchronize(st));
+    DFT_CHECK(cudaGetLastError());
+    float ms = 0.f;
+    DFT_CHECK(cudaEventElapsedTime(&ms, ev0, ev1));
+    c->last_ms = ms; c->last_launches = launches;
+    {
+        unsigned long long hw[8] = {};
+        DFT_CHECK(cudaMemcpy(hw, d_work, sizeof(hw), cudaMemcpyDeviceToHost));
+        for (int k = 0; k < DFTATOM_K_COUNT; ++k) { c->prof[k].ms = 0.; c->prof[k].launches = 0; c->prof[k].work = (double)hw[k]; }
+        for (Span& s : spans) {
+            float t = 0.f;
+            cudaEventElapsedTime(&t, s.a, s.b);
+            c->prof[s.cls].ms += t;
+            c->prof[s.cls].launches += (s.cls == DFTATOM_K_SEARCH) ? rounds + 1 : 1;
+            cudaEventDestroy(s.a); cudaEventDestroy(s.b);
+        }
+    }
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    for (auto& e : step_ev) cudaEventDestroy(e);
+
+    // ---- results ----
+    std::vector<dftatom_step> hsteps((size_t)n_atoms * stride);
+    DFT_CHECK(cudaMemcpy(astate.data(), b.astate, sizeof(AtomState) * n_atoms, cudaMemcpyDeviceToHost));
+    DFT_CHECK(cudaMemcpy(hsteps.data(), b.steps, sizeof(dftatom_step) * hsteps.size(), cudaMemcpyDeviceToHost));
+    for (int a = 0; a < n_atoms; ++a) {
+        dftatom_result& R = out[a];
+        std::memset(&R, 0, sizeof(R));
+        R.status = astate[a].status;
+        R.n_steps = astate[a].n_steps;
+        R.n_spin = atoms[a].n_spin;
+        const dftatom_step& last = hsteps[(size_t)a * stride + std::max(0, R.n_steps - 1)];
+        for (int s = 0; s < R.n_spin; ++s) {
+            const auto& L = s ? lev_b[a] : lev_a[a];
+            R.n_levels[s] = (int)L.size();
+            for (size_t k = 0; k < L.size(); ++k) { R.levels[s][k] = L[k]; R.levels[s][k].E = last.E[s][k]; R.sorted[s][k] = R.levels[s][k]; }
+            // std::sort by E (DFTAtom.cpp:487 / :1012-1013)
+            std::sort(R.sorted[s], R.sorted[s] + L.size(), [](const dftatom_level& x, const dftatom_level& y) { return x.E < y.E; });
+        }
+        R.Etotal = last.Etotal; R.Ekin = last.Ekin; R.Ecoul = last.Ecoul; R.Eenuc = last.Eenuc; R.Exc = last.Exc;
+        if (steps) {
+            const int ncopy = std::min(steps_stride, stride);
+            std::memcpy(steps + (size_t)a * steps_stride, &hsteps[(size_t)a * stride], sizeof(dftatom_step) * ncopy);
+        }
+    }
+    (void)steps_enqueued;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// component entry points (host buffers)
+// ---------------------------------------------------------------------------------------------------------
+
+int dftatom_numerov_lanes(dftatom_ctx* c, const double* V, int levels, double delta, double max_r, int n_lanes, const int* l,
+                          const double* E, const int* nodes_limit, int* y0_sign, double* y0_log2, int* count)
+{
+    if (!c || !V || n_lanes <= 0) return DFTATOM_E_ARG;
+    DFT_CHECK(cudaSetDevice(c->device));
+    GridDev* gp; int rc = get_grid(c, levels, delta, max_r, &gp); if (rc) return rc;
+    const GridDev g = *gp; const int N = g.N; cudaStream_t st = c->stream;
+    DevBuf& dV = c->scratch[0]; DevBuf& dA = c->scratch[1]; DevBuf& di = c->scratch[2]; DevBuf& dd = c->scratch[3];
+    if ((rc = dV.ensure(sizeof(double) * N)) || (rc = dA.ensure(sizeof(double) * N))) return rc;
+    if ((rc = di.ensure(sizeof(int) * (size_t)n_lanes * 5)) || (rc = dd.ensure(sizeof(double) * (size_t)n_lanes * 2))) return rc;
+    DFT_CHECK(cudaMemcpyAsync(dV.p, V, sizeof(double) * N, cudaMemcpyHostToDevice, st));
+    launch_build_atab(g, dV.as<double>(), dA.as<double>(), 1, st);
+    int* d_tab = di.as<int>(); int* d_l = d_tab + n_lanes; int* d_lim = d_l + n_lanes; int* d_sign = d_lim + n_lanes; int* d_cnt = d_sign + n_lanes;
+    double* d_E = dd.as<double>(); double* d_log = d_E + n_lanes;
+    DFT_CHECK(cudaMemsetAsync(d_tab, 0, sizeof(int) * n_lanes, st));
+    DFT_CHECK(cudaMemcpyAsync(d_l, l, sizeof(int) * n_lanes, cudaMemcpyHostToDevice, st));
+    DFT_CHECK(cudaMemcpyAsync(d_lim, nodes_limit, sizeof(int) * n_lanes, cudaMemcpyHostToDevice, st));
+    DFT_CHECK(cudaMemcpyAsync(d_E, E, sizeof(double) * n_lanes, cudaMemcpyHostToDevice, st));
+    NumerovLaneArgs a{ dA.as<double>(), n_lanes, d_tab, d_l, d_E, d_lim, d_sign, d_log, d_cnt };
+    launch_numerov_lanes(g, a, st);
+    if (y0_sign) DFT_CHECK(cudaMemcpyAsync(y0_sign, d_sign, sizeof(int) * n_lanes, cudaMemcpyDeviceToHost, st));
+    if (y0_log2) DFT_CHECK(cudaMemcpyAsync(y0_log2, d_log, sizeof(double) * n_lanes, cudaMemcpyDeviceToHost, st));
+    if (count) DFT_CHECK(cudaMemcpyAsync(count, d_cnt, sizeof(int) * n_lanes, cudaMemcpyDeviceToHost, st));
+    DFT_CHECK(cudaStreamSynchronize(st));
+    DFT_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// shared by level_search / numerov_orbital: one pseudo-atom with the given potential
+static int setup_single(dftatom_ctx* c, const GridDev& g, const double* V, int Z, const std::vector<OrbitalDev>& orbs,
+                        AtomDev** d_atoms, AtomState** d_astate, OrbitalDev** d_orbs, SearchState** d_ss, double** d_atab)
+{
+    const int N = g.N; cudaStream_t st = c->stream;
+    int rc;
+    DevBuf& dV = c->scratch[0]; DevBuf& dA = c->scratch[1];
+    if ((rc = dV.ensure(sizeof(double) * N)) || (rc = dA.ensure(sizeof(double) * N))) return rc;
+    DFT_CHECK(cudaMemcpyAsync(dV.p, V, sizeof(double) * N, cudaMemcpyHostToDevice, st));
+    launch_build_atab(g, dV.as<double>(), dA.as<double>(), 1, st);
+    std::vector<AtomDev> atoms(1); atoms[0] = AtomDev{}; atoms[0].Z = Z; atoms[0].n_spin = 1;
+    std::vector<AtomState> as(1); as[0] = AtomState{ 0., 0, 0, 0, 0 };
+    if ((rc = upload(c, c->scratch[4], atoms)) || (rc = upload(c, c->scratch[5], as)) || (rc = upload(c, c->scratch[6], orbs))) return rc;
+    if ((rc = c->scratch[7].ensure(sizeof(SearchState) * orbs.size()))) return rc;
+    *d_atoms = c->scratch[4].as<AtomDev>(); *d_astate = c->scratch[5].as<AtomState>(); *d_orbs = c->scratch[6].as<OrbitalDev>();
+    *d_ss = c->scratch[7].as<SearchState>(); *d_atab = dA.as<double>();
+    return 0;
+}
+
+int dftatom_level_search(dftatom_ctx* c, const double* V, int levels, double delta, double max_r, int Z, int n_levels,
+                         const int* n, const int* l, double* E_out, int* converged_out)
+{
+    if (!c || !V || n_levels <= 0) return DFTATOM_E_ARG;
+    DFT_CHECK(cudaSetDevice(c->device));
+    GridDev* gp; int rc = get_grid(c, levels, delta, max_r, &gp); if (rc) return rc;
+    const GridDev g = *gp; cudaStream_t st = c->stream;
+    std::vector<OrbitalDev> orbs(n_levels);
+    for (int k = 0; k < n_levels; ++k) { orbs[k] = OrbitalDev{ 0, 0, n[k] - 1, l[k], 1, n[k] - 1 - l[k], 0 }; }
+    AtomDev* da; AtomState* ds; OrbitalDev* dorb; SearchState* dss; double* datab;
+    if ((rc = setup_single(c, g, V, Z, orbs, &da, &ds, &dorb, &dss, &datab))) return rc;
+    launch_search_init(g, da, ds, dorb, dss, n_levels, st);
+    const int rounds = search_rounds_needed(Z);
+    for (int r = 0; r < rounds; ++r) launch_search_round(g, datab, dorb, ds, dss, n_levels, nullptr, st);
+    std::vector<SearchState> h(n_levels);
+    DFT_CHECK(cudaMemcpyAsync(h.data(), dss, sizeof(SearchState) * n_levels, cudaMemcpyDeviceToHost, st));
+    DFT_CHECK(cudaStreamSynchronize(st));
+    DFT_CHECK(cudaGetLastError());
+    for (int k = 0; k < n_levels; ++k) {
+        const bool fin = h[k].stage == 3;
+        if (E_out) E_out[k] = fin ? h[k].E : (h[k].stage == 0 ? h[k].dn_hi : h[k].bot);
+        if (converged_out) converged_out[k] = fin ? h[k].converged : 0;
+    }
+    return 0;
+}
+
+int dftatom_numerov_orbital(dftatom_ctx* c, const double* V, int levels, double delta, double max_r, int l, double E,
+                            double* u_out, int* match_point)
+{
+    if (!c || !V || !u_out) return DFTATOM_E_ARG;
+    DFT_CHECK(cudaSetDevice(c->device));
+    GridDev* gp; int rc = get_grid(c, levels, delta, max_r, &gp); if (rc) return rc;
+    const GridDev g = *gp; const int N = g.N; cudaStream_t st = c->stream;
+    std::vector<OrbitalDev> orbs(1); orbs[0] = OrbitalDev{ 0, 0, l, l, 1, 0, 0 };
+    AtomDev* da; AtomState* ds; OrbitalDev* dorb; SearchState* dss; double* datab;
+    if ((rc = setup_single(c, g, V, 1, orbs, &da, &ds, &dorb, &dss, &datab))) return rc;
+    SearchState s{}; s.E = E; s.stage = 3; s.converged = 1;
+    DFT_CHECK(cudaMemcpyAsync(dss, &s, sizeof(s), cudaMemcpyHostToDevice, st));
+    // single-atom ScfBuffers so that density_update's normalisation path is the one exercised
+    if ((rc = c->psi.ensure(sizeof(double) * N)) || (rc = c->match_pt.ensure(sizeof(int)))) return rc;
+    launch_match(g, datab, dorb, ds, dss, c->psi.as<double>(), c->match_pt.as<int>(), 1, st);
+    std::vector<double> y(N), sq(N), wj(N);
+    int mp = 0;
+    DFT_CHECK(cudaMemcpyAsync(y.data(), c->psi.p, sizeof(double) * N, cudaMemcpyDeviceToHost, st));
+    DFT_CHECK(cudaMemcpyAsync(sq.data(), g.sqex, sizeof(double) * N, cudaMemcpyDeviceToHost, st));
+    DFT_CHECK(cudaMemcpyAsync(wj.data(), g.wjac, sizeof(double) * N, cudaMemcpyDeviceToHost, st));
+    DFT_CHECK(cudaMemcpyAsync(&mp, c->match_pt.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    DFT_CHECK(cudaStreamSynchronize(st));
+    DFT_CHECK(cudaGetLastError());
+    // normalisation on the host here only to return u(r) for inspection; the SCF path normalises on the device
+    double I = 0.;
+    for (int i = 0; i < N; ++i) { y[i] *= sq[i]; I += wj[i] * y[i] * y[i]; }
+    const double s_ = 1. / std::sqrt(I);
+    for (int i = 0; i < N; ++i) u_out[i] = y[i] * s_;
+    if (match_point) *match_point = mp;
+    return 0;
+}
+
+int dftatom_poisson_solve(dftatom_ctx* c, int levels, double delta, double max_r, int n_dens, const int* Z, const double* rho,
+                          double* U, int* vcycles_used)
+{
+    if (!c || !Z || !rho || !U || n_dens <= 0) return DFTATOM_E_ARG;
+    DFT_CHECK(cudaSetDevice(c->device));
+    GridDev* gp; int rc = get_grid(c, levels, delta, max_r, &gp); if (rc) return rc;
+    const GridDev g = *gp; const int N = g.N; cudaStream_t st = c->stream;
+    const PoissonLevels lv = make_levels(levels);
+    DevBuf& dr = c->scratch[0]; DevBuf& dz = c->scratch[2]; DevBuf& dv = c->scratch[3];
+    if ((rc = dr.ensure(sizeof(double) * (size_t)n_dens * N)) || (rc = dz.ensure(sizeof(int) * n_dens)) || (rc = dv.ensure(sizeof(int) * n_dens))) return rc;
+    if ((rc = c->phi.ensure(sizeof(double) * (size_t)n_dens * lv.total)) || (rc = c->src.ensure(sizeof(double) * (size_t)n_dens * lv.total))) return rc;
+    DFT_CHECK(cudaMemcpyAsync(dr.p, rho, sizeof(double) * (size_t)n_dens * N, cudaMemcpyHostToDevice, st));
+    DFT_CHECK(cudaMemcpyAsync(dz.p, Z, sizeof(int) * n_dens, cudaMemcpyHostToDevice, st));
+    PoissonArgs pa{};
+    pa.n_dens = n_dens; pa.rho = dr.as<double>(); pa.Zbc = dz.as<int>(); pa.phi = c->phi.as<double>(); pa.src = c->src.as<double>();
+    pa.max_vcycles = c->max_vcycles; pa.floor_stop = c->floor_stop; pa.vcycles_used = dv.as<int>();
+    launch_poisson_full(g, lv, pa, st);
+    DFT_CHECK(cudaMemcpy2DAsync(U, sizeof(double) * N, c->phi.p, sizeof(double) * lv.total, sizeof(double) * N, n_dens, cudaMemcpyDeviceToHost, st));
+    if (vcycles_used) DFT_CHECK(cudaMemcpyAsync(vcycles_used, dv.p, sizeof(int) * n_dens, cudaMemcpyDeviceToHost, st));
+    DFT_CHECK(cudaStreamSynchronize(st));
+    DFT_CHECK(cudaGetLastError());
+    return 0;
+}
+
+long long dftatom_poisson_scratch_bytes(int levels, int n_dens)
+{
+    const PoissonLevels lv = make_levels(levels);
+    return (long long)sizeof(double) * 2 * (long long)lv.total * n_dens;
+}
+
+int dftatom_poisson_vcycles(dftatom_ctx* c, int levels, double delta, int n_dens, double* phi, const double* src, int n_cycles,
+                            double* last_err)
+{
+    if (!c || !phi || !src || n_dens <= 0) return DFTATOM_E_ARG;
+    DFT_CHECK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const PoissonLevels lv = make_levels(levels);
+    const int N = (1 << levels) + 1;
+    int rc;
+    if ((rc = c->phi.ensure(sizeof(double) * (size_t)n_dens * lv.total)) || (rc = c->src.ensure(sizeof(double) * (size_t)n_dens * lv.total))) return rc;
+    DevBuf& de = c->scratch[3];
+    if ((rc = de.ensure(sizeof(double) * n_dens))) return rc;
+    DFT_CHECK(cudaMemsetAsync(c->phi.p, 0, sizeof(double) * (size_t)n_dens * lv.total, st));
+    DFT_CHECK(cudaMemsetAsync(c->src.p, 0, sizeof(double) * (size_t)n_dens * lv.total, st));
+    DFT_CHECK(cudaMemcpy2DAsync(c->phi.p, sizeof(double) * lv.total, phi, sizeof(double) * N, sizeof(double) * N, n_dens, cudaMemcpyHostToDevice, st));
+    DFT_CHECK(cudaMemcpy2DAsync(c->src.p, sizeof(double) * lv.total, src, sizeof(double) * N, sizeof(double) * N, n_dens, cudaMemcpyHostToDevice, st));
+    launch_poisson_vcycles(levels, delta, lv, n_dens, c->phi.as<double>(), c->src.as<double>(), n_cycles, de.as<double>(), st);
+    DFT_CHECK(cudaMemcpy2DAsync(phi, sizeof(double) * N, c->phi.p, sizeof(double) * lv.total, sizeof(double) * N, n_dens, cudaMemcpyDeviceToHost, st));
+    if (last_err) DFT_CHECK(cudaMemcpyAsync(last_err, de.p, sizeof(double) * n_dens, cudaMemcpyDeviceToHost, st));
+    DFT_CHECK(cudaStreamSynchronize(st));
+    DFT_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int dftatom_poisson_vcycles_dev(dftatom_ctx* c, int levels, double delta, int n_dens, void* d_phi, const void* d_src, void* d_scratch,
+                                long long scratch_bytes, int n_cycles, float* device_ms)
+{
+    (void)c; (void)levels; (void)delta; (void)n_dens; (void)d_phi; (void)d_src; (void)d_scratch; (void)scratch_bytes; (void)n_cycles; (void)device_ms;
+    set_error("dftatom_poisson_vcycles_dev: not implemented yet");
+    return DFTATOM_E_ARG;
+}
+
+int dftatom_vwn(dftatom_ctx* c, int n, const double* rho_a, const double* rho_b, double* va, double* vb, double* vexc, double* eexcdif)
+{
+    if (!c || !rho_a || !vexc || !eexcdif || n <= 0) return DFTATOM_E_ARG;
+    if (rho_b && (!va || !vb)) return DFTATOM_E_ARG;
+    DFT_CHECK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    int rc;
+    DevBuf& d = c->scratch[0];
+    if ((rc = d.ensure(sizeof(double) * (size_t)n * 6))) return rc;
+    double* p = d.as<double>();
+    double* ra = p; double* rb = p + n; double* dva = p + 2 * (size_t)n; double* dvb = p + 3 * (size_t)n; double* dvx = p + 4 * (size_t)n; double* ded = p + 5 * (size_t)n;
+    DFT_CHECK(cudaMemcpyAsync(ra, rho_a, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    if (rho_b) DFT_CHECK(cudaMemcpyAsync(rb, rho_b, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    launch_vwn(n, ra, rho_b ? rb : nullptr, dva, dvb, dvx, ded, st);
+    if (rho_b) {
+        DFT_CHECK(cudaMemcpyAsync(va, dva, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+        DFT_CHECK(cudaMemcpyAsync(vb, dvb, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    }
+    DFT_CHECK(cudaMemcpyAsync(vexc, dvx, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    DFT_CHECK(cudaMemcpyAsync(eexcdif, ded, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    DFT_CHECK(cudaStreamSynchronize(st));
+    DFT_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int dftatom_simpson38(dftatom_ctx* c, double step, const double* v, int n, int n_rows, double* out)
+{
+    if (!c || !v || !out || n < 5 || n_rows <= 0) return DFTATOM_E_ARG;
+    DFT_CHECK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    int rc;
+    DevBuf& d = c->scratch[0]; DevBuf& o = c->scratch[1];
+    if ((rc = d.ensure(sizeof(double) * (size_t)n * n_rows)) || (rc = o.ensure(sizeof(double) * n_rows))) return rc;
+    DFT_CHECK(cudaMemcpyAsync(d.p, v, sizeof(double) * (size_t)n * n_rows, cudaMemcpyHostToDevice, st));
+    launch_simpson38(step, d.as<double>(), n, n_rows, o.as<double>(), st);
+    DFT_CHECK(cudaMemcpyAsync(out, o.p, sizeof(double) * n_rows, cudaMemcpyDeviceToHost, st));
+    DFT_CHECK(cudaStreamSynchronize(st));
+    DFT_CHECK(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,153 @@
+// Internal declarations shared by the CUDA translation units of libdftatom_b200.so.
+// Data layout in HBM (all FP64, contiguous, index = radial node i, N = 2^L + 1):
+//   grid tables  (one set per batch, shared by all atoms):  r, ex=e^{δi}, sqex=e^{δi/2}, b12, c6, k2, simpson-weighted jacobians
+//   per (atom,spin): rho[N], atab[N] (Numerov table a_i built from the potential), vpot[N]
+//   per atom:        rhot[N] (total density; aliases rho of spin 0 for LDA), Poisson hierarchy phi/src (2N-ish each)
+//   per orbital:     psi[N], search state
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <string>
+#include <vector>
+#include "../../include/dftatom_b200.h"
+
+#define DFT_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { dft::set_error(std::string(#x) + ": " + cudaGetErrorString(e_)); return DFTATOM_E_CUDA; } } while (0)
+
+namespace dft {
+
+void set_error(const std::string& s);
+
+constexpr double kEnergyTol = 1e-12;        // energyErr, DFTAtom.cpp:348
+constexpr double kTotalEnergyTol = 1e-11;   // totalEnergyErr, DFTAtom.cpp:349
+constexpr double kTopEnergy = 50.0;         // DFTAtom.cpp:499
+constexpr double kFarLog = -460.51701859880916;   // ln(1e-200): Numerov.h:195 cut-off
+constexpr double kFourPi = 12.566370614359172;
+
+// Grid-only tables (device pointers).  K_i = Rp^2 δ^2 e^{2δ i}  (Numerov.h:85,100; PoissonSolver.h:66-74)
+struct GridDev {
+    int N, L;
+    double delta, rp, max_r;
+    double* r;       // r_i = Rp (e^{δ i} - 1)                      (Numerov.h:181-184)
+    double* ex;      // e^{δ i}
+    double* sqex;    // e^{δ i / 2}                                  (DFTAtom.cpp:42)
+    double* b12;     // K_i / (12 r_i^2)   (b12[0] = 0)              centrifugal part of 1 - f/12
+    double* c6;      // K_i / 6                                      energy part of 1 - f/12
+    double* k2;      // 2 K_i                                        potential part of f
+    double* wjac;    // simpson38 weight_i * Rp δ e^{δ i}            (Integral.h:50-73 × jacobian DFTAtom.cpp:47,442)
+    double* psrc;    // r_i * 4π K_i  (0 at i=0 and i=N-1)           (PoissonSolver.h:55-74)
+    double* inv4pr2; // 1 / (4π r_i^2) (0 at i=0)                    (DFTAtom.cpp:340)
+};
+
+// One orbital = one (atom, spin, n, l) level; also the unit of the batched energy search.
+struct OrbitalDev {
+    int atom, spin, n0, l, occ;
+    int want;            // n0 - l = number of nodes (DFTAtom.cpp:497)
+    int tab;             // index of the (atom,spin) table row
+};
+
+// Search state, one per orbital (device).  Stage A finds both edges of the node-count window
+// (LocateInterval, DFTAtom.cpp:566-604), stage B the sign change of y(0) inside it (:513-534).
+struct SearchState {
+    double up_lo, up_hi;     // bracket of the upper edge (count > want above it)
+    double dn_lo, dn_hi;     // bracket of the lower edge (count < want below it)
+    double bot, top;         // stage B bracket
+    double y0_log2;          // log2|y0| of the last stage-B midpoint (1e15 guard)
+    double E;                // result (= bot)
+    int stage;               // 0 = A, 1 = B first round (needs sign at bot), 2 = B, 3 = done
+    int sgn_bottom;
+    int converged;
+    int pad;
+};
+
+struct AtomDev {
+    int Z, method, n_spin, n_steps_max;
+    double mixing;
+    int orb_begin[2], orb_count[2];
+    int n_el[2];
+};
+
+struct AtomState {
+    double e_old;
+    int prev_ok;
+    int done;            // 1 once the stop criterion fired or the cap was reached
+    int n_steps;
+    int status;
+};
+
+struct PoissonLevels {       // offsets of each level inside one density's phi/src block
+    int L;
+    int off[24];
+    int size[24];
+    int total;
+};
+PoissonLevels make_levels(int L);
+
+// ---- launchers (all asynchronous on `st`) ----
+struct NumerovLaneArgs {
+    const double* atab;   // [n_tabs][N]
+    int n_lanes;
+    const int* tab; const int* l; const double* E; const int* limit;   // device arrays
+    int* y0_sign; double* y0_log2; int* count;
+};
+void launch_numerov_lanes(const GridDev& g, const NumerovLaneArgs& a, cudaStream_t st);
+
+void launch_search_init(const GridDev& g, const AtomDev* atoms, const AtomState* astate, const OrbitalDev* orbs, SearchState* ss,
+                        int n_orbs, cudaStream_t st);
+void launch_search_round(const GridDev& g, const double* atab, const OrbitalDev* orbs, const AtomState* astate, SearchState* ss,
+                         int n_orbs, unsigned long long* work, cudaStream_t st);
+void launch_dfma_peak(double* out, int blocks, int threads, int iters, cudaStream_t st);
+int search_rounds_needed(int Zmax);
+
+void launch_match(const GridDev& g, const double* atab, const OrbitalDev* orbs, const AtomState* astate, const SearchState* ss,
+                  double* psi, int* match_pt, int n_orbs, cudaStream_t st);
+
+// potential -> a-table (a_i = 1 - (2K_i V_i + δ²/4)/12), n_tabs rows
+void launch_build_atab(const GridDev& g, const double* vpot, double* atab, int n_tabs, cudaStream_t st);
+
+// Poisson
+struct PoissonArgs {
+    int n_dens;
+    const double* rho;      // [n_dens][N] total density (may be NULL when src is pre-filled)
+    const int* Zbc;         // [n_dens] boundary value at Rmax (may be NULL: use hi_bc)
+    double* phi; double* src;   // [n_dens][levels.total]
+    const int* skip;        // optional per-density skip flag (AtomState.done), stride given
+    int skip_stride_bytes;
+    int max_vcycles; int floor_stop;
+    unsigned long long* work;   // optional: += Gauss-Seidel node-updates performed
+    int* vcycles_used;      // optional [n_dens]
+    double* last_err;       // optional [n_dens]
+};
+void launch_poisson_full(const GridDev& g, const PoissonLevels& lv, const PoissonArgs& a, cudaStream_t st);
+void launch_poisson_vcycles(int L, double delta, const PoissonLevels& lv, int n_dens, double* phi, double* src, int n_cycles,
+                            double* last_err, cudaStream_t st);
+
+// XC
+void launch_vwn(int n, const double* ra, const double* rb, double* va, double* vb, double* vexc, double* edif, cudaStream_t st);
+void launch_simpson38(double step, const double* v, int n, int n_rows, double* out, cudaStream_t st);
+
+// SCF pieces (scf.cu)
+struct ScfBuffers {
+    int n_atoms, n_orbs, n_tabs, N;
+    AtomDev* atoms; AtomState* astate; OrbitalDev* orbs; SearchState* ss;
+    double* rho;      // [n_tabs][N] per-spin densities
+    double* rhot;     // [n_atoms][N] total density
+    double* vpot;     // [n_tabs][N]
+    double* atab;     // [n_tabs][N]
+    double* psi;      // [n_orbs][N]
+    int* match_pt;    // [n_orbs]
+    double* phi; double* src;   // Poisson hierarchy [n_atoms][levels.total]
+    int* Zbc;         // [n_atoms]
+    int* tab_of;      // [n_atoms][2] table row of (atom, spin) or -1
+    dftatom_step* steps;  // [n_atoms][steps_stride]
+    int steps_stride;
+    int* n_active;    // device counter of atoms not done
+};
+void launch_initial_density(const GridDev& g, const ScfBuffers& b, cudaStream_t st);
+void launch_density_update(const GridDev& g, const ScfBuffers& b, cudaStream_t st);
+void launch_potential_energy(const GridDev& g, const PoissonLevels& lv, const ScfBuffers& b, int first, cudaStream_t st);
+
+// host rules (aufbau.cpp)
+int aufbau(int Z, dftatom_level* out, int max_out);
+int split_spin(int Z, dftatom_level* a, int* na, dftatom_level* b, int* nb, int* ea, int* eb);
+
+}  // namespace dft

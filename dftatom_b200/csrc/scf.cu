@@ -1,0 +1,338 @@
+// SCF state kernels: initial guess, orbital normalisation + density accumulation + mixing, VWN exchange-
+// correlation + potential + the five energy integrals + the convergence test.  Everything stays on the device;
+// the host only enqueues (engine.cpp).
+//
+// Replaces (reference DFTAtom/): DFTAtom.cpp:36-56 NormalizeNonUniform, :328-343 CalculateNonUniformDensity
+// (mixing), :371-392 initial guess, :413-481 (LDA) and :937-1006 (LSDA) potential/energies/stop test,
+// VWNExcCor.h:73-128 (LDA), :134-312 (LSDA), ExcCorBase.h:14-26, Integral.h:50-73 Simpson38.
+#include "internal.h"
+#include <cmath>
+
+namespace dft {
+
+// ---------------------------------------------------------------------------------------------------------
+// VWN (Vosko-Wilk-Nusair) parametrisation, constants VWNExcCor.h:24-41
+// ---------------------------------------------------------------------------------------------------------
+struct VwnSet { double A, y0, b, c; };
+__device__ __constant__ VwnSet kVwnP = { 0.0310907, -0.10498, 3.72744, 12.93532 };
+__device__ __constant__ VwnSet kVwnF = { 0.01554535, -0.325, 7.06042, 18.0578 };
+__device__ __constant__ VwnSet kVwnA = { -0.016886863940389628 /* -1/(6 pi^2) */, -0.0047584, 1.13107, 13.0045 };
+
+struct VwnVal { double eps, deps; };
+
+// eps: VWN eq. B.5 (VWNExcCor.h:43-50); deps: eq. B.6 (:52-55); y = sqrt(rs)
+__device__ __forceinline__ VwnVal vwn_eval(double y, const VwnSet p)
+{
+    const double Y = y * (y + p.b) + p.c;
+    const double Y0 = p.y0 * p.y0 + p.b * p.y0 + p.c;
+    const double dy = y - p.y0;
+    const double Q = sqrt(4. * p.c - p.b * p.b);
+    const double at = atan(Q / (2. * y + p.b));
+    VwnVal v;
+    v.eps = p.A * (log(y * y / Y) + 2. * p.b / Q * at - p.b * p.y0 / Y0 * (log(dy * dy / Y) + 2. * (p.b + 2. * p.y0) / Q * at));
+    v.deps = p.A * (p.c * dy - p.b * p.y0 * y) / (dy * Y);
+    return v;
+}
+
+#define DFT_X1 0.6108870577108572        /* (3/(2 pi))^(2/3), VWNExcCor.h:75 */
+#define DFT_CBRT2 1.2599210498948732
+#define DFT_THREE_OVER_4PI 0.23873241463784300
+
+struct XcLda { double vexc, edif; };
+__device__ __forceinline__ XcLda xc_lda(double rho)
+{   // VWNExcCor.h:73-128
+    XcLda o; o.vexc = 0.; o.edif = 0.;
+    if (rho < 1e-18) return o;
+    const double third = 1. / 3.;
+    const double rs = pow(3. / (kFourPi * rho), third);
+    const VwnVal p = vwn_eval(sqrt(rs), kVwnP);
+    o.vexc = -DFT_X1 / rs + p.eps - third * p.deps;
+    o.edif = 0.25 * DFT_X1 / rs + third * p.deps;
+    return o;
+}
+
+struct XcLsda { double va, vb, vexc, edif; };
+__device__ __forceinline__ XcLsda xc_lsda(double roa, double rob)
+{   // VWNExcCor.h:134-312, ExcCorBase.h:14-26
+    XcLsda o; o.va = o.vb = o.vexc = o.edif = 0.;
+    const double n = roa + rob;
+    if (n < 1e-18) return o;
+    const double third = 1. / 3.;
+    const double rs = pow(3. / (kFourPi * n), third);
+    const double rsa = pow(3. / (kFourPi * roa), third);
+    const double rsb = pow(3. / (kFourPi * rob), third);
+    const double exp_ = -DFT_X1 / rs;
+    const double exdif = DFT_CBRT2 * exp_ - exp_;
+    const double zeta = (roa - rob) / n;
+    const double z3 = zeta * zeta * zeta, z4 = z3 * zeta;
+    const double fdd = 4. / (9. * (DFT_CBRT2 - 1.));
+    const double fv = (pow(1. + zeta, 4. * third) + pow(1. - zeta, 4. * third) - 2.) / (2. * (DFT_CBRT2 - 1.));
+    const double dfv = 2. / (3. * (DFT_CBRT2 - 1.)) * (pow(1. + zeta, third) - pow(1. - zeta, third));
+    const double y = sqrt(rs);
+    const VwnVal P = vwn_eval(y, kVwnP), F = vwn_eval(y, kVwnF), A = vwn_eval(y, kVwnA);
+    const double dfp = F.eps - P.eps;
+    const double beta = fdd * dfp / A.eps - 1.;
+    const double opbz4 = 1. + beta * z4;
+    const double interp = fv / fdd * opbz4;
+    const double betad = fdd / A.eps * (F.deps - P.deps - A.deps * dfp / A.eps);
+    const double interpd = fv / fdd * z4 * betad;
+    const double deriv = third * (P.deps + A.deps * interp + A.eps * interpd);
+    const double dterm = A.eps / fdd * (4. * beta * z3 * fv + opbz4 * dfv);
+    const double core = P.eps + A.eps * interp - deriv;
+    o.va = -DFT_X1 * DFT_CBRT2 / rsa + core + (1. - zeta) * dterm;
+    o.vb = -DFT_X1 * DFT_CBRT2 / rsb + core - (1. + zeta) * dterm;
+    o.vexc = core + (exp_ + exdif * fv);
+    const double expd = 0.25 * DFT_X1 / rs;
+    o.edif = expd + (DFT_CBRT2 * expd - expd) * fv + deriv;
+    return o;
+}
+
+__global__ void vwn_kernel(int n, const double* ra, const double* rb, double* va, double* vb, double* vexc, double* edif)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (rb) {
+            const XcLsda x = xc_lsda(ra[i], rb[i]);
+            va[i] = x.va; vb[i] = x.vb; vexc[i] = x.vexc; edif[i] = x.edif;
+        } else {
+            const XcLda x = xc_lda(ra[i]);
+            vexc[i] = x.vexc; edif[i] = x.edif;
+        }
+    }
+}
+
+void launch_vwn(int n, const double* ra, const double* rb, double* va, double* vb, double* vexc, double* edif, cudaStream_t st)
+{
+    vwn_kernel<<<std::min((n + 255) / 256, 148 * 8), 256, 0, st>>>(n, ra, rb, va, vb, vexc, edif);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// block reductions
+// ---------------------------------------------------------------------------------------------------------
+template <int NV>
+__device__ __forceinline__ void block_sum_n(double (&v)[NV], double* smem /* NV*32 doubles */)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+    }
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < NV; ++q) smem[q * 32 + w] = v[q];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        double t = lane < nw ? smem[q * 32 + lane] : 0.;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        v[q] = t;
+    }
+}
+
+// Simpson38 weights of Integral.h:50-73 (times 3/8): ends 1, i%3==0 -> 2, else 3
+__device__ __forceinline__ double simpson_w(int i, int n)
+{
+    const double w = (i == 0 || i == n - 1) ? 1. : ((i % 3 == 0) ? 2. : 3.);
+    return w * 0.375;
+}
+
+__global__ void simpson38_kernel(double step, const double* v, int n, double* out)
+{
+    __shared__ double sm[32];
+    const double* row = v + (size_t)blockIdx.x * n;
+    double acc[1] = { 0. };
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc[0] = fma(simpson_w(i, n), row[i], acc[0]);
+    block_sum_n<1>(acc, sm);
+    if (threadIdx.x == 0) out[blockIdx.x] = acc[0] * step;
+}
+
+void launch_simpson38(double step, const double* v, int n, int n_rows, double* out, cudaStream_t st)
+{
+    simpson38_kernel<<<n_rows, 512, 0, st>>>(step, v, n, out);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// SCF kernels, one CTA per atom
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kAT = 512;
+
+__global__ void __launch_bounds__(kAT) initial_density_kernel(GridDev g, ScfBuffers b)
+{   // DFTAtom.cpp:371-376 / :876-884: uniform charge inside the sphere of radius MaxR
+    const int a = blockIdx.x;
+    const AtomDev at = b.atoms[a];
+    const double volume = kFourPi / 3. * g.max_r * g.max_r * g.max_r;
+    const int N = g.N;
+    double* rt = b.rhot + (size_t)a * N;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        double tot = 0.;
+        for (int s = 0; s < at.n_spin; ++s) {
+            const double c = (i == 0) ? 0. : (double)at.n_el[s] / volume;
+            b.rho[(size_t)b.tab_of[2 * a + s] * N + i] = c;
+            tot += c;
+        }
+        rt[i] = tot;
+    }
+}
+
+void launch_initial_density(const GridDev& g, const ScfBuffers& b, cudaStream_t st)
+{
+    initial_density_kernel<<<b.n_atoms, kAT, 0, st>>>(g, b);
+}
+
+// LoopOverLevels' tail (normalise, accumulate occ u^2, Eel) + CalculateNonUniformDensity's mixing.
+// psi holds the matched y_i of every orbital (inner part final, outer part already scaled).
+__global__ void __launch_bounds__(kAT) density_update_kernel(GridDev g, ScfBuffers b)
+{
+    __shared__ double sm[32];
+    __shared__ double inv_norm[2 * DFTATOM_MAX_LEVELS];
+    const int a = blockIdx.x;
+    AtomState& as = b.astate[a];
+    if (as.done) return;
+    const AtomDev at = b.atoms[a];
+    const int N = g.N;
+    dftatom_step* rec = b.steps + (size_t)a * b.steps_stride + as.n_steps;
+
+    // 1. norms: integral of u^2 dr, u_i = y_i e^{i δ/2}, dr = Rp δ e^{δ i} di  (DFTAtom.cpp:36-56)
+    for (int s = 0; s < at.n_spin; ++s) {
+        for (int k = 0; k < at.orb_count[s]; ++k) {
+            const int o = at.orb_begin[s] + k;
+            const double* psi = b.psi + (size_t)o * N;
+            double acc[1] = { 0. };
+            for (int i = threadIdx.x; i < N; i += blockDim.x) {
+                const double u = psi[i] * g.sqex[i];
+                acc[0] = fma(g.wjac[i], u * u, acc[0]);
+            }
+            block_sum_n<1>(acc, sm);
+            if (threadIdx.x == 0) inv_norm[s * DFTATOM_MAX_LEVELS + k] = 1. / acc[0];
+            __syncthreads();
+        }
+    }
+    // 2. new density and mixing (DFTAtom.cpp:558-559, :332-342)
+    const double keep = at.mixing, take = 1. - at.mixing;
+    double* rt = b.rhot + (size_t)a * N;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        double tot = 0.;
+        const double sq = g.sqex[i];
+        for (int s = 0; s < at.n_spin; ++s) {
+            double acc = 0.;
+            if (i < N - 1) {
+                for (int k = 0; k < at.orb_count[s]; ++k) {
+                    const int o = at.orb_begin[s] + k;
+                    const double u = b.psi[(size_t)o * N + i] * sq;
+                    acc = fma((double)b.orbs[o].occ * inv_norm[s * DFTATOM_MAX_LEVELS + k], u * u, acc);
+                }
+            }
+            double* rho = b.rho + (size_t)b.tab_of[2 * a + s] * N;
+            double r = rho[i];
+            if (i >= 1) { r = keep * r + take * (acc * g.inv4pr2[i]); rho[i] = r; }
+            tot += r;
+        }
+        if (at.n_spin == 2 && i >= 1) rt[i] = tot;     // DFTAtom.cpp:933-934 (LDA: rhot aliases rho)
+        else if (at.n_spin == 1) rt[i] = tot;
+    }
+    // 3. eigenvalues of this step into the record; electronic energy; reallyConverged
+    if (threadIdx.x == 0) {
+        double eel = 0.;
+        int ok = 1;
+        for (int s = 0; s < at.n_spin; ++s)
+            for (int k = 0; k < at.orb_count[s]; ++k) {
+                const int o = at.orb_begin[s] + k;
+                const SearchState& st = b.ss[o];
+                rec->E[s][k] = st.E;
+                eel += (double)b.orbs[o].occ * st.E;       // DFTAtom.cpp:561
+                if (!st.converged) ok = 0;
+            }
+        rec->levels_converged = ok;
+        rec->Ekin = eel;                                     // parked here until potential_energy_kernel
+    }
+}
+
+void launch_density_update(const GridDev& g, const ScfBuffers& b, cudaStream_t st)
+{
+    density_update_kernel<<<b.n_atoms, kAT, 0, st>>>(g, b);
+}
+
+// Potential from (U, rho), the five integrals, energies, stop test.  first != 0: only the initial potential.
+__global__ void __launch_bounds__(kAT) potential_energy_kernel(GridDev g, PoissonLevels lv, ScfBuffers b, int first)
+{
+    __shared__ double sm[5 * 32];
+    const int a = blockIdx.x;
+    AtomState& as = b.astate[a];
+    if (as.done) return;
+    const AtomDev at = b.atoms[a];
+    const int N = g.N;
+    const double Z = (double)at.Z;
+    const double* U = b.phi + (size_t)a * lv.total;       // level 0 of the Poisson hierarchy = U(r) = r V_H
+    const double* rt = b.rhot + (size_t)a * N;
+    const int ta = b.tab_of[2 * a], tb = b.tab_of[2 * a + 1];
+    const double q = g.delta * g.delta * 0.25;
+
+    double e[5] = { 0., 0., 0., 0., 0. };   // nuclear, exccor, eexcDeriv, hartree, potentiale
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        double Va = 0., Vb = 0.;
+        if (i >= 1) {
+            const double r = g.r[i];
+            const double uc = (-Z + U[i]) / r;
+            const double rho = rt[i];
+            const double wj = g.wjac[i];                  // simpson weight x jacobian
+            const double rd = r * rho * wj;
+            const double r2d = r * rd;
+            double vexc, edif, pot;
+            if (at.n_spin == 2) {                          // DFTAtom.cpp:956-983
+                const double ra = b.rho[(size_t)ta * N + i], rb = b.rho[(size_t)tb * N + i];
+                const XcLsda x = xc_lsda(ra, rb);
+                Va = uc + x.va; Vb = uc + x.vb;
+                vexc = x.vexc; edif = x.edif;
+                pot = r * r * wj * (ra * Va + rb * Vb);
+            } else {                                       // DFTAtom.cpp:437-457
+                const XcLda x = xc_lda(rho);
+                Va = uc + x.vexc;
+                vexc = x.vexc; edif = x.edif;
+                pot = r2d * Va;
+            }
+            e[0] += Z * rd;
+            e[1] = fma(r2d, vexc, e[1]);
+            e[2] = fma(r2d, edif, e[2]);
+            e[3] = fma(rd, U[i], e[3]);
+            e[4] += pot;
+        }
+        b.vpot[(size_t)ta * N + i] = Va;
+        b.atab[(size_t)ta * N + i] = 1. - (g.k2[i] * Va + q) * (1. / 12.);
+        if (at.n_spin == 2) {
+            b.vpot[(size_t)tb * N + i] = Vb;
+            b.atab[(size_t)tb * N + i] = 1. - (g.k2[i] * Vb + q) * (1. / 12.);
+        }
+    }
+    if (first) return;
+    block_sum_n<5>(e, sm);
+    if (threadIdx.x == 0) {
+        dftatom_step* rec = b.steps + (size_t)a * b.steps_stride + as.n_steps;
+        const double eel = rec->Ekin;                      // parked by density_update_kernel
+        const double e_nuc = -kFourPi * e[0];              // DFTAtom.cpp:459-470
+        const double e_dif = kFourPi * e[2];
+        const double e_xc = kFourPi * e[1] + e_dif;
+        const double e_har = -0.5 * kFourPi * e[3];
+        const double e_pot = kFourPi * e[4];
+        const double etot = eel + e_har + e_dif;
+        rec->Etotal = etot; rec->Ekin = eel - e_pot; rec->Ecoul = -e_har; rec->Eenuc = e_nuc; rec->Exc = e_xc;
+        const int ok = rec->levels_converged;
+        int done = 0, status = DFTATOM_MAX_STEPS;
+        if (fabs((as.e_old - etot) / etot) < kTotalEnergyTol && ok && as.prev_ok) { done = 1; status = DFTATOM_CONVERGED; }   // :474
+        as.e_old = etot;
+        as.prev_ok = ok;
+        as.n_steps += 1;
+        if (!done && as.n_steps >= at.n_steps_max) { done = 1; status = DFTATOM_MAX_STEPS; }
+        if (!done && !(fabs(etot) <= 1.7e308)) { done = 1; status = DFTATOM_NUMERIC_FAILURE; }
+        if (done) { as.done = 1; as.status = status; atomicAdd(b.n_active, -1); }
+    }
+}
+
+void launch_potential_energy(const GridDev& g, const PoissonLevels& lv, const ScfBuffers& b, int first, cudaStream_t st)
+{
+    potential_energy_kernel<<<b.n_atoms, kAT, 0, st>>>(g, lv, b, first);
+}
+
+}  // namespace dft

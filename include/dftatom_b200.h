@@ -1,0 +1,155 @@
+/*
+ * dftatom_b200 — C ABI of the B200-native radial Kohn-Sham SCF engine.
+ *
+ * Drop-in boundary for the computation behind aromanro/DFTAtom's
+ *     static void DFT::DFTAtom::CalculateNonUniformLDA (int Z, int MultigridLevels, double alpha, double MaxR, double deltaGrid)
+ *     static void DFT::DFTAtom::CalculateNonUniformLSDA(int Z, int MultigridLevels, double alpha, double MaxR, double deltaGrid)
+ * (reference DFTAtom/DFTAtom.h:14,17; only call site DFTAtomFrame.cpp:190-195).  The reference has no
+ * FFI / plugin interface: that static-function pair, selected by Options::method (Options.h:54), and the
+ * text it prints on std::cout ARE the interface, so the entry points below carry the same arguments
+ * (as `dftatom_options`, mirroring Options.h:48-54) and return the same numbers the text holds
+ * (per-step eigenvalues + node counts + Etotal/Ekin/Ecoul/Eenuc/Exc, final configuration).
+ *
+ * Plain C: pointers and sizes only, no C++/torch types.  All floating point is IEEE FP64.
+ * Every function returns 0 on success or a negative DFTATOM_E_* code; dftatom_last_error() gives text.
+ * There is NO CPU fallback: without a CUDA device dftatom_create fails with DFTATOM_E_NO_DEVICE.
+ */
+#ifndef DFTATOM_B200_H
+#define DFTATOM_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFTATOM_MAX_LEVELS 24          /* per spin channel; Z <= 118 needs 19 */
+#define DFTATOM_MAX_STEPS_LDA 100      /* DFTAtom.cpp:396 */
+#define DFTATOM_MAX_STEPS_LSDA 150     /* DFTAtom.cpp:908 */
+
+enum {
+    DFTATOM_OK = 0,
+    DFTATOM_E_NO_DEVICE = -1,
+    DFTATOM_E_BAD_OPTION = -2,         /* outside the ranges OptionsFrame.cpp:46,152-173 enforces */
+    DFTATOM_E_MIXED_GRID = -3,         /* atoms of one batch must share (levels, delta, max_r) */
+    DFTATOM_E_CUDA = -4,
+    DFTATOM_E_ARG = -5
+};
+
+/* per-atom status (the reference is silent about non-convergence, DFTAtom.cpp:516-539) */
+enum {
+    DFTATOM_CONVERGED = 0,             /* the reference would have printed "Finished!" */
+    DFTATOM_MAX_STEPS = 1,             /* step cap hit (100 LDA / 150 LSDA), like the reference's silent fall-through */
+    DFTATOM_NUMERIC_FAILURE = 2        /* NaN/Inf in the energies */
+};
+
+/* Options.h:48-54 (field meaning identical; defaults Options.cpp:6: Z=36, levels=12, MaxR=10, delta=0.001, alpha=0.5, method=0) */
+typedef struct {
+    int Z;              /* 1..118 (OptionsFrame.cpp:152-154) */
+    int levels;         /* MultigridLevels, N = 2^levels + 1 nodes; 4..20 accepted (dialog shows 10..20) */
+    double max_r;       /* MaxR, 1..90 */
+    double delta;       /* deltaGrid, (0,1] */
+    double mixing;      /* alpha = weight of the OLD density, [0,1] */
+    int method;         /* 0 = LDA (banner says "LSD"), 1 = LSDA */
+} dftatom_options;
+
+typedef struct {
+    int n;              /* principal quantum number, 1-based as printed */
+    int l;              /* 0..3 -> s p d f */
+    int occ;            /* electrons in this (spin) subshell */
+    int nodes;          /* n - l - 1, the "Num nodes" the reference prints */
+    double E;           /* eigenvalue, Hartree */
+} dftatom_level;
+
+/* one "Step: k" block of the reference's output */
+typedef struct {
+    double E[2][DFTATOM_MAX_LEVELS];   /* eigenvalues, [spin][level in (n,l) order] */
+    double Etotal, Ekin, Ecoul, Eenuc, Exc;
+    int levels_converged;              /* reallyConverged of this step (DFTAtom.cpp:406,538) */
+    int reserved;
+} dftatom_step;
+
+typedef struct {
+    int status;                        /* DFTATOM_CONVERGED / MAX_STEPS / NUMERIC_FAILURE */
+    int n_steps;                       /* number of "Step:" blocks = index of last step + 1 */
+    int n_spin;                        /* 1 (LDA) or 2 (LSDA: alpha, beta) */
+    int n_levels[2];
+    dftatom_level levels[2][DFTATOM_MAX_LEVELS];   /* (n,l) order, eigenvalues of the last step */
+    dftatom_level sorted[2][DFTATOM_MAX_LEVELS];   /* same, sorted by eigenvalue: the final "1s2 2s2 ..." line (DFTAtom.cpp:487-490) */
+    double Etotal, Ekin, Ecoul, Eenuc, Exc;        /* last step */
+} dftatom_result;
+
+typedef struct dftatom_ctx dftatom_ctx;
+
+/* ---- context ---- */
+int dftatom_create(dftatom_ctx** ctx, int cuda_device);
+void dftatom_destroy(dftatom_ctx* ctx);
+const char* dftatom_last_error(void);
+const char* dftatom_version(void);
+/* tuning knobs (all default to reference-equivalent behaviour):
+ *   "max_vcycles"  (default 100 = PoissonSolver.h:117; V-cycles stop earlier once the update norm stagnates
+ *                   at its rounding floor unless "vcycle_floor_stop" is 0)
+ *   "vcycle_floor_stop" (default 1)
+ *   "r_segments"   (0 = auto) parallel-in-r split of the Numerov sweeps
+ *   "profile"      (default 0) time every kernel class with CUDA events, see dftatom_last_profile
+ */
+int dftatom_set_option(dftatom_ctx* ctx, const char* key, double value);
+
+/* ---- L0 rules (host, integer) ---- */
+/* AufbauPrinciple::GetSubshells + sort (AufbauPrinciple.h:36-75, DFTAtom.cpp:367). returns number of levels, or <0 */
+int dftatom_aufbau(int Z, dftatom_level* out, int max_out);
+/* DFTAtom::InitializeLevels (DFTAtom.cpp:611-638) */
+int dftatom_split_spin(int Z, dftatom_level* alpha, int* n_alpha, dftatom_level* beta, int* n_beta, int* n_alpha_el, int* n_beta_el);
+int dftatom_n_nodes(int levels);       /* PoissonSolver::GetNumberOfNodes, PoissonSolver.h:127-135 */
+
+/* ---- L2: the SCF (replaces CalculateNonUniformLDA/LSDA for a whole batch of independent atoms) ----
+ * opts[n_atoms], out[n_atoms] are HOST arrays.  steps may be NULL; otherwise it is a HOST array of
+ * n_atoms * steps_stride records receiving every SCF step (record k of atom a at steps[a*steps_stride + k]).
+ * All atoms of one call must share (levels, delta, max_r); Z, mixing, method may differ. */
+int dftatom_solve_batch(dftatom_ctx* ctx, const dftatom_options* opts, int n_atoms, dftatom_result* out,
+                        dftatom_step* steps, int steps_stride);
+/* device time (ms, CUDA events) of the last solve_batch's SCF loop, and number of kernel launches it issued */
+int dftatom_last_timing(dftatom_ctx* ctx, double* device_ms, long long* kernel_launches);
+
+/* Per-kernel-class profile of the last solve_batch, filled when set_option("profile", 1) was on: device time of
+ * every launch of the class (CUDA events on the launching stream), launch count and algorithmic work
+ * (class 0: Numerov (lane, node-step) pairs; class 3: Gauss-Seidel node-updates; others: 0). */
+enum { DFTATOM_K_SEARCH = 0, DFTATOM_K_MATCH = 1, DFTATOM_K_DENSITY = 2, DFTATOM_K_POISSON = 3, DFTATOM_K_POTENTIAL = 4, DFTATOM_K_COUNT = 5 };
+typedef struct { double ms; long long launches; double work; } dftatom_kernel_profile;
+int dftatom_last_profile(dftatom_ctx* ctx, dftatom_kernel_profile* out /* [DFTATOM_K_COUNT] */);
+/* measured FP64 FMA peak of the device (TFLOP/s, 2 flops per DFMA), the roofline denominator of the shooting kernel */
+int dftatom_measure_fp64_peak(dftatom_ctx* ctx, double* tflops);
+
+/* ---- L1 component entry points (HOST buffers; used by the parity tests and the microbenches) ---- */
+
+/* Batched inward Numerov sweeps on one potential (Numerov.h:272-349 CountNodes and :351-401 SolutionInZero).
+ * V[n_nodes] potential on the log grid, lanes k = 0..n_lanes-1 with (l[k], E[k], nodes_limit[k]).
+ * y0_sign[k] = 1 if SolutionInZero > 0 else 0; y0_log2[k] ~ log2|y0| (for the 1e15 guard); count[k] as CountNodes. */
+int dftatom_numerov_lanes(dftatom_ctx* ctx, const double* V, int levels, double delta, double max_r, int n_lanes,
+                          const int* l, const double* E, const int* nodes_limit,
+                          int* y0_sign, double* y0_log2, int* count);
+/* per-level eigenvalue search on one potential (DFTAtom.cpp:497-541 + LocateInterval :566-604), all levels concurrently */
+int dftatom_level_search(dftatom_ctx* ctx, const double* V, int levels, double delta, double max_r, int Z,
+                         int n_levels, const int* n, const int* l, double* E_out, int* converged_out);
+/* two-sided matched + normalised solution u(r) (Numerov.h:403-504 + DFTAtom.cpp:36-56) */
+int dftatom_numerov_orbital(dftatom_ctx* ctx, const double* V, int levels, double delta, double max_r,
+                            int l, double E, double* u_out, int* match_point);
+/* SolvePoissonNonUniform (PoissonSolver.h:51-81) for n_dens densities rho[n_dens][N] with boundary values (0, Z[k]) */
+int dftatom_poisson_solve(dftatom_ctx* ctx, int levels, double delta, double max_r, int n_dens, const int* Z,
+                          const double* rho, double* U, int* vcycles_used);
+/* n_cycles reference-shaped V-cycles (PoissonSolver.h:155-159) in place on phi[n_dens][N] with source src[n_dens][N] */
+int dftatom_poisson_vcycles(dftatom_ctx* ctx, int levels, double delta, int n_dens, double* phi, const double* src,
+                            int n_cycles, double* last_err);
+/* VWNExchCor::Vexc / eexcDif, LDA (VWNExcCor.h:73-128) and LSDA (:134-312; pass rho_b != NULL) */
+int dftatom_vwn(dftatom_ctx* ctx, int n, const double* rho_a, const double* rho_b, double* va, double* vb,
+                double* vexc, double* eexcdif);
+/* Integral::Simpson38 (Integral.h:50-73) of n_rows rows of length n */
+int dftatom_simpson38(dftatom_ctx* ctx, double step, const double* v, int n, int n_rows, double* out);
+
+/* ---- microbenches on DEVICE-resident data (bench.py `value` legs); pointers are CUDA device addresses ---- */
+int dftatom_poisson_vcycles_dev(dftatom_ctx* ctx, int levels, double delta, int n_dens, void* d_phi, const void* d_src,
+                                void* d_scratch, long long scratch_bytes, int n_cycles, float* device_ms);
+long long dftatom_poisson_scratch_bytes(int levels, int n_dens);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

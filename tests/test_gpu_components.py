@@ -1,0 +1,132 @@
+"""GPU parity tests of the component entry points (through the C ABI) against the CPU oracle on the same inputs."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _potential(kind, Z, r):
+    V = np.zeros_like(r)
+    if kind == "coulomb":
+        V[1:] = -Z / r[1:]
+    else:   # screened, with a bump: not monotone, exercises the turning-point logic
+        V[1:] = -Z / r[1:] * (0.35 + 0.65 * np.exp(-1.3 * r[1:])) + 1.5 * np.exp(-0.4 * r[1:])
+    return V
+
+
+@pytest.mark.parametrize("kind,L,delta,rmax,Z", [("coulomb", 12, 0.001, 15.0, 18), ("screened", 13, 0.0008, 30.0, 64),
+                                                 ("coulomb", 10, 0.004, 15.0, 92)])
+def test_numerov_lanes_match_oracle(ctx, kind, L, delta, rmax, Z):
+    """(sign y0, node count) of SolutionInZero / CountNodes: bit-exact except where |y0| is at its rounding floor."""
+    N, rp, r = O.grid(L, delta, rmax)
+    V = _potential(kind, Z, r)
+    rng = np.random.default_rng(L)
+    n_l = 384
+    ls = rng.integers(0, 4, n_l).astype(np.int32)
+    Es = np.concatenate([-10 ** rng.uniform(-2, np.log10(Z * Z + 1.0), n_l - 48), rng.uniform(0, 50, 48)])
+    lim = rng.integers(0, 6, n_l).astype(np.int32)
+    sign, lg, cnt = ctx.numerov_lanes(V, L, delta, rmax, ls, Es, lim)
+    y0, cnt_o = O.numerov_lanes(V, delta, rmax, ls, Es, lim)
+    assert np.array_equal(cnt, cnt_o)
+    assert np.array_equal(sign, (y0 > 0).astype(np.int32))
+    np.testing.assert_allclose(lg, np.log2(np.abs(y0)), atol=1e-6)     # |y0| to ~1e-6 relative (1e15 guard needs a factor 2)
+
+
+def test_numerov_known_answer_hydrogenic(ctx):
+    """V = -Z/r: y0(E) changes sign at E_n = -Z^2/2n^2; for l = 0 the node count steps from n-1 to n there."""
+    L, delta, rmax, Z = 14, 0.0005, 25.0, 18
+    N, rp, r = O.grid(L, delta, rmax)
+    V = _potential("coulomb", Z, r)
+    for n, l in [(1, 0), (2, 0), (2, 1), (3, 0), (3, 2), (4, 3)]:
+        En = -Z * Z / (2.0 * n * n)
+        E = np.array([En - 1e-3, En + 1e-3])
+        sign, lg, cnt = ctx.numerov_lanes(V, L, delta, rmax, [l, l], E, [50, 50])
+        assert sign[0] != sign[1]
+        if l == 0:
+            assert (cnt[0], cnt[1]) == (n - 1, n)
+
+
+@pytest.mark.parametrize("kind,L,delta,rmax,Z", [("coulomb", 12, 0.001, 15.0, 18), ("screened", 13, 0.0008, 30.0, 64)])
+def test_level_search_matches_oracle(ctx, kind, L, delta, rmax, Z):
+    """Eigenvalues of the concurrent K-section search vs the reference's chained bisection: <= 1e-9 Ha (bar: 1e-6)."""
+    N, rp, r = O.grid(L, delta, rmax)
+    V = _potential(kind, Z, r)
+    ns = [1, 2, 2, 3, 3, 3, 4, 4, 4, 4]
+    ls = [0, 0, 1, 0, 1, 2, 0, 1, 2, 3]
+    if kind == "screened":
+        ns, ls = ns[:6], ls[:6]
+    E_g, ok_g = ctx.level_search(V, L, delta, rmax, Z, ns, ls)
+    E_o, ok_o = O.level_search(V, delta, rmax, Z, ns, ls, chained=True)
+    np.testing.assert_allclose(E_g, E_o, rtol=0, atol=1e-9)
+    assert ok_g.tolist() == ok_o.tolist()
+    if kind == "coulomb":
+        np.testing.assert_allclose(E_g, [-Z * Z / (2.0 * n * n) for n in ns], atol=5e-5)
+
+
+def test_orbital_matches_oracle(ctx):
+    L, delta, rmax, Z = 12, 0.001, 15.0, 18
+    N, rp, r = O.grid(L, delta, rmax)
+    V = _potential("coulomb", Z, r)
+    for n, l in [(1, 0), (2, 1), (3, 0), (3, 2), (4, 3)]:
+        E = O.level_search(V, delta, rmax, Z, [n], [l], chained=False)[0][0] if l < 3 else -Z * Z / 32.0 - 1e-7
+        u_g, mp_g = ctx.numerov_orbital(V, L, delta, rmax, l, E)
+        u_o, mp_o = O.orbital(V, delta, rmax, l, E)
+        assert mp_g == mp_o
+        np.testing.assert_allclose(u_g, u_o, rtol=0, atol=1e-10)
+
+
+@pytest.mark.parametrize("L,delta,rmax", [(10, 0.004, 15.0), (14, 0.0005, 25.0), (16, 0.0002, 50.0)])
+def test_poisson_matches_oracle_and_analytic(ctx, L, delta, rmax):
+    """U(r) of FMG + V-cycles vs the reference algorithm (oracle, 100 V-cycles) and vs the analytic Hartree potential."""
+    N, rp, r = O.grid(L, delta, rmax)
+    Zs = [1, 18, 86]
+    a = [0.8, 1.7, 3.1]
+    rho = np.stack([Z * k ** 3 / np.pi * np.exp(-2 * k * r) for Z, k in zip(Zs, a)])
+    U, used = ctx.poisson_solve(L, delta, rmax, Zs, rho)
+    assert (used <= 20).all() and (used >= 3).all()
+    for j, (Z, k) in enumerate(zip(Zs, a)):
+        U_o, errs = O.poisson(L, delta, rmax, Z, rho[j], max_vcycles=100 if L <= 14 else 12)
+        U_x = Z * (1 - np.exp(-2 * k * r) * (1 + k * r))
+        # both are the same discrete solution up to their FP64 rounding floors (7e-10 at L=14)
+        assert np.max(np.abs(U[j] - U_o)) < 2e-9 * max(1, Z) * (4 if L > 14 else 1)
+        assert abs(np.max(np.abs(U[j] - U_x)) - np.max(np.abs(U_o - U_x))) < 1e-8 * Z
+        assert U[j][0] == 0.0 and U[j][-1] == Z
+
+
+def test_poisson_vcycle_shape(ctx):
+    """One reference-shaped V-cycle (3+3 lexicographic GS sweeps per level, injection, linear prolongation) from the same
+    state gives the same iterate as the oracle: the parallel scan evaluates the same sweep."""
+    L, delta = 12, 0.001
+    N, rp, r = O.grid(L, delta, 15.0)
+    rng = np.random.default_rng(3)
+    src = np.zeros((2, N)); src[:, 1:-1] = rng.standard_normal((2, N - 2)) * 1e-3
+    phi = np.zeros((2, N)); phi[:, -1] = [3.0, 40.0]
+    g, err = ctx.poisson_vcycles(L, delta, phi, src, 1)
+    for j in range(2):
+        o, err_o = O.poisson_vcycles(L, delta, phi[j], src[j], 1)
+        np.testing.assert_allclose(g[j], o, rtol=0, atol=1e-12 * np.max(np.abs(o)))
+        assert abs(err[j] - err_o) <= 1e-9 * err_o + 1e-15
+
+
+def test_vwn_matches_oracle(ctx):
+    rng = np.random.default_rng(0)
+    rho = np.concatenate([10.0 ** rng.uniform(-20, 5, 4000), [0.0, 1e-19, 1e-18, 0.999e-18]])
+    v, e = ctx.vwn(rho)
+    v_o, e_o = O.vwn_lda(rho)
+    np.testing.assert_allclose(v, v_o, rtol=2e-14, atol=1e-300)
+    np.testing.assert_allclose(e, e_o, rtol=2e-13, atol=1e-300)
+    rb = rho * rng.uniform(0, 1, len(rho))
+    rb[:10] = 0.0                        # fully polarised: rs_beta = inf (H atom)
+    for x, y in zip(ctx.vwn(rho, rb), O.vwn_lsda(rho, rb)):
+        np.testing.assert_allclose(x, y, rtol=5e-12, atol=1e-300)
+
+
+def test_simpson38_matches_oracle(ctx):
+    rng = np.random.default_rng(1)
+    for n in (5, 17, 1025, 16385):
+        v = rng.standard_normal((3, n))
+        out = ctx.simpson38(0.7, v)
+        ref = np.array([O.simpson38(0.7, row) for row in v])
+        np.testing.assert_allclose(out, ref, rtol=0, atol=1e-12 * np.sqrt(n))

@@ -1,0 +1,70 @@
+"""CPU tests of the host logic: C-ABI exports, Aufbau rules of the product library, report format, sharding."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import dftatom_b200 as D
+import oracle_lib as O
+from conftest import ROOT, golden
+from dftatom_b200.report import format_report, parse_report
+from dftatom_b200.shard import partition_atoms
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "dftatom_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dftatom_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = D.load_library()
+    names = _declared_symbols()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), n
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device creating a context must fail loudly (DFTATOM_E_NO_DEVICE), never fall back to the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(D.DFTAtomError):
+        D.Context(0)
+
+
+def test_product_aufbau_matches_oracle():
+    for Z in range(1, 119):
+        assert [(l.n, l.l, l.occ) for l in D.aufbau(Z)] == O.aufbau(Z)
+        assert all(l.nodes == l.n - l.l - 1 for l in D.aufbau(Z))
+        a, b, ea, eb = D.split_spin(Z)
+        oa, ob, oea, oeb = O.split_spin(Z)
+        assert [(l.n, l.l, l.occ) for l in a] == oa and [(l.n, l.l, l.occ) for l in b] == ob and (ea, eb) == (oea, oeb)
+    assert D.n_nodes(14) == 16385 and D.n_nodes(17) == 131073
+
+
+def test_report_roundtrip_against_reference_text():
+    """format_report(parse_report(reference stdout)) reproduces the reference's text byte for byte (6 decimals)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "dftatom_ref")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref not built")
+    import subprocess
+    for args, method in ((["3", "10", "0.5", "15", "0.004", "1"], 1), (["10", "10", "0.5", "15", "0.004", "0"], 0)):
+        text = subprocess.run([exe] + args, capture_output=True, text=True, check=True).stdout
+        rec = parse_report(text)
+        steps = [dict(levels=[(l["n"], l["l"], l["E"], l["nodes"]) for l in s["levels"]], **{k: s[k] for k in ("Etotal", "Ekin", "Ecoul", "Eenuc", "Exc")})
+                 for s in rec["steps"]]
+        out = format_report(rec["Z"], method, steps, rec["finished"], rec["final"]["alpha"], rec["final"].get("beta"))
+        assert out.rstrip("\n") == text.rstrip("\n")
+
+
+def test_partition_atoms_lpt():
+    zs = list(range(1, 93))
+    for g in (1, 2, 4, 8):
+        parts = partition_atoms(zs, g, method=0)
+        assert sorted(sum(parts, [])) == list(range(92))
+        loads = [sum(len(O.aufbau(zs[i])) for i in p) for p in parts]
+        assert max(loads) - min(loads) <= 19          # LPT: within one heaviest item
