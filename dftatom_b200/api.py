@@ -79,7 +79,7 @@ def load_library():
     lib.dftatom_last_timing.argtypes = [C.c_void_p, _dp, C.POINTER(C.c_longlong)]
     lib.dftatom_last_profile.argtypes = [C.c_void_p, C.POINTER(_CProfile)]
     lib.dftatom_measure_fp64_peak.argtypes = [C.c_void_p, _dp]
-    lib.dftatom_numerov_lanes.argtypes = [C.c_void_p, _dp, C.c_int, C.c_double, C.c_double, C.c_int, _ip, _dp, _ip, _ip, _dp, _ip]
+    lib.dftatom_numerov_lanes.argtypes = [C.c_void_p, _dp, C.c_int, C.c_double, C.c_double, C.c_int, _ip, _dp, _ip, C.c_int, _ip, _dp, _ip]
     lib.dftatom_level_search.argtypes = [C.c_void_p, _dp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, _ip, _ip, _dp, _ip]
     lib.dftatom_numerov_orbital.argtypes = [C.c_void_p, _dp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, _dp, _ip]
     lib.dftatom_poisson_solve.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, _ip, _dp, _dp, _ip]
@@ -276,11 +276,12 @@ class Context:
         return v.value
 
     # ---- L1 components ----
-    def numerov_lanes(self, V, levels, delta, max_r, l, E, nodes_limit):
+    def numerov_lanes(self, V, levels, delta, max_r, l, E, nodes_limit, impl=1):
+        """impl=1: reference-shaped sweep (count = CountNodes); impl=0: production sweep (count = full Sturm count)."""
         V = _f64(V); l = _i32(l); E = _f64(E); lim = _i32(nodes_limit)
         n = len(E)
         sign = np.zeros(n, np.int32); lg = np.zeros(n, np.float64); cnt = np.zeros(n, np.int32)
-        _check(self._lib.dftatom_numerov_lanes(self._h, _d(V), int(levels), float(delta), float(max_r), n, _i(l), _d(E), _i(lim),
+        _check(self._lib.dftatom_numerov_lanes(self._h, _d(V), int(levels), float(delta), float(max_r), n, _i(l), _d(E), _i(lim), int(impl),
                                                _i(sign), _d(lg), _i(cnt)))
         return sign, lg, cnt
 

@@ -47,13 +47,16 @@ struct dftatom_ctx {
     cudaStream_t stream = nullptr;
     std::map<GridKey, GridEntry> grids;
     // options
-    int max_vcycles = 100;
-    int floor_stop = 1;
+    int max_vcycles = 8;
+    int floor_stop = 0;
+    int refine_vcycles = 0;
     int r_segments = 0;
     int profile = 0;
+    int search_mode = 0;
+    int match_mode = 0;
     dftatom_kernel_profile prof[DFTATOM_K_COUNT] = {};
     // reusable buffers
-    DevBuf atoms, astate, orbs, ss, rho, rhot, vpot, atab, psi, match_pt, phi, src, zbc, tab_of, steps, n_active;
+    DevBuf atoms, astate, orbs, ss, rho, rhot, vpot, atab, psi, match_pt, phi, src, u0, zbc, tab_of, steps, n_active;
     DevBuf scratch[8];
     int* h_active = nullptr;       // pinned
     // timing of the last solve
@@ -155,7 +158,7 @@ void dftatom_destroy(dftatom_ctx* c)
     cudaStreamSynchronize(c->stream);
     for (auto& kv : c->grids) kv.second.mem.release();
     DevBuf* all[] = { &c->atoms, &c->astate, &c->orbs, &c->ss, &c->rho, &c->rhot, &c->vpot, &c->atab, &c->psi, &c->match_pt,
-                      &c->phi, &c->src, &c->zbc, &c->tab_of, &c->steps, &c->n_active };
+                      &c->phi, &c->src, &c->u0, &c->zbc, &c->tab_of, &c->steps, &c->n_active };
     for (DevBuf* b : all) b->release();
     for (DevBuf& b : c->scratch) b.release();
     if (c->h_active) cudaFreeHost(c->h_active);
@@ -169,8 +172,11 @@ int dftatom_set_option(dftatom_ctx* c, const char* key, double value)
     const std::string k(key);
     if (k == "max_vcycles") c->max_vcycles = std::max(1, (int)value);
     else if (k == "vcycle_floor_stop") c->floor_stop = value != 0.;
+    else if (k == "refine_vcycles") c->refine_vcycles = std::max(0, (int)value);
     else if (k == "r_segments") c->r_segments = (int)value;
     else if (k == "profile") c->profile = value != 0.;
+    else if (k == "search_mode") c->search_mode = (int)value;
+    else if (k == "match_mode") c->match_mode = (int)value;
     else { set_error("unknown option " + k); return DFTATOM_E_ARG; }
     return 0;
 }
@@ -297,6 +303,7 @@ int dftatom_solve_batch(dftatom_ctx* c, const dftatom_options* opts, int n_atoms
     if ((rc = c->match_pt.ensure(sizeof(int) * (size_t)n_orbs))) return rc;
     if ((rc = c->phi.ensure(sizeof(double) * (size_t)n_atoms * lv.total))) return rc;
     if ((rc = c->src.ensure(sizeof(double) * (size_t)n_atoms * lv.total))) return rc;
+    if ((rc = c->u0.ensure(sizeof(double) * (size_t)n_atoms * N))) return rc;
     if ((rc = c->steps.ensure(sizeof(dftatom_step) * (size_t)n_atoms * stride))) return rc;
     if ((rc = c->n_active.ensure(sizeof(int)))) return rc;
     DFT_CHECK(cudaMemsetAsync(c->steps.p, 0, sizeof(dftatom_step) * (size_t)n_atoms * stride, st));
@@ -314,6 +321,7 @@ int dftatom_solve_batch(dftatom_ctx* c, const dftatom_options* opts, int n_atoms
     pa.n_dens = n_atoms; pa.rho = b.rhot; pa.Zbc = b.Zbc; pa.phi = b.phi; pa.src = b.src;
     pa.skip = &b.astate[0].done; pa.skip_stride_bytes = (int)sizeof(AtomState);
     pa.max_vcycles = c->max_vcycles; pa.floor_stop = c->floor_stop;
+    pa.refine_vcycles = c->refine_vcycles; pa.u0 = c->u0.as<double>();
 
     cudaEvent_t ev0, ev1;
     DFT_CHECK(cudaEventCreate(&ev0));
@@ -346,10 +354,13 @@ int dftatom_solve_batch(dftatom_ctx* c, const dftatom_options* opts, int n_atoms
     for (int sp = 0; sp < max_steps; ++sp) {
         begin_span(DFTATOM_K_SEARCH);
         launch_search_init(g, b.atoms, b.astate, b.orbs, b.ss, n_orbs, st); ++launches;
-        for (int r = 0; r < rounds; ++r) { launch_search_round(g, b.atab, b.orbs, b.astate, b.ss, n_orbs, d_work + DFTATOM_K_SEARCH, st); ++launches; }
+        if (c->search_mode == 0) { launch_search_fused(g, b.atab, b.atoms, b.orbs, b.astate, b.ss, n_orbs, d_work + DFTATOM_K_SEARCH, st); ++launches; }
+        else for (int r = 0; r < rounds; ++r) { launch_search_round(g, b.atab, b.orbs, b.astate, b.ss, n_orbs, d_work + DFTATOM_K_SEARCH, st); ++launches; }
         end_span();
         begin_span(DFTATOM_K_MATCH);
-        launch_match(g, b.atab, b.orbs, b.astate, b.ss, b.psi, b.match_pt, n_orbs, st); ++launches;
+        if (c->match_mode == 0) launch_match_seg(g, b.atab, b.orbs, b.astate, b.ss, b.psi, b.match_pt, n_orbs, st);
+        else launch_match(g, b.atab, b.orbs, b.astate, b.ss, b.psi, b.match_pt, n_orbs, st);
+        ++launches;
         end_span();
         begin_span(DFTATOM_K_DENSITY);
         launch_density_update(g, b, st); ++launches;
@@ -383,7 +394,7 @@ int dftatom_solve_batch(dftatom_ctx* c, const dftatom_options* opts, int n_atoms
             float t = 0.f;
             cudaEventElapsedTime(&t, s.a, s.b);
             c->prof[s.cls].ms += t;
-            c->prof[s.cls].launches += (s.cls == DFTATOM_K_SEARCH) ? rounds + 1 : 1;
+            c->prof[s.cls].launches += (s.cls == DFTATOM_K_SEARCH) ? (c->search_mode == 0 ? 2 : rounds + 1) : 1;
             cudaEventDestroy(s.a); cudaEventDestroy(s.b);
         }
     }
@@ -422,10 +433,22 @@ int dftatom_solve_batch(dftatom_ctx* c, const dftatom_options* opts, int n_atoms
 // component entry points (host buffers)
 // ---------------------------------------------------------------------------------------------------------
 
-int dftatom_numerov_lanes(dftatom_ctx* c, const double* V, int levels, double delta, double max_r, int n_lanes, const int* l,
-                          const double* E, const int* nodes_limit, int* y0_sign, double* y0_log2, int* count)
+int dftatom_numerov_lanes(dftatom_ctx* c, const double* V, int levels, double delta, double max_r, int n_lanes_in, const int* l_in,
+                          const double* E_in, const int* limit_in, int impl, int* y0_sign_out, double* y0_log2_out, int* count_out)
 {
-    if (!c || !V || n_lanes <= 0) return DFTATOM_E_ARG;
+    if (!c || !V || n_lanes_in <= 0 || !l_in || !E_in || !limit_in) return DFTATOM_E_ARG;
+    // the production sweep shares one (potential, l) table tile per warp: group the lanes by l, pad every group to 32
+    std::vector<int> perm, lv, limv; std::vector<double> Ev;
+    for (int ll = 0; ll < 8; ++ll) {
+        size_t before = lv.size();
+        for (int k = 0; k < n_lanes_in; ++k) if (l_in[k] == ll) { perm.push_back(k); lv.push_back(ll); Ev.push_back(E_in[k]); limv.push_back(limit_in[k]); }
+        while (lv.size() > before && (lv.size() & 31)) { perm.push_back(-1); lv.push_back(ll); Ev.push_back(Ev.back()); limv.push_back(limv.back()); }
+    }
+    if (lv.empty()) { set_error("l out of range"); return DFTATOM_E_ARG; }
+    const int n_lanes = (int)lv.size();
+    const int* l = lv.data(); const double* E = Ev.data(); const int* nodes_limit = limv.data();
+    std::vector<int> hs(n_lanes), hc(n_lanes); std::vector<double> hl(n_lanes);
+    int* y0_sign = hs.data(); double* y0_log2 = hl.data(); int* count = hc.data();
     DFT_CHECK(cudaSetDevice(c->device));
     GridDev* gp; int rc = get_grid(c, levels, delta, max_r, &gp); if (rc) return rc;
     const GridDev g = *gp; const int N = g.N; cudaStream_t st = c->stream;
@@ -441,12 +464,18 @@ int dftatom_numerov_lanes(dftatom_ctx* c, const double* V, int levels, double de
     DFT_CHECK(cudaMemcpyAsync(d_lim, nodes_limit, sizeof(int) * n_lanes, cudaMemcpyHostToDevice, st));
     DFT_CHECK(cudaMemcpyAsync(d_E, E, sizeof(double) * n_lanes, cudaMemcpyHostToDevice, st));
     NumerovLaneArgs a{ dA.as<double>(), n_lanes, d_tab, d_l, d_E, d_lim, d_sign, d_log, d_cnt };
-    launch_numerov_lanes(g, a, st);
+    if (impl == 0) launch_numerov_lanes_fast(g, a, st); else launch_numerov_lanes(g, a, st);
     if (y0_sign) DFT_CHECK(cudaMemcpyAsync(y0_sign, d_sign, sizeof(int) * n_lanes, cudaMemcpyDeviceToHost, st));
     if (y0_log2) DFT_CHECK(cudaMemcpyAsync(y0_log2, d_log, sizeof(double) * n_lanes, cudaMemcpyDeviceToHost, st));
     if (count) DFT_CHECK(cudaMemcpyAsync(count, d_cnt, sizeof(int) * n_lanes, cudaMemcpyDeviceToHost, st));
     DFT_CHECK(cudaStreamSynchronize(st));
     DFT_CHECK(cudaGetLastError());
+    for (int k = 0; k < n_lanes; ++k) {
+        if (perm[k] < 0) continue;
+        if (y0_sign_out) y0_sign_out[perm[k]] = hs[k];
+        if (y0_log2_out) y0_log2_out[perm[k]] = hl[k];
+        if (count_out) count_out[perm[k]] = hc[k];
+    }
     return 0;
 }
 
@@ -482,7 +511,8 @@ int dftatom_level_search(dftatom_ctx* c, const double* V, int levels, double del
     if ((rc = setup_single(c, g, V, Z, orbs, &da, &ds, &dorb, &dss, &datab))) return rc;
     launch_search_init(g, da, ds, dorb, dss, n_levels, st);
     const int rounds = search_rounds_needed(Z);
-    for (int r = 0; r < rounds; ++r) launch_search_round(g, datab, dorb, ds, dss, n_levels, nullptr, st);
+    if (c->search_mode == 0) launch_search_fused(g, datab, da, dorb, ds, dss, n_levels, nullptr, st);
+    else for (int r = 0; r < rounds; ++r) launch_search_round(g, datab, dorb, ds, dss, n_levels, nullptr, st);
     std::vector<SearchState> h(n_levels);
     DFT_CHECK(cudaMemcpyAsync(h.data(), dss, sizeof(SearchState) * n_levels, cudaMemcpyDeviceToHost, st));
     DFT_CHECK(cudaStreamSynchronize(st));
@@ -509,7 +539,8 @@ int dftatom_numerov_orbital(dftatom_ctx* c, const double* V, int levels, double 
     DFT_CHECK(cudaMemcpyAsync(dss, &s, sizeof(s), cudaMemcpyHostToDevice, st));
     // single-atom ScfBuffers so that density_update's normalisation path is the one exercised
     if ((rc = c->psi.ensure(sizeof(double) * N)) || (rc = c->match_pt.ensure(sizeof(int)))) return rc;
-    launch_match(g, datab, dorb, ds, dss, c->psi.as<double>(), c->match_pt.as<int>(), 1, st);
+    if (c->match_mode == 0) launch_match_seg(g, datab, dorb, ds, dss, c->psi.as<double>(), c->match_pt.as<int>(), 1, st);
+    else launch_match(g, datab, dorb, ds, dss, c->psi.as<double>(), c->match_pt.as<int>(), 1, st);
     std::vector<double> y(N), sq(N), wj(N);
     int mp = 0;
     DFT_CHECK(cudaMemcpyAsync(y.data(), c->psi.p, sizeof(double) * N, cudaMemcpyDeviceToHost, st));
@@ -543,6 +574,8 @@ int dftatom_poisson_solve(dftatom_ctx* c, int levels, double delta, double max_r
     PoissonArgs pa{};
     pa.n_dens = n_dens; pa.rho = dr.as<double>(); pa.Zbc = dz.as<int>(); pa.phi = c->phi.as<double>(); pa.src = c->src.as<double>();
     pa.max_vcycles = c->max_vcycles; pa.floor_stop = c->floor_stop; pa.vcycles_used = dv.as<int>();
+    if ((rc = c->u0.ensure(sizeof(double) * (size_t)n_dens * N))) return rc;
+    pa.refine_vcycles = c->refine_vcycles; pa.u0 = c->u0.as<double>();
     launch_poisson_full(g, lv, pa, st);
     DFT_CHECK(cudaMemcpy2DAsync(U, sizeof(double) * N, c->phi.p, sizeof(double) * lv.total, sizeof(double) * N, n_dens, cudaMemcpyDeviceToHost, st));
     if (vcycles_used) DFT_CHECK(cudaMemcpyAsync(vcycles_used, dv.p, sizeof(int) * n_dens, cudaMemcpyDeviceToHost, st));

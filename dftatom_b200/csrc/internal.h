@@ -95,11 +95,17 @@ void launch_search_init(const GridDev& g, const AtomDev* atoms, const AtomState*
                         int n_orbs, cudaStream_t st);
 void launch_search_round(const GridDev& g, const double* atab, const OrbitalDev* orbs, const AtomState* astate, SearchState* ss,
                          int n_orbs, unsigned long long* work, cudaStream_t st);
+void launch_numerov_lanes_fast(const GridDev& g, const NumerovLaneArgs& a, cudaStream_t st);
+void launch_search_fused(const GridDev& g, const double* atab, const AtomDev* atoms, const OrbitalDev* orbs, const AtomState* astate,
+                         SearchState* ss, int n_orbs, unsigned long long* work, cudaStream_t st);
 void launch_dfma_peak(double* out, int blocks, int threads, int iters, cudaStream_t st);
 int search_rounds_needed(int Zmax);
 
 void launch_match(const GridDev& g, const double* atab, const OrbitalDev* orbs, const AtomState* astate, const SearchState* ss,
                   double* psi, int* match_pt, int n_orbs, cudaStream_t st);
+
+void launch_match_seg(const GridDev& g, const double* atab, const OrbitalDev* orbs, const AtomState* astate, const SearchState* ss,
+                      double* psi, int* match_pt, int n_orbs, cudaStream_t st);
 
 // potential -> a-table (a_i = 1 - (2K_i V_i + δ²/4)/12), n_tabs rows
 void launch_build_atab(const GridDev& g, const double* vpot, double* atab, int n_tabs, cudaStream_t st);
@@ -113,6 +119,8 @@ struct PoissonArgs {
     const int* skip;        // optional per-density skip flag (AtomState.done), stride given
     int skip_stride_bytes;
     int max_vcycles; int floor_stop;
+    int refine_vcycles;     // > 0: double-double defect correction with this many V-cycles on the error equation
+    double* u0;             // [n_dens][N] scratch for the correction (required when refine_vcycles > 0)
     unsigned long long* work;   // optional: += Gauss-Seidel node-updates performed
     int* vcycles_used;      // optional [n_dens]
     double* last_err;       // optional [n_dens]

@@ -6,9 +6,15 @@
 //
 // The reference's smoother is a lexicographic in-place Gauss-Seidel sweep, i.e. the first-order recurrence
 //     Phi_i <- a Phi_{i-1} + c_i ,   a = (1 + d_l/2)/2 ,   c_i = (S_i + (1 - d_l/2) Phi_{i+1}^old)/2 ,  d_l = δ 2^l .
-// Here every thread owns M consecutive nodes: it runs the recurrence locally with zero carry-in, the carries are
-// resolved by an associative block scan of the affine maps x -> a^m x + p, and the result is patched in.  That is
-// the same sweep (same operator, same ordering), evaluated in O(M + log T) depth instead of O(N).
+// Every thread owns NPT consecutive nodes: it runs the recurrence locally with zero carry-in, the carries are
+// resolved by an associative scan of the affine maps x -> a^m x + p (warp shuffles, then one shared-memory hop
+// across warps), and the result is patched in.  That is the same sweep (same operator, same ordering), evaluated
+// in O(NPT + log T) depth instead of O(N).
+//
+// Level visits keep a thread's nodes of Phi and Source in registers for the three sweeps (levels up to 16384 nodes);
+// the six coarsest levels (<= 32 nodes) are run by warp 0 alone with no block barrier.  The update norm of the
+// reference's IterateGaussSeidel only drives its early exits; with a fixed number of sweeps it is evaluated once,
+// for the last fine-grid sweep of the solve.
 #include "internal.h"
 #include <cmath>
 
@@ -29,14 +35,18 @@ PoissonLevels make_levels(int L)
 }
 
 constexpr int kPT = 512;     // threads per CTA
-constexpr int kPM = 16;      // nodes per thread per pass
+constexpr int kPM = 16;      // nodes per thread per pass of the generic (global-memory) sweep
+constexpr int kMaxNpt = 32;  // register-resident visits handle levels with up to kPT * kMaxNpt nodes
+constexpr int kWarpLevelNodes = 32;
 
 struct PoissonSmem {
     double scanA[32], scanP[32];
+    double edge[32];
     double red[32];
     double carry;        // last new value of the previous pass
     double bcast;
     unsigned long long updates;   // Gauss-Seidel node-updates performed by this CTA (work counter)
+    int pending;
 };
 
 __device__ __forceinline__ double block_sum(double v, PoissonSmem& sm)
@@ -57,8 +67,10 @@ __device__ __forceinline__ double block_sum(double v, PoissonSmem& sm)
     return sm.bcast;
 }
 
-// One lexicographic Gauss-Seidel sweep over level arrays (phi, src) of `size` nodes; returns sqrt(sum (old-new)^2).
-__device__ double gs_sweep(double* __restrict__ phi, const double* __restrict__ src, int size, double d, PoissonSmem& sm)
+// ---------------------------------------------------------------------------------------------------------
+// generic sweep on global-memory level arrays (any size, multi-pass); returns sqrt(sum (old-new)^2)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __noinline__ double gs_sweep(double* __restrict__ phi, const double* __restrict__ src, int size, double d, PoissonSmem& sm)
 {
     const int T = blockDim.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
     const double a = 0.5 * (1. + 0.5 * d), bcoef = 0.5 * (1. - 0.5 * d);
@@ -73,19 +85,16 @@ __device__ double gs_sweep(double* __restrict__ phi, const double* __restrict__ 
         double p[kPM];
         double A = 1., x = 0.;
         if (m > 0) {
-            double nxt = phi[i0];
 #pragma unroll
             for (int k = 0; k < kPM; ++k) {
                 if (k < m) {
-                    nxt = phi[i0 + k + 1];
-                    const double c = fma(bcoef, nxt, 0.5 * src[i0 + k]);
+                    const double c = fma(bcoef, phi[i0 + k + 1], 0.5 * src[i0 + k]);
                     x = fma(a, x, c);
                     p[k] = x;
                     A *= a;
                 }
             }
         }
-        // inclusive scan of the affine maps (A, x) across the block
         double sA = A, sP = x;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -106,12 +115,11 @@ __device__ double gs_sweep(double* __restrict__ phi, const double* __restrict__ 
             sm.scanA[lane] = wa; sm.scanP[lane] = wp;   // inclusive over warps
         }
         __syncthreads();
-        // exclusive prefix for this thread = (warps before) o (lanes before)
         double eA = __shfl_up_sync(0xffffffffu, sA, 1), eP = __shfl_up_sync(0xffffffffu, sP, 1);
         if (lane == 0) { eA = 1.; eP = 0.; }
         if (w > 0) { const double wa = sm.scanA[w - 1], wp = sm.scanP[w - 1]; eP = fma(eA, wp, eP); eA *= wa; }
         const double left = sm.carry;
-        double cin = fma(eA, left, eP);             // new value of node i0-1
+        const double cin = fma(eA, left, eP);       // new value of node i0-1
         if (m > 0) {
             double q = a;
 #pragma unroll
@@ -127,26 +135,109 @@ __device__ double gs_sweep(double* __restrict__ phi, const double* __restrict__ 
         }
         __syncthreads();
         if (t == T - 1) sm.carry = fma(sm.scanA[(T >> 5) - 1], left, sm.scanP[(T >> 5) - 1]);
-        // (visible to all after the next pass's first __syncthreads; thread 0 re-reads it only after that)
         __syncthreads();
     }
     return sqrt(block_sum(err2, sm));
 }
 
-__device__ double gs_smooth(double* phi, const double* src, int size, double d, double tol, int sweeps, PoissonSmem& sm)
-{   // IterateGaussSeidel, PoissonSolver.cpp:66-77
-    double err = 1e10;
-    for (int k = 0; k < sweeps; ++k) {
-        err = gs_sweep(phi, src, size, d, sm);
-        if (err < tol) break;
+// ---------------------------------------------------------------------------------------------------------
+// register-resident level visit: `sweeps` Gauss-Seidel sweeps on a level with n = size-1 <= kPT*NPT owned nodes
+// (thread t owns nodes [t NPT, (t+1) NPT); node 0 is the fixed left boundary, node n the fixed right boundary)
+// ---------------------------------------------------------------------------------------------------------
+template <int NPT, bool SRC_REGS>
+__device__ __noinline__ void visit_regs(double* __restrict__ phi_g, const double* __restrict__ src_g, int size, double d, int sweeps,
+                                           PoissonSmem& sm)
+{
+    const unsigned full = 0xffffffffu;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5, nw = blockDim.x >> 5;
+    const int n = size - 1;
+    const int i0 = t * NPT;
+    const bool active = i0 < n;
+    const double a = 0.5 * (1. + 0.5 * d), bcoef = 0.5 * (1. - 0.5 * d);
+    const double right_bc = phi_g[n];
+    double phi[NPT], src[SRC_REGS ? NPT : 1];
+    const double* __restrict__ sp = src_g + (active ? i0 : 0);      // Source is read-only during the visit
+#pragma unroll
+    for (int k = 0; k < NPT; ++k) {
+        phi[k] = active ? phi_g[i0 + k] : 0.;
+        if (SRC_REGS) src[k] = active ? 0.5 * src_g[i0 + k] : 0.;
     }
-    return err;
+    double aN = a;
+#pragma unroll
+    for (int k = 1; k < NPT; ++k) aN *= a;
+    if (t == 0) sm.updates += (unsigned long long)sweeps * (unsigned long long)(n - 1);
+
+    for (int sw = 0; sw < sweeps; ++sw) {
+        // old value of the right neighbour's first node
+        double nb = __shfl_down_sync(full, phi[0], 1);
+        if (lane == 0) sm.edge[w] = phi[0];
+        __syncthreads();
+        if (lane == 31) nb = (w + 1 < nw) ? sm.edge[w + 1] : right_bc;
+        if (i0 + NPT >= n) nb = right_bc;
+        // local recurrence with zero carry-in, in place
+        double x = 0.;
+#pragma unroll
+        for (int k = 0; k < NPT; ++k) {
+            const double nxt = (k + 1 < NPT) ? phi[k + 1] : nb;
+            const double c = fma(bcoef, nxt, SRC_REGS ? src[k] : 0.5 * __ldg(sp + k));
+            x = (t == 0 && k == 0) ? phi[0] : fma(a, x, c);      // node 0 keeps its boundary value
+            phi[k] = x;
+        }
+        double sA = active ? (t == 0 ? 0. : aN) : 1., sP = active ? x : 0.;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double pa = __shfl_up_sync(full, sA, o), pp = __shfl_up_sync(full, sP, o);
+            if (lane >= o) { sP = fma(sA, pp, sP); sA *= pa; }
+        }
+        if (lane == 31) { sm.scanA[w] = sA; sm.scanP[w] = sP; }
+        __syncthreads();
+        double carry = 0.;
+        for (int q = 0; q < w; ++q) carry = fma(sm.scanA[q], carry, sm.scanP[q]);
+        double eA = __shfl_up_sync(full, sA, 1), eP = __shfl_up_sync(full, sP, 1);
+        if (lane == 0) { eA = 1.; eP = 0.; }
+        const double cin = fma(eA, carry, eP);                    // new value of node i0-1
+        double q = a;
+#pragma unroll
+        for (int k = 0; k < NPT; ++k) { phi[k] = fma(q, cin, phi[k]); q *= a; }
+    }
+    if (active) {
+#pragma unroll
+        for (int k = 0; k < NPT; ++k) phi_g[i0 + k] = phi[k];
+    }
+    __syncthreads();
 }
 
-__device__ void mg_restrict(const double* __restrict__ pf, const double* __restrict__ sf, double* __restrict__ pc,
-                            double* __restrict__ sc, int nc, double dc)
+// same for a level of <= 32 owned nodes, executed by one warp, no block barrier
+__device__ __noinline__ void visit_warp(double* __restrict__ phi_g, const double* __restrict__ src_g, int size, double d, int sweeps)
+{
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int n = size - 1;
+    const bool active = lane < n;
+    const double a = 0.5 * (1. + 0.5 * d), bcoef = 0.5 * (1. - 0.5 * d);
+    const double right_bc = phi_g[n];
+    double phi = active ? phi_g[lane] : 0.;
+    const double src = active ? 0.5 * src_g[lane] : 0.;
+    for (int sw = 0; sw < sweeps; ++sw) {
+        double nb = __shfl_down_sync(full, phi, 1);
+        if (lane + 1 >= n) nb = right_bc;
+        const double c = fma(bcoef, nb, src);
+        double sA = active ? (lane == 0 ? 0. : a) : 1., sP = active ? (lane == 0 ? phi : c) : 0.;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double pa = __shfl_up_sync(full, sA, o), pp = __shfl_up_sync(full, sP, o);
+            if (lane >= o) { sP = fma(sA, pp, sP); sA *= pa; }
+        }
+        phi = sP;      // inclusive scan value = new Phi of this node (carry-in of node 0 is its own fixed value)
+    }
+    if (active) phi_g[lane] = phi;
+    __syncwarp();
+}
+
+__device__ __forceinline__ void restrict_nodes(const double* __restrict__ pf, const double* __restrict__ sf, double* __restrict__ pc,
+                                               double* __restrict__ sc, int nc, double dc, int tid, int nthr)
 {   // Restrict, PoissonSolver.cpp:126-157
-    for (int i = threadIdx.x; i < nc; i += blockDim.x) {
+    for (int i = tid; i < nc; i += nthr) {
         pc[i] = 0.;
         double v = 0.;
         if (i > 0 && i < nc - 1) {
@@ -156,40 +247,127 @@ __device__ void mg_restrict(const double* __restrict__ pf, const double* __restr
         }
         sc[i] = v;
     }
-    __syncthreads();
 }
 
-__device__ void mg_prolong(const double* __restrict__ pc, double* __restrict__ pf, int nc)
+__device__ __forceinline__ void prolong_nodes(const double* __restrict__ pc, double* __restrict__ pf, int nc, int tid, int nthr)
 {   // Prolong, PoissonSolver.cpp:110-123
-    for (int i = threadIdx.x; i < nc; i += blockDim.x) {
+    for (int i = tid; i < nc; i += nthr) {
         const double c = pc[i];
         pf[2 * i] += c;
         if (i > 0) pf[2 * i - 1] += 0.5 * (pc[i - 1] + c);
     }
-    __syncthreads();
 }
 
-struct LevelPtrs { double* phi; double* src; };
+// One multigrid hierarchy of one density; every method is called by all threads of the CTA.
+struct Hierarchy {
+    double* phi; double* src;
+    const PoissonLevels& lv;
+    double delta;
+    PoissonSmem& sm;
+    bool pending;        // warp 0 wrote coarse levels that the other warps have not synchronised with yet
 
-__device__ __forceinline__ void to_coarse(double* phi, double* src, const PoissonLevels& lv, double delta, int from, int to,
-                                          double tol, PoissonSmem& sm)
-{   // "Ascend", PoissonSolver.cpp:162-171
-    for (int l = from; l < to; ++l) {
-        gs_smooth(phi + lv.off[l], src + lv.off[l], lv.size[l], delta * (double)(1 << l), tol, 3, sm);
-        mg_restrict(phi + lv.off[l], src + lv.off[l], phi + lv.off[l + 1], src + lv.off[l + 1], lv.size[l + 1], delta * (double)(1 << (l + 1)));
+    __device__ __forceinline__ double dl(int l) const { return delta * (double)(1 << l); }
+    __device__ __forceinline__ bool warp_level(int l) const { return lv.size[l] - 1 <= kWarpLevelNodes; }
+    __device__ __forceinline__ void block_begin() { if (pending) { __syncthreads(); pending = false; } }
+
+    // IterateGaussSeidel(l, ., sweeps) without the early exit
+    __device__ __forceinline__ void smooth(int l, int sweeps)
+    {
+        double* p = phi + lv.off[l];
+        const double* s = src + lv.off[l];
+        const int size = lv.size[l], n = size - 1;
+        if (warp_level(l)) {
+            if (threadIdx.x < 32) {
+                if (threadIdx.x == 0) sm.updates += (unsigned long long)sweeps * (unsigned long long)(n - 1);
+                visit_warp(p, s, size, dl(l), sweeps);
+            }
+            pending = true;
+            return;
+        }
+        block_begin();
+        if (n > kPT * kMaxNpt) { for (int k = 0; k < sweeps; ++k) gs_sweep(p, s, size, dl(l), sm); }
+        else if (n > kPT * 16) visit_regs<32, false>(p, s, size, dl(l), sweeps, sm);
+        else if (n > kPT * 8) visit_regs<16, true>(p, s, size, dl(l), sweeps, sm);
+        else if (n > kPT * 4) visit_regs<8, true>(p, s, size, dl(l), sweeps, sm);
+        else if (n > kPT * 2) visit_regs<4, true>(p, s, size, dl(l), sweeps, sm);
+        else if (n > kPT) visit_regs<2, true>(p, s, size, dl(l), sweeps, sm);
+        else visit_regs<1, true>(p, s, size, dl(l), sweeps, sm);
     }
-    gs_smooth(phi + lv.off[to], src + lv.off[to], lv.size[to], delta * (double)(1 << to), tol, 3, sm);
+    __device__ __forceinline__ void restrict_to(int l)       // level l-1 -> l
+    {
+        if (warp_level(l)) {                                  // <= 33 coarse nodes: warp 0 alone (level l-1 is complete: either
+            if (threadIdx.x < 32) {                           //  a block op ended with a barrier or warp 0 wrote it itself)
+                restrict_nodes(phi + lv.off[l - 1], src + lv.off[l - 1], phi + lv.off[l], src + lv.off[l], lv.size[l], dl(l), threadIdx.x, 32);
+                __syncwarp();
+            }
+            pending = true;
+            return;
+        }
+        block_begin();
+        restrict_nodes(phi + lv.off[l - 1], src + lv.off[l - 1], phi + lv.off[l], src + lv.off[l], lv.size[l], dl(l), threadIdx.x, blockDim.x);
+        __syncthreads();
+    }
+    __device__ __forceinline__ void prolong_from(int l)      // level l -> l-1
+    {
+        if (warp_level(l - 1)) {
+            if (threadIdx.x < 32) { prolong_nodes(phi + lv.off[l], phi + lv.off[l - 1], lv.size[l], threadIdx.x, 32); __syncwarp(); }
+            pending = true;
+            return;
+        }
+        block_begin();
+        prolong_nodes(phi + lv.off[l], phi + lv.off[l - 1], lv.size[l], threadIdx.x, blockDim.x);
+        __syncthreads();
+    }
+    __device__ __forceinline__ void to_coarse(int from, int to)      // "Ascend", PoissonSolver.cpp:162-171
+    {
+        for (int l = from; l < to; ++l) { smooth(l, 3); restrict_to(l + 1); }
+        smooth(to, 3);
+    }
+    __device__ __forceinline__ void to_fine(int from, int to)        // "Descend", PoissonSolver.cpp:173-186
+    {
+        for (int l = from; l > to; --l) { prolong_from(l); smooth(l - 1, 3); }
+    }
+    // the last fine-grid visit of a solve: two register sweeps + one generic sweep that also returns the update norm
+    __device__ __forceinline__ double to_fine_with_norm(int from)
+    {
+        for (int l = from; l > 1; --l) { prolong_from(l); smooth(l - 1, 3); }
+        if (from >= 1) prolong_from(1);
+        smooth(0, 2);
+        block_begin();
+        return gs_sweep(phi, src, lv.size[0], dl(0), sm);
+    }
+};
+
+// error-free transformations (Dekker / Knuth); the intrinsics keep nvcc from contracting or re-associating them
+__device__ __forceinline__ void two_sum(double a, double b, double& s, double& e)
+{
+    s = __dadd_rn(a, b);
+    const double bb = __dadd_rn(s, -a);
+    e = __dadd_rn(__dadd_rn(a, -__dadd_rn(s, -bb)), __dadd_rn(b, -bb));
+}
+__device__ __forceinline__ void two_prod(double a, double b, double& p, double& e)
+{
+    p = __dmul_rn(a, b);
+    e = __fma_rn(a, b, -p);
+}
+__device__ __forceinline__ void dd_add(double& hi, double& lo, double x, double xe)
+{
+    double s, e;
+    two_sum(hi, x, s, e);
+    hi = s;
+    lo = __dadd_rn(lo, __dadd_rn(e, xe));
 }
 
-__device__ __forceinline__ double to_fine(double* phi, double* src, const PoissonLevels& lv, double delta, int from, int to,
-                                          double tol, PoissonSmem& sm)
-{   // "Descend", PoissonSolver.cpp:173-186
-    double err = 1e10;
-    for (int l = from; l > to; --l) {
-        mg_prolong(phi + lv.off[l], phi + lv.off[l - 1], lv.size[l]);
-        err = gs_smooth(phi + lv.off[l - 1], src + lv.off[l - 1], lv.size[l - 1], delta * (double)(1 << (l - 1)), tol, 3, sm);
-    }
-    return err;
+// residual of the fine-grid equation  U_{i-1}(1+δ/2) - 2 U_i + U_{i+1}(1-δ/2) = -S_i  in double-double.
+// In FP64 the three U terms cancel to ~1e-7 of their size, which is what floors the plain iteration at ~1e-9 in U
+// (SURVEY fact 3); evaluated with error-free transformations the residual is exact to ~1e-30.
+__device__ __forceinline__ double dd_residual(double S, double um, double u0, double up, double cl, double cr)
+{
+    double hi = S, lo = 0., p, e;
+    two_prod(cl, um, p, e); dd_add(hi, lo, p, e);
+    dd_add(hi, lo, -2. * u0, 0.);
+    two_prod(cr, up, p, e); dd_add(hi, lo, p, e);
+    return __dadd_rn(hi, lo);
 }
 
 __global__ void __launch_bounds__(kPT) poisson_full_kernel(GridDev g, PoissonLevels lv, PoissonArgs a)
@@ -201,7 +379,6 @@ __global__ void __launch_bounds__(kPT) poisson_full_kernel(GridDev g, PoissonLev
     double* phi = a.phi + (size_t)k * lv.total;
     double* src = a.src + (size_t)k * lv.total;
     const int N = g.N, L = lv.L, c = L - 1;
-    const double delta = g.delta;
 
     // Source_0 (PoissonSolver.h:55-74) and Initialize (PoissonSolver.cpp:80-106)
     if (a.rho) {
@@ -227,27 +404,52 @@ __global__ void __launch_bounds__(kPT) poisson_full_kernel(GridDev g, PoissonLev
         phi[lv.off[c] + lv.size[c] - 1] = a.Zbc ? (double)a.Zbc[k] : 0.;
     }
     __syncthreads();
-    gs_smooth(phi + lv.off[c], src + lv.off[c], lv.size[c], delta * (double)(1 << c), 1e-3, 15, sm);
+    Hierarchy h{ phi, src, lv, g.delta, sm, false };
+    h.smooth(c, 2);        // the coarsest level has one interior node: the reference's <= 15 sweeps converge in one
 
     // FullCycle, PoissonSolver.h:89-124
     for (int l = L - 2; l > 0; --l) {
-        to_fine(phi, src, lv, delta, c, l, 1e-3, sm);
-        to_coarse(phi, src, lv, delta, l, c, 1e-3, sm);
+        h.to_fine(c, l);
+        h.to_coarse(l, c);
     }
-    to_fine(phi, src, lv, delta, c, 0, 1e-14, sm);
+    h.to_fine(c, 0);
     double err = 0., prev = 1e300;
     int used = 0, stagnant = 0;
     for (int it = 0; it < a.max_vcycles; ++it) {
-        to_coarse(phi, src, lv, delta, 0, c, 1e-14, sm);
-        err = to_fine(phi, src, lv, delta, c, 0, 1e-14, sm);
+        h.to_coarse(0, c);
+        const bool last = (it == a.max_vcycles - 1);
         ++used;
-        if (err < 1e-14) break;                                       // PoissonSolver.h:120
-        if (a.floor_stop) {
-            // the update norm contracts ~25x per cycle until it reaches its FP64 rounding floor;
-            // once it stops contracting, further cycles only re-roll the rounding noise.
-            if (err > 0.25 * prev) { if (++stagnant >= 2) break; } else stagnant = 0;
+        if (last || a.floor_stop) {
+            err = h.to_fine_with_norm(c);
+            if (err < 1e-14) break;                                   // PoissonSolver.h:120
+            // the update norm contracts ~25x per cycle until it reaches its FP64 rounding floor
+            if (a.floor_stop) { if (err > 0.25 * prev) { if (++stagnant >= 2) break; } else stagnant = 0; }
+            prev = err;
+        } else {
+            h.to_fine(c, 0);
         }
-        prev = err;
+    }
+    h.block_begin();
+    // Defect correction (beyond the reference): one residual in double-double, then the error equation A e = r is solved
+    // by the same V-cycles from e = 0 (its own rounding floor is ~1e-9 |e|, i.e. negligible) and U <- U + e.  The result
+    // is the discrete solution to FP64 representation accuracy instead of ~1e-9, which removes the rounding-noise floor
+    // of the SCF energies (the reference's |dE/E| wanders at 2e-11..1e-10 before it randomly dips below 1e-11).
+    if (a.refine_vcycles > 0 && a.u0) {
+        double* u0 = a.u0 + (size_t)k * N;
+        const double cl = 1. + 0.5 * g.delta, cr = 1. - 0.5 * g.delta;
+        // r into a register, U0 saved, then Source_0 <- r, Phi_0 <- 0 (all levels' Phi are re-zeroed by restriction)
+        for (int i = threadIdx.x; i < N; i += blockDim.x)
+            u0[i] = (i > 0 && i < N - 1) ? dd_residual(src[i], phi[i - 1], phi[i], phi[i + 1], cl, cr) : 0.;
+        __syncthreads();
+        for (int i = threadIdx.x; i < N; i += blockDim.x) {      // same thread owns node i in both passes
+            const double r = u0[i];
+            u0[i] = phi[i]; src[i] = r; phi[i] = 0.;
+        }
+        __syncthreads();
+        for (int it = 0; it < a.refine_vcycles; ++it) { h.to_coarse(0, c); h.to_fine(c, 0); }
+        h.block_begin();
+        for (int i = threadIdx.x; i < N; i += blockDim.x) phi[i] += u0[i];
+        __syncthreads();
     }
     if (threadIdx.x == 0) {
         if (a.work) atomicAdd(a.work, sm.updates);
@@ -270,11 +472,13 @@ __global__ void __launch_bounds__(kPT) poisson_vcycles_kernel(double delta, Pois
     double* phi = phi_all + (size_t)k * lv.total;
     double* src = src_all + (size_t)k * lv.total;
     const int c = lv.L - 1;
+    Hierarchy h{ phi, src, lv, delta, sm, false };
     double err = 0.;
     for (int it = 0; it < n_cycles; ++it) {
-        to_coarse(phi, src, lv, delta, 0, c, 1e-14, sm);
-        err = to_fine(phi, src, lv, delta, c, 0, 1e-14, sm);
+        h.to_coarse(0, c);
+        if (it == n_cycles - 1) err = h.to_fine_with_norm(c); else h.to_fine(c, 0);
     }
+    h.block_begin();
     if (threadIdx.x == 0 && last_err) last_err[k] = err;
 }
 

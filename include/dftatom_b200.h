@@ -85,10 +85,19 @@ void dftatom_destroy(dftatom_ctx* ctx);
 const char* dftatom_last_error(void);
 const char* dftatom_version(void);
 /* tuning knobs (all default to reference-equivalent behaviour):
- *   "max_vcycles"  (default 100 = PoissonSolver.h:117; V-cycles stop earlier once the update norm stagnates
- *                   at its rounding floor unless "vcycle_floor_stop" is 0)
- *   "vcycle_floor_stop" (default 1)
+ *   "max_vcycles"  (default 8) V-cycles after the FMG ramp.  The reference runs 100 (PoissonSolver.h:117) because its
+ *                   exit test err < 1e-14 never fires; the update norm reaches its FP64 rounding floor after ~6
+ *                   (SURVEY fact 3).  A fixed, data-independent count keeps the solve a smooth function of the density,
+ *                   which the SCF stop test |dE/E| < 1e-11 needs.  Set 100 to reproduce the reference's count.
+ *   "refine_vcycles" (default 0 = off) V-cycles of an optional double-double defect correction after the plain solve.
+ *                   It yields the discrete solution to FP64 representation accuracy, but the reference's own answer
+ *                   carries the ~1e-9 rounding-floor bias of plain FP64 multigrid (worth ~1e-5 Ha in Etotal at Z~90),
+ *                   so parity with the reference requires it to stay off.
+ *   "vcycle_floor_stop" (default 0) 1 = stop as soon as the update norm stagnates (data dependent)
+ *   "match_mode"   (default 0) 0 = segmented two-sided solve (production); 1 = serial reference-arithmetic kernel
  *   "r_segments"   (0 = auto) parallel-in-r split of the Numerov sweeps
+ *   "search_mode"  (default 0) 0 = fused single-predicate multisection (production); 1 = reference-shaped three-stage
+ *                   search (node-count window edges, then the sign change of y(0)), kept for validation
  *   "profile"      (default 0) time every kernel class with CUDA events, see dftatom_last_profile
  */
 int dftatom_set_option(dftatom_ctx* ctx, const char* key, double value);
@@ -122,9 +131,12 @@ int dftatom_measure_fp64_peak(dftatom_ctx* ctx, double* tflops);
 
 /* Batched inward Numerov sweeps on one potential (Numerov.h:272-349 CountNodes and :351-401 SolutionInZero).
  * V[n_nodes] potential on the log grid, lanes k = 0..n_lanes-1 with (l[k], E[k], nodes_limit[k]).
- * y0_sign[k] = 1 if SolutionInZero > 0 else 0; y0_log2[k] ~ log2|y0| (for the 1e15 guard); count[k] as CountNodes. */
+ * y0_sign[k] = 1 if SolutionInZero > 0 else 0; y0_log2[k] ~ log2|y0| (for the 1e15 guard).
+ * impl = 1: reference-shaped sweep, count[k] = CountNodes (with its early exits, clamped at nodes_limit+1).
+ * impl = 0: the production tile-staged sweep, count[k] = number of ALL sign changes of y_start..y_1,y_0 (the Sturm count
+ *           the fused search uses; nodes_limit ignored; -1 if the lane hit a non-positive 1 - f/12). */
 int dftatom_numerov_lanes(dftatom_ctx* ctx, const double* V, int levels, double delta, double max_r, int n_lanes,
-                          const int* l, const double* E, const int* nodes_limit,
+                          const int* l, const double* E, const int* nodes_limit, int impl,
                           int* y0_sign, double* y0_log2, int* count);
 /* per-level eigenvalue search on one potential (DFTAtom.cpp:497-541 + LocateInterval :566-604), all levels concurrently */
 int dftatom_level_search(dftatom_ctx* ctx, const double* V, int levels, double delta, double max_r, int Z,

@@ -206,6 +206,33 @@ int orc_numerov_count_nodes(const double* V, int n_nodes, double delta, double m
     return count;
 }
 
+int orc_numerov_count_all(const double* V, int n_nodes, double delta, double max_r, int l, double E)
+{   /* NOT a reference function: the sweep of Numerov.h:272-349 with its three early exits disabled, i.e. the number
+     * of sign changes in y_start-1 .. y_1, y_0 (the Sturm count the CUDA search uses as its predicate). */
+    const nfun g = nfun_make(V, n_nodes, delta, max_r);
+    const long start = nf_start(&g, E, n_nodes - 1);
+    const double twelfth = 1. / 12.;
+    double y = nf_far(&g, (double)start, E);
+    double yprev = y;
+    double f = nf_f(&g, l, E, start);
+    double wprev = (1 - twelfth * f) * y;
+    y = nf_far(&g, (double)start - 1., E);
+    f = nf_f(&g, l, E, start - 1);
+    double w = (1 - twelfth * f) * y;
+    int positive = y > 0, count = 0;
+    for (long i = start - 2; i > 0; --i) {
+        const double wnext = 2. * w - wprev + y * f;
+        wprev = w; w = wnext;
+        f = nf_f(&g, l, E, i);
+        yprev = y;
+        y = GETU(w, f);
+        if ((y > 0) != positive) { ++count; positive = !positive; }
+    }
+    y = y * (2 + f) - yprev;
+    if ((y > 0) != positive) ++count;
+    return count;
+}
+
 double orc_numerov_y0(const double* V, int n_nodes, double delta, double max_r, int l, double E)
 {   /* Numerov.h:351-401 */
     const nfun g = nfun_make(V, n_nodes, delta, max_r);
@@ -653,6 +680,12 @@ static void spin_channel_density(const double* V, int n, double delta, double ma
 
 int orc_scf(const orc_options* opt, orc_result* res, orc_step_cb cb, void* user, int max_vcycles)
 {
+    return orc_scf_ex(opt, res, cb, user, max_vcycles, NULL, NULL);
+}
+
+/* same, additionally exporting the final potentials V_out[2][N] and spin densities rho_out[2][N] (either may be NULL) */
+int orc_scf_ex(const orc_options* opt, orc_result* res, orc_step_cb cb, void* user, int max_vcycles, double* V_out, double* rho_out)
+{
     const int Z = opt->Z, lsda = opt->method != 0;
     const int n = orc_n_nodes(opt->levels);
     const double delta = opt->delta, max_r = opt->max_r;
@@ -769,6 +802,8 @@ int orc_scf(const orc_options* opt, orc_result* res, orc_step_cb cb, void* user,
         sort_levels_by_energy(res->sorted[s], n_lv[s]);            /* :487 / :1012-1013 */
     }
 
+    if (V_out) { memcpy(V_out, V[0], bytes); memcpy(V_out + n, V[1], bytes); }
+    if (rho_out) { memcpy(rho_out, rho_s[0], bytes); memcpy(rho_out + n, rho_s[1], bytes); }
     free(rho_s[0]); free(rho_s[1]); if (lsda) free(rho);
     free(V[0]); free(V[1]); free(vxc_s[0]); free(vxc_s[1]); free(U); free(vexc); free(edif); free(acc); free(psi);
     free(g_nuc); free(g_xc); free(g_dif); free(g_har); free(g_pot);

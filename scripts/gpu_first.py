@@ -22,7 +22,7 @@ for E in [-400., -1., 10., 49.]:
     for l in range(4):
         ls.append(l); Es.append(E); lim.append(2)
 t0 = time.time()
-sign, lg, cnt = ctx.numerov_lanes(V, L, delta, rmax, ls, Es, lim)
+sign, lg, cnt = ctx.numerov_lanes(V, L, delta, rmax, ls, Es, lim, impl=1)
 y0, cnt_o = O.numerov_lanes(V, delta, rmax, ls, Es, lim)
 print("numerov lanes:", len(Es), "sign mismatches", int(np.sum(sign != (y0 > 0))), "count mismatches", int(np.sum(cnt != cnt_o)),
       "max |log2 diff|", float(np.nanmax(np.abs(lg - np.log2(np.abs(y0))))))

@@ -66,6 +66,7 @@ def main():
     if a.name in FINAL_ONLY:
         for r in res:
             r["etotal_per_step"] = [s["Etotal"] for s in r["steps"]]
+            r["eig_per_step"] = [[l["E"] for l in s["levels"]] for s in r["steps"]]
             r["steps_kept"] = "last"
             r["n_steps"] = len(r["steps"])
             r["steps"] = r["steps"][-1:]

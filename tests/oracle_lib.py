@@ -56,6 +56,7 @@ def oracle():
         L.orc_rp.argtypes = [C.c_int, C.c_double, C.c_double]
         L.orc_numerov_start_index.argtypes = [C.c_double, C.c_int, C.c_double, C.c_double]
         L.orc_numerov_count_nodes.argtypes = [_dp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_int]
+        L.orc_numerov_count_all.argtypes = [_dp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double]
         L.orc_numerov_y0.restype = C.c_double
         L.orc_numerov_y0.argtypes = [_dp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double]
         L.orc_numerov_match.restype = C.c_long
@@ -136,6 +137,11 @@ def numerov_lanes(V, delta, max_r, l, E, limit):
     y0 = np.array([oracle().orc_numerov_y0(d(V), len(V), delta, max_r, int(li), float(Ei)) for li, Ei in zip(l, E)])
     cnt = np.array([oracle().orc_numerov_count_nodes(d(V), len(V), delta, max_r, int(li), float(Ei), int(k)) for li, Ei, k in zip(l, E, limit)], np.int32)
     return y0, cnt
+
+
+def numerov_count_all(V, delta, max_r, l, E):
+    V = np.ascontiguousarray(V, np.float64)
+    return np.array([oracle().orc_numerov_count_all(d(V), len(V), delta, max_r, int(li), float(Ei)) for li, Ei in zip(l, E)], np.int32)
 
 
 def level_search(V, delta, max_r, Z, n, l, chained=True):
