@@ -54,6 +54,8 @@ struct dftatom_ctx {
     int profile = 0;
     int search_mode = 0;
     int match_mode = 0;
+    int energies_per_lane = 1;
+    int warm_start = 1;
     dftatom_kernel_profile prof[DFTATOM_K_COUNT] = {};
     // reusable buffers
     DevBuf atoms, astate, orbs, ss, rho, rhot, vpot, atab, psi, match_pt, phi, src, u0, zbc, tab_of, steps, n_active;
@@ -177,6 +179,8 @@ int dftatom_set_option(dftatom_ctx* c, const char* key, double value)
     else if (k == "profile") c->profile = value != 0.;
     else if (k == "search_mode") c->search_mode = (int)value;
     else if (k == "match_mode") c->match_mode = (int)value;
+    else if (k == "warm_start") c->warm_start = value != 0.;
+    else if (k == "energies_per_lane") c->energies_per_lane = ((int)value == 2) ? 2 : 1;
     else { set_error("unknown option " + k); return DFTATOM_E_ARG; }
     return 0;
 }
@@ -307,6 +311,7 @@ int dftatom_solve_batch(dftatom_ctx* c, const dftatom_options* opts, int n_atoms
     if ((rc = c->steps.ensure(sizeof(dftatom_step) * (size_t)n_atoms * stride))) return rc;
     if ((rc = c->n_active.ensure(sizeof(int)))) return rc;
     DFT_CHECK(cudaMemsetAsync(c->steps.p, 0, sizeof(dftatom_step) * (size_t)n_atoms * stride, st));
+    DFT_CHECK(cudaMemsetAsync(c->ss.p, 0, sizeof(SearchState) * (size_t)n_orbs, st));
     DFT_CHECK(cudaMemcpyAsync(c->n_active.p, &n_atoms, sizeof(int), cudaMemcpyHostToDevice, st));
 
     ScfBuffers b{};
@@ -353,9 +358,13 @@ int dftatom_solve_batch(dftatom_ctx* c, const dftatom_options* opts, int n_atoms
     const int lag = 2;
     for (int sp = 0; sp < max_steps; ++sp) {
         begin_span(DFTATOM_K_SEARCH);
-        launch_search_init(g, b.atoms, b.astate, b.orbs, b.ss, n_orbs, st); ++launches;
-        if (c->search_mode == 0) { launch_search_fused(g, b.atab, b.atoms, b.orbs, b.astate, b.ss, n_orbs, d_work + DFTATOM_K_SEARCH, st); ++launches; }
-        else for (int r = 0; r < rounds; ++r) { launch_search_round(g, b.atab, b.orbs, b.astate, b.ss, n_orbs, d_work + DFTATOM_K_SEARCH, st); ++launches; }
+        if (c->search_mode == 0) {
+            launch_search_fused(g, b.atab, b.atoms, b.orbs, b.astate, b.ss, n_orbs, d_work + DFTATOM_K_SEARCH, c->energies_per_lane, c->warm_start, st);
+            ++launches;
+        } else {
+            launch_search_init(g, b.atoms, b.astate, b.orbs, b.ss, n_orbs, st); ++launches;
+        }
+        if (c->search_mode != 0) for (int r = 0; r < rounds; ++r) { launch_search_round(g, b.atab, b.orbs, b.astate, b.ss, n_orbs, d_work + DFTATOM_K_SEARCH, st); ++launches; }
         end_span();
         begin_span(DFTATOM_K_MATCH);
         if (c->match_mode == 0) launch_match_seg(g, b.atab, b.orbs, b.astate, b.ss, b.psi, b.match_pt, n_orbs, st);
@@ -394,7 +403,7 @@ int dftatom_solve_batch(dftatom_ctx* c, const dftatom_options* opts, int n_atoms
             float t = 0.f;
             cudaEventElapsedTime(&t, s.a, s.b);
             c->prof[s.cls].ms += t;
-            c->prof[s.cls].launches += (s.cls == DFTATOM_K_SEARCH) ? (c->search_mode == 0 ? 2 : rounds + 1) : 1;
+            c->prof[s.cls].launches += (s.cls == DFTATOM_K_SEARCH) ? (c->search_mode == 0 ? 1 : rounds + 1) : 1;
             cudaEventDestroy(s.a); cudaEventDestroy(s.b);
         }
     }
@@ -511,7 +520,7 @@ int dftatom_level_search(dftatom_ctx* c, const double* V, int levels, double del
     if ((rc = setup_single(c, g, V, Z, orbs, &da, &ds, &dorb, &dss, &datab))) return rc;
     launch_search_init(g, da, ds, dorb, dss, n_levels, st);
     const int rounds = search_rounds_needed(Z);
-    if (c->search_mode == 0) launch_search_fused(g, datab, da, dorb, ds, dss, n_levels, nullptr, st);
+    if (c->search_mode == 0) launch_search_fused(g, datab, da, dorb, ds, dss, n_levels, nullptr, c->energies_per_lane, 0, st);
     else for (int r = 0; r < rounds; ++r) launch_search_round(g, datab, dorb, ds, dss, n_levels, nullptr, st);
     std::vector<SearchState> h(n_levels);
     DFT_CHECK(cudaMemcpyAsync(h.data(), dss, sizeof(SearchState) * n_levels, cudaMemcpyDeviceToHost, st));

@@ -97,7 +97,7 @@ void launch_search_round(const GridDev& g, const double* atab, const OrbitalDev*
                          int n_orbs, unsigned long long* work, cudaStream_t st);
 void launch_numerov_lanes_fast(const GridDev& g, const NumerovLaneArgs& a, cudaStream_t st);
 void launch_search_fused(const GridDev& g, const double* atab, const AtomDev* atoms, const OrbitalDev* orbs, const AtomState* astate,
-                         SearchState* ss, int n_orbs, unsigned long long* work, cudaStream_t st);
+                         SearchState* ss, int n_orbs, unsigned long long* work, int epl, int warm_start, cudaStream_t st);
 void launch_dfma_peak(double* out, int blocks, int threads, int iters, cudaStream_t st);
 int search_rounds_needed(int Zmax);
 

@@ -23,23 +23,47 @@
 
 namespace dft {
 
-struct FastOut { int cfull; int y0_pos; int bad; int steps; double y0_log2; double d_first; };
+// ld.shared.v2.f64 as volatile asm: keeps the staged-table loads where they are written (ptxas otherwise sinks every
+// LDS next to its first use and recycles the same destination registers, which serialises the loads and puts the
+// ~30-cycle shared-memory latency on every node).
+__device__ __forceinline__ double2 lds_f64x2(unsigned addr)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
 
-// warp-collective; sbuf = this warp's double-buffered tile staging area [2][32]
-__device__ __forceinline__ FastOut fast_sweep(const GridDev& g, const double* __restrict__ atab, double nll1, double E, double2* sbuf)
+template <int EPL> struct FastOut {
+    int cfull[EPL]; int y0_pos[EPL]; double y0_log2[EPL]; double d_first[EPL];
+    int bad; long long steps;
+};
+
+// warp-collective; sbuf = this warp's double-buffered tile staging area [2][32].
+// Every lane carries EPL independent trial energies (EPL chains of the recurrence interleave in the pipeline).
+template <int EPL>
+__device__ __forceinline__ void fast_sweep(const GridDev& g, const double* __restrict__ atab, double nll1, const double (&E)[EPL],
+                                           double2* sbuf, FastOut<EPL>& out)
 {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const double kappa = sqrt(2. * fabs(E));
-    const int start = start_index(g, kappa);
-    int imax = start;
+    double kappa[EPL];
+    int start[EPL];
+    int imax = 0;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+        kappa[e] = sqrt(2. * fabs(E[e]));
+        start[e] = start_index(g, kappa[e]);
+        imax = max(imax, start[e]);
+    }
 #pragma unroll
     for (int o = 16; o; o >>= 1) imax = max(imax, __shfl_xor_sync(full, imax, o));
     const int nmax = g.N - 1;
 
-    double W1 = 0., W2 = 0., d1 = 1., dd1 = 1., n1 = 2., P = 1.;
-    unsigned prev = 0;
-    int count = 0, bad = 0;
+    double W1[EPL], W2[EPL], d1[EPL], dd1[EPL], n1[EPL], P[EPL];
+    unsigned prev[EPL];
+    int count[EPL], bad = 0;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) { W1[e] = 0.; W2[e] = 0.; d1[e] = 1.; dd1[e] = 1.; n1[e] = 2.; P[e] = 1.; prev[e] = 0; count[e] = 0; }
 
     int m = imax >> 5;
     // prefetch the top tile: lane j holds node 32 m + 31 - j
@@ -57,68 +81,113 @@ __device__ __forceinline__ FastOut fast_sweep(const GridDev& g, const double* __
             pa = __ldg(atab + i); pb = __ldg(g.b12 + i); pc = __ldg(g.c6 + i);
         }
         const int hi_i = (m << 5) + 31, lo_i = m << 5;
-        const bool uniform = (start >= hi_i + 2) || (start < lo_i);
+        bool uniform = true;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) uniform = uniform && ((start[e] >= hi_i + 2) || (start[e] < lo_i));
         const double2* tile = sbuf + cur * 32;
         if (m > 0 && __all_sync(full, uniform)) {
-            // ---- fast tile: every lane is either fully inside its sweep or has not started yet (W stays 0) ----
-            unsigned sb = 0;
+            // ---- fast tile: every chain is either fully inside its sweep or has not started yet (W stays 0) ----
+            // Four quarters of 8 nodes.  Phase A (no loop-carried dependence): d, n = 12 - 10 d, dd = d_k d_{k-1} of the
+            // quarter.  Phase B: the W chain, one dependent DFMA per node.
+            unsigned sb[EPL];
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-                const double2 t = tile[k];
-                const double W = fma(n1, W1, -(dd1 * W2));
-                sb = __funnelshift_l((unsigned)hi32(W), sb, 1);
-                const double d = fma(E, t.y, t.x);
-                const double dd = d * d1;
-                n1 = fma(-10., d, 12.);
-                if (k & 1) P *= dd;                     // even node index: pairs (i, i+1)
-                W2 = W1; W1 = W; d1 = d; dd1 = dd;
+            for (int e = 0; e < EPL; ++e) sb[e] = 0;
+            // Four quarters of 8 nodes.  The 8 staged table entries of quarter q+1 are fetched (8 LDS.128 into distinct
+            // registers) before quarter q is computed, so the shared-memory latency never sits on the dependency chain.
+            // Phase A (no loop-carried dependence): d, n = 12 - 10 d, dd = d_k d_{k-1}.  Phase B: the W chain.
+            double2 tq[2][8];
+            const unsigned taddr = (unsigned)__cvta_generic_to_shared(tile);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) tq[0][k] = lds_f64x2(taddr + 16u * k);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int cb = q & 1, nb = cb ^ 1;
+                if (q < 3) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) tq[nb][k] = lds_f64x2(taddr + 16u * ((q + 1) * 8 + k));
+                }
+                double nq[EPL][8], dq[EPL][8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+#pragma unroll
+                    for (int e = 0; e < EPL; ++e) {
+                        const double d = fma(E[e], tq[cb][k].y, tq[cb][k].x);
+                        dq[e][k] = d * d1[e];
+                        nq[e][k] = fma(-10., d, 12.);
+                        d1[e] = d;
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < EPL; ++e)      // even node index <=> odd k: pairs (i, i+1) of the running product of d
+                    P[e] *= (dq[e][1] * dq[e][3]) * (dq[e][5] * dq[e][7]);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+#pragma unroll
+                    for (int e = 0; e < EPL; ++e) {
+                        const double nu = k ? nq[e][k - 1] : n1[e], du = k ? dq[e][k - 1] : dd1[e];
+                        const double W = fma(nu, W1[e], -(du * W2[e]));
+                        sb[e] = __funnelshift_l((unsigned)hi32(W), sb[e], 1);
+                        W2[e] = W1[e]; W1[e] = W;
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < EPL; ++e) { n1[e] = nq[e][7]; dd1[e] = dq[e][7]; }
             }
-            const unsigned x = sb ^ ((sb >> 1) | (prev << 31));
-            count += __popc(x);
-            prev = sb & 1u;
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) {
+                const unsigned x = sb[e] ^ ((sb[e] >> 1) | (prev[e] << 31));
+                count[e] += __popc(x);
+                prev[e] = sb[e] & 1u;
+            }
         } else {
             // ---- general tile: seeds (far boundary values), the last tile down to i = 1, sign of d ----
             for (int k = 0; k < 32; ++k) {
                 const int i = hi_i - k;
                 if (i < 1) break;
                 const double2 t = tile[k];
-                const double d = fma(E, t.y, t.x);
-                if (i <= start) {
-                    double W, dd;
-                    if (i == start) {                      // w_start = d_start far(start)   (Numerov.h:294-298)
-                        W = d * far_value(g, kappa, i);
-                        dd = d; P = 1.; count = 0; prev = 0;
-                        bad |= !(d > 0.);
-                    } else if (i == start - 1) {           // w_{start-1}                    (Numerov.h:300-303)
-                        W = d * far_value(g, kappa, i) * d1;
-                        dd = d * d1;
-                        bad |= !(d > 0.);
-                    } else {
-                        W = fma(n1, W1, -(dd1 * W2));
-                        dd = d * d1;
-                        const unsigned sy = ((unsigned)hi32(W) ^ (unsigned)hi32(d)) >> 31;    // y_i = W_i / (P_i d_i), P_i > 0
-                        count += (sy != prev);
-                        prev = sy;
-                        if (i == 2) bad |= !(d > 0.);
+#pragma unroll
+                for (int e = 0; e < EPL; ++e) {
+                    const double d = fma(E[e], t.y, t.x);
+                    if (i <= start[e]) {
+                        double W, dd;
+                        if (i == start[e]) {                      // w_start = d_start far(start)   (Numerov.h:294-298)
+                            W = d * far_value(g, kappa[e], i);
+                            dd = d; P[e] = 1.; count[e] = 0; prev[e] = 0;
+                            bad |= !(d > 0.);
+                        } else if (i == start[e] - 1) {           // w_{start-1}                    (Numerov.h:300-303)
+                            W = d * far_value(g, kappa[e], i) * d1[e];
+                            dd = d * d1[e];
+                            bad |= !(d > 0.);
+                        } else {
+                            W = fma(n1[e], W1[e], -(dd1[e] * W2[e]));
+                            dd = d * d1[e];
+                            const unsigned sy = ((unsigned)hi32(W) ^ (unsigned)hi32(d)) >> 31;    // y_i = W_i / (P_i d_i), P_i > 0
+                            count[e] += (sy != prev[e]);
+                            prev[e] = sy;
+                            if (i == 2) bad |= !(d > 0.);
+                        }
+                        if (!(i & 1)) P[e] *= dd;
+                        n1[e] = fma(-10., d, 12.);
+                        W2[e] = W1[e]; W1[e] = W; d1[e] = d; dd1[e] = dd;
                     }
-                    if (!(i & 1)) P *= dd;
-                    n1 = fma(-10., d, 12.);
-                    W2 = W1; W1 = W; d1 = d; dd1 = dd;
                 }
             }
         }
         cur ^= 1;
     }
-    // W1 = W_1, W2 = W_2, d1 = d_1, P = prod_{j=2..start} d_j;  y_0 = y_1 (2 + f_1) - y_2  (Numerov.h:398)
-    const double Y0s = W1 * fma(-12., d1, 14.) / d1 - W2;
-    FastOut o;
-    o.y0_pos = Y0s > 0.;
-    o.y0_log2 = (fabs(Y0s) <= 1.7e308) ? log2(fabs(Y0s)) - log2(fabs(P)) : INFINITY;
-    o.cfull = count + (((o.y0_pos ? 0u : 1u) != prev) ? 1 : 0);
-    o.bad = bad | !(P > 0.);
-    o.steps = start - 1;
-    o.d_first = d1;
-    return o;
+    out.bad = bad;
+    out.steps = 0;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+        // W1 = W_1, W2 = W_2, d1 = d_1, P = prod_{j=2..start} d_j;  y_0 = y_1 (2 + f_1) - y_2  (Numerov.h:398)
+        const double Y0s = W1[e] * fma(-12., d1[e], 14.) / d1[e] - W2[e];
+        out.y0_pos[e] = Y0s > 0.;
+        out.y0_log2[e] = (fabs(Y0s) <= 1.7e308) ? log2(fabs(Y0s)) - log2(fabs(P[e])) : INFINITY;
+        out.cfull[e] = count[e] + (((out.y0_pos[e] ? 0u : 1u) != prev[e]) ? 1 : 0);
+        out.bad |= !(P[e] > 0.);
+        out.steps += start[e] - 1;
+        out.d_first[e] = d1[e];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -132,11 +201,13 @@ __global__ void __launch_bounds__(128) numerov_lanes_fast_kernel(GridDev g, Nume
     if ((k & ~31) >= a.n_lanes) return;
     const int kk = min(k, a.n_lanes - 1);
     const int l = a.l[kk];
-    const FastOut o = fast_sweep(g, a.atab + (size_t)a.tab[kk] * g.N, -(double)(l * (l + 1)), a.E[kk], sbuf + warp * 64);
+    FastOut<1> o;
+    const double E1[1] = { a.E[kk] };
+    fast_sweep<1>(g, a.atab + (size_t)a.tab[kk] * g.N, -(double)(l * (l + 1)), E1, sbuf + warp * 64, o);
     if (k < a.n_lanes) {
-        if (a.y0_sign) a.y0_sign[k] = o.y0_pos;
-        if (a.y0_log2) a.y0_log2[k] = o.y0_log2;
-        if (a.count) a.count[k] = o.bad ? -1 : o.cfull;
+        if (a.y0_sign) a.y0_sign[k] = o.y0_pos[0];
+        if (a.y0_log2) a.y0_log2[k] = o.y0_log2[0];
+        if (a.count) a.count[k] = o.bad ? -1 : o.cfull[0];
     }
 }
 
@@ -148,11 +219,13 @@ void launch_numerov_lanes_fast(const GridDev& g, const NumerovLaneArgs& a, cudaS
 // ---------------------------------------------------------------------------------------------------------
 // fused search: one warp per orbital, all rounds in one launch
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) search_fused_kernel(GridDev g, const double* __restrict__ atab_all, const AtomDev* atoms,
+template <int EPL>
+__global__ void __launch_bounds__(128, 1) search_fused_kernel(GridDev g, const double* __restrict__ atab_all, const AtomDev* atoms,
                                                            const OrbitalDev* orbs, const AtomState* astate, SearchState* ss, int n_orbs,
-                                                           unsigned long long* work)
+                                                           unsigned long long* work, int warm_start)
 {
     __shared__ double2 sbuf[4 * 64];
+    constexpr int K = 32 * EPL;                           // trial energies per round
     const unsigned full = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int k = blockIdx.x * 4 + warp;
@@ -165,23 +238,59 @@ __global__ void __launch_bounds__(128) search_fused_kernel(GridDev g, const doub
     double lo = -Z * Z - 1., hi = kTopEnergy;             // DFTAtom.cpp:407,499
     double ylog = 0.;
     long long steps = 0;
+    // Warm start: the predicate is monotone, so ANY ascending set of trial energies brackets the same root.  From the
+    // second SCF step on, the first round samples a geometric ladder around the previous step's eigenvalue
+    // (+-2.4e-13 ... +-8.4 Ha); a root outside the ladder just leaves the global bracket's far end in place.
+    const bool warm = warm_start && ss[k].pad == 1;
+    const double e_prev = ss[k].E;
     for (int round = 0; round < 64 && bracket_open(lo, hi); ++round) {
-        const double E = lo + (hi - lo) * ((double)(lane + 1) / 33.);
-        FastOut o = fast_sweep(g, atab, nll1, E, sbuf + warp * 64);
-        int cfull = o.cfull; int off = o.d_first < 0.;
+        // point j of the round (j = 0..K-1, ascending in energy) lives in lane j % 32, slot j / 32
+        double E[EPL];
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+            const int j = e * 32 + lane;
+            E[e] = lo + (hi - lo) * ((double)(j + 1) / (double)(K + 1));
+            if (warm && round == 0) {
+                const int half = K / 2;
+                const int mstep = (j < half) ? (half - 1 - j) : (j - half);            // 0 = closest to e_prev
+                const double off = 2.4e-13 * exp2((double)mstep * (EPL == 1 ? 3.0 : 1.5));
+                E[e] = fmin(fmax((j < half) ? e_prev - off : e_prev + off, lo), hi);
+            }
+        }
+        FastOut<EPL> o;
+        fast_sweep<EPL>(g, atab, nll1, E, sbuf + warp * 64, o);
         if (__any_sync(full, o.bad)) {
             // a non-positive 1 - f/12 inside the sweep (grid far too coarse for this energy): generic path
-            const LaneOut s = sweep_lane(g, atab, ob.l, E, ob.want);
-            cfull = s.count_full; off = s.d_first < 0.; o.y0_log2 = s.y0_log2;
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) {
+                const LaneOut s = sweep_lane(g, atab, ob.l, E[e], ob.want);
+                o.cfull[e] = s.count_full; o.d_first[e] = s.d_first; o.y0_log2[e] = s.y0_log2;
+            }
         }
         steps += o.steps;
-        const unsigned m_hi = __ballot_sync(full, cfull > ob.want + off);
-        int lo_i, hi_i, lm;
-        virtual_bisect(m_hi, 32, lo_i, hi_i, lm);
-        const double e_lo = __shfl_sync(full, E, max(lo_i, 0)), e_hi = __shfl_sync(full, E, min(hi_i, 31));
-        ylog = __shfl_sync(full, o.y0_log2, lm);
-        if (lo_i >= 0) lo = e_lo;
-        if (hi_i < 32) hi = e_hi;
+        unsigned m_hi[EPL];
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) m_hi[e] = __ballot_sync(full, o.cfull[e] > ob.want + (o.d_first[e] < 0. ? 1 : 0));
+        // virtual bisection over the K sampled points (what a bisection restricted to them would do)
+        int lo_i = -1, hi_i = K, lm = -1;
+        while (hi_i - lo_i > 1) {
+            const int mid = (lo_i + hi_i) >> 1;
+            lm = mid;
+            bool high = false;
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) if ((mid >> 5) == e) high = (m_hi[e] >> (mid & 31)) & 1u;
+            if (high) hi_i = mid; else lo_i = mid;
+        }
+        double e_lo = lo, e_hi = hi, yl = 0.;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+            const double a_lo = __shfl_sync(full, E[e], max(lo_i, 0) & 31), a_hi = __shfl_sync(full, E[e], min(hi_i, K - 1) & 31);
+            const double a_y = __shfl_sync(full, o.y0_log2[e], lm & 31);
+            if (lo_i >= 0 && (lo_i >> 5) == e) e_lo = a_lo;
+            if (hi_i < K && (hi_i >> 5) == e) e_hi = a_hi;
+            if ((lm >> 5) == e) yl = a_y;
+        }
+        lo = e_lo; hi = e_hi; ylog = yl;
     }
     if (lane == 0) {
         SearchState s = ss[k];
@@ -189,6 +298,7 @@ __global__ void __launch_bounds__(128) search_fused_kernel(GridDev g, const doub
         s.y0_log2 = ylog;
         s.converged = (hi - lo < kEnergyTol) && (ylog < 49.828921423310435); // DFTAtom.cpp:528
         s.stage = 3;
+        s.pad = 1;                                                           // E is a valid warm start for the next step
         ss[k] = s;
     }
     if (work) {
@@ -199,9 +309,10 @@ __global__ void __launch_bounds__(128) search_fused_kernel(GridDev g, const doub
 }
 
 void launch_search_fused(const GridDev& g, const double* atab, const AtomDev* atoms, const OrbitalDev* orbs, const AtomState* astate,
-                         SearchState* ss, int n_orbs, unsigned long long* work, cudaStream_t st)
+                         SearchState* ss, int n_orbs, unsigned long long* work, int epl, int warm_start, cudaStream_t st)
 {
-    search_fused_kernel<<<(n_orbs + 3) / 4, 128, 0, st>>>(g, atab, atoms, orbs, astate, ss, n_orbs, work);
+    if (epl == 2) search_fused_kernel<2><<<(n_orbs + 3) / 4, 128, 0, st>>>(g, atab, atoms, orbs, astate, ss, n_orbs, work, warm_start);
+    else search_fused_kernel<1><<<(n_orbs + 3) / 4, 128, 0, st>>>(g, atab, atoms, orbs, astate, ss, n_orbs, work, warm_start);
 }
 
 }  // namespace dft

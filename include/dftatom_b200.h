@@ -94,6 +94,9 @@ const char* dftatom_version(void);
  *                   carries the ~1e-9 rounding-floor bias of plain FP64 multigrid (worth ~1e-5 Ha in Etotal at Z~90),
  *                   so parity with the reference requires it to stay off.
  *   "vcycle_floor_stop" (default 0) 1 = stop as soon as the update norm stagnates (data dependent)
+ *   "warm_start"   (default 1) from the second SCF step on, the first search round samples a geometric ladder of trial
+ *                   energies around the previous step's eigenvalue (same root: the predicate is monotone); 0 = every
+ *                   step searches [-Z^2-1, 50] from scratch like the reference
  *   "match_mode"   (default 0) 0 = segmented two-sided solve (production); 1 = serial reference-arithmetic kernel
  *   "r_segments"   (0 = auto) parallel-in-r split of the Numerov sweeps
  *   "search_mode"  (default 0) 0 = fused single-predicate multisection (production); 1 = reference-shaped three-stage
