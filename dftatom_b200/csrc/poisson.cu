@@ -191,8 +191,19 @@ __device__ __noinline__ void visit_regs(double* __restrict__ phi_g, const double
         }
         if (lane == 31) { sm.scanA[w] = sA; sm.scanP[w] = sP; }
         __syncthreads();
-        double carry = 0.;
-        for (int q = 0; q < w; ++q) carry = fma(sm.scanA[q], carry, sm.scanP[q]);
+        // carry into this warp = composition of the total maps of the warps before it, applied to 0: every warp scans
+        // the (<= 32) warp totals itself with shuffles (no second barrier, no serial chain)
+        double carry;
+        {
+            double wa = lane < nw ? sm.scanA[lane] : 1., wp = lane < nw ? sm.scanP[lane] : 0.;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double pa = __shfl_up_sync(full, wa, o), pp = __shfl_up_sync(full, wp, o);
+                if (lane >= o) { wp = fma(wa, pp, wp); wa *= pa; }
+            }
+            carry = __shfl_sync(full, wp, (w + 31) & 31);       // inclusive prefix of warp w-1 (map applied to 0 = its P)
+            if (w == 0) carry = 0.;
+        }
         double eA = __shfl_up_sync(full, sA, 1), eP = __shfl_up_sync(full, sP, 1);
         if (lane == 0) { eA = 1.; eP = 0.; }
         const double cin = fma(eA, carry, eP);                    // new value of node i0-1

@@ -129,3 +129,25 @@ def test_sweep_c3_final_records(ctx):
     # the slow convergers (Cu, Zn, Er, Tm, Yb ...) stop at a noise-driven step in the reference itself; all others must stop
     n_fin = sum(r.finished for r in res)
     assert n_fin >= 84, n_fin
+
+
+def test_radon_c2_every_step(ctx):
+    """C2: Rn, LSDA, 17 levels (131073 nodes), delta 1e-4, mixing 0.5, Rmax 50: every step vs the unmodified reference.
+    The finest three Poisson levels exceed the register-resident size and take the streaming sweep."""
+    a = golden("radon")["atoms"][0]
+    res = ctx.solve_batch([_opt(a["options"])])[0]
+    _check_against_golden(res, a)
+    # README.md:32-47 (the published run used "LSD"; LSDA gives "basically the same", README.md:58)
+    readme = [-3204.756288, -546.577961, -527.533025, -133.369145, -124.172863, -106.945007, -31.230804, -27.108985,
+              -19.449995, -8.953318, -5.889683, -4.408703, -1.911330, -0.626571, -0.293180]
+    np.testing.assert_allclose(res.steps[-1].E[0], readme, rtol=0, atol=2e-6)
+    assert abs(res.Etotal - -21861.346900) < 2e-5
+
+
+def test_lsda_batch_c4(ctx):
+    """C4: spin-polarised open-shell batch, Z = 21-30 and 57-71, LSDA, 16 levels (65537 nodes), delta 2e-4, Rmax 50."""
+    atoms = golden("lsda_batch")["atoms"]
+    res = ctx.solve_batch([_opt(a["options"]) for a in atoms])
+    for r, a in zip(res, atoms):
+        _check_against_golden(r, a)
+    assert sum(r.finished for r in res) >= 19          # reference: 22 of 25 (Z = 29, 69, 70 hit the 150-step cap)
