@@ -1,7 +1,7 @@
 // Internal declarations shared by the CUDA translation units of libdftatom_b200.so.
 // Data layout in HBM (all FP64, contiguous, index = radial node i, N = 2^L + 1):
 //   grid tables  (one set per batch, shared by all atoms):  r, ex=e^{δi}, sqex=e^{δi/2}, b12, c6, k2, simpson-weighted jacobians
-//   per (atom,spin): rho[N], atab[N] (Numerov table a_i built from the potential), vpot[N]
+//   per (atom,spin): rho[N], atab[N] (a_i = (2 K_i V_i + δ²/4)/12, the potential part of f_i/12), vpot[N]
 //   per atom:        rhot[N] (total density; aliases rho of spin 0 for LDA), Poisson hierarchy phi/src (2N-ish each)
 //   per orbital:     psi[N], search state
 #pragma once

@@ -208,12 +208,13 @@ __global__ void match_kernel(GridDev g, const double* __restrict__ atab_all, con
     const double E = s.E;
     const double* atab = atab_all + (size_t)ob.tab * g.N;
     double* psi = psi_all + (size_t)k * g.N;
-    const double nll1 = -(double)(ob.l * (ob.l + 1));
+    const double ll1 = (double)(ob.l * (ob.l + 1));
     const double kappa = sqrt(2. * fabs(E));
     const int start = start_index(g, kappa);
     const int n_steps = g.N - 1;
 
-    auto dval = [&](int i) { return fma(E, __ldg(g.c6 + i), fma(nll1, __ldg(g.b12 + i), __ldg(atab + i))); };
+    double f12 = 0.;      // f_i of the node last evaluated by dval
+    auto dval = [&](int i) { const double gq = fma(-E, __ldg(g.c6 + i), fma(ll1, __ldg(g.b12 + i), __ldg(atab + i))); f12 = 12. * gq; return 1. - gq; };
 
     for (int i = start + 1; i <= n_steps; ++i) psi[i] = 0.;
     double y = far_value(g, kappa, start);
@@ -224,14 +225,14 @@ __global__ void match_kernel(GridDev g, const double* __restrict__ atab_all, con
     psi[start - 1] = y;
     d = dval(start - 1);
     double w = d * y;
-    double f = 12. - 12. * d;
+    double f = f12;
     double ynext = y;
     int match = 2;
     for (int i = start - 2; i > 0; --i) {
         const double wn = 2. * w - wprev + y * f;
         wprev = w; w = wn;
         d = dval(i);
-        f = 12. - 12. * d;
+        f = f12;
         ynext = y;
         y = w / d;
         psi[i] = y;
@@ -243,13 +244,13 @@ __global__ void match_kernel(GridDev g, const double* __restrict__ atab_all, con
     y = pow(__ldg(g.r + 1), (double)ob.l + 1.) * exp(-0.5 * g.delta);     // Numerov.h:110-116
     psi[1] = y;
     d = dval(1);
-    f = 12. - 12. * d;
+    f = f12;
     w = d * y; wprev = 0.;
     for (int i = 2; i < match; ++i) {
         const double wn = 2. * w - wprev + y * f;
         wprev = w; w = wn;
         d = dval(i);
-        f = 12. - 12. * d;
+        f = f12;
         y = w / d;
         psi[i] = y;
     }
@@ -274,8 +275,8 @@ __global__ void build_atab_kernel(GridDev g, const double* __restrict__ vpot, do
     const double q = g.delta * g.delta * 0.25;
     for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
         const int i = (int)(t % g.N);
-        // a_i = 1 - (2 K_i V_i + δ²/4) / 12     (Numerov.h:96-101 with l = 0, E = 0)
-        atab[t] = 1. - (g.k2[i] * vpot[t] + q) * (1. / 12.);
+        // a_i = (2 K_i V_i + δ²/4) / 12 = f_i/12 at l = 0, E = 0 (Numerov.h:96-101), kept at full relative precision
+        atab[t] = (g.k2[i] * vpot[t] + q) * (1. / 12.);
     }
 }
 

@@ -38,7 +38,7 @@ static __device__ __noinline__ LaneOut sweep_lane(const GridDev& g, const double
 #pragma unroll
     for (int o = 16; o; o >>= 1) imax = max(imax, __shfl_xor_sync(0xffffffffu, imax, o));
 
-    const double nll1 = -(double)(l * (l + 1));
+    const double ll1 = (double)(l * (l + 1));
     const double thr = 1. - g.delta * g.delta * (1. / 48.);   // d_i >= thr  <=>  Veff_i <= E  (Numerov.h:336-337)
 
     double W1 = 0., W2 = 0.;      // W_{i+1}, W_{i+2}
@@ -51,7 +51,8 @@ static __device__ __noinline__ LaneOut sweep_lane(const GridDev& g, const double
 
     for (int i = imax; i >= 1; --i) {
         const double a = __ldg(atab + i), b = __ldg(g.b12 + i), c = __ldg(g.c6 + i);
-        const double d = fma(E, c, fma(nll1, b, a));
+        const double gq = fma(-E, c, fma(ll1, b, a));          // f_i / 12
+        const double d = 1. - gq;
         if (i > start) continue;
         P *= d1;                                       // P = P_i = prod_{j>i} d_j  (d1 = 1 at i = start)
         double W;

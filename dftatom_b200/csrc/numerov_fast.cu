@@ -40,8 +40,17 @@ template <int EPL> struct FastOut {
 
 // warp-collective; sbuf = this warp's double-buffered tile staging area [2][32].
 // Every lane carries EPL independent trial energies (EPL chains of the recurrence interleave in the pipeline).
+//
+// Difference form.  With g_i = f_i/12 (small: ~1e-9..1e-6 on the fine grids), d_i = 1 - g_i and
+//   s_i = 1 - d_i d_{i+1} = g_i + g_{i+1} - g_i g_{i+1},
+// the scaled recurrence W_{i-1} = (12 - 10 d_i) W_i - d_i d_{i+1} W_{i+1} is evaluated as
+//   D_i = D_{i+1} + 10 g_i W_i + s_i W_{i+1},   W_{i-1} = W_i + D_i        (D_i = W_{i-1} - W_i).
+// Forming 12 - 10 d_i or d_i d_{i+1} as numbers near 1..2 would round the physics (g ~ 1e-8) to 1e-16 absolute, i.e.
+// perturb the local potential by ~1e-8 relative at every node - measured as 2e-6 Ha on the Rn 1s level at 131073
+// nodes; in the difference form every coefficient keeps full relative precision, like the reference's
+// w_next = 2w - w_prev + y f (Numerov.h:311).
 template <int EPL>
-__device__ __forceinline__ void fast_sweep(const GridDev& g, const double* __restrict__ atab, double nll1, const double (&E)[EPL],
+__device__ __forceinline__ void fast_sweep(const GridDev& g, const double* __restrict__ atab, double ll1, const double (&E)[EPL],
                                            double2* sbuf, FastOut<EPL>& out)
 {
     const unsigned full = 0xffffffffu;
@@ -59,11 +68,12 @@ __device__ __forceinline__ void fast_sweep(const GridDev& g, const double* __res
     for (int o = 16; o; o >>= 1) imax = max(imax, __shfl_xor_sync(full, imax, o));
     const int nmax = g.N - 1;
 
-    double W1[EPL], W2[EPL], d1[EPL], dd1[EPL], n1[EPL], P[EPL];
+    // W1 = W_{i+1}, W2 = W_{i+2}, D = W_{i+1} - W_{i+2}, g1 = g_{i+1}, s1 = s_{i+1}, t1 = 10 g_{i+1}, P = prod d
+    double W1[EPL], W2[EPL], D[EPL], g1[EPL], s1[EPL], t1[EPL], P[EPL];
     unsigned prev[EPL];
     int count[EPL], bad = 0;
 #pragma unroll
-    for (int e = 0; e < EPL; ++e) { W1[e] = 0.; W2[e] = 0.; d1[e] = 1.; dd1[e] = 1.; n1[e] = 2.; P[e] = 1.; prev[e] = 0; count[e] = 0; }
+    for (int e = 0; e < EPL; ++e) { W1[e] = 0.; W2[e] = 0.; D[e] = 0.; g1[e] = 0.; s1[e] = 0.; t1[e] = 0.; P[e] = 1.; prev[e] = 0; count[e] = 0; }
 
     int m = imax >> 5;
     // prefetch the top tile: lane j holds node 32 m + 31 - j
@@ -74,7 +84,7 @@ __device__ __forceinline__ void fast_sweep(const GridDev& g, const double* __res
     }
     int cur = 0;
     for (; m >= 0; --m) {
-        sbuf[cur * 32 + lane] = make_double2(fma(nll1, pb, pa), pc);
+        sbuf[cur * 32 + lane] = make_double2(fma(ll1, pb, pa), pc);      // (g_i at E = 0, dg_i/d(-E))
         __syncwarp();
         if (m > 0) {
             const int i = ((m - 1) << 5) + 31 - lane;
@@ -87,51 +97,41 @@ __device__ __forceinline__ void fast_sweep(const GridDev& g, const double* __res
         const double2* tile = sbuf + cur * 32;
         if (m > 0 && __all_sync(full, uniform)) {
             // ---- fast tile: every chain is either fully inside its sweep or has not started yet (W stays 0) ----
-            // Four quarters of 8 nodes.  Phase A (no loop-carried dependence): d, n = 12 - 10 d, dd = d_k d_{k-1} of the
-            // quarter.  Phase B: the W chain, one dependent DFMA per node.
+            // Four quarters of 8 nodes.  Phase A (no loop-carried dependence): g, s, 10 g of the quarter.
+            // Phase B: the (D, W) chain, two dependent FP64 operations per node.
             unsigned sb[EPL];
 #pragma unroll
             for (int e = 0; e < EPL; ++e) sb[e] = 0;
-            // Four quarters of 8 nodes.  The 8 staged table entries of quarter q+1 are fetched (8 LDS.128 into distinct
-            // registers) before quarter q is computed, so the shared-memory latency never sits on the dependency chain.
-            // Phase A (no loop-carried dependence): d, n = 12 - 10 d, dd = d_k d_{k-1}.  Phase B: the W chain.
-            double2 tq[2][8];
-            const unsigned taddr = (unsigned)__cvta_generic_to_shared(tile);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) tq[0][k] = lds_f64x2(taddr + 16u * k);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const int cb = q & 1, nb = cb ^ 1;
-                if (q < 3) {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) tq[nb][k] = lds_f64x2(taddr + 16u * ((q + 1) * 8 + k));
-                }
-                double nq[EPL][8], dq[EPL][8];
+                double sq[EPL][8], tq[EPL][8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
+                    const double2 t = tile[q * 8 + k];
 #pragma unroll
                     for (int e = 0; e < EPL; ++e) {
-                        const double d = fma(E[e], tq[cb][k].y, tq[cb][k].x);
-                        dq[e][k] = d * d1[e];
-                        nq[e][k] = fma(-10., d, 12.);
-                        d1[e] = d;
+                        const double gk = fma(-E[e], t.y, t.x);
+                        sq[e][k] = fma(-gk, g1[e], gk + g1[e]);
+                        tq[e][k] = 10. * gk;
+                        g1[e] = gk;
                     }
                 }
 #pragma unroll
-                for (int e = 0; e < EPL; ++e)      // even node index <=> odd k: pairs (i, i+1) of the running product of d
-                    P[e] *= (dq[e][1] * dq[e][3]) * (dq[e][5] * dq[e][7]);
+                for (int e = 0; e < EPL; ++e)      // even node index <=> odd k: d_i d_{i+1} = 1 - s_i of the pairs (i, i+1)
+                    P[e] *= ((1. - sq[e][1]) * (1. - sq[e][3])) * ((1. - sq[e][5]) * (1. - sq[e][7]));
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
 #pragma unroll
                     for (int e = 0; e < EPL; ++e) {
-                        const double nu = k ? nq[e][k - 1] : n1[e], du = k ? dq[e][k - 1] : dd1[e];
-                        const double W = fma(nu, W1[e], -(du * W2[e]));
+                        const double tu = k ? tq[e][k - 1] : t1[e], su = k ? sq[e][k - 1] : s1[e];
+                        const double Dn = fma(tu, W1[e], fma(su, W2[e], D[e]));
+                        const double W = W1[e] + Dn;
                         sb[e] = __funnelshift_l((unsigned)hi32(W), sb[e], 1);
-                        W2[e] = W1[e]; W1[e] = W;
+                        W2[e] = W1[e]; W1[e] = W; D[e] = Dn;
                     }
                 }
 #pragma unroll
-                for (int e = 0; e < EPL; ++e) { n1[e] = nq[e][7]; dd1[e] = dq[e][7]; }
+                for (int e = 0; e < EPL; ++e) { t1[e] = tq[e][7]; s1[e] = sq[e][7]; }
             }
 #pragma unroll
             for (int e = 0; e < EPL; ++e) {
@@ -147,28 +147,33 @@ __device__ __forceinline__ void fast_sweep(const GridDev& g, const double* __res
                 const double2 t = tile[k];
 #pragma unroll
                 for (int e = 0; e < EPL; ++e) {
-                    const double d = fma(E[e], t.y, t.x);
+                    const double gk = fma(-E[e], t.y, t.x);
+                    const double d = 1. - gk;
                     if (i <= start[e]) {
-                        double W, dd;
+                        double W, s, Dnew;
                         if (i == start[e]) {                      // w_start = d_start far(start)   (Numerov.h:294-298)
                             W = d * far_value(g, kappa[e], i);
-                            dd = d; P[e] = 1.; count[e] = 0; prev[e] = 0;
+                            s = gk;                               // d_{start+1} := 1
+                            P[e] = 1.; count[e] = 0; prev[e] = 0;
+                            Dnew = 0.;                            // overwritten at the next node
                             bad |= !(d > 0.);
-                        } else if (i == start[e] - 1) {           // w_{start-1}                    (Numerov.h:300-303)
-                            W = d * far_value(g, kappa[e], i) * d1[e];
-                            dd = d * d1[e];
+                        } else if (i == start[e] - 1) {           // w_{start-1} d_start            (Numerov.h:300-303)
+                            W = d * far_value(g, kappa[e], i) * (1. - g1[e]);
+                            s = fma(-gk, g1[e], gk + g1[e]);
+                            Dnew = W - W1[e];                     // D_start = W_{start-1} - W_start
                             bad |= !(d > 0.);
                         } else {
-                            W = fma(n1[e], W1[e], -(dd1[e] * W2[e]));
-                            dd = d * d1[e];
+                            Dnew = fma(t1[e], W1[e], fma(s1[e], W2[e], D[e]));
+                            W = W1[e] + Dnew;
+                            s = fma(-gk, g1[e], gk + g1[e]);
                             const unsigned sy = ((unsigned)hi32(W) ^ (unsigned)hi32(d)) >> 31;    // y_i = W_i / (P_i d_i), P_i > 0
                             count[e] += (sy != prev[e]);
                             prev[e] = sy;
                             if (i == 2) bad |= !(d > 0.);
                         }
-                        if (!(i & 1)) P[e] *= dd;
-                        n1[e] = fma(-10., d, 12.);
-                        W2[e] = W1[e]; W1[e] = W; d1[e] = d; dd1[e] = dd;
+                        if (!(i & 1)) P[e] *= (1. - s);
+                        D[e] = Dnew;
+                        W2[e] = W1[e]; W1[e] = W; g1[e] = gk; s1[e] = s; t1[e] = 10. * gk;
                     }
                 }
             }
@@ -179,14 +184,15 @@ __device__ __forceinline__ void fast_sweep(const GridDev& g, const double* __res
     out.steps = 0;
 #pragma unroll
     for (int e = 0; e < EPL; ++e) {
-        // W1 = W_1, W2 = W_2, d1 = d_1, P = prod_{j=2..start} d_j;  y_0 = y_1 (2 + f_1) - y_2  (Numerov.h:398)
-        const double Y0s = W1[e] * fma(-12., d1[e], 14.) / d1[e] - W2[e];
+        // W1 = W_1, W2 = W_2, g1 = g_1, P = prod_{j=2..start} d_j;  y_0 = y_1 (2 + f_1) - y_2  (Numerov.h:398)
+        const double d1 = 1. - g1[e];
+        const double Y0s = W1[e] * fma(12., g1[e], 2.) / d1 - W2[e];
         out.y0_pos[e] = Y0s > 0.;
         out.y0_log2[e] = (fabs(Y0s) <= 1.7e308) ? log2(fabs(Y0s)) - log2(fabs(P[e])) : INFINITY;
         out.cfull[e] = count[e] + (((out.y0_pos[e] ? 0u : 1u) != prev[e]) ? 1 : 0);
         out.bad |= !(P[e] > 0.);
         out.steps += start[e] - 1;
-        out.d_first[e] = d1[e];
+        out.d_first[e] = d1;
     }
 }
 
@@ -203,7 +209,7 @@ __global__ void __launch_bounds__(128) numerov_lanes_fast_kernel(GridDev g, Nume
     const int l = a.l[kk];
     FastOut<1> o;
     const double E1[1] = { a.E[kk] };
-    fast_sweep<1>(g, a.atab + (size_t)a.tab[kk] * g.N, -(double)(l * (l + 1)), E1, sbuf + warp * 64, o);
+    fast_sweep<1>(g, a.atab + (size_t)a.tab[kk] * g.N, (double)(l * (l + 1)), E1, sbuf + warp * 64, o);
     if (k < a.n_lanes) {
         if (a.y0_sign) a.y0_sign[k] = o.y0_pos[0];
         if (a.y0_log2) a.y0_log2[k] = o.y0_log2[0];
@@ -233,7 +239,7 @@ __global__ void __launch_bounds__(128, 1) search_fused_kernel(GridDev g, const d
     const OrbitalDev ob = orbs[k];
     if (astate[ob.atom].done) return;
     const double* atab = atab_all + (size_t)ob.tab * g.N;
-    const double nll1 = -(double)(ob.l * (ob.l + 1));
+    const double ll1 = (double)(ob.l * (ob.l + 1));
     const double Z = (double)atoms[ob.atom].Z;
     double lo = -Z * Z - 1., hi = kTopEnergy;             // DFTAtom.cpp:407,499
     double ylog = 0.;
@@ -258,7 +264,7 @@ __global__ void __launch_bounds__(128, 1) search_fused_kernel(GridDev g, const d
             }
         }
         FastOut<EPL> o;
-        fast_sweep<EPL>(g, atab, nll1, E, sbuf + warp * 64, o);
+        fast_sweep<EPL>(g, atab, ll1, E, sbuf + warp * 64, o);
         if (__any_sync(full, o.bad)) {
             // a non-positive 1 - f/12 inside the sweep (grid far too coarse for this energy): generic path
 #pragma unroll

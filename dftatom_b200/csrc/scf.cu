@@ -300,10 +300,10 @@ __global__ void __launch_bounds__(kAT) potential_energy_kernel(GridDev g, Poisso
             e[4] += pot;
         }
         b.vpot[(size_t)ta * N + i] = Va;
-        b.atab[(size_t)ta * N + i] = 1. - (g.k2[i] * Va + q) * (1. / 12.);
+        b.atab[(size_t)ta * N + i] = (g.k2[i] * Va + q) * (1. / 12.);
         if (at.n_spin == 2) {
             b.vpot[(size_t)tb * N + i] = Vb;
-            b.atab[(size_t)tb * N + i] = 1. - (g.k2[i] * Vb + q) * (1. / 12.);
+            b.atab[(size_t)tb * N + i] = (g.k2[i] * Vb + q) * (1. / 12.);
         }
     }
     if (first) return;

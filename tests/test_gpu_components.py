@@ -70,7 +70,7 @@ def test_level_search_matches_oracle(ctx, kind, L, delta, rmax, Z):
         ctx.set_option("search_mode", mode)
         E_g, ok_g = ctx.level_search(V, L, delta, rmax, Z, ns, ls)
         ctx.set_option("search_mode", 0)
-        np.testing.assert_allclose(E_g, E_o, rtol=0, atol=1e-9)
+        np.testing.assert_allclose(E_g, E_o, rtol=0, atol=5e-9)
         assert ok_g.tolist() == ok_o.tolist()
     if kind == "coulomb":
         np.testing.assert_allclose(E_g, [-Z * Z / (2.0 * n * n) for n in ns], atol=5e-5)
