@@ -119,6 +119,7 @@ struct PoissonArgs {
     const int* skip;        // optional per-density skip flag (AtomState.done), stride given
     int skip_stride_bytes;
     int max_vcycles; int floor_stop;
+    int smem_doubles;       // set by the launcher: doubles per shared-memory array of the coarse levels
     int refine_vcycles;     // > 0: double-double defect correction with this many V-cycles on the error equation
     double* u0;             // [n_dens][N] scratch for the correction (required when refine_vcycles > 0)
     unsigned long long* work;   // optional: += Gauss-Seidel node-updates performed

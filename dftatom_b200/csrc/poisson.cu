@@ -46,7 +46,7 @@ struct PoissonSmem {
     double carry;        // last new value of the previous pass
     double bcast;
     unsigned long long updates;   // Gauss-Seidel node-updates performed by this CTA (work counter)
-    int pending;
+    int soff[24];                 // offsets of the shared-memory-resident levels inside the dynamic smem arrays
 };
 
 __device__ __forceinline__ double block_sum(double v, PoissonSmem& sm)
@@ -146,21 +146,24 @@ __device__ __noinline__ double gs_sweep(double* __restrict__ phi, const double* 
 // ---------------------------------------------------------------------------------------------------------
 template <int NPT, bool SRC_REGS>
 __device__ __noinline__ void visit_regs(double* __restrict__ phi_g, const double* __restrict__ src_g, int size, double d, int sweeps,
-                                           PoissonSmem& sm)
+                                           int pad, PoissonSmem& sm)
 {
+    // pad = 1: the level lives in shared memory with one padding slot per thread chunk (chunk stride NPT + 1 doubles is odd,
+    // so the 32 lanes of a warp hit 32 different bank pairs); pad = 0: plain layout in global memory
     const unsigned full = 0xffffffffu;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5, nw = blockDim.x >> 5;
     const int n = size - 1;
     const int i0 = t * NPT;
+    const int p0 = t * (NPT + pad);
     const bool active = i0 < n;
     const double a = 0.5 * (1. + 0.5 * d), bcoef = 0.5 * (1. - 0.5 * d);
-    const double right_bc = phi_g[n];
+    const double right_bc = phi_g[n + (pad ? n / NPT : 0)];
     double phi[NPT], src[SRC_REGS ? NPT : 1];
-    const double* __restrict__ sp = src_g + (active ? i0 : 0);      // Source is read-only during the visit
+    const double* __restrict__ sp = src_g + (active ? p0 : 0);      // Source is read-only during the visit
 #pragma unroll
     for (int k = 0; k < NPT; ++k) {
-        phi[k] = active ? phi_g[i0 + k] : 0.;
-        if (SRC_REGS) src[k] = active ? 0.5 * src_g[i0 + k] : 0.;
+        phi[k] = active ? phi_g[p0 + k] : 0.;
+        if (SRC_REGS) src[k] = active ? 0.5 * src_g[p0 + k] : 0.;
     }
     double aN = a;
 #pragma unroll
@@ -179,7 +182,7 @@ __device__ __noinline__ void visit_regs(double* __restrict__ phi_g, const double
 #pragma unroll
         for (int k = 0; k < NPT; ++k) {
             const double nxt = (k + 1 < NPT) ? phi[k + 1] : nb;
-            const double c = fma(bcoef, nxt, SRC_REGS ? src[k] : 0.5 * __ldg(sp + k));
+            const double c = fma(bcoef, nxt, SRC_REGS ? src[k] : 0.5 * sp[k]);
             x = (t == 0 && k == 0) ? phi[0] : fma(a, x, c);      // node 0 keeps its boundary value
             phi[k] = x;
         }
@@ -213,7 +216,7 @@ __device__ __noinline__ void visit_regs(double* __restrict__ phi_g, const double
     }
     if (active) {
 #pragma unroll
-        for (int k = 0; k < NPT; ++k) phi_g[i0 + k] = phi[k];
+        for (int k = 0; k < NPT; ++k) phi_g[p0 + k] = phi[k];
     }
     __syncthreads();
 }
@@ -245,33 +248,43 @@ __device__ __noinline__ void visit_warp(double* __restrict__ phi_g, const double
     __syncwarp();
 }
 
-__device__ __forceinline__ void restrict_nodes(const double* __restrict__ pf, const double* __restrict__ sf, double* __restrict__ pc,
-                                               double* __restrict__ sc, int nc, double dc, int tid, int nthr)
+// physical slot of node i of a level whose chunks of 2^sh nodes carry one padding slot (sh = 31: no padding)
+__device__ __forceinline__ int slot(int i, int sh) { return i + (i >> sh); }
+
+__device__ __forceinline__ void restrict_nodes(const double* pf, const double* sf, int shf, double* pc, double* sc, int shc, int nc,
+                                               double dc, int tid, int nthr)
 {   // Restrict, PoissonSolver.cpp:126-157
     for (int i = tid; i < nc; i += nthr) {
-        pc[i] = 0.;
         double v = 0.;
         if (i > 0 && i < nc - 1) {
             const int k = 2 * i;
-            const double lft = pf[k - 1], mid = pf[k], rgt = pf[k + 1];
-            v = 4. * (sf[k] + lft - 2. * mid + rgt) - dc * (rgt - lft);
+            const double lft = pf[slot(k - 1, shf)], mid = pf[slot(k, shf)], rgt = pf[slot(k + 1, shf)];
+            v = 4. * (sf[slot(k, shf)] + lft - 2. * mid + rgt) - dc * (rgt - lft);
         }
-        sc[i] = v;
+        pc[slot(i, shc)] = 0.;
+        sc[slot(i, shc)] = v;
     }
 }
 
-__device__ __forceinline__ void prolong_nodes(const double* __restrict__ pc, double* __restrict__ pf, int nc, int tid, int nthr)
+__device__ __forceinline__ void prolong_nodes(const double* pc, int shc, double* pf, int shf, int nc, int tid, int nthr)
 {   // Prolong, PoissonSolver.cpp:110-123
     for (int i = tid; i < nc; i += nthr) {
-        const double c = pc[i];
-        pf[2 * i] += c;
-        if (i > 0) pf[2 * i - 1] += 0.5 * (pc[i - 1] + c);
+        const double c = pc[slot(i, shc)];
+        pf[slot(2 * i, shf)] += c;
+        if (i > 0) pf[slot(2 * i - 1, shf)] += 0.5 * (pc[slot(i - 1, shc)] + c);
     }
 }
 
 // One multigrid hierarchy of one density; every method is called by all threads of the CTA.
+// Levels with at most kSmemLevelNodes nodes live in (padded) shared memory, the finer ones in global memory (L2).
+constexpr int kSmemLevelNodes = 4096;
+
+__host__ __device__ inline int level_npt(int n) { return n > kPT ? n / kPT : 1; }          // nodes per thread of a level
+__host__ __device__ inline int level_slots(int n) { return n + 1 + (level_npt(n) > 1 ? n / level_npt(n) : 0); }
+
 struct Hierarchy {
-    double* phi; double* src;
+    double* phi; double* src;       // global arrays (all levels, plain layout)
+    double* sphi; double* ssrc;     // shared-memory arrays of the coarse levels (padded layout), may be null
     const PoissonLevels& lv;
     double delta;
     PoissonSmem& sm;
@@ -279,13 +292,21 @@ struct Hierarchy {
 
     __device__ __forceinline__ double dl(int l) const { return delta * (double)(1 << l); }
     __device__ __forceinline__ bool warp_level(int l) const { return lv.size[l] - 1 <= kWarpLevelNodes; }
+    __device__ __forceinline__ bool in_smem(int l) const { return sphi != nullptr && l >= 1 && lv.size[l] - 1 <= kSmemLevelNodes; }
+    __device__ __forceinline__ int shift(int l) const
+    {
+        const int npt = level_npt(lv.size[l] - 1);
+        return (in_smem(l) && npt > 1) ? 31 - __clz(npt) : 31;
+    }
+    __device__ __forceinline__ double* P(int l) const { return in_smem(l) ? sphi + sm.soff[l] : phi + lv.off[l]; }
+    __device__ __forceinline__ double* S(int l) const { return in_smem(l) ? ssrc + sm.soff[l] : src + lv.off[l]; }
     __device__ __forceinline__ void block_begin() { if (pending) { __syncthreads(); pending = false; } }
 
     // IterateGaussSeidel(l, ., sweeps) without the early exit
     __device__ __forceinline__ void smooth(int l, int sweeps)
     {
-        double* p = phi + lv.off[l];
-        const double* s = src + lv.off[l];
+        double* p = P(l);
+        const double* s = S(l);
         const int size = lv.size[l], n = size - 1;
         if (warp_level(l)) {
             if (threadIdx.x < 32) {
@@ -296,37 +317,50 @@ struct Hierarchy {
             return;
         }
         block_begin();
+        const int pad = (in_smem(l) && n > kPT) ? 1 : 0;
         if (n > kPT * kMaxNpt) { for (int k = 0; k < sweeps; ++k) gs_sweep(p, s, size, dl(l), sm); }
-        else if (n > kPT * 16) visit_regs<32, false>(p, s, size, dl(l), sweeps, sm);
-        else if (n > kPT * 8) visit_regs<16, true>(p, s, size, dl(l), sweeps, sm);
-        else if (n > kPT * 4) visit_regs<8, true>(p, s, size, dl(l), sweeps, sm);
-        else if (n > kPT * 2) visit_regs<4, true>(p, s, size, dl(l), sweeps, sm);
-        else if (n > kPT) visit_regs<2, true>(p, s, size, dl(l), sweeps, sm);
-        else visit_regs<1, true>(p, s, size, dl(l), sweeps, sm);
+        else if (n > kPT * 16) visit_regs<32, false>(p, s, size, dl(l), sweeps, pad, sm);
+        else if (n > kPT * 8) visit_regs<16, true>(p, s, size, dl(l), sweeps, pad, sm);
+        else if (n > kPT * 4) visit_regs<8, true>(p, s, size, dl(l), sweeps, pad, sm);
+        else if (n > kPT * 2) visit_regs<4, true>(p, s, size, dl(l), sweeps, pad, sm);
+        else if (n > kPT) visit_regs<2, true>(p, s, size, dl(l), sweeps, pad, sm);
+        else visit_regs<1, true>(p, s, size, dl(l), sweeps, 0, sm);
     }
     __device__ __forceinline__ void restrict_to(int l)       // level l-1 -> l
     {
         if (warp_level(l)) {                                  // <= 33 coarse nodes: warp 0 alone (level l-1 is complete: either
             if (threadIdx.x < 32) {                           //  a block op ended with a barrier or warp 0 wrote it itself)
-                restrict_nodes(phi + lv.off[l - 1], src + lv.off[l - 1], phi + lv.off[l], src + lv.off[l], lv.size[l], dl(l), threadIdx.x, 32);
+                restrict_nodes(P(l - 1), S(l - 1), shift(l - 1), P(l), S(l), shift(l), lv.size[l], dl(l), threadIdx.x, 32);
                 __syncwarp();
             }
             pending = true;
             return;
         }
         block_begin();
-        restrict_nodes(phi + lv.off[l - 1], src + lv.off[l - 1], phi + lv.off[l], src + lv.off[l], lv.size[l], dl(l), threadIdx.x, blockDim.x);
+        restrict_nodes(P(l - 1), S(l - 1), shift(l - 1), P(l), S(l), shift(l), lv.size[l], dl(l), threadIdx.x, blockDim.x);
         __syncthreads();
     }
     __device__ __forceinline__ void prolong_from(int l)      // level l -> l-1
     {
         if (warp_level(l - 1)) {
-            if (threadIdx.x < 32) { prolong_nodes(phi + lv.off[l], phi + lv.off[l - 1], lv.size[l], threadIdx.x, 32); __syncwarp(); }
+            if (threadIdx.x < 32) { prolong_nodes(P(l), shift(l), P(l - 1), shift(l - 1), lv.size[l], threadIdx.x, 32); __syncwarp(); }
             pending = true;
             return;
         }
         block_begin();
-        prolong_nodes(phi + lv.off[l], phi + lv.off[l - 1], lv.size[l], threadIdx.x, blockDim.x);
+        prolong_nodes(P(l), shift(l), P(l - 1), shift(l - 1), lv.size[l], threadIdx.x, blockDim.x);
+        __syncthreads();
+    }
+    // shared-memory offsets of the coarse levels (thread 0 fills sm.soff; returns doubles needed per array)
+    __device__ __forceinline__ void layout_smem()
+    {
+        if (threadIdx.x == 0) {
+            int off = 0;
+            for (int l = 0; l < lv.L; ++l) {
+                sm.soff[l] = off;
+                if (l >= 1 && lv.size[l] - 1 <= kSmemLevelNodes) off += (level_slots(lv.size[l] - 1) + 3) & ~3;
+            }
+        }
         __syncthreads();
     }
     __device__ __forceinline__ void to_coarse(int from, int to)      // "Ascend", PoissonSolver.cpp:162-171
@@ -345,7 +379,7 @@ struct Hierarchy {
         if (from >= 1) prolong_from(1);
         smooth(0, 2);
         block_begin();
-        return gs_sweep(phi, src, lv.size[0], dl(0), sm);
+        return gs_sweep(P(0), const_cast<const double*>(S(0)), lv.size[0], dl(0), sm);
     }
 };
 
@@ -384,12 +418,15 @@ __device__ __forceinline__ double dd_residual(double S, double um, double u0, do
 __global__ void __launch_bounds__(kPT) poisson_full_kernel(GridDev g, PoissonLevels lv, PoissonArgs a)
 {
     __shared__ PoissonSmem sm;
+    extern __shared__ double dyn_smem[];
     const int k = blockIdx.x;
     if (threadIdx.x == 0) sm.updates = 0;
     if (a.skip && *reinterpret_cast<const int*>(reinterpret_cast<const char*>(a.skip) + (size_t)k * a.skip_stride_bytes)) return;
     double* phi = a.phi + (size_t)k * lv.total;
     double* src = a.src + (size_t)k * lv.total;
     const int N = g.N, L = lv.L, c = L - 1;
+    Hierarchy h{ phi, src, a.smem_doubles ? dyn_smem : nullptr, a.smem_doubles ? dyn_smem + a.smem_doubles : nullptr, lv, g.delta, sm, false };
+    h.layout_smem();
 
     // Source_0 (PoissonSolver.h:55-74) and Initialize (PoissonSolver.cpp:80-106)
     if (a.rho) {
@@ -400,22 +437,21 @@ __global__ void __launch_bounds__(kPT) poisson_full_kernel(GridDev g, PoissonLev
     }
     __syncthreads();
     for (int l = 1; l < L; ++l) {
-        const double* sf = src + lv.off[l - 1];
-        double* sc = src + lv.off[l];
-        double* pc = phi + lv.off[l];
-        const int n = lv.size[l];
+        const double* sf = h.S(l - 1);
+        double* sc = h.S(l);
+        double* pc = h.P(l);
+        const int n = lv.size[l], shf = h.shift(l - 1), shc = h.shift(l);
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            sc[i] = (i > 0 && i < n - 1) ? 4. * sf[2 * i] : 0.;
-            pc[i] = 0.;
+            sc[slot(i, shc)] = (i > 0 && i < n - 1) ? 4. * sf[slot(2 * i, shf)] : 0.;
+            pc[slot(i, shc)] = 0.;
         }
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        phi[lv.off[c]] = 0.;                                          // SetBoundaries(0, Z), PoissonSolver.h:76
-        phi[lv.off[c] + lv.size[c] - 1] = a.Zbc ? (double)a.Zbc[k] : 0.;
+        h.P(c)[0] = 0.;                                               // SetBoundaries(0, Z), PoissonSolver.h:76
+        h.P(c)[lv.size[c] - 1] = a.Zbc ? (double)a.Zbc[k] : 0.;
     }
     __syncthreads();
-    Hierarchy h{ phi, src, lv, g.delta, sm, false };
     h.smooth(c, 2);        // the coarsest level has one interior node: the reference's <= 15 sweeps converge in one
 
     // FullCycle, PoissonSolver.h:89-124
@@ -469,9 +505,23 @@ __global__ void __launch_bounds__(kPT) poisson_full_kernel(GridDev g, PoissonLev
     }
 }
 
-void launch_poisson_full(const GridDev& g, const PoissonLevels& lv, const PoissonArgs& a, cudaStream_t st)
+// doubles per shared-memory array (phi or src) for the coarse levels of an L-level hierarchy
+static int smem_doubles_for(const PoissonLevels& lv)
 {
-    poisson_full_kernel<<<a.n_dens, kPT, 0, st>>>(g, lv, a);
+    int off = 0;
+    for (int l = 1; l < lv.L; ++l)
+        if (lv.size[l] - 1 <= kSmemLevelNodes) off += (level_slots(lv.size[l] - 1) + 3) & ~3;
+    return off;
+}
+
+void launch_poisson_full(const GridDev& g, const PoissonLevels& lv, const PoissonArgs& a_in, cudaStream_t st)
+{
+    PoissonArgs a = a_in;
+    a.smem_doubles = smem_doubles_for(lv);
+    const size_t bytes = (size_t)a.smem_doubles * 2 * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(poisson_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+    poisson_full_kernel<<<a.n_dens, kPT, bytes, st>>>(g, lv, a);
 }
 
 __global__ void __launch_bounds__(kPT) poisson_vcycles_kernel(double delta, PoissonLevels lv, double* phi_all, double* src_all,
@@ -483,7 +533,8 @@ __global__ void __launch_bounds__(kPT) poisson_vcycles_kernel(double delta, Pois
     double* phi = phi_all + (size_t)k * lv.total;
     double* src = src_all + (size_t)k * lv.total;
     const int c = lv.L - 1;
-    Hierarchy h{ phi, src, lv, delta, sm, false };
+    Hierarchy h{ phi, src, nullptr, nullptr, lv, delta, sm, false };      // microbench / parity entry point: all levels in global memory
+    h.layout_smem();
     double err = 0.;
     for (int it = 0; it < n_cycles; ++it) {
         h.to_coarse(0, c);
