@@ -50,6 +50,8 @@ struct dftatom_ctx {
     int max_vcycles = 8;
     int floor_stop = 0;
     int refine_vcycles = 0;
+    int warm_vcycles = 0;      // Poisson warm start from SCF step warm_after on (0 = off)
+    int warm_after = 3;
     int r_segments = 0;
     int profile = 0;
     int search_mode = 0;
@@ -58,7 +60,7 @@ struct dftatom_ctx {
     int warm_start = 1;
     dftatom_kernel_profile prof[DFTATOM_K_COUNT] = {};
     // reusable buffers
-    DevBuf atoms, astate, orbs, ss, rho, rhot, vpot, atab, psi, match_pt, phi, src, u0, zbc, tab_of, steps, n_active;
+    DevBuf atoms, astate, orbs, ss, rho, rhot, vpot, atab, psi, match_pt, phi, src, u0, ubuf, zbc, tab_of, steps, n_active;
     DevBuf scratch[8];
     int* h_active = nullptr;       // pinned
     // timing of the last solve
@@ -96,7 +98,7 @@ static int get_grid(dftatom_ctx* c, int L, double delta, double max_r, GridDev**
         inv4pr2[i] = i ? 1. / (kFourPi * r[i] * r[i]) : 0.;                  // DFTAtom.cpp:340
     }
     GridEntry& e = c->grids[key];
-    int rc = e.mem.ensure(h.size() * sizeof(double));
+    int rc = e.mem.ensure((h.size() + 32 * 32) * sizeof(double));
     if (rc) { c->grids.erase(key); return rc; }
     DFT_CHECK(cudaMemcpyAsync(e.mem.p, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     DFT_CHECK(cudaStreamSynchronize(c->stream));
@@ -105,6 +107,12 @@ static int get_grid(dftatom_ctx* c, int L, double delta, double max_r, GridDev**
     e.dev.r = d; e.dev.ex = d + (size_t)N; e.dev.sqex = d + (size_t)2 * N; e.dev.b12 = d + (size_t)3 * N;
     e.dev.c6 = d + (size_t)4 * N; e.dev.k2 = d + (size_t)5 * N; e.dev.wjac = d + (size_t)6 * N;
     e.dev.psrc = d + (size_t)7 * N; e.dev.inv4pr2 = d + (size_t)8 * N;
+    e.dev.coarse_op = nullptr;
+    if (L >= 6) {
+        e.dev.coarse_op = d + (size_t)9 * N;
+        launch_coarse_op(L, delta, e.dev.coarse_op, c->stream);
+        DFT_CHECK(cudaStreamSynchronize(c->stream));
+    }
     *out = &e.dev;
     return 0;
 }
@@ -160,7 +168,7 @@ void dftatom_destroy(dftatom_ctx* c)
     cudaStreamSynchronize(c->stream);
     for (auto& kv : c->grids) kv.second.mem.release();
     DevBuf* all[] = { &c->atoms, &c->astate, &c->orbs, &c->ss, &c->rho, &c->rhot, &c->vpot, &c->atab, &c->psi, &c->match_pt,
-                      &c->phi, &c->src, &c->u0, &c->zbc, &c->tab_of, &c->steps, &c->n_active };
+                      &c->phi, &c->src, &c->u0, &c->ubuf, &c->zbc, &c->tab_of, &c->steps, &c->n_active };
     for (DevBuf* b : all) b->release();
     for (DevBuf& b : c->scratch) b.release();
     if (c->h_active) cudaFreeHost(c->h_active);
@@ -175,6 +183,8 @@ int dftatom_set_option(dftatom_ctx* c, const char* key, double value)
     if (k == "max_vcycles") c->max_vcycles = std::max(1, (int)value);
     else if (k == "vcycle_floor_stop") c->floor_stop = value != 0.;
     else if (k == "refine_vcycles") c->refine_vcycles = std::max(0, (int)value);
+    else if (k == "warm_vcycles") c->warm_vcycles = std::max(0, (int)value);
+    else if (k == "warm_after") c->warm_after = std::max(0, (int)value);
     else if (k == "r_segments") c->r_segments = (int)value;
     else if (k == "profile") c->profile = value != 0.;
     else if (k == "search_mode") c->search_mode = (int)value;
@@ -308,6 +318,7 @@ int dftatom_solve_batch(dftatom_ctx* c, const dftatom_options* opts, int n_atoms
     if ((rc = c->phi.ensure(sizeof(double) * (size_t)n_atoms * lv.total))) return rc;
     if ((rc = c->src.ensure(sizeof(double) * (size_t)n_atoms * lv.total))) return rc;
     if ((rc = c->u0.ensure(sizeof(double) * (size_t)n_atoms * N))) return rc;
+    if ((rc = c->ubuf.ensure(sizeof(double) * (size_t)n_atoms * N))) return rc;
     if ((rc = c->steps.ensure(sizeof(dftatom_step) * (size_t)n_atoms * stride))) return rc;
     if ((rc = c->n_active.ensure(sizeof(int)))) return rc;
     DFT_CHECK(cudaMemsetAsync(c->steps.p, 0, sizeof(dftatom_step) * (size_t)n_atoms * stride, st));
@@ -319,11 +330,11 @@ int dftatom_solve_batch(dftatom_ctx* c, const dftatom_options* opts, int n_atoms
     b.atoms = c->atoms.as<AtomDev>(); b.astate = c->astate.as<AtomState>(); b.orbs = c->orbs.as<OrbitalDev>();
     b.ss = c->ss.as<SearchState>(); b.rho = c->rho.as<double>(); b.rhot = c->rhot.as<double>(); b.vpot = c->vpot.as<double>();
     b.atab = c->atab.as<double>(); b.psi = c->psi.as<double>(); b.match_pt = c->match_pt.as<int>();
-    b.phi = c->phi.as<double>(); b.src = c->src.as<double>(); b.Zbc = c->zbc.as<int>(); b.tab_of = c->tab_of.as<int>();
+    b.phi = c->phi.as<double>(); b.src = c->src.as<double>(); b.U = c->ubuf.as<double>(); b.Zbc = c->zbc.as<int>(); b.tab_of = c->tab_of.as<int>();
     b.steps = c->steps.as<dftatom_step>(); b.steps_stride = stride; b.n_active = c->n_active.as<int>();
 
     PoissonArgs pa{};
-    pa.n_dens = n_atoms; pa.rho = b.rhot; pa.Zbc = b.Zbc; pa.phi = b.phi; pa.src = b.src;
+    pa.n_dens = n_atoms; pa.rho = b.rhot; pa.Zbc = b.Zbc; pa.phi = b.phi; pa.src = b.src; pa.u_out = b.U; pa.coarse_op = g.coarse_op;
     pa.skip = &b.astate[0].done; pa.skip_stride_bytes = (int)sizeof(AtomState);
     pa.max_vcycles = c->max_vcycles; pa.floor_stop = c->floor_stop;
     pa.refine_vcycles = c->refine_vcycles; pa.u0 = c->u0.as<double>();
@@ -375,6 +386,7 @@ int dftatom_solve_batch(dftatom_ctx* c, const dftatom_options* opts, int n_atoms
         launch_density_update(g, b, st); ++launches;
         end_span();
         begin_span(DFTATOM_K_POISSON);
+        pa.warm_vcycles = (sp >= c->warm_after) ? c->warm_vcycles : 0;
         launch_poisson_full(g, lv, pa, st); ++launches;
         end_span();
         begin_span(DFTATOM_K_POTENTIAL);
@@ -583,10 +595,23 @@ int dftatom_poisson_solve(dftatom_ctx* c, int levels, double delta, double max_r
     PoissonArgs pa{};
     pa.n_dens = n_dens; pa.rho = dr.as<double>(); pa.Zbc = dz.as<int>(); pa.phi = c->phi.as<double>(); pa.src = c->src.as<double>();
     pa.max_vcycles = c->max_vcycles; pa.floor_stop = c->floor_stop; pa.vcycles_used = dv.as<int>();
-    if ((rc = c->u0.ensure(sizeof(double) * (size_t)n_dens * N))) return rc;
-    pa.refine_vcycles = c->refine_vcycles; pa.u0 = c->u0.as<double>();
+    if ((rc = c->u0.ensure(sizeof(double) * (size_t)n_dens * N)) || (rc = c->ubuf.ensure(sizeof(double) * (size_t)n_dens * N))) return rc;
+    pa.refine_vcycles = c->refine_vcycles; pa.u0 = c->u0.as<double>(); pa.u_out = c->ubuf.as<double>(); pa.coarse_op = g.coarse_op;
+    if (c->profile) {
+        if ((rc = c->scratch[5].ensure(sizeof(long long) * 128))) return rc;
+        DFT_CHECK(cudaMemsetAsync(c->scratch[5].p, 0, sizeof(long long) * 128, st));
+        pa.dbg = c->scratch[5].as<long long>();
+    }
     launch_poisson_full(g, lv, pa, st);
-    DFT_CHECK(cudaMemcpy2DAsync(U, sizeof(double) * N, c->phi.p, sizeof(double) * lv.total, sizeof(double) * N, n_dens, cudaMemcpyDeviceToHost, st));
+    if (c->profile) {
+        long long h[128];
+        DFT_CHECK(cudaMemcpyAsync(h, pa.dbg, sizeof(h), cudaMemcpyDeviceToHost, st));
+        DFT_CHECK(cudaStreamSynchronize(st));
+        fprintf(stderr, "poisson cycles (CTA 0): setup %lld  solve %lld  +export %lld\n", h[98], h[96], h[97]);
+        for (int l = 0; l < levels; ++l)
+            fprintf(stderr, "  level %2d n=%7d  smooth %9lld (%lld visits)  restrict_to %8lld  prolong_from %8lld\n", l, (1 << (levels - l)), h[l], h[72 + l], h[24 + l], h[48 + l]);
+    }
+    DFT_CHECK(cudaMemcpyAsync(U, c->ubuf.p, sizeof(double) * (size_t)n_dens * N, cudaMemcpyDeviceToHost, st));
     if (vcycles_used) DFT_CHECK(cudaMemcpyAsync(vcycles_used, dv.p, sizeof(int) * n_dens, cudaMemcpyDeviceToHost, st));
     DFT_CHECK(cudaStreamSynchronize(st));
     DFT_CHECK(cudaGetLastError());
@@ -609,14 +634,15 @@ int dftatom_poisson_vcycles(dftatom_ctx* c, int levels, double delta, int n_dens
     const int N = (1 << levels) + 1;
     int rc;
     if ((rc = c->phi.ensure(sizeof(double) * (size_t)n_dens * lv.total)) || (rc = c->src.ensure(sizeof(double) * (size_t)n_dens * lv.total))) return rc;
-    DevBuf& de = c->scratch[3];
+    DevBuf& de = c->scratch[3]; DevBuf& dp = c->scratch[0]; DevBuf& ds = c->scratch[1];
     if ((rc = de.ensure(sizeof(double) * n_dens))) return rc;
+    if ((rc = dp.ensure(sizeof(double) * (size_t)n_dens * N)) || (rc = ds.ensure(sizeof(double) * (size_t)n_dens * N))) return rc;
     DFT_CHECK(cudaMemsetAsync(c->phi.p, 0, sizeof(double) * (size_t)n_dens * lv.total, st));
     DFT_CHECK(cudaMemsetAsync(c->src.p, 0, sizeof(double) * (size_t)n_dens * lv.total, st));
-    DFT_CHECK(cudaMemcpy2DAsync(c->phi.p, sizeof(double) * lv.total, phi, sizeof(double) * N, sizeof(double) * N, n_dens, cudaMemcpyHostToDevice, st));
-    DFT_CHECK(cudaMemcpy2DAsync(c->src.p, sizeof(double) * lv.total, src, sizeof(double) * N, sizeof(double) * N, n_dens, cudaMemcpyHostToDevice, st));
-    launch_poisson_vcycles(levels, delta, lv, n_dens, c->phi.as<double>(), c->src.as<double>(), n_cycles, de.as<double>(), st);
-    DFT_CHECK(cudaMemcpy2DAsync(phi, sizeof(double) * N, c->phi.p, sizeof(double) * lv.total, sizeof(double) * N, n_dens, cudaMemcpyDeviceToHost, st));
+    DFT_CHECK(cudaMemcpyAsync(dp.p, phi, sizeof(double) * (size_t)n_dens * N, cudaMemcpyHostToDevice, st));
+    DFT_CHECK(cudaMemcpyAsync(ds.p, src, sizeof(double) * (size_t)n_dens * N, cudaMemcpyHostToDevice, st));
+    launch_poisson_vcycles(lv, delta, n_dens, c->phi.as<double>(), c->src.as<double>(), dp.as<double>(), ds.as<double>(), n_cycles, de.as<double>(), st);
+    DFT_CHECK(cudaMemcpyAsync(phi, dp.p, sizeof(double) * (size_t)n_dens * N, cudaMemcpyDeviceToHost, st));
     if (last_err) DFT_CHECK(cudaMemcpyAsync(last_err, de.p, sizeof(double) * n_dens, cudaMemcpyDeviceToHost, st));
     DFT_CHECK(cudaStreamSynchronize(st));
     DFT_CHECK(cudaGetLastError());

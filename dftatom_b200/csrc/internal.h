@@ -36,6 +36,7 @@ struct GridDev {
     double* wjac;    // simpson38 weight_i * Rp δ e^{δ i}            (Integral.h:50-73 × jacobian DFTAtom.cpp:47,442)
     double* psrc;    // r_i * 4π K_i  (0 at i=0 and i=N-1)           (PoissonSolver.h:55-74)
     double* inv4pr2; // 1 / (4π r_i^2) (0 at i=0)                    (DFTAtom.cpp:340)
+    double* coarse_op; // [32*32] dense operator of the Poisson sub-cycle below the 32-node level (poisson.cu), NULL for L < 6
 };
 
 // One orbital = one (atom, spin, n, l) level; also the unit of the batched energy search.
@@ -113,22 +114,28 @@ void launch_build_atab(const GridDev& g, const double* vpot, double* atab, int n
 // Poisson
 struct PoissonArgs {
     int n_dens;
-    const double* rho;      // [n_dens][N] total density (may be NULL when src is pre-filled)
+    const double* rho;      // [n_dens][N] total density, natural node order (or NULL)
+    const double* src_nat;  // [n_dens][N] Source_0 in natural node order, used when rho is NULL (or NULL)
+    double* u_out;          // [n_dens][N] result U(r) = Phi_0 in natural node order (or NULL)
     const int* Zbc;         // [n_dens] boundary value at Rmax (may be NULL: use hi_bc)
-    double* phi; double* src;   // [n_dens][levels.total]
+    double* phi; double* src;   // [n_dens][levels.total] the hierarchy, thread-major node order inside a level (poisson.cu)
     const int* skip;        // optional per-density skip flag (AtomState.done), stride given
     int skip_stride_bytes;
     int max_vcycles; int floor_stop;
+    int warm_vcycles;       // > 0: keep Phi_0 of the previous solve as the initial guess and run this many V-cycles (no FMG ramp)
     int smem_doubles;       // set by the launcher: doubles per shared-memory array of the coarse levels
     int refine_vcycles;     // > 0: double-double defect correction with this many V-cycles on the error equation
     double* u0;             // [n_dens][N] scratch for the correction (required when refine_vcycles > 0)
+    const double* coarse_op; // [32*32] dense operator of the coarse sub-cycle (GridDev.coarse_op) or NULL: run it level by level
+    long long* dbg;         // optional [128] cycle counters of CTA 0 (development aid)
     unsigned long long* work;   // optional: += Gauss-Seidel node-updates performed
     int* vcycles_used;      // optional [n_dens]
     double* last_err;       // optional [n_dens]
 };
+void launch_coarse_op(int L, double delta, double* G, cudaStream_t st);
 void launch_poisson_full(const GridDev& g, const PoissonLevels& lv, const PoissonArgs& a, cudaStream_t st);
-void launch_poisson_vcycles(int L, double delta, const PoissonLevels& lv, int n_dens, double* phi, double* src, int n_cycles,
-                            double* last_err, cudaStream_t st);
+void launch_poisson_vcycles(const PoissonLevels& lv, double delta, int n_dens, double* phi, double* src, double* phi_nat,
+                            const double* src_nat, int n_cycles, double* last_err, cudaStream_t st);
 
 // XC
 void launch_vwn(int n, const double* ra, const double* rb, double* va, double* vb, double* vexc, double* edif, cudaStream_t st);
@@ -145,6 +152,7 @@ struct ScfBuffers {
     double* psi;      // [n_orbs][N]
     int* match_pt;    // [n_orbs]
     double* phi; double* src;   // Poisson hierarchy [n_atoms][levels.total]
+    double* U;        // [n_atoms][N] Hartree U(r) = r V_H, natural node order (output of the Poisson solve)
     int* Zbc;         // [n_atoms]
     int* tab_of;      // [n_atoms][2] table row of (atom, spin) or -1
     dftatom_step* steps;  // [n_atoms][steps_stride]

@@ -1,4 +1,4 @@
-// Radial Poisson multigrid, one CTA per density, all levels of the 2^L+1 hierarchy L2-resident.
+// Radial Poisson multigrid, one CTA per density.
 //
 // Replaces (reference DFTAtom/) PoissonSolver.h:51-81 SolvePoissonNonUniform, :89-124 FullCycle, :155-159 VCycle and
 // PoissonSolver.cpp:40-64 GaussSeidel, :66-77 IterateGaussSeidel, :80-106 Initialize, :110-123 Prolong, :126-157
@@ -7,14 +7,19 @@
 // The reference's smoother is a lexicographic in-place Gauss-Seidel sweep, i.e. the first-order recurrence
 //     Phi_i <- a Phi_{i-1} + c_i ,   a = (1 + d_l/2)/2 ,   c_i = (S_i + (1 - d_l/2) Phi_{i+1}^old)/2 ,  d_l = δ 2^l .
 // Every thread owns NPT consecutive nodes: it runs the recurrence locally with zero carry-in, the carries are
-// resolved by an associative scan of the affine maps x -> a^m x + p (warp shuffles, then one shared-memory hop
-// across warps), and the result is patched in.  That is the same sweep (same operator, same ordering), evaluated
-// in O(NPT + log T) depth instead of O(N).
+// resolved by a scan of the affine maps x -> a^NPT x + p (warp shuffles, then one shared-memory hop across warps),
+// and the result is patched in.  That is the same sweep (same operator, same ordering), evaluated in O(NPT + log T)
+// depth instead of O(N).  Because a ~ 1/2, a^k drops below FP64 resolution after ~64 nodes: the scans are truncated
+// where the dropped terms are < 1e-19 relative.
 //
-// Level visits keep a thread's nodes of Phi and Source in registers for the three sweeps (levels up to 16384 nodes);
-// the six coarsest levels (<= 32 nodes) are run by warp 0 alone with no block barrier.  The update norm of the
-// reference's IterateGaussSeidel only drives its early exits; with a fixed number of sweeps it is evaluated once,
-// for the last fine-grid sweep of the solve.
+// Where the time goes is latency, not flops (one solve = ~400 level visits of three dependent sweeps each), so:
+//  * levels live in an owner-major layout (below): every access of a visit is unit-stride across the warp;
+//  * a visit keeps the thread's nodes in registers for its three sweeps;
+//  * levels with <= 1024 nodes are run by warp 0 alone out of static shared memory: no block barrier;
+//  * the sub-cycle below the 32-node level is one precomputed 32x32 operator (it depends on the grid only);
+//  * Source_0 (read by every fine-grid sweep) and the mid levels sit in dynamic shared memory when they fit.
+// The update norm of the reference's IterateGaussSeidel only drives its early exits; with a fixed number of sweeps it
+// is evaluated once, for the last fine-grid sweep of the solve, and only when the caller asks for it.
 #include "internal.h"
 #include <cmath>
 
@@ -35,353 +40,552 @@ PoissonLevels make_levels(int L)
 }
 
 constexpr int kPT = 512;     // threads per CTA
-constexpr int kPM = 16;      // nodes per thread per pass of the generic (global-memory) sweep
-constexpr int kMaxNpt = 32;  // register-resident visits handle levels with up to kPT * kMaxNpt nodes
-constexpr int kWarpLevelNodes = 32;
+constexpr int kLogPT = 9;
+constexpr int kMaxNpt = 32;  // nodes per thread of a register-resident chunk (a chunk = T * npt consecutive nodes)
+constexpr int kWarpLevelNodes = 1024;   // levels up to this size are run by warp 0 alone (no block barrier)
+constexpr int kWarpSmemDoubles = 2112;  // sum of the sizes of all levels with <= 1024 owned nodes, 4-aligned each
+constexpr double kTiny = 1e-19;   // carry terms below this (relative) are dropped from the truncated scans (FP64 eps = 1.1e-16)
+constexpr int kMaxDynBytes = 180 * 1024;   // dynamic shared memory the solve kernels may ask for (static part: ~45 KB)
 
-struct PoissonSmem {
-    double scanA[32], scanP[32];
-    double edge[32];
-    double red[32];
-    double carry;        // last new value of the previous pass
-    double bcast;
-    unsigned long long updates;   // Gauss-Seidel node-updates performed by this CTA (work counter)
-    int soff[24];                 // offsets of the shared-memory-resident levels inside the dynamic smem arrays
+// ---------------------------------------------------------------------------------------------------------
+// Owner-major level layout.  A level with n owned nodes (0..n-1; node n is the fixed right boundary) is run by T
+// threads (T = 512: the CTA, or T = 32: warp 0 for the small levels).  It is cut into chunks of C = T * npt nodes,
+// npt = clamp(n / T, 1, 32); inside a chunk thread t owns the npt consecutive nodes [t npt, (t+1) npt) and its k-th
+// node is stored at  chunk_base + k T + t.  Every per-thread walk over "my nodes" is then a unit-stride access across
+// the warp (coalesced in global memory, conflict-free in shared memory), and restriction / prolongation only touch
+// the same thread's nodes plus one halo value.  Node n keeps slot n.
+// ---------------------------------------------------------------------------------------------------------
+struct Lay { int lgT, lg; };     // log2 T, log2 npt
+__host__ __device__ inline Lay layout_of(int n)
+{
+    Lay y;
+    y.lgT = (n <= kWarpLevelNodes) ? 5 : kLogPT;
+    y.lg = 0;
+    while (((1 << y.lgT) << (y.lg + 1)) <= n && y.lg < 5) ++y.lg;
+    return y;
+}
+__host__ __device__ inline int slot(int i, Lay y)
+{
+    const int cm = ((1 << y.lgT) << y.lg) - 1;
+    return (i & ~cm) | ((i & ((1 << y.lg) - 1)) << y.lgT) | ((i & cm) >> y.lg);
+}
+__host__ __device__ inline int unslot(int s, Lay y)
+{
+    const int cm = ((1 << y.lgT) << y.lg) - 1;
+    const int j = s & cm;
+    return (s & ~cm) | ((j & ((1 << y.lgT) - 1)) << y.lg) | (j >> y.lgT);
+}
+
+enum { kGlobal = 0, kDyn = 1, kWarp = 2 };     // where a level array lives
+
+struct LevelConst {
+    double d, a, bcoef;      // d_l = delta 2^l; a = (1 + d/2)/2; bcoef = (1 - d/2)/2       (PoissonSolver.cpp:56-57)
+    double Ap[5];            // A^(2^j), A = a^npt: the multiplier of one thread's local affine map
+    double B;                // A^32: the multiplier of one warp
+    int nsteps;              // warp-scan steps that still matter (A^(2^j) >= kTiny)
+    int n;                   // owned nodes
+    Lay lay;
+    int wp, ws;              // where Phi / Source live
+    int op, os;              // their offsets (global: inside the density's hierarchy block; kDyn: in g_dyn; kWarp: in g_sm.w)
 };
 
-__device__ __forceinline__ double block_sum(double v, PoissonSmem& sm)
+struct PoissonSmem {
+    LevelConst lc[24];
+    double* gphi; double* gsrc;   // this density's block of the global hierarchy arrays
+    long long* dbg;      // optional cycle counters (development aid): [0,24) smooth, [24,48) restrict, [48,72) prolong, [72,96) visits
+    int L, m, has_G;     // levels; level with 32 owned nodes that the dense operator starts from (valid when has_G)
+    double wtot[16];     // per-warp totals of the local affine maps
+    double edge[16];     // first node of every warp (old value for the left neighbour warp)
+    double red[32];
+    double carry;        // last new value of the previous chunk
+    double bcast;
+    unsigned long long updates;   // Gauss-Seidel node-updates performed by this CTA (work counter)
+    double w[2 * kWarpSmemDoubles];   // the warp levels: Phi at [0, kWarpSmemDoubles), Source behind it
+    double G[32 * 32];   // dense operator of the sub-cycle below the 32-node level, column-major G[j * 32 + i]
+};
+
+// File-scope shared variables: every access compiles to LDS/STS (a PoissonSmem& parameter would make them generic
+// loads, which wait on the long scoreboard like global memory).
+__shared__ PoissonSmem g_sm;
+extern __shared__ double g_dyn[];
+
+// one level array, wherever it lives
+struct Ref {
+    int w, off;
+    double* g;
+    static __device__ __forceinline__ Ref P(int l) { const LevelConst& c = g_sm.lc[l]; return Ref{ c.wp, c.op, g_sm.gphi }; }
+    static __device__ __forceinline__ Ref S(int l) { const LevelConst& c = g_sm.lc[l]; return Ref{ c.ws, c.os, g_sm.gsrc }; }
+    __device__ __forceinline__ double ld(int i) const { return w == kWarp ? g_sm.w[off + i] : (w == kDyn ? g_dyn[off + i] : g[off + i]); }
+    __device__ __forceinline__ void st(int i, double v) const
+    {
+        if (w == kWarp) g_sm.w[off + i] = v; else if (w == kDyn) g_dyn[off + i] = v; else g[off + i] = v;
+    }
+};
+
+__device__ __forceinline__ double block_sum(double v)
 {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     __syncthreads();
-    if (lane == 0) sm.red[w] = v;
+    if (lane == 0) g_sm.red[w] = v;
     __syncthreads();
     if (w == 0) {
-        double t = (lane < (blockDim.x >> 5)) ? sm.red[lane] : 0.;
+        double t = (lane < (blockDim.x >> 5)) ? g_sm.red[lane] : 0.;
 #pragma unroll
         for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (lane == 0) sm.bcast = t;
+        if (lane == 0) g_sm.bcast = t;
     }
     __syncthreads();
-    return sm.bcast;
+    return g_sm.bcast;
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// generic sweep on global-memory level arrays (any size, multi-pass); returns sqrt(sum (old-new)^2)
-// ---------------------------------------------------------------------------------------------------------
-__device__ __noinline__ double gs_sweep(double* __restrict__ phi, const double* __restrict__ src, int size, double d, PoissonSmem& sm)
-{
-    const int T = blockDim.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
-    const double a = 0.5 * (1. + 0.5 * d), bcoef = 0.5 * (1. - 0.5 * d);
-    const int n_int = size - 2;
-    double err2 = 0.;
-    if (t == 0) { sm.carry = phi[0]; sm.updates += (unsigned long long)n_int; }
-    const int per_pass = T * kPM;
-    for (int base = 0; base < n_int; base += per_pass) {
-        const int i0 = 1 + base + t * kPM;
-        int m = n_int + 1 - i0;                 // valid nodes of this thread in this pass
-        m = m < 0 ? 0 : (m > kPM ? kPM : m);
-        double p[kPM];
-        double A = 1., x = 0.;
-        if (m > 0) {
-#pragma unroll
-            for (int k = 0; k < kPM; ++k) {
-                if (k < m) {
-                    const double c = fma(bcoef, phi[i0 + k + 1], 0.5 * src[i0 + k]);
-                    x = fma(a, x, c);
-                    p[k] = x;
-                    A *= a;
-                }
-            }
-        }
-        double sA = A, sP = x;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const double pa = __shfl_up_sync(0xffffffffu, sA, o), pp = __shfl_up_sync(0xffffffffu, sP, o);
-            if (lane >= o) { sP = fma(sA, pp, sP); sA *= pa; }
-        }
-        __syncthreads();                           // all loads of old values done; smem from previous pass consumed
-        if (lane == 31) { sm.scanA[w] = sA; sm.scanP[w] = sP; }
-        __syncthreads();
-        if (w == 0) {
-            const int nw = T >> 5;
-            double wa = lane < nw ? sm.scanA[lane] : 1., wp = lane < nw ? sm.scanP[lane] : 0.;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const double pa = __shfl_up_sync(0xffffffffu, wa, o), pp = __shfl_up_sync(0xffffffffu, wp, o);
-                if (lane >= o) { wp = fma(wa, pp, wp); wa *= pa; }
-            }
-            sm.scanA[lane] = wa; sm.scanP[lane] = wp;   // inclusive over warps
-        }
-        __syncthreads();
-        double eA = __shfl_up_sync(0xffffffffu, sA, 1), eP = __shfl_up_sync(0xffffffffu, sP, 1);
-        if (lane == 0) { eA = 1.; eP = 0.; }
-        if (w > 0) { const double wa = sm.scanA[w - 1], wp = sm.scanP[w - 1]; eP = fma(eA, wp, eP); eA *= wa; }
-        const double left = sm.carry;
-        const double cin = fma(eA, left, eP);       // new value of node i0-1
-        if (m > 0) {
-            double q = a;
-#pragma unroll
-            for (int k = 0; k < kPM; ++k) {
-                if (k < m) {
-                    const double v = fma(q, cin, p[k]);
-                    const double dif = phi[i0 + k] - v;
-                    err2 = fma(dif, dif, err2);
-                    phi[i0 + k] = v;
-                    q *= a;
-                }
-            }
-        }
-        __syncthreads();
-        if (t == T - 1) sm.carry = fma(sm.scanA[(T >> 5) - 1], left, sm.scanP[(T >> 5) - 1]);
-        __syncthreads();
-    }
-    return sqrt(block_sum(err2, sm));
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// register-resident level visit: `sweeps` Gauss-Seidel sweeps on a level with n = size-1 <= kPT*NPT owned nodes
-// (thread t owns nodes [t NPT, (t+1) NPT); node 0 is the fixed left boundary, node n the fixed right boundary)
+// Register-resident visit of one chunk by the whole CTA: `sweeps` lexicographic Gauss-Seidel sweeps.
+//   l, c0        : level and first slot of the chunk (Phi / Source: global memory or g_dyn, see LevelConst)
+//   first        : the chunk starts with node 0 (fixed left boundary); otherwise left_new = new value of the node
+//                  before the chunk
+//   right_old    : value of the node after the chunk (old value: it is swept later, or it is the right boundary)
 // ---------------------------------------------------------------------------------------------------------
 template <int NPT, bool SRC_REGS>
-__device__ __noinline__ void visit_regs(double* __restrict__ phi_g, const double* __restrict__ src_g, int size, double d, int sweeps,
-                                           int pad, PoissonSmem& sm)
+__device__ __noinline__ void visit_regs(int l, int c0, int sweeps, bool first, double left_new, double right_old)
 {
-    // pad = 1: the level lives in shared memory with one padding slot per thread chunk (chunk stride NPT + 1 doubles is odd,
-    // so the 32 lanes of a warp hit 32 different bank pairs); pad = 0: plain layout in global memory
     const unsigned full = 0xffffffffu;
-    const int t = threadIdx.x, lane = t & 31, w = t >> 5, nw = blockDim.x >> 5;
-    const int n = size - 1;
-    const int i0 = t * NPT;
-    const int p0 = t * (NPT + pad);
-    const bool active = i0 < n;
-    const double a = 0.5 * (1. + 0.5 * d), bcoef = 0.5 * (1. - 0.5 * d);
-    const double right_bc = phi_g[n + (pad ? n / NPT : 0)];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const bool last_thr = (t == kPT - 1);
+    const LevelConst& lc = g_sm.lc[l];
+    const double a = lc.a, bcoef = lc.bcoef;
+    const bool p_dyn = lc.wp == kDyn, s_dyn = lc.ws == kDyn;
+    const int op = lc.op + c0, os = lc.os + c0;
+    double* gp = g_sm.gphi + op;            // only dereferenced when the array is global
+    const double* gs = g_sm.gsrc + os;
     double phi[NPT], src[SRC_REGS ? NPT : 1];
-    const double* __restrict__ sp = src_g + (active ? p0 : 0);      // Source is read-only during the visit
+    if (p_dyn) {
 #pragma unroll
-    for (int k = 0; k < NPT; ++k) {
-        phi[k] = active ? phi_g[p0 + k] : 0.;
-        if (SRC_REGS) src[k] = active ? 0.5 * src_g[p0 + k] : 0.;
+        for (int k = 0; k < NPT; ++k) phi[k] = g_dyn[op + k * kPT + t];
+    } else {
+#pragma unroll
+        for (int k = 0; k < NPT; ++k) phi[k] = gp[k * kPT + t];
     }
-    double aN = a;
+    if (SRC_REGS) {
+        if (s_dyn) {
 #pragma unroll
-    for (int k = 1; k < NPT; ++k) aN *= a;
-    if (t == 0) sm.updates += (unsigned long long)sweeps * (unsigned long long)(n - 1);
+            for (int k = 0; k < NPT; ++k) src[k] = 0.5 * g_dyn[os + k * kPT + t];
+        } else {
+#pragma unroll
+            for (int k = 0; k < NPT; ++k) src[k] = 0.5 * gs[k * kPT + t];
+        }
+    }
+    // multipliers of the warp scan, pre-selected per lane (0 where the step does not apply or no longer matters)
+    double Am[5];
+    double Alane = 1.;                       // A^lane
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        Am[j] = (lane >= (1 << j) && j < lc.nsteps) ? lc.Ap[j] : 0.;
+        if ((lane >> j) & 1) Alane *= lc.Ap[j];
+    }
+    const double B = lc.B;
+    const int nsteps = lc.nsteps;
+    if (t == 0) g_sm.updates += (unsigned long long)sweeps * (unsigned long long)(NPT * kPT);
 
     for (int sw = 0; sw < sweeps; ++sw) {
         // old value of the right neighbour's first node
         double nb = __shfl_down_sync(full, phi[0], 1);
-        if (lane == 0) sm.edge[w] = phi[0];
+        if (lane == 0) g_sm.edge[w] = phi[0];
         __syncthreads();
-        if (lane == 31) nb = (w + 1 < nw) ? sm.edge[w + 1] : right_bc;
-        if (i0 + NPT >= n) nb = right_bc;
+        if (lane == 31 && w + 1 < (kPT >> 5)) nb = g_sm.edge[w + 1];
+        if (last_thr) nb = right_old;
         // local recurrence with zero carry-in, in place
+        double x = 0.;
+        if (SRC_REGS) {
+#pragma unroll
+            for (int k = 0; k < NPT; ++k) {
+                const double c = fma(bcoef, (k + 1 < NPT) ? phi[k + 1] : nb, src[k]);
+                x = (first && t == 0 && k == 0) ? phi[0] : fma(a, x, c);      // node 0 keeps its boundary value
+                phi[k] = x;
+            }
+        } else if (s_dyn) {
+#pragma unroll
+            for (int k = 0; k < NPT; ++k) {
+                const double c = fma(bcoef, (k + 1 < NPT) ? phi[k + 1] : nb, 0.5 * g_dyn[os + k * kPT + t]);
+                x = (first && t == 0 && k == 0) ? phi[0] : fma(a, x, c);
+                phi[k] = x;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < NPT; ++k) {
+                const double c = fma(bcoef, (k + 1 < NPT) ? phi[k + 1] : nb, 0.5 * gs[k * kPT + t]);
+                x = (first && t == 0 && k == 0) ? phi[0] : fma(a, x, c);
+                phi[k] = x;
+            }
+        }
+        // warp scan of the totals (uniform multiplier): P_lane = sum_j A^(lane-j) p_j
+        double P = x;
+        P = fma(Am[0], __shfl_up_sync(full, P, 1), P);
+        if (nsteps > 1) {
+            P = fma(Am[1], __shfl_up_sync(full, P, 2), P);
+            if (nsteps > 2) {
+                P = fma(Am[2], __shfl_up_sync(full, P, 4), P);
+                P = fma(Am[3], __shfl_up_sync(full, P, 8), P);
+                P = fma(Am[4], __shfl_up_sync(full, P, 16), P);
+            }
+        }
+        if (lane == 31) g_sm.wtot[w] = P;
+        __syncthreads();
+        // carry into this warp: sum_k B^(k-1) W_(w-k)  (+ B^w left_new), truncated
+        double carry = 0.;
+        {
+            double bp = 1.;
+            int k = 1;
+            for (; k <= w && bp >= kTiny; ++k) { carry = fma(bp, g_sm.wtot[w - k], carry); bp *= B; }
+            if (k > w && bp >= kTiny && !first) carry = fma(bp, left_new, carry);
+        }
+        double Pex = __shfl_up_sync(full, P, 1);
+        if (lane == 0) Pex = 0.;
+        double cin = fma(Alane, carry, Pex);                   // new value of the node before this thread's first node
+        if (first && t == 0) cin = 0.;
+        double q = a;
+#pragma unroll
+        for (int k = 0; k < NPT; ++k) { phi[k] = fma(q, cin, phi[k]); q *= a; }
+    }
+    if (p_dyn) {
+#pragma unroll
+        for (int k = 0; k < NPT; ++k) g_dyn[op + k * kPT + t] = phi[k];
+    } else {
+#pragma unroll
+        for (int k = 0; k < NPT; ++k) gp[k * kPT + t] = phi[k];
+    }
+    if (last_thr) g_sm.carry = phi[NPT - 1];
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The same visit for a level of <= 1024 owned nodes, executed by warp 0 alone (no block barrier): lane owns NPT
+// consecutive nodes (owner-major layout with T = 32, static shared memory).  n < 32: one node per lane, n lanes active.
+// ---------------------------------------------------------------------------------------------------------
+template <int NPT, bool SRC_REGS>
+__device__ __noinline__ void visit_warp(int l, int sweeps)
+{
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const LevelConst& lc = g_sm.lc[l];
+    const int n = lc.n, op = lc.op, os = lc.os;
+    const bool active = lane * NPT < n;
+    const bool last_lane = ((lane + 1) * NPT >= n) && active;
+    const double a = lc.a, bcoef = lc.bcoef;
+    const double right_bc = g_sm.w[op + n];
+    double phi[NPT], src[SRC_REGS ? NPT : 1];
+#pragma unroll
+    for (int k = 0; k < NPT; ++k) {
+        phi[k] = active ? g_sm.w[op + k * 32 + lane] : 0.;
+        if (SRC_REGS) src[k] = active ? 0.5 * g_sm.w[os + k * 32 + lane] : 0.;
+    }
+    double Am[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) Am[j] = (lane >= (1 << j) && j < lc.nsteps) ? lc.Ap[j] : 0.;
+    const int nsteps = lc.nsteps;
+    for (int sw = 0; sw < sweeps; ++sw) {
+        double nb = __shfl_down_sync(full, phi[0], 1);
+        if (last_lane) nb = right_bc;
         double x = 0.;
 #pragma unroll
         for (int k = 0; k < NPT; ++k) {
-            const double nxt = (k + 1 < NPT) ? phi[k + 1] : nb;
-            const double c = fma(bcoef, nxt, SRC_REGS ? src[k] : 0.5 * sp[k]);
-            x = (t == 0 && k == 0) ? phi[0] : fma(a, x, c);      // node 0 keeps its boundary value
+            const double c = fma(bcoef, (k + 1 < NPT) ? phi[k + 1] : nb, SRC_REGS ? src[k] : 0.5 * g_sm.w[os + k * 32 + lane]);
+            x = (lane == 0 && k == 0) ? phi[0] : fma(a, x, c);
             phi[k] = x;
         }
-        double sA = active ? (t == 0 ? 0. : aN) : 1., sP = active ? x : 0.;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const double pa = __shfl_up_sync(full, sA, o), pp = __shfl_up_sync(full, sP, o);
-            if (lane >= o) { sP = fma(sA, pp, sP); sA *= pa; }
-        }
-        if (lane == 31) { sm.scanA[w] = sA; sm.scanP[w] = sP; }
-        __syncthreads();
-        // carry into this warp = composition of the total maps of the warps before it, applied to 0: every warp scans
-        // the (<= 32) warp totals itself with shuffles (no second barrier, no serial chain)
-        double carry;
-        {
-            double wa = lane < nw ? sm.scanA[lane] : 1., wp = lane < nw ? sm.scanP[lane] : 0.;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const double pa = __shfl_up_sync(full, wa, o), pp = __shfl_up_sync(full, wp, o);
-                if (lane >= o) { wp = fma(wa, pp, wp); wa *= pa; }
+        double P = active ? x : 0.;
+        P = fma(Am[0], __shfl_up_sync(full, P, 1), P);
+        if (nsteps > 1) {
+            P = fma(Am[1], __shfl_up_sync(full, P, 2), P);
+            if (nsteps > 2) {
+                P = fma(Am[2], __shfl_up_sync(full, P, 4), P);
+                P = fma(Am[3], __shfl_up_sync(full, P, 8), P);
+                P = fma(Am[4], __shfl_up_sync(full, P, 16), P);
             }
-            carry = __shfl_sync(full, wp, (w + 31) & 31);       // inclusive prefix of warp w-1 (map applied to 0 = its P)
-            if (w == 0) carry = 0.;
         }
-        double eA = __shfl_up_sync(full, sA, 1), eP = __shfl_up_sync(full, sP, 1);
-        if (lane == 0) { eA = 1.; eP = 0.; }
-        const double cin = fma(eA, carry, eP);                    // new value of node i0-1
+        double cin = __shfl_up_sync(full, P, 1);
+        if (lane == 0) cin = 0.;
         double q = a;
 #pragma unroll
         for (int k = 0; k < NPT; ++k) { phi[k] = fma(q, cin, phi[k]); q *= a; }
     }
     if (active) {
 #pragma unroll
-        for (int k = 0; k < NPT; ++k) phi_g[p0 + k] = phi[k];
+        for (int k = 0; k < NPT; ++k) g_sm.w[op + k * 32 + lane] = phi[k];
     }
-    __syncthreads();
-}
-
-// same for a level of <= 32 owned nodes, executed by one warp, no block barrier
-__device__ __noinline__ void visit_warp(double* __restrict__ phi_g, const double* __restrict__ src_g, int size, double d, int sweeps)
-{
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int n = size - 1;
-    const bool active = lane < n;
-    const double a = 0.5 * (1. + 0.5 * d), bcoef = 0.5 * (1. - 0.5 * d);
-    const double right_bc = phi_g[n];
-    double phi = active ? phi_g[lane] : 0.;
-    const double src = active ? 0.5 * src_g[lane] : 0.;
-    for (int sw = 0; sw < sweeps; ++sw) {
-        double nb = __shfl_down_sync(full, phi, 1);
-        if (lane + 1 >= n) nb = right_bc;
-        const double c = fma(bcoef, nb, src);
-        double sA = active ? (lane == 0 ? 0. : a) : 1., sP = active ? (lane == 0 ? phi : c) : 0.;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const double pa = __shfl_up_sync(full, sA, o), pp = __shfl_up_sync(full, sP, o);
-            if (lane >= o) { sP = fma(sA, pp, sP); sA *= pa; }
-        }
-        phi = sP;      // inclusive scan value = new Phi of this node (carry-in of node 0 is its own fixed value)
-    }
-    if (active) phi_g[lane] = phi;
     __syncwarp();
 }
 
-// physical slot of node i of a level whose chunks of 2^sh nodes carry one padding slot (sh = 31: no padding)
-__device__ __forceinline__ int slot(int i, int sh) { return i + (i >> sh); }
-
-__device__ __forceinline__ void restrict_nodes(const double* pf, const double* sf, int shf, double* pc, double* sc, int shc, int nc,
-                                               double dc, int tid, int nthr)
-{   // Restrict, PoissonSolver.cpp:126-157
-    for (int i = tid; i < nc; i += nthr) {
+// Restrict, PoissonSolver.cpp:126-157: coarse slots are walked in storage order (coalesced); the three fine nodes of a
+// coarse node belong to the same thread's chunk (plus one halo node of the left neighbour)
+__device__ __forceinline__ void restrict_nodes(Ref pf, Ref sf, Lay yf, Ref pc, Ref sc, Lay yc, int nc, double dc, int tid, int nthr)
+{
+    for (int s = tid; s < nc; s += nthr) {          // nc = size of the coarse level; slot nc-1 is its right boundary
+        const int i = unslot(s, yc);
         double v = 0.;
         if (i > 0 && i < nc - 1) {
             const int k = 2 * i;
-            const double lft = pf[slot(k - 1, shf)], mid = pf[slot(k, shf)], rgt = pf[slot(k + 1, shf)];
-            v = 4. * (sf[slot(k, shf)] + lft - 2. * mid + rgt) - dc * (rgt - lft);
+            const double lft = pf.ld(slot(k - 1, yf)), mid = pf.ld(slot(k, yf)), rgt = pf.ld(slot(k + 1, yf));
+            v = 4. * (sf.ld(slot(k, yf)) + lft - 2. * mid + rgt) - dc * (rgt - lft);
         }
-        pc[slot(i, shc)] = 0.;
-        sc[slot(i, shc)] = v;
+        pc.st(s, 0.);
+        sc.st(s, v);
     }
 }
 
-__device__ __forceinline__ void prolong_nodes(const double* pc, int shc, double* pf, int shf, int nc, int tid, int nthr)
+__device__ __forceinline__ void prolong_nodes(Ref pc, Lay yc, Ref pf, Lay yf, int nc, int tid, int nthr)
 {   // Prolong, PoissonSolver.cpp:110-123
-    for (int i = tid; i < nc; i += nthr) {
-        const double c = pc[slot(i, shc)];
-        pf[slot(2 * i, shf)] += c;
-        if (i > 0) pf[slot(2 * i - 1, shf)] += 0.5 * (pc[slot(i - 1, shc)] + c);
+    for (int s = tid; s < nc; s += nthr) {
+        const int i = unslot(s, yc);
+        const double c = pc.ld(s);
+        const int s2 = slot(2 * i, yf);
+        pf.st(s2, pf.ld(s2) + c);
+        if (i > 0) {
+            const int s1 = slot(2 * i - 1, yf);
+            pf.st(s1, pf.ld(s1) + 0.5 * (pc.ld(slot(i - 1, yc)) + c));
+        }
     }
 }
 
-// One multigrid hierarchy of one density; every method is called by all threads of the CTA.
-// Levels with at most kSmemLevelNodes nodes live in (padded) shared memory, the finer ones in global memory (L2).
-constexpr int kSmemLevelNodes = 4096;
+// ---------------------------------------------------------------------------------------------------------
+// One multigrid hierarchy of one density.  All state is in g_sm; the functions below are called by all threads of the
+// CTA.  The heavy bodies are __noinline__ functions of the level index only (a fat inlined dispatcher costs hundreds of
+// spill instructions per call), the wrappers that carry the per-thread `pending` flag are inlined.
+// ---------------------------------------------------------------------------------------------------------
+struct Ctl { bool pending; };    // warp 0 wrote coarse levels that the other warps have not synchronised with yet
 
-__host__ __device__ inline int level_npt(int n) { return n > kPT ? n / kPT : 1; }          // nodes per thread of a level
-__host__ __device__ inline int level_slots(int n) { return n + 1 + (level_npt(n) > 1 ? n / level_npt(n) : 0); }
+__device__ __forceinline__ void block_begin(Ctl& ctl) { if (ctl.pending) { __syncthreads(); ctl.pending = false; } }
 
-struct Hierarchy {
-    double* phi; double* src;       // global arrays (all levels, plain layout)
-    double* sphi; double* ssrc;     // shared-memory arrays of the coarse levels (padded layout), may be null
-    const PoissonLevels& lv;
-    double delta;
-    PoissonSmem& sm;
-    bool pending;        // warp 0 wrote coarse levels that the other warps have not synchronised with yet
-
-    __device__ __forceinline__ double dl(int l) const { return delta * (double)(1 << l); }
-    __device__ __forceinline__ bool warp_level(int l) const { return lv.size[l] - 1 <= kWarpLevelNodes; }
-    __device__ __forceinline__ bool in_smem(int l) const { return sphi != nullptr && l >= 1 && lv.size[l] - 1 <= kSmemLevelNodes; }
-    __device__ __forceinline__ int shift(int l) const
-    {
-        const int npt = level_npt(lv.size[l] - 1);
-        return (in_smem(l) && npt > 1) ? 31 - __clz(npt) : 31;
-    }
-    __device__ __forceinline__ double* P(int l) const { return in_smem(l) ? sphi + sm.soff[l] : phi + lv.off[l]; }
-    __device__ __forceinline__ double* S(int l) const { return in_smem(l) ? ssrc + sm.soff[l] : src + lv.off[l]; }
-    __device__ __forceinline__ void block_begin() { if (pending) { __syncthreads(); pending = false; } }
-
-    // IterateGaussSeidel(l, ., sweeps) without the early exit
-    __device__ __forceinline__ void smooth(int l, int sweeps)
-    {
-        double* p = P(l);
-        const double* s = S(l);
-        const int size = lv.size[l], n = size - 1;
-        if (warp_level(l)) {
-            if (threadIdx.x < 32) {
-                if (threadIdx.x == 0) sm.updates += (unsigned long long)sweeps * (unsigned long long)(n - 1);
-                visit_warp(p, s, size, dl(l), sweeps);
+// per-level constants and placement (threads 0..L-1 fill one level each; every thread computes the same placement)
+__device__ __noinline__ void hierarchy_setup(const PoissonLevels& lv, double delta, double* gphi, double* gsrc, int dyn_doubles,
+                                             const double* Gg, long long* dbg)
+{
+    const int l = threadIdx.x;
+    if (l < lv.L) {
+        LevelConst c;
+        c.n = lv.size[l] - 1;
+        c.d = delta * (double)(1 << l);
+        c.a = 0.5 * (1. + 0.5 * c.d);
+        c.bcoef = 0.5 * (1. - 0.5 * c.d);
+        c.lay = layout_of(c.n);
+        double A = c.a;
+        for (int k = 0; k < c.lay.lg; ++k) A *= A;
+        c.Ap[0] = A;
+        for (int j = 1; j < 5; ++j) c.Ap[j] = c.Ap[j - 1] * c.Ap[j - 1];
+        c.B = c.Ap[4] * c.Ap[4];
+        c.nsteps = 5;
+        for (int j = 4; j >= 0; --j) if (c.Ap[j] < kTiny) c.nsteps = j;
+        c.wp = c.ws = kGlobal; c.op = c.os = lv.off[l];
+        // warp levels: static shared memory
+        int woff = 0;
+        for (int k = 0; k < lv.L; ++k) {
+            const int nk = lv.size[k] - 1;
+            if (nk > kWarpLevelNodes) continue;
+            if (k == l) { c.wp = c.ws = kWarp; c.op = woff; c.os = kWarpSmemDoubles + woff; }
+            woff += (nk + 4) & ~3;
+        }
+        // dynamic shared memory: Source_0 first (every fine-grid sweep streams it), then whole levels, coarsest first
+        int avail = dyn_doubles, doff = 0;
+        const int n0 = lv.size[0] - 1;
+        bool src0_dyn = false;
+        if (n0 > kWarpLevelNodes && ((n0 + 4) & ~3) <= avail) {
+            src0_dyn = true;
+            if (l == 0) { c.ws = kDyn; c.os = doff; }
+            doff += (n0 + 4) & ~3; avail -= (n0 + 4) & ~3;
+        }
+        for (int k = lv.L - 1; k >= 0; --k) {
+            const int nk = lv.size[k] - 1;
+            if (nk <= kWarpLevelNodes) continue;
+            const int one = (nk + 4) & ~3;
+            const int need = (k == 0 && src0_dyn) ? one : 2 * one;
+            if (need > avail) break;
+            if (k == l) {
+                c.wp = kDyn; c.op = doff;
+                if (!(k == 0 && src0_dyn)) { c.ws = kDyn; c.os = doff + one; }
             }
-            pending = true;
-            return;
+            doff += need; avail -= need;
         }
-        block_begin();
-        const int pad = (in_smem(l) && n > kPT) ? 1 : 0;
-        if (n > kPT * kMaxNpt) { for (int k = 0; k < sweeps; ++k) gs_sweep(p, s, size, dl(l), sm); }
-        else if (n > kPT * 16) visit_regs<32, false>(p, s, size, dl(l), sweeps, pad, sm);
-        else if (n > kPT * 8) visit_regs<16, true>(p, s, size, dl(l), sweeps, pad, sm);
-        else if (n > kPT * 4) visit_regs<8, true>(p, s, size, dl(l), sweeps, pad, sm);
-        else if (n > kPT * 2) visit_regs<4, true>(p, s, size, dl(l), sweeps, pad, sm);
-        else if (n > kPT) visit_regs<2, true>(p, s, size, dl(l), sweeps, pad, sm);
-        else visit_regs<1, true>(p, s, size, dl(l), sweeps, 0, sm);
+        g_sm.lc[l] = c;
     }
-    __device__ __forceinline__ void restrict_to(int l)       // level l-1 -> l
-    {
-        if (warp_level(l)) {                                  // <= 33 coarse nodes: warp 0 alone (level l-1 is complete: either
-            if (threadIdx.x < 32) {                           //  a block op ended with a barrier or warp 0 wrote it itself)
-                restrict_nodes(P(l - 1), S(l - 1), shift(l - 1), P(l), S(l), shift(l), lv.size[l], dl(l), threadIdx.x, 32);
-                __syncwarp();
+    if (threadIdx.x == 0) {
+        g_sm.gphi = gphi; g_sm.gsrc = gsrc; g_sm.dbg = dbg;
+        g_sm.L = lv.L; g_sm.m = lv.L - 5; g_sm.has_G = (Gg != nullptr && lv.L - 5 >= 1) ? 1 : 0;
+        g_sm.updates = 0;
+    }
+    if (Gg != nullptr && lv.L - 5 >= 1) for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) g_sm.G[i] = Gg[i];
+    __syncthreads();
+}
+
+// IterateGaussSeidel(l, ., sweeps) without the early exit, levels run by warp 0
+__device__ __noinline__ void smooth_warp(int l, int sweeps)
+{
+    const long long t0 = g_sm.dbg ? clock64() : 0;
+    const LevelConst& c = g_sm.lc[l];
+    if (threadIdx.x == 0) g_sm.updates += (unsigned long long)sweeps * (unsigned long long)(c.n - 1);
+    switch (c.lay.lg) {
+        case 5: visit_warp<32, false>(l, sweeps); break;
+        case 4: visit_warp<16, true>(l, sweeps); break;
+        case 3: visit_warp<8, true>(l, sweeps); break;
+        case 2: visit_warp<4, true>(l, sweeps); break;
+        case 1: visit_warp<2, true>(l, sweeps); break;
+        default: visit_warp<1, true>(l, sweeps); break;
+    }
+    if (g_sm.dbg && threadIdx.x == 0) { g_sm.dbg[l] += clock64() - t0; g_sm.dbg[72 + l] += 1; }
+}
+// ... levels run by the whole CTA
+__device__ __noinline__ void smooth_block(int l, int sweeps)
+{
+    const long long t0 = g_sm.dbg ? clock64() : 0;
+    const LevelConst& c = g_sm.lc[l];
+    const int n = c.n;
+    const Ref pr = Ref::P(l);
+    if (n > kPT * kMaxNpt) {
+        // multi-chunk level: one sweep at a time, chunk after chunk (carry = new value of the previous chunk's last node)
+        const int C = kPT * kMaxNpt;
+        for (int k = 0; k < sweeps; ++k) {
+            double left = 0.;
+            for (int c0 = 0; c0 < n; c0 += C) {
+                const double right = pr.ld(c0 + C);      // first node of the next chunk (slot c0 + C) or the boundary node n
+                visit_regs<32, false>(l, c0, 1, c0 == 0, left, right);
+                left = g_sm.carry;
             }
-            pending = true;
-            return;
         }
-        block_begin();
-        restrict_nodes(P(l - 1), S(l - 1), shift(l - 1), P(l), S(l), shift(l), lv.size[l], dl(l), threadIdx.x, blockDim.x);
-        __syncthreads();
-    }
-    __device__ __forceinline__ void prolong_from(int l)      // level l -> l-1
-    {
-        if (warp_level(l - 1)) {
-            if (threadIdx.x < 32) { prolong_nodes(P(l), shift(l), P(l - 1), shift(l - 1), lv.size[l], threadIdx.x, 32); __syncwarp(); }
-            pending = true;
-            return;
+    } else {
+        const double right = pr.ld(n);
+        switch (c.lay.lg) {
+            case 5: visit_regs<32, false>(l, 0, sweeps, true, 0., right); break;
+            case 4: visit_regs<16, true>(l, 0, sweeps, true, 0., right); break;
+            case 3: visit_regs<8, true>(l, 0, sweeps, true, 0., right); break;
+            default: visit_regs<4, true>(l, 0, sweeps, true, 0., right); break;   // n = 2048 (n <= 1024 are warp levels)
         }
-        block_begin();
-        prolong_nodes(P(l), shift(l), P(l - 1), shift(l - 1), lv.size[l], threadIdx.x, blockDim.x);
-        __syncthreads();
     }
-    // shared-memory offsets of the coarse levels (thread 0 fills sm.soff; returns doubles needed per array)
-    __device__ __forceinline__ void layout_smem()
-    {
-        if (threadIdx.x == 0) {
-            int off = 0;
-            for (int l = 0; l < lv.L; ++l) {
-                sm.soff[l] = off;
-                if (l >= 1 && lv.size[l] - 1 <= kSmemLevelNodes) off += (level_slots(lv.size[l] - 1) + 3) & ~3;
-            }
-        }
-        __syncthreads();
+    if (g_sm.dbg && threadIdx.x == 0) { g_sm.dbg[l] += clock64() - t0; g_sm.dbg[72 + l] += 1; }
+}
+__device__ __forceinline__ void smooth(Ctl& ctl, int l, int sweeps)
+{
+    if (g_sm.lc[l].wp == kWarp) {
+        if (threadIdx.x < 32) smooth_warp(l, sweeps);
+        ctl.pending = true;
+    } else {
+        block_begin(ctl);
+        smooth_block(l, sweeps);
     }
-    __device__ __forceinline__ void to_coarse(int from, int to)      // "Ascend", PoissonSolver.cpp:162-171
-    {
-        for (int l = from; l < to; ++l) { smooth(l, 3); restrict_to(l + 1); }
-        smooth(to, 3);
+}
+
+__device__ __noinline__ void restrict_impl(int l, int tid, int nthr)       // level l-1 -> l
+{
+    const long long t0 = g_sm.dbg ? clock64() : 0;
+    const LevelConst& cf = g_sm.lc[l - 1];
+    const LevelConst& cc = g_sm.lc[l];
+    restrict_nodes(Ref::P(l - 1), Ref::S(l - 1), cf.lay, Ref::P(l), Ref::S(l), cc.lay, cc.n + 1, cc.d, tid, nthr);
+    if (nthr == 32) __syncwarp(); else __syncthreads();
+    if (g_sm.dbg && threadIdx.x == 0) g_sm.dbg[24 + l] += clock64() - t0;
+}
+__device__ __forceinline__ void restrict_to(Ctl& ctl, int l)
+{
+    if (g_sm.lc[l - 1].wp == kWarp) {                           // both levels belong to warp 0
+        if (threadIdx.x < 32) restrict_impl(l, threadIdx.x, 32);
+        ctl.pending = true;
+    } else {
+        block_begin(ctl);
+        restrict_impl(l, threadIdx.x, kPT);
     }
-    __device__ __forceinline__ void to_fine(int from, int to)        // "Descend", PoissonSolver.cpp:173-186
-    {
-        for (int l = from; l > to; --l) { prolong_from(l); smooth(l - 1, 3); }
+}
+__device__ __noinline__ void prolong_impl(int l, int tid, int nthr)        // level l -> l-1
+{
+    const long long t0 = g_sm.dbg ? clock64() : 0;
+    const LevelConst& cf = g_sm.lc[l - 1];
+    const LevelConst& cc = g_sm.lc[l];
+    prolong_nodes(Ref::P(l), cc.lay, Ref::P(l - 1), cf.lay, cc.n + 1, tid, nthr);
+    if (nthr == 32) __syncwarp(); else __syncthreads();
+    if (g_sm.dbg && threadIdx.x == 0) g_sm.dbg[48 + l] += clock64() - t0;
+}
+__device__ __forceinline__ void prolong_from(Ctl& ctl, int l)
+{
+    if (g_sm.lc[l - 1].wp == kWarp) {
+        if (threadIdx.x < 32) prolong_impl(l, threadIdx.x, 32);
+        ctl.pending = true;
+    } else {
+        block_begin(ctl);
+        prolong_impl(l, threadIdx.x, kPT);
     }
-    // the last fine-grid visit of a solve: two register sweeps + one generic sweep that also returns the update norm
-    __device__ __forceinline__ double to_fine_with_norm(int from)
-    {
-        for (int l = from; l > 1; --l) { prolong_from(l); smooth(l - 1, 3); }
-        if (from >= 1) prolong_from(1);
-        smooth(0, 2);
-        block_begin();
-        return gs_sweep(P(0), const_cast<const double*>(S(0)), lv.size[0], dl(0), sm);
+}
+// phi_m = G src_m : the whole sub-cycle  smooth(m) restrict ... smooth(c) ... prolong smooth(m)  entered with phi_m = 0
+// is a fixed linear map of the 31 interior source values (it depends on the grid only; built by coarse_op_kernel)
+__device__ __noinline__ void dense_apply_warp()
+{
+    const LevelConst& c = g_sm.lc[g_sm.m];
+    const int i = threadIdx.x;
+    double a0 = 0., a1 = 0., a2 = 0., a3 = 0.;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+        a0 = fma(g_sm.G[(j + 0) * 32 + i], g_sm.w[c.os + j + 0], a0);
+        a1 = fma(g_sm.G[(j + 1) * 32 + i], g_sm.w[c.os + j + 1], a1);
+        a2 = fma(g_sm.G[(j + 2) * 32 + i], g_sm.w[c.os + j + 2], a2);
+        a3 = fma(g_sm.G[(j + 3) * 32 + i], g_sm.w[c.os + j + 3], a3);
     }
-};
+    g_sm.w[c.op + i] = (a0 + a1) + (a2 + a3);      // row 0 of G is zero: the left boundary stays 0
+    __syncwarp();
+}
+__device__ __forceinline__ void to_coarse(Ctl& ctl, int from, int to)      // "Ascend", PoissonSolver.cpp:162-171
+{
+    for (int l = from; l < to; ++l) { smooth(ctl, l, 3); restrict_to(ctl, l + 1); }
+    smooth(ctl, to, 3);
+}
+__device__ __forceinline__ void to_fine(Ctl& ctl, int from, int to)        // "Descend", PoissonSolver.cpp:173-186
+{
+    for (int l = from; l > to; --l) { prolong_from(ctl, l); smooth(ctl, l - 1, 3); }
+}
+// to_coarse(from, c) followed by to_fine(c, to).  With norm_scratch (N doubles of global memory) and to == 0 it also
+// returns sqrt(sum (old - new)^2) of the last fine-grid sweep (the reference's IterateGaussSeidel norm).
+__device__ __noinline__ double cycle(Ctl& ctl, int from, int to, double* norm_scratch)
+{
+    const int c = g_sm.L - 1, m = g_sm.m;
+    int top;
+    if (g_sm.has_G && from < m && to < m) {
+        for (int l = from; l < m; ++l) { smooth(ctl, l, 3); restrict_to(ctl, l + 1); }
+        if (threadIdx.x < 32) dense_apply_warp();
+        ctl.pending = true;
+        top = m;
+    } else {
+        to_coarse(ctl, from, c);
+        top = c;
+    }
+    const bool norm = norm_scratch != nullptr && to == 0 && top > 0;
+    for (int l = top; l > to; --l) {
+        prolong_from(ctl, l);
+        if (norm && l == 1) break;
+        smooth(ctl, l - 1, 3);
+    }
+    if (!norm) return 0.;
+    smooth(ctl, 0, 2);
+    block_begin(ctl);
+    const Ref p0 = Ref::P(0);
+    const int N = g_sm.lc[0].n + 1;
+    for (int s = threadIdx.x; s < N; s += blockDim.x) norm_scratch[s] = p0.ld(s);
+    __syncthreads();
+    smooth(ctl, 0, 1);
+    block_begin(ctl);
+    double e2 = 0.;
+    for (int s = threadIdx.x; s < N; s += blockDim.x) { const double dif = norm_scratch[s] - p0.ld(s); e2 = fma(dif, dif, e2); }
+    return sqrt(block_sum(e2));
+}
+// natural order <-> owner-major order of level 0
+__device__ __forceinline__ void import_level0(Ref dst, const double* nat, const double* scale, int N)
+{
+    const Lay y = g_sm.lc[0].lay;
+    for (int s = threadIdx.x; s < N; s += blockDim.x) {
+        const int i = unslot(s, y);
+        dst.st(s, scale ? scale[i] * nat[i] : nat[i]);
+    }
+}
+__device__ __forceinline__ void export_level0(double* nat, int N)
+{
+    const Lay y = g_sm.lc[0].lay;
+    const Ref p = Ref::P(0);
+    for (int s = threadIdx.x; s < N; s += blockDim.x) nat[unslot(s, y)] = p.ld(s);
+}
 
 // error-free transformations (Dekker / Knuth); the intrinsics keep nvcc from contracting or re-associating them
 __device__ __forceinline__ void two_sum(double a, double b, double& s, double& e)
@@ -417,138 +621,210 @@ __device__ __forceinline__ double dd_residual(double S, double um, double u0, do
 
 __global__ void __launch_bounds__(kPT) poisson_full_kernel(GridDev g, PoissonLevels lv, PoissonArgs a)
 {
-    __shared__ PoissonSmem sm;
-    extern __shared__ double dyn_smem[];
     const int k = blockIdx.x;
-    if (threadIdx.x == 0) sm.updates = 0;
     if (a.skip && *reinterpret_cast<const int*>(reinterpret_cast<const char*>(a.skip) + (size_t)k * a.skip_stride_bytes)) return;
-    double* phi = a.phi + (size_t)k * lv.total;
-    double* src = a.src + (size_t)k * lv.total;
     const int N = g.N, L = lv.L, c = L - 1;
-    Hierarchy h{ phi, src, a.smem_doubles ? dyn_smem : nullptr, a.smem_doubles ? dyn_smem + a.smem_doubles : nullptr, lv, g.delta, sm, false };
-    h.layout_smem();
+    const long long t_start = clock64();
+    long long* dbg = (a.dbg && blockIdx.x == 0) ? a.dbg : nullptr;
+    hierarchy_setup(lv, g.delta, a.phi + (size_t)k * lv.total, a.src + (size_t)k * lv.total, a.smem_doubles, a.coarse_op, dbg);
+    Ctl ctl{ false };
+    const Ref phi = Ref::P(0), src = Ref::S(0);
 
-    // Source_0 (PoissonSolver.h:55-74) and Initialize (PoissonSolver.cpp:80-106)
-    if (a.rho) {
-        const double* rho = a.rho + (size_t)k * N;
-        for (int i = threadIdx.x; i < N; i += blockDim.x) { src[i] = g.psrc[i] * rho[i]; phi[i] = 0.; }
+    // Source_0 (PoissonSolver.h:55-74)
+    if (a.rho) import_level0(src, a.rho + (size_t)k * N, g.psrc, N);
+    else if (a.src_nat) import_level0(src, a.src_nat + (size_t)k * N, nullptr, N);
+    const int n_cycles = a.warm_vcycles > 0 ? a.warm_vcycles : a.max_vcycles;
+    if (a.warm_vcycles > 0) {
+        // Warm start (beyond the reference): Phi_0 still holds the previous solve of this density (same boundary values);
+        // the V-cycles contract the difference ~25x each, so a few of them reach the same FP64 fixed point as the full cycle
+        __syncthreads();
     } else {
-        for (int i = threadIdx.x; i < N; i += blockDim.x) phi[i] = 0.;
-    }
-    __syncthreads();
-    for (int l = 1; l < L; ++l) {
-        const double* sf = h.S(l - 1);
-        double* sc = h.S(l);
-        double* pc = h.P(l);
-        const int n = lv.size[l], shf = h.shift(l - 1), shc = h.shift(l);
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            sc[slot(i, shc)] = (i > 0 && i < n - 1) ? 4. * sf[slot(2 * i, shf)] : 0.;
-            pc[slot(i, shc)] = 0.;
+        // Initialize (PoissonSolver.cpp:80-106) and the full-multigrid ramp (PoissonSolver.h:89-112)
+        for (int s = threadIdx.x; s < N; s += blockDim.x) phi.st(s, 0.);
+        __syncthreads();
+        for (int l = 1; l < L; ++l) {
+            const Ref sf = Ref::S(l - 1), sc = Ref::S(l), pc = Ref::P(l);
+            const int n = g_sm.lc[l].n + 1;
+            const Lay yf = g_sm.lc[l - 1].lay, yc = g_sm.lc[l].lay;
+            for (int s = threadIdx.x; s < n; s += blockDim.x) {
+                const int i = unslot(s, yc);
+                sc.st(s, (i > 0 && i < n - 1) ? 4. * sf.ld(slot(2 * i, yf)) : 0.);
+                pc.st(s, 0.);
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            Ref::P(c).st(0, 0.);                                          // SetBoundaries(0, Z), PoissonSolver.h:76
+            Ref::P(c).st(g_sm.lc[c].n, a.Zbc ? (double)a.Zbc[k] : 0.);
         }
         __syncthreads();
+        if (dbg && threadIdx.x == 0) dbg[98] += clock64() - t_start;
+        smooth(ctl, c, 2);     // the coarsest level has one interior node: the reference's <= 15 sweeps converge in one
+        // to_fine(c, l), to_coarse(l, c) for l = L-2 .. 1, then to_fine(c, 0)
+        to_fine(ctl, c, L - 2);
+        for (int l = L - 2; l > 0; --l) cycle(ctl, l, l - 1, nullptr);
     }
-    if (threadIdx.x == 0) {
-        h.P(c)[0] = 0.;                                               // SetBoundaries(0, Z), PoissonSolver.h:76
-        h.P(c)[lv.size[c] - 1] = a.Zbc ? (double)a.Zbc[k] : 0.;
-    }
-    __syncthreads();
-    h.smooth(c, 2);        // the coarsest level has one interior node: the reference's <= 15 sweeps converge in one
-
-    // FullCycle, PoissonSolver.h:89-124
-    for (int l = L - 2; l > 0; --l) {
-        h.to_fine(c, l);
-        h.to_coarse(l, c);
-    }
-    h.to_fine(c, 0);
+    const bool want_norm = (a.floor_stop || a.last_err || a.vcycles_used) && a.u_out != nullptr;
+    double* scratch = want_norm ? a.u_out + (size_t)k * N : nullptr;      // overwritten by the export below
     double err = 0., prev = 1e300;
     int used = 0, stagnant = 0;
-    for (int it = 0; it < a.max_vcycles; ++it) {
-        h.to_coarse(0, c);
-        const bool last = (it == a.max_vcycles - 1);
+    for (int it = 0; it < n_cycles; ++it) {
+        const bool last = (it == n_cycles - 1);
         ++used;
-        if (last || a.floor_stop) {
-            err = h.to_fine_with_norm(c);
+        if (want_norm && (last || a.floor_stop)) {
+            err = cycle(ctl, 0, 0, scratch);
             if (err < 1e-14) break;                                   // PoissonSolver.h:120
             // the update norm contracts ~25x per cycle until it reaches its FP64 rounding floor
             if (a.floor_stop) { if (err > 0.25 * prev) { if (++stagnant >= 2) break; } else stagnant = 0; }
             prev = err;
         } else {
-            h.to_fine(c, 0);
+            cycle(ctl, 0, 0, nullptr);
         }
     }
-    h.block_begin();
+    block_begin(ctl);
     // Defect correction (beyond the reference): one residual in double-double, then the error equation A e = r is solved
     // by the same V-cycles from e = 0 (its own rounding floor is ~1e-9 |e|, i.e. negligible) and U <- U + e.  The result
     // is the discrete solution to FP64 representation accuracy instead of ~1e-9, which removes the rounding-noise floor
     // of the SCF energies (the reference's |dE/E| wanders at 2e-11..1e-10 before it randomly dips below 1e-11).
     if (a.refine_vcycles > 0 && a.u0) {
-        double* u0 = a.u0 + (size_t)k * N;
+        double* u0 = a.u0 + (size_t)k * N;                            // slot order, like phi
         const double cl = 1. + 0.5 * g.delta, cr = 1. - 0.5 * g.delta;
-        // r into a register, U0 saved, then Source_0 <- r, Phi_0 <- 0 (all levels' Phi are re-zeroed by restriction)
-        for (int i = threadIdx.x; i < N; i += blockDim.x)
-            u0[i] = (i > 0 && i < N - 1) ? dd_residual(src[i], phi[i - 1], phi[i], phi[i + 1], cl, cr) : 0.;
-        __syncthreads();
-        for (int i = threadIdx.x; i < N; i += blockDim.x) {      // same thread owns node i in both passes
-            const double r = u0[i];
-            u0[i] = phi[i]; src[i] = r; phi[i] = 0.;
+        const Lay y0 = g_sm.lc[0].lay;
+        // r into scratch, U0 saved, then Source_0 <- r, Phi_0 <- 0 (all levels' Phi are re-zeroed by restriction)
+        for (int s = threadIdx.x; s < N; s += blockDim.x) {
+            const int i = unslot(s, y0);
+            u0[s] = (i > 0 && i < N - 1) ? dd_residual(src.ld(s), phi.ld(slot(i - 1, y0)), phi.ld(s), phi.ld(slot(i + 1, y0)), cl, cr) : 0.;
         }
         __syncthreads();
-        for (int it = 0; it < a.refine_vcycles; ++it) { h.to_coarse(0, c); h.to_fine(c, 0); }
-        h.block_begin();
-        for (int i = threadIdx.x; i < N; i += blockDim.x) phi[i] += u0[i];
+        for (int s = threadIdx.x; s < N; s += blockDim.x) {      // same thread owns slot s in both passes
+            const double r = u0[s];
+            u0[s] = phi.ld(s); src.st(s, r); phi.st(s, 0.);
+        }
+        __syncthreads();
+        for (int it = 0; it < a.refine_vcycles; ++it) cycle(ctl, 0, 0, nullptr);
+        block_begin(ctl);
+        for (int s = threadIdx.x; s < N; s += blockDim.x) phi.st(s, phi.ld(s) + u0[s]);
         __syncthreads();
     }
+    if (dbg && threadIdx.x == 0) dbg[96] += clock64() - t_start;
+    if (a.u_out) export_level0(a.u_out + (size_t)k * N, N);
+    if (dbg && threadIdx.x == 0) dbg[97] += clock64() - t_start;
     if (threadIdx.x == 0) {
-        if (a.work) atomicAdd(a.work, sm.updates);
+        if (a.work) atomicAdd(a.work, g_sm.updates);
         if (a.vcycles_used) a.vcycles_used[k] = used;
         if (a.last_err) a.last_err[k] = err;
     }
 }
 
-// doubles per shared-memory array (phi or src) for the coarse levels of an L-level hierarchy
-static int smem_doubles_for(const PoissonLevels& lv)
+// ---------------------------------------------------------------------------------------------------------
+// Dense operator of the coarse sub-cycle.  Thread j (1..31) runs the reference's sequence serially on the unit source
+// e_j of the 32-node level m = L - 5:  [3 sweeps, restrict] down to the coarsest level, 3 sweeps there, [prolong,
+// 3 sweeps] back up to level m (PoissonSolver.cpp:40-64, :110-157, :162-186), and stores the resulting Phi_m as
+// column j.  Depends on (L, delta) only: built once per grid.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void coarse_op_kernel(int L, double delta, double* G)
 {
-    int off = 0;
-    for (int l = 1; l < lv.L; ++l)
-        if (lv.size[l] - 1 <= kSmemLevelNodes) off += (level_slots(lv.size[l] - 1) + 3) & ~3;
-    return off;
+    const int j = threadIdx.x;
+    double phi[6][33], src[6][33];          // levels m .. m+4 (32, 16, 8, 4, 2 owned nodes)
+    const int m = L - 5;
+    for (int q = 0; q < 6; ++q) for (int i = 0; i < 33; ++i) { phi[q][i] = 0.; src[q][i] = 0.; }
+    if (j >= 1 && j < 32) src[0][j] = 1.;
+    auto sweep3 = [&](int q) {
+        const int n = 32 >> q;
+        const double d = delta * (double)(1 << (m + q));
+        const double a = 0.5 * (1. + 0.5 * d), b = 0.5 * (1. - 0.5 * d);
+        for (int sw = 0; sw < 3; ++sw)
+            for (int i = 1; i < n; ++i) phi[q][i] = fma(a, phi[q][i - 1], fma(b, phi[q][i + 1], 0.5 * src[q][i]));
+    };
+    for (int q = 0; q < 4; ++q) {
+        sweep3(q);
+        const int nc = 32 >> (q + 1);
+        const double dc = delta * (double)(1 << (m + q + 1));
+        for (int i = 0; i <= nc; ++i) {
+            double v = 0.;
+            if (i > 0 && i < nc) {
+                const double lft = phi[q][2 * i - 1], mid = phi[q][2 * i], rgt = phi[q][2 * i + 1];
+                v = 4. * (src[q][2 * i] + lft - 2. * mid + rgt) - dc * (rgt - lft);
+            }
+            phi[q + 1][i] = 0.;
+            src[q + 1][i] = v;
+        }
+    }
+    sweep3(4);
+    for (int q = 4; q > 0; --q) {
+        const int nc = 32 >> q;
+        for (int i = 0; i <= nc; ++i) {
+            const double c = phi[q][i];
+            phi[q - 1][2 * i] += c;
+            if (i > 0) phi[q - 1][2 * i - 1] += 0.5 * (phi[q][i - 1] + c);
+        }
+        sweep3(q - 1);
+    }
+    for (int i = 0; i < 32; ++i) G[j * 32 + i] = (j >= 1) ? phi[0][i] : 0.;
+}
+
+void launch_coarse_op(int L, double delta, double* G, cudaStream_t st)
+{
+    coarse_op_kernel<<<1, 32, 0, st>>>(L, delta, G);
+}
+
+// dynamic shared memory worth asking for: Source_0 plus every block level that fits (same greedy order as Hierarchy::setup)
+static int dyn_doubles_for(const PoissonLevels& lv)
+{
+    const int cap = kMaxDynBytes / (int)sizeof(double);
+    int avail = cap;
+    const int n0 = lv.size[0] - 1;
+    bool src0 = false;
+    if (n0 > kWarpLevelNodes && ((n0 + 4) & ~3) <= avail) { src0 = true; avail -= (n0 + 4) & ~3; }
+    for (int k = lv.L - 1; k >= 0; --k) {
+        const int nk = lv.size[k] - 1;
+        if (nk <= kWarpLevelNodes) continue;
+        const int one = (nk + 4) & ~3;
+        const int need = (k == 0 && src0) ? one : 2 * one;
+        if (need > avail) break;
+        avail -= need;
+    }
+    return cap - avail;
 }
 
 void launch_poisson_full(const GridDev& g, const PoissonLevels& lv, const PoissonArgs& a_in, cudaStream_t st)
 {
     PoissonArgs a = a_in;
-    a.smem_doubles = smem_doubles_for(lv);
-    const size_t bytes = (size_t)a.smem_doubles * 2 * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(poisson_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+    a.smem_doubles = dyn_doubles_for(lv);
+    const size_t bytes = (size_t)a.smem_doubles * sizeof(double);
+    static size_t attr_bytes = 0;
+    if (bytes > attr_bytes) { cudaFuncSetAttribute(poisson_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); attr_bytes = bytes; }
     poisson_full_kernel<<<a.n_dens, kPT, bytes, st>>>(g, lv, a);
 }
 
+// V-cycles as defined by the reference on given (Phi_0, Source_0) in natural node order: parity / microbench entry point
+// (every level is swept level by level: no dense coarse operator)
 __global__ void __launch_bounds__(kPT) poisson_vcycles_kernel(double delta, PoissonLevels lv, double* phi_all, double* src_all,
-                                                             int n_cycles, double* last_err)
+                                                             double* phi_nat, const double* src_nat, int smem_doubles, int n_cycles,
+                                                             double* last_err)
 {
-    __shared__ PoissonSmem sm;
     const int k = blockIdx.x;
-    if (threadIdx.x == 0) sm.updates = 0;
-    double* phi = phi_all + (size_t)k * lv.total;
-    double* src = src_all + (size_t)k * lv.total;
-    const int c = lv.L - 1;
-    Hierarchy h{ phi, src, nullptr, nullptr, lv, delta, sm, false };      // microbench / parity entry point: all levels in global memory
-    h.layout_smem();
+    const int N = lv.size[0];
+    hierarchy_setup(lv, delta, phi_all + (size_t)k * lv.total, src_all + (size_t)k * lv.total, smem_doubles, nullptr, nullptr);
+    Ctl ctl{ false };
+    import_level0(Ref::P(0), phi_nat + (size_t)k * N, nullptr, N);
+    import_level0(Ref::S(0), src_nat + (size_t)k * N, nullptr, N);
+    __syncthreads();
     double err = 0.;
-    for (int it = 0; it < n_cycles; ++it) {
-        h.to_coarse(0, c);
-        if (it == n_cycles - 1) err = h.to_fine_with_norm(c); else h.to_fine(c, 0);
-    }
-    h.block_begin();
+    for (int it = 0; it < n_cycles; ++it) err = cycle(ctl, 0, 0, it == n_cycles - 1 ? phi_nat + (size_t)k * N : nullptr);
+    block_begin(ctl);
+    export_level0(phi_nat + (size_t)k * N, N);
     if (threadIdx.x == 0 && last_err) last_err[k] = err;
 }
 
-void launch_poisson_vcycles(int L, double delta, const PoissonLevels& lv, int n_dens, double* phi, double* src, int n_cycles,
-                            double* last_err, cudaStream_t st)
+void launch_poisson_vcycles(const PoissonLevels& lv, double delta, int n_dens, double* phi, double* src, double* phi_nat,
+                            const double* src_nat, int n_cycles, double* last_err, cudaStream_t st)
 {
-    (void)L;
-    poisson_vcycles_kernel<<<n_dens, kPT, 0, st>>>(delta, lv, phi, src, n_cycles, last_err);
+    const int sd = dyn_doubles_for(lv);
+    const size_t bytes = (size_t)sd * sizeof(double);
+    static size_t attr_bytes = 0;
+    if (bytes > attr_bytes) { cudaFuncSetAttribute(poisson_vcycles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); attr_bytes = bytes; }
+    poisson_vcycles_kernel<<<n_dens, kPT, bytes, st>>>(delta, lv, phi, src, phi_nat, src_nat, sd, n_cycles, last_err);
 }
 
 }  // namespace dft

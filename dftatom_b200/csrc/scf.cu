@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(kAT) potential_energy_kernel(GridDev g, Poisso
     const AtomDev at = b.atoms[a];
     const int N = g.N;
     const double Z = (double)at.Z;
-    const double* U = b.phi + (size_t)a * lv.total;       // level 0 of the Poisson hierarchy = U(r) = r V_H
+    const double* U = b.U + (size_t)a * g.N;               // U(r) = r V_H, written by the Poisson solve in natural node order
     const double* rt = b.rhot + (size_t)a * N;
     const int ta = b.tab_of[2 * a], tb = b.tab_of[2 * a + 1];
     const double q = g.delta * g.delta * 0.25;
