@@ -244,23 +244,33 @@ __global__ void __launch_bounds__(128, 1) search_fused_kernel(GridDev g, const d
     double lo = -Z * Z - 1., hi = kTopEnergy;             // DFTAtom.cpp:407,499
     double ylog = 0.;
     long long steps = 0;
-    // Warm start: the predicate is monotone, so ANY ascending set of trial energies brackets the same root.  From the
-    // second SCF step on, the first round samples a geometric ladder around the previous step's eigenvalue
-    // (+-2.4e-13 ... +-8.4 Ha); a root outside the ladder just leaves the global bracket's far end in place.
+    int rounds = 0;
+    // Sampling.  The predicate is monotone, so ANY ascending set of trial energies brackets the same root; what the set
+    // looks like only decides how fast the bracket shrinks.  Two shapes are used:
+    //   uniform : K points that cut [lo, hi] into K + 1 equal parts (cold start, and whenever nothing better is known);
+    //   ladder  : a two-sided geometric ladder  c -+ eps g^m  (m = 0 .. K/2 - 1, outermost offset = R) around an estimate
+    //             c of the root.  Round 0 of SCF step >= 1 centres it on the previous step's eigenvalue; later rounds
+    //             centre it on the zero of y0(E) interpolated (inverse cubic Lagrange) through the samples next to the
+    //             sign change, with R = 4 |cubic - secant| as the trust radius.  A wrong estimate only leaves a wide
+    //             bracket (next round: uniform); a good one closes the bracket to 1e-12 in 2-3 rounds instead of ~6.
     const bool warm = warm_start && ss[k].pad == 1;
-    const double e_prev = ss[k].E;
+    bool ladder = warm;
+    double c_est = ss[k].E, radius = 8.4;
+    constexpr double kEps = 2.4e-13;
     for (int round = 0; round < 64 && bracket_open(lo, hi); ++round) {
         // point j of the round (j = 0..K-1, ascending in energy) lives in lane j % 32, slot j / 32
         double E[EPL];
+        const double lg = ladder ? log2(fmax(radius, 2. * kEps) / kEps) / (double)(K / 2 - 1) : 0.;
 #pragma unroll
         for (int e = 0; e < EPL; ++e) {
             const int j = e * 32 + lane;
-            E[e] = lo + (hi - lo) * ((double)(j + 1) / (double)(K + 1));
-            if (warm && round == 0) {
+            if (ladder) {
                 const int half = K / 2;
-                const int mstep = (j < half) ? (half - 1 - j) : (j - half);            // 0 = closest to e_prev
-                const double off = 2.4e-13 * exp2((double)mstep * (EPL == 1 ? 3.0 : 1.5));
-                E[e] = fmin(fmax((j < half) ? e_prev - off : e_prev + off, lo), hi);
+                const int mstep = (j < half) ? (half - 1 - j) : (j - half);            // 0 = closest to the estimate
+                const double off = kEps * exp2((double)mstep * lg);
+                E[e] = fmin(fmax((j < half) ? c_est - off : c_est + off, lo), hi);
+            } else {
+                E[e] = lo + (hi - lo) * ((double)(j + 1) / (double)(K + 1));
             }
         }
         FastOut<EPL> o;
@@ -270,10 +280,11 @@ __global__ void __launch_bounds__(128, 1) search_fused_kernel(GridDev g, const d
 #pragma unroll
             for (int e = 0; e < EPL; ++e) {
                 const LaneOut s = sweep_lane(g, atab, ob.l, E[e], ob.want);
-                o.cfull[e] = s.count_full; o.d_first[e] = s.d_first; o.y0_log2[e] = s.y0_log2;
+                o.cfull[e] = s.count_full; o.d_first[e] = s.d_first; o.y0_log2[e] = s.y0_log2; o.y0_pos[e] = s.y0_pos;
             }
         }
         steps += o.steps;
+        ++rounds;
         unsigned m_hi[EPL];
 #pragma unroll
         for (int e = 0; e < EPL; ++e) m_hi[e] = __ballot_sync(full, o.cfull[e] > ob.want + (o.d_first[e] < 0. ? 1 : 0));
@@ -296,6 +307,57 @@ __global__ void __launch_bounds__(128, 1) search_fused_kernel(GridDev g, const d
             if (hi_i < K && (hi_i >> 5) == e) e_hi = a_hi;
             if ((lm >> 5) == e) yl = a_y;
         }
+        // estimate of the root for the next round: zero of y0(E) through the samples around the sign change
+        ladder = false;
+        if (EPL == 1 && lo_i >= 0 && hi_i < K && e_lo < e_hi) {
+            double Ek[4], yk[4], lgv[4];
+            bool ok[4];
+            double ref = -INFINITY;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int idx = lo_i - 1 + q;
+                const int src_lane = min(max(idx, 0), 31);
+                Ek[q] = __shfl_sync(full, E[0], src_lane);
+                lgv[q] = __shfl_sync(full, o.y0_log2[0], src_lane);
+                yk[q] = __shfl_sync(full, o.y0_pos[0], src_lane) ? 1. : -1.;
+                ok[q] = idx >= 0 && idx < K && lgv[q] > -1e300 && lgv[q] < 1e300;
+                if (ok[q]) ref = fmax(ref, lgv[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) yk[q] = ok[q] ? yk[q] * exp2(lgv[q] - ref) : 0.;      // relative to the largest sample
+            // the bracket ends must be proper samples with opposite signs and distinct energies
+            if (ok[1] && ok[2] && yk[1] * yk[2] < 0. && Ek[1] < Ek[2]) {
+                const double E2 = Ek[1] - yk[1] * (Ek[2] - Ek[1]) / (yk[2] - yk[1]);          // secant
+                // outer points are usable when they extend the table monotonically in E and in y (inverse interpolation)
+                const bool use0 = ok[0] && Ek[0] < Ek[1] && (yk[0] - yk[1]) * (yk[1] - yk[2]) > 0.;
+                const bool use3 = ok[3] && Ek[3] > Ek[2] && (yk[2] - yk[3]) * (yk[1] - yk[2]) > 0.;
+                double Eh = E2;
+                if (use0 || use3) {
+                    double num = 0.;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const bool uq = (q == 0) ? use0 : (q == 3 ? use3 : true);
+                        if (!uq) continue;
+                        double w = Ek[q];
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            const bool ur = (r == 0) ? use0 : (r == 3 ? use3 : true);
+                            if (r == q || !ur) continue;
+                            w *= (0. - yk[r]) / (yk[q] - yk[r]);
+                        }
+                        num += w;
+                    }
+                    Eh = num;
+                }
+                if (!(Eh > e_lo && Eh < e_hi)) Eh = E2;
+                if (Eh > e_lo && Eh < e_hi) {
+                    c_est = Eh;
+                    const double trust = (use0 || use3) ? 4. * fabs(Eh - E2) : 0.25 * (e_hi - e_lo);
+                    radius = fmin(fmax(trust, 16. * kEps), fmax(e_hi - Eh, Eh - e_lo));
+                    ladder = true;
+                }
+            }
+        }
         lo = e_lo; hi = e_hi; ylog = yl;
     }
     if (lane == 0) {
@@ -310,7 +372,11 @@ __global__ void __launch_bounds__(128, 1) search_fused_kernel(GridDev g, const d
     if (work) {
 #pragma unroll
         for (int o = 16; o; o >>= 1) steps += __shfl_xor_sync(full, steps, o);
-        if (lane == 0) atomicAdd(work, (unsigned long long)steps);
+        if (lane == 0) {
+            atomicAdd(work, (unsigned long long)steps);
+            atomicAdd(work + DFTATOM_K_MATCH, 1ULL);                          // orbital solves
+            atomicAdd(work + DFTATOM_K_DENSITY, (unsigned long long)rounds);  // search rounds
+        }
     }
 }
 

@@ -317,6 +317,237 @@ __device__ __noinline__ void visit_warp(int l, int sweeps)
     __syncwarp();
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Fused visits.  Restriction and prolongation only need the thread's own nodes plus one halo value (owner-major layout,
+// coarse node i <-> fine node 2i belong to the same thread), so they are folded into the visit that has the level in
+// registers anyway:
+//   kLoadPhi     : Phi_l starts from memory (otherwise from zero: a level entered by restriction)
+//   kProlongIn   : Phi_l += P Phi_{l+1} before sweeping                      (Prolong, PoissonSolver.cpp:110-123)
+//   kRestrictOut : after sweeping, Source_{l+1} = 4 R (residual) (- d_{l+1} first-difference term); Phi_{l+1} is implicitly
+//                  zero: the visit of level l+1 that follows starts from zero   (Restrict, PoissonSolver.cpp:126-157)
+// A V-cycle is then one visit per level and leg, and a level costs one load and one store of Phi per visit instead of
+// the separate smoothing / restriction / prolongation passes.  An up-visit followed by the down-visit of the next cycle
+// on the same level is ONE visit with 6 sweeps (kLoadPhi | kProlongIn | kRestrictOut).
+// ---------------------------------------------------------------------------------------------------------
+enum { kLoadPhi = 1, kProlongIn = 2, kRestrictOut = 4 };
+
+template <int NPT, bool SRC_REGS>
+__device__ __noinline__ void fused_block(int l, int flags, int sweeps)
+{
+    const unsigned full = 0xffffffffu;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    constexpr int NC = NPT / 2;
+    const bool last_thr = (t == kPT - 1);
+    const LevelConst& lc = g_sm.lc[l];
+    const LevelConst& lcc = g_sm.lc[l + 1];
+    const double a = lc.a, bcoef = lc.bcoef;
+    const int n = NPT * kPT;
+    const Ref P = Ref::P(l), S = Ref::S(l);
+    double phi[NPT], src[SRC_REGS ? NPT : 1];
+    double right = 0.;
+    if (flags & kLoadPhi) {
+#pragma unroll
+        for (int k = 0; k < NPT; ++k) phi[k] = P.ld(k * kPT + t);
+        right = P.ld(n);
+    } else {
+#pragma unroll
+        for (int k = 0; k < NPT; ++k) phi[k] = 0.;
+    }
+    if (flags & kProlongIn) {
+        const Ref Pc = Ref::P(l + 1);
+        const Lay yc = lcc.lay;
+        double corr[NC + 1];
+#pragma unroll
+        for (int m = 0; m <= NC; ++m) corr[m] = Pc.ld(slot(t * NC + m, yc));      // m = NC: the right neighbour's first node (or the boundary)
+#pragma unroll
+        for (int m = 0; m < NC; ++m) {
+            phi[2 * m] += corr[m];
+            phi[2 * m + 1] += 0.5 * (corr[m] + corr[m + 1]);
+        }
+        right += Pc.ld(lcc.n);
+    }
+    if (SRC_REGS) {
+#pragma unroll
+        for (int k = 0; k < NPT; ++k) src[k] = 0.5 * S.ld(k * kPT + t);
+    }
+    const bool s_dyn = lc.ws == kDyn;
+    const int os = lc.os;
+    const double* gs = g_sm.gsrc + os;
+    double Am[5];
+    double Alane = 1.;                       // A^lane
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        Am[j] = (lane >= (1 << j) && j < lc.nsteps) ? lc.Ap[j] : 0.;
+        if ((lane >> j) & 1) Alane *= lc.Ap[j];
+    }
+    const double B = lc.B;
+    const int nsteps = lc.nsteps;
+    if (t == 0) g_sm.updates += (unsigned long long)sweeps * (unsigned long long)(n - 1);
+    double cin = 0.;
+    for (int sw = 0; sw < sweeps; ++sw) {
+        double nb = __shfl_down_sync(full, phi[0], 1);
+        if (lane == 0) g_sm.edge[w] = phi[0];
+        __syncthreads();
+        if (lane == 31 && w + 1 < (kPT >> 5)) nb = g_sm.edge[w + 1];
+        if (last_thr) nb = right;
+        double x = 0.;
+        if (SRC_REGS) {
+#pragma unroll
+            for (int k = 0; k < NPT; ++k) {
+                const double c = fma(bcoef, (k + 1 < NPT) ? phi[k + 1] : nb, src[k]);
+                x = (t == 0 && k == 0) ? phi[0] : fma(a, x, c);      // node 0 keeps its boundary value
+                phi[k] = x;
+            }
+        } else if (s_dyn) {
+#pragma unroll
+            for (int k = 0; k < NPT; ++k) {
+                const double c = fma(bcoef, (k + 1 < NPT) ? phi[k + 1] : nb, 0.5 * g_dyn[os + k * kPT + t]);
+                x = (t == 0 && k == 0) ? phi[0] : fma(a, x, c);
+                phi[k] = x;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < NPT; ++k) {
+                const double c = fma(bcoef, (k + 1 < NPT) ? phi[k + 1] : nb, 0.5 * gs[k * kPT + t]);
+                x = (t == 0 && k == 0) ? phi[0] : fma(a, x, c);
+                phi[k] = x;
+            }
+        }
+        double Pw = x;
+        Pw = fma(Am[0], __shfl_up_sync(full, Pw, 1), Pw);
+        if (nsteps > 1) {
+            Pw = fma(Am[1], __shfl_up_sync(full, Pw, 2), Pw);
+            if (nsteps > 2) {
+                Pw = fma(Am[2], __shfl_up_sync(full, Pw, 4), Pw);
+                Pw = fma(Am[3], __shfl_up_sync(full, Pw, 8), Pw);
+                Pw = fma(Am[4], __shfl_up_sync(full, Pw, 16), Pw);
+            }
+        }
+        if (lane == 31) g_sm.wtot[w] = Pw;
+        __syncthreads();
+        double carry = 0.;
+        {
+            double bp = 1.;
+            for (int k = 1; k <= w && bp >= kTiny; ++k) { carry = fma(bp, g_sm.wtot[w - k], carry); bp *= B; }
+        }
+        double Pex = __shfl_up_sync(full, Pw, 1);
+        if (lane == 0) Pex = 0.;
+        cin = fma(Alane, carry, Pex);                           // new value of the node before this thread's first node
+        if (t == 0) cin = 0.;
+        double q = a;
+#pragma unroll
+        for (int k = 0; k < NPT; ++k) { phi[k] = fma(q, cin, phi[k]); q *= a; }
+    }
+#pragma unroll
+    for (int k = 0; k < NPT; ++k) P.st(k * kPT + t, phi[k]);
+    if (t == 0) P.st(n, right);
+    if (flags & kRestrictOut) {
+        const Ref Sc = Ref::S(l + 1);
+        const Lay yc = lcc.lay;
+        const double dc = lcc.d;
+#pragma unroll
+        for (int m = 0; m < NC; ++m) {
+            const int k = 2 * m;
+            const double lft = (m == 0) ? cin : phi[k - 1], mid = phi[k], rgt = phi[k + 1];
+            const double sv = SRC_REGS ? 2. * src[k] : S.ld(k * kPT + t);
+            double v = 4. * (sv + lft - 2. * mid + rgt) - dc * (rgt - lft);
+            if (t == 0 && m == 0) v = 0.;
+            Sc.st(slot(t * NC + m, yc), v);
+        }
+        if (t == 0) Sc.st(lcc.n, 0.);
+    }
+    __syncthreads();
+}
+
+// the same for the levels run by warp 0 (T = 32, static shared memory, 64 <= n <= 1024, NPT = n / 32)
+template <int NPT, bool SRC_REGS>
+__device__ __noinline__ void fused_warp(int l, int flags, int sweeps)
+{
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    constexpr int NC = NPT / 2;
+    const LevelConst& lc = g_sm.lc[l];
+    const LevelConst& lcc = g_sm.lc[l + 1];
+    const int n = NPT * 32, op = lc.op, os = lc.os, opc = lcc.op, osc = lcc.os;
+    const double a = lc.a, bcoef = lc.bcoef;
+    double phi[NPT], src[SRC_REGS ? NPT : 1];
+    double right = 0.;
+    if (flags & kLoadPhi) {
+#pragma unroll
+        for (int k = 0; k < NPT; ++k) phi[k] = g_sm.w[op + k * 32 + lane];
+        right = g_sm.w[op + n];
+    } else {
+#pragma unroll
+        for (int k = 0; k < NPT; ++k) phi[k] = 0.;
+    }
+    if (flags & kProlongIn) {
+        // coarse level: NC nodes per lane (NC >= 1), owner-major with T = 32: node lane NC + m at slot m 32 + lane
+        double corr[NC + 1];
+#pragma unroll
+        for (int m = 0; m < NC; ++m) corr[m] = g_sm.w[opc + m * 32 + lane];
+        corr[NC] = (lane == 31) ? g_sm.w[opc + lcc.n] : g_sm.w[opc + lane + 1];      // first node of the right neighbour / boundary
+#pragma unroll
+        for (int m = 0; m < NC; ++m) {
+            phi[2 * m] += corr[m];
+            phi[2 * m + 1] += 0.5 * (corr[m] + corr[m + 1]);
+        }
+        right += g_sm.w[opc + lcc.n];
+    }
+    if (SRC_REGS) {
+#pragma unroll
+        for (int k = 0; k < NPT; ++k) src[k] = 0.5 * g_sm.w[os + k * 32 + lane];
+    }
+    double Am[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) Am[j] = (lane >= (1 << j) && j < lc.nsteps) ? lc.Ap[j] : 0.;
+    const int nsteps = lc.nsteps;
+    if (lane == 0) g_sm.updates += (unsigned long long)sweeps * (unsigned long long)(n - 1);
+    double cin = 0.;
+    for (int sw = 0; sw < sweeps; ++sw) {
+        double nb = __shfl_down_sync(full, phi[0], 1);
+        if (lane == 31) nb = right;
+        double x = 0.;
+#pragma unroll
+        for (int k = 0; k < NPT; ++k) {
+            const double c = fma(bcoef, (k + 1 < NPT) ? phi[k + 1] : nb, SRC_REGS ? src[k] : 0.5 * g_sm.w[os + k * 32 + lane]);
+            x = (lane == 0 && k == 0) ? phi[0] : fma(a, x, c);
+            phi[k] = x;
+        }
+        double Pw = x;
+        Pw = fma(Am[0], __shfl_up_sync(full, Pw, 1), Pw);
+        if (nsteps > 1) {
+            Pw = fma(Am[1], __shfl_up_sync(full, Pw, 2), Pw);
+            if (nsteps > 2) {
+                Pw = fma(Am[2], __shfl_up_sync(full, Pw, 4), Pw);
+                Pw = fma(Am[3], __shfl_up_sync(full, Pw, 8), Pw);
+                Pw = fma(Am[4], __shfl_up_sync(full, Pw, 16), Pw);
+            }
+        }
+        cin = __shfl_up_sync(full, Pw, 1);
+        if (lane == 0) cin = 0.;
+        double q = a;
+#pragma unroll
+        for (int k = 0; k < NPT; ++k) { phi[k] = fma(q, cin, phi[k]); q *= a; }
+    }
+#pragma unroll
+    for (int k = 0; k < NPT; ++k) g_sm.w[op + k * 32 + lane] = phi[k];
+    if (lane == 0) g_sm.w[op + n] = right;
+    if (flags & kRestrictOut) {
+        const double dc = lcc.d;
+#pragma unroll
+        for (int m = 0; m < NC; ++m) {
+            const int k = 2 * m;
+            const double lft = (m == 0) ? cin : phi[k - 1], mid = phi[k], rgt = phi[k + 1];
+            const double sv = SRC_REGS ? 2. * src[k] : g_sm.w[os + k * 32 + lane];
+            double v = 4. * (sv + lft - 2. * mid + rgt) - dc * (rgt - lft);
+            if (lane == 0 && m == 0) v = 0.;
+            g_sm.w[osc + m * 32 + lane] = v;
+        }
+        if (lane == 0) g_sm.w[osc + lcc.n] = 0.;
+    }
+    __syncwarp();
+}
+
 // Restrict, PoissonSolver.cpp:126-157: coarse slots are walked in storage order (coalesced); the three fine nodes of a
 // coarse node belong to the same thread's chunk (plus one halo node of the left neighbour)
 __device__ __forceinline__ void restrict_nodes(Ref pf, Ref sf, Lay yf, Ref pc, Ref sc, Lay yc, int nc, double dc, int tid, int nthr)
@@ -526,6 +757,7 @@ __device__ __noinline__ void dense_apply_warp()
         a3 = fma(g_sm.G[(j + 3) * 32 + i], g_sm.w[c.os + j + 3], a3);
     }
     g_sm.w[c.op + i] = (a0 + a1) + (a2 + a3);      // row 0 of G is zero: the left boundary stays 0
+    if (i == 0) g_sm.w[c.op + 32] = 0.;            // a level entered by restriction has zero boundaries
     __syncwarp();
 }
 __device__ __forceinline__ void to_coarse(Ctl& ctl, int from, int to)      // "Ascend", PoissonSolver.cpp:162-171
@@ -571,6 +803,79 @@ __device__ __noinline__ double cycle(Ctl& ctl, int from, int to, double* norm_sc
     for (int s = threadIdx.x; s < N; s += blockDim.x) { const double dif = norm_scratch[s] - p0.ld(s); e2 = fma(dif, dif, e2); }
     return sqrt(block_sum(e2));
 }
+// is level l run by a fused visit?  (single-chunk block levels and warp levels down to 64 nodes, all above the dense level m)
+__device__ __forceinline__ bool fused_level(int l)
+{
+    const int n = g_sm.lc[l].n;
+    return g_sm.has_G && l < g_sm.m && n <= kPT * kMaxNpt && n >= 64;
+}
+__device__ __noinline__ void fused_visit_block(int l, int flags, int sweeps)
+{
+    const long long t0 = g_sm.dbg ? clock64() : 0;
+    switch (g_sm.lc[l].lay.lg) {
+        case 5: fused_block<32, false>(l, flags, sweeps); break;
+        case 4: fused_block<16, true>(l, flags, sweeps); break;
+        case 3: fused_block<8, true>(l, flags, sweeps); break;
+        default: fused_block<4, true>(l, flags, sweeps); break;
+    }
+    if (g_sm.dbg && threadIdx.x == 0) { g_sm.dbg[l] += clock64() - t0; g_sm.dbg[72 + l] += 1; }
+}
+__device__ __noinline__ void fused_visit_warp(int l, int flags, int sweeps)
+{
+    const long long t0 = g_sm.dbg ? clock64() : 0;
+    switch (g_sm.lc[l].lay.lg) {
+        case 5: fused_warp<32, false>(l, flags, sweeps); break;
+        case 4: fused_warp<16, true>(l, flags, sweeps); break;
+        case 3: fused_warp<8, true>(l, flags, sweeps); break;
+        case 2: fused_warp<4, true>(l, flags, sweeps); break;
+        default: fused_warp<2, true>(l, flags, sweeps); break;
+    }
+    if (g_sm.dbg && threadIdx.x == 0) { g_sm.dbg[l] += clock64() - t0; g_sm.dbg[72 + l] += 1; }
+}
+// one level visit of a cycle, fused where possible, otherwise spelled out with the generic operators
+__device__ __forceinline__ void visit(Ctl& ctl, int l, int flags, int sweeps)
+{
+    if (fused_level(l)) {
+        if (g_sm.lc[l].wp == kWarp) {
+            if (threadIdx.x < 32) fused_visit_warp(l, flags, sweeps);
+            ctl.pending = true;
+        } else {
+            block_begin(ctl);
+            fused_visit_block(l, flags, sweeps);
+        }
+        return;
+    }
+    // generic: the level arrays in memory are complete (Phi_l zeroed by the restriction that entered the level)
+    if (flags & kProlongIn) prolong_from(ctl, l + 1);
+    smooth(ctl, l, sweeps);
+    if (flags & kRestrictOut) restrict_to(ctl, l + 1);
+}
+// The cycles  to_coarse(tops[q], c); to_fine(c, tops[q+1])  for the chain of top levels
+//     first, first-1, ..., 1, 0, 0, ..., 0   (n_v times 0 -> 0 at the end),
+// entered with Phi_first holding the result of the previous ascent (3 sweeps done) and left after the last ascent.
+// Tops in the middle of the chain are one visit: prolong in, 3 + 3 sweeps, restrict out.
+__device__ __noinline__ void cycle_chain(Ctl& ctl, int first, int n_v)
+{
+    const int m = g_sm.m;
+    const int n_cycles = first + n_v;
+    int a = first;
+    bool top_done = false;               // the down-visit of level a was already part of the previous fused top
+    for (int q = 0; q < n_cycles; ++q) {
+        const int b = a > 0 ? a - 1 : 0;
+        const bool last = (q == n_cycles - 1);
+        for (int l = a; l < m; ++l) {
+            if (l == a && top_done) continue;
+            visit(ctl, l, (l == a ? kLoadPhi : 0) | kRestrictOut, 3);
+        }
+        if (threadIdx.x < 32) dense_apply_warp();
+        ctl.pending = true;
+        for (int l = m - 1; l > b; --l) visit(ctl, l, kLoadPhi | kProlongIn, 3);
+        if (last) { visit(ctl, b, kLoadPhi | kProlongIn, 3); top_done = false; }
+        else { visit(ctl, b, kLoadPhi | kProlongIn | kRestrictOut, 6); top_done = true; }
+        a = b;
+    }
+}
+
 // natural order <-> owner-major order of level 0
 __device__ __forceinline__ void import_level0(Ref dst, const double* nat, const double* scale, int N)
 {
@@ -634,6 +939,7 @@ __global__ void __launch_bounds__(kPT) poisson_full_kernel(GridDev g, PoissonLev
     if (a.rho) import_level0(src, a.rho + (size_t)k * N, g.psrc, N);
     else if (a.src_nat) import_level0(src, a.src_nat + (size_t)k * N, nullptr, N);
     const int n_cycles = a.warm_vcycles > 0 ? a.warm_vcycles : a.max_vcycles;
+    int fmg_top = 0;                     // top level the full-multigrid ramp has reached (0: only V-cycles are left)
     if (a.warm_vcycles > 0) {
         // Warm start (beyond the reference): Phi_0 still holds the previous solve of this density (same boundary values);
         // the V-cycles contract the difference ~25x each, so a few of them reach the same FP64 fixed point as the full cycle
@@ -662,23 +968,31 @@ __global__ void __launch_bounds__(kPT) poisson_full_kernel(GridDev g, PoissonLev
         smooth(ctl, c, 2);     // the coarsest level has one interior node: the reference's <= 15 sweeps converge in one
         // to_fine(c, l), to_coarse(l, c) for l = L-2 .. 1, then to_fine(c, 0)
         to_fine(ctl, c, L - 2);
-        for (int l = L - 2; l > 0; --l) cycle(ctl, l, l - 1, nullptr);
+        fmg_top = L - 2;
     }
-    const bool want_norm = (a.floor_stop || a.last_err || a.vcycles_used) && a.u_out != nullptr;
+    const bool want_norm = (a.floor_stop || a.last_err) && a.u_out != nullptr;
     double* scratch = want_norm ? a.u_out + (size_t)k * N : nullptr;      // overwritten by the export below
     double err = 0., prev = 1e300;
     int used = 0, stagnant = 0;
-    for (int it = 0; it < n_cycles; ++it) {
-        const bool last = (it == n_cycles - 1);
-        ++used;
-        if (want_norm && (last || a.floor_stop)) {
-            err = cycle(ctl, 0, 0, scratch);
-            if (err < 1e-14) break;                                   // PoissonSolver.h:120
-            // the update norm contracts ~25x per cycle until it reaches its FP64 rounding floor
-            if (a.floor_stop) { if (err > 0.25 * prev) { if (++stagnant >= 2) break; } else stagnant = 0; }
-            prev = err;
-        } else {
-            cycle(ctl, 0, 0, nullptr);
+    // the ramp cycles whose top level is at or below the dense level are run level by level
+    while (fmg_top > 0 && !(g_sm.has_G && fmg_top < g_sm.m)) { cycle(ctl, fmg_top, fmg_top - 1, nullptr); --fmg_top; }
+    if (g_sm.has_G && !want_norm) {
+        cycle_chain(ctl, fmg_top, n_cycles);          // the rest of the ramp and the V-cycles, fused visits
+        used = n_cycles;
+    } else {
+        for (; fmg_top > 0; --fmg_top) cycle(ctl, fmg_top, fmg_top - 1, nullptr);
+        for (int it = 0; it < n_cycles; ++it) {
+            const bool last = (it == n_cycles - 1);
+            ++used;
+            if (want_norm && (last || a.floor_stop)) {
+                err = cycle(ctl, 0, 0, scratch);
+                if (err < 1e-14) break;                                   // PoissonSolver.h:120
+                // the update norm contracts ~25x per cycle until it reaches its FP64 rounding floor
+                if (a.floor_stop) { if (err > 0.25 * prev) { if (++stagnant >= 2) break; } else stagnant = 0; }
+                prev = err;
+            } else {
+                cycle(ctl, 0, 0, nullptr);
+            }
         }
     }
     block_begin(ctl);

@@ -125,6 +125,8 @@ int dftatom_last_timing(dftatom_ctx* ctx, double* device_ms, long long* kernel_l
  * every launch of the class (CUDA events on the launching stream), launch count and algorithmic work
  * (class 0: Numerov (lane, node-step) pairs; class 3: Gauss-Seidel node-updates; others: 0). */
 enum { DFTATOM_K_SEARCH = 0, DFTATOM_K_MATCH = 1, DFTATOM_K_DENSITY = 2, DFTATOM_K_POISSON = 3, DFTATOM_K_POTENTIAL = 4, DFTATOM_K_COUNT = 5 };
+/* work: search = (lane, node-step) pairs of the shooting sweeps; match = orbital solves; density = search rounds summed over the
+   orbital solves; poisson = Gauss-Seidel node updates; potential = 0 */
 typedef struct { double ms; long long launches; double work; } dftatom_kernel_profile;
 int dftatom_last_profile(dftatom_ctx* ctx, dftatom_kernel_profile* out /* [DFTATOM_K_COUNT] */);
 /* measured FP64 FMA peak of the device (TFLOP/s, 2 flops per DFMA), the roofline denominator of the shooting kernel */

@@ -15,7 +15,8 @@ opts = [D.Options(a["options"]["Z"], a["options"]["levels"], a["options"]["rmax"
 t0 = time.time()
 res = ctx.solve_batch(opts)
 print("wall", time.time() - t0, "dev ms", ctx.last_timing())
-print("profile", {k: round(v["ms"], 1) for k, v in ctx.last_profile().items()})
+pr = ctx.last_profile()
+print("profile", {k: round(v["ms"], 1) for k, v in pr.items()}, "orbital solves", pr["match"]["work"], "rounds/solve", pr["density"]["work"] / max(1, pr["match"]["work"]))
 worst_e = worst_t = 0
 for r, a in zip(res, g):
     nref = a.get("n_steps", len(a["steps"]))
