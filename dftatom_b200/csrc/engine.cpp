@@ -52,7 +52,8 @@ struct dftatom_ctx {
     int refine_vcycles = 0;
     int warm_vcycles = 0;      // Poisson warm start from SCF step warm_after on (0 = off)
     int warm_after = 3;
-    int r_segments = 0;
+    int r_segments = 32;       // radial segments per orbital of the parallel-in-r search (<= 1: serial-in-r search only)
+    int seg_threshold = 300;   // the parallel-in-r search takes over once at most this many orbitals are still active
     int profile = 0;
     int search_mode = 0;
     int match_mode = 0;
@@ -186,6 +187,7 @@ int dftatom_set_option(dftatom_ctx* c, const char* key, double value)
     else if (k == "warm_vcycles") c->warm_vcycles = std::max(0, (int)value);
     else if (k == "warm_after") c->warm_after = std::max(0, (int)value);
     else if (k == "r_segments") c->r_segments = (int)value;
+    else if (k == "seg_threshold") c->seg_threshold = (int)value;
     else if (k == "profile") c->profile = value != 0.;
     else if (k == "search_mode") c->search_mode = (int)value;
     else if (k == "match_mode") c->match_mode = (int)value;
@@ -320,10 +322,11 @@ int dftatom_solve_batch(dftatom_ctx* c, const dftatom_options* opts, int n_atoms
     if ((rc = c->u0.ensure(sizeof(double) * (size_t)n_atoms * N))) return rc;
     if ((rc = c->ubuf.ensure(sizeof(double) * (size_t)n_atoms * N))) return rc;
     if ((rc = c->steps.ensure(sizeof(dftatom_step) * (size_t)n_atoms * stride))) return rc;
-    if ((rc = c->n_active.ensure(sizeof(int)))) return rc;
+    if ((rc = c->n_active.ensure(sizeof(int) * 2))) return rc;
     DFT_CHECK(cudaMemsetAsync(c->steps.p, 0, sizeof(dftatom_step) * (size_t)n_atoms * stride, st));
     DFT_CHECK(cudaMemsetAsync(c->ss.p, 0, sizeof(SearchState) * (size_t)n_orbs, st));
-    DFT_CHECK(cudaMemcpyAsync(c->n_active.p, &n_atoms, sizeof(int), cudaMemcpyHostToDevice, st));
+    const int h_counts[2] = { n_atoms, n_orbs };        // atoms / orbitals still iterating, kept up to date by potential_energy_kernel
+    DFT_CHECK(cudaMemcpyAsync(c->n_active.p, h_counts, sizeof(int) * 2, cudaMemcpyHostToDevice, st));
 
     ScfBuffers b{};
     b.n_atoms = n_atoms; b.n_orbs = n_orbs; b.n_tabs = n_tabs; b.N = N;
@@ -370,8 +373,16 @@ int dftatom_solve_batch(dftatom_ctx* c, const dftatom_options* opts, int n_atoms
     for (int sp = 0; sp < max_steps; ++sp) {
         begin_span(DFTATOM_K_SEARCH);
         if (c->search_mode == 0) {
-            launch_search_fused(g, b.atab, b.atoms, b.orbs, b.astate, b.ss, n_orbs, d_work + DFTATOM_K_SEARCH, c->energies_per_lane, c->warm_start, st);
+            // two shapes of the same search: serial-in-r (one warp per orbital) while many orbitals are active, parallel-in-r
+            // (one cluster per orbital) once few are left.  Both are enqueued; the device-side count of active orbitals
+            // decides which one runs (the other returns at once), so the host never has to know.
+            const int thr = c->r_segments > 1 ? c->seg_threshold : -1;
+            launch_search_fused(g, b.atab, b.atoms, b.orbs, b.astate, b.ss, n_orbs, d_work + DFTATOM_K_SEARCH, b.n_active + 1, thr, c->warm_start, st);
             ++launches;
+            if (c->r_segments > 1) {
+                launch_search_seg(g, b.atab, b.atoms, b.orbs, b.astate, b.ss, n_orbs, d_work + DFTATOM_K_SEARCH, c->r_segments, b.n_active + 1, thr, c->warm_start, st);
+                ++launches;
+            }
         } else {
             launch_search_init(g, b.atoms, b.astate, b.orbs, b.ss, n_orbs, st); ++launches;
         }
@@ -415,7 +426,7 @@ int dftatom_solve_batch(dftatom_ctx* c, const dftatom_options* opts, int n_atoms
             float t = 0.f;
             cudaEventElapsedTime(&t, s.a, s.b);
             c->prof[s.cls].ms += t;
-            c->prof[s.cls].launches += (s.cls == DFTATOM_K_SEARCH) ? (c->search_mode == 0 ? 1 : rounds + 1) : 1;
+            c->prof[s.cls].launches += (s.cls == DFTATOM_K_SEARCH) ? (c->search_mode == 0 ? (c->r_segments > 1 ? 2 : 1) : rounds + 1) : 1;
             cudaEventDestroy(s.a); cudaEventDestroy(s.b);
         }
     }
@@ -532,7 +543,8 @@ int dftatom_level_search(dftatom_ctx* c, const double* V, int levels, double del
     if ((rc = setup_single(c, g, V, Z, orbs, &da, &ds, &dorb, &dss, &datab))) return rc;
     launch_search_init(g, da, ds, dorb, dss, n_levels, st);
     const int rounds = search_rounds_needed(Z);
-    if (c->search_mode == 0) launch_search_fused(g, datab, da, dorb, ds, dss, n_levels, nullptr, c->energies_per_lane, 0, st);
+    if (c->search_mode == 0 && c->r_segments > 1) launch_search_seg(g, datab, da, dorb, ds, dss, n_levels, nullptr, c->r_segments, nullptr, 0, 0, st);
+    else if (c->search_mode == 0) launch_search_fused(g, datab, da, dorb, ds, dss, n_levels, nullptr, nullptr, 0, 0, st);
     else for (int r = 0; r < rounds; ++r) launch_search_round(g, datab, dorb, ds, dss, n_levels, nullptr, st);
     std::vector<SearchState> h(n_levels);
     DFT_CHECK(cudaMemcpyAsync(h.data(), dss, sizeof(SearchState) * n_levels, cudaMemcpyDeviceToHost, st));

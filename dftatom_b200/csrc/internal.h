@@ -97,8 +97,14 @@ void launch_search_init(const GridDev& g, const AtomDev* atoms, const AtomState*
 void launch_search_round(const GridDev& g, const double* atab, const OrbitalDev* orbs, const AtomState* astate, SearchState* ss,
                          int n_orbs, unsigned long long* work, cudaStream_t st);
 void launch_numerov_lanes_fast(const GridDev& g, const NumerovLaneArgs& a, cudaStream_t st);
+// n_active_orbs (device, may be NULL) and threshold select between the two search kernels on the device: the serial-in-r
+// kernel runs while *n_active_orbs > threshold, the parallel-in-r kernel once *n_active_orbs <= threshold
 void launch_search_fused(const GridDev& g, const double* atab, const AtomDev* atoms, const OrbitalDev* orbs, const AtomState* astate,
-                         SearchState* ss, int n_orbs, unsigned long long* work, int epl, int warm_start, cudaStream_t st);
+                         SearchState* ss, int n_orbs, unsigned long long* work, const int* n_active_orbs, int threshold, int warm_start,
+                         cudaStream_t st);
+void launch_search_seg(const GridDev& g, const double* atab, const AtomDev* atoms, const OrbitalDev* orbs, const AtomState* astate,
+                       SearchState* ss, int n_orbs, unsigned long long* work, int segments, const int* n_active_orbs, int threshold,
+                       int warm_start, cudaStream_t st);
 void launch_dfma_peak(double* out, int blocks, int threads, int iters, cudaStream_t st);
 int search_rounds_needed(int Zmax);
 

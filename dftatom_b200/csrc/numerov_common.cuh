@@ -113,4 +113,101 @@ __device__ __forceinline__ bool bracket_open(double lo, double hi)
     return (hi - lo > kEnergyTol) && (0.5 * (lo + hi) != lo) && (0.5 * (lo + hi) != hi);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Energy search of one level: sampling of the trial energies and bracket update, shared by the search kernels.
+// One round = 32 trial energies (one per lane, ascending in energy) + the monotone predicate
+//     Q(E) = [full sign-change count of the inward solution > wanted node count]
+// evaluated on each.  The predicate is monotone, so ANY ascending set of trial energies brackets the same root; what
+// the set looks like only decides how fast the bracket shrinks.  Two shapes are used:
+//   uniform : 32 points that cut [lo, hi] into 33 equal parts (cold start, and whenever nothing better is known);
+//   ladder  : a two-sided geometric ladder  c -+ eps g^m  (m = 0 .. 15, outermost offset = R) around an estimate c of
+//             the root.  Round 0 of SCF step >= 1 centres it on the previous step's eigenvalue; later rounds centre
+//             it on the zero of y0(E) interpolated (inverse cubic Lagrange) through the samples next to the sign
+//             change, with R = 4 |cubic - secant| as the trust radius.  A wrong estimate only leaves a wide bracket
+//             (next round: uniform); a good one closes the bracket to 1e-12 in 2-3 rounds instead of ~6 (33-section)
+//             or ~140 serial sweeps (the reference's three bisections, DFTAtom.cpp:513-604).
+// ---------------------------------------------------------------------------------------------------------
+struct Bracket {
+    double lo, hi;          // the root is in (lo, hi]
+    double c_est, radius;   // ladder centre and outermost offset
+    double ylog;            // log2 |y0| of the last virtual-bisection midpoint (1e15 guard, DFTAtom.cpp:528)
+    bool ladder;
+};
+constexpr double kLadderEps = 2.4e-13;
+
+__device__ __forceinline__ double sample_energy(const Bracket& b, int lane)
+{
+    if (b.ladder) {
+        const double lg = log2(fmax(b.radius, 2. * kLadderEps) / kLadderEps) * (1. / 15.);
+        const int mstep = (lane < 16) ? (15 - lane) : (lane - 16);            // 0 = closest to the estimate
+        const double off = kLadderEps * exp2((double)mstep * lg);
+        return fmin(fmax((lane < 16) ? b.c_est - off : b.c_est + off, b.lo), b.hi);
+    }
+    return b.lo + (b.hi - b.lo) * ((double)(lane + 1) * (1. / 33.));
+}
+
+// warp-collective: every lane passes its own trial energy and results; all lanes end with the same bracket
+__device__ __forceinline__ void update_bracket(Bracket& b, double E, bool high, int y0_pos, double y0_log2)
+{
+    const unsigned full = 0xffffffffu;
+    const unsigned m_hi = __ballot_sync(full, high);
+    int lo_i, hi_i, lm;
+    virtual_bisect(m_hi, 32, lo_i, hi_i, lm);
+    const double a_lo = __shfl_sync(full, E, max(lo_i, 0)), a_hi = __shfl_sync(full, E, min(hi_i, 31));
+    const double e_lo = lo_i >= 0 ? a_lo : b.lo, e_hi = hi_i < 32 ? a_hi : b.hi;
+    b.ylog = __shfl_sync(full, y0_log2, lm);
+    b.ladder = false;
+    // estimate of the root for the next round: zero of y0(E) through the samples around the sign change
+    if (lo_i >= 0 && hi_i < 32 && e_lo < e_hi) {
+        double Ek[4], yk[4], lgv[4];
+        bool ok[4];
+        double ref = -INFINITY;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int idx = lo_i - 1 + q;
+            const int src_lane = min(max(idx, 0), 31);
+            Ek[q] = __shfl_sync(full, E, src_lane);
+            lgv[q] = __shfl_sync(full, y0_log2, src_lane);
+            yk[q] = __shfl_sync(full, y0_pos, src_lane) ? 1. : -1.;
+            ok[q] = idx >= 0 && idx < 32 && lgv[q] > -1e300 && lgv[q] < 1e300;
+            if (ok[q]) ref = fmax(ref, lgv[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) yk[q] = ok[q] ? yk[q] * exp2(lgv[q] - ref) : 0.;      // relative to the largest sample
+        // the bracket ends must be proper samples with opposite signs and distinct energies
+        if (ok[1] && ok[2] && yk[1] * yk[2] < 0. && Ek[1] < Ek[2]) {
+            const double E2 = Ek[1] - yk[1] * (Ek[2] - Ek[1]) / (yk[2] - yk[1]);          // secant
+            // outer points are usable when they extend the table monotonically in E and in y (inverse interpolation)
+            const bool use0 = ok[0] && Ek[0] < Ek[1] && (yk[0] - yk[1]) * (yk[1] - yk[2]) > 0.;
+            const bool use3 = ok[3] && Ek[3] > Ek[2] && (yk[2] - yk[3]) * (yk[1] - yk[2]) > 0.;
+            double Eh = E2;
+            if (use0 || use3) {
+                double num = 0.;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const bool uq = (q == 0) ? use0 : (q == 3 ? use3 : true);
+                    if (!uq) continue;
+                    double wgt = Ek[q];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const bool ur = (r == 0) ? use0 : (r == 3 ? use3 : true);
+                        if (r == q || !ur) continue;
+                        wgt *= (0. - yk[r]) / (yk[q] - yk[r]);
+                    }
+                    num += wgt;
+                }
+                Eh = num;
+            }
+            if (!(Eh > e_lo && Eh < e_hi)) Eh = E2;
+            if (Eh > e_lo && Eh < e_hi) {
+                b.c_est = Eh;
+                const double trust = (use0 || use3) ? 4. * fabs(Eh - E2) : 0.25 * (e_hi - e_lo);
+                b.radius = fmin(fmax(trust, 16. * kLadderEps), fmax(e_hi - Eh, Eh - e_lo));
+                b.ladder = true;
+            }
+        }
+    }
+    b.lo = e_lo; b.hi = e_hi;
+}
+
 }  // namespace dft

@@ -1,0 +1,204 @@
+// Parallel-in-r Numerov shooting: the energy search of one level by a whole CTA.
+//
+// Replaces the same reference code as numerov_fast.cu (DFTAtom.cpp:493-541, :566-604; Numerov.h:272-401) with the same
+// search (numerov_common.cuh: Bracket), but one thread-block CLUSTER per orbital: warp s of the cluster = radial segment s
+// (counted from the far end), lane = trial energy.  The CTAs of a cluster (4 warps each) sit on different SMs, so the
+// segments of one orbital get several FP64 pipes (a B200 SM issues one FP64 warp-instruction per 2 cycles and scheduler:
+// 32 warps on ONE SM would be throughput-bound again); the per-segment results are exchanged through distributed
+// shared memory.  One inward sweep of N nodes is a chain of N dependent steps; cut into S segments it becomes
+//   pass 1  every (segment, energy) pushes the two basis states (W, D) = (1, 0), (0, 1) through its segment of the
+//           three-term recurrence: the segment's 2x2 transfer matrix.  The segment that contains the far seeds of an
+//           energy (Numerov.h:294-303) runs the real solution instead; segments beyond the seeds are idle;
+//   scan    the S maps of an energy are applied in order (shared memory), which gives every segment its entry state;
+//   pass 2  every segment re-runs from its entry state and counts the sign changes of y (the Sturm count).
+// 2.25x the arithmetic of the serial sweep, 2/S of its depth: this is the kernel for few active orbitals (late SCF
+// steps, small batches), where the serial sweep leaves the GPU idle and the step time is pure latency.
+// The recurrence is the scaled difference form of numerov_fast.cu:
+//   g = f/12, d = 1 - g, s_i = 1 - d_i d_{i+1},  D_i = D_{i+1} + 10 g_i W_i + s_i W_{i+1},  W_{i-1} = W_i + D_i,
+//   y_i = W_i / (P_i d_i), P_i = prod_{j>i} d_j > 0.
+#include "numerov_sweep.cuh"
+#include <cooperative_groups.h>
+#include <cstdio>
+
+namespace cg = cooperative_groups;
+
+namespace dft {
+
+constexpr int kSegMax = 32;        // segments per orbital = 4 warps x cluster size (<= 8 CTAs: the portable maximum)
+constexpr int kSegWarps = 4;       // warps (segments) per CTA
+
+struct SegShared {                 // one per CTA: the results of its 4 segments; y0s / d1 / bad are used in the rank-0 CTA only
+    double m[4][kSegWarps][32];    // normal: transfer matrix (ww, wd, dw, dd); seeded: outgoing state (W, D) in [0], [1]
+    double pseg[kSegWarps][32];    // product of d_i d_{i+1} over the even nodes of the segment (nodes <= start)
+    double y0s[32], d1[32];        // bottom segment: scaled y0 and d_1 per energy
+    int meta[kSegWarps][32];       // kind (bits 0-1: 0 idle, 1 normal, 2 seeded) | sign of y at the lowest node (bit 2) | sign changes inside the segment << 3
+    int bad[32];
+};
+
+__global__ void __launch_bounds__(32 * kSegWarps) search_seg_kernel(GridDev g, const double* __restrict__ atab_all, const AtomDev* atoms,
+                                                             const OrbitalDev* orbs, const AtomState* astate, SearchState* ss, int n_orbs,
+                                                             unsigned long long* work, const int* n_active_orbs, int threshold,
+                                                             int warm_start)
+{
+    __shared__ SegShared sh;
+    __shared__ double2 sbuf[kSegWarps * 64];
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned full = 0xffffffffu;
+    const int CL = (int)cluster.num_blocks();             // CTAs per orbital
+    const int S = CL * kSegWarps;
+    const int rank = (int)cluster.block_rank();
+    const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = rank * kSegWarps + wl;                  // segment index inside the orbital
+    const int k = blockIdx.x / CL;
+    SegShared* sh0 = cluster.map_shared_rank(&sh, 0);     // the rank-0 CTA collects y0 / d1 / bad
+    if (k >= n_orbs) return;
+    if (n_active_orbs && *n_active_orbs > threshold) return;       // the serial-in-r kernel is still the faster one
+    const OrbitalDev ob = orbs[k];
+    if (astate[ob.atom].done) return;
+    const double* __restrict__ atab = atab_all + (size_t)ob.tab * g.N;
+    const double ll1 = (double)(ob.l * (ob.l + 1));
+    const double Z = (double)atoms[ob.atom].Z;
+    Bracket b;
+    b.lo = -Z * Z - 1.; b.hi = kTopEnergy;                // DFTAtom.cpp:407,499
+    b.ylog = 0.;
+    b.ladder = warm_start && ss[k].pad == 1;
+    b.c_est = ss[k].E; b.radius = 8.4;
+    long long steps = 0;
+    int rounds = 0;
+
+    for (int round = 0; round < 64 && bracket_open(b.lo, b.hi); ++round) {
+        // every warp computes the same 32 trial energies
+        const double E = sample_energy(b, lane);
+        const double kappa = sqrt(2. * fabs(E));
+        const int start = start_index(g, kappa);
+        int imax = start;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) imax = max(imax, __shfl_xor_sync(full, imax, o));
+        const int len = (imax + S - 1) / S;
+        const int top = imax - w * len;
+        const int bot = max(top - len + 1, 1);
+        const bool valid = top >= 1;
+        // this segment's role for this energy: the seeds are nodes start, start - 1; the segment that contains start - 1 runs
+        // the real solution from the seeds (w_start itself depends on the tables only)
+        const int kind = (!valid || start - 1 < bot) ? 0 : (start - 1 > top ? 1 : 2);
+        const bool is_bottom = valid && bot == 1;
+
+        // ---------------- pass 1: transfer matrix (two basis chains) or the seeded real solution ----------------
+        {
+            SweepIn<2> in;
+            in.E[0] = E; in.E[1] = E;
+            in.running[0] = kind == 1; in.W_in[0] = 1.; in.D_in[0] = 0.;
+            in.running[1] = kind == 1; in.W_in[1] = 0.; in.D_in[1] = 1.;
+            in.start[0] = kind == 2 ? start : -1;
+            in.start[1] = -1;
+            FastOut<2> o;
+            o.bad = 0;
+            if (valid && __any_sync(full, kind != 0)) range_sweep<2>(g, atab, ll1, in, top, bot, sbuf + wl * 64, o);
+            sh.meta[wl][lane] = kind | ((int)o.prev[0] << 2) | (o.count[0] << 3);      // normal segments: count and sign follow in pass 2
+            sh.pseg[wl][lane] = kind ? o.P[0] : 1.;
+            sh.m[0][wl][lane] = o.W[0]; sh.m[2][wl][lane] = o.D[0];      // normal: (ww, dw); seeded: outgoing state (W, D)
+            sh.m[1][wl][lane] = o.W[1]; sh.m[3][wl][lane] = o.D[1];      // normal: (wd, dd)
+            if (w == 0) sh.bad[lane] = 0;
+            if (kind == 2 && is_bottom) { sh0->y0s[lane] = o.Y0s[0]; sh0->d1[lane] = o.d_first[0]; }
+            cluster.sync();
+            if (kind == 2 && o.bad) atomicOr(&sh0->bad[lane], 1);
+        }
+        // ---------------- scan: entry state of this segment ----------------
+        double A = 0., Bd = 0.;
+        if (kind == 1) {
+#pragma unroll 4
+            for (int v = 0; v < w; ++v) {
+                const SegShared* r = cluster.map_shared_rank(&sh, v / kSegWarps);
+                const int vl = v % kSegWarps;
+                const int kv = r->meta[vl][lane] & 3;
+                const double m0 = r->m[0][vl][lane], m1 = r->m[1][vl][lane], m2 = r->m[2][vl][lane], m3 = r->m[3][vl][lane];
+                if (kv == 2) { A = m0; Bd = m2; }
+                else if (kv == 1) {
+                    const double na = fma(m0, A, m1 * Bd);
+                    const double nb = fma(m2, A, m3 * Bd);
+                    A = na; Bd = nb;
+                }
+            }
+        }
+        // ---------------- pass 2: the real solution through the normal segments, counting sign changes ----------------
+        if (__any_sync(full, kind == 1)) {
+            SweepIn<1> in;
+            in.E[0] = E; in.running[0] = kind == 1; in.W_in[0] = A; in.D_in[0] = Bd; in.start[0] = -1;
+            FastOut<1> o;
+            range_sweep<1>(g, atab, ll1, in, top, bot, sbuf + wl * 64, o);
+            if (kind == 1) {
+                sh.meta[wl][lane] = 1 | ((int)o.prev[0] << 2) | (o.count[0] << 3);
+                if (is_bottom) { sh0->y0s[lane] = o.Y0s[0]; sh0->d1[lane] = o.d_first[0]; }
+                if (o.bad) atomicOr(&sh0->bad[lane], 1);
+            }
+        }
+        cluster.sync();
+
+        // ---------------- totals (every warp redundantly, so that all warps hold the same bracket) ----------------
+        int cfull = 0;
+        double Ptot = 1.;
+        unsigned pbot = 0;
+        int have_bottom = 0;
+#pragma unroll 4
+        for (int v = 0; v < S; ++v) {
+            const SegShared* r = cluster.map_shared_rank(&sh, v / kSegWarps);
+            const int mv = r->meta[v % kSegWarps][lane];
+            const double pv = r->pseg[v % kSegWarps][lane];
+            if (mv & 3) { cfull += mv >> 3; pbot = (unsigned)(mv >> 2) & 1u; Ptot *= pv; have_bottom = 1; }
+        }
+        const double Y0s = sh0->y0s[lane], d1v = sh0->d1[lane];
+        int y0_pos = Y0s > 0.;
+        double y0_log2 = (fabs(Y0s) <= 1.7e308) ? log2(fabs(Y0s)) - log2(fabs(Ptot)) : INFINITY;
+        cfull += (((y0_pos ? 0u : 1u) != pbot) ? 1 : 0);
+        int lane_bad = sh0->bad[lane] | !(Ptot > 0.) | !have_bottom | (start < 3);
+        double d_first = d1v;
+        if (__any_sync(full, lane_bad)) {
+            if (work && threadIdx.x == 0) atomicAdd(work + DFTATOM_K_POTENTIAL, 1ULL);       // rounds that fell back to the serial sweep
+            // a non-positive 1 - f/12 inside the sweep (grid far too coarse for this energy): generic serial path
+            const LaneOut so = sweep_lane(g, atab, ob.l, E, ob.want);
+            cfull = so.count_full; d_first = so.d_first; y0_log2 = so.y0_log2; y0_pos = so.y0_pos;
+        }
+        if (w == 0) steps += start - 1;
+        ++rounds;
+        update_bracket(b, E, cfull > ob.want + (d_first < 0. ? 1 : 0), y0_pos, y0_log2);
+        cluster.sync();                                    // shared results are consumed before the next round overwrites them
+    }
+    if (w == 0 && lane == 0) {
+        SearchState s = ss[k];
+        s.bot = b.lo; s.top = b.hi; s.E = b.lo;                              // level.E = BottomEnergy, DFTAtom.cpp:534
+        s.y0_log2 = b.ylog;
+        s.converged = (b.hi - b.lo < kEnergyTol) && (b.ylog < 49.828921423310435); // DFTAtom.cpp:528
+        s.stage = 3;
+        s.pad = 1;
+        ss[k] = s;
+    }
+    if (work && w == 0) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) steps += __shfl_xor_sync(full, steps, o);
+        if (lane == 0) {
+            atomicAdd(work, (unsigned long long)steps);
+            atomicAdd(work + DFTATOM_K_MATCH, 1ULL);                          // orbital solves
+            atomicAdd(work + DFTATOM_K_DENSITY, (unsigned long long)rounds);  // search rounds
+        }
+    }
+}
+
+void launch_search_seg(const GridDev& g, const double* atab, const AtomDev* atoms, const OrbitalDev* orbs, const AtomState* astate,
+                       SearchState* ss, int n_orbs, unsigned long long* work, int segments, const int* n_active_orbs, int threshold,
+                       int warm_start, cudaStream_t st)
+{
+    int CL = 1;
+    while (CL * 2 * kSegWarps <= segments && CL * 2 * kSegWarps <= kSegMax) CL *= 2;      // 1, 2, 4 or 8 CTAs per orbital
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_orbs * CL));
+    cfg.blockDim = dim3(32 * kSegWarps);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, search_seg_kernel, g, atab, atoms, orbs, astate, ss, n_orbs, work, n_active_orbs, threshold, warm_start);
+}
+
+}  // namespace dft

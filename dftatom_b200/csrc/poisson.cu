@@ -15,7 +15,7 @@
 // Where the time goes is latency, not flops (one solve = ~400 level visits of three dependent sweeps each), so:
 //  * levels live in an owner-major layout (below): every access of a visit is unit-stride across the warp;
 //  * a visit keeps the thread's nodes in registers for its three sweeps;
-//  * levels with <= 1024 nodes are run by warp 0 alone out of static shared memory: no block barrier;
+//  * levels with <= 512 nodes are run by warp 0 alone out of static shared memory: no block barrier;
 //  * the sub-cycle below the 32-node level is one precomputed 32x32 operator (it depends on the grid only);
 //  * Source_0 (read by every fine-grid sweep) and the mid levels sit in dynamic shared memory when they fit.
 // The update norm of the reference's IterateGaussSeidel only drives its early exits; with a fixed number of sweeps it
@@ -42,8 +42,8 @@ PoissonLevels make_levels(int L)
 constexpr int kPT = 512;     // threads per CTA
 constexpr int kLogPT = 9;
 constexpr int kMaxNpt = 32;  // nodes per thread of a register-resident chunk (a chunk = T * npt consecutive nodes)
-constexpr int kWarpLevelNodes = 1024;   // levels up to this size are run by warp 0 alone (no block barrier)
-constexpr int kWarpSmemDoubles = 2112;  // sum of the sizes of all levels with <= 1024 owned nodes, 4-aligned each
+constexpr int kWarpLevelNodes = 512;    // levels up to this size are run by warp 0 alone (no block barrier)
+constexpr int kWarpSmemDoubles = 2112;  // sum of the sizes of all levels with <= 512 owned nodes, 4-aligned each
 constexpr double kTiny = 1e-19;   // carry terms below this (relative) are dropped from the truncated scans (FP64 eps = 1.1e-16)
 constexpr int kMaxDynBytes = 180 * 1024;   // dynamic shared memory the solve kernels may ask for (static part: ~45 KB)
 
@@ -459,7 +459,7 @@ __device__ __noinline__ void fused_block(int l, int flags, int sweeps)
     __syncthreads();
 }
 
-// the same for the levels run by warp 0 (T = 32, static shared memory, 64 <= n <= 1024, NPT = n / 32)
+// the same for the levels run by warp 0 (T = 32, static shared memory, 64 <= n <= 512, NPT = n / 32)
 template <int NPT, bool SRC_REGS>
 __device__ __noinline__ void fused_warp(int l, int flags, int sweeps)
 {
@@ -655,7 +655,6 @@ __device__ __noinline__ void smooth_warp(int l, int sweeps)
     const LevelConst& c = g_sm.lc[l];
     if (threadIdx.x == 0) g_sm.updates += (unsigned long long)sweeps * (unsigned long long)(c.n - 1);
     switch (c.lay.lg) {
-        case 5: visit_warp<32, false>(l, sweeps); break;
         case 4: visit_warp<16, true>(l, sweeps); break;
         case 3: visit_warp<8, true>(l, sweeps); break;
         case 2: visit_warp<4, true>(l, sweeps); break;
@@ -688,7 +687,8 @@ __device__ __noinline__ void smooth_block(int l, int sweeps)
             case 5: visit_regs<32, false>(l, 0, sweeps, true, 0., right); break;
             case 4: visit_regs<16, true>(l, 0, sweeps, true, 0., right); break;
             case 3: visit_regs<8, true>(l, 0, sweeps, true, 0., right); break;
-            default: visit_regs<4, true>(l, 0, sweeps, true, 0., right); break;   // n = 2048 (n <= 1024 are warp levels)
+            case 2: visit_regs<4, true>(l, 0, sweeps, true, 0., right); break;
+            default: visit_regs<2, true>(l, 0, sweeps, true, 0., right); break;   // n = 1024 (n <= 512 are warp levels)
         }
     }
     if (g_sm.dbg && threadIdx.x == 0) { g_sm.dbg[l] += clock64() - t0; g_sm.dbg[72 + l] += 1; }
@@ -816,7 +816,8 @@ __device__ __noinline__ void fused_visit_block(int l, int flags, int sweeps)
         case 5: fused_block<32, false>(l, flags, sweeps); break;
         case 4: fused_block<16, true>(l, flags, sweeps); break;
         case 3: fused_block<8, true>(l, flags, sweeps); break;
-        default: fused_block<4, true>(l, flags, sweeps); break;
+        case 2: fused_block<4, true>(l, flags, sweeps); break;
+        default: fused_block<2, true>(l, flags, sweeps); break;
     }
     if (g_sm.dbg && threadIdx.x == 0) { g_sm.dbg[l] += clock64() - t0; g_sm.dbg[72 + l] += 1; }
 }
@@ -824,7 +825,6 @@ __device__ __noinline__ void fused_visit_warp(int l, int flags, int sweeps)
 {
     const long long t0 = g_sm.dbg ? clock64() : 0;
     switch (g_sm.lc[l].lay.lg) {
-        case 5: fused_warp<32, false>(l, flags, sweeps); break;
         case 4: fused_warp<16, true>(l, flags, sweeps); break;
         case 3: fused_warp<8, true>(l, flags, sweeps); break;
         case 2: fused_warp<4, true>(l, flags, sweeps); break;

@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(kAT) potential_energy_kernel(GridDev g, Poisso
         as.n_steps += 1;
         if (!done && as.n_steps >= at.n_steps_max) { done = 1; status = DFTATOM_MAX_STEPS; }
         if (!done && !(fabs(etot) <= 1.7e308)) { done = 1; status = DFTATOM_NUMERIC_FAILURE; }
-        if (done) { as.done = 1; as.status = status; atomicAdd(b.n_active, -1); }
+        if (done) { as.done = 1; as.status = status; atomicAdd(b.n_active, -1); atomicAdd(b.n_active + 1, -(at.orb_count[0] + at.orb_count[1])); }
     }
 }
 

@@ -16,7 +16,7 @@ t0 = time.time()
 res = ctx.solve_batch(opts)
 print("wall", time.time() - t0, "dev ms", ctx.last_timing())
 pr = ctx.last_profile()
-print("profile", {k: round(v["ms"], 1) for k, v in pr.items()}, "orbital solves", pr["match"]["work"], "rounds/solve", pr["density"]["work"] / max(1, pr["match"]["work"]))
+print("profile", {k: round(v["ms"], 1) for k, v in pr.items()}, "orbital solves", pr["match"]["work"], "rounds/solve", pr["density"]["work"] / max(1, pr["match"]["work"]), "fallback rounds", pr["potential"]["work"])
 worst_e = worst_t = 0
 for r, a in zip(res, g):
     nref = a.get("n_steps", len(a["steps"]))
