@@ -114,6 +114,9 @@ void launch_match(const GridDev& g, const double* atab, const OrbitalDev* orbs, 
 void launch_match_seg(const GridDev& g, const double* atab, const OrbitalDev* orbs, const AtomState* astate, const SearchState* ss,
                       double* psi, int* match_pt, int n_orbs, cudaStream_t st);
 
+void launch_match_cta(const GridDev& g, const double* atab, const OrbitalDev* orbs, const AtomState* astate, const SearchState* ss,
+                      double* psi, int* match_pt, double* inv_norm, int n_orbs, cudaStream_t st);
+
 // potential -> a-table (a_i = 1 - (2K_i V_i + δ²/4)/12), n_tabs rows
 void launch_build_atab(const GridDev& g, const double* vpot, double* atab, int n_tabs, cudaStream_t st);
 
@@ -157,6 +160,7 @@ struct ScfBuffers {
     double* atab;     // [n_tabs][N]
     double* psi;      // [n_orbs][N]
     int* match_pt;    // [n_orbs]
+    double* inv_norm; // [n_orbs] 1 / integral u^2 dr of the matched solution in psi
     double* phi; double* src;   // Poisson hierarchy [n_atoms][levels.total]
     double* U;        // [n_atoms][N] Hartree U(r) = r V_H, natural node order (output of the Poisson solve)
     int* Zbc;         // [n_atoms]
@@ -166,6 +170,7 @@ struct ScfBuffers {
     int* n_active;    // device counter of atoms not done
 };
 void launch_initial_density(const GridDev& g, const ScfBuffers& b, cudaStream_t st);
+void launch_orbital_norms(const GridDev& g, const ScfBuffers& b, cudaStream_t st);
 void launch_density_update(const GridDev& g, const ScfBuffers& b, cudaStream_t st);
 void launch_potential_energy(const GridDev& g, const PoissonLevels& lv, const ScfBuffers& b, int first, cudaStream_t st);
 

@@ -12,6 +12,7 @@
 // The state carried between segments is (W, D) rather than two consecutive W: the second component is small, so
 // combining transfer matrices does not cancel leading digits.  One division per node, where y_i = w_i / d_i is stored.
 #include "numerov_common.cuh"
+#include <cstdio>
 
 namespace dft {
 
@@ -181,6 +182,304 @@ __global__ void __launch_bounds__(128) match_seg_kernel(GridDev g, const double*
     const double factor = y_out_match / y_in_match;
     for (int i = match + 1 + lane; i <= start; i += 32) psi[i] *= factor;
     if (lane == 0) match_pt[k] = match;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The same two-sided matched solution by a whole CTA: kMT threads = kMT radial segments per direction (64 nodes each at
+// 16385 nodes instead of 512), the 2x2 transfer matrices combined by a log-depth scan (Kogge-Stone in the warp, one
+// shared-memory hop across warps).  Also returns 1 / integral u^2 dr (NormalizeNonUniform, DFTAtom.cpp:36-56), so the
+// density kernel reads every orbital once.  This is the latency-optimised shape: ~30 us per orbital instead of ~500.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kMT = 256;
+
+struct MatP { double ww, wd, dw, dd, p; };      // transfer matrix of (W, D) and the product of d over the segment
+
+__device__ __forceinline__ MatP matp_mul(const MatP& later, const MatP& earlier)
+{   // apply `earlier` first, then `later`
+    MatP r;
+    r.ww = fma(later.ww, earlier.ww, later.wd * earlier.dw);
+    r.wd = fma(later.ww, earlier.wd, later.wd * earlier.dd);
+    r.dw = fma(later.dw, earlier.ww, later.dd * earlier.dw);
+    r.dd = fma(later.dw, earlier.wd, later.dd * earlier.dd);
+    r.p = later.p * earlier.p;
+    return r;
+}
+__device__ __forceinline__ MatP matp_shfl_up(const MatP& m, int o)
+{
+    const unsigned full = 0xffffffffu;
+    MatP r;
+    r.ww = __shfl_up_sync(full, m.ww, o); r.wd = __shfl_up_sync(full, m.wd, o);
+    r.dw = __shfl_up_sync(full, m.dw, o); r.dd = __shfl_up_sync(full, m.dd, o);
+    r.p = __shfl_up_sync(full, m.p, o);
+    return r;
+}
+
+struct MatchShared {
+    MatP wtot[kMT / 32];
+    int cand[kMT / 32]; double ycand[kMT / 32];
+    double red[kMT / 32];
+    double y2, ylast, bcast;
+    int match;
+};
+
+// entry state of every thread's segment: (A, B, Pin) = [product of the maps of all earlier segments] applied to (A0, B0, P0);
+// segments are ordered by thread index.  Block-collective.
+__device__ __forceinline__ void segment_entries(const MatP& mine, double A0, double B0, double P0, MatchShared& sh,
+                                                double& A, double& B, double& Pin)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    MatP t = mine;                                   // inclusive scan: maps of lanes 0 .. lane, composed in order
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const MatP prevm = matp_shfl_up(t, o);
+        if (lane >= o) t = matp_mul(t, prevm);
+    }
+    if (lane == 31) sh.wtot[w] = t;
+    __syncthreads();
+    double a = A0, b = B0, p = P0;                   // state entering this warp
+    for (int v = 0; v < w; ++v) {
+        const MatP m = sh.wtot[v];
+        const double na = fma(m.ww, a, m.wd * b), nb = fma(m.dw, a, m.dd * b);
+        a = na; b = nb; p *= m.p;
+    }
+    MatP ex = matp_shfl_up(t, 1);                    // exclusive prefix inside the warp
+    if (lane == 0) { ex.ww = 1.; ex.wd = 0.; ex.dw = 0.; ex.dd = 1.; ex.p = 1.; }
+    A = fma(ex.ww, a, ex.wd * b);
+    B = fma(ex.dw, a, ex.dd * b);
+    Pin = p * ex.p;
+    __syncthreads();                                 // wtot may be reused
+}
+
+// Node i of the staged arrays lives at slot i + i / 32: a thread walking its own contiguous chunk and a warp reading 32
+// consecutive nodes are both free of bank conflicts as long as the chunk length is a multiple of 32 (or the chunk stride
+// in slots is odd); the launcher rounds the chunk length accordingly.
+__device__ __forceinline__ int pslot(int i) { return i + (i >> 5); }
+
+// SMEM = true: g_i = f_i / 12 of the whole orbital is staged in shared memory (one coalesced pass over the tables) and
+// the solution is built in place of it, then copied out coalesced; per-thread chunk walks through global memory would
+// touch 32 cache lines per warp instruction (measured: 800 cycles per node, L1-bound).  SMEM = false (grids too large for
+// shared memory): same algorithm on global memory.
+template <bool SMEM>
+__global__ void __launch_bounds__(kMT) match_cta_kernel(GridDev g, const double* __restrict__ atab_all, const OrbitalDev* orbs,
+                                                        const AtomState* astate, SearchState* ss, double* psi_all, int* match_pt,
+                                                        double* inv_norm, int n_orbs)
+{
+    __shared__ MatchShared sh;
+    extern __shared__ double gy[];                       // SMEM: g_i, later y_i, slot pslot(i)
+    const unsigned full = 0xffffffffu;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int k = blockIdx.x;
+    if (k >= n_orbs) return;
+    const OrbitalDev ob = orbs[k];
+    if (astate[ob.atom].done) return;
+    SearchState s = ss[k];
+    if (s.stage != 3) {                 // search budget exhausted: didNotConverge (DFTAtom.cpp:516,538)
+        s.converged = 0;
+        s.E = (s.stage == 0) ? s.dn_hi : s.bot;
+        s.stage = 3;
+        if (t == 0) ss[k] = s;
+    }
+    const double E = s.E;
+    const double* __restrict__ atab = atab_all + (size_t)ob.tab * g.N;
+    double* __restrict__ psi = psi_all + (size_t)k * g.N;
+    const double ll1 = (double)(ob.l * (ob.l + 1));
+    const double kappa = sqrt(2. * fabs(E));
+    const int start = start_index(g, kappa);
+    const int N = g.N;
+    auto gtab = [&](int i) { return fma(-E, __ldg(g.c6 + i), fma(ll1, __ldg(g.b12 + i), __ldg(atab + i))); };   // f_i / 12
+    if (SMEM) {
+        for (int i = t; i <= start; i += kMT) gy[pslot(i)] = gtab(i);
+        __syncthreads();
+    }
+    auto gval = [&](int i) { return SMEM ? gy[pslot(i)] : gtab(i); };
+    auto put = [&](int i, double y) { if (SMEM) gy[pslot(i)] = y; else psi[i] = y; };
+
+    // far seeds (Numerov.h:427-447)
+    const double y_s0 = far_value(g, kappa, start), y_s1 = far_value(g, kappa, start - 1);
+    const double g_s0 = gval(start), g_s1 = gval(start - 1);
+    const double d_s0 = 1. - g_s0, d_s1 = 1. - g_s1;
+    if (t == 0) { sh.y2 = 0.; sh.ylast = 0.; }
+
+    // ------------------------------------------------------------------------------------------------
+    // inward: nodes i = start-2 ... 1, thread t owns [bot, top] counted from the top
+    // state entering a segment: (W_{top+1}, D_{top+2} = W_{top+1} - W_{top+2})
+    // ------------------------------------------------------------------------------------------------
+    int match = 2;
+    double y_in_match = 0.;
+    {
+        const int n_in = start - 2;
+        const int len = (((n_in + kMT - 1) / kMT) + 31) & ~31;      // chunk length: a multiple of 32 (bank-conflict-free walks)
+        const int top = start - 2 - t * len;
+        const int bot = max(top - len + 1, 1);
+        const bool have = top >= 1 && n_in > 0;
+        MatP M = { 1., 0., 0., 1., 1. };
+        double g1e = 0., g2e = 0.;                             // g_{top+1}, g_{top+2}: read before anything is overwritten
+        if (have) { g1e = gval(top + 1); g2e = (top + 2 <= start) ? gval(top + 2) : 0.; }
+        if (have) {
+            double g1 = g1e, g2 = g2e;
+            // basis a: (W, D) = (1, 0) -> W_{top+1} = W_{top+2} = 1;   basis b: (0, 1) -> W_{top+1} = 0, W_{top+2} = -1
+            double aW1 = 1., aW2 = 1., aD = 0., bW1 = 0., bW2 = -1., bD = 1., prod = 1.;
+            for (int i = top; i >= bot; --i) {
+                const double s1 = fma(-g1, g2, g1 + g2), t1 = 10. * g1;
+                const double aDn = fma(t1, aW1, fma(s1, aW2, aD)), bDn = fma(t1, bW1, fma(s1, bW2, bD));
+                aW2 = aW1; aW1 += aDn; aD = aDn;
+                bW2 = bW1; bW1 += bDn; bD = bDn;
+                prod *= (1. - g1);
+                g2 = g1; g1 = gval(i);
+            }
+            M.ww = aW1; M.wd = bW1; M.dw = aD; M.dd = bD; M.p = prod;      // out = (W_bot, D_{bot+1})
+        }
+        // entry of segment 0: W_{start-1} = d_{s1} y_{s1} d_{s0}, W_start = d_{s0} y_{s0}; P_{start-1} = d_{s0}
+        const double Ws1 = d_s1 * y_s1 * d_s0, Ws0 = d_s0 * y_s0;
+        double A, B, Pin;
+        segment_entries(M, Ws1, Ws1 - Ws0, d_s0, sh, A, B, Pin);
+        // pass 2a: y_i = W_i / (P_i d_i), P_i = P_{i+1} d_{i+1}; first node (descending) with y_i < y_{i+1} or |y_i| > 1e15.
+        // Nothing is stored yet: the nodes below the match point still need their g for the outward solution.
+        int cand = 0;
+        double ycand = 0.;
+        if (have) {
+            double g1 = g1e, g2 = g2e;
+            double W1 = A, W2 = A - B, D = B, P = Pin;     // P = P_{top+1}
+            double ynext = W1 / (P * (1. - g1));
+            for (int i = top; i >= bot; --i) {
+                const double s1 = fma(-g1, g2, g1 + g2), t1 = 10. * g1;
+                const double Dn = fma(t1, W1, fma(s1, W2, D));
+                const double W = W1 + Dn;
+                P *= (1. - g1);
+                const double gi = gval(i);
+                const double y = W / (P * (1. - gi));
+                if (!cand && (y < ynext || fabs(y) > 1e15)) { cand = i; ycand = y; }
+                if (i == 2) sh.y2 = y;
+                ynext = y;
+                W2 = W1; W1 = W; D = Dn; g2 = g1; g1 = gi;
+                if (cand) break;                             // everything below belongs to the outward solution
+            }
+        }
+        // the first candidate from the top = the candidate of the lowest thread index that has one
+        const unsigned mc = __ballot_sync(full, cand != 0);
+        const int srcl = mc ? __ffs(mc) - 1 : 0;
+        const int wc = __shfl_sync(full, cand, srcl);
+        const double wy = __shfl_sync(full, ycand, srcl);
+        if (lane == 0) { sh.cand[w] = mc ? wc : 0; sh.ycand[w] = wy; }
+        __syncthreads();
+        bool found = false;
+        for (int v = 0; v < kMT / 32; ++v)
+            if (!found && sh.cand[v]) { match = sh.cand[v]; y_in_match = sh.ycand[v]; found = true; }
+        if (!found) {                                      // matchPoint stays 2 (Numerov.h:449)
+            y_in_match = (start - 2 >= 2) ? sh.y2 : ((start - 1 == 2) ? y_s1 : y_s0);
+        }
+        // pass 2b: the inward solution above the match point, stored (in place of g: every thread only overwrites nodes
+        // whose g it has already consumed; the entry values g1e, g2e of the neighbours are in registers)
+        __syncthreads();
+        if (have && top > match) {
+            double g1 = g1e, g2 = g2e;
+            double W1 = A, W2 = A - B, D = B, P = Pin;
+            for (int i = top; i >= bot && i > match; --i) {
+                const double s1 = fma(-g1, g2, g1 + g2), t1 = 10. * g1;
+                const double Dn = fma(t1, W1, fma(s1, W2, D));
+                const double W = W1 + Dn;
+                P *= (1. - g1);
+                const double gi = gval(i);
+                put(i, W / (P * (1. - gi)));
+                W2 = W1; W1 = W; D = Dn; g2 = g1; g1 = gi;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------------------------------------------
+    // outward: y_0 = 0, y_1 = r_1^{l+1} e^{-δ/2} (Numerov.h:110-116, :470-477); nodes i = 2 ... match
+    // state entering a segment: (W_{bot-1}, D_{bot-2} = W_{bot-1} - W_{bot-2});  Q_i = prod_{j<i} d_j
+    // ------------------------------------------------------------------------------------------------
+    double y_out_match;
+    const double y1 = pow(__ldg(g.r + 1), (double)ob.l + 1.) * exp(-0.5 * g.delta);
+    {
+        const double gn1 = gval(1);
+        const int n_out = match - 1;                       // nodes 2..match
+        const int len = (((n_out + kMT - 1) / kMT) + 31) & ~31;
+        const int bot = 2 + t * len;
+        const int top = min(bot + len - 1, match);
+        const bool have = bot <= match;
+        MatP M = { 1., 0., 0., 1., 1. };
+        double g1e = 0., g2e = 0.;                             // g_{bot-1}, g_{bot-2}; d_0 := 1
+        if (have) { g1e = gval(bot - 1); g2e = (bot - 2 >= 1) ? gval(bot - 2) : 0.; }
+        if (have) {
+            double g1 = g1e, g2 = g2e;
+            double aW1 = 1., aW2 = 1., aD = 0., bW1 = 0., bW2 = -1., bD = 1., prod = 1.;
+            for (int i = bot; i <= top; ++i) {
+                const double s1 = fma(-g1, g2, g1 + g2), t1 = 10. * g1;
+                const double aDn = fma(t1, aW1, fma(s1, aW2, aD)), bDn = fma(t1, bW1, fma(s1, bW2, bD));
+                aW2 = aW1; aW1 += aDn; aD = aDn;
+                bW2 = bW1; bW1 += bDn; bD = bDn;
+                prod *= (1. - g1);
+                g2 = g1; g1 = gval(i);
+            }
+            M.ww = aW1; M.wd = bW1; M.dw = aD; M.dd = bD; M.p = prod;
+        }
+        // entry of segment 0: W_1 = d_1 y_1 (Q_1 = 1), W_0 = 0  ->  (W, D) = (W_1, W_1)
+        const double Wn1 = (1. - gn1) * y1;
+        double A, B, Qin;
+        segment_entries(M, Wn1, Wn1, 1., sh, A, B, Qin);      // (its barriers also order the entry reads before the stores below)
+        if (have) {
+            double g1 = g1e, g2 = g2e;
+            double W1 = A, W2 = A - B, D = B, Q = Qin;     // Q = Q_{bot-1}
+            double ylast = 0.;
+            for (int i = bot; i <= top; ++i) {
+                const double s1 = fma(-g1, g2, g1 + g2), t1 = 10. * g1;
+                const double Dn = fma(t1, W1, fma(s1, W2, D));
+                const double W = W1 + Dn;
+                Q *= (1. - g1);                            // Q_i = Q_{i-1} d_{i-1}
+                const double gi = gval(i);
+                const double y = W / (Q * (1. - gi));
+                put(i, y);                                 // includes node `match` = outward value (Numerov.h:499)
+                ylast = y;
+                W2 = W1; W1 = W; D = Dn; g2 = g1; g1 = gi;
+            }
+            if (top == match) sh.ylast = ylast;
+        }
+        __syncthreads();
+        y_out_match = sh.ylast;
+    }
+    // the seeds and the nodes 0, 1; then scale the outer part so that both pieces meet at the match point
+    // (Numerov.h:497-501), zero the tail, and the norm integral of u^2 dr, u_i = y_i e^{i δ/2}, dr = Rp δ e^{δ i} di
+    // (DFTAtom.cpp:36-56)
+    if (t == 0) { put(start, y_s0); put(start - 1, y_s1); put(0, 0.); put(1, y1); }
+    __syncthreads();
+    const double factor = y_out_match / y_in_match;
+    double acc = 0.;
+    for (int i = t; i < N; i += kMT) {
+        double y = 0.;
+        if (i <= start) {
+            y = SMEM ? gy[pslot(i)] : psi[i];
+            if (i > match) y *= factor;
+            const double u = y * __ldg(g.sqex + i);
+            acc = fma(__ldg(g.wjac + i), u * u, acc);
+        }
+        if (SMEM || i > match) psi[i] = y;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(full, acc, o);
+    if (lane == 0) sh.red[w] = acc;
+    __syncthreads();
+    if (t == 0) {
+        double tot = 0.;
+        for (int v = 0; v < kMT / 32; ++v) tot += sh.red[v];
+        inv_norm[k] = 1. / tot;
+        match_pt[k] = match;
+    }
+}
+
+void launch_match_cta(const GridDev& g, const double* atab, const OrbitalDev* orbs, const AtomState* astate, const SearchState* ss,
+                      double* psi, int* match_pt, double* inv_norm, int n_orbs, cudaStream_t st)
+{
+    const size_t bytes = ((size_t)g.N + (size_t)g.N / 32 + 8) * sizeof(double);
+    if (bytes <= 200 * 1024) {
+        static size_t attr_bytes = 0;
+        if (bytes > attr_bytes) { cudaFuncSetAttribute(match_cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); attr_bytes = bytes; }
+        match_cta_kernel<true><<<n_orbs, kMT, bytes, st>>>(g, atab, orbs, astate, const_cast<SearchState*>(ss), psi, match_pt, inv_norm, n_orbs);
+    } else {
+        match_cta_kernel<false><<<n_orbs, kMT, 0, st>>>(g, atab, orbs, astate, const_cast<SearchState*>(ss), psi, match_pt, inv_norm, n_orbs);
+    }
 }
 
 void launch_match_seg(const GridDev& g, const double* atab, const OrbitalDev* orbs, const AtomState* astate, const SearchState* ss,

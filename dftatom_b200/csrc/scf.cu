@@ -184,45 +184,63 @@ void launch_initial_density(const GridDev& g, const ScfBuffers& b, cudaStream_t 
 
 // LoopOverLevels' tail (normalise, accumulate occ u^2, Eel) + CalculateNonUniformDensity's mixing.
 // psi holds the matched y_i of every orbital (inner part final, outer part already scaled).
-__global__ void __launch_bounds__(kAT) density_update_kernel(GridDev g, ScfBuffers b)
+// 1 / integral u^2 dr of every orbital, u_i = y_i e^{i δ/2}, dr = Rp δ e^{δ i} di  (DFTAtom.cpp:36-56); only needed after the
+// validation-path match kernels, the production one (match_cta_kernel) returns it itself
+__global__ void __launch_bounds__(256) orbital_norm_kernel(GridDev g, ScfBuffers b)
 {
-    __shared__ double sm[32];
-    __shared__ double inv_norm[2 * DFTATOM_MAX_LEVELS];
+    __shared__ double red[8];
+    const int o = blockIdx.x;
+    if (b.astate[b.orbs[o].atom].done) return;
+    const double* psi = b.psi + (size_t)o * g.N;
+    double acc = 0.;
+    for (int i = threadIdx.x; i < g.N; i += blockDim.x) {
+        const double u = psi[i] * g.sqex[i];
+        acc = fma(g.wjac[i], u * u, acc);
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.;
+        for (int v = 0; v < 8; ++v) tot += red[v];
+        b.inv_norm[o] = 1. / tot;
+    }
+}
+
+// New density and mixing (DFTAtom.cpp:558-559, :332-342).  grid = (atoms, kDensChunks): every CTA owns a contiguous range of
+// nodes of one atom (the nodes are independent), so a handful of atoms still fills the GPU.
+constexpr int kDensChunks = 8;
+constexpr int kDT = 256;
+__global__ void __launch_bounds__(kDT) density_update_kernel(GridDev g, ScfBuffers b)
+{
+    __shared__ double wgt[2 * DFTATOM_MAX_LEVELS];          // occupation / norm of every orbital
     const int a = blockIdx.x;
     AtomState& as = b.astate[a];
     if (as.done) return;
     const AtomDev at = b.atoms[a];
     const int N = g.N;
-    dftatom_step* rec = b.steps + (size_t)a * b.steps_stride + as.n_steps;
-
-    // 1. norms: integral of u^2 dr, u_i = y_i e^{i δ/2}, dr = Rp δ e^{δ i} di  (DFTAtom.cpp:36-56)
-    for (int s = 0; s < at.n_spin; ++s) {
-        for (int k = 0; k < at.orb_count[s]; ++k) {
-            const int o = at.orb_begin[s] + k;
-            const double* psi = b.psi + (size_t)o * N;
-            double acc[1] = { 0. };
-            for (int i = threadIdx.x; i < N; i += blockDim.x) {
-                const double u = psi[i] * g.sqex[i];
-                acc[0] = fma(g.wjac[i], u * u, acc[0]);
-            }
-            block_sum_n<1>(acc, sm);
-            if (threadIdx.x == 0) inv_norm[s * DFTATOM_MAX_LEVELS + k] = 1. / acc[0];
-            __syncthreads();
-        }
+    for (int q = threadIdx.x; q < at.orb_count[0] + at.orb_count[1]; q += blockDim.x) {
+        const int s = q >= at.orb_count[0];
+        const int k = s ? q - at.orb_count[0] : q;
+        const int o = at.orb_begin[s] + k;
+        wgt[s * DFTATOM_MAX_LEVELS + k] = (double)b.orbs[o].occ * b.inv_norm[o];
     }
-    // 2. new density and mixing (DFTAtom.cpp:558-559, :332-342)
+    __syncthreads();
+    const int per = (N + kDensChunks - 1) / kDensChunks;
+    const int i0 = blockIdx.y * per, i1 = min(i0 + per, N);
     const double keep = at.mixing, take = 1. - at.mixing;
     double* rt = b.rhot + (size_t)a * N;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
         double tot = 0.;
         const double sq = g.sqex[i];
         for (int s = 0; s < at.n_spin; ++s) {
             double acc = 0.;
             if (i < N - 1) {
+                const double* p = b.psi + (size_t)at.orb_begin[s] * N + i;
                 for (int k = 0; k < at.orb_count[s]; ++k) {
-                    const int o = at.orb_begin[s] + k;
-                    const double u = b.psi[(size_t)o * N + i] * sq;
-                    acc = fma((double)b.orbs[o].occ * inv_norm[s * DFTATOM_MAX_LEVELS + k], u * u, acc);
+                    const double u = p[(size_t)k * N] * sq;
+                    acc = fma(wgt[s * DFTATOM_MAX_LEVELS + k], u * u, acc);
                 }
             }
             double* rho = b.rho + (size_t)b.tab_of[2 * a + s] * N;
@@ -233,8 +251,9 @@ __global__ void __launch_bounds__(kAT) density_update_kernel(GridDev g, ScfBuffe
         if (at.n_spin == 2 && i >= 1) rt[i] = tot;     // DFTAtom.cpp:933-934 (LDA: rhot aliases rho)
         else if (at.n_spin == 1) rt[i] = tot;
     }
-    // 3. eigenvalues of this step into the record; electronic energy; reallyConverged
-    if (threadIdx.x == 0) {
+    // eigenvalues of this step into the record; electronic energy; reallyConverged
+    if (blockIdx.y == 0 && threadIdx.x == 0) {
+        dftatom_step* rec = b.steps + (size_t)a * b.steps_stride + as.n_steps;
         double eel = 0.;
         int ok = 1;
         for (int s = 0; s < at.n_spin; ++s)
@@ -250,9 +269,14 @@ __global__ void __launch_bounds__(kAT) density_update_kernel(GridDev g, ScfBuffe
     }
 }
 
+void launch_orbital_norms(const GridDev& g, const ScfBuffers& b, cudaStream_t st)
+{
+    orbital_norm_kernel<<<b.n_orbs, 256, 0, st>>>(g, b);
+}
+
 void launch_density_update(const GridDev& g, const ScfBuffers& b, cudaStream_t st)
 {
-    density_update_kernel<<<b.n_atoms, kAT, 0, st>>>(g, b);
+    density_update_kernel<<<dim3(b.n_atoms, kDensChunks), kDT, 0, st>>>(g, b);
 }
 
 // Potential from (U, rho), the five integrals, energies, stop test.  first != 0: only the initial potential.
