@@ -50,8 +50,8 @@ struct dftatom_ctx {
     int max_vcycles = 8;
     int floor_stop = 0;
     int refine_vcycles = 0;
-    int warm_vcycles = 0;      // Poisson warm start from SCF step warm_after on (0 = off)
-    int warm_after = 3;
+    int warm_vcycles = 7;      // Poisson warm start from SCF step warm_after on: V-cycles per solve (0 = always the full cycle)
+    int warm_after = 4;
     int r_segments = 32;       // radial segments per orbital of the parallel-in-r search (<= 1: serial-in-r search only)
     int seg_threshold = 300;   // the parallel-in-r search takes over once at most this many orbitals are still active
     int profile = 0;
@@ -61,7 +61,7 @@ struct dftatom_ctx {
     int warm_start = 1;
     dftatom_kernel_profile prof[DFTATOM_K_COUNT] = {};
     // reusable buffers
-    DevBuf atoms, astate, orbs, ss, rho, rhot, vpot, atab, psi, match_pt, inv_norm, phi, src, u0, ubuf, zbc, tab_of, steps, n_active;
+    DevBuf atoms, astate, orbs, ss, rho, rhot, vpot, atab, psi, match_pt, inv_norm, epart, eticket, phi, src, u0, ubuf, zbc, tab_of, steps, n_active;
     DevBuf scratch[8];
     int* h_active = nullptr;       // pinned
     // timing of the last solve
@@ -168,7 +168,7 @@ void dftatom_destroy(dftatom_ctx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto& kv : c->grids) kv.second.mem.release();
-    DevBuf* all[] = { &c->atoms, &c->astate, &c->orbs, &c->ss, &c->rho, &c->rhot, &c->vpot, &c->atab, &c->psi, &c->match_pt, &c->inv_norm,
+    DevBuf* all[] = { &c->atoms, &c->astate, &c->orbs, &c->ss, &c->rho, &c->rhot, &c->vpot, &c->atab, &c->psi, &c->match_pt, &c->inv_norm, &c->epart, &c->eticket,
                       &c->phi, &c->src, &c->u0, &c->ubuf, &c->zbc, &c->tab_of, &c->steps, &c->n_active };
     for (DevBuf* b : all) b->release();
     for (DevBuf& b : c->scratch) b.release();
@@ -318,6 +318,8 @@ int dftatom_solve_batch(dftatom_ctx* c, const dftatom_options* opts, int n_atoms
     if ((rc = c->psi.ensure(sizeof(double) * (size_t)n_orbs * N))) return rc;
     if ((rc = c->match_pt.ensure(sizeof(int) * (size_t)n_orbs))) return rc;
     if ((rc = c->inv_norm.ensure(sizeof(double) * (size_t)n_orbs))) return rc;
+    if ((rc = c->epart.ensure(sizeof(double) * (size_t)n_atoms * 8 * 5)) || (rc = c->eticket.ensure(sizeof(int) * (size_t)n_atoms))) return rc;
+    DFT_CHECK(cudaMemsetAsync(c->eticket.p, 0, sizeof(int) * (size_t)n_atoms, st));
     if ((rc = c->phi.ensure(sizeof(double) * (size_t)n_atoms * lv.total))) return rc;
     if ((rc = c->src.ensure(sizeof(double) * (size_t)n_atoms * lv.total))) return rc;
     if ((rc = c->u0.ensure(sizeof(double) * (size_t)n_atoms * N))) return rc;
@@ -333,7 +335,7 @@ int dftatom_solve_batch(dftatom_ctx* c, const dftatom_options* opts, int n_atoms
     b.n_atoms = n_atoms; b.n_orbs = n_orbs; b.n_tabs = n_tabs; b.N = N;
     b.atoms = c->atoms.as<AtomDev>(); b.astate = c->astate.as<AtomState>(); b.orbs = c->orbs.as<OrbitalDev>();
     b.ss = c->ss.as<SearchState>(); b.rho = c->rho.as<double>(); b.rhot = c->rhot.as<double>(); b.vpot = c->vpot.as<double>();
-    b.atab = c->atab.as<double>(); b.psi = c->psi.as<double>(); b.match_pt = c->match_pt.as<int>(); b.inv_norm = c->inv_norm.as<double>();
+    b.atab = c->atab.as<double>(); b.psi = c->psi.as<double>(); b.match_pt = c->match_pt.as<int>(); b.inv_norm = c->inv_norm.as<double>(); b.epart = c->epart.as<double>(); b.eticket = c->eticket.as<int>();
     b.phi = c->phi.as<double>(); b.src = c->src.as<double>(); b.U = c->ubuf.as<double>(); b.Zbc = c->zbc.as<int>(); b.tab_of = c->tab_of.as<int>();
     b.steps = c->steps.as<dftatom_step>(); b.steps_stride = stride; b.n_active = c->n_active.as<int>();
 

@@ -938,11 +938,14 @@ __global__ void __launch_bounds__(kPT) poisson_full_kernel(GridDev g, PoissonLev
     // Source_0 (PoissonSolver.h:55-74)
     if (a.rho) import_level0(src, a.rho + (size_t)k * N, g.psrc, N);
     else if (a.src_nat) import_level0(src, a.src_nat + (size_t)k * N, nullptr, N);
-    const int n_cycles = a.warm_vcycles > 0 ? a.warm_vcycles : a.max_vcycles;
+    const bool warm = a.warm_vcycles > 0 && a.u_out != nullptr;
+    const int n_cycles = warm ? a.warm_vcycles : a.max_vcycles;
     int fmg_top = 0;                     // top level the full-multigrid ramp has reached (0: only V-cycles are left)
-    if (a.warm_vcycles > 0) {
-        // Warm start (beyond the reference): Phi_0 still holds the previous solve of this density (same boundary values);
-        // the V-cycles contract the difference ~25x each, so a few of them reach the same FP64 fixed point as the full cycle
+    if (warm) {
+        // Warm start (beyond the reference): Phi_0 = the previous solve of this density (u_out, same boundary values); the
+        // V-cycles contract the difference by more than 10x each, so a few of them reach the same FP64 fixed point as the
+        // full cycle from zero
+        import_level0(phi, a.u_out + (size_t)k * N, nullptr, N);
         __syncthreads();
     } else {
         // Initialize (PoissonSolver.cpp:80-106) and the full-multigrid ramp (PoissonSolver.h:89-112)

@@ -280,9 +280,14 @@ void launch_density_update(const GridDev& g, const ScfBuffers& b, cudaStream_t s
 }
 
 // Potential from (U, rho), the five integrals, energies, stop test.  first != 0: only the initial potential.
-__global__ void __launch_bounds__(kAT) potential_energy_kernel(GridDev g, PoissonLevels lv, ScfBuffers b, int first)
+// grid = (atoms, kPotChunks): every CTA owns a contiguous range of nodes; the partial sums of the five integrals go to
+// b.epart, and the CTA that finishes last (per-atom ticket) adds them in chunk order - deterministic - and runs the stop test.
+constexpr int kPotChunks = 8;
+constexpr int kPT2 = 256;
+__global__ void __launch_bounds__(kPT2) potential_energy_kernel(GridDev g, PoissonLevels lv, ScfBuffers b, int first)
 {
     __shared__ double sm[5 * 32];
+    __shared__ int is_last;
     const int a = blockIdx.x;
     AtomState& as = b.astate[a];
     if (as.done) return;
@@ -295,7 +300,9 @@ __global__ void __launch_bounds__(kAT) potential_energy_kernel(GridDev g, Poisso
     const double q = g.delta * g.delta * 0.25;
 
     double e[5] = { 0., 0., 0., 0., 0. };   // nuclear, exccor, eexcDeriv, hartree, potentiale
-    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const int per = (N + kPotChunks - 1) / kPotChunks;
+    const int i0 = blockIdx.y * per, i1 = min(i0 + per, N);
+    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
         double Va = 0., Vb = 0.;
         if (i >= 1) {
             const double r = g.r[i];
@@ -333,6 +340,23 @@ __global__ void __launch_bounds__(kAT) potential_energy_kernel(GridDev g, Poisso
     if (first) return;
     block_sum_n<5>(e, sm);
     if (threadIdx.x == 0) {
+        double* part = b.epart + ((size_t)a * kPotChunks + blockIdx.y) * 5;
+        for (int q = 0; q < 5; ++q) part[q] = e[q];
+        __threadfence();
+        const int ticket = atomicAdd(b.eticket + a, 1);
+        is_last = (ticket == kPotChunks - 1);
+        if (is_last) b.eticket[a] = 0;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const volatile double* part = b.epart + (size_t)a * kPotChunks * 5;
+        for (int q = 0; q < 5; ++q) {
+            double t = 0.;
+            for (int c = 0; c < kPotChunks; ++c) t += part[c * 5 + q];
+            e[q] = t;
+        }
         dftatom_step* rec = b.steps + (size_t)a * b.steps_stride + as.n_steps;
         const double eel = rec->Ekin;                      // parked by density_update_kernel
         const double e_nuc = -kFourPi * e[0];              // DFTAtom.cpp:459-470
@@ -356,7 +380,7 @@ __global__ void __launch_bounds__(kAT) potential_energy_kernel(GridDev g, Poisso
 
 void launch_potential_energy(const GridDev& g, const PoissonLevels& lv, const ScfBuffers& b, int first, cudaStream_t st)
 {
-    potential_energy_kernel<<<b.n_atoms, kAT, 0, st>>>(g, lv, b, first);
+    potential_energy_kernel<<<dim3(b.n_atoms, kPotChunks), kPT2, 0, st>>>(g, lv, b, first);
 }
 
 }  // namespace dft
