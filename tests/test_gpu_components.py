@@ -66,10 +66,15 @@ def test_level_search_matches_oracle(ctx, kind, L, delta, rmax, Z):
     if kind == "screened":
         ns, ls = ns[:6], ls[:6]
     E_o, ok_o = O.level_search(V, delta, rmax, Z, ns, ls, chained=True)
-    for mode in (0, 1):        # 0: fused Sturm-count multisection (production), 1: reference-shaped three-stage search
+    # search_mode 0: Sturm-count search with interpolated ladders (production) in its two shapes - serial in r (one warp
+    # per orbital, r_segments <= 1) and parallel in r (one cluster per orbital, 8 / 32 radial segments);
+    # search_mode 1: reference-shaped three-stage search
+    for mode, segs in ((0, 0), (0, 8), (0, 32), (1, 0)):
         ctx.set_option("search_mode", mode)
+        ctx.set_option("r_segments", segs)
         E_g, ok_g = ctx.level_search(V, L, delta, rmax, Z, ns, ls)
         ctx.set_option("search_mode", 0)
+        ctx.set_option("r_segments", 32)
         np.testing.assert_allclose(E_g, E_o, rtol=0, atol=5e-9)
         assert ok_g.tolist() == ok_o.tolist()
     if kind == "coulomb":
@@ -83,11 +88,13 @@ def test_orbital_matches_oracle(ctx):
     for n, l in [(1, 0), (2, 1), (3, 0), (3, 2), (4, 3)]:
         E = O.level_search(V, delta, rmax, Z, [n], [l], chained=False)[0][0] if l < 3 else -Z * Z / 32.0 - 1e-7
         u_o, mp_o = O.orbital(V, delta, rmax, l, E)
-        for mode in (0, 1):     # 0: segmented transfer-matrix solve (production), 1: serial kernel in the reference's arithmetic
+        # 0: CTA-wide segmented transfer-matrix solve out of shared memory (production), 2: the same by one warp,
+        # 1: serial kernel in the reference's arithmetic
+        for mode in (0, 2, 1):
             ctx.set_option("match_mode", mode)
             u_g, mp_g = ctx.numerov_orbital(V, L, delta, rmax, l, E)
             ctx.set_option("match_mode", 0)
-            assert abs(mp_g - mp_o) <= (0 if mode else 1)      # the match point is an argmax: rounding may move it by one node
+            assert abs(mp_g - mp_o) <= (0 if mode == 1 else 1)      # the match point is an argmax: rounding may move it by one node
             np.testing.assert_allclose(u_g, u_o, rtol=0, atol=1e-10)
 
 

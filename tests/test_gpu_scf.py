@@ -104,6 +104,30 @@ def test_batch_independence_and_determinism(ctx):
             assert [s.E for s in alone.steps] == [s.E for s in other.steps]
 
 
+def test_kernel_shapes_agree(ctx):
+    """The alternative shapes of the hot kernels are the same computation: serial-in-r vs parallel-in-r search, Poisson
+    full cycle vs warm start, CTA-wide vs warp-wide matched solution.  Same trajectories to far below the parity bars."""
+    opts = [D.Options(Z, 12, 20.0, 0.001, 0.5, m) for Z, m in [(4, 0), (18, 0), (26, 1), (47, 0)]]
+    base = ctx.solve_batch(opts)
+    variants = [{"r_segments": 0}, {"seg_threshold": 1 << 20}, {"seg_threshold": 1 << 20, "r_segments": 8}, {"warm_vcycles": 0},
+                {"match_mode": 2}]
+    defaults = {"r_segments": 32, "seg_threshold": 300, "warm_vcycles": 7, "match_mode": 0}
+    for v in variants:
+        for k_, x in v.items():
+            ctx.set_option(k_, x)
+        try:
+            res = ctx.solve_batch(opts)
+        finally:
+            for k_ in v:
+                ctx.set_option(k_, defaults[k_])
+        for r, b in zip(res, base):
+            n = min(r.n_steps, b.n_steps)
+            assert n >= 10, v
+            for k in range(n):
+                assert abs(r.steps[k].Etotal - b.steps[k].Etotal) < 2e-6, (v, k)
+                np.testing.assert_allclose([x for ch in r.steps[k].E for x in ch], [x for ch in b.steps[k].E for x in ch], rtol=0, atol=2e-7)
+
+
 def test_options_validation(ctx):
     """Same ranges as the reference's dialog validators (OptionsFrame.cpp:46,152-173); mixed grids are refused."""
     for bad in (D.Options(0, 10, 15.0, 0.004, 0.5, 0), D.Options(119, 10, 15.0, 0.004, 0.5, 0), D.Options(2, 10, 0.5, 0.004, 0.5, 0),
