@@ -238,15 +238,33 @@ def run_cuda_arm(a):
                         note="every rank solves one full sweep; 89/92 atoms meet the reference's stop test, Z=68-70 run to the 100-step cap like the reference"),
             e2e=dict(value=n_atoms_total / wall, unit="atoms/s", h2d_bytes_per_step=opt_bytes, d2h_bytes_per_step=res_bytes),
             gpu_launches=int(launches),
-            roofline=dict(kernel="search_round_kernel (Numerov shooting, multisection)", bound="fp64", achieved=achieved, peak=peak, unit="TFLOP/s",
+            roofline=dict(kernel="search_fused_kernel + search_seg_kernel (Numerov shooting: Sturm-count search, serial-in-r / parallel-in-r)",
+                          bound="fp64", achieved=achieved, peak=peak, unit="TFLOP/s",
                           frac=achieved / peak if peak else None, traffic=None,
                           peak_source="measured live: DFMA microbench in libdftatom_b200 (MEASURED_PEAKS.json has no FP64 entry)",
                           flop_per_lane_node_step=FLOP_PER_NODE_STEP, lane_node_steps=s["work"], kernel_ms=s["ms"], share_of_step=shares),
             kernels={k: dict(ms=v["ms"], launches=int(v["launches"]), work=v["work"]) for k, v in prof.items()},
+            search=dict(orbital_solves=prof["match"]["work"], rounds_per_solve=prof["density"]["work"] / max(1.0, prof["match"]["work"]),
+                        inward_sweeps_per_solve_reference=140, note="one round = 32 concurrent inward sweeps"),
+            poisson=dict(solves=int(prof["poisson"]["launches"]) * len(opts), gs_node_updates=prof["poisson"]["work"], ms=prof["poisson"]["ms"],
+                         gs_updates_per_s=prof["poisson"]["work"] / (prof["poisson"]["ms"] * 1e-3) if prof["poisson"]["ms"] else None,
+                         bound="shared memory / L2 latency (grid resident on chip at 16385 nodes; compulsory HBM traffic 16 N B per solve)"),
             clocks=clocks,
         )
         if strong:
             line["strong_c3"] = strong
+        if world == 1 and not a.no_rn:
+            # second half of BASELINE.json's metric: wall-ms of one Radon SCF (C2: Z=86 LSDA, 17 levels = 131073 nodes, delta 1e-4,
+            # mixing 0.5, Rmax 50) through the same public call, host options in, host results out; warm-up run first
+            rn = [D.Options(86, 17, 50.0, 0.0001, 0.5, 1)]
+            ctx.solve_batch(rn, keep_steps=False)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            r_rn = ctx.solve_batch(rn, keep_steps=False)[0]
+            rn_ms = (time.perf_counter() - t1) * 1e3
+            line["rn_scf"] = dict(metric="Rn SCF ms", value=rn_ms, unit="ms", device_ms=ctx.last_timing()[0], scf_steps=r_rn.n_steps, finished=bool(r_rn.finished),
+                                  Etotal=r_rn.Etotal, workload="C2 Radon Z=86 LSDA, 17 levels (131073 nodes), delta 0.0001, mixing 0.5, Rmax 50",
+                                  reference_cpu_seconds_1core=518.0, reference_source="SURVEY.md section 6 (unmodified reference, g++ -O2, one core)")
         if world == 1 and not a.no_cpu_baseline:
             cb = cpu_reference_sample(30.0)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -263,6 +281,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-rn", action="store_true", help="skip the Radon (C2) SCF timing")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference_arm(a)

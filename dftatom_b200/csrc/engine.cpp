@@ -358,9 +358,9 @@ int dftatom_solve_batch(dftatom_ctx* c, const dftatom_options* opts, int n_atoms
     std::vector<Span> spans;
     const bool prof = c->profile != 0;
     unsigned long long* d_work = nullptr;
-    if ((rc = c->scratch[7].ensure(sizeof(unsigned long long) * 8))) return rc;
+    if ((rc = c->scratch[7].ensure(sizeof(unsigned long long) * 32))) return rc;
     d_work = c->scratch[7].as<unsigned long long>();
-    DFT_CHECK(cudaMemsetAsync(d_work, 0, sizeof(unsigned long long) * 8, st));
+    DFT_CHECK(cudaMemsetAsync(d_work, 0, sizeof(unsigned long long) * 32, st));
     pa.work = d_work + DFTATOM_K_POISSON;
     auto begin_span = [&](int cls) { if (prof) { Span s{ cls, nullptr, nullptr }; cudaEventCreate(&s.a); cudaEventCreate(&s.b); cudaEventRecord(s.a, st); spans.push_back(s); } };
     auto end_span = [&]() { if (prof) cudaEventRecord(spans.back().b, st); };
@@ -426,8 +426,13 @@ int dftatom_solve_batch(dftatom_ctx* c, const dftatom_options* opts, int n_atoms
     DFT_CHECK(cudaEventElapsedTime(&ms, ev0, ev1));
     c->last_ms = ms; c->last_launches = launches;
     {
-        unsigned long long hw[8] = {};
+        unsigned long long hw[32] = {};
         DFT_CHECK(cudaMemcpy(hw, d_work, sizeof(hw), cudaMemcpyDeviceToHost));
+        if (prof && getenv("DFTATOM_DEBUG_ROUNDS")) {
+            fprintf(stderr, "search rounds histogram (orbital solves with r rounds, r = 1..15+):");
+            for (int r = 1; r < 16; ++r) fprintf(stderr, " %llu", hw[8 + r]);
+            fprintf(stderr, "\n");
+        }
         for (int k = 0; k < DFTATOM_K_COUNT; ++k) { c->prof[k].ms = 0.; c->prof[k].launches = 0; c->prof[k].work = (double)hw[k]; }
         for (Span& s : spans) {
             float t = 0.f;

@@ -20,6 +20,7 @@
 //     W_{i-1} = (12 - 10 d_i) W_i - d_i d_{i+1} W_{i+1}     (5.5 FP64 instructions per lane and node).
 // Sign bits are shifted into a register (one SHF per node) and popcounted per tile.
 #include "numerov_common.cuh"
+#include <cstdio>
 
 namespace dft {
 
@@ -85,7 +86,11 @@ __global__ void __launch_bounds__(128, 1) search_fused_kernel(GridDev g, const d
     b.lo = -Z * Z - 1.; b.hi = kTopEnergy;                // DFTAtom.cpp:407,499
     b.ylog = 0.;
     b.ladder = warm_start && ss[k].pad == 1;              // the previous step's eigenvalue is a valid centre
-    b.c_est = ss[k].E; b.radius = 8.4;
+    // first ladder: the levels move geometrically from one SCF step to the next (linear mixing), by tens of Hartree in
+    // the first steps; centre = previous eigenvalue + last shift x (ratio of the last two shifts), radius = 1.5 x last shift
+    const double e_prev = ss[k].E, s1 = ss[k].up_lo, s2 = ss[k].up_hi;
+    const double ratio = (s2 != 0. && fabs(s1) < fabs(s2)) ? s1 / s2 : 0.;
+    b.c_est = fmin(fmax(e_prev + s1 * ratio, b.lo), b.hi); b.radius = fmin(fmax(1.5 * fabs(s1), 1e-3), Z * Z + 51.);
     long long steps = 0;
     int rounds = 0;
     for (int round = 0; round < 64 && bracket_open(b.lo, b.hi); ++round) {
@@ -107,6 +112,8 @@ __global__ void __launch_bounds__(128, 1) search_fused_kernel(GridDev g, const d
         s.y0_log2 = b.ylog;
         s.converged = (b.hi - b.lo < kEnergyTol) && (b.ylog < 49.828921423310435); // DFTAtom.cpp:528
         s.stage = 3;
+        s.up_hi = s.pad == 1 ? s.up_lo : 0.;                                 // the last two shifts of the level
+        s.up_lo = s.pad == 1 ? b.lo - e_prev : Z * Z;
         s.pad = 1;                                                           // E is a valid warm start for the next step
         ss[k] = s;
     }
@@ -117,6 +124,7 @@ __global__ void __launch_bounds__(128, 1) search_fused_kernel(GridDev g, const d
             atomicAdd(work, (unsigned long long)steps);
             atomicAdd(work + DFTATOM_K_MATCH, 1ULL);                          // orbital solves
             atomicAdd(work + DFTATOM_K_DENSITY, (unsigned long long)rounds);  // search rounds
+            atomicAdd(work + 8 + min(rounds, 15), 1ULL);                      // histogram (debug aid)
         }
     }
 }

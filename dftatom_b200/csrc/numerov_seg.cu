@@ -62,7 +62,11 @@ __global__ void __launch_bounds__(32 * kSegWarps) search_seg_kernel(GridDev g, c
     b.lo = -Z * Z - 1.; b.hi = kTopEnergy;                // DFTAtom.cpp:407,499
     b.ylog = 0.;
     b.ladder = warm_start && ss[k].pad == 1;
-    b.c_est = ss[k].E; b.radius = 8.4;
+    // first ladder: the levels move geometrically from one SCF step to the next (linear mixing), by tens of Hartree in
+    // the first steps; centre = previous eigenvalue + last shift x (ratio of the last two shifts), radius = 1.5 x last shift
+    const double e_prev = ss[k].E, s1 = ss[k].up_lo, s2 = ss[k].up_hi;
+    const double ratio = (s2 != 0. && fabs(s1) < fabs(s2)) ? s1 / s2 : 0.;
+    b.c_est = fmin(fmax(e_prev + s1 * ratio, b.lo), b.hi); b.radius = fmin(fmax(1.5 * fabs(s1), 1e-3), Z * Z + 51.);
     long long steps = 0;
     int rounds = 0;
 
@@ -169,6 +173,8 @@ __global__ void __launch_bounds__(32 * kSegWarps) search_seg_kernel(GridDev g, c
         s.y0_log2 = b.ylog;
         s.converged = (b.hi - b.lo < kEnergyTol) && (b.ylog < 49.828921423310435); // DFTAtom.cpp:528
         s.stage = 3;
+        s.up_hi = s.pad == 1 ? s.up_lo : 0.;                                 // the last two shifts of the level
+        s.up_lo = s.pad == 1 ? b.lo - e_prev : Z * Z;
         s.pad = 1;
         ss[k] = s;
     }
@@ -179,6 +185,7 @@ __global__ void __launch_bounds__(32 * kSegWarps) search_seg_kernel(GridDev g, c
             atomicAdd(work, (unsigned long long)steps);
             atomicAdd(work + DFTATOM_K_MATCH, 1ULL);                          // orbital solves
             atomicAdd(work + DFTATOM_K_DENSITY, (unsigned long long)rounds);  // search rounds
+            atomicAdd(work + 8 + min(rounds, 15), 1ULL);                      // histogram (debug aid)
         }
     }
 }
