@@ -10,11 +10,14 @@ __device__ __forceinline__ int hi32(double x) { return __double2hiint(x); }
 // Numerov.h:119-136: bisection on the index for far(idx) = exp(-r_idx sqrt(2|E|) - idx δ/2) < 1e-200
 __device__ __forceinline__ int start_index(const GridDev& g, double kappa)
 {
+    // r_i = Rp (e^{δ i} - 1) evaluated in place of the table: 14 dependent table loads would cost ~5000 cycles per call
+    // (L2 latency) on kernels whose whole round is ~50000; a last-ulp difference can move the index by one node, where the
+    // solution is 1e-200
     int hi = g.N - 1, lo = 1;
     const double hd = 0.5 * g.delta;
     while (hi - lo > 1) {
         const int mid = (hi + lo) >> 1;
-        const double arg = -__ldg(g.r + mid) * kappa - (double)mid * hd;
+        const double arg = -(g.rp * expm1(g.delta * (double)mid)) * kappa - (double)mid * hd;
         if (arg < kFarLog) hi = mid; else lo = mid;
     }
     return hi;

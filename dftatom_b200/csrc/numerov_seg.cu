@@ -31,6 +31,8 @@ struct SegShared {                 // one per CTA: the results of its 4 segments
     double m[4][kSegWarps][32];    // normal: transfer matrix (ww, wd, dw, dd); seeded: outgoing state (W, D) in [0], [1]
     double pseg[kSegWarps][32];    // product of d_i d_{i+1} over the even nodes of the segment (nodes <= start)
     double y0s[32], d1[32];        // bottom segment: scaled y0 and d_1 per energy
+    double ct[4][32];              // the composition of this CTA's 4 segment maps (same encoding), kind in ctk
+    int ctk[32];
     int meta[kSegWarps][32];       // kind (bits 0-1: 0 idle, 1 normal, 2 seeded) | sign of y at the lowest node (bit 2) | sign changes inside the segment << 3
     int bad[32];
 };
@@ -104,24 +106,47 @@ __global__ void __launch_bounds__(32 * kSegWarps) search_seg_kernel(GridDev g, c
             sh.m[1][wl][lane] = o.W[1]; sh.m[3][wl][lane] = o.D[1];      // normal: (wd, dd)
             if (w == 0) sh.bad[lane] = 0;
             if (kind == 2 && is_bottom) { sh0->y0s[lane] = o.Y0s[0]; sh0->d1[lane] = o.d_first[0]; }
+            // the map of the whole CTA (its 4 segments in order): identity / matrix / constant state
+            __syncthreads();
+            if (wl == 0) {
+                int ck = 0;
+                double c0 = 1., c1 = 0., c2 = 0., c3 = 1.;
+#pragma unroll
+                for (int vl = 0; vl < kSegWarps; ++vl) {
+                    const int kv = sh.meta[vl][lane] & 3;
+                    const double m0 = sh.m[0][vl][lane], m1 = sh.m[1][vl][lane], m2 = sh.m[2][vl][lane], m3 = sh.m[3][vl][lane];
+                    if (kv == 2) { ck = 2; c0 = m0; c2 = m2; }
+                    else if (kv == 1) {
+                        if (ck == 2) { const double na = fma(m0, c0, m1 * c2), nb = fma(m2, c0, m3 * c2); c0 = na; c2 = nb; }
+                        else if (ck == 1) {
+                            const double n0 = fma(m0, c0, m1 * c2), n1 = fma(m0, c1, m1 * c3), n2 = fma(m2, c0, m3 * c2), n3 = fma(m2, c1, m3 * c3);
+                            c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+                        } else { ck = 1; c0 = m0; c1 = m1; c2 = m2; c3 = m3; }
+                    }
+                }
+                sh.ctk[lane] = ck;
+                sh.ct[0][lane] = c0; sh.ct[1][lane] = c1; sh.ct[2][lane] = c2; sh.ct[3][lane] = c3;
+            }
             cluster.sync();
             if (kind == 2 && o.bad) atomicOr(&sh0->bad[lane], 1);
         }
         // ---------------- scan: entry state of this segment ----------------
         double A = 0., Bd = 0.;
         if (kind == 1) {
+            // the CTAs before this one (their composed maps, distributed shared memory), then the warps before this one
 #pragma unroll 4
-            for (int v = 0; v < w; ++v) {
-                const SegShared* r = cluster.map_shared_rank(&sh, v / kSegWarps);
-                const int vl = v % kSegWarps;
-                const int kv = r->meta[vl][lane] & 3;
-                const double m0 = r->m[0][vl][lane], m1 = r->m[1][vl][lane], m2 = r->m[2][vl][lane], m3 = r->m[3][vl][lane];
+            for (int rk = 0; rk < rank; ++rk) {
+                const SegShared* r = cluster.map_shared_rank(&sh, rk);
+                const int kv = r->ctk[lane];
+                const double m0 = r->ct[0][lane], m1 = r->ct[1][lane], m2 = r->ct[2][lane], m3 = r->ct[3][lane];
                 if (kv == 2) { A = m0; Bd = m2; }
-                else if (kv == 1) {
-                    const double na = fma(m0, A, m1 * Bd);
-                    const double nb = fma(m2, A, m3 * Bd);
-                    A = na; Bd = nb;
-                }
+                else if (kv == 1) { const double na = fma(m0, A, m1 * Bd), nb = fma(m2, A, m3 * Bd); A = na; Bd = nb; }
+            }
+            for (int vl = 0; vl < wl; ++vl) {
+                const int kv = sh.meta[vl][lane] & 3;
+                const double m0 = sh.m[0][vl][lane], m1 = sh.m[1][vl][lane], m2 = sh.m[2][vl][lane], m3 = sh.m[3][vl][lane];
+                if (kv == 2) { A = m0; Bd = m2; }
+                else if (kv == 1) { const double na = fma(m0, A, m1 * Bd), nb = fma(m2, A, m3 * Bd); A = na; Bd = nb; }
             }
         }
         // ---------------- pass 2: the real solution through the normal segments, counting sign changes ----------------
