@@ -253,6 +253,17 @@ def run_cuda_arm(a):
         )
         if strong:
             line["strong_c3"] = strong
+        if world == 1 and not a.no_batch:
+            # the same sweep replicated 8x in ONE batch (736 atoms): C3 as given is bounded by the SCF chain of its slowest atoms
+            # (from step ~35 on fewer than 30 atoms are left), a larger batch shows what the kernels sustain when the GPU is full
+            big = opts * 8
+            ctx.solve_batch(big, keep_steps=False)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            ctx.solve_batch(big, keep_steps=False)
+            tb = time.perf_counter() - t1
+            line["batch_8xC3"] = dict(value=len(big) / tb, unit="atoms/s", atoms=len(big), seconds=tb, device_ms=ctx.last_timing()[0],
+                                      note="8 copies of the Z=1-92 sweep in one dftatom_solve_batch call, host options in, host results out")
         if world == 1 and not a.no_rn:
             # second half of BASELINE.json's metric: wall-ms of one Radon SCF (C2: Z=86 LSDA, 17 levels = 131073 nodes, delta 1e-4,
             # mixing 0.5, Rmax 50) through the same public call, host options in, host results out; warm-up run first
@@ -282,6 +293,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-rn", action="store_true", help="skip the Radon (C2) SCF timing")
+    ap.add_argument("--no-batch", action="store_true", help="skip the replicated-batch (8 x C3) throughput figure")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference_arm(a)
