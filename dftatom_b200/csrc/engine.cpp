@@ -52,6 +52,7 @@ struct dftatom_ctx {
     int refine_vcycles = 0;
     int warm_vcycles = 7;      // Poisson warm start from SCF step warm_after on: V-cycles per solve (0 = always the full cycle)
     int warm_after = 4;
+    int team_poisson = 1;      // large grids, few atoms: several CTAs per density (poisson.cu, team mode)
     int r_segments = 32;       // radial segments per orbital of the parallel-in-r search (<= 1: serial-in-r search only)
     int seg_threshold = 300;   // the parallel-in-r search takes over once at most this many orbitals are still active
     int profile = 0;
@@ -61,7 +62,7 @@ struct dftatom_ctx {
     int warm_start = 1;
     dftatom_kernel_profile prof[DFTATOM_K_COUNT] = {};
     // reusable buffers
-    DevBuf atoms, astate, orbs, ss, rho, rhot, vpot, atab, psi, match_pt, inv_norm, epart, eticket, phi, src, u0, ubuf, zbc, tab_of, steps, n_active;
+    DevBuf atoms, astate, orbs, ss, rho, rhot, vpot, atab, psi, match_pt, inv_norm, epart, eticket, team_bar, phi, src, u0, ubuf, zbc, tab_of, steps, n_active;
     DevBuf scratch[8];
     int* h_active = nullptr;       // pinned
     // timing of the last solve
@@ -168,7 +169,7 @@ void dftatom_destroy(dftatom_ctx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto& kv : c->grids) kv.second.mem.release();
-    DevBuf* all[] = { &c->atoms, &c->astate, &c->orbs, &c->ss, &c->rho, &c->rhot, &c->vpot, &c->atab, &c->psi, &c->match_pt, &c->inv_norm, &c->epart, &c->eticket,
+    DevBuf* all[] = { &c->atoms, &c->astate, &c->orbs, &c->ss, &c->rho, &c->rhot, &c->vpot, &c->atab, &c->psi, &c->match_pt, &c->inv_norm, &c->epart, &c->eticket, &c->team_bar,
                       &c->phi, &c->src, &c->u0, &c->ubuf, &c->zbc, &c->tab_of, &c->steps, &c->n_active };
     for (DevBuf* b : all) b->release();
     for (DevBuf& b : c->scratch) b.release();
@@ -186,6 +187,7 @@ int dftatom_set_option(dftatom_ctx* c, const char* key, double value)
     else if (k == "refine_vcycles") c->refine_vcycles = std::max(0, (int)value);
     else if (k == "warm_vcycles") c->warm_vcycles = std::max(0, (int)value);
     else if (k == "warm_after") c->warm_after = std::max(0, (int)value);
+    else if (k == "team_poisson") c->team_poisson = value != 0.;
     else if (k == "r_segments") c->r_segments = (int)value;
     else if (k == "seg_threshold") c->seg_threshold = (int)value;
     else if (k == "profile") c->profile = value != 0.;
@@ -344,6 +346,8 @@ int dftatom_solve_batch(dftatom_ctx* c, const dftatom_options* opts, int n_atoms
     pa.skip = &b.astate[0].done; pa.skip_stride_bytes = (int)sizeof(AtomState);
     pa.max_vcycles = c->max_vcycles; pa.floor_stop = c->floor_stop;
     pa.refine_vcycles = c->refine_vcycles; pa.u0 = c->u0.as<double>();
+    if ((rc = c->team_bar.ensure(sizeof(unsigned) * (size_t)n_atoms))) return rc;
+    pa.team_bar = c->team_poisson ? c->team_bar.as<unsigned>() : nullptr;
 
     cudaEvent_t ev0, ev1;
     DFT_CHECK(cudaEventCreate(&ev0));
@@ -623,6 +627,8 @@ int dftatom_poisson_solve(dftatom_ctx* c, int levels, double delta, double max_r
     pa.max_vcycles = c->max_vcycles; pa.floor_stop = c->floor_stop; pa.vcycles_used = dv.as<int>();
     if ((rc = c->u0.ensure(sizeof(double) * (size_t)n_dens * N)) || (rc = c->ubuf.ensure(sizeof(double) * (size_t)n_dens * N))) return rc;
     pa.refine_vcycles = c->refine_vcycles; pa.u0 = c->u0.as<double>(); pa.u_out = c->ubuf.as<double>(); pa.coarse_op = g.coarse_op;
+    if ((rc = c->team_bar.ensure(sizeof(unsigned) * (size_t)n_dens))) return rc;
+    pa.team_bar = c->team_poisson ? c->team_bar.as<unsigned>() : nullptr;
     if (c->profile) {
         if ((rc = c->scratch[5].ensure(sizeof(long long) * 128))) return rc;
         DFT_CHECK(cudaMemsetAsync(c->scratch[5].p, 0, sizeof(long long) * 128, st));

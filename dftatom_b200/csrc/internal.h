@@ -132,6 +132,8 @@ struct PoissonArgs {
     int skip_stride_bytes;
     int max_vcycles; int floor_stop;
     int warm_vcycles;       // > 0: keep Phi_0 of the previous solve as the initial guess and run this many V-cycles (no FMG ramp)
+    int team_G;             // set by the launcher: CTAs per density (team mode, poisson.cu), 1 = off
+    unsigned* team_bar;     // [n_dens] scratch for the team barriers (or NULL: no team mode)
     int smem_doubles;       // set by the launcher: doubles per shared-memory array of the coarse levels
     int refine_vcycles;     // > 0: double-double defect correction with this many V-cycles on the error equation
     double* u0;             // [n_dens][N] scratch for the correction (required when refine_vcycles > 0)

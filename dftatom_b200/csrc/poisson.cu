@@ -21,6 +21,7 @@
 // The update norm of the reference's IterateGaussSeidel only drives its early exits; with a fixed number of sweeps it
 // is evaluated once, for the last fine-grid sweep of the solve, and only when the caller asks for it.
 #include "internal.h"
+#include <algorithm>
 #include <cmath>
 
 namespace dft {
@@ -94,6 +95,11 @@ struct PoissonSmem {
     double* gphi; double* gsrc;   // this density's block of the global hierarchy arrays
     long long* dbg;      // optional cycle counters (development aid): [0,24) smooth, [24,48) restrict, [48,72) prolong, [72,96) visits
     int L, m, has_G;     // levels; level with 32 owned nodes that the dense operator starts from (valid when has_G)
+    // team mode (large grids, few densities): team_G CTAs per density; rank 0 (the leader) runs the levels of <= 16384 nodes
+    // as always, the others (workers) share every visit of the larger levels (big_visit); 0 / 1 = off
+    int team_G, team_rank;
+    unsigned* team_bar;  // arrival counter of this density's team (global memory, zero at launch)
+    unsigned team_epoch;
     double wtot[16];     // per-warp totals of the local affine maps
     double edge[16];     // first node of every warp (old value for the left neighbour warp)
     double red[32];
@@ -115,7 +121,8 @@ struct Ref {
     double* g;
     static __device__ __forceinline__ Ref P(int l) { const LevelConst& c = g_sm.lc[l]; return Ref{ c.wp, c.op, g_sm.gphi }; }
     static __device__ __forceinline__ Ref S(int l) { const LevelConst& c = g_sm.lc[l]; return Ref{ c.ws, c.os, g_sm.gsrc }; }
-    __device__ __forceinline__ double ld(int i) const { return w == kWarp ? g_sm.w[off + i] : (w == kDyn ? g_dyn[off + i] : g[off + i]); }
+    // global arrays are read with ld.cg: in team mode other CTAs write them between visits (L1 is not coherent across SMs)
+    __device__ __forceinline__ double ld(int i) const { return w == kWarp ? g_sm.w[off + i] : (w == kDyn ? g_dyn[off + i] : __ldcg(g + off + i)); }
     __device__ __forceinline__ void st(int i, double v) const
     {
         if (w == kWarp) g_sm.w[off + i] = v; else if (w == kDyn) g_dyn[off + i] = v; else g[off + i] = v;
@@ -408,7 +415,7 @@ __device__ __noinline__ void fused_block(int l, int flags, int sweeps)
         } else {
 #pragma unroll
             for (int k = 0; k < NPT; ++k) {
-                const double c = fma(bcoef, (k + 1 < NPT) ? phi[k + 1] : nb, 0.5 * gs[k * kPT + t]);
+                const double c = fma(bcoef, (k + 1 < NPT) ? phi[k + 1] : nb, 0.5 * __ldcg(gs + k * kPT + t));
                 x = (t == 0 && k == 0) ? phi[0] : fma(a, x, c);
                 phi[k] = x;
             }
@@ -584,13 +591,18 @@ __device__ __forceinline__ void prolong_nodes(Ref pc, Lay yc, Ref pf, Lay yf, in
 // CTA.  The heavy bodies are __noinline__ functions of the level index only (a fat inlined dispatcher costs hundreds of
 // spill instructions per call), the wrappers that carry the per-thread `pending` flag are inlined.
 // ---------------------------------------------------------------------------------------------------------
-struct Ctl { bool pending; };    // warp 0 wrote coarse levels that the other warps have not synchronised with yet
+struct Ctl {
+    bool pending;        // warp 0 wrote coarse levels that the other warps have not synchronised with yet
+    bool small_done;     // team mode: the leader has worked on its own levels since the last team barrier
+};
 
 __device__ __forceinline__ void block_begin(Ctl& ctl) { if (ctl.pending) { __syncthreads(); ctl.pending = false; } }
 
 // per-level constants and placement (threads 0..L-1 fill one level each; every thread computes the same placement)
+constexpr int kTeamLevelNodes = kPT * kMaxNpt;     // team mode: levels with more nodes than this are shared by the team
+
 __device__ __noinline__ void hierarchy_setup(const PoissonLevels& lv, double delta, double* gphi, double* gsrc, int dyn_doubles,
-                                             const double* Gg, long long* dbg)
+                                             const double* Gg, long long* dbg, int team_G = 1, int team_rank = 0, unsigned* team_bar = nullptr)
 {
     const int l = threadIdx.x;
     if (l < lv.L) {
@@ -637,12 +649,19 @@ __device__ __noinline__ void hierarchy_setup(const PoissonLevels& lv, double del
             }
             doff += need; avail -= need;
         }
+        if (team_G > 1) {
+            // the team's levels: natural node order in global memory (every CTA reads and writes contiguous windows);
+            // the first level below them is written by the workers and read by the leader: global memory as well
+            if (c.n > kTeamLevelNodes) { c.lay.lgT = 0; c.lay.lg = 0; c.wp = c.ws = kGlobal; c.op = c.os = lv.off[l]; }
+            else if (l > 0 && lv.size[l - 1] - 1 > kTeamLevelNodes) { c.wp = c.ws = kGlobal; c.op = c.os = lv.off[l]; }
+        }
         g_sm.lc[l] = c;
     }
     if (threadIdx.x == 0) {
         g_sm.gphi = gphi; g_sm.gsrc = gsrc; g_sm.dbg = dbg;
         g_sm.L = lv.L; g_sm.m = lv.L - 5; g_sm.has_G = (Gg != nullptr && lv.L - 5 >= 1) ? 1 : 0;
         g_sm.updates = 0;
+        g_sm.team_G = team_G; g_sm.team_rank = team_rank; g_sm.team_bar = team_bar; g_sm.team_epoch = 0;
     }
     if (Gg != nullptr && lv.L - 5 >= 1) for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) g_sm.G[i] = Gg[i];
     __syncthreads();
@@ -803,6 +822,181 @@ __device__ __noinline__ double cycle(Ctl& ctl, int from, int to, double* norm_sc
     for (int s = threadIdx.x; s < N; s += blockDim.x) { const double dif = norm_scratch[s] - p0.ld(s); e2 = fma(dif, dif, e2); }
     return sqrt(block_sum(e2));
 }
+// ---------------------------------------------------------------------------------------------------------
+// Team mode.  A level visit (3 or 6 lexicographic sweeps) only needs old values up to `sweeps` nodes to the right of a
+// node and, because a ~ 1/2, new values up to ~64 nodes to its left per sweep (a^64 < 1e-19).  A slab of a large level
+// can therefore be swept by one CTA on its own, from a window that extends the slab by a halo (HL = 128 / 256 nodes on
+// the left for 3 / 6 sweeps, 8 on the right) whose ends are held fixed at their old values: inside the slab the result is
+// the lexicographic sweep of the whole level to FP64 resolution, and the CTAs of a team need no carry exchange inside a
+// visit - only a barrier between visits.  The window lives in shared memory (coalesced global reads and writes).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool team_level(int l) { return g_sm.team_G > 1 && g_sm.lc[l].n > kTeamLevelNodes; }
+
+__device__ __forceinline__ void team_barrier()
+{
+    if (g_sm.team_G <= 1) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned target = (unsigned)g_sm.team_G * (++g_sm.team_epoch);
+        atomicAdd(g_sm.team_bar, 1u);
+        while (*(volatile unsigned*)g_sm.team_bar < target) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+constexpr int kHaloR = 8;
+__host__ __device__ inline int team_halo_left(int sweeps) { return sweeps > 3 ? 256 : 128; }
+// nodes per thread of the window of a team visit: the smallest of 4, 8, 16 whose slabs cover the level with `workers` CTAs (0: none)
+__host__ __device__ inline int team_npt(int n, int sweeps, int workers)
+{
+    for (int npt = 4; npt <= 16; npt *= 2) {
+        const int slab = kPT * npt - team_halo_left(sweeps) - kHaloR;
+        if ((n + slab - 1) / slab <= workers) return npt;
+    }
+    return 0;
+}
+
+template <int NPT>
+__device__ __noinline__ void big_visit(int l, int flags, int sweeps)
+{
+    const unsigned full = 0xffffffffu;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const LevelConst& lc = g_sm.lc[l];
+    const LevelConst& lcc = g_sm.lc[l + 1];
+    const int n = lc.n;
+    const int HL = team_halo_left(sweeps);
+    const int slab = kPT * NPT - HL - kHaloR;
+    const int wk = g_sm.team_rank - 1;
+    const int a0 = wk * slab;
+    if (a0 >= n) return;                                   // more workers than slabs
+    const int b0 = min(a0 + slab, n);
+    constexpr int W = kPT * NPT;                           // owned nodes of the window; node W is its fixed right end
+    int wa = max(a0 - HL, 0);
+    if (wa + W > n) wa = n - W;
+    // window arrays in dynamic shared memory, node j at j + j / NPT (conflict-free per-thread chunks and coalesced copies)
+    constexpr int WS = W + W / NPT + 2;
+    double* phiL = g_dyn;
+    double* srcL = g_dyn + WS;
+    double* cL = g_dyn + 2 * WS;                           // coarse window (prolongation)
+    const double* gp = g_sm.gphi + lc.op;
+    const double* gs = g_sm.gsrc + lc.os;
+    for (int j = t; j <= W; j += kPT) {
+        const int sj = j + j / NPT;
+        phiL[sj] = (flags & kLoadPhi) ? __ldcg(gp + wa + j) : 0.;
+        srcL[sj] = __ldcg(gs + wa + j);
+    }
+    if (flags & kProlongIn) {
+        const Ref Pc = Ref::P(l + 1);
+        const Lay yc = lcc.lay;
+        for (int q = t; q <= W / 2 + 1; q += kPT) cL[q] = Pc.ld(slot(min(wa / 2 + q, lcc.n), yc));
+        __syncthreads();
+        for (int j = t; j <= W; j += kPT) {
+            const int sj = j + j / NPT;
+            phiL[sj] += (j & 1) ? 0.5 * (cL[(j - 1) >> 1] + cL[(j + 1) >> 1]) : cL[j >> 1];
+        }
+    }
+    __syncthreads();
+    // sweeps: thread t owns window nodes [t NPT, (t+1) NPT); nodes 0 and W are fixed
+    const double a = lc.a, bcoef = lc.bcoef;
+    double phi[NPT], src[NPT];
+#pragma unroll
+    for (int k = 0; k < NPT; ++k) { phi[k] = phiL[t * (NPT + 1) + k]; src[k] = 0.5 * srcL[t * (NPT + 1) + k]; }
+    const double right = phiL[W + W / NPT];
+    double Ap[5];
+    {
+        double A = a;
+#pragma unroll
+        for (int k = 1; k < NPT; k <<= 1) A *= A;
+        Ap[0] = A;
+#pragma unroll
+        for (int j = 1; j < 5; ++j) Ap[j] = Ap[j - 1] * Ap[j - 1];
+    }
+    const double B = Ap[4] * Ap[4];
+    double Am[5];
+    double Alane = 1.;
+    int nsteps = 5;
+#pragma unroll
+    for (int j = 4; j >= 0; --j) if (Ap[j] < kTiny) nsteps = j;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        Am[j] = (lane >= (1 << j) && j < nsteps) ? Ap[j] : 0.;
+        if ((lane >> j) & 1) Alane *= Ap[j];
+    }
+    if (t == 0) g_sm.updates += (unsigned long long)sweeps * (unsigned long long)(b0 - a0);
+    for (int sw = 0; sw < sweeps; ++sw) {
+        double nb = __shfl_down_sync(full, phi[0], 1);
+        if (lane == 0) g_sm.edge[w] = phi[0];
+        __syncthreads();
+        if (lane == 31 && w + 1 < (kPT >> 5)) nb = g_sm.edge[w + 1];
+        if (t == kPT - 1) nb = right;
+        double x = 0.;
+#pragma unroll
+        for (int k = 0; k < NPT; ++k) {
+            const double c = fma(bcoef, (k + 1 < NPT) ? phi[k + 1] : nb, src[k]);
+            x = (t == 0 && k == 0) ? phi[0] : fma(a, x, c);
+            phi[k] = x;
+        }
+        double Pw = x;
+        Pw = fma(Am[0], __shfl_up_sync(full, Pw, 1), Pw);
+        if (nsteps > 1) {
+            Pw = fma(Am[1], __shfl_up_sync(full, Pw, 2), Pw);
+            if (nsteps > 2) {
+                Pw = fma(Am[2], __shfl_up_sync(full, Pw, 4), Pw);
+                Pw = fma(Am[3], __shfl_up_sync(full, Pw, 8), Pw);
+                Pw = fma(Am[4], __shfl_up_sync(full, Pw, 16), Pw);
+            }
+        }
+        if (lane == 31) g_sm.wtot[w] = Pw;
+        __syncthreads();
+        double carry = 0.;
+        {
+            double bp = 1.;
+            for (int k = 1; k <= w && bp >= kTiny; ++k) { carry = fma(bp, g_sm.wtot[w - k], carry); bp *= B; }
+        }
+        double Pex = __shfl_up_sync(full, Pw, 1);
+        if (lane == 0) Pex = 0.;
+        double cin = fma(Alane, carry, Pex);
+        if (t == 0) cin = 0.;
+        double q = a;
+#pragma unroll
+        for (int k = 0; k < NPT; ++k) { phi[k] = fma(q, cin, phi[k]); q *= a; }
+    }
+#pragma unroll
+    for (int k = 0; k < NPT; ++k) phiL[t * (NPT + 1) + k] = phi[k];
+    __syncthreads();
+    // the slab (and the right boundary node of the level, if it ends the slab) back to global memory
+    double* gpw = g_sm.gphi + lc.op;
+    for (int i = a0 + t; i < b0; i += kPT) { const int j = i - wa; gpw[i] = phiL[j + j / NPT]; }
+    if (b0 == n && t == 0) gpw[n] = phiL[W + W / NPT];     // wa + W == n for the last slab
+    if (flags & kRestrictOut) {
+        const Ref Sc = Ref::S(l + 1);
+        const Lay yc = lcc.lay;
+        const double dc = lcc.d;
+        for (int i = a0 / 2 + t; i < b0 / 2; i += kPT) {
+            double v = 0.;
+            if (i > 0) {
+                const int j = 2 * i - wa;
+                const double lft = phiL[(j - 1) + (j - 1) / NPT], mid = phiL[j + j / NPT], rgt = phiL[(j + 1) + (j + 1) / NPT];
+                v = 4. * (srcL[j + j / NPT] + lft - 2. * mid + rgt) - dc * (rgt - lft);
+            }
+            Sc.st(slot(i, yc), v);
+        }
+        if (b0 == n && t == 0) Sc.st(lcc.n, 0.);
+    }
+    __syncthreads();
+}
+
+__device__ __noinline__ void big_visit_dispatch(int l, int flags, int sweeps)
+{
+    switch (team_npt(g_sm.lc[l].n, sweeps, g_sm.team_G - 1)) {
+        case 4: big_visit<4>(l, flags, sweeps); break;
+        case 8: big_visit<8>(l, flags, sweeps); break;
+        default: big_visit<16>(l, flags, sweeps); break;
+    }
+}
+
 // is level l run by a fused visit?  (single-chunk block levels and warp levels down to 64 nodes, all above the dense level m)
 __device__ __forceinline__ bool fused_level(int l)
 {
@@ -835,6 +1029,14 @@ __device__ __noinline__ void fused_visit_warp(int l, int flags, int sweeps)
 // one level visit of a cycle, fused where possible, otherwise spelled out with the generic operators
 __device__ __forceinline__ void visit(Ctl& ctl, int l, int flags, int sweeps)
 {
+    if (team_level(l)) {
+        if (ctl.small_done) { block_begin(ctl); team_barrier(); ctl.small_done = false; }     // the leader's results become visible
+        if (g_sm.team_rank > 0) big_visit_dispatch(l, flags, sweeps);
+        team_barrier();
+        return;
+    }
+    ctl.small_done = true;
+    if (g_sm.team_rank > 0) return;                                                            // the leader's levels
     if (fused_level(l)) {
         if (g_sm.lc[l].wp == kWarp) {
             if (threadIdx.x < 32) fused_visit_warp(l, flags, sweeps);
@@ -867,8 +1069,10 @@ __device__ __noinline__ void cycle_chain(Ctl& ctl, int first, int n_v)
             if (l == a && top_done) continue;
             visit(ctl, l, (l == a ? kLoadPhi : 0) | kRestrictOut, 3);
         }
-        if (threadIdx.x < 32) dense_apply_warp();
-        ctl.pending = true;
+        if (g_sm.team_rank == 0) {
+            if (threadIdx.x < 32) dense_apply_warp();
+            ctl.pending = true;
+        }
         for (int l = m - 1; l > b; --l) visit(ctl, l, kLoadPhi | kProlongIn, 3);
         if (last) { visit(ctl, b, kLoadPhi | kProlongIn, 3); top_done = false; }
         else { visit(ctl, b, kLoadPhi | kProlongIn | kRestrictOut, 6); top_done = true; }
@@ -926,17 +1130,28 @@ __device__ __forceinline__ double dd_residual(double S, double um, double u0, do
 
 __global__ void __launch_bounds__(kPT) poisson_full_kernel(GridDev g, PoissonLevels lv, PoissonArgs a)
 {
-    const int k = blockIdx.x;
+    const int G = a.team_G > 1 ? a.team_G : 1;          // CTAs per density (team mode: 1 leader + G - 1 workers)
+    const int k = blockIdx.x / G, rank = blockIdx.x % G;
+    const bool team = G > 1, leader = rank == 0;
     if (a.skip && *reinterpret_cast<const int*>(reinterpret_cast<const char*>(a.skip) + (size_t)k * a.skip_stride_bytes)) return;
     const int N = g.N, L = lv.L, c = L - 1;
     const long long t_start = clock64();
     long long* dbg = (a.dbg && blockIdx.x == 0) ? a.dbg : nullptr;
-    hierarchy_setup(lv, g.delta, a.phi + (size_t)k * lv.total, a.src + (size_t)k * lv.total, a.smem_doubles, a.coarse_op, dbg);
-    Ctl ctl{ false };
+    hierarchy_setup(lv, g.delta, a.phi + (size_t)k * lv.total, a.src + (size_t)k * lv.total, a.smem_doubles, a.coarse_op, dbg, G, rank,
+                    team ? a.team_bar + k : nullptr);
+    Ctl ctl{ false, false };
     const Ref phi = Ref::P(0), src = Ref::S(0);
+    // team mode: level 0 is in natural node order in global memory, the workers split every pass over it
+    const int ws0 = (rank - 1) * kPT + threadIdx.x, wstride = (G - 1) * kPT;
 
     // Source_0 (PoissonSolver.h:55-74)
-    if (a.rho) import_level0(src, a.rho + (size_t)k * N, g.psrc, N);
+    if (team) {
+        if (!leader) {
+            const double* rho = a.rho ? a.rho + (size_t)k * N : a.src_nat + (size_t)k * N;
+            double* s0 = g_sm.gsrc + g_sm.lc[0].os;
+            for (int i = ws0; i < N; i += wstride) s0[i] = a.rho ? g.psrc[i] * rho[i] : rho[i];
+        }
+    } else if (a.rho) import_level0(src, a.rho + (size_t)k * N, g.psrc, N);
     else if (a.src_nat) import_level0(src, a.src_nat + (size_t)k * N, nullptr, N);
     const bool warm = a.warm_vcycles > 0 && a.u_out != nullptr;
     const int n_cycles = warm ? a.warm_vcycles : a.max_vcycles;
@@ -944,45 +1159,60 @@ __global__ void __launch_bounds__(kPT) poisson_full_kernel(GridDev g, PoissonLev
     if (warm) {
         // Warm start (beyond the reference): Phi_0 = the previous solve of this density (u_out, same boundary values); the
         // V-cycles contract the difference by more than 10x each, so a few of them reach the same FP64 fixed point as the
-        // full cycle from zero
-        import_level0(phi, a.u_out + (size_t)k * N, nullptr, N);
+        // full cycle from zero.  (Team mode: Phi_0 is still in place in global memory.)
+        if (!team) import_level0(phi, a.u_out + (size_t)k * N, nullptr, N);
         __syncthreads();
+        team_barrier();
     } else {
         // Initialize (PoissonSolver.cpp:80-106) and the full-multigrid ramp (PoissonSolver.h:89-112)
-        for (int s = threadIdx.x; s < N; s += blockDim.x) phi.st(s, 0.);
-        __syncthreads();
+        if (team) {
+            if (!leader) { double* p0 = g_sm.gphi + g_sm.lc[0].op; for (int i = ws0; i < N; i += wstride) p0[i] = 0.; }
+            team_barrier();
+        } else {
+            for (int s = threadIdx.x; s < N; s += blockDim.x) phi.st(s, 0.);
+            __syncthreads();
+        }
         for (int l = 1; l < L; ++l) {
             const Ref sf = Ref::S(l - 1), sc = Ref::S(l), pc = Ref::P(l);
             const int n = g_sm.lc[l].n + 1;
             const Lay yf = g_sm.lc[l - 1].lay, yc = g_sm.lc[l].lay;
-            for (int s = threadIdx.x; s < n; s += blockDim.x) {
-                const int i = unslot(s, yc);
-                sc.st(s, (i > 0 && i < n - 1) ? 4. * sf.ld(slot(2 * i, yf)) : 0.);
-                pc.st(s, 0.);
+            if (team_level(l)) {
+                if (!leader)
+                    for (int i = ws0; i < n; i += wstride) { sc.st(i, (i > 0 && i < n - 1) ? 4. * sf.ld(2 * i) : 0.); pc.st(i, 0.); }
+                team_barrier();
+            } else if (leader) {
+                for (int s = threadIdx.x; s < n; s += blockDim.x) {
+                    const int i = unslot(s, yc);
+                    sc.st(s, (i > 0 && i < n - 1) ? 4. * sf.ld(slot(2 * i, yf)) : 0.);
+                    pc.st(s, 0.);
+                }
+                __syncthreads();
+            }
+        }
+        if (leader) {
+            if (threadIdx.x == 0) {
+                Ref::P(c).st(0, 0.);                                          // SetBoundaries(0, Z), PoissonSolver.h:76
+                Ref::P(c).st(g_sm.lc[c].n, a.Zbc ? (double)a.Zbc[k] : 0.);
             }
             __syncthreads();
+            if (dbg && threadIdx.x == 0) dbg[98] += clock64() - t_start;
+            smooth(ctl, c, 2);     // the coarsest level has one interior node: the reference's <= 15 sweeps converge in one
+            // to_fine(c, l), to_coarse(l, c) for l = L-2 .. 1, then to_fine(c, 0)
+            to_fine(ctl, c, L - 2);
         }
-        if (threadIdx.x == 0) {
-            Ref::P(c).st(0, 0.);                                          // SetBoundaries(0, Z), PoissonSolver.h:76
-            Ref::P(c).st(g_sm.lc[c].n, a.Zbc ? (double)a.Zbc[k] : 0.);
-        }
-        __syncthreads();
-        if (dbg && threadIdx.x == 0) dbg[98] += clock64() - t_start;
-        smooth(ctl, c, 2);     // the coarsest level has one interior node: the reference's <= 15 sweeps converge in one
-        // to_fine(c, l), to_coarse(l, c) for l = L-2 .. 1, then to_fine(c, 0)
-        to_fine(ctl, c, L - 2);
         fmg_top = L - 2;
     }
     const bool want_norm = (a.floor_stop || a.last_err) && a.u_out != nullptr;
     double* scratch = want_norm ? a.u_out + (size_t)k * N : nullptr;      // overwritten by the export below
     double err = 0., prev = 1e300;
     int used = 0, stagnant = 0;
-    // the ramp cycles whose top level is at or below the dense level are run level by level
-    while (fmg_top > 0 && !(g_sm.has_G && fmg_top < g_sm.m)) { cycle(ctl, fmg_top, fmg_top - 1, nullptr); --fmg_top; }
+    // the ramp cycles whose top level is at or below the dense level are run level by level (the leader's levels)
+    while (fmg_top > 0 && !(g_sm.has_G && fmg_top < g_sm.m)) { if (leader) cycle(ctl, fmg_top, fmg_top - 1, nullptr); --fmg_top; }
+    ctl.small_done = true;
     if (g_sm.has_G && !want_norm) {
         cycle_chain(ctl, fmg_top, n_cycles);          // the rest of the ramp and the V-cycles, fused visits
         used = n_cycles;
-    } else {
+    } else if (!team) {
         for (; fmg_top > 0; --fmg_top) cycle(ctl, fmg_top, fmg_top - 1, nullptr);
         for (int it = 0; it < n_cycles; ++it) {
             const bool last = (it == n_cycles - 1);
@@ -1003,7 +1233,7 @@ __global__ void __launch_bounds__(kPT) poisson_full_kernel(GridDev g, PoissonLev
     // by the same V-cycles from e = 0 (its own rounding floor is ~1e-9 |e|, i.e. negligible) and U <- U + e.  The result
     // is the discrete solution to FP64 representation accuracy instead of ~1e-9, which removes the rounding-noise floor
     // of the SCF energies (the reference's |dE/E| wanders at 2e-11..1e-10 before it randomly dips below 1e-11).
-    if (a.refine_vcycles > 0 && a.u0) {
+    if (a.refine_vcycles > 0 && a.u0 && !team) {
         double* u0 = a.u0 + (size_t)k * N;                            // slot order, like phi
         const double cl = 1. + 0.5 * g.delta, cr = 1. - 0.5 * g.delta;
         const Lay y0 = g_sm.lc[0].lay;
@@ -1024,12 +1254,18 @@ __global__ void __launch_bounds__(kPT) poisson_full_kernel(GridDev g, PoissonLev
         __syncthreads();
     }
     if (dbg && threadIdx.x == 0) dbg[96] += clock64() - t_start;
-    if (a.u_out) export_level0(a.u_out + (size_t)k * N, N);
+    if (team) {
+        if (a.u_out && !leader) {
+            const double* p0 = g_sm.gphi + g_sm.lc[0].op;
+            double* u = a.u_out + (size_t)k * N;
+            for (int i = ws0; i < N; i += wstride) u[i] = __ldcg(p0 + i);
+        }
+    } else if (a.u_out) export_level0(a.u_out + (size_t)k * N, N);
     if (dbg && threadIdx.x == 0) dbg[97] += clock64() - t_start;
     if (threadIdx.x == 0) {
         if (a.work) atomicAdd(a.work, g_sm.updates);
-        if (a.vcycles_used) a.vcycles_used[k] = used;
-        if (a.last_err) a.last_err[k] = err;
+        if (leader && a.vcycles_used) a.vcycles_used[k] = used;
+        if (leader && a.last_err) a.last_err[k] = err;
     }
 }
 
@@ -1108,10 +1344,28 @@ void launch_poisson_full(const GridDev& g, const PoissonLevels& lv, const Poisso
 {
     PoissonArgs a = a_in;
     a.smem_doubles = dyn_doubles_for(lv);
-    const size_t bytes = (size_t)a.smem_doubles * sizeof(double);
+    size_t bytes = (size_t)a.smem_doubles * sizeof(double);
+    // Team mode: large grids (levels above 16384 nodes) with so few densities that one CTA each would leave the GPU idle:
+    // team_G CTAs per density, launched cooperatively (they synchronise through a per-density counter, so all of them must
+    // be resident).  Needs the dense coarse operator (fused visits), no norm / refinement requests, and a barrier array.
+    a.team_G = 1;
+    const int n0 = lv.size[0] - 1;
+    static int n_sm = 0;
+    if (n_sm == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+    if (n0 > kTeamLevelNodes && a.team_bar != nullptr && a.coarse_op != nullptr && !a.floor_stop && !a.last_err && a.refine_vcycles == 0) {
+        const int G = std::min(41, n_sm / std::max(1, a.n_dens));
+        if (G >= 2 && team_npt(n0, 6, G - 1) != 0) { a.team_G = G; bytes = kMaxDynBytes; }
+    }
     static size_t attr_bytes = 0;
     if (bytes > attr_bytes) { cudaFuncSetAttribute(poisson_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); attr_bytes = bytes; }
-    poisson_full_kernel<<<a.n_dens, kPT, bytes, st>>>(g, lv, a);
+    if (a.team_G > 1) {
+        cudaMemsetAsync(a.team_bar, 0, sizeof(unsigned) * a.n_dens, st);
+        GridDev gg = g; PoissonLevels ll = lv;
+        void* args[] = { &gg, &ll, &a };
+        cudaLaunchCooperativeKernel((const void*)poisson_full_kernel, dim3(a.n_dens * a.team_G), dim3(kPT), args, bytes, st);
+    } else {
+        poisson_full_kernel<<<a.n_dens, kPT, bytes, st>>>(g, lv, a);
+    }
 }
 
 // V-cycles as defined by the reference on given (Phi_0, Source_0) in natural node order: parity / microbench entry point
@@ -1123,7 +1377,7 @@ __global__ void __launch_bounds__(kPT) poisson_vcycles_kernel(double delta, Pois
     const int k = blockIdx.x;
     const int N = lv.size[0];
     hierarchy_setup(lv, delta, phi_all + (size_t)k * lv.total, src_all + (size_t)k * lv.total, smem_doubles, nullptr, nullptr);
-    Ctl ctl{ false };
+    Ctl ctl{ false, false };
     import_level0(Ref::P(0), phi_nat + (size_t)k * N, nullptr, N);
     import_level0(Ref::S(0), src_nat + (size_t)k * N, nullptr, N);
     __syncthreads();

@@ -5,7 +5,7 @@ using namespace dft;
 __global__ void __launch_bounds__(kPT) k_visit(PoissonLevels lv, double delta, double* phi, double* src, int dyn_doubles, long long* out, int reps)
 {
     hierarchy_setup(lv, delta, phi, src, dyn_doubles, nullptr, nullptr);
-    Ctl ctl{ false };
+    Ctl ctl{ false, false };
     for (int l = 0; l < lv.L; ++l) {
         const Ref p = Ref::P(l), s = Ref::S(l);
         for (int i = threadIdx.x; i < lv.size[l]; i += blockDim.x) { p.st(i, 1e-3 * i); s.st(i, 1e-6 * (i % 7)); }
