@@ -320,7 +320,7 @@ int dftatom_solve_batch(dftatom_ctx* c, const dftatom_options* opts, int n_atoms
     if ((rc = c->psi.ensure(sizeof(double) * (size_t)n_orbs * N))) return rc;
     if ((rc = c->match_pt.ensure(sizeof(int) * (size_t)n_orbs))) return rc;
     if ((rc = c->inv_norm.ensure(sizeof(double) * (size_t)n_orbs))) return rc;
-    if ((rc = c->epart.ensure(sizeof(double) * (size_t)n_atoms * 8 * 5)) || (rc = c->eticket.ensure(sizeof(int) * (size_t)n_atoms))) return rc;
+    if ((rc = c->epart.ensure(sizeof(double) * (size_t)n_atoms * 64 * 5)) || (rc = c->eticket.ensure(sizeof(int) * (size_t)n_atoms))) return rc;
     DFT_CHECK(cudaMemsetAsync(c->eticket.p, 0, sizeof(int) * (size_t)n_atoms, st));
     if ((rc = c->phi.ensure(sizeof(double) * (size_t)n_atoms * lv.total))) return rc;
     if ((rc = c->src.ensure(sizeof(double) * (size_t)n_atoms * lv.total))) return rc;

@@ -162,7 +162,7 @@ struct ScfBuffers {
     double* atab;     // [n_tabs][N]
     double* psi;      // [n_orbs][N]
     int* match_pt;    // [n_orbs]
-    double* epart;    // [n_atoms][8][5] partial sums of the five energy integrals (potential_energy_kernel)
+    double* epart;    // [n_atoms][<= 64 node ranges][5] partial sums of the five energy integrals (potential_energy_kernel)
     int* eticket;     // [n_atoms] arrival counter of its CTAs (zero between launches)
     double* inv_norm; // [n_orbs] 1 / integral u^2 dr of the matched solution in psi
     double* phi; double* src;   // Poisson hierarchy [n_atoms][levels.total]

@@ -208,9 +208,10 @@ __global__ void __launch_bounds__(256) orbital_norm_kernel(GridDev g, ScfBuffers
     }
 }
 
-// New density and mixing (DFTAtom.cpp:558-559, :332-342).  grid = (atoms, kDensChunks): every CTA owns a contiguous range of
+// New density and mixing (DFTAtom.cpp:558-559, :332-342).  grid = (atoms, node_chunks(N)): every CTA owns a contiguous range of
 // nodes of one atom (the nodes are independent), so a handful of atoms still fills the GPU.
-constexpr int kDensChunks = 8;
+// node ranges per atom: 8 up to 16385 nodes, one per 2048 nodes above (gridDim.y)
+__host__ __device__ inline int node_chunks(int N) { const int c = (N + 2047) / 2048; return c < 8 ? 8 : (c > 64 ? 64 : c); }
 constexpr int kDT = 256;
 __global__ void __launch_bounds__(kDT) density_update_kernel(GridDev g, ScfBuffers b)
 {
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(kDT) density_update_kernel(GridDev g, ScfBuffe
         wgt[s * DFTATOM_MAX_LEVELS + k] = (double)b.orbs[o].occ * b.inv_norm[o];
     }
     __syncthreads();
-    const int per = (N + kDensChunks - 1) / kDensChunks;
+    const int per = (N + (int)gridDim.y - 1) / (int)gridDim.y;
     const int i0 = blockIdx.y * per, i1 = min(i0 + per, N);
     const double keep = at.mixing, take = 1. - at.mixing;
     double* rt = b.rhot + (size_t)a * N;
@@ -276,13 +277,12 @@ void launch_orbital_norms(const GridDev& g, const ScfBuffers& b, cudaStream_t st
 
 void launch_density_update(const GridDev& g, const ScfBuffers& b, cudaStream_t st)
 {
-    density_update_kernel<<<dim3(b.n_atoms, kDensChunks), kDT, 0, st>>>(g, b);
+    density_update_kernel<<<dim3(b.n_atoms, node_chunks(g.N)), kDT, 0, st>>>(g, b);
 }
 
 // Potential from (U, rho), the five integrals, energies, stop test.  first != 0: only the initial potential.
-// grid = (atoms, kPotChunks): every CTA owns a contiguous range of nodes; the partial sums of the five integrals go to
+// grid = (atoms, node_chunks(N)): every CTA owns a contiguous range of nodes; the partial sums of the five integrals go to
 // b.epart, and the CTA that finishes last (per-atom ticket) adds them in chunk order - deterministic - and runs the stop test.
-constexpr int kPotChunks = 8;
 constexpr int kPT2 = 256;
 __global__ void __launch_bounds__(kPT2) potential_energy_kernel(GridDev g, PoissonLevels lv, ScfBuffers b, int first)
 {
@@ -300,6 +300,7 @@ __global__ void __launch_bounds__(kPT2) potential_energy_kernel(GridDev g, Poiss
     const double q = g.delta * g.delta * 0.25;
 
     double e[5] = { 0., 0., 0., 0., 0. };   // nuclear, exccor, eexcDeriv, hartree, potentiale
+    const int kPotChunks = (int)gridDim.y;
     const int per = (N + kPotChunks - 1) / kPotChunks;
     const int i0 = blockIdx.y * per, i1 = min(i0 + per, N);
     for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
@@ -380,7 +381,7 @@ __global__ void __launch_bounds__(kPT2) potential_energy_kernel(GridDev g, Poiss
 
 void launch_potential_energy(const GridDev& g, const PoissonLevels& lv, const ScfBuffers& b, int first, cudaStream_t st)
 {
-    potential_energy_kernel<<<dim3(b.n_atoms, kPotChunks), kPT2, 0, st>>>(g, lv, b, first);
+    potential_energy_kernel<<<dim3(b.n_atoms, node_chunks(g.N)), kPT2, 0, st>>>(g, lv, b, first);
 }
 
 }  // namespace dft
