@@ -276,6 +276,10 @@ def run_cuda_arm(a):
             line["rn_scf"] = dict(metric="Rn SCF ms", value=rn_ms, unit="ms", device_ms=ctx.last_timing()[0], scf_steps=r_rn.n_steps, finished=bool(r_rn.finished),
                                   Etotal=r_rn.Etotal, workload="C2 Radon Z=86 LSDA, 17 levels (131073 nodes), delta 0.0001, mixing 0.5, Rmax 50",
                                   reference_cpu_seconds_1core=518.0, reference_source="SURVEY.md section 6 (unmodified reference, g++ -O2, one core)")
+        if world == 1 and not a.no_micro:
+            # BASELINE.json configs[4]: the two kernels at scale, each against its own roofline
+            line["c5b_numerov_lanes"] = micro_c5b(ctx, peak, cpu_baseline=not a.no_cpu_baseline)
+            line["c5a_poisson_vcycle"] = micro_c5a(ctx, torch, _hbm_peak(), n_dens=a.micro_densities, cpu_baseline=not a.no_cpu_baseline)
         if world == 1 and not a.no_cpu_baseline:
             cb = cpu_reference_sample(30.0)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -283,6 +287,167 @@ def run_cuda_arm(a):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# kernel micro-benchmarks (BASELINE.json configs[4], SURVEY 8d: C5a Poisson V-cycle, C5b Numerov lanes)
+# ------------------------------------------------------------------------------------------------------------
+def _splitmix64_unit(seed, n):
+    """k-th output of splitmix64(seed) / 2^64, k = 0..n-1."""
+    import numpy as np
+    out = np.empty(n, np.float64)
+    x = seed & 0xFFFFFFFFFFFFFFFF
+    M = 0xFFFFFFFFFFFFFFFF
+    for k in range(n):
+        x = (x + 0x9E3779B97F4A7C15) & M
+        z = x
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M
+        z = z ^ (z >> 31)
+        out[k] = z / 2.0 ** 64
+    return out
+
+
+def micro_c5a(ctx, torch, hbm_peak_gbs, n_dens=1024, levels=20, delta=1.25e-5, rmax=50.0, cycles=8, reps=3, cpu_baseline=True):
+    """C5a: batched Poisson V-cycle on 2^20+1 nodes x 1024 densities rho_k = Z_k a_k^3/pi exp(-2 a_k r), boundary
+    values (0, Z_k), device-resident.  Unit of work = one reference-shaped V-cycle on all densities; algorithmic traffic
+    112 B x N per V-cycle per density."""
+    import numpy as np
+    N = (1 << levels) + 1
+    ld = N + 3
+    Zk = 1.0 + (np.arange(n_dens) % 92)
+    ak = 0.5 + 3.5 * _splitmix64_unit(20261017, n_dens)
+    dev = torch.device("cuda")
+    i = torch.arange(N, dtype=torch.float64, device=dev)
+    rp = rmax / (np.exp((N - 1) * delta) - 1.0)
+    ex = torch.exp(i * delta)
+    r = rp * (ex - 1.0)
+    psrc = r * (4.0 * np.pi * rp * rp * delta * delta) * ex * ex           # r 4 pi K_i, K_i = Rp^2 delta^2 e^{2 delta i}
+    psrc[0] = 0.0; psrc[-1] = 0.0
+    d_src = torch.zeros((n_dens, ld), dtype=torch.float64, device=dev)
+    d_phi = torch.zeros((n_dens, ld), dtype=torch.float64, device=dev)
+    tZ = torch.from_numpy(Zk).to(dev); ta = torch.from_numpy(ak).to(dev)
+    for k0 in range(0, n_dens, 32):
+        k1 = min(k0 + 32, n_dens)
+        a_ = ta[k0:k1, None]
+        d_src[k0:k1, :N] = psrc[None, :] * (tZ[k0:k1, None] * a_ ** 3 / np.pi) * torch.exp(-2.0 * a_ * r[None, :])
+    sb = ctx.poisson_scratch_bytes(levels, n_dens)
+    scratch = torch.empty(sb // 8, dtype=torch.float64, device=dev)
+
+    def reset():
+        d_phi.zero_()
+        d_phi[:, N - 1] = tZ
+        torch.cuda.synchronize()
+
+    out = dict(workload=f"C5a Poisson V-cycle, {N} nodes x {n_dens} densities, delta {delta}, Rmax {rmax}, device-resident "
+                        f"({(2 * n_dens * ld * 8 + sb) / 2 ** 30:.1f} GiB >> L2)",
+               bytes_per_vcycle_algorithmic=112.0 * N * n_dens)
+    best = {}
+    for name, ncyc, fuse in (("single", 1, False), ("chained", cycles, True)):
+        times = []
+        for rep in range(reps + 1):                  # first repetition = warm-up
+            reset()
+            ms, nl = ctx.poisson_vcycles_dev(levels, delta, n_dens, d_phi.data_ptr(), d_src.data_ptr(), ld, scratch.data_ptr(), sb, ncyc, fuse)
+            if rep:
+                times.append(ms / ncyc)
+        best[name] = dict(ms_per_vcycle=statistics.median(times), launches_per_call=nl, vcycles_per_call=ncyc)
+    for name, b in best.items():
+        b["vcycles_per_s"] = n_dens / (b["ms_per_vcycle"] * 1e-3)
+        b["achieved_gbs"] = 112.0 * N * n_dens / (b["ms_per_vcycle"] * 1e-3) / 1e9
+        b["frac_of_hbm_peak"] = b["achieved_gbs"] / hbm_peak_gbs
+    out["single_vcycle"] = best["single"]
+    out["chained_vcycles"] = best["chained"]
+    out["chained_vcycles"]["note"] = (f"{cycles} V-cycles per call; the last visit of level 0 of one cycle and the first of the next are one "
+                                      "pass (6 sweeps): actual level-0 traffic 56+28 B/node instead of 2 x 56")
+    # known answer: after `cycles` V-cycles from zero, U_k -> Z_k (1 - exp(-2 a_k r)(1 + a_k r)) up to the discretisation error
+    ks = [0, n_dens // 2, n_dens - 1]
+    err = 0.0
+    for k in ks:
+        ux = Zk[k] * (1.0 - torch.exp(-2.0 * ak[k] * r) * (1.0 + ak[k] * r))
+        err = max(err, float(torch.max(torch.abs(d_phi[k, :N] - ux))) / Zk[k])
+    out["known_answer_max_err_over_Z"] = err
+    out["roofline"] = dict(kernel="stream_visit_kernel (+ poisson_mid_kernel below 16385 nodes)", bound="hbm",
+                           achieved=best["chained"]["achieved_gbs"], peak=hbm_peak_gbs, unit="GB/s",
+                           frac=best["chained"]["achieved_gbs"] / hbm_peak_gbs, traffic=None,
+                           bytes_per_node_per_vcycle=112.0, peak_source="MEASURED_PEAKS.json hbm copy (fallback 6459 GB/s)")
+    if cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as O
+        k = n_dens - 1
+        src_h = d_src[k, :N].cpu().numpy(); phi_h = np.zeros(N); phi_h[-1] = Zk[k]
+        t0 = time.time()
+        o, _ = O.poisson_vcycles(levels, delta, phi_h, src_h, cycles)
+        dt = time.time() - t0
+        out["cpu_baseline"] = dict(value=cycles / dt, unit="V-cycles/s (one density)", cores=1, kind="port",
+                                   sample=f"{cycles} V-cycles of density {k} with the oracle's PoissonSolver restatement ({dt:.2f} s)",
+                                   max_abs_diff_gpu_vs_oracle=float(np.max(np.abs(d_phi[k, :N].cpu().numpy() - o))))
+    del d_src, d_phi, scratch
+    torch.cuda.empty_cache()
+    return out
+
+
+def micro_c5b(ctx, fp64_peak_tflops, reps=20, cpu_baseline=True):
+    """C5b: 4096 lanes = 16 (n,l) x 256 trial energies in [1.5 E_n, 0.5 E_n], E_n = -Z^2/2n^2, V = -Z/r, Z = 86, on C2's grid
+    (131073 nodes, delta 1e-4, Rmax 50); each lane = one inward sweep returning (sign y0, node count)."""
+    import numpy as np
+    levels, delta, rmax, Z = 17, 1e-4, 50.0, 86
+    N = (1 << levels) + 1
+    rp = rmax / (np.exp((N - 1) * delta) - 1.0)
+    r = rp * (np.exp(np.arange(N) * delta) - 1.0)
+    V = np.zeros(N); V[1:] = -Z / r[1:]
+    shells = [(1, 0), (2, 0), (2, 1), (3, 0), (3, 1), (3, 2), (4, 0), (4, 1), (4, 2), (4, 3), (5, 0), (5, 1), (5, 2), (5, 3), (6, 0), (6, 1)]
+    ls, Es = [], []
+    for n, l in shells:
+        En = -Z * Z / (2.0 * n * n)
+        Es.append(np.linspace(1.5 * En, 0.5 * En, 256)); ls.append(np.full(256, l, np.int32))
+    Es = np.concatenate(Es); ls = np.concatenate(ls); lim = np.zeros(len(Es), np.int32)
+    # two shapes of the same sweep: serial in r (one warp = 32 energies walks the whole grid) and parallel in r (one cluster
+    # of 8 CTAs per 32 energies, warp = one of 32 radial segments: 2.25x the arithmetic, 2/32 of the depth)
+    kernels = {}
+    for name, impl in (("serial_in_r", 0), ("parallel_in_r", 2)):
+        sign, lg, cnt, ms, steps = ctx.numerov_lanes_timed(V, levels, delta, rmax, ls, Es, lim, impl=impl, reps=reps)
+        # known answer: the Sturm count of a lane = number of Coulomb levels n' > l with -Z^2/2n'^2 below its energy (+1
+        # throughout for l = 3, SURVEY fact 6); it steps from n-l-1 to n-l where E crosses E_n
+        ok = True
+        for g, (n, l) in enumerate(shells):
+            e = Es[g * 256:(g + 1) * 256]
+            want = sum((-Z * Z / (2.0 * q * q) < e).astype(np.int64) for q in range(l + 1, 40))
+            ok = ok and bool((cnt[g * 256:(g + 1) * 256] - (1 if l == 3 else 0) == want).all())
+            ok = ok and int(want[127]) == n - l - 1 and int(want[128]) == n - l
+        tf = 11.0 * steps / (ms * 1e-3) / 1e12
+        kernels[name] = dict(ms_per_launch=ms, lanes_per_s=len(Es) / (ms * 1e-3), achieved_tflops=tf, known_answer_ok=ok)
+    best = max(kernels, key=lambda k_: kernels[k_]["achieved_tflops"])
+    tf = kernels[best]["achieved_tflops"]
+    out = dict(workload="C5b Numerov shooting, 4096 (orbital, trial-energy) lanes, Z=86 Coulomb well, 131073 nodes",
+               lane_node_steps=steps, kernels=kernels, known_answer_ok=all(k_["known_answer_ok"] for k_ in kernels.values()),
+               roofline=dict(kernel={"serial_in_r": "numerov_lanes_fast_kernel", "parallel_in_r": "numerov_lanes_seg_kernel"}[best] + f" ({best})",
+                             bound="fp64", achieved=tf, peak=fp64_peak_tflops, unit="TFLOP/s",
+                             frac=tf / fp64_peak_tflops if fp64_peak_tflops else None, traffic=None, flop_per_lane_node_step=11.0,
+                             note="credited 11 FLOP per (lane, node-step) whatever the kernel executes (SURVEY 8d); 4096 lanes are 128 warps "
+                                  "for 148 SMs x 4 FP64 pipes, so the serial sweep cannot fill the machine and the parallel-in-r one pays 2.25x"))
+    if cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as O
+        sel = np.arange(0, len(Es), 16)
+        t0 = time.time()
+        O.numerov_lanes(V, delta, rmax, ls[sel], Es[sel], lim[sel])
+        dt = time.time() - t0
+        out["cpu_baseline"] = dict(value=len(sel) / dt, unit="lanes/s", cores=1, kind="port",
+                                   sample=f"every 16th lane ({len(sel)} lanes) with the oracle's CountNodes + SolutionInZero restatement ({dt:.2f} s)")
+    return out
+
+
+def _hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            m = json.load(f)
+        for key in ("hbm_gbs", "hbm_copy_gbs", "hbm_GBps", "hbm"):
+            if key in m:
+                v = m[key]
+                return float(v["burst"] if isinstance(v, dict) and "burst" in v else (v["value"] if isinstance(v, dict) else v))
+    except Exception:
+        pass
+    return 6459.0
 
 
 def main():
@@ -294,6 +459,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-rn", action="store_true", help="skip the Radon (C2) SCF timing")
     ap.add_argument("--no-batch", action="store_true", help="skip the replicated-batch (8 x C3) throughput figure")
+    ap.add_argument("--no-micro", action="store_true", help="skip the kernel micro-benchmarks (C5a Poisson V-cycle, C5b Numerov lanes)")
+    ap.add_argument("--micro-densities", type=int, default=1024, help="densities of the C5a micro-benchmark (1024 = BASELINE.json; ~34 GiB)")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference_arm(a)

@@ -80,6 +80,8 @@ def load_library():
     lib.dftatom_last_profile.argtypes = [C.c_void_p, C.POINTER(_CProfile)]
     lib.dftatom_measure_fp64_peak.argtypes = [C.c_void_p, _dp]
     lib.dftatom_numerov_lanes.argtypes = [C.c_void_p, _dp, C.c_int, C.c_double, C.c_double, C.c_int, _ip, _dp, _ip, C.c_int, _ip, _dp, _ip]
+    lib.dftatom_numerov_lanes_timed.argtypes = [C.c_void_p, _dp, C.c_int, C.c_double, C.c_double, C.c_int, _ip, _dp, _ip, C.c_int, _ip, _dp, _ip,
+                                                C.c_int, C.POINTER(C.c_float), _dp]
     lib.dftatom_level_search.argtypes = [C.c_void_p, _dp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, _ip, _ip, _dp, _ip]
     lib.dftatom_numerov_orbital.argtypes = [C.c_void_p, _dp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, _dp, _ip]
     lib.dftatom_poisson_solve.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, _ip, _dp, _dp, _ip]
@@ -88,8 +90,8 @@ def load_library():
     lib.dftatom_simpson38.argtypes = [C.c_void_p, C.c_double, _dp, C.c_int, C.c_int, _dp]
     lib.dftatom_poisson_scratch_bytes.argtypes = [C.c_int, C.c_int]
     lib.dftatom_poisson_scratch_bytes.restype = C.c_longlong
-    lib.dftatom_poisson_vcycles_dev.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
-                                                C.c_longlong, C.c_int, C.POINTER(C.c_float)]
+    lib.dftatom_poisson_vcycles_dev.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p,
+                                                C.c_longlong, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_longlong)]
     _lib = lib
     return lib
 
@@ -285,6 +287,16 @@ class Context:
                                                _i(sign), _d(lg), _i(cnt)))
         return sign, lg, cnt
 
+    def numerov_lanes_timed(self, V, levels, delta, max_r, l, E, nodes_limit, impl=0, reps=10):
+        """numerov_lanes plus (ms per launch over `reps` device-timed launches, lane node-steps per launch)."""
+        V = _f64(V); l = _i32(l); E = _f64(E); lim = _i32(nodes_limit)
+        n = len(E)
+        sign = np.zeros(n, np.int32); lg = np.zeros(n, np.float64); cnt = np.zeros(n, np.int32)
+        ms = C.c_float(); ns = C.c_double()
+        _check(self._lib.dftatom_numerov_lanes_timed(self._h, _d(V), int(levels), float(delta), float(max_r), n, _i(l), _d(E), _i(lim), int(impl),
+                                                     _i(sign), _d(lg), _i(cnt), int(reps), C.byref(ms), C.byref(ns)))
+        return sign, lg, cnt, ms.value, ns.value
+
     def level_search(self, V, levels, delta, max_r, Z, n, l):
         V = _f64(V); n = _i32(n); l = _i32(l)
         E = np.zeros(len(n), np.float64); ok = np.zeros(len(n), np.int32)
@@ -308,6 +320,18 @@ class Context:
         err = np.zeros(phi.shape[0], np.float64)
         _check(self._lib.dftatom_poisson_vcycles(self._h, int(levels), float(delta), phi.shape[0], _d(phi), _d(src), int(n_cycles), _d(err)))
         return phi, err
+
+    def poisson_scratch_bytes(self, levels, n_dens) -> int:
+        return int(self._lib.dftatom_poisson_scratch_bytes(int(levels), int(n_dens)))
+
+    def poisson_vcycles_dev(self, levels, delta, n_dens, d_phi, d_src, ld, d_scratch, scratch_bytes, n_cycles, fuse_tops=True):
+        """Stream-mode V-cycles on DEVICE arrays (addresses as ints, e.g. torch.Tensor.data_ptr()): phi[n_dens][ld] in place,
+        src[n_dens][ld]; returns (device ms, kernel launches).  levels >= 15 (config C5a)."""
+        ms, nl = C.c_float(), C.c_longlong()
+        _check(self._lib.dftatom_poisson_vcycles_dev(self._h, int(levels), float(delta), int(n_dens), C.c_void_p(int(d_phi)), C.c_void_p(int(d_src)),
+                                                     int(ld), C.c_void_p(int(d_scratch)), int(scratch_bytes), int(n_cycles), int(bool(fuse_tops)),
+                                                     C.byref(ms), C.byref(nl)))
+        return ms.value, nl.value
 
     def vwn(self, rho_a, rho_b=None):
         ra = _f64(rho_a); n = len(ra)

@@ -60,6 +60,8 @@ struct dftatom_ctx {
     int match_mode = 0;
     int energies_per_lane = 1;
     int warm_start = 1;
+    int stream_variant = 0;    // window shape of the stream-mode Poisson visits (poisson_stream.cu)
+    DevBuf stream_G; int stream_G_levels = 0; double stream_G_delta = 0.;   // dense coarse operator of the stream-mode V-cycle
     dftatom_kernel_profile prof[DFTATOM_K_COUNT] = {};
     // reusable buffers
     DevBuf atoms, astate, orbs, ss, rho, rhot, vpot, atab, psi, match_pt, inv_norm, epart, eticket, team_bar, phi, src, u0, ubuf, zbc, tab_of, steps, n_active;
@@ -173,6 +175,7 @@ void dftatom_destroy(dftatom_ctx* c)
                       &c->phi, &c->src, &c->u0, &c->ubuf, &c->zbc, &c->tab_of, &c->steps, &c->n_active };
     for (DevBuf* b : all) b->release();
     for (DevBuf& b : c->scratch) b.release();
+    c->stream_G.release();
     if (c->h_active) cudaFreeHost(c->h_active);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -194,6 +197,7 @@ int dftatom_set_option(dftatom_ctx* c, const char* key, double value)
     else if (k == "search_mode") c->search_mode = (int)value;
     else if (k == "match_mode") c->match_mode = (int)value;
     else if (k == "warm_start") c->warm_start = value != 0.;
+    else if (k == "stream_variant") c->stream_variant = std::min(2, std::max(0, (int)value));
     else if (k == "energies_per_lane") c->energies_per_lane = ((int)value == 2) ? 2 : 1;
     else { set_error("unknown option " + k); return DFTATOM_E_ARG; }
     return 0;
@@ -481,8 +485,9 @@ int dftatom_solve_batch(dftatom_ctx* c, const dftatom_options* opts, int n_atoms
 // component entry points (host buffers)
 // ---------------------------------------------------------------------------------------------------------
 
-int dftatom_numerov_lanes(dftatom_ctx* c, const double* V, int levels, double delta, double max_r, int n_lanes_in, const int* l_in,
-                          const double* E_in, const int* limit_in, int impl, int* y0_sign_out, double* y0_log2_out, int* count_out)
+static int numerov_lanes_impl(dftatom_ctx* c, const double* V, int levels, double delta, double max_r, int n_lanes_in, const int* l_in,
+                             const double* E_in, const int* limit_in, int impl, int* y0_sign_out, double* y0_log2_out, int* count_out,
+                             int reps, float* ms_per_launch, double* node_steps)
 {
     if (!c || !V || n_lanes_in <= 0 || !l_in || !E_in || !limit_in) return DFTATOM_E_ARG;
     // the production sweep shares one (potential, l) table tile per warp: group the lanes by l, pad every group to 32
@@ -512,7 +517,33 @@ int dftatom_numerov_lanes(dftatom_ctx* c, const double* V, int levels, double de
     DFT_CHECK(cudaMemcpyAsync(d_lim, nodes_limit, sizeof(int) * n_lanes, cudaMemcpyHostToDevice, st));
     DFT_CHECK(cudaMemcpyAsync(d_E, E, sizeof(double) * n_lanes, cudaMemcpyHostToDevice, st));
     NumerovLaneArgs a{ dA.as<double>(), n_lanes, d_tab, d_l, d_E, d_lim, d_sign, d_log, d_cnt };
-    if (impl == 0) launch_numerov_lanes_fast(g, a, st); else launch_numerov_lanes(g, a, st);
+    if (impl == 0) launch_numerov_lanes_fast(g, a, st); else if (impl == 2) launch_numerov_lanes_seg(g, a, c->r_segments > 1 ? c->r_segments : 32, st); else launch_numerov_lanes(g, a, st);
+    if (reps > 0) {          // microbench: the same launch `reps` more times between CUDA events (tables and lanes resident)
+        cudaEvent_t e0, e1;
+        DFT_CHECK(cudaEventCreate(&e0)); DFT_CHECK(cudaEventCreate(&e1));
+        DFT_CHECK(cudaEventRecord(e0, st));
+        for (int r = 0; r < reps; ++r) { if (impl == 0) launch_numerov_lanes_fast(g, a, st); else if (impl == 2) launch_numerov_lanes_seg(g, a, c->r_segments > 1 ? c->r_segments : 32, st); else launch_numerov_lanes(g, a, st); }
+        DFT_CHECK(cudaEventRecord(e1, st));
+        DFT_CHECK(cudaStreamSynchronize(st));
+        float ms = 0.f;
+        DFT_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        if (ms_per_launch) *ms_per_launch = ms / (float)reps;
+    }
+    if (node_steps) {        // algorithmic work: (cut-off index - 1) node-steps per lane (Numerov.h:119-136, 1e-200 cut-off)
+        double ns = 0.;
+        for (int k = 0; k < n_lanes_in; ++k) {
+            const double kappa = std::sqrt(2. * std::fabs(E_in[k]));
+            int hi = N - 1, lo = 1;                         // same rule as numerov_common.cuh:start_index
+            while (hi - lo > 1) {
+                const int mid = (hi + lo) >> 1;
+                const double arg = -(g.rp * std::expm1(delta * (double)mid)) * kappa - (double)mid * 0.5 * delta;
+                if (arg < kFarLog) hi = mid; else lo = mid;
+            }
+            ns += (double)(hi - 1);
+        }
+        *node_steps = ns;
+    }
     if (y0_sign) DFT_CHECK(cudaMemcpyAsync(y0_sign, d_sign, sizeof(int) * n_lanes, cudaMemcpyDeviceToHost, st));
     if (y0_log2) DFT_CHECK(cudaMemcpyAsync(y0_log2, d_log, sizeof(double) * n_lanes, cudaMemcpyDeviceToHost, st));
     if (count) DFT_CHECK(cudaMemcpyAsync(count, d_cnt, sizeof(int) * n_lanes, cudaMemcpyDeviceToHost, st));
@@ -525,6 +556,21 @@ int dftatom_numerov_lanes(dftatom_ctx* c, const double* V, int levels, double de
         if (count_out) count_out[perm[k]] = hc[k];
     }
     return 0;
+}
+
+int dftatom_numerov_lanes(dftatom_ctx* c, const double* V, int levels, double delta, double max_r, int n_lanes, const int* l,
+                          const double* E, const int* nodes_limit, int impl, int* y0_sign, double* y0_log2, int* count)
+{
+    return numerov_lanes_impl(c, V, levels, delta, max_r, n_lanes, l, E, nodes_limit, impl, y0_sign, y0_log2, count, 0, nullptr, nullptr);
+}
+
+int dftatom_numerov_lanes_timed(dftatom_ctx* c, const double* V, int levels, double delta, double max_r, int n_lanes, const int* l,
+                                const double* E, const int* nodes_limit, int impl, int* y0_sign, double* y0_log2, int* count,
+                                int reps, float* ms_per_launch, double* lane_node_steps)
+{
+    if (reps <= 0) return DFTATOM_E_ARG;
+    return numerov_lanes_impl(c, V, levels, delta, max_r, n_lanes, l, E, nodes_limit, impl, y0_sign, y0_log2, count, reps, ms_per_launch,
+                              lane_node_steps);
 }
 
 // shared by level_search / numerov_orbital: one pseudo-atom with the given potential
@@ -652,8 +698,8 @@ int dftatom_poisson_solve(dftatom_ctx* c, int levels, double delta, double max_r
 
 long long dftatom_poisson_scratch_bytes(int levels, int n_dens)
 {
-    const PoissonLevels lv = make_levels(levels);
-    return (long long)sizeof(double) * 2 * (long long)lv.total * n_dens;
+    if (levels < 15 || levels > 22 || n_dens <= 0) return 0;
+    return (long long)sizeof(double) * make_stream_plan(levels, n_dens).total;
 }
 
 int dftatom_poisson_vcycles(dftatom_ctx* c, int levels, double delta, int n_dens, double* phi, const double* src, int n_cycles,
@@ -681,12 +727,39 @@ int dftatom_poisson_vcycles(dftatom_ctx* c, int levels, double delta, int n_dens
     return 0;
 }
 
-int dftatom_poisson_vcycles_dev(dftatom_ctx* c, int levels, double delta, int n_dens, void* d_phi, const void* d_src, void* d_scratch,
-                                long long scratch_bytes, int n_cycles, float* device_ms)
+int dftatom_poisson_vcycles_dev(dftatom_ctx* c, int levels, double delta, int n_dens, void* d_phi, const void* d_src, long long ld,
+                                void* d_scratch, long long scratch_bytes, int n_cycles, int fuse_tops, float* device_ms, long long* kernel_launches)
 {
-    (void)c; (void)levels; (void)delta; (void)n_dens; (void)d_phi; (void)d_src; (void)d_scratch; (void)scratch_bytes; (void)n_cycles; (void)device_ms;
-    set_error("dftatom_poisson_vcycles_dev: not implemented yet");
-    return DFTATOM_E_ARG;
+    if (!c || !d_phi || !d_src || !d_scratch || n_dens <= 0 || n_dens > 65535 || n_cycles <= 0) return DFTATOM_E_ARG;
+    if (levels < 15 || levels > 22) { set_error("stream-mode V-cycles need 15 <= levels <= 22 (smaller grids are solved on chip: dftatom_poisson_vcycles)"); return DFTATOM_E_BAD_OPTION; }
+    const long long N = (1ll << levels) + 1;
+    if (ld < N || (ld & 1) || ((uintptr_t)d_phi & 15) || ((uintptr_t)d_src & 15) || ((uintptr_t)d_scratch & 15)) { set_error("ld must be even and >= N, pointers 16-byte aligned"); return DFTATOM_E_ARG; }
+    const StreamPlan sp = make_stream_plan(levels, n_dens);
+    if (scratch_bytes < (long long)sizeof(double) * sp.total) { set_error("scratch too small"); return DFTATOM_E_ARG; }
+    DFT_CHECK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    // dense operator of the coarse sub-cycle: depends on (levels, delta) only
+    int rc;
+    if ((rc = c->stream_G.ensure(sizeof(double) * 32 * 32))) return rc;
+    if (c->stream_G_levels != levels || c->stream_G_delta != delta) {
+        launch_coarse_op(levels, delta, c->stream_G.as<double>(), st);
+        c->stream_G_levels = levels; c->stream_G_delta = delta;
+    }
+    cudaEvent_t e0, e1;
+    DFT_CHECK(cudaEventCreate(&e0)); DFT_CHECK(cudaEventCreate(&e1));
+    DFT_CHECK(cudaEventRecord(e0, st));
+    long long nl = 0;
+    launch_poisson_stream_vcycles(sp, delta, n_dens, (double*)d_phi, (const double*)d_src, ld, (double*)d_scratch, c->stream_G.as<double>(),
+                                  n_cycles, fuse_tops, c->stream_variant, st, &nl);
+    DFT_CHECK(cudaEventRecord(e1, st));
+    DFT_CHECK(cudaStreamSynchronize(st));
+    DFT_CHECK(cudaGetLastError());
+    float ms = 0.f;
+    DFT_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (device_ms) *device_ms = ms;
+    if (kernel_launches) *kernel_launches = nl;
+    return 0;
 }
 
 int dftatom_vwn(dftatom_ctx* c, int n, const double* rho_a, const double* rho_b, double* va, double* vb, double* vexc, double* eexcdif)

@@ -105,6 +105,8 @@ void launch_search_fused(const GridDev& g, const double* atab, const AtomDev* at
 void launch_search_seg(const GridDev& g, const double* atab, const AtomDev* atoms, const OrbitalDev* orbs, const AtomState* astate,
                        SearchState* ss, int n_orbs, unsigned long long* work, int segments, const int* n_active_orbs, int threshold,
                        int warm_start, cudaStream_t st);
+// lanes through the parallel-in-r sweep: one cluster per 32 lanes sharing (tab, l); segments = 4 x cluster size (<= 32)
+void launch_numerov_lanes_seg(const GridDev& g, const NumerovLaneArgs& a, int segments, cudaStream_t st);
 void launch_dfma_peak(double* out, int blocks, int threads, int iters, cudaStream_t st);
 int search_rounds_needed(int Zmax);
 
@@ -147,6 +149,36 @@ void launch_coarse_op(int L, double delta, double* G, cudaStream_t st);
 void launch_poisson_full(const GridDev& g, const PoissonLevels& lv, const PoissonArgs& a, cudaStream_t st);
 void launch_poisson_vcycles(const PoissonLevels& lv, double delta, int n_dens, double* phi, double* src, double* phi_nat,
                             const double* src_nat, int n_cycles, double* last_err, cudaStream_t st);
+
+// Poisson, stream mode (poisson_stream.cu + poisson_mid_kernel): many densities on a grid that does not fit on chip
+enum { kVisitLoadPhi = 1, kVisitProlongIn = 2, kVisitRestrictOut = 4 };
+struct StreamVisitArgs {
+    double* phi_f; const double* src_f; long long stride_f;   // level l of density k at phi_f + k stride_f (natural node order, 16-byte aligned rows)
+    double* phi_c; double* src_c; long long stride_c;         // level l+1
+    int n;                  // owned nodes of level l (2^(L-l)); node n is the right boundary
+    int slab, HL;           // set by the launcher
+    int flags, sweeps;
+    double a, bcoef, dc;    // (1 + d_l/2)/2, (1 - d_l/2)/2, d_{l+1}                      (PoissonSolver.cpp:56-57, :150)
+};
+void launch_stream_visit(const StreamVisitArgs& v, int n_dens, int variant, cudaStream_t st);
+int stream_window_nodes(int variant);
+void launch_poisson_mid(const PoissonLevels& lv, double delta, int K, int n_dens, double* nat_phi, const double* nat_src, long long nat_stride,
+                        double* mid_phi, double* mid_src, int mid_total, const double* coarse_op, cudaStream_t st);
+// Layout of the scratch block of the stream-mode V-cycle (all offsets in doubles, 4-aligned)
+struct StreamPlan {
+    int L, K;               // levels; K = the 16384-node level (first level run by poisson_mid_kernel)
+    PoissonLevels lv;
+    long long cstride;      // per-density block of the natural-order levels 1..K
+    int coff[24];           // offset of level l (1..K) inside that block
+    int mid_total;          // per-density block of the owner-major levels K..L-1
+    long long off_cphi, off_csrc, off_mphi, off_msrc, total;   // inside the scratch block, for n_dens densities
+};
+StreamPlan make_stream_plan(int L, int n_dens);
+// n_cycles V-cycles (PoissonSolver.h:155-159) on level-0 arrays phi0/src0 [n_dens][ld0] (device, natural order, ld0 % 2 == 0);
+// fuse_tops: the up-visit of cycle k and the down-visit of cycle k+1 of level 0 are one visit with 6 sweeps
+void launch_poisson_stream_vcycles(const StreamPlan& sp, double delta, int n_dens, double* phi0, const double* src0, long long ld0,
+                                   double* scratch, const double* coarse_op, int n_cycles, int fuse_tops, int variant, cudaStream_t st,
+                                   long long* launches);
 
 // XC
 void launch_vwn(int n, const double* ra, const double* rb, double* va, double* vb, double* vexc, double* edif, cudaStream_t st);

@@ -37,6 +37,134 @@ struct SegShared {                 // one per CTA: the results of its 4 segments
     int bad[32];
 };
 
+struct SegRoundOut { int cfull, y0_pos, start; double d_first, y0_log2; };
+
+// One inward sweep of 32 trial energies (lane = energy) by all S = CL x 4 warps of the cluster (warp = radial segment):
+// pass 1, scan, pass 2, totals.  Every warp returns the same result.  Ends with a cluster barrier: the shared results have
+// been consumed when it returns.
+__device__ __forceinline__ SegRoundOut seg_round(const GridDev& g, const double* __restrict__ atab, double ll1, int l, int want, double E,
+                                                 cg::cluster_group& cluster, SegShared& sh, SegShared* sh0, double2* sbuf, int S, int rank,
+                                                 int wl, int w, int lane, unsigned long long* work)
+{
+    const unsigned full = 0xffffffffu;
+    const double kappa = sqrt(2. * fabs(E));
+    const int start = start_index(g, kappa);
+    int imax = start;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) imax = max(imax, __shfl_xor_sync(full, imax, o));
+    const int len = (imax + S - 1) / S;
+    const int top = imax - w * len;
+    const int bot = max(top - len + 1, 1);
+    const bool valid = top >= 1;
+    // this segment's role for this energy: the seeds are nodes start, start - 1; the segment that contains start - 1 runs
+    // the real solution from the seeds (w_start itself depends on the tables only)
+    const int kind = (!valid || start - 1 < bot) ? 0 : (start - 1 > top ? 1 : 2);
+    const bool is_bottom = valid && bot == 1;
+
+    // ---------------- pass 1: transfer matrix (two basis chains) or the seeded real solution ----------------
+    {
+        SweepIn<2> in;
+        in.E[0] = E; in.E[1] = E;
+        in.running[0] = kind == 1; in.W_in[0] = 1.; in.D_in[0] = 0.;
+        in.running[1] = kind == 1; in.W_in[1] = 0.; in.D_in[1] = 1.;
+        in.start[0] = kind == 2 ? start : -1;
+        in.start[1] = -1;
+        FastOut<2> o;
+        o.bad = 0;
+        if (valid && __any_sync(full, kind != 0)) range_sweep<2>(g, atab, ll1, in, top, bot, sbuf + wl * 64, o);
+        sh.meta[wl][lane] = kind | ((int)o.prev[0] << 2) | (o.count[0] << 3);      // normal segments: count and sign follow in pass 2
+        sh.pseg[wl][lane] = kind ? o.P[0] : 1.;
+        sh.m[0][wl][lane] = o.W[0]; sh.m[2][wl][lane] = o.D[0];      // normal: (ww, dw); seeded: outgoing state (W, D)
+        sh.m[1][wl][lane] = o.W[1]; sh.m[3][wl][lane] = o.D[1];      // normal: (wd, dd)
+        if (w == 0) sh.bad[lane] = 0;
+        if (kind == 2 && is_bottom) { sh0->y0s[lane] = o.Y0s[0]; sh0->d1[lane] = o.d_first[0]; }
+        // the map of the whole CTA (its 4 segments in order): identity / matrix / constant state
+        __syncthreads();
+        if (wl == 0) {
+            int ck = 0;
+            double c0 = 1., c1 = 0., c2 = 0., c3 = 1.;
+#pragma unroll
+            for (int vl = 0; vl < kSegWarps; ++vl) {
+                const int kv = sh.meta[vl][lane] & 3;
+                const double m0 = sh.m[0][vl][lane], m1 = sh.m[1][vl][lane], m2 = sh.m[2][vl][lane], m3 = sh.m[3][vl][lane];
+                if (kv == 2) { ck = 2; c0 = m0; c2 = m2; }
+                else if (kv == 1) {
+                    if (ck == 2) { const double na = fma(m0, c0, m1 * c2), nb = fma(m2, c0, m3 * c2); c0 = na; c2 = nb; }
+                    else if (ck == 1) {
+                        const double n0 = fma(m0, c0, m1 * c2), n1 = fma(m0, c1, m1 * c3), n2 = fma(m2, c0, m3 * c2), n3 = fma(m2, c1, m3 * c3);
+                        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+                    } else { ck = 1; c0 = m0; c1 = m1; c2 = m2; c3 = m3; }
+                }
+            }
+            sh.ctk[lane] = ck;
+            sh.ct[0][lane] = c0; sh.ct[1][lane] = c1; sh.ct[2][lane] = c2; sh.ct[3][lane] = c3;
+        }
+        cluster.sync();
+        if (kind == 2 && o.bad) atomicOr(&sh0->bad[lane], 1);
+    }
+    // ---------------- scan: entry state of this segment ----------------
+    double A = 0., Bd = 0.;
+    if (kind == 1) {
+        // the CTAs before this one (their composed maps, distributed shared memory), then the warps before this one
+#pragma unroll 4
+        for (int rk = 0; rk < rank; ++rk) {
+            const SegShared* r = cluster.map_shared_rank(&sh, rk);
+            const int kv = r->ctk[lane];
+            const double m0 = r->ct[0][lane], m1 = r->ct[1][lane], m2 = r->ct[2][lane], m3 = r->ct[3][lane];
+            if (kv == 2) { A = m0; Bd = m2; }
+            else if (kv == 1) { const double na = fma(m0, A, m1 * Bd), nb = fma(m2, A, m3 * Bd); A = na; Bd = nb; }
+        }
+        for (int vl = 0; vl < wl; ++vl) {
+            const int kv = sh.meta[vl][lane] & 3;
+            const double m0 = sh.m[0][vl][lane], m1 = sh.m[1][vl][lane], m2 = sh.m[2][vl][lane], m3 = sh.m[3][vl][lane];
+            if (kv == 2) { A = m0; Bd = m2; }
+            else if (kv == 1) { const double na = fma(m0, A, m1 * Bd), nb = fma(m2, A, m3 * Bd); A = na; Bd = nb; }
+        }
+    }
+    // ---------------- pass 2: the real solution through the normal segments, counting sign changes ----------------
+    if (__any_sync(full, kind == 1)) {
+        SweepIn<1> in;
+        in.E[0] = E; in.running[0] = kind == 1; in.W_in[0] = A; in.D_in[0] = Bd; in.start[0] = -1;
+        FastOut<1> o;
+        range_sweep<1>(g, atab, ll1, in, top, bot, sbuf + wl * 64, o);
+        if (kind == 1) {
+            sh.meta[wl][lane] = 1 | ((int)o.prev[0] << 2) | (o.count[0] << 3);
+            if (is_bottom) { sh0->y0s[lane] = o.Y0s[0]; sh0->d1[lane] = o.d_first[0]; }
+            if (o.bad) atomicOr(&sh0->bad[lane], 1);
+        }
+    }
+    cluster.sync();
+
+    // ---------------- totals (every warp redundantly, so that all warps hold the same bracket) ----------------
+    int cfull = 0;
+    double Ptot = 1.;
+    unsigned pbot = 0;
+    int have_bottom = 0;
+#pragma unroll 4
+    for (int v = 0; v < S; ++v) {
+        const SegShared* r = cluster.map_shared_rank(&sh, v / kSegWarps);
+        const int mv = r->meta[v % kSegWarps][lane];
+        const double pv = r->pseg[v % kSegWarps][lane];
+        if (mv & 3) { cfull += mv >> 3; pbot = (unsigned)(mv >> 2) & 1u; Ptot *= pv; have_bottom = 1; }
+    }
+    const double Y0s = sh0->y0s[lane], d1v = sh0->d1[lane];
+    int y0_pos = Y0s > 0.;
+    double y0_log2 = (fabs(Y0s) <= 1.7e308) ? log2(fabs(Y0s)) - log2(fabs(Ptot)) : INFINITY;
+    cfull += (((y0_pos ? 0u : 1u) != pbot) ? 1 : 0);
+    int lane_bad = sh0->bad[lane] | !(Ptot > 0.) | !have_bottom | (start < 3);
+    double d_first = d1v;
+    if (__any_sync(full, lane_bad)) {
+        if (work && threadIdx.x == 0) atomicAdd(work + DFTATOM_K_POTENTIAL, 1ULL);       // rounds that fell back to the serial sweep
+        // a non-positive 1 - f/12 inside the sweep (grid far too coarse for this energy): generic serial path
+        const LaneOut so = sweep_lane(g, atab, l, E, want);
+        cfull = so.count_full; d_first = so.d_first; y0_log2 = so.y0_log2; y0_pos = so.y0_pos;
+    }
+    cluster.sync();
+    SegRoundOut r;
+    r.cfull = cfull; r.y0_pos = y0_pos; r.start = start; r.d_first = d_first; r.y0_log2 = y0_log2;
+    return r;
+}
+
 __global__ void __launch_bounds__(32 * kSegWarps) search_seg_kernel(GridDev g, const double* __restrict__ atab_all, const AtomDev* atoms,
                                                              const OrbitalDev* orbs, const AtomState* astate, SearchState* ss, int n_orbs,
                                                              unsigned long long* work, const int* n_active_orbs, int threshold,
@@ -75,122 +203,10 @@ __global__ void __launch_bounds__(32 * kSegWarps) search_seg_kernel(GridDev g, c
     for (int round = 0; round < 64 && bracket_open(b.lo, b.hi); ++round) {
         // every warp computes the same 32 trial energies
         const double E = sample_energy(b, lane);
-        const double kappa = sqrt(2. * fabs(E));
-        const int start = start_index(g, kappa);
-        int imax = start;
-#pragma unroll
-        for (int o = 16; o; o >>= 1) imax = max(imax, __shfl_xor_sync(full, imax, o));
-        const int len = (imax + S - 1) / S;
-        const int top = imax - w * len;
-        const int bot = max(top - len + 1, 1);
-        const bool valid = top >= 1;
-        // this segment's role for this energy: the seeds are nodes start, start - 1; the segment that contains start - 1 runs
-        // the real solution from the seeds (w_start itself depends on the tables only)
-        const int kind = (!valid || start - 1 < bot) ? 0 : (start - 1 > top ? 1 : 2);
-        const bool is_bottom = valid && bot == 1;
-
-        // ---------------- pass 1: transfer matrix (two basis chains) or the seeded real solution ----------------
-        {
-            SweepIn<2> in;
-            in.E[0] = E; in.E[1] = E;
-            in.running[0] = kind == 1; in.W_in[0] = 1.; in.D_in[0] = 0.;
-            in.running[1] = kind == 1; in.W_in[1] = 0.; in.D_in[1] = 1.;
-            in.start[0] = kind == 2 ? start : -1;
-            in.start[1] = -1;
-            FastOut<2> o;
-            o.bad = 0;
-            if (valid && __any_sync(full, kind != 0)) range_sweep<2>(g, atab, ll1, in, top, bot, sbuf + wl * 64, o);
-            sh.meta[wl][lane] = kind | ((int)o.prev[0] << 2) | (o.count[0] << 3);      // normal segments: count and sign follow in pass 2
-            sh.pseg[wl][lane] = kind ? o.P[0] : 1.;
-            sh.m[0][wl][lane] = o.W[0]; sh.m[2][wl][lane] = o.D[0];      // normal: (ww, dw); seeded: outgoing state (W, D)
-            sh.m[1][wl][lane] = o.W[1]; sh.m[3][wl][lane] = o.D[1];      // normal: (wd, dd)
-            if (w == 0) sh.bad[lane] = 0;
-            if (kind == 2 && is_bottom) { sh0->y0s[lane] = o.Y0s[0]; sh0->d1[lane] = o.d_first[0]; }
-            // the map of the whole CTA (its 4 segments in order): identity / matrix / constant state
-            __syncthreads();
-            if (wl == 0) {
-                int ck = 0;
-                double c0 = 1., c1 = 0., c2 = 0., c3 = 1.;
-#pragma unroll
-                for (int vl = 0; vl < kSegWarps; ++vl) {
-                    const int kv = sh.meta[vl][lane] & 3;
-                    const double m0 = sh.m[0][vl][lane], m1 = sh.m[1][vl][lane], m2 = sh.m[2][vl][lane], m3 = sh.m[3][vl][lane];
-                    if (kv == 2) { ck = 2; c0 = m0; c2 = m2; }
-                    else if (kv == 1) {
-                        if (ck == 2) { const double na = fma(m0, c0, m1 * c2), nb = fma(m2, c0, m3 * c2); c0 = na; c2 = nb; }
-                        else if (ck == 1) {
-                            const double n0 = fma(m0, c0, m1 * c2), n1 = fma(m0, c1, m1 * c3), n2 = fma(m2, c0, m3 * c2), n3 = fma(m2, c1, m3 * c3);
-                            c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-                        } else { ck = 1; c0 = m0; c1 = m1; c2 = m2; c3 = m3; }
-                    }
-                }
-                sh.ctk[lane] = ck;
-                sh.ct[0][lane] = c0; sh.ct[1][lane] = c1; sh.ct[2][lane] = c2; sh.ct[3][lane] = c3;
-            }
-            cluster.sync();
-            if (kind == 2 && o.bad) atomicOr(&sh0->bad[lane], 1);
-        }
-        // ---------------- scan: entry state of this segment ----------------
-        double A = 0., Bd = 0.;
-        if (kind == 1) {
-            // the CTAs before this one (their composed maps, distributed shared memory), then the warps before this one
-#pragma unroll 4
-            for (int rk = 0; rk < rank; ++rk) {
-                const SegShared* r = cluster.map_shared_rank(&sh, rk);
-                const int kv = r->ctk[lane];
-                const double m0 = r->ct[0][lane], m1 = r->ct[1][lane], m2 = r->ct[2][lane], m3 = r->ct[3][lane];
-                if (kv == 2) { A = m0; Bd = m2; }
-                else if (kv == 1) { const double na = fma(m0, A, m1 * Bd), nb = fma(m2, A, m3 * Bd); A = na; Bd = nb; }
-            }
-            for (int vl = 0; vl < wl; ++vl) {
-                const int kv = sh.meta[vl][lane] & 3;
-                const double m0 = sh.m[0][vl][lane], m1 = sh.m[1][vl][lane], m2 = sh.m[2][vl][lane], m3 = sh.m[3][vl][lane];
-                if (kv == 2) { A = m0; Bd = m2; }
-                else if (kv == 1) { const double na = fma(m0, A, m1 * Bd), nb = fma(m2, A, m3 * Bd); A = na; Bd = nb; }
-            }
-        }
-        // ---------------- pass 2: the real solution through the normal segments, counting sign changes ----------------
-        if (__any_sync(full, kind == 1)) {
-            SweepIn<1> in;
-            in.E[0] = E; in.running[0] = kind == 1; in.W_in[0] = A; in.D_in[0] = Bd; in.start[0] = -1;
-            FastOut<1> o;
-            range_sweep<1>(g, atab, ll1, in, top, bot, sbuf + wl * 64, o);
-            if (kind == 1) {
-                sh.meta[wl][lane] = 1 | ((int)o.prev[0] << 2) | (o.count[0] << 3);
-                if (is_bottom) { sh0->y0s[lane] = o.Y0s[0]; sh0->d1[lane] = o.d_first[0]; }
-                if (o.bad) atomicOr(&sh0->bad[lane], 1);
-            }
-        }
-        cluster.sync();
-
-        // ---------------- totals (every warp redundantly, so that all warps hold the same bracket) ----------------
-        int cfull = 0;
-        double Ptot = 1.;
-        unsigned pbot = 0;
-        int have_bottom = 0;
-#pragma unroll 4
-        for (int v = 0; v < S; ++v) {
-            const SegShared* r = cluster.map_shared_rank(&sh, v / kSegWarps);
-            const int mv = r->meta[v % kSegWarps][lane];
-            const double pv = r->pseg[v % kSegWarps][lane];
-            if (mv & 3) { cfull += mv >> 3; pbot = (unsigned)(mv >> 2) & 1u; Ptot *= pv; have_bottom = 1; }
-        }
-        const double Y0s = sh0->y0s[lane], d1v = sh0->d1[lane];
-        int y0_pos = Y0s > 0.;
-        double y0_log2 = (fabs(Y0s) <= 1.7e308) ? log2(fabs(Y0s)) - log2(fabs(Ptot)) : INFINITY;
-        cfull += (((y0_pos ? 0u : 1u) != pbot) ? 1 : 0);
-        int lane_bad = sh0->bad[lane] | !(Ptot > 0.) | !have_bottom | (start < 3);
-        double d_first = d1v;
-        if (__any_sync(full, lane_bad)) {
-            if (work && threadIdx.x == 0) atomicAdd(work + DFTATOM_K_POTENTIAL, 1ULL);       // rounds that fell back to the serial sweep
-            // a non-positive 1 - f/12 inside the sweep (grid far too coarse for this energy): generic serial path
-            const LaneOut so = sweep_lane(g, atab, ob.l, E, ob.want);
-            cfull = so.count_full; d_first = so.d_first; y0_log2 = so.y0_log2; y0_pos = so.y0_pos;
-        }
-        if (w == 0) steps += start - 1;
+        const SegRoundOut r = seg_round(g, atab, ll1, ob.l, ob.want, E, cluster, sh, sh0, sbuf, S, rank, wl, w, lane, work);
+        if (w == 0) steps += r.start - 1;
         ++rounds;
-        update_bracket(b, E, cfull > ob.want + (d_first < 0. ? 1 : 0), y0_pos, y0_log2);
-        cluster.sync();                                    // shared results are consumed before the next round overwrites them
+        update_bracket(b, E, r.cfull > ob.want + (r.d_first < 0. ? 1 : 0), r.y0_pos, r.y0_log2);
     }
     if (w == 0 && lane == 0) {
         SearchState s = ss[k];
@@ -231,6 +247,55 @@ void launch_search_seg(const GridDev& g, const double* atab, const AtomDev* atom
     attr[0].val.clusterDim.x = (unsigned)CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     cudaLaunchKernelEx(&cfg, search_seg_kernel, g, atab, atoms, orbs, astate, ss, n_orbs, work, n_active_orbs, threshold, warm_start);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// lanes kernel (component entry point / C5b microbench): one cluster per group of 32 lanes that share (tab, l)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32 * kSegWarps) numerov_lanes_seg_kernel(GridDev g, NumerovLaneArgs a)
+{
+    __shared__ SegShared sh;
+    __shared__ double2 sbuf[kSegWarps * 64];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int CL = (int)cluster.num_blocks();
+    const int S = CL * kSegWarps;
+    const int rank = (int)cluster.block_rank();
+    const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = rank * kSegWarps + wl;
+    const int grp = blockIdx.x / CL;
+    SegShared* sh0 = cluster.map_shared_rank(&sh, 0);
+    if (grp * 32 >= a.n_lanes) return;
+    const int k = grp * 32 + lane, kk = min(k, a.n_lanes - 1);
+    const int l = a.l[kk];
+    const SegRoundOut r = seg_round(g, a.atab + (size_t)a.tab[kk] * g.N, (double)(l * (l + 1)), l, a.limit ? a.limit[kk] : 0, a.E[kk], cluster, sh,
+                                    sh0, sbuf, S, rank, wl, w, lane, nullptr);
+    if (w == 0 && k < a.n_lanes) {
+        if (a.y0_sign) a.y0_sign[k] = r.y0_pos;
+        if (a.y0_log2) a.y0_log2[k] = r.y0_log2;
+        if (a.count) a.count[k] = r.cfull;
+    }
+}
+
+static int seg_cluster_size(int segments)
+{
+    int CL = 1;
+    while (CL * 2 * kSegWarps <= segments && CL * 2 * kSegWarps <= kSegMax) CL *= 2;      // 1, 2, 4 or 8 CTAs per orbital
+    return CL;
+}
+
+void launch_numerov_lanes_seg(const GridDev& g, const NumerovLaneArgs& a, int segments, cudaStream_t st)
+{
+    const int CL = seg_cluster_size(segments);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(((a.n_lanes + 31) / 32) * CL));
+    cfg.blockDim = dim3(32 * kSegWarps);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, numerov_lanes_seg_kernel, g, a);
 }
 
 }  // namespace dft

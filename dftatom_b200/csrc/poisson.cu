@@ -1368,6 +1368,48 @@ void launch_poisson_full(const GridDev& g, const PoissonLevels& lv, const Poisso
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Stream mode (many densities on a grid that does not fit on chip, poisson_stream.cu): the levels above 16384 nodes are
+// visited by stream_visit_kernel launches over all densities; this kernel is the part of the V-cycle below them, one CTA
+// per density: it takes Source_K (K = the 16384-node level, natural node order, written by the restriction of level K-1),
+// runs  visit(K) ... restrict ... dense coarse operator ... prolong ... visit(K)  with Phi_K starting from zero, and leaves
+// Phi_K in natural order for the prolongation into level K-1.  Its own level arrays (owner-major) live in mid_phi/mid_src.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPT) poisson_mid_kernel(double delta, PoissonLevels lv, int K, double* nat_phi, const double* nat_src,
+                                                         long long nat_stride, double* mid_phi, double* mid_src, int mid_total,
+                                                         const double* Gg, int smem_doubles)
+{
+    const int k = blockIdx.x;
+    // (the level offsets of `lv` count from level 0: shift the block so that level K lands at its start)
+    hierarchy_setup(lv, delta, mid_phi + (size_t)k * mid_total - lv.off[K], mid_src + (size_t)k * mid_total - lv.off[K], smem_doubles, Gg,
+                    nullptr, 2, 0, nullptr);
+    const int nK = g_sm.lc[K].n, m = g_sm.m;
+    const Lay yK = g_sm.lc[K].lay;
+    const Ref SK = Ref::S(K), PK = Ref::P(K);
+    const double* ns = nat_src + (size_t)k * nat_stride;
+    double* np = nat_phi + (size_t)k * nat_stride;
+    for (int i = threadIdx.x; i <= nK; i += blockDim.x) SK.st(slot(i, yK), __ldcg(ns + i));
+    __syncthreads();
+    Ctl ctl{ false, false };
+    for (int l = K; l < m; ++l) visit(ctl, l, kRestrictOut, 3);
+    if (threadIdx.x < 32) dense_apply_warp();
+    ctl.pending = true;
+    for (int l = m - 1; l >= K; --l) visit(ctl, l, kLoadPhi | kProlongIn, 3);
+    block_begin(ctl);
+    __syncthreads();
+    for (int i = threadIdx.x; i <= nK; i += blockDim.x) np[i] = PK.ld(slot(i, yK));
+}
+
+void launch_poisson_mid(const PoissonLevels& lv, double delta, int K, int n_dens, double* nat_phi, const double* nat_src, long long nat_stride,
+                        double* mid_phi, double* mid_src, int mid_total, const double* coarse_op, cudaStream_t st)
+{
+    const int sd = dyn_doubles_for(lv);
+    const size_t bytes = (size_t)sd * sizeof(double);
+    static size_t attr_bytes = 0;
+    if (bytes > attr_bytes) { cudaFuncSetAttribute(poisson_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); attr_bytes = bytes; }
+    poisson_mid_kernel<<<n_dens, kPT, bytes, st>>>(delta, lv, K, nat_phi, nat_src, nat_stride, mid_phi, mid_src, mid_total, coarse_op, sd);
+}
+
 // V-cycles as defined by the reference on given (Phi_0, Source_0) in natural node order: parity / microbench entry point
 // (every level is swept level by level: no dense coarse operator)
 __global__ void __launch_bounds__(kPT) poisson_vcycles_kernel(double delta, PoissonLevels lv, double* phi_all, double* src_all,

@@ -102,6 +102,7 @@ const char* dftatom_version(void);
  *   "search_mode"  (default 0) 0 = fused single-predicate multisection (production); 1 = reference-shaped three-stage
  *                   search (node-count window edges, then the sign change of y(0)), kept for validation
  *   "profile"      (default 0) time every kernel class with CUDA events, see dftatom_last_profile
+ *   "stream_variant" (default 0) window shape of the stream-mode Poisson visits: 0 = 256 threads x 16 nodes, 1 = 256 x 8, 2 = 512 x 8
  */
 int dftatom_set_option(dftatom_ctx* ctx, const char* key, double value);
 
@@ -139,10 +140,18 @@ int dftatom_measure_fp64_peak(dftatom_ctx* ctx, double* tflops);
  * y0_sign[k] = 1 if SolutionInZero > 0 else 0; y0_log2[k] ~ log2|y0| (for the 1e15 guard).
  * impl = 1: reference-shaped sweep, count[k] = CountNodes (with its early exits, clamped at nodes_limit+1).
  * impl = 0: the production tile-staged sweep, count[k] = number of ALL sign changes of y_start..y_1,y_0 (the Sturm count
- *           the fused search uses; nodes_limit ignored; -1 if the lane hit a non-positive 1 - f/12). */
+ *           the fused search uses; nodes_limit ignored; -1 if the lane hit a non-positive 1 - f/12).
+ * impl = 2: the same count through the parallel-in-r sweep (one thread-block cluster per 32 lanes, warp = radial segment,
+ *           set_option("r_segments") segments). */
 int dftatom_numerov_lanes(dftatom_ctx* ctx, const double* V, int levels, double delta, double max_r, int n_lanes,
                           const int* l, const double* E, const int* nodes_limit, int impl,
                           int* y0_sign, double* y0_log2, int* count);
+/* the same, plus a device-timed repetition for the C5b microbench: after the checked launch the kernel is launched `reps` more
+ * times between CUDA events (potential table and lanes resident in HBM); ms_per_launch = their average,
+ * lane_node_steps = sum over lanes of (cut-off index - 1), the node-steps one launch performs (11 FLOP each) */
+int dftatom_numerov_lanes_timed(dftatom_ctx* ctx, const double* V, int levels, double delta, double max_r, int n_lanes,
+                                const int* l, const double* E, const int* nodes_limit, int impl,
+                                int* y0_sign, double* y0_log2, int* count, int reps, float* ms_per_launch, double* lane_node_steps);
 /* per-level eigenvalue search on one potential (DFTAtom.cpp:497-541 + LocateInterval :566-604), all levels concurrently */
 int dftatom_level_search(dftatom_ctx* ctx, const double* V, int levels, double delta, double max_r, int Z,
                          int n_levels, const int* n, const int* l, double* E_out, int* converged_out);
@@ -162,8 +171,15 @@ int dftatom_vwn(dftatom_ctx* ctx, int n, const double* rho_a, const double* rho_
 int dftatom_simpson38(dftatom_ctx* ctx, double step, const double* v, int n, int n_rows, double* out);
 
 /* ---- microbenches on DEVICE-resident data (bench.py `value` legs); pointers are CUDA device addresses ---- */
-int dftatom_poisson_vcycles_dev(dftatom_ctx* ctx, int levels, double delta, int n_dens, void* d_phi, const void* d_src,
-                                void* d_scratch, long long scratch_bytes, int n_cycles, float* device_ms);
+/* Stream-mode V-cycles (config C5a: many densities on a grid that does not fit on chip; levels >= 15).  n_cycles V-cycles
+ * (PoissonSolver.h:155-159: 3 + 3 Gauss-Seidel sweeps per level, injection of the residual, linear prolongation) in place on
+ * d_phi[n_dens][ld] with source d_src[n_dens][ld] (natural node order, N = 2^levels + 1 <= ld, ld even, both 16-byte aligned).
+ * d_scratch: dftatom_poisson_scratch_bytes(levels, n_dens) bytes.  fuse_tops != 0: the last visit of level 0 of one cycle and
+ * the first visit of the next are one pass over the level (6 sweeps).  device_ms: CUDA-event time of the n_cycles cycles;
+ * kernel_launches: launches issued.  The call returns after the work has completed. */
+int dftatom_poisson_vcycles_dev(dftatom_ctx* ctx, int levels, double delta, int n_dens, void* d_phi, const void* d_src, long long ld,
+                                void* d_scratch, long long scratch_bytes, int n_cycles, int fuse_tops, float* device_ms,
+                                long long* kernel_launches);
 long long dftatom_poisson_scratch_bytes(int levels, int n_dens);
 
 #ifdef __cplusplus
