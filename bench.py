@@ -150,6 +150,10 @@ def run_cuda_arm(a):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (dftatom_b200 has no CPU fallback)")
+    # stdout carries exactly one JSON line: whatever libraries print on fd 1 meanwhile (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
@@ -283,7 +287,9 @@ def run_cuda_arm(a):
         if world == 1 and not a.no_cpu_baseline:
             cb = cpu_reference_sample(30.0)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

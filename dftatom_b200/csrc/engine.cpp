@@ -61,6 +61,9 @@ struct dftatom_ctx {
     int energies_per_lane = 1;
     int warm_start = 1;
     int stream_variant = 0;    // window shape of the stream-mode Poisson visits (poisson_stream.cu)
+    int stream_poisson = 1;    // grids above 16385 nodes: level visits streamed over all densities (poisson_stream.cu) instead of one CTA / team per density
+    int stream_min_dens = 4;   // ... when the batch has at least this many densities (below, the team of CTAs per density is faster)
+    DevBuf stream_src0, stream_scratch;
     DevBuf stream_G; int stream_G_levels = 0; double stream_G_delta = 0.;   // dense coarse operator of the stream-mode V-cycle
     dftatom_kernel_profile prof[DFTATOM_K_COUNT] = {};
     // reusable buffers
@@ -175,7 +178,7 @@ void dftatom_destroy(dftatom_ctx* c)
                       &c->phi, &c->src, &c->u0, &c->ubuf, &c->zbc, &c->tab_of, &c->steps, &c->n_active };
     for (DevBuf* b : all) b->release();
     for (DevBuf& b : c->scratch) b.release();
-    c->stream_G.release();
+    c->stream_G.release(); c->stream_src0.release(); c->stream_scratch.release();
     if (c->h_active) cudaFreeHost(c->h_active);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -197,6 +200,8 @@ int dftatom_set_option(dftatom_ctx* c, const char* key, double value)
     else if (k == "search_mode") c->search_mode = (int)value;
     else if (k == "match_mode") c->match_mode = (int)value;
     else if (k == "warm_start") c->warm_start = value != 0.;
+    else if (k == "stream_poisson") c->stream_poisson = value != 0.;
+    else if (k == "stream_min_dens") c->stream_min_dens = std::max(1, (int)value);
     else if (k == "stream_variant") c->stream_variant = std::min(2, std::max(0, (int)value));
     else if (k == "energies_per_lane") c->energies_per_lane = ((int)value == 2) ? 2 : 1;
     else { set_error("unknown option " + k); return DFTATOM_E_ARG; }
@@ -329,7 +334,11 @@ int dftatom_solve_batch(dftatom_ctx* c, const dftatom_options* opts, int n_atoms
     if ((rc = c->phi.ensure(sizeof(double) * (size_t)n_atoms * lv.total))) return rc;
     if ((rc = c->src.ensure(sizeof(double) * (size_t)n_atoms * lv.total))) return rc;
     if ((rc = c->u0.ensure(sizeof(double) * (size_t)n_atoms * N))) return rc;
-    if ((rc = c->ubuf.ensure(sizeof(double) * (size_t)n_atoms * N))) return rc;
+    const bool stream = c->stream_poisson && n_atoms >= c->stream_min_dens && g.L >= 15 && g.L <= 22 && c->refine_vcycles == 0 && !c->floor_stop;
+    const int ldU = stream ? ((N + 3) & ~3) : N;
+    const StreamPlan splan = stream ? make_stream_plan(g.L, n_atoms) : StreamPlan{};
+    if ((rc = c->ubuf.ensure(sizeof(double) * (size_t)n_atoms * ldU))) return rc;
+    if (stream && ((rc = c->stream_src0.ensure(sizeof(double) * (size_t)n_atoms * ldU)) || (rc = c->stream_scratch.ensure(sizeof(double) * (size_t)splan.total)))) return rc;
     if ((rc = c->steps.ensure(sizeof(dftatom_step) * (size_t)n_atoms * stride))) return rc;
     if ((rc = c->n_active.ensure(sizeof(int) * 2))) return rc;
     DFT_CHECK(cudaMemsetAsync(c->steps.p, 0, sizeof(dftatom_step) * (size_t)n_atoms * stride, st));
@@ -342,7 +351,7 @@ int dftatom_solve_batch(dftatom_ctx* c, const dftatom_options* opts, int n_atoms
     b.atoms = c->atoms.as<AtomDev>(); b.astate = c->astate.as<AtomState>(); b.orbs = c->orbs.as<OrbitalDev>();
     b.ss = c->ss.as<SearchState>(); b.rho = c->rho.as<double>(); b.rhot = c->rhot.as<double>(); b.vpot = c->vpot.as<double>();
     b.atab = c->atab.as<double>(); b.psi = c->psi.as<double>(); b.match_pt = c->match_pt.as<int>(); b.inv_norm = c->inv_norm.as<double>(); b.epart = c->epart.as<double>(); b.eticket = c->eticket.as<int>();
-    b.phi = c->phi.as<double>(); b.src = c->src.as<double>(); b.U = c->ubuf.as<double>(); b.Zbc = c->zbc.as<int>(); b.tab_of = c->tab_of.as<int>();
+    b.phi = c->phi.as<double>(); b.src = c->src.as<double>(); b.U = c->ubuf.as<double>(); b.ldU = ldU; b.Zbc = c->zbc.as<int>(); b.tab_of = c->tab_of.as<int>();
     b.steps = c->steps.as<dftatom_step>(); b.steps_stride = stride; b.n_active = c->n_active.as<int>();
 
     PoissonArgs pa{};
@@ -352,6 +361,24 @@ int dftatom_solve_batch(dftatom_ctx* c, const dftatom_options* opts, int n_atoms
     pa.refine_vcycles = c->refine_vcycles; pa.u0 = c->u0.as<double>();
     if ((rc = c->team_bar.ensure(sizeof(unsigned) * (size_t)n_atoms))) return rc;
     pa.team_bar = c->team_poisson ? c->team_bar.as<unsigned>() : nullptr;
+    pa.nat_stride = 0;
+    StreamSolveArgs sa{};
+    sa.n_dens = n_atoms; sa.rho = b.rhot; sa.rho_stride = N; sa.psrc = g.psrc; sa.src0 = c->stream_src0.as<double>(); sa.U = b.U; sa.ld0 = ldU;
+    sa.Zbc = b.Zbc; sa.scratch = c->stream_scratch.as<double>(); sa.coarse_op = g.coarse_op; sa.variant = c->stream_variant;
+    sa.skip = &b.astate[0].done; sa.skip_stride_bytes = (int)sizeof(AtomState);
+    // the Poisson solve of one SCF step: FullCycle (ramp + max_vcycles V-cycles), or warm_vcycles V-cycles from the previous U
+    auto poisson_solve = [&](int warm_vcycles, long long& n_launch) {
+        if (stream) {
+            sa.warm = warm_vcycles > 0; sa.n_v = warm_vcycles > 0 ? warm_vcycles : c->max_vcycles;
+            long long nl = 0;
+            launch_poisson_stream_solve(splan, g.delta, sa, st, &nl);
+            n_launch += nl;
+        } else {
+            pa.warm_vcycles = warm_vcycles;
+            launch_poisson_full(g, lv, pa, st);
+            ++n_launch;
+        }
+    };
 
     cudaEvent_t ev0, ev1;
     DFT_CHECK(cudaEventCreate(&ev0));
@@ -375,7 +402,7 @@ int dftatom_solve_batch(dftatom_ctx* c, const dftatom_options* opts, int n_atoms
     DFT_CHECK(cudaEventRecord(ev0, st));
     // initial guess -> U -> V   (DFTAtom.cpp:371-392)
     launch_initial_density(g, b, st); ++launches;
-    launch_poisson_full(g, lv, pa, st); ++launches;
+    poisson_solve(0, launches);
     launch_potential_energy(g, lv, b, 1, st); ++launches;
 
     const int rounds = search_rounds_needed(zmax);
@@ -412,8 +439,7 @@ int dftatom_solve_batch(dftatom_ctx* c, const dftatom_options* opts, int n_atoms
         launch_density_update(g, b, st); ++launches;
         end_span();
         begin_span(DFTATOM_K_POISSON);
-        pa.warm_vcycles = (sp >= c->warm_after) ? c->warm_vcycles : 0;
-        launch_poisson_full(g, lv, pa, st); ++launches;
+        poisson_solve((sp >= c->warm_after) ? c->warm_vcycles : 0, launches);
         end_span();
         begin_span(DFTATOM_K_POTENTIAL);
         launch_potential_energy(g, lv, b, 0, st); ++launches;
@@ -679,6 +705,24 @@ int dftatom_poisson_solve(dftatom_ctx* c, int levels, double delta, double max_r
         if ((rc = c->scratch[5].ensure(sizeof(long long) * 128))) return rc;
         DFT_CHECK(cudaMemsetAsync(c->scratch[5].p, 0, sizeof(long long) * 128, st));
         pa.dbg = c->scratch[5].as<long long>();
+    }
+    const bool stream = c->stream_poisson && n_dens >= c->stream_min_dens && levels >= 15 && levels <= 22 && c->refine_vcycles == 0 && !c->floor_stop && !c->profile;
+    if (stream) {
+        // grids beyond the chip: level visits streamed over all densities (poisson_stream.cu)
+        const StreamPlan splan = make_stream_plan(levels, n_dens);
+        const long long ld = (N + 3) & ~3;
+        if ((rc = c->stream_src0.ensure(sizeof(double) * (size_t)n_dens * ld)) || (rc = c->stream_scratch.ensure(sizeof(double) * (size_t)splan.total))) return rc;
+        if ((rc = c->ubuf.ensure(sizeof(double) * (size_t)n_dens * ld))) return rc;
+        StreamSolveArgs sa{};
+        sa.n_dens = n_dens; sa.rho = dr.as<double>(); sa.rho_stride = N; sa.psrc = g.psrc; sa.src0 = c->stream_src0.as<double>();
+        sa.U = c->ubuf.as<double>(); sa.ld0 = ld; sa.Zbc = dz.as<int>(); sa.scratch = c->stream_scratch.as<double>(); sa.coarse_op = g.coarse_op;
+        sa.n_v = c->max_vcycles; sa.warm = 0; sa.variant = c->stream_variant;
+        launch_poisson_stream_solve(splan, delta, sa, st, nullptr);
+        DFT_CHECK(cudaMemcpy2DAsync(U, sizeof(double) * N, c->ubuf.p, sizeof(double) * ld, sizeof(double) * N, n_dens, cudaMemcpyDeviceToHost, st));
+        if (vcycles_used) for (int k = 0; k < n_dens; ++k) vcycles_used[k] = c->max_vcycles;
+        DFT_CHECK(cudaStreamSynchronize(st));
+        DFT_CHECK(cudaGetLastError());
+        return 0;
     }
     launch_poisson_full(g, lv, pa, st);
     if (c->profile) {

@@ -128,6 +128,7 @@ struct PoissonArgs {
     const double* rho;      // [n_dens][N] total density, natural node order (or NULL)
     const double* src_nat;  // [n_dens][N] Source_0 in natural node order, used when rho is NULL (or NULL)
     double* u_out;          // [n_dens][N] result U(r) = Phi_0 in natural node order (or NULL)
+    long long nat_stride;   // row stride of rho / src_nat / u_out / u0 in doubles (0: N)
     const int* Zbc;         // [n_dens] boundary value at Rmax (may be NULL: use hi_bc)
     double* phi; double* src;   // [n_dens][levels.total] the hierarchy, thread-major node order inside a level (poisson.cu)
     const int* skip;        // optional per-density skip flag (AtomState.done), stride given
@@ -159,11 +160,13 @@ struct StreamVisitArgs {
     int slab, HL;           // set by the launcher
     int flags, sweeps;
     double a, bcoef, dc;    // (1 + d_l/2)/2, (1 - d_l/2)/2, d_{l+1}                      (PoissonSolver.cpp:56-57, :150)
+    const int* skip; int skip_stride_bytes;                   // optional per-density skip flag (AtomState.done)
 };
 void launch_stream_visit(const StreamVisitArgs& v, int n_dens, int variant, cudaStream_t st);
 int stream_window_nodes(int variant);
 void launch_poisson_mid(const PoissonLevels& lv, double delta, int K, int n_dens, double* nat_phi, const double* nat_src, long long nat_stride,
-                        double* mid_phi, double* mid_src, int mid_total, const double* coarse_op, cudaStream_t st);
+                        double* mid_phi, double* mid_src, int mid_total, const double* coarse_op, const int* skip, int skip_stride_bytes,
+                        cudaStream_t st);
 // Layout of the scratch block of the stream-mode V-cycle (all offsets in doubles, 4-aligned)
 struct StreamPlan {
     int L, K;               // levels; K = the 16384-node level (first level run by poisson_mid_kernel)
@@ -179,6 +182,18 @@ StreamPlan make_stream_plan(int L, int n_dens);
 void launch_poisson_stream_vcycles(const StreamPlan& sp, double delta, int n_dens, double* phi0, const double* src0, long long ld0,
                                    double* scratch, const double* coarse_op, int n_cycles, int fuse_tops, int variant, cudaStream_t st,
                                    long long* launches);
+// SolvePoissonNonUniform (PoissonSolver.h:51-81) in stream mode: FullCycle's full-multigrid ramp + n_v V-cycles, or (warm) n_v
+// V-cycles from the previous solution held in U.  Source_0 = psrc * rho is built into src0 when rho is given.
+struct StreamSolveArgs {
+    int n_dens;
+    const double* rho; long long rho_stride; const double* psrc;    // optional: densities [n_dens][rho_stride] and the grid's r 4 pi K table
+    double* src0; double* U; long long ld0;                         // level 0: Source_0 and the solution U(r) = Phi_0, rows of ld0 doubles
+    const int* Zbc;                                                 // [n_dens] boundary value at Rmax
+    double* scratch; const double* coarse_op;
+    int n_v, warm, variant;
+    const int* skip; int skip_stride_bytes;
+};
+void launch_poisson_stream_solve(const StreamPlan& sp, double delta, const StreamSolveArgs& a, cudaStream_t st, long long* launches);
 
 // XC
 void launch_vwn(int n, const double* ra, const double* rb, double* va, double* vb, double* vexc, double* edif, cudaStream_t st);
@@ -198,7 +213,8 @@ struct ScfBuffers {
     int* eticket;     // [n_atoms] arrival counter of its CTAs (zero between launches)
     double* inv_norm; // [n_orbs] 1 / integral u^2 dr of the matched solution in psi
     double* phi; double* src;   // Poisson hierarchy [n_atoms][levels.total]
-    double* U;        // [n_atoms][N] Hartree U(r) = r V_H, natural node order (output of the Poisson solve)
+    double* U;        // [n_atoms][ldU] Hartree U(r) = r V_H, natural node order (output of the Poisson solve)
+    int ldU;          // row stride of U (N, or N rounded up to a multiple of 4 when the stream-mode Poisson solver writes it)
     int* Zbc;         // [n_atoms]
     int* tab_of;      // [n_atoms][2] table row of (atom, spin) or -1
     dftatom_step* steps;  // [n_atoms][steps_stride]

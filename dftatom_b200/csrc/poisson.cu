@@ -1135,6 +1135,7 @@ __global__ void __launch_bounds__(kPT) poisson_full_kernel(GridDev g, PoissonLev
     const bool team = G > 1, leader = rank == 0;
     if (a.skip && *reinterpret_cast<const int*>(reinterpret_cast<const char*>(a.skip) + (size_t)k * a.skip_stride_bytes)) return;
     const int N = g.N, L = lv.L, c = L - 1;
+    const size_t NS = a.nat_stride ? (size_t)a.nat_stride : (size_t)N;       // row stride of the natural-order arrays
     const long long t_start = clock64();
     long long* dbg = (a.dbg && blockIdx.x == 0) ? a.dbg : nullptr;
     hierarchy_setup(lv, g.delta, a.phi + (size_t)k * lv.total, a.src + (size_t)k * lv.total, a.smem_doubles, a.coarse_op, dbg, G, rank,
@@ -1147,12 +1148,12 @@ __global__ void __launch_bounds__(kPT) poisson_full_kernel(GridDev g, PoissonLev
     // Source_0 (PoissonSolver.h:55-74)
     if (team) {
         if (!leader) {
-            const double* rho = a.rho ? a.rho + (size_t)k * N : a.src_nat + (size_t)k * N;
+            const double* rho = a.rho ? a.rho + (size_t)k * NS : a.src_nat + (size_t)k * NS;
             double* s0 = g_sm.gsrc + g_sm.lc[0].os;
             for (int i = ws0; i < N; i += wstride) s0[i] = a.rho ? g.psrc[i] * rho[i] : rho[i];
         }
-    } else if (a.rho) import_level0(src, a.rho + (size_t)k * N, g.psrc, N);
-    else if (a.src_nat) import_level0(src, a.src_nat + (size_t)k * N, nullptr, N);
+    } else if (a.rho) import_level0(src, a.rho + (size_t)k * NS, g.psrc, N);
+    else if (a.src_nat) import_level0(src, a.src_nat + (size_t)k * NS, nullptr, N);
     const bool warm = a.warm_vcycles > 0 && a.u_out != nullptr;
     const int n_cycles = warm ? a.warm_vcycles : a.max_vcycles;
     int fmg_top = 0;                     // top level the full-multigrid ramp has reached (0: only V-cycles are left)
@@ -1160,7 +1161,7 @@ __global__ void __launch_bounds__(kPT) poisson_full_kernel(GridDev g, PoissonLev
         // Warm start (beyond the reference): Phi_0 = the previous solve of this density (u_out, same boundary values); the
         // V-cycles contract the difference by more than 10x each, so a few of them reach the same FP64 fixed point as the
         // full cycle from zero.  (Team mode: Phi_0 is still in place in global memory.)
-        if (!team) import_level0(phi, a.u_out + (size_t)k * N, nullptr, N);
+        if (!team) import_level0(phi, a.u_out + (size_t)k * NS, nullptr, N);
         __syncthreads();
         team_barrier();
     } else {
@@ -1203,7 +1204,7 @@ __global__ void __launch_bounds__(kPT) poisson_full_kernel(GridDev g, PoissonLev
         fmg_top = L - 2;
     }
     const bool want_norm = (a.floor_stop || a.last_err) && a.u_out != nullptr;
-    double* scratch = want_norm ? a.u_out + (size_t)k * N : nullptr;      // overwritten by the export below
+    double* scratch = want_norm ? a.u_out + (size_t)k * NS : nullptr;      // overwritten by the export below
     double err = 0., prev = 1e300;
     int used = 0, stagnant = 0;
     // the ramp cycles whose top level is at or below the dense level are run level by level (the leader's levels)
@@ -1234,7 +1235,7 @@ __global__ void __launch_bounds__(kPT) poisson_full_kernel(GridDev g, PoissonLev
     // is the discrete solution to FP64 representation accuracy instead of ~1e-9, which removes the rounding-noise floor
     // of the SCF energies (the reference's |dE/E| wanders at 2e-11..1e-10 before it randomly dips below 1e-11).
     if (a.refine_vcycles > 0 && a.u0 && !team) {
-        double* u0 = a.u0 + (size_t)k * N;                            // slot order, like phi
+        double* u0 = a.u0 + (size_t)k * NS;                            // slot order, like phi
         const double cl = 1. + 0.5 * g.delta, cr = 1. - 0.5 * g.delta;
         const Lay y0 = g_sm.lc[0].lay;
         // r into scratch, U0 saved, then Source_0 <- r, Phi_0 <- 0 (all levels' Phi are re-zeroed by restriction)
@@ -1257,10 +1258,10 @@ __global__ void __launch_bounds__(kPT) poisson_full_kernel(GridDev g, PoissonLev
     if (team) {
         if (a.u_out && !leader) {
             const double* p0 = g_sm.gphi + g_sm.lc[0].op;
-            double* u = a.u_out + (size_t)k * N;
+            double* u = a.u_out + (size_t)k * NS;
             for (int i = ws0; i < N; i += wstride) u[i] = __ldcg(p0 + i);
         }
-    } else if (a.u_out) export_level0(a.u_out + (size_t)k * N, N);
+    } else if (a.u_out) export_level0(a.u_out + (size_t)k * NS, N);
     if (dbg && threadIdx.x == 0) dbg[97] += clock64() - t_start;
     if (threadIdx.x == 0) {
         if (a.work) atomicAdd(a.work, g_sm.updates);
@@ -1377,9 +1378,10 @@ void launch_poisson_full(const GridDev& g, const PoissonLevels& lv, const Poisso
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kPT) poisson_mid_kernel(double delta, PoissonLevels lv, int K, double* nat_phi, const double* nat_src,
                                                          long long nat_stride, double* mid_phi, double* mid_src, int mid_total,
-                                                         const double* Gg, int smem_doubles)
+                                                         const double* Gg, int smem_doubles, const int* skip, int skip_stride_bytes)
 {
     const int k = blockIdx.x;
+    if (skip && *reinterpret_cast<const int*>(reinterpret_cast<const char*>(skip) + (size_t)k * skip_stride_bytes)) return;
     // (the level offsets of `lv` count from level 0: shift the block so that level K lands at its start)
     hierarchy_setup(lv, delta, mid_phi + (size_t)k * mid_total - lv.off[K], mid_src + (size_t)k * mid_total - lv.off[K], smem_doubles, Gg,
                     nullptr, 2, 0, nullptr);
@@ -1401,13 +1403,14 @@ __global__ void __launch_bounds__(kPT) poisson_mid_kernel(double delta, PoissonL
 }
 
 void launch_poisson_mid(const PoissonLevels& lv, double delta, int K, int n_dens, double* nat_phi, const double* nat_src, long long nat_stride,
-                        double* mid_phi, double* mid_src, int mid_total, const double* coarse_op, cudaStream_t st)
+                        double* mid_phi, double* mid_src, int mid_total, const double* coarse_op, const int* skip, int skip_stride_bytes,
+                        cudaStream_t st)
 {
     const int sd = dyn_doubles_for(lv);
     const size_t bytes = (size_t)sd * sizeof(double);
     static size_t attr_bytes = 0;
     if (bytes > attr_bytes) { cudaFuncSetAttribute(poisson_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); attr_bytes = bytes; }
-    poisson_mid_kernel<<<n_dens, kPT, bytes, st>>>(delta, lv, K, nat_phi, nat_src, nat_stride, mid_phi, mid_src, mid_total, coarse_op, sd);
+    poisson_mid_kernel<<<n_dens, kPT, bytes, st>>>(delta, lv, K, nat_phi, nat_src, nat_stride, mid_phi, mid_src, mid_total, coarse_op, sd, skip, skip_stride_bytes);
 }
 
 // V-cycles as defined by the reference on given (Phi_0, Source_0) in natural node order: parity / microbench entry point

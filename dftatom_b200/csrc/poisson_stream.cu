@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(T, MINB) stream_visit_kernel(StreamVisitArgs v
     __shared__ double s_edge[NW], s_wtot[NW];
     const unsigned full = 0xffffffffu;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    if (v.skip && *reinterpret_cast<const int*>(reinterpret_cast<const char*>(v.skip) + (size_t)blockIdx.y * v.skip_stride_bytes)) return;
     const int n = v.n;
     const int a0 = blockIdx.x * v.slab;
     const int b0 = min(a0 + v.slab, n);
@@ -218,6 +219,27 @@ __global__ void __launch_bounds__(T, MINB) stream_visit_kernel(StreamVisitArgs v
     }
 }
 
+// Initialize (PoissonSolver.cpp:80-106) for the streamed levels: Source_{l+1} = 4 x injection of Source_l, zero at the ends
+__global__ void __launch_bounds__(256) stream_inject_kernel(const double* __restrict__ src_f, long long stride_f, double* __restrict__ src_c,
+                                                           long long stride_c, int nc, const int* skip, int skip_stride_bytes)
+{
+    const size_t k = blockIdx.y;
+    if (skip && *reinterpret_cast<const int*>(reinterpret_cast<const char*>(skip) + k * skip_stride_bytes)) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > nc) return;
+    src_c[k * (size_t)stride_c + i] = (i > 0 && i < nc) ? 4. * __ldg(src_f + k * (size_t)stride_f + 2 * (size_t)i) : 0.;
+}
+
+// Source_0 = r 4 pi K rho (PoissonSolver.h:55-74; psrc is zero at both ends)
+__global__ void __launch_bounds__(256) stream_source_kernel(const double* __restrict__ psrc, const double* __restrict__ rho, long long rho_stride,
+                                                           double* __restrict__ src0, long long ld0, int N, const int* skip, int skip_stride_bytes)
+{
+    const size_t k = blockIdx.y;
+    if (skip && *reinterpret_cast<const int*>(reinterpret_cast<const char*>(skip) + k * skip_stride_bytes)) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) src0[k * (size_t)ld0 + i] = __ldg(psrc + i) * __ldg(rho + k * (size_t)rho_stride + i);
+}
+
 template <int T, int NPT, int MINB>
 void launch_variant(const StreamVisitArgs& v_in, int n_dens, cudaStream_t st)
 {
@@ -289,11 +311,90 @@ void launch_poisson_stream_vcycles(const StreamPlan& sp, double delta, int n_den
             visit(l, (l == 0 ? kVisitLoadPhi : 0) | kVisitRestrictOut, 3);
         }
         launch_poisson_mid(sp.lv, delta, K, n_dens, cphi + sp.coff[K], csrc + sp.coff[K], sp.cstride, scratch + sp.off_mphi,
-                           scratch + sp.off_msrc, sp.mid_total, coarse_op, st);
+                           scratch + sp.off_msrc, sp.mid_total, coarse_op, nullptr, 0, st);
         ++nl;
         for (int l = K - 1; l > 0; --l) visit(l, kVisitLoadPhi | kVisitProlongIn, 3);
         if (fuse_tops && c + 1 < n_cycles) { visit(0, kVisitLoadPhi | kVisitProlongIn | kVisitRestrictOut, 6); top_done = true; }
         else { visit(0, kVisitLoadPhi | kVisitProlongIn, 3); top_done = false; }
+    }
+    if (launches) *launches = nl;
+}
+
+// The chain of cycles  to_coarse(top, c); to_fine(c, next top)  (PoissonSolver.h:89-124) over the streamed levels.  An "arrival"
+// is the visit that ends an ascent at its top level b: prolongation in, 3 sweeps - fused with the 3 sweeps and the restriction
+// that start the next descent unless it is the last visit of the solve.  fresh: Phi_b is still zero (first visit of the ramp).
+void launch_poisson_stream_solve(const StreamPlan& sp, double delta, const StreamSolveArgs& a, cudaStream_t st, long long* launches)
+{
+    const int K = sp.K, nd = a.n_dens;
+    double* cphi = a.scratch + sp.off_cphi;
+    double* csrc = a.scratch + sp.off_csrc;
+    double* mphi = a.scratch + sp.off_mphi;
+    double* msrc = a.scratch + sp.off_msrc;
+    long long nl = 0;
+    auto visit = [&](int l, int flags, int sweeps) {
+        StreamVisitArgs v{};
+        if (l == 0) { v.phi_f = a.U; v.src_f = a.src0; v.stride_f = a.ld0; }
+        else { v.phi_f = cphi + sp.coff[l]; v.src_f = csrc + sp.coff[l]; v.stride_f = sp.cstride; }
+        v.phi_c = cphi + sp.coff[l + 1]; v.src_c = csrc + sp.coff[l + 1]; v.stride_c = sp.cstride;
+        v.n = sp.lv.size[l] - 1;
+        v.flags = flags; v.sweeps = sweeps;
+        const double d = delta * (double)(1 << l);
+        v.a = 0.5 * (1. + 0.5 * d); v.bcoef = 0.5 * (1. - 0.5 * d); v.dc = 2. * d;
+        v.skip = a.skip; v.skip_stride_bytes = a.skip_stride_bytes;
+        launch_stream_visit(v, nd, a.variant, st);
+        ++nl;
+    };
+    auto descend_mid_ascend = [&](int from, int to) {      // down-visits from+1 .. K-1, the levels below, up-visits K-1 .. to+1
+        for (int l = from + 1; l < K; ++l) visit(l, kVisitRestrictOut, 3);
+        launch_poisson_mid(sp.lv, delta, K, nd, cphi + sp.coff[K], csrc + sp.coff[K], sp.cstride, mphi, msrc, sp.mid_total, a.coarse_op,
+                           a.skip, a.skip_stride_bytes, st);
+        ++nl;
+        for (int l = K - 1; l > to; --l) visit(l, kVisitLoadPhi | kVisitProlongIn, 3);
+    };
+    const int N = sp.lv.size[0];
+    if (a.rho) {
+        stream_source_kernel<<<dim3((N + 255) / 256, nd), 256, 0, st>>>(a.psrc, a.rho, a.rho_stride, a.src0, a.ld0, N, a.skip, a.skip_stride_bytes);
+        ++nl;
+    }
+    int remaining;        // arrivals still to come
+    if (a.warm) {
+        visit(0, kVisitLoadPhi | kVisitRestrictOut, 3);
+        remaining = a.n_v;
+        for (int q = 0; q < a.n_v; ++q) {
+            descend_mid_ascend(0, 0);
+            --remaining;
+            if (remaining) visit(0, kVisitLoadPhi | kVisitProlongIn | kVisitRestrictOut, 6); else visit(0, kVisitLoadPhi | kVisitProlongIn, 3);
+        }
+    } else {
+        // Initialize: Source_l of every level by injection; the levels <= 16384 nodes run their part of the ramp - every cycle whose
+        // top is below the streamed levels, and the descent + ascent back to level K of the cycle whose top is K - as one
+        // full-multigrid solve with one V-cycle on the 14-level grid of spacing delta 2^K (same operators, same order)
+        for (int l = 0; l < K; ++l) {
+            const int nc = sp.lv.size[l + 1] - 1;
+            const double* sf = l == 0 ? a.src0 : csrc + sp.coff[l];
+            stream_inject_kernel<<<dim3((nc + 256) / 256, nd), 256, 0, st>>>(sf, l == 0 ? a.ld0 : sp.cstride, csrc + sp.coff[l + 1], sp.cstride, nc,
+                                                                           a.skip, a.skip_stride_bytes);
+            ++nl;
+        }
+        GridDev gm{};
+        gm.N = sp.lv.size[K]; gm.L = sp.L - K; gm.delta = delta * (double)(1 << K);
+        const PoissonLevels lvm = make_levels(gm.L);
+        PoissonArgs pa{};
+        pa.n_dens = nd; pa.src_nat = csrc + sp.coff[K]; pa.u_out = cphi + sp.coff[K]; pa.nat_stride = sp.cstride; pa.Zbc = a.Zbc;
+        pa.phi = mphi; pa.src = msrc; pa.max_vcycles = 1; pa.coarse_op = a.coarse_op; pa.skip = a.skip; pa.skip_stride_bytes = a.skip_stride_bytes;
+        launch_poisson_full(gm, lvm, pa, st);
+        ++nl;
+        remaining = K + a.n_v;
+        int prev = K;
+        for (int q = 0; q < K + a.n_v; ++q) {
+            const int b = prev > 0 ? prev - 1 : 0;
+            const bool fresh = prev > 0;
+            if (q > 0) descend_mid_ascend(prev, b);
+            --remaining;
+            const int ld = fresh ? 0 : kVisitLoadPhi;
+            if (remaining) visit(b, ld | kVisitProlongIn | kVisitRestrictOut, 6); else visit(b, ld | kVisitProlongIn, 3);
+            prev = b;
+        }
     }
     if (launches) *launches = nl;
 }

@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(kPT2) potential_energy_kernel(GridDev g, Poiss
     const AtomDev at = b.atoms[a];
     const int N = g.N;
     const double Z = (double)at.Z;
-    const double* U = b.U + (size_t)a * g.N;               // U(r) = r V_H, written by the Poisson solve in natural node order
+    const double* U = b.U + (size_t)a * b.ldU;               // U(r) = r V_H, written by the Poisson solve in natural node order
     const double* rt = b.rhot + (size_t)a * N;
     const int ta = b.tab_of[2 * a], tb = b.tab_of[2 * a + 1];
     const double q = g.delta * g.delta * 0.25;

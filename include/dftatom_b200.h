@@ -102,6 +102,9 @@ const char* dftatom_version(void);
  *   "search_mode"  (default 0) 0 = fused single-predicate multisection (production); 1 = reference-shaped three-stage
  *                   search (node-count window edges, then the sign change of y(0)), kept for validation
  *   "profile"      (default 0) time every kernel class with CUDA events, see dftatom_last_profile
+ *   "stream_poisson" (default 1) grids above 16385 nodes with at least "stream_min_dens" (default 4) densities in the batch: the
+ *                   Poisson solve runs as level visits streamed over all densities (poisson_stream.cu: HBM-bound, slab windows
+ *                   with halos) instead of one CTA / team of CTAs per density; 0 = never
  *   "stream_variant" (default 0) window shape of the stream-mode Poisson visits: 0 = 256 threads x 16 nodes, 1 = 256 x 8, 2 = 512 x 8
  */
 int dftatom_set_option(dftatom_ctx* ctx, const char* key, double value);

@@ -108,14 +108,22 @@ def test_orbital_matches_oracle(ctx):
             np.testing.assert_allclose(u_g, u_o, rtol=0, atol=1e-10)
 
 
-@pytest.mark.parametrize("L,delta,rmax", [(10, 0.004, 15.0), (14, 0.0005, 25.0), (16, 0.0002, 50.0)])
-def test_poisson_matches_oracle_and_analytic(ctx, L, delta, rmax):
-    """U(r) of FMG + V-cycles vs the reference algorithm (oracle, 100 V-cycles) and vs the analytic Hartree potential."""
+@pytest.mark.parametrize("L,delta,rmax,stream", [(10, 0.004, 15.0, 0), (14, 0.0005, 25.0, 0), (16, 0.0002, 50.0, 0), (15, 0.0004, 50.0, 1),
+                                                 (16, 0.0002, 50.0, 1), (17, 0.0001, 50.0, 1)])
+def test_poisson_matches_oracle_and_analytic(ctx, L, delta, rmax, stream):
+    """U(r) of FMG + V-cycles vs the reference algorithm (oracle, 100 V-cycles) and vs the analytic Hartree potential.
+    stream: the solver for many densities on grids beyond the chip (poisson_stream.cu) instead of one CTA / team per density."""
     N, rp, r = O.grid(L, delta, rmax)
     Zs = [1, 18, 86]
     a = [0.8, 1.7, 3.1]
     rho = np.stack([Z * k ** 3 / np.pi * np.exp(-2 * k * r) for Z, k in zip(Zs, a)])
-    U, used = ctx.poisson_solve(L, delta, rmax, Zs, rho)
+    ctx.set_option("stream_poisson", stream)
+    ctx.set_option("stream_min_dens", 1)
+    try:
+        U, used = ctx.poisson_solve(L, delta, rmax, Zs, rho)
+    finally:
+        ctx.set_option("stream_poisson", 1)
+        ctx.set_option("stream_min_dens", 4)
     assert (used <= 20).all() and (used >= 3).all()
     for j, (Z, k) in enumerate(zip(Zs, a)):
         U_o, errs = O.poisson(L, delta, rmax, Z, rho[j], max_vcycles=100 if L <= 14 else 12)

@@ -128,6 +128,26 @@ def test_kernel_shapes_agree(ctx):
                 np.testing.assert_allclose([x for ch in r.steps[k].E for x in ch], [x for ch in b.steps[k].E for x in ch], rtol=0, atol=2e-7)
 
 
+def test_stream_poisson_agrees(ctx):
+    """Grids above 16385 nodes: the stream-mode Poisson solver (level visits over all densities, poisson_stream.cu) and the
+    one-CTA / team-per-density solver are the same FullCycle: same SCF trajectories far below the parity bars."""
+    opts = [D.Options(Z, 15, 25.0, 0.00025, 0.5, m) for Z, m in [(4, 0), (18, 0), (26, 1)]]
+    ctx.set_option("stream_min_dens", 1)
+    try:
+        base = ctx.solve_batch(opts)
+        ctx.set_option("stream_poisson", 0)
+        res = ctx.solve_batch(opts)
+    finally:
+        ctx.set_option("stream_poisson", 1)
+        ctx.set_option("stream_min_dens", 4)
+    for r, b in zip(res, base):
+        n = min(r.n_steps, b.n_steps)
+        assert n >= 10
+        for k in range(n):
+            assert abs(r.steps[k].Etotal - b.steps[k].Etotal) < 2e-6, k
+            np.testing.assert_allclose([x for ch in r.steps[k].E for x in ch], [x for ch in b.steps[k].E for x in ch], rtol=0, atol=2e-7)
+
+
 def test_options_validation(ctx):
     """Same ranges as the reference's dialog validators (OptionsFrame.cpp:46,152-173); mixed grids are refused."""
     for bad in (D.Options(0, 10, 15.0, 0.004, 0.5, 0), D.Options(119, 10, 15.0, 0.004, 0.5, 0), D.Options(2, 10, 0.5, 0.004, 0.5, 0),
