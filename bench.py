@@ -408,10 +408,14 @@ def micro_c5b(ctx, fp64_peak_tflops, reps=20, cpu_baseline=True):
         Es.append(np.linspace(1.5 * En, 0.5 * En, 256)); ls.append(np.full(256, l, np.int32))
     Es = np.concatenate(Es); ls = np.concatenate(ls); lim = np.zeros(len(Es), np.int32)
     # two shapes of the same sweep: serial in r (one warp = 32 energies walks the whole grid) and parallel in r (one cluster
-    # of 8 CTAs per 32 energies, warp = one of 32 radial segments: 2.25x the arithmetic, 2/32 of the depth)
+    # of 4 CTAs per 32 energies, warp = one of 16 radial segments; the Sturm count comes from the segments' transfer matrices alone)
     kernels = {}
     for name, impl in (("serial_in_r", 0), ("parallel_in_r", 2)):
-        sign, lg, cnt, ms, steps = ctx.numerov_lanes_timed(V, levels, delta, rmax, ls, Es, lim, impl=impl, reps=reps)
+        ctx.set_option("r_segments", 16 if impl == 2 else 32)          # 16 segments (clusters of 4 CTAs) measured best for these lanes
+        try:
+            sign, lg, cnt, ms, steps = ctx.numerov_lanes_timed(V, levels, delta, rmax, ls, Es, lim, impl=impl, reps=reps)
+        finally:
+            ctx.set_option("r_segments", 32)
         # known answer: the Sturm count of a lane = number of Coulomb levels n' > l with -Z^2/2n'^2 below its energy (+1
         # throughout for l = 3); it steps from n-l-1 to n-l where E crosses E_n
         ok = True
@@ -430,7 +434,7 @@ def micro_c5b(ctx, fp64_peak_tflops, reps=20, cpu_baseline=True):
                              bound="fp64", achieved=tf, peak=fp64_peak_tflops, unit="TFLOP/s",
                              frac=tf / fp64_peak_tflops if fp64_peak_tflops else None, traffic=None, flop_per_lane_node_step=11.0,
                              note="credited 11 FLOP per (lane, node-step) whatever the kernel executes (SURVEY 8d); 4096 lanes are 128 warps "
-                                  "for 148 SMs x 4 FP64 pipes, so the serial sweep cannot fill the machine and the parallel-in-r one pays 2.25x"))
+                                  "for 148 SMs x 4 FP64 pipes, so the serial sweep cannot fill the machine; the parallel-in-r one executes 11 FP64 instructions per (lane, node) for the two basis chains"))
     if cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_lib as O

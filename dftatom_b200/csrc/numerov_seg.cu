@@ -62,6 +62,7 @@ __device__ __forceinline__ SegRoundOut seg_round(const GridDev& g, const double*
     const bool is_bottom = valid && bot == 1;
 
     // ---------------- pass 1: transfer matrix (two basis chains) or the seeded real solution ----------------
+    FastOut<2> o;
     {
         SweepIn<2> in;
         in.E[0] = E; in.E[1] = E;
@@ -69,7 +70,6 @@ __device__ __forceinline__ SegRoundOut seg_round(const GridDev& g, const double*
         in.running[1] = kind == 1; in.W_in[1] = 0.; in.D_in[1] = 1.;
         in.start[0] = kind == 2 ? start : -1;
         in.start[1] = -1;
-        FastOut<2> o;
         o.bad = 0;
         if (valid && __any_sync(full, kind != 0)) range_sweep<2>(g, atab, ll1, in, top, bot, sbuf + wl * 64, o);
         sh.meta[wl][lane] = kind | ((int)o.prev[0] << 2) | (o.count[0] << 3);      // normal segments: count and sign follow in pass 2
@@ -121,17 +121,36 @@ __device__ __forceinline__ SegRoundOut seg_round(const GridDev& g, const double*
             else if (kv == 1) { const double na = fma(m0, A, m1 * Bd), nb = fma(m2, A, m3 * Bd); A = na; Bd = nb; }
         }
     }
-    // ---------------- pass 2: the real solution through the normal segments, counting sign changes ----------------
-    if (__any_sync(full, kind == 1)) {
+    // ---------------- sign changes of the real solution inside the normal segments ----------------
+    // The real solution is W_i = A u_i + B v_i with (u, v) the two basis chains of pass 1.  X_i = (u_i, v_i) turns counter-
+    // clockwise as i decreases (its Wronskian keeps its sign: d_i d_{i+1} > 0) by less than pi per node, so W changes sign
+    // between two nodes exactly when X crosses the line L perpendicular to (A, B), and u when X crosses the axis u = 0.  Lines
+    // through the origin are crossed alternately: #L = #(sign changes of u, counted by pass 1) + [end past L] - [start past L],
+    // "past L" = on the far side of L within the half turn that starts at the axis:  [sigma_X sigma_L W(X) <= 0],
+    // sigma_X = -sign(u), sigma_L = sign(B).  No second sweep: the Sturm count of a segment costs its transfer matrix only.
+    // (Exception: the bottom segment of an l = 3 level, where 1 - f_1/12 < 0 flips y_1, SURVEY fact 6: re-run as before.)
+    const bool flip_node1 = kind == 1 && is_bottom && !(o.d_first[0] > 0.);
+    if (__any_sync(full, flip_node1)) {
         SweepIn<1> in;
         in.E[0] = E; in.running[0] = kind == 1; in.W_in[0] = A; in.D_in[0] = Bd; in.start[0] = -1;
-        FastOut<1> o;
-        range_sweep<1>(g, atab, ll1, in, top, bot, sbuf + wl * 64, o);
+        FastOut<1> o2;
+        range_sweep<1>(g, atab, ll1, in, top, bot, sbuf + wl * 64, o2);
         if (kind == 1) {
-            sh.meta[wl][lane] = 1 | ((int)o.prev[0] << 2) | (o.count[0] << 3);
-            if (is_bottom) { sh0->y0s[lane] = o.Y0s[0]; sh0->d1[lane] = o.d_first[0]; }
-            if (o.bad) atomicOr(&sh0->bad[lane], 1);
+            sh.meta[wl][lane] = 1 | ((int)o2.prev[0] << 2) | (o2.count[0] << 3);
+            if (is_bottom) { sh0->y0s[lane] = o2.Y0s[0]; sh0->d1[lane] = o2.d_first[0]; }
+            if (o2.bad) atomicOr(&sh0->bad[lane], 1);
         }
+    } else if (kind == 1) {
+        const double ue = o.W[0], ve = o.W[1];
+        const double We = fma(A, ue, Bd * ve);                       // the real W at the lowest node of the segment
+        const double sl = Bd < 0. ? -1. : (Bd > 0. ? 1. : (A >= 0. ? 1. : -1.));
+        const int past0 = (sl * A >= 0.) ? 1 : 0;                    // X_start = (1, 0): sigma_X = -1, W = A
+        const int past1 = ((ue >= 0. ? 1. : -1.) * sl * We >= 0.) ? 1 : 0;
+        const int cnt = o.count[0] + past1 - past0;
+        const unsigned sgn = (unsigned)hi32(We) >> 31;
+        sh.meta[wl][lane] = 1 | ((int)sgn << 2) | (cnt << 3);
+        if (is_bottom) { sh0->y0s[lane] = fma(A, o.Y0s[0], Bd * o.Y0s[1]); sh0->d1[lane] = o.d_first[0]; }
+        if (o.bad) atomicOr(&sh0->bad[lane], 1);
     }
     cluster.sync();
 
