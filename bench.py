@@ -411,11 +411,11 @@ def micro_c5b(ctx, fp64_peak_tflops, reps=20, cpu_baseline=True):
     # of 4 CTAs per 32 energies, warp = one of 16 radial segments; the Sturm count comes from the segments' transfer matrices alone)
     kernels = {}
     for name, impl in (("serial_in_r", 0), ("parallel_in_r", 2)):
-        ctx.set_option("r_segments", 16 if impl == 2 else 32)          # 16 segments (clusters of 4 CTAs) measured best for these lanes
+        ctx.set_option("r_segments", 16 if impl == 2 else -1)          # 16 segments (clusters of 4 CTAs) measured best for these lanes
         try:
             sign, lg, cnt, ms, steps = ctx.numerov_lanes_timed(V, levels, delta, rmax, ls, Es, lim, impl=impl, reps=reps)
         finally:
-            ctx.set_option("r_segments", 32)
+            ctx.set_option("r_segments", -1)
         # known answer: the Sturm count of a lane = number of Coulomb levels n' > l with -Z^2/2n'^2 below its energy (+1
         # throughout for l = 3); it steps from n-l-1 to n-l where E crosses E_n
         ok = True

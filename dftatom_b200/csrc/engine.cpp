@@ -53,8 +53,10 @@ struct dftatom_ctx {
     int warm_vcycles = 7;      // Poisson warm start from SCF step warm_after on: V-cycles per solve (0 = always the full cycle)
     int warm_after = 4;
     int team_poisson = 1;      // large grids, few atoms: several CTAs per density (poisson.cu, team mode)
-    int r_segments = 32;       // radial segments per orbital of the parallel-in-r search (<= 1: serial-in-r search only)
-    int seg_threshold = 300;   // the parallel-in-r search takes over once at most this many orbitals are still active
+    int r_segments = -1;       // radial segments per orbital of the parallel-in-r search; -1 = auto (16 up to 16385 nodes, 32 above), 0 / 1 = serial-in-r search only
+    int seg_threshold = 1 << 30;   // the parallel-in-r search runs once at most this many orbitals are still active (default: always; the
+                               // serial-in-r kernel, one warp per orbital, runs above it)
+    int segments(int N) const { return r_segments < 0 ? (N <= 16385 ? 16 : 32) : r_segments; }
     int profile = 0;
     int search_mode = 0;
     int match_mode = 0;
@@ -414,11 +416,15 @@ int dftatom_solve_batch(dftatom_ctx* c, const dftatom_options* opts, int n_atoms
             // two shapes of the same search: serial-in-r (one warp per orbital) while many orbitals are active, parallel-in-r
             // (one cluster per orbital) once few are left.  Both are enqueued; the device-side count of active orbitals
             // decides which one runs (the other returns at once), so the host never has to know.
-            const int thr = c->r_segments > 1 ? c->seg_threshold : -1;
-            launch_search_fused(g, b.atab, b.atoms, b.orbs, b.astate, b.ss, n_orbs, d_work + DFTATOM_K_SEARCH, b.n_active + 1, thr, c->warm_start, st);
-            ++launches;
-            if (c->r_segments > 1) {
-                launch_search_seg(g, b.atab, b.atoms, b.orbs, b.astate, b.ss, n_orbs, d_work + DFTATOM_K_SEARCH, c->r_segments, b.n_active + 1, thr, c->warm_start, st);
+            const int segs = c->segments(N);
+            const int thr = segs > 1 ? c->seg_threshold : -1;
+            const bool serial_too = !(segs > 1 && c->seg_threshold >= n_orbs);      // the serial-in-r kernel can never be selected: do not launch it
+            if (serial_too) {
+                launch_search_fused(g, b.atab, b.atoms, b.orbs, b.astate, b.ss, n_orbs, d_work + DFTATOM_K_SEARCH, b.n_active + 1, thr, c->warm_start, st);
+                ++launches;
+            }
+            if (segs > 1) {
+                launch_search_seg(g, b.atab, b.atoms, b.orbs, b.astate, b.ss, n_orbs, d_work + DFTATOM_K_SEARCH, segs, b.n_active + 1, thr, c->warm_start, st);
                 ++launches;
             }
         } else {
@@ -472,7 +478,7 @@ int dftatom_solve_batch(dftatom_ctx* c, const dftatom_options* opts, int n_atoms
             float t = 0.f;
             cudaEventElapsedTime(&t, s.a, s.b);
             c->prof[s.cls].ms += t;
-            c->prof[s.cls].launches += (s.cls == DFTATOM_K_SEARCH) ? (c->search_mode == 0 ? (c->r_segments > 1 ? 2 : 1) : rounds + 1) : 1;
+            c->prof[s.cls].launches += (s.cls == DFTATOM_K_SEARCH) ? (c->search_mode == 0 ? ((c->segments(N) > 1 && c->seg_threshold < n_orbs) ? 2 : 1) : rounds + 1) : 1;
             cudaEventDestroy(s.a); cudaEventDestroy(s.b);
         }
     }
@@ -543,12 +549,12 @@ static int numerov_lanes_impl(dftatom_ctx* c, const double* V, int levels, doubl
     DFT_CHECK(cudaMemcpyAsync(d_lim, nodes_limit, sizeof(int) * n_lanes, cudaMemcpyHostToDevice, st));
     DFT_CHECK(cudaMemcpyAsync(d_E, E, sizeof(double) * n_lanes, cudaMemcpyHostToDevice, st));
     NumerovLaneArgs a{ dA.as<double>(), n_lanes, d_tab, d_l, d_E, d_lim, d_sign, d_log, d_cnt };
-    if (impl == 0) launch_numerov_lanes_fast(g, a, st); else if (impl == 2) launch_numerov_lanes_seg(g, a, c->r_segments > 1 ? c->r_segments : 32, st); else launch_numerov_lanes(g, a, st);
+    if (impl == 0) launch_numerov_lanes_fast(g, a, st); else if (impl == 2) launch_numerov_lanes_seg(g, a, c->segments(N) > 1 ? c->segments(N) : 32, st); else launch_numerov_lanes(g, a, st);
     if (reps > 0) {          // microbench: the same launch `reps` more times between CUDA events (tables and lanes resident)
         cudaEvent_t e0, e1;
         DFT_CHECK(cudaEventCreate(&e0)); DFT_CHECK(cudaEventCreate(&e1));
         DFT_CHECK(cudaEventRecord(e0, st));
-        for (int r = 0; r < reps; ++r) { if (impl == 0) launch_numerov_lanes_fast(g, a, st); else if (impl == 2) launch_numerov_lanes_seg(g, a, c->r_segments > 1 ? c->r_segments : 32, st); else launch_numerov_lanes(g, a, st); }
+        for (int r = 0; r < reps; ++r) { if (impl == 0) launch_numerov_lanes_fast(g, a, st); else if (impl == 2) launch_numerov_lanes_seg(g, a, c->segments(N) > 1 ? c->segments(N) : 32, st); else launch_numerov_lanes(g, a, st); }
         DFT_CHECK(cudaEventRecord(e1, st));
         DFT_CHECK(cudaStreamSynchronize(st));
         float ms = 0.f;
@@ -631,7 +637,7 @@ int dftatom_level_search(dftatom_ctx* c, const double* V, int levels, double del
     if ((rc = setup_single(c, g, V, Z, orbs, &da, &ds, &dorb, &dss, &datab))) return rc;
     launch_search_init(g, da, ds, dorb, dss, n_levels, st);
     const int rounds = search_rounds_needed(Z);
-    if (c->search_mode == 0 && c->r_segments > 1) launch_search_seg(g, datab, da, dorb, ds, dss, n_levels, nullptr, c->r_segments, nullptr, 0, 0, st);
+    if (c->search_mode == 0 && c->segments(g.N) > 1) launch_search_seg(g, datab, da, dorb, ds, dss, n_levels, nullptr, c->segments(g.N), nullptr, 0, 0, st);
     else if (c->search_mode == 0) launch_search_fused(g, datab, da, dorb, ds, dss, n_levels, nullptr, nullptr, 0, 0, st);
     else for (int r = 0; r < rounds; ++r) launch_search_round(g, datab, dorb, ds, dss, n_levels, nullptr, st);
     std::vector<SearchState> h(n_levels);

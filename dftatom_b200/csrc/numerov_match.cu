@@ -219,6 +219,7 @@ struct MatchShared {
     int cand[kMT / 32]; double ycand[kMT / 32];
     double red[kMT / 32];
     double y2, ylast, bcast;
+    double xW, xD, xP;        // windowed kernel: state leaving a window
     int match;
 };
 
@@ -469,6 +470,220 @@ __global__ void __launch_bounds__(kMT) match_cta_kernel(GridDev g, const double*
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// The same algorithm for grids whose g = f/12 does not fit in shared memory (65537, 131073 nodes ...): the orbital is
+// processed in windows of kWinNodes nodes, each staged in shared memory by coalesced loads, solved exactly like the
+// single-window kernel above (256 segments, transfer matrices, log-depth scan) with the state leaving one window as the
+// entry state of the next, and copied out coalesced.  Inward windows run from the far seeds down to the match point,
+// outward windows from the nucleus up to it.  (Per-thread chunk walks through global memory - the old large-grid path -
+// touch 32 cache lines per warp instruction: measured 1.15 ms per Rn orbital against ~0.2 ms here.)
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kWinNodes = 24576;
+
+__global__ void __launch_bounds__(kMT) match_win_kernel(GridDev g, const double* __restrict__ atab_all, const OrbitalDev* orbs,
+                                                        const AtomState* astate, SearchState* ss, double* psi_all, int* match_pt,
+                                                        double* inv_norm, int n_orbs)
+{
+    __shared__ MatchShared sh;
+    extern __shared__ double gy[];                       // g_i of the window, later y_i; node i at pslot(i - base)
+    const unsigned full = 0xffffffffu;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int k = blockIdx.x;
+    if (k >= n_orbs) return;
+    const OrbitalDev ob = orbs[k];
+    if (astate[ob.atom].done) return;
+    SearchState s = ss[k];
+    if (s.stage != 3) {                 // search budget exhausted: didNotConverge (DFTAtom.cpp:516,538)
+        s.converged = 0;
+        s.E = (s.stage == 0) ? s.dn_hi : s.bot;
+        s.stage = 3;
+        if (t == 0) ss[k] = s;
+    }
+    const double E = s.E;
+    const double* __restrict__ atab = atab_all + (size_t)ob.tab * g.N;
+    double* __restrict__ psi = psi_all + (size_t)k * g.N;
+    const double ll1 = (double)(ob.l * (ob.l + 1));
+    const double kappa = sqrt(2. * fabs(E));
+    const int start = start_index(g, kappa);
+    const int N = g.N;
+    auto gtab = [&](int i) { return fma(-E, __ldg(g.c6 + i), fma(ll1, __ldg(g.b12 + i), __ldg(atab + i))); };   // f_i / 12
+
+    // far seeds (Numerov.h:427-447)
+    const double y_s0 = far_value(g, kappa, start), y_s1 = far_value(g, kappa, start - 1);
+    const double d_s0 = 1. - gtab(start), d_s1 = 1. - gtab(start - 1);
+    if (t == 0) { sh.y2 = 0.; sh.ylast = 0.; }
+
+    // ---------------- inward windows: nodes start-2 ... down to the match point ----------------
+    int match = 2;
+    double y_in_match = 0.;
+    bool found = false;
+    double eW = d_s1 * y_s1 * d_s0, eD = d_s1 * y_s1 * d_s0 - d_s0 * y_s0, eP = d_s0;      // (W_{hi+1}, W_{hi+1} - W_{hi+2}, P_{hi+1})
+    for (int hi = start - 2; hi >= 1 && !found; hi -= kWinNodes) {
+        const int lo = max(hi - kWinNodes + 1, 1);
+        const int base = lo;
+        const int sth = min(hi + 2, start);
+        __syncthreads();
+        for (int i = lo + t; i <= sth; i += kMT) gy[pslot(i - base)] = gtab(i);
+        __syncthreads();
+        auto gval = [&](int i) { return gy[pslot(i - base)]; };
+        const int n_in = hi - lo + 1;
+        const int len = (((n_in + kMT - 1) / kMT) + 31) & ~31;
+        const int top = hi - t * len;
+        const int bot = max(top - len + 1, lo);
+        const bool have = top >= lo;
+        MatP M = { 1., 0., 0., 1., 1. };
+        double g1e = 0., g2e = 0.;
+        if (have) { g1e = gval(top + 1); g2e = (top + 2 <= start) ? gval(top + 2) : 0.; }
+        if (have) {
+            double g1 = g1e, g2 = g2e;
+            double aW1 = 1., aW2 = 1., aD = 0., bW1 = 0., bW2 = -1., bD = 1., prod = 1.;
+            for (int i = top; i >= bot; --i) {
+                const double s1 = fma(-g1, g2, g1 + g2), t1 = 10. * g1;
+                const double aDn = fma(t1, aW1, fma(s1, aW2, aD)), bDn = fma(t1, bW1, fma(s1, bW2, bD));
+                aW2 = aW1; aW1 += aDn; aD = aDn;
+                bW2 = bW1; bW1 += bDn; bD = bDn;
+                prod *= (1. - g1);
+                g2 = g1; g1 = gval(i);
+            }
+            M.ww = aW1; M.wd = bW1; M.dw = aD; M.dd = bD; M.p = prod;
+        }
+        double A, B, Pin;
+        segment_entries(M, eW, eD, eP, sh, A, B, Pin);
+        // first node (descending) with y_i < y_{i+1} or |y_i| > 1e15 (Numerov.h:449-468)
+        int cand = 0;
+        double ycand = 0.;
+        if (have) {
+            double g1 = g1e, g2 = g2e;
+            double W1 = A, W2 = A - B, D = B, P = Pin;
+            double ynext = W1 / (P * (1. - g1));
+            for (int i = top; i >= bot; --i) {
+                const double s1 = fma(-g1, g2, g1 + g2), t1 = 10. * g1;
+                const double Dn = fma(t1, W1, fma(s1, W2, D));
+                const double W = W1 + Dn;
+                P *= (1. - g1);
+                const double gi = gval(i);
+                const double y = W / (P * (1. - gi));
+                if (!cand && (y < ynext || fabs(y) > 1e15)) { cand = i; ycand = y; }
+                if (i == 2) sh.y2 = y;
+                ynext = y;
+                W2 = W1; W1 = W; D = Dn; g2 = g1; g1 = gi;
+                if (cand) break;
+            }
+        }
+        const unsigned mc = __ballot_sync(full, cand != 0);
+        const int srcl = mc ? __ffs(mc) - 1 : 0;
+        const int wc = __shfl_sync(full, cand, srcl);
+        const double wy = __shfl_sync(full, ycand, srcl);
+        if (lane == 0) { sh.cand[w] = mc ? wc : 0; sh.ycand[w] = wy; }
+        __syncthreads();
+        for (int v = 0; v < kMT / 32; ++v)
+            if (!found && sh.cand[v]) { match = sh.cand[v]; y_in_match = sh.ycand[v]; found = true; }
+        __syncthreads();
+        // the inward solution above the match point, stored in place of g, and the state leaving the window
+        const int stop = found ? match : 0;
+        if (have && top > stop) {
+            double g1 = g1e, g2 = g2e;
+            double W1 = A, W2 = A - B, D = B, P = Pin;
+            for (int i = top; i >= bot && i > stop; --i) {
+                const double s1 = fma(-g1, g2, g1 + g2), t1 = 10. * g1;
+                const double Dn = fma(t1, W1, fma(s1, W2, D));
+                const double W = W1 + Dn;
+                P *= (1. - g1);
+                const double gi = gval(i);
+                gy[pslot(i - base)] = W / (P * (1. - gi));
+                W2 = W1; W1 = W; D = Dn; g2 = g1; g1 = gi;
+            }
+            if (bot == lo && !found) { sh.xW = W1; sh.xD = D; sh.xP = P; }
+        }
+        __syncthreads();
+        for (int i = max(lo, stop + 1) + t; i <= hi; i += kMT) psi[i] = gy[pslot(i - base)];
+        if (!found) { eW = sh.xW; eD = sh.xD; eP = sh.xP; }
+    }
+    if (!found) y_in_match = (start - 2 >= 2) ? sh.y2 : ((start - 1 == 2) ? y_s1 : y_s0);      // matchPoint stays 2 (Numerov.h:449)
+
+    // ---------------- outward windows: nodes 2 ... match ----------------
+    const double y1 = pow(__ldg(g.r + 1), (double)ob.l + 1.) * exp(-0.5 * g.delta);
+    double oW = (1. - gtab(1)) * y1, oD = oW, oQ = 1.;          // (W_{lo-1}, W_{lo-1} - W_{lo-2}, Q_{lo-1}); W_0 = 0
+    for (int lo = 2; lo <= match; lo += kWinNodes) {
+        const int hi = min(lo + kWinNodes - 1, match);
+        const int base = lo - 2;
+        __syncthreads();
+        for (int i = max(lo - 2, 1) + t; i <= hi; i += kMT) gy[pslot(i - base)] = gtab(i);
+        __syncthreads();
+        auto gval = [&](int i) { return gy[pslot(i - base)]; };
+        const int n_out = hi - lo + 1;
+        const int len = (((n_out + kMT - 1) / kMT) + 31) & ~31;
+        const int bot = lo + t * len;
+        const int top = min(bot + len - 1, hi);
+        const bool have = bot <= hi;
+        MatP M = { 1., 0., 0., 1., 1. };
+        double g1e = 0., g2e = 0.;                             // g_{bot-1}, g_{bot-2}; d_0 := 1
+        if (have) { g1e = gval(bot - 1); g2e = (bot - 2 >= 1) ? gval(bot - 2) : 0.; }
+        if (have) {
+            double g1 = g1e, g2 = g2e;
+            double aW1 = 1., aW2 = 1., aD = 0., bW1 = 0., bW2 = -1., bD = 1., prod = 1.;
+            for (int i = bot; i <= top; ++i) {
+                const double s1 = fma(-g1, g2, g1 + g2), t1 = 10. * g1;
+                const double aDn = fma(t1, aW1, fma(s1, aW2, aD)), bDn = fma(t1, bW1, fma(s1, bW2, bD));
+                aW2 = aW1; aW1 += aDn; aD = aDn;
+                bW2 = bW1; bW1 += bDn; bD = bDn;
+                prod *= (1. - g1);
+                g2 = g1; g1 = gval(i);
+            }
+            M.ww = aW1; M.wd = bW1; M.dw = aD; M.dd = bD; M.p = prod;
+        }
+        double A, B, Qin;
+        segment_entries(M, oW, oD, oQ, sh, A, B, Qin);
+        if (have) {
+            double g1 = g1e, g2 = g2e;
+            double W1 = A, W2 = A - B, D = B, Q = Qin;
+            double ylast = 0.;
+            for (int i = bot; i <= top; ++i) {
+                const double s1 = fma(-g1, g2, g1 + g2), t1 = 10. * g1;
+                const double Dn = fma(t1, W1, fma(s1, W2, D));
+                const double W = W1 + Dn;
+                Q *= (1. - g1);
+                const double gi = gval(i);
+                const double y = W / (Q * (1. - gi));
+                gy[pslot(i - base)] = y;
+                ylast = y;
+                W2 = W1; W1 = W; D = Dn; g2 = g1; g1 = gi;
+            }
+            if (top == hi) { sh.xW = W1; sh.xD = D; sh.xP = Q; sh.ylast = ylast; }
+        }
+        __syncthreads();
+        for (int i = lo + t; i <= hi; i += kMT) psi[i] = gy[pslot(i - base)];
+        oW = sh.xW; oD = sh.xD; oQ = sh.xP;
+    }
+    __syncthreads();
+    const double y_out_match = sh.ylast;
+    if (t == 0) { psi[start] = y_s0; psi[start - 1] = y_s1; psi[0] = 0.; psi[1] = y1; }
+    __syncthreads();
+    // scale the outer part so that both pieces meet at the match point (Numerov.h:497-501), zero the tail, norm integral
+    const double factor = y_out_match / y_in_match;
+    double acc = 0.;
+    for (int i = t; i < N; i += kMT) {
+        double y = 0.;
+        if (i <= start) {
+            y = psi[i];
+            if (i > match) y *= factor;
+            const double u = y * __ldg(g.sqex + i);
+            acc = fma(__ldg(g.wjac + i), u * u, acc);
+        }
+        if (i > match) psi[i] = y;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(full, acc, o);
+    if (lane == 0) sh.red[w] = acc;
+    __syncthreads();
+    if (t == 0) {
+        double tot = 0.;
+        for (int v = 0; v < kMT / 32; ++v) tot += sh.red[v];
+        inv_norm[k] = 1. / tot;
+        match_pt[k] = match;
+    }
+}
+
 void launch_match_cta(const GridDev& g, const double* atab, const OrbitalDev* orbs, const AtomState* astate, const SearchState* ss,
                       double* psi, int* match_pt, double* inv_norm, int n_orbs, cudaStream_t st)
 {
@@ -478,7 +693,10 @@ void launch_match_cta(const GridDev& g, const double* atab, const OrbitalDev* or
         if (bytes > attr_bytes) { cudaFuncSetAttribute(match_cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); attr_bytes = bytes; }
         match_cta_kernel<true><<<n_orbs, kMT, bytes, st>>>(g, atab, orbs, astate, const_cast<SearchState*>(ss), psi, match_pt, inv_norm, n_orbs);
     } else {
-        match_cta_kernel<false><<<n_orbs, kMT, 0, st>>>(g, atab, orbs, astate, const_cast<SearchState*>(ss), psi, match_pt, inv_norm, n_orbs);
+        const size_t wb = ((size_t)kWinNodes + 2 + (size_t)(kWinNodes + 2) / 32 + 8) * sizeof(double);
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(match_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wb); attr = true; }
+        match_win_kernel<<<n_orbs, kMT, wb, st>>>(g, atab, orbs, astate, const_cast<SearchState*>(ss), psi, match_pt, inv_norm, n_orbs);
     }
 }
 

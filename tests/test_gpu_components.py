@@ -47,7 +47,7 @@ def test_numerov_lanes_match_oracle(ctx, kind, L, delta, rmax, Z):
             np.testing.assert_allclose(lg, np.log2(np.abs(y0)), atol=1e-6)
             assert np.array_equal(cnt, O.numerov_count_all(V, delta, rmax, ls, Es))
     finally:
-        ctx.set_option("r_segments", 32)
+        ctx.set_option("r_segments", -1)
 
 
 def test_numerov_known_answer_hydrogenic(ctx):
@@ -84,15 +84,17 @@ def test_level_search_matches_oracle(ctx, kind, L, delta, rmax, Z):
         ctx.set_option("r_segments", segs)
         E_g, ok_g = ctx.level_search(V, L, delta, rmax, Z, ns, ls)
         ctx.set_option("search_mode", 0)
-        ctx.set_option("r_segments", 32)
+        ctx.set_option("r_segments", -1)
         np.testing.assert_allclose(E_g, E_o, rtol=0, atol=5e-9)
         assert ok_g.tolist() == ok_o.tolist()
     if kind == "coulomb":
         np.testing.assert_allclose(E_g, [-Z * Z / (2.0 * n * n) for n in ns], atol=5e-5)
 
 
-def test_orbital_matches_oracle(ctx):
-    L, delta, rmax, Z = 12, 0.001, 15.0, 18
+@pytest.mark.parametrize("L,delta,rmax,Z", [(12, 0.001, 15.0, 18), (16, 0.0002, 50.0, 30), (17, 0.0001, 50.0, 86)])
+def test_orbital_matches_oracle(ctx, L, delta, rmax, Z):
+    """Two-sided matched + normalised solution (Numerov.h:403-504, DFTAtom.cpp:36-56).  16, 17 levels: the grid does not fit
+    in shared memory and the production kernel works through it window by window (match_win_kernel)."""
     N, rp, r = O.grid(L, delta, rmax)
     V = _potential("coulomb", Z, r)
     for n, l in [(1, 0), (2, 1), (3, 0), (3, 2), (4, 3)]:
@@ -105,7 +107,8 @@ def test_orbital_matches_oracle(ctx):
             u_g, mp_g = ctx.numerov_orbital(V, L, delta, rmax, l, E)
             ctx.set_option("match_mode", 0)
             assert abs(mp_g - mp_o) <= (0 if mode == 1 else 1)      # the match point is an argmax: rounding may move it by one node
-            np.testing.assert_allclose(u_g, u_o, rtol=0, atol=1e-10)
+            # rounding accumulates with the number of nodes: 2e-10 observed at 131073 nodes (relative 1e-10)
+            np.testing.assert_allclose(u_g, u_o, rtol=0, atol=1e-10 if L <= 14 else 1e-9)
 
 
 @pytest.mark.parametrize("L,delta,rmax,stream", [(10, 0.004, 15.0, 0), (14, 0.0005, 25.0, 0), (16, 0.0002, 50.0, 0), (15, 0.0004, 50.0, 1),

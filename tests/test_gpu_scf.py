@@ -109,9 +109,9 @@ def test_kernel_shapes_agree(ctx):
     full cycle vs warm start, CTA-wide vs warp-wide matched solution.  Same trajectories to far below the parity bars."""
     opts = [D.Options(Z, 12, 20.0, 0.001, 0.5, m) for Z, m in [(4, 0), (18, 0), (26, 1), (47, 0)]]
     base = ctx.solve_batch(opts)
-    variants = [{"r_segments": 0}, {"seg_threshold": 1 << 20}, {"seg_threshold": 1 << 20, "r_segments": 8}, {"warm_vcycles": 0},
+    variants = [{"r_segments": 0}, {"seg_threshold": 30}, {"r_segments": 32}, {"r_segments": 8}, {"warm_vcycles": 0},
                 {"match_mode": 2}]
-    defaults = {"r_segments": 32, "seg_threshold": 300, "warm_vcycles": 7, "match_mode": 0}
+    defaults = {"r_segments": -1, "seg_threshold": 1 << 30, "warm_vcycles": 7, "match_mode": 0}
     for v in variants:
         for k_, x in v.items():
             ctx.set_option(k_, x)
