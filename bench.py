@@ -242,7 +242,7 @@ def run_cuda_arm(a):
                         note="every rank solves one full sweep; 89/92 atoms meet the reference's stop test, Z=68-70 run to the 100-step cap like the reference"),
             e2e=dict(value=n_atoms_total / wall, unit="atoms/s", h2d_bytes_per_step=opt_bytes, d2h_bytes_per_step=res_bytes),
             gpu_launches=int(launches),
-            roofline=dict(kernel="search_fused_kernel + search_seg_kernel (Numerov shooting: Sturm-count search, serial-in-r / parallel-in-r)",
+            roofline=dict(kernel="search_seg_kernel (Numerov shooting: Sturm-count search, parallel in r: cluster of 4 CTAs per orbital, warp = radial segment, lane = trial energy)",
                           bound="fp64", achieved=achieved, peak=peak, unit="TFLOP/s",
                           frac=achieved / peak if peak else None, traffic=None,
                           peak_source="measured live: DFMA microbench in libdftatom_b200 (MEASURED_PEAKS.json has no FP64 entry)",

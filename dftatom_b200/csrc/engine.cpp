@@ -9,6 +9,8 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <numeric>
+#include <thread>
 
 namespace dft {
 
@@ -62,6 +64,8 @@ struct dftatom_ctx {
     int match_mode = 0;
     int energies_per_lane = 1;
     int warm_start = 1;
+    int stream_groups = 1;     // 2: a batch of >= 32 atoms is split into two groups that run their SCF chains concurrently on separate streams
+    dftatom_ctx* child = nullptr;   // context (stream + buffers) of the second group
     int stream_variant = 0;    // window shape of the stream-mode Poisson visits (poisson_stream.cu)
     int stream_poisson = 1;    // grids above 16385 nodes: level visits streamed over all densities (poisson_stream.cu) instead of one CTA / team per density
     int stream_min_dens = 4;   // ... when the batch has at least this many densities (below, the team of CTAs per density is faster)
@@ -173,6 +177,7 @@ int dftatom_create(dftatom_ctx** out, int device)
 void dftatom_destroy(dftatom_ctx* c)
 {
     if (!c) return;
+    if (c->child) { dftatom_destroy(c->child); c->child = nullptr; }
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto& kv : c->grids) kv.second.mem.release();
@@ -202,6 +207,7 @@ int dftatom_set_option(dftatom_ctx* c, const char* key, double value)
     else if (k == "search_mode") c->search_mode = (int)value;
     else if (k == "match_mode") c->match_mode = (int)value;
     else if (k == "warm_start") c->warm_start = value != 0.;
+    else if (k == "stream_groups") c->stream_groups = std::min(2, std::max(1, (int)value));
     else if (k == "stream_poisson") c->stream_poisson = value != 0.;
     else if (k == "stream_min_dens") c->stream_min_dens = std::max(1, (int)value);
     else if (k == "stream_variant") c->stream_variant = std::min(2, std::max(0, (int)value));
@@ -258,8 +264,9 @@ int dftatom_measure_fp64_peak(dftatom_ctx* c, double* tflops)
     return 0;
 }
 
-int dftatom_solve_batch(dftatom_ctx* c, const dftatom_options* opts, int n_atoms, dftatom_result* out, dftatom_step* steps,
-                        int steps_stride)
+// one group of atoms: its whole SCF, enqueued on the context's stream
+static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms, dftatom_result* out, dftatom_step* steps,
+                       int steps_stride)
 {
     if (!c || !opts || !out || n_atoms <= 0) { set_error("bad argument"); return DFTATOM_E_ARG; }
     DFT_CHECK(cudaSetDevice(c->device));
@@ -510,6 +517,66 @@ int dftatom_solve_batch(dftatom_ctx* c, const dftatom_options* opts, int n_atoms
         }
     }
     (void)steps_enqueued;
+    return 0;
+}
+
+// Every kernel of the SCF chain of one atom depends on the previous one, and from the middle of a batch on most launches
+// are latency-bound and leave SMs idle (the Poisson solve runs one CTA per density).  Atoms are independent, so a large
+// batch is dealt into two groups whose chains are enqueued by two host threads on two streams: the search of one group
+// overlaps the Poisson solve of the other.  Results are identical to the single-group run (no atom sees another).
+int dftatom_solve_batch(dftatom_ctx* c, const dftatom_options* opts, int n_atoms, dftatom_result* out, dftatom_step* steps,
+                        int steps_stride)
+{
+    if (!c || !opts || !out || n_atoms <= 0) { set_error("bad argument"); return DFTATOM_E_ARG; }
+    if (c->stream_groups < 2 || n_atoms < 32) return solve_group(c, opts, n_atoms, out, steps, steps_stride);
+    for (int a = 0; a < n_atoms; ++a) {
+        int rc = validate(opts[a]);
+        if (rc) return rc;
+        if (opts[a].levels != opts[0].levels || opts[a].delta != opts[0].delta || opts[a].max_r != opts[0].max_r) {
+            set_error("all atoms of one batch must share (levels, delta, max_r)");
+            return DFTATOM_E_MIXED_GRID;
+        }
+    }
+    if (!c->child) { int rc = dftatom_create(&c->child, c->device); if (rc) return rc; }
+    dftatom_ctx* ch = c->child;
+    ch->max_vcycles = c->max_vcycles; ch->floor_stop = c->floor_stop; ch->refine_vcycles = c->refine_vcycles; ch->warm_vcycles = c->warm_vcycles;
+    ch->warm_after = c->warm_after; ch->team_poisson = c->team_poisson; ch->r_segments = c->r_segments; ch->seg_threshold = c->seg_threshold;
+    ch->profile = c->profile; ch->search_mode = c->search_mode; ch->match_mode = c->match_mode; ch->energies_per_lane = c->energies_per_lane;
+    ch->warm_start = c->warm_start; ch->stream_variant = c->stream_variant; ch->stream_poisson = c->stream_poisson;
+    ch->stream_min_dens = c->stream_min_dens; ch->stream_groups = 1;
+    // deal the atoms in order of decreasing cost (orbital count ~ Z; LSDA doubles it) alternately into the two groups
+    std::vector<int> order(n_atoms);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return opts[x].Z * (1 + opts[x].method) > opts[y].Z * (1 + opts[y].method); });
+    std::vector<int> idx[2];
+    for (int q = 0; q < n_atoms; ++q) idx[q & 1].push_back(order[q]);
+    for (auto& v : idx) std::sort(v.begin(), v.end());
+    std::vector<dftatom_options> gopts[2];
+    std::vector<dftatom_result> gout[2];
+    std::vector<dftatom_step> gsteps[2];
+    for (int gI = 0; gI < 2; ++gI) {
+        for (int a : idx[gI]) gopts[gI].push_back(opts[a]);
+        gout[gI].resize(idx[gI].size());
+        if (steps) gsteps[gI].resize(idx[gI].size() * (size_t)steps_stride);
+    }
+    int rc1 = 0;
+    std::string err1;
+    std::thread th([&]() {
+        rc1 = solve_group(ch, gopts[1].data(), (int)gopts[1].size(), gout[1].data(), steps ? gsteps[1].data() : nullptr, steps_stride);
+        if (rc1) err1 = g_err;
+    });
+    const int rc0 = solve_group(c, gopts[0].data(), (int)gopts[0].size(), gout[0].data(), steps ? gsteps[0].data() : nullptr, steps_stride);
+    th.join();
+    if (rc0) return rc0;
+    if (rc1) { set_error(err1); return rc1; }
+    for (int gI = 0; gI < 2; ++gI)
+        for (size_t q = 0; q < idx[gI].size(); ++q) {
+            out[idx[gI][q]] = gout[gI][q];
+            if (steps) std::memcpy(steps + (size_t)idx[gI][q] * steps_stride, &gsteps[gI][q * (size_t)steps_stride], sizeof(dftatom_step) * (size_t)steps_stride);
+        }
+    c->last_ms = std::max(c->last_ms, ch->last_ms);
+    c->last_launches += ch->last_launches;
+    for (int k = 0; k < DFTATOM_K_COUNT; ++k) { c->prof[k].ms += ch->prof[k].ms; c->prof[k].launches += ch->prof[k].launches; c->prof[k].work += ch->prof[k].work; }
     return 0;
 }
 

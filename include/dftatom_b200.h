@@ -105,6 +105,11 @@ const char* dftatom_version(void);
  *   "search_mode"  (default 0) 0 = fused single-predicate multisection (production); 1 = reference-shaped three-stage
  *                   search (node-count window edges, then the sign change of y(0)), kept for validation
  *   "profile"      (default 0) time every kernel class with CUDA events, see dftatom_last_profile
+ *   "stream_groups" (default 1) 2 = a batch of >= 32 atoms is dealt into two groups whose SCF chains run concurrently on two
+ *                   streams (atoms are independent; every launch of one chain depends on the previous one and most are
+ *                   latency-bound).  Measured: C3 590 -> 624 atoms/s, but 8 x C3 in one batch 1135 -> 1027, and the per-kernel
+ *                   CUDA-event times then include the contention between the groups, so it is off by default.  Per-atom
+ *                   results do not depend on it.
  *   "stream_poisson" (default 1) grids above 16385 nodes with at least "stream_min_dens" (default 4) densities in the batch: the
  *                   Poisson solve runs as level visits streamed over all densities (poisson_stream.cu: HBM-bound, slab windows
  *                   with halos) instead of one CTA / team of CTAs per density; 0 = never

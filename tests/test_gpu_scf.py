@@ -148,6 +148,23 @@ def test_stream_poisson_agrees(ctx):
             np.testing.assert_allclose([x for ch in r.steps[k].E for x in ch], [x for ch in b.steps[k].E for x in ch], rtol=0, atol=2e-7)
 
 
+def test_stream_groups_same_results(ctx):
+    """Two groups of atoms on two streams (stream_groups = 2, batches of >= 32 atoms): every atom's trajectory is bit-identical
+    to the single-group run - no atom sees another."""
+    opts = [D.Options(Z, 10, 15.0, 0.004, 0.5, Z % 2) for Z in range(1, 41)]
+    base = ctx.solve_batch(opts)
+    ctx.set_option("stream_groups", 2)
+    try:
+        res = ctx.solve_batch(opts)
+    finally:
+        ctx.set_option("stream_groups", 1)
+    for r, b in zip(res, base):
+        assert r.n_steps == b.n_steps and r.status == b.status
+        assert [s.Etotal for s in r.steps] == [s.Etotal for s in b.steps]
+        assert [s.E for s in r.steps] == [s.E for s in b.steps]
+        assert [[(L.n, L.l, L.occ) for L in ch] for ch in r.sorted_levels] == [[(L.n, L.l, L.occ) for L in ch] for ch in b.sorted_levels]
+
+
 def test_options_validation(ctx):
     """Same ranges as the reference's dialog validators (OptionsFrame.cpp:46,152-173); mixed grids are refused."""
     for bad in (D.Options(0, 10, 15.0, 0.004, 0.5, 0), D.Options(119, 10, 15.0, 0.004, 0.5, 0), D.Options(2, 10, 0.5, 0.004, 0.5, 0),
