@@ -1096,6 +1096,54 @@ __device__ __forceinline__ void export_level0(double* nat, int N)
     for (int s = threadIdx.x; s < N; s += blockDim.x) nat[unslot(s, y)] = p.ld(s);
 }
 
+// The same conversions for the 16385-node level 0 (512 threads x 32 nodes) with both sides coalesced: natural order <->
+// padded natural order in dynamic shared memory (node i at i + i/32: a thread walking its own 32 nodes and a warp walking 32
+// consecutive nodes are both conflict-free) <-> registers <-> owner-major slots.  The plain loops above gather 8-byte words
+// 256 bytes apart (one 32-byte sector per word): measured ~10 % of a warm-started solve.  The staging area overlaps
+// Source_0 and the start of the next shared level; it is only used before they are filled / after they are dead.
+constexpr int kStageDoubles = kPT * kMaxNpt + kPT + 8;
+__device__ __forceinline__ void stage_natural(const double* __restrict__ nat, const double* __restrict__ scale, int N)
+{
+    for (int i = threadIdx.x; i < N; i += kPT) g_dyn[i + (i >> 5)] = scale ? __ldg(scale + i) * __ldg(nat + i) : __ldg(nat + i);
+    __syncthreads();
+}
+__device__ __forceinline__ void import_level0_staged(bool to_source, const double* __restrict__ nat, const double* __restrict__ scale, int N)
+{
+    const int t = threadIdx.x, n = N - 1;
+    stage_natural(nat, scale, N);
+    double v[kMaxNpt];
+#pragma unroll
+    for (int k = 0; k < kMaxNpt; ++k) v[k] = g_dyn[t * (kMaxNpt + 1) + k];
+    const double vb = g_dyn[n + (n >> 5)];
+    __syncthreads();
+    const LevelConst& c = g_sm.lc[0];
+    if (to_source) {                     // Source_0 lives in dynamic shared memory
+#pragma unroll
+        for (int k = 0; k < kMaxNpt; ++k) g_dyn[c.os + k * kPT + t] = v[k];
+        if (t == 0) g_dyn[c.os + n] = vb;
+    } else {                             // Phi_0 lives in global memory
+        double* gp = g_sm.gphi + c.op;
+#pragma unroll
+        for (int k = 0; k < kMaxNpt; ++k) gp[k * kPT + t] = v[k];
+        if (t == 0) gp[n] = vb;
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void export_level0_staged(double* __restrict__ nat, int N)
+{
+    const int t = threadIdx.x, n = N - 1;
+    const double* gp = g_sm.gphi + g_sm.lc[0].op;
+    __syncthreads();
+    double v[kMaxNpt];
+#pragma unroll
+    for (int k = 0; k < kMaxNpt; ++k) v[k] = __ldcg(gp + k * kPT + t);
+#pragma unroll
+    for (int k = 0; k < kMaxNpt; ++k) g_dyn[t * (kMaxNpt + 1) + k] = v[k];
+    if (t == 0) g_dyn[n + (n >> 5)] = __ldcg(gp + n);
+    __syncthreads();
+    for (int i = t; i < N; i += kPT) nat[i] = g_dyn[i + (i >> 5)];
+}
+
 // error-free transformations (Dekker / Knuth); the intrinsics keep nvcc from contracting or re-associating them
 __device__ __forceinline__ void two_sum(double a, double b, double& s, double& e)
 {
@@ -1152,16 +1200,23 @@ __global__ void __launch_bounds__(kPT) poisson_full_kernel(GridDev g, PoissonLev
             double* s0 = g_sm.gsrc + g_sm.lc[0].os;
             for (int i = ws0; i < N; i += wstride) s0[i] = a.rho ? g.psrc[i] * rho[i] : rho[i];
         }
-    } else if (a.rho) import_level0(src, a.rho + (size_t)k * NS, g.psrc, N);
-    else if (a.src_nat) import_level0(src, a.src_nat + (size_t)k * NS, nullptr, N);
+    }
     const bool warm = a.warm_vcycles > 0 && a.u_out != nullptr;
+    // 16385 nodes, one CTA: level 0 goes in and out through the staged (coalesced) conversions
+    const bool staged_io = !team && N == kPT * kMaxNpt + 1 && g_sm.lc[0].ws == kDyn && g_sm.lc[0].wp == kGlobal && a.smem_doubles >= kStageDoubles;
+    if (staged_io && warm) import_level0_staged(false, a.u_out + (size_t)k * NS, nullptr, N);       // (before Source_0: shares the staging area)
+    if (!team) {
+        if (staged_io && (a.rho || a.src_nat)) import_level0_staged(true, a.rho ? a.rho + (size_t)k * NS : a.src_nat + (size_t)k * NS, a.rho ? g.psrc : nullptr, N);
+        else if (a.rho) import_level0(src, a.rho + (size_t)k * NS, g.psrc, N);
+        else if (a.src_nat) import_level0(src, a.src_nat + (size_t)k * NS, nullptr, N);
+    }
     const int n_cycles = warm ? a.warm_vcycles : a.max_vcycles;
     int fmg_top = 0;                     // top level the full-multigrid ramp has reached (0: only V-cycles are left)
     if (warm) {
         // Warm start (beyond the reference): Phi_0 = the previous solve of this density (u_out, same boundary values); the
         // V-cycles contract the difference by more than 10x each, so a few of them reach the same FP64 fixed point as the
         // full cycle from zero.  (Team mode: Phi_0 is still in place in global memory.)
-        if (!team) import_level0(phi, a.u_out + (size_t)k * NS, nullptr, N);
+        if (!team && !staged_io) import_level0(phi, a.u_out + (size_t)k * NS, nullptr, N);
         __syncthreads();
         team_barrier();
     } else {
@@ -1261,7 +1316,7 @@ __global__ void __launch_bounds__(kPT) poisson_full_kernel(GridDev g, PoissonLev
             double* u = a.u_out + (size_t)k * NS;
             for (int i = ws0; i < N; i += wstride) u[i] = __ldcg(p0 + i);
         }
-    } else if (a.u_out) export_level0(a.u_out + (size_t)k * NS, N);
+    } else if (a.u_out) { if (staged_io) export_level0_staged(a.u_out + (size_t)k * NS, N); else export_level0(a.u_out + (size_t)k * NS, N); }
     if (dbg && threadIdx.x == 0) dbg[97] += clock64() - t_start;
     if (threadIdx.x == 0) {
         if (a.work) atomicAdd(a.work, g_sm.updates);
