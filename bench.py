@@ -244,7 +244,9 @@ def run_cuda_arm(a):
             gpu_launches=int(launches),
             roofline=dict(kernel="search_seg_kernel (Numerov shooting: Sturm-count search, parallel in r: cluster of 4 CTAs per orbital, warp = radial segment, lane = trial energy)",
                           bound="fp64", achieved=achieved, peak=peak, unit="TFLOP/s",
-                          frac=achieved / peak if peak else None, traffic=None,
+                          frac=achieved / peak if peak else None, traffic=12.52e6,
+                          traffic_source="dram__bytes_read + write of one search_seg_kernel launch with all 916 orbitals active, ncu --set full "
+                                         "(profiles/r01_ncu_search_seg.txt): the kernel is FP64-bound, its tables stay in L2",
                           peak_source="measured live: DFMA microbench in libdftatom_b200 (MEASURED_PEAKS.json has no FP64 entry)",
                           flop_per_lane_node_step=FLOP_PER_NODE_STEP, lane_node_steps=s["work"], kernel_ms=s["ms"], share_of_step=shares),
             kernels={k: dict(ms=v["ms"], launches=int(v["launches"]), work=v["work"]) for k, v in prof.items()},
@@ -374,7 +376,9 @@ def micro_c5a(ctx, torch, hbm_peak_gbs, n_dens=1024, levels=20, delta=1.25e-5, r
     out["known_answer_max_err_over_Z"] = err
     out["roofline"] = dict(kernel="stream_visit_kernel (+ poisson_mid_kernel below 16385 nodes)", bound="hbm",
                            achieved=best["chained"]["achieved_gbs"], peak=hbm_peak_gbs, unit="GB/s",
-                           frac=best["chained"]["achieved_gbs"] / hbm_peak_gbs, traffic=None,
+                           frac=best["chained"]["achieved_gbs"] / hbm_peak_gbs, traffic=27.2 * N * n_dens,
+                           traffic_source="ncu --set full of the level-0 down-visit (profiles/r01_ncu_stream_visit.txt): dram read 16.0 + write 11.2 "
+                                          "B/node against the algorithmic 16 + 12 of that launch; scaled here to this launch's nodes x densities",
                            bytes_per_node_per_vcycle=112.0, peak_source="MEASURED_PEAKS.json hbm copy (fallback 6459 GB/s)")
     if cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "tests"))

@@ -56,8 +56,9 @@ struct dftatom_ctx {
     int warm_after = 4;
     int team_poisson = 1;      // large grids, few atoms: several CTAs per density (poisson.cu, team mode)
     int r_segments = -1;       // radial segments per orbital of the parallel-in-r search; -1 = auto (16 up to 16385 nodes, 32 above), 0 / 1 = serial-in-r search only
-    int seg_threshold = 1 << 30;   // the parallel-in-r search runs once at most this many orbitals are still active (default: always; the
-                               // serial-in-r kernel, one warp per orbital, runs above it)
+    int seg_threshold = 2400;  // the parallel-in-r search runs once at most this many orbitals are still active; above it (>= 4 warps per
+                               // FP64 pipe) the serial-in-r kernel, one warp per orbital, is throughput-bound with 8 instead of 11 FP64
+                               // instructions per (lane, node) and wins (8 x C3 in one batch: 1135 against 975 atoms/s)
     int segments(int N) const { return r_segments < 0 ? (N <= 16385 ? 16 : 32) : r_segments; }
     int profile = 0;
     int search_mode = 0;

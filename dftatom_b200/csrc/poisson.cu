@@ -104,6 +104,7 @@ struct PoissonSmem {
     double edge[16];     // first node of every warp (old value for the left neighbour warp)
     double red[32];
     double carry;        // last new value of the previous chunk
+    double apow[kMaxNpt]; // a^(k+1) of the level being visited (fused_block): the carry patch reads it instead of running its own product chain
     double bcast;
     unsigned long long updates;   // Gauss-Seidel node-updates performed by this CTA (work counter)
     double w[2 * kWarpSmemDoubles];   // the warp levels: Phi at [0, kWarpSmemDoubles), Source behind it
@@ -390,6 +391,7 @@ __device__ __noinline__ void fused_block(int l, int flags, int sweeps)
     const double B = lc.B;
     const int nsteps = lc.nsteps;
     if (t == 0) g_sm.updates += (unsigned long long)sweeps * (unsigned long long)(n - 1);
+    if (t < NPT) { double q = a; for (int j = 0; j < t; ++j) q *= a; g_sm.apow[t] = q; }      // same products, same order, as a running q *= a
     double cin = 0.;
     for (int sw = 0; sw < sweeps; ++sw) {
         double nb = __shfl_down_sync(full, phi[0], 1);
@@ -441,9 +443,8 @@ __device__ __noinline__ void fused_block(int l, int flags, int sweeps)
         if (lane == 0) Pex = 0.;
         cin = fma(Alane, carry, Pex);                           // new value of the node before this thread's first node
         if (t == 0) cin = 0.;
-        double q = a;
 #pragma unroll
-        for (int k = 0; k < NPT; ++k) { phi[k] = fma(q, cin, phi[k]); q *= a; }
+        for (int k = 0; k < NPT; ++k) phi[k] = fma(g_sm.apow[k], cin, phi[k]);
     }
 #pragma unroll
     for (int k = 0; k < NPT; ++k) P.st(k * kPT + t, phi[k]);

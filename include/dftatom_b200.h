@@ -100,8 +100,8 @@ const char* dftatom_version(void);
  *   "match_mode"   (default 0) 0 = segmented two-sided solve (production); 1 = serial reference-arithmetic kernel
  *   "r_segments"   (default -1 = auto: 16 up to 16385 nodes, 32 above) radial segments per orbital of the parallel-in-r search
  *                   (one thread-block cluster per orbital); 0 = serial-in-r search only (one warp per orbital)
- *   "seg_threshold" (default: always) the parallel-in-r search runs once at most this many orbitals are still active, the
- *                   serial-in-r one above
+ *   "seg_threshold" (default 2400) the parallel-in-r search runs once at most this many orbitals are still active, the
+ *                   serial-in-r one (fewer instructions, needs >= 4 warps per FP64 pipe to hide its dependent chain) above
  *   "search_mode"  (default 0) 0 = fused single-predicate multisection (production); 1 = reference-shaped three-stage
  *                   search (node-count window edges, then the sign change of y(0)), kept for validation
  *   "profile"      (default 0) time every kernel class with CUDA events, see dftatom_last_profile

@@ -111,7 +111,7 @@ def test_kernel_shapes_agree(ctx):
     base = ctx.solve_batch(opts)
     variants = [{"r_segments": 0}, {"seg_threshold": 30}, {"r_segments": 32}, {"r_segments": 8}, {"warm_vcycles": 0},
                 {"match_mode": 2}]
-    defaults = {"r_segments": -1, "seg_threshold": 1 << 30, "warm_vcycles": 7, "match_mode": 0}
+    defaults = {"r_segments": -1, "seg_threshold": 2400, "warm_vcycles": 7, "match_mode": 0}
     for v in variants:
         for k_, x in v.items():
             ctx.set_option(k_, x)
