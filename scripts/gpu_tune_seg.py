@@ -7,8 +7,8 @@ ctx = D.Context(0)
 ctx.set_option("profile", 1)
 opts = [D.Options(Z, 14, 25.0, 0.0005, 0.5, 0) for Z in range(1, 93)]
 ctx.solve_batch(opts, keep_steps=False)
-for segs in (4, 8, 16, 32):
-    for thr in (100000,):
+for segs in (-1,):
+    for thr in (2400,):
         ctx.set_option("r_segments", segs); ctx.set_option("seg_threshold", thr)
         best = 1e9
         for _ in range(2):
