@@ -134,7 +134,9 @@ static int get_grid(dftatom_ctx* c, int L, double delta, double max_r, GridDev**
 static int validate(const dftatom_options& o)
 {   // ranges of the reference's dialog validators, OptionsFrame.cpp:46,152-173 (levels: the class itself accepts any >= 1)
     if (o.Z < 1 || o.Z > 118) { set_error("Z must be in 1..118"); return DFTATOM_E_BAD_OPTION; }
-    if (o.levels < 4 || o.levels > 20) { set_error("levels must be in 4..20"); return DFTATOM_E_BAD_OPTION; }
+    // the dialog offers 10..20; below 8 levels (257 nodes) 1 - f/12 turns negative over much of the grid and the reference's own
+    // sweeps stop meaning anything (measured: Ne at 65 nodes, 42 Ha between two evaluation orders of the same recurrence)
+    if (o.levels < 8 || o.levels > 20) { set_error("levels must be in 8..20"); return DFTATOM_E_BAD_OPTION; }
     if (!(o.max_r >= 1. && o.max_r <= 90.)) { set_error("max_r must be in 1..90"); return DFTATOM_E_BAD_OPTION; }
     if (!(o.delta > 0. && o.delta <= 1.)) { set_error("delta must be in (0,1]"); return DFTATOM_E_BAD_OPTION; }
     if (!(o.mixing >= 0. && o.mixing <= 1.)) { set_error("mixing must be in [0,1]"); return DFTATOM_E_BAD_OPTION; }

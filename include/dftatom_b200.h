@@ -44,7 +44,7 @@ enum {
 /* Options.h:48-54 (field meaning identical; defaults Options.cpp:6: Z=36, levels=12, MaxR=10, delta=0.001, alpha=0.5, method=0) */
 typedef struct {
     int Z;              /* 1..118 (OptionsFrame.cpp:152-154) */
-    int levels;         /* MultigridLevels, N = 2^levels + 1 nodes; 4..20 accepted (dialog shows 10..20) */
+    int levels;         /* MultigridLevels, N = 2^levels + 1 nodes; 8..20 accepted (dialog shows 10..20) */
     double max_r;       /* MaxR, 1..90 */
     double delta;       /* deltaGrid, (0,1] */
     double mixing;      /* alpha = weight of the OLD density, [0,1] */

@@ -165,11 +165,27 @@ def test_stream_groups_same_results(ctx):
         assert [[(L.n, L.l, L.occ) for L in ch] for ch in r.sorted_levels] == [[(L.n, L.l, L.occ) for L in ch] for ch in b.sorted_levels]
 
 
+def test_edge_options_match_oracle(ctx):
+    """Corners of the option space against the oracle, every step: hydrogen fully polarised (LSDA), the heaviest element the
+    dialog admits (Z = 118, 19 levels per spin incl. 5f/6d/7p), the coarsest accepted grid, strong damping."""
+    cases = [(1, 10, 15.0, 0.004, 0.5, 1), (118, 12, 25.0, 0.002, 0.5, 0), (118, 12, 25.0, 0.002, 0.5, 1), (2, 8, 10.0, 0.02, 0.5, 0),
+             (36, 12, 10.0, 0.001, 0.9, 0)]
+    for Z, L, rmax, delta, mix, m in cases:
+        r = ctx.solve_batch([D.Options(Z, L, rmax, delta, mix, m)])[0]
+        ref = O.scf(Z, L, mix, rmax, delta, m, max_vcycles=12)
+        n = min(r.n_steps, len(ref["steps"]))
+        assert n >= 20 and abs(r.n_steps - len(ref["steps"])) <= 3
+        for k in range(n):
+            s, g = r.steps[k], ref["steps"][k]
+            assert abs(s.Etotal - g["Etotal"]) <= ENERGY_TOL, (Z, m, k)
+            np.testing.assert_allclose([x for ch in s.E for x in ch], g["E"][0] + g["E"][1], rtol=0, atol=EIG_TOL)
+
+
 def test_options_validation(ctx):
     """Same ranges as the reference's dialog validators (OptionsFrame.cpp:46,152-173); mixed grids are refused."""
     for bad in (D.Options(0, 10, 15.0, 0.004, 0.5, 0), D.Options(119, 10, 15.0, 0.004, 0.5, 0), D.Options(2, 10, 0.5, 0.004, 0.5, 0),
                 D.Options(2, 10, 15.0, 0.0, 0.5, 0), D.Options(2, 10, 15.0, 0.004, 1.5, 0), D.Options(2, 10, 15.0, 0.004, 0.5, 2),
-                D.Options(2, 21, 15.0, 0.004, 0.5, 0)):
+                D.Options(2, 21, 15.0, 0.004, 0.5, 0), D.Options(2, 7, 15.0, 0.004, 0.5, 0)):
         with pytest.raises(D.DFTAtomError):
             ctx.solve_batch([bad])
     with pytest.raises(D.DFTAtomError):
