@@ -481,7 +481,8 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
         if (prof && getenv("DFTATOM_DEBUG_ROUNDS")) {
             fprintf(stderr, "search rounds histogram (orbital solves with r rounds, r = 1..15+):");
             for (int r = 1; r < 16; ++r) fprintf(stderr, " %llu", hw[8 + r]);
-            fprintf(stderr, "\n");
+            fprintf(stderr, "\n  rounds summed per l = s p d f: %llu %llu %llu %llu;  solves with >= 4 rounds per l: %llu %llu %llu %llu\n", hw[24], hw[25], hw[26], hw[27],
+                    hw[28], hw[29], hw[30], hw[31]);
         }
         for (int k = 0; k < DFTATOM_K_COUNT; ++k) { c->prof[k].ms = 0.; c->prof[k].launches = 0; c->prof[k].work = (double)hw[k]; }
         for (Span& s : spans) {

@@ -135,6 +135,11 @@ struct Bracket {
     double c_est, radius;   // ladder centre and outermost offset
     double ylog;            // log2 |y0| of the last virtual-bisection midpoint (1e15 guard, DFTAtom.cpp:528)
     bool ladder;
+    // after a round whose 32 samples all fell on one side of the root (a ladder that missed): the next uniform round covers
+    // only a window of this width next to the samples (32 x their span), not the whole remaining bracket, which after a
+    // warm start still reaches to -Z^2 - 1 or +50 and would cost ~6 more 33-section rounds.  side: -1 below hi, +1 above lo
+    double win = 0.;
+    int win_side = 0;
 };
 constexpr double kLadderEps = 2.4e-13;
 
@@ -146,7 +151,9 @@ __device__ __forceinline__ double sample_energy(const Bracket& b, int lane)
         const double off = kLadderEps * exp2((double)mstep * lg);
         return fmin(fmax((lane < 16) ? b.c_est - off : b.c_est + off, b.lo), b.hi);
     }
-    return b.lo + (b.hi - b.lo) * ((double)(lane + 1) * (1. / 33.));
+    double lo = b.lo, hi = b.hi;
+    if (b.win_side < 0) lo = fmax(lo, hi - b.win); else if (b.win_side > 0) hi = fmin(hi, lo + b.win);
+    return lo + (hi - lo) * ((double)(lane + 1) * (1. / 33.));
 }
 
 // warp-collective: every lane passes its own trial energy and results; all lanes end with the same bracket
@@ -160,6 +167,11 @@ __device__ __forceinline__ void update_bracket(Bracket& b, double E, bool high, 
     const double e_lo = lo_i >= 0 ? a_lo : b.lo, e_hi = hi_i < 32 ? a_hi : b.hi;
     b.ylog = __shfl_sync(full, y0_log2, lm);
     b.ladder = false;
+    {
+        const double span = __shfl_sync(full, E, 31) - __shfl_sync(full, E, 0);
+        b.win_side = (lo_i < 0 && hi_i < 32) ? -1 : ((hi_i == 32 && lo_i >= 0) ? 1 : 0);
+        b.win = 32. * fmax(span, 16. * kLadderEps);
+    }
     // estimate of the root for the next round: zero of y0(E) through the samples around the sign change
     if (lo_i >= 0 && hi_i < 32 && e_lo < e_hi) {
         double Ek[4], yk[4], lgv[4];

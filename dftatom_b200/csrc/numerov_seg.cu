@@ -246,6 +246,8 @@ __global__ void __launch_bounds__(32 * kSegWarps) search_seg_kernel(GridDev g, c
             atomicAdd(work + DFTATOM_K_MATCH, 1ULL);                          // orbital solves
             atomicAdd(work + DFTATOM_K_DENSITY, (unsigned long long)rounds);  // search rounds
             atomicAdd(work + 8 + min(rounds, 15), 1ULL);                      // histogram (debug aid)
+            atomicAdd(work + 24 + min(ob.l, 3), (unsigned long long)rounds);  // rounds and solves with >= 4 rounds per l (debug aid)
+            if (rounds >= 4) atomicAdd(work + 28 + min(ob.l, 3), 1ULL);
         }
     }
 }
