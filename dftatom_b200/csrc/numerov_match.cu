@@ -258,8 +258,8 @@ __device__ __forceinline__ int pslot(int i) { return i + (i >> 5); }
 
 // SMEM = true: g_i = f_i / 12 of the whole orbital is staged in shared memory (one coalesced pass over the tables) and
 // the solution is built in place of it, then copied out coalesced; per-thread chunk walks through global memory would
-// touch 32 cache lines per warp instruction (measured: 800 cycles per node, L1-bound).  SMEM = false (grids too large for
-// shared memory): same algorithm on global memory.
+// touch 32 cache lines per warp instruction (measured: 800 cycles per node, L1-bound).  SMEM = false: the same algorithm
+// on global memory (kept for comparison only: grids too large for one shared-memory stage take match_win_kernel below).
 template <bool SMEM>
 __global__ void __launch_bounds__(kMT) match_cta_kernel(GridDev g, const double* __restrict__ atab_all, const OrbitalDev* orbs,
                                                         const AtomState* astate, SearchState* ss, double* psi_all, int* match_pt,
