@@ -203,6 +203,38 @@ def test_report_text_matches_reference_format(ctx):
     assert rec["final"]["alpha"] == [(1, 0, 2), (2, 0, 2), (2, 1, 6)]
 
 
+def test_cli_text_matches_reference(tmp_path):
+    """bin/dftatom prints the reference's report (DFTAtom.cpp:358-490): byte-identical at 6 decimals to the text rebuilt from
+    the oracle's records for a small atom, with the options given as flags and as the reference's INI keys (Options.cpp:42-49);
+    --json carries the same final record."""
+    import json
+    import os
+    import subprocess
+    from conftest import ROOT
+    from dftatom_b200.report import format_report
+    exe = os.path.join(ROOT, "bin", "dftatom")
+    ref = O.scf(10, 10, 0.5, 15.0, 0.004, 0, max_vcycles=100)
+    lev = D.aufbau(10)
+    steps = [dict(levels=[(L.n, L.l, e, L.nodes) for L, e in zip(lev, s["E"][0])], **{k: s[k] for k in KEYS}) for s in ref["steps"]]
+    conf = sorted(zip(ref["steps"][-1]["E"][0], [(L.n, L.l, L.occ) for L in lev]))
+    text = format_report(10, 0, steps, ref["finished"], [c for _, c in conf], None)
+    out = subprocess.run([exe, "--Z", "10", "--levels", "10", "--delta", "0.004", "--mixing", "0.5", "--rmax", "15", "--method", "0"],
+                         capture_output=True, text=True, check=True).stdout
+    if out.count("Step: ") == text.count("Step: "):
+        assert out.rstrip("\n") == text.rstrip("\n")
+    else:       # the stop step is noise-driven (DESIGN.md section 5): every block before the earlier stop must still be identical
+        a, b = out.split("Step: "), text.split("Step: ")
+        n = min(len(a), len(b)) - 1
+        assert n >= 20 and a[:n] == b[:n]
+    ini = tmp_path / "DFTAtom.ini"
+    ini.write_text("Z=10\nMultigridLevels=10\nMaxR=15\ndeltaGrid=0.004\nalpha=0.5\nMethod=0\n")
+    assert subprocess.run([exe, "--ini", str(ini)], capture_output=True, text=True, check=True).stdout == out
+    js = json.loads(subprocess.run([exe, "--ini", str(ini), "--json"], capture_output=True, text=True, check=True).stdout)
+    assert js[0]["Z"] == 10 and js[0]["status"] == 0 and abs(js[0]["Etotal"] - ref["steps"][-1]["Etotal"]) < 1e-9
+    bad = subprocess.run([exe, "--Z", "10", "--levels", "30"], capture_output=True, text=True)
+    assert bad.returncode == 1 and "levels" in bad.stderr
+
+
 def test_sweep_c3_final_records(ctx):
     """C3: Z = 1..92, LDA, 14 levels: every atom's last step vs the reference; Etotal trajectory at every step."""
     atoms = golden("sweep")["atoms"]

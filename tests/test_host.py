@@ -68,3 +68,18 @@ def test_partition_atoms_lpt():
         assert sorted(sum(parts, [])) == list(range(92))
         loads = [sum(len(O.aufbau(zs[i])) for i in p) for p in parts]
         assert max(loads) - min(loads) <= 19          # LPT: within one heaviest item
+
+
+def test_cli_fails_loudly_without_gpu():
+    """bin/dftatom (the headless replacement of the wx shell) has no CPU path: without a device it exits 1 and says so."""
+    import subprocess
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    exe = os.path.join(ROOT, "bin", "dftatom")
+    if not os.path.exists(exe):
+        pytest.skip("bin/dftatom not built")
+    r = subprocess.run([exe, "--Z", "10", "--levels", "10", "--delta", "0.004", "--rmax", "15"], capture_output=True, text=True)
+    assert r.returncode == 1 and "no CUDA device" in r.stderr and r.stdout == ""
+    assert subprocess.run([exe, "--bogus"], capture_output=True).returncode == 2
+
