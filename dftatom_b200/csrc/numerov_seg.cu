@@ -52,10 +52,15 @@ __device__ __forceinline__ SegRoundOut seg_round(const GridDev& g, const double*
     int imax = start;
 #pragma unroll
     for (int o = 16; o; o >>= 1) imax = max(imax, __shfl_xor_sync(full, imax, o));
-    const int len = (imax + S - 1) / S;
-    const int top = imax - w * len;
-    const int bot = max(top - len + 1, 1);
-    const bool valid = top >= 1;
+    // segments are whole 32-node tiles of the staged tables (numerov_sweep.cuh): only the tile with the far seeds, the top tile
+    // (partial) and tile 0 (node 0 is not swept) take the general per-node path, every interior boundary is tile-aligned
+    const int m_top = imax >> 5;
+    const int tps = (m_top + S) / S;                       // ceil((m_top + 1) / S) tiles per segment
+    const int m_hi = m_top - w * tps;
+    const int m_lo = max(m_hi - tps + 1, 0);
+    const bool valid = m_hi >= 0;
+    const int top = valid ? min(imax, (m_hi << 5) + 31) : 0;
+    const int bot = max(m_lo << 5, 1);
     // this segment's role for this energy: the seeds are nodes start, start - 1; the segment that contains start - 1 runs
     // the real solution from the seeds (w_start itself depends on the tables only)
     const int kind = (!valid || start - 1 < bot) ? 0 : (start - 1 > top ? 1 : 2);
