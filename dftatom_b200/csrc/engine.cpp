@@ -809,6 +809,16 @@ int dftatom_poisson_solve(dftatom_ctx* c, int levels, double delta, double max_r
         fprintf(stderr, "poisson cycles (CTA 0): setup %lld  solve %lld  +export %lld\n", h[98], h[96], h[97]);
         for (int l = 0; l < levels; ++l)
             fprintf(stderr, "  level %2d n=%7d  smooth %9lld (%lld visits)  restrict_to %8lld  prolong_from %8lld\n", l, (1 << (levels - l)), h[l], h[72 + l], h[24 + l], h[48 + l]);
+        if (getenv("DFTATOM_DEBUG_WARM")) {      // the SCF's steady state: warm_vcycles V-cycles from the solution just computed
+            DFT_CHECK(cudaMemsetAsync(pa.dbg, 0, sizeof(long long) * 128, st));
+            pa.warm_vcycles = c->warm_vcycles;
+            launch_poisson_full(g, lv, pa, st);
+            DFT_CHECK(cudaMemcpyAsync(h, pa.dbg, sizeof(h), cudaMemcpyDeviceToHost, st));
+            DFT_CHECK(cudaStreamSynchronize(st));
+            fprintf(stderr, "warm start, %d V-cycles (CTA 0): setup %lld  solve %lld  +export %lld\n", c->warm_vcycles, h[98], h[96], h[97]);
+            for (int l = 0; l < levels; ++l)
+                fprintf(stderr, "  level %2d n=%7d  visits %9lld cycles (%lld visits)\n", l, (1 << (levels - l)), h[l], h[72 + l]);
+        }
     }
     DFT_CHECK(cudaMemcpyAsync(U, c->ubuf.p, sizeof(double) * (size_t)n_dens * N, cudaMemcpyDeviceToHost, st));
     if (vcycles_used) DFT_CHECK(cudaMemcpyAsync(vcycles_used, dv.p, sizeof(int) * n_dens, cudaMemcpyDeviceToHost, st));
