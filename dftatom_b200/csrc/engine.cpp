@@ -70,6 +70,8 @@ struct dftatom_ctx {
     int stream_variant = 0;    // window shape of the stream-mode Poisson visits (poisson_stream.cu)
     int stream_poisson = 1;    // grids above 16385 nodes: level visits streamed over all densities (poisson_stream.cu) instead of one CTA / team per density
     int stream_min_dens = 4;   // ... when the batch has at least this many densities (below, the team of CTAs per density is faster)
+    int stream_mid_levels = 11; // stream mode: levels of up to 2^this nodes are run by one CTA per density, the larger ones by slab windows
+    int stream_min_levels = 15; // stream mode from this many levels on (at 14 levels one CTA per density is as fast: measured 57.6 against 58.5 ms on C3)
     DevBuf stream_src0, stream_scratch;
     DevBuf stream_G; int stream_G_levels = 0; double stream_G_delta = 0.;   // dense coarse operator of the stream-mode V-cycle
     dftatom_kernel_profile prof[DFTATOM_K_COUNT] = {};
@@ -213,6 +215,8 @@ int dftatom_set_option(dftatom_ctx* c, const char* key, double value)
     else if (k == "stream_groups") c->stream_groups = std::min(2, std::max(1, (int)value));
     else if (k == "stream_poisson") c->stream_poisson = value != 0.;
     else if (k == "stream_min_dens") c->stream_min_dens = std::max(1, (int)value);
+    else if (k == "stream_mid_levels") c->stream_mid_levels = std::min(14, std::max(11, (int)value));
+    else if (k == "stream_min_levels") c->stream_min_levels = std::min(23, std::max(13, (int)value));
     else if (k == "stream_variant") c->stream_variant = std::min(2, std::max(0, (int)value));
     else if (k == "energies_per_lane") c->energies_per_lane = ((int)value == 2) ? 2 : 1;
     else { set_error("unknown option " + k); return DFTATOM_E_ARG; }
@@ -346,9 +350,9 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
     if ((rc = c->phi.ensure(sizeof(double) * (size_t)n_atoms * lv.total))) return rc;
     if ((rc = c->src.ensure(sizeof(double) * (size_t)n_atoms * lv.total))) return rc;
     if ((rc = c->u0.ensure(sizeof(double) * (size_t)n_atoms * N))) return rc;
-    const bool stream = c->stream_poisson && n_atoms >= c->stream_min_dens && g.L >= 15 && g.L <= 22 && c->refine_vcycles == 0 && !c->floor_stop;
+    const bool stream = c->stream_poisson && n_atoms >= c->stream_min_dens && g.L >= c->stream_min_levels && g.L > c->stream_mid_levels && g.L <= 22 && c->refine_vcycles == 0 && !c->floor_stop;
     const int ldU = stream ? ((N + 3) & ~3) : N;
-    const StreamPlan splan = stream ? make_stream_plan(g.L, n_atoms) : StreamPlan{};
+    const StreamPlan splan = stream ? make_stream_plan(g.L, n_atoms, c->stream_mid_levels) : StreamPlan{};
     if ((rc = c->ubuf.ensure(sizeof(double) * (size_t)n_atoms * ldU))) return rc;
     if (stream && ((rc = c->stream_src0.ensure(sizeof(double) * (size_t)n_atoms * ldU)) || (rc = c->stream_scratch.ensure(sizeof(double) * (size_t)splan.total)))) return rc;
     if ((rc = c->steps.ensure(sizeof(dftatom_step) * (size_t)n_atoms * stride))) return rc;
@@ -783,10 +787,10 @@ int dftatom_poisson_solve(dftatom_ctx* c, int levels, double delta, double max_r
         DFT_CHECK(cudaMemsetAsync(c->scratch[5].p, 0, sizeof(long long) * 128, st));
         pa.dbg = c->scratch[5].as<long long>();
     }
-    const bool stream = c->stream_poisson && n_dens >= c->stream_min_dens && levels >= 15 && levels <= 22 && c->refine_vcycles == 0 && !c->floor_stop && !c->profile;
+    const bool stream = c->stream_poisson && n_dens >= c->stream_min_dens && levels >= c->stream_min_levels && levels > c->stream_mid_levels && levels <= 22 && c->refine_vcycles == 0 && !c->floor_stop && !c->profile;
     if (stream) {
         // grids beyond the chip: level visits streamed over all densities (poisson_stream.cu)
-        const StreamPlan splan = make_stream_plan(levels, n_dens);
+        const StreamPlan splan = make_stream_plan(levels, n_dens, c->stream_mid_levels);
         const long long ld = (N + 3) & ~3;
         if ((rc = c->stream_src0.ensure(sizeof(double) * (size_t)n_dens * ld)) || (rc = c->stream_scratch.ensure(sizeof(double) * (size_t)splan.total))) return rc;
         if ((rc = c->ubuf.ensure(sizeof(double) * (size_t)n_dens * ld))) return rc;
@@ -830,7 +834,9 @@ int dftatom_poisson_solve(dftatom_ctx* c, int levels, double delta, double max_r
 long long dftatom_poisson_scratch_bytes(int levels, int n_dens)
 {
     if (levels < 15 || levels > 22 || n_dens <= 0) return 0;
-    return (long long)sizeof(double) * make_stream_plan(levels, n_dens).total;
+    long long t = 0;
+    for (int mid = 11; mid <= 14; ++mid) t = std::max(t, make_stream_plan(levels, n_dens, mid).total);       // whatever "stream_mid_levels" is set to
+    return (long long)sizeof(double) * t;
 }
 
 int dftatom_poisson_vcycles(dftatom_ctx* c, int levels, double delta, int n_dens, double* phi, const double* src, int n_cycles,
@@ -865,7 +871,7 @@ int dftatom_poisson_vcycles_dev(dftatom_ctx* c, int levels, double delta, int n_
     if (levels < 15 || levels > 22) { set_error("stream-mode V-cycles need 15 <= levels <= 22 (smaller grids are solved on chip: dftatom_poisson_vcycles)"); return DFTATOM_E_BAD_OPTION; }
     const long long N = (1ll << levels) + 1;
     if (ld < N || (ld & 1) || ((uintptr_t)d_phi & 15) || ((uintptr_t)d_src & 15) || ((uintptr_t)d_scratch & 15)) { set_error("ld must be even and >= N, pointers 16-byte aligned"); return DFTATOM_E_ARG; }
-    const StreamPlan sp = make_stream_plan(levels, n_dens);
+    const StreamPlan sp = make_stream_plan(levels, n_dens, c->stream_mid_levels);
     if (scratch_bytes < (long long)sizeof(double) * sp.total) { set_error("scratch too small"); return DFTATOM_E_ARG; }
     DFT_CHECK(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;

@@ -169,14 +169,16 @@ void launch_poisson_mid(const PoissonLevels& lv, double delta, int K, int n_dens
                         cudaStream_t st);
 // Layout of the scratch block of the stream-mode V-cycle (all offsets in doubles, 4-aligned)
 struct StreamPlan {
-    int L, K;               // levels; K = the 16384-node level (first level run by poisson_mid_kernel)
+    int L, K;               // levels; K = the first level run by poisson_mid_kernel (2^mid_levels nodes)
     PoissonLevels lv;
     long long cstride;      // per-density block of the natural-order levels 1..K
     int coff[24];           // offset of level l (1..K) inside that block
     int mid_total;          // per-density block of the owner-major levels K..L-1
     long long off_cphi, off_csrc, off_mphi, off_msrc, total;   // inside the scratch block, for n_dens densities
 };
-StreamPlan make_stream_plan(int L, int n_dens);
+// mid_levels: the levels of up to 2^mid_levels nodes are run by one CTA per density (poisson_mid_kernel); 12 <= mid_levels <= 14
+// (the streamed levels must hold at least one 4096-node window), L - mid_levels >= 1
+StreamPlan make_stream_plan(int L, int n_dens, int mid_levels = 14);
 // n_cycles V-cycles (PoissonSolver.h:155-159) on level-0 arrays phi0/src0 [n_dens][ld0] (device, natural order, ld0 % 2 == 0);
 // fuse_tops: the up-visit of cycle k and the down-visit of cycle k+1 of level 0 are one visit with 6 sweeps
 void launch_poisson_stream_vcycles(const StreamPlan& sp, double delta, int n_dens, double* phi0, const double* src0, long long ld0,

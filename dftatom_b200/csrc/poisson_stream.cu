@@ -266,12 +266,12 @@ void launch_stream_visit(const StreamVisitArgs& v, int n_dens, int variant, cuda
     else launch_variant<256, 16, 2>(v, n_dens, st);
 }
 
-StreamPlan make_stream_plan(int L, int n_dens)
+StreamPlan make_stream_plan(int L, int n_dens, int mid_levels)
 {
     StreamPlan sp{};
     sp.L = L;
     sp.lv = make_levels(L);
-    sp.K = L - 14;                                   // size[K] - 1 == 16384
+    sp.K = L - mid_levels;                           // size[K] - 1 == 2^mid_levels (16384 for 14, 2048 for 11)
     long long off = 0;
     for (int l = 1; l <= sp.K; ++l) { sp.coff[l] = (int)off; off += (sp.lv.size[l] + 3) & ~3; }
     sp.cstride = off;

@@ -110,9 +110,11 @@ const char* dftatom_version(void);
  *                   latency-bound).  Measured: C3 590 -> 624 atoms/s, but 8 x C3 in one batch 1135 -> 1027, and the per-kernel
  *                   CUDA-event times then include the contention between the groups, so it is off by default.  Per-atom
  *                   results do not depend on it.
- *   "stream_poisson" (default 1) grids above 16385 nodes with at least "stream_min_dens" (default 4) densities in the batch: the
- *                   Poisson solve runs as level visits streamed over all densities (poisson_stream.cu: HBM-bound, slab windows
- *                   with halos) instead of one CTA / team of CTAs per density; 0 = never
+ *   "stream_poisson" (default 1) grids of at least "stream_min_levels" (default 15) levels with at least "stream_min_dens"
+ *                   (default 4) densities in the batch: the Poisson solve runs as level visits streamed over all densities
+ *                   (poisson_stream.cu: slab windows with halos, one launch per level visit) for the levels above
+ *                   2^"stream_mid_levels" (default 11, 11..14) nodes and one CTA per density below, instead of one CTA / team
+ *                   of CTAs per density for everything; 0 = never
  *   "stream_variant" (default 0) window shape of the stream-mode Poisson visits: 0 = 256 threads x 16 nodes, 1 = 256 x 8, 2 = 512 x 8
  */
 int dftatom_set_option(dftatom_ctx* ctx, const char* key, double value);

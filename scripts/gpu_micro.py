@@ -16,6 +16,7 @@ peak = ctx.measure_fp64_peak()
 print("fp64 peak", peak, flush=True)
 print(json.dumps(bench.micro_c5b(ctx, peak)), flush=True)
 for v in variants:
-    ctx.set_option("stream_variant", v)
+    ctx.set_option("stream_variant", v % 10)
+    ctx.set_option("stream_mid_levels", 14 if v >= 10 else 11)
     r = bench.micro_c5a(ctx, torch, bench._hbm_peak(), n_dens=nd, cpu_baseline=(v == variants[0]))
     print("variant", v, json.dumps(r), flush=True)

@@ -111,8 +111,8 @@ def test_orbital_matches_oracle(ctx, L, delta, rmax, Z):
             np.testing.assert_allclose(u_g, u_o, rtol=0, atol=1e-10 if L <= 14 else 1e-9)
 
 
-@pytest.mark.parametrize("L,delta,rmax,stream", [(10, 0.004, 15.0, 0), (14, 0.0005, 25.0, 0), (16, 0.0002, 50.0, 0), (15, 0.0004, 50.0, 1),
-                                                 (16, 0.0002, 50.0, 1), (17, 0.0001, 50.0, 1)])
+@pytest.mark.parametrize("L,delta,rmax,stream", [(10, 0.004, 15.0, 0), (14, 0.0005, 25.0, 0), (16, 0.0002, 50.0, 0), (14, 0.0005, 25.0, 1),
+                                                 (15, 0.0004, 50.0, 1), (16, 0.0002, 50.0, 1), (17, 0.0001, 50.0, 1)])
 def test_poisson_matches_oracle_and_analytic(ctx, L, delta, rmax, stream):
     """U(r) of FMG + V-cycles vs the reference algorithm (oracle, 100 V-cycles) and vs the analytic Hartree potential.
     stream: the solver for many densities on grids beyond the chip (poisson_stream.cu) instead of one CTA / team per density."""
@@ -122,11 +122,13 @@ def test_poisson_matches_oracle_and_analytic(ctx, L, delta, rmax, stream):
     rho = np.stack([Z * k ** 3 / np.pi * np.exp(-2 * k * r) for Z, k in zip(Zs, a)])
     ctx.set_option("stream_poisson", stream)
     ctx.set_option("stream_min_dens", 1)
+    ctx.set_option("stream_min_levels", 14)
     try:
         U, used = ctx.poisson_solve(L, delta, rmax, Zs, rho)
     finally:
         ctx.set_option("stream_poisson", 1)
         ctx.set_option("stream_min_dens", 4)
+        ctx.set_option("stream_min_levels", 15)
     assert (used <= 20).all() and (used >= 3).all()
     for j, (Z, k) in enumerate(zip(Zs, a)):
         U_o, errs = O.poisson(L, delta, rmax, Z, rho[j], max_vcycles=100 if L <= 14 else 12)
@@ -152,8 +154,8 @@ def test_poisson_vcycle_shape(ctx):
         assert abs(err[j] - err_o) <= 1e-9 * err_o + 1e-15
 
 
-@pytest.mark.parametrize("L,delta,variant", [(15, 0.0004, 0), (15, 0.0004, 1), (15, 0.0004, 2), (16, 0.0002, 0), (17, 0.0001, 0)])
-def test_poisson_stream_vcycles_match_oracle(ctx, L, delta, variant):
+@pytest.mark.parametrize("L,delta,variant,mid", [(15, 0.0004, 0, 11), (15, 0.0004, 1, 12), (15, 0.0004, 2, 14), (16, 0.0002, 0, 11), (17, 0.0001, 0, 14)])
+def test_poisson_stream_vcycles_match_oracle(ctx, L, delta, variant, mid):
     """Stream mode (config C5a's kernel: slab windows with halos over the levels above 16384 nodes, one launch per level visit
     of all densities, poisson_mid_kernel below): 1 and 3 V-cycles, with and without the fused 6-sweep top visit, give the
     oracle's iterate (PoissonSolver.h:155-159) from the same state."""
@@ -172,6 +174,7 @@ def test_poisson_stream_vcycles_match_oracle(ctx, L, delta, variant):
     phi[1, 1:-1] = 40.0 * r[1:-1] ** 2 + 1e-3 * rng.standard_normal(N - 2)  # large smooth starting iterate
     phi[3, 1:-1] = 1e-3 * rng.standard_normal(N - 2)                        # rough starting iterate
     ctx.set_option("stream_variant", variant)
+    ctx.set_option("stream_mid_levels", mid)        # levels of up to 2^mid nodes: one CTA per density; above: slab windows
     sb = ctx.poisson_scratch_bytes(L, nd)
     scratch = torch.empty(sb // 8, dtype=torch.float64, device="cuda")
     d_src = torch.zeros((nd, ld), dtype=torch.float64, device="cuda")
@@ -188,7 +191,7 @@ def test_poisson_stream_vcycles_match_oracle(ctx, L, delta, variant):
             d_phi[:, :N] = torch.from_numpy(phi).cuda()
             torch.cuda.synchronize()
             ms, nl = ctx.poisson_vcycles_dev(L, delta, nd, d_phi.data_ptr(), d_src.data_ptr(), ld, scratch.data_ptr(), sb, n_cycles, fuse)
-            K = L - 14
+            K = L - mid
             assert nl == n_cycles * (2 * K + 1) - (n_cycles - 1 if fuse else 0)
             g = d_phi[:, :N].cpu().numpy()
             for j in range(nd):
@@ -199,6 +202,7 @@ def test_poisson_stream_vcycles_match_oracle(ctx, L, delta, variant):
                 assert g[j][0] == phi[j][0] and g[j][-1] == phi[j][-1]
     finally:
         ctx.set_option("stream_variant", 0)
+        ctx.set_option("stream_mid_levels", 11)
 
 
 def test_vwn_matches_oracle(ctx):

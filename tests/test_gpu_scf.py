@@ -131,8 +131,9 @@ def test_kernel_shapes_agree(ctx):
 def test_stream_poisson_agrees(ctx):
     """Grids above 16385 nodes: the stream-mode Poisson solver (level visits over all densities, poisson_stream.cu) and the
     one-CTA / team-per-density solver are the same FullCycle: same SCF trajectories far below the parity bars."""
-    opts = [D.Options(Z, 15, 25.0, 0.00025, 0.5, m) for Z, m in [(4, 0), (18, 0), (26, 1)]]
+    opts = [D.Options(Z, 14, 25.0, 0.0005, 0.5, m) for Z, m in [(4, 0), (18, 0), (26, 1)]]
     ctx.set_option("stream_min_dens", 1)
+    ctx.set_option("stream_min_levels", 14)
     try:
         base = ctx.solve_batch(opts)
         ctx.set_option("stream_poisson", 0)
@@ -140,6 +141,7 @@ def test_stream_poisson_agrees(ctx):
     finally:
         ctx.set_option("stream_poisson", 1)
         ctx.set_option("stream_min_dens", 4)
+        ctx.set_option("stream_min_levels", 15)
     for r, b in zip(res, base):
         n = min(r.n_steps, b.n_steps)
         assert n >= 10
