@@ -434,10 +434,12 @@ __device__ __noinline__ void fused_block(int l, int flags, int sweeps)
         }
         if (lane == 31) g_sm.wtot[w] = Pw;
         __syncthreads();
-        double carry = 0.;
-        {
-            double bp = 1.;
-            for (int k = 1; k <= w && bp >= kTiny; ++k) { carry = fma(bp, g_sm.wtot[w - k], carry); bp *= B; }
+        // carry into this warp: the new value of the previous warp's last node; terms from further back carry B = A^32 per warp,
+        // below FP64 resolution for every block level (a^64 < 1e-19), so the general loop almost never runs
+        double carry = (w > 0) ? g_sm.wtot[w - 1] : 0.;
+        if (B >= kTiny) {
+            double bp = B;
+            for (int k = 2; k <= w && bp >= kTiny; ++k) { carry = fma(bp, g_sm.wtot[w - k], carry); bp *= B; }
         }
         double Pex = __shfl_up_sync(full, Pw, 1);
         if (lane == 0) Pex = 0.;
