@@ -42,7 +42,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.gpu)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.gpu)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -50,14 +50,23 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Clocks and throttle reasons of the samples taken inside [t0, t1] (the timed region); the sampler is started before the
+        warm-up steps so that nvidia-smi is already running, and if the timed region is too short to hold two samples the
+        warm-up samples (same workload, same load) are used as well."""
         if self.proc is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.12)
         self.proc.terminate()
+        inside = [ln for ts, ln in self.lines if t0 is None or (t0 <= ts <= (t1 or ts) + 0.1)]
+        window = "timed region"
+        if len(inside) < 2:
+            inside = [ln for ts, ln in self.lines]
+            window = "warm-up + timed region"
         sm, smax, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -71,7 +80,7 @@ class ClockSampler:
         # under load = samples above the idle clock
         load = [x for x in sm if x > 0.5 * max(smax or [0])] or sm
         return dict(sm_mhz=statistics.median(load) if load else None, sm_max_mhz=max(smax) if smax else None,
-                    reasons=sorted(reasons), samples=len(sm))
+                    reasons=sorted(reasons), samples=len(sm), window=window)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -184,13 +193,13 @@ def run_cuda_arm(a):
     opts = [D.Options(Z, C3["levels"], C3["rmax"], C3["delta"], C3["mixing"], C3["method"]) for Z in range(1, 93)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(a.warmup):
         flush.zero_()
         res = ctx.solve_batch(opts, keep_steps=False)
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     dev_ms = 0.0
     launches = 0
     prof = {k: dict(ms=0.0, launches=0, work=0.0) for k in D.api.KERNEL_CLASSES}
@@ -207,7 +216,8 @@ def run_cuda_arm(a):
                 prof[k][f] += v[f]
     barrier()
     wall = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None
+    t_end = time.time()
+    clocks = sampler.stop(t_end - wall, t_end) if rank == 0 else None
 
     wall = max_over_ranks(wall)
     dev_s = max_over_ranks(dev_ms * 1e-3)

@@ -34,6 +34,9 @@ struct SegShared {                 // one per CTA: the results of its 4 segments
     double ct[4][32];              // the composition of this CTA's 4 segment maps (same encoding), kind in ctk
     int ctk[32];
     int meta[kSegWarps][32];       // kind (bits 0-1: 0 idle, 1 normal, 2 seeded) | sign of y at the lowest node (bit 2) | sign changes inside the segment << 3
+                                   // (written once per round, by pass 1; the scan of the other warps reads its kind bits)
+    int res[kSegWarps][32];        // normal segments: the same fields for the REAL solution, written after the scan (a separate word: no
+                                   // write into meta while another warp's scan may still be reading it)
     int bad[32];
 };
 
@@ -141,7 +144,7 @@ __device__ __forceinline__ SegRoundOut seg_round(const GridDev& g, const double*
         FastOut<1> o2;
         range_sweep<1>(g, atab, ll1, in, top, bot, sbuf + wl * 64, o2);
         if (kind == 1) {
-            sh.meta[wl][lane] = 1 | ((int)o2.prev[0] << 2) | (o2.count[0] << 3);
+            sh.res[wl][lane] = 1 | ((int)o2.prev[0] << 2) | (o2.count[0] << 3);
             if (is_bottom) { sh0->y0s[lane] = o2.Y0s[0]; sh0->d1[lane] = o2.d_first[0]; }
             if (o2.bad) atomicOr(&sh0->bad[lane], 1);
         }
@@ -153,7 +156,7 @@ __device__ __forceinline__ SegRoundOut seg_round(const GridDev& g, const double*
         const int past1 = ((ue >= 0. ? 1. : -1.) * sl * We >= 0.) ? 1 : 0;
         const int cnt = o.count[0] + past1 - past0;
         const unsigned sgn = (unsigned)hi32(We) >> 31;
-        sh.meta[wl][lane] = 1 | ((int)sgn << 2) | (cnt << 3);
+        sh.res[wl][lane] = 1 | ((int)sgn << 2) | (cnt << 3);
         if (is_bottom) { sh0->y0s[lane] = fma(A, o.Y0s[0], Bd * o.Y0s[1]); sh0->d1[lane] = o.d_first[0]; }
         if (o.bad) atomicOr(&sh0->bad[lane], 1);
     }
@@ -167,7 +170,8 @@ __device__ __forceinline__ SegRoundOut seg_round(const GridDev& g, const double*
 #pragma unroll 4
     for (int v = 0; v < S; ++v) {
         const SegShared* r = cluster.map_shared_rank(&sh, v / kSegWarps);
-        const int mv = r->meta[v % kSegWarps][lane];
+        const int mk = r->meta[v % kSegWarps][lane];
+        const int mv = (mk & 3) == 1 ? r->res[v % kSegWarps][lane] : mk;       // normal segments: the real solution's count and sign
         const double pv = r->pseg[v % kSegWarps][lane];
         if (mv & 3) { cfull += mv >> 3; pbot = (unsigned)(mv >> 2) & 1u; Ptot *= pv; have_bottom = 1; }
     }
