@@ -88,6 +88,7 @@ def load_library():
     lib.dftatom_poisson_vcycles.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, _dp, _dp, C.c_int, _dp]
     lib.dftatom_vwn.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp]
     lib.dftatom_simpson38.argtypes = [C.c_void_p, C.c_double, _dp, C.c_int, C.c_int, _dp]
+    lib.dftatom_integrate.argtypes = [C.c_void_p, C.c_int, C.c_double, _dp, C.c_int, C.c_int, _dp]
     lib.dftatom_poisson_scratch_bytes.argtypes = [C.c_int, C.c_int]
     lib.dftatom_poisson_scratch_bytes.restype = C.c_longlong
     lib.dftatom_poisson_vcycles_dev.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p,
@@ -342,6 +343,13 @@ class Context:
         rb = _f64(rho_b); va = np.zeros(n); vb = np.zeros(n)
         _check(self._lib.dftatom_vwn(self._h, n, _d(ra), _d(rb), _d(va), _d(vb), _d(vexc), _d(edif)))
         return va, vb, vexc, edif
+
+    def integrate(self, rule, step, v):
+        """Integral.h quadratures by rule: 0 Trapezoid, 1 SimpsonOneThird, 2 Simpson38, 3 Boole, 4 Romberg; one result per row of v."""
+        v = _f64(np.atleast_2d(v))
+        out = np.zeros(v.shape[0])
+        _check(self._lib.dftatom_integrate(self._h, int(rule), float(step), _d(v), v.shape[1], v.shape[0], _d(out)))
+        return out
 
     def simpson38(self, step, v):
         v = _f64(np.atleast_2d(v))

@@ -940,4 +940,23 @@ int dftatom_simpson38(dftatom_ctx* c, double step, const double* v, int n, int n
     return 0;
 }
 
+int dftatom_integrate(dftatom_ctx* c, int rule, double step, const double* v, int n, int n_rows, double* out)
+{
+    if (!c || !v || !out || n_rows <= 0 || rule < 0 || rule > 4) return DFTATOM_E_ARG;
+    // the size conditions the reference asserts (Integral.h:13, :27-28, :52-53, :77-78, :110)
+    const bool ok = (rule == 0) ? n >= 2 : (rule == 1 || rule == 2) ? (n >= 5 && (n & 1)) : (rule == 3) ? (n > 4 && n % 4 == 1) : (n >= 3 && (n & 1) && n <= (1 << 22) + 1);
+    if (!ok) { set_error("number of samples not admissible for this quadrature rule"); return DFTATOM_E_ARG; }
+    DFT_CHECK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    int rc;
+    DevBuf& d = c->scratch[0]; DevBuf& o = c->scratch[1];
+    if ((rc = d.ensure(sizeof(double) * (size_t)n * n_rows)) || (rc = o.ensure(sizeof(double) * n_rows))) return rc;
+    DFT_CHECK(cudaMemcpyAsync(d.p, v, sizeof(double) * (size_t)n * n_rows, cudaMemcpyHostToDevice, st));
+    launch_integrate(rule, step, d.as<double>(), n, n_rows, o.as<double>(), st);
+    DFT_CHECK(cudaMemcpyAsync(out, o.p, sizeof(double) * n_rows, cudaMemcpyDeviceToHost, st));
+    DFT_CHECK(cudaStreamSynchronize(st));
+    DFT_CHECK(cudaGetLastError());
+    return 0;
+}
+
 }  // extern "C"

@@ -154,6 +154,71 @@ void launch_simpson38(double step, const double* v, int n, int n_rows, double* o
     simpson38_kernel<<<n_rows, 512, 0, st>>>(step, v, n, out);
 }
 
+// The other quadratures of Integral.h as block reductions (no call site in the reference's SCF; north_star names Romberg):
+// rule 0 Trapezoid (Integral.h:11-23), 1 SimpsonOneThird (:25-48), 3 Boole (:75-104): one weighted sum; 4 Romberg (:106-155):
+// the trapezoid refinements R(i,0) need the sum of the samples that are new at level i (stride numPoints >> (i-1), offset
+// numPoints >> i) - one block reduction per level - then thread 0 runs the reference's extrapolation table and stop rule.
+__device__ __forceinline__ double rule_weight(int rule, int i, int n)
+{
+    const bool end = (i == 0 || i == n - 1);
+    if (rule == 0) return end ? 0.5 : 1.;
+    if (rule == 1) return end ? 1. : ((i & 1) ? 4. : 2.);
+    return end ? 7. : ((i & 1) ? 32. : ((i & 3) == 0 ? 14. : 12.));          // Boole
+}
+
+__global__ void __launch_bounds__(512) integrate_kernel(int rule, double step, const double* v, int n, double* out)
+{
+    __shared__ double sm[32];
+    __shared__ double lsum[64];
+    const double* row = v + (size_t)blockIdx.x * n;
+    if (rule != 4) {
+        double acc[1] = { 0. };
+        for (int i = threadIdx.x; i < n; i += blockDim.x) acc[0] = fma(rule_weight(rule, i, n), row[i], acc[0]);
+        block_sum_n<1>(acc, sm);
+        const double coef = rule == 0 ? 1. : (rule == 1 ? 1. / 3. : 2. / 45.);
+        if (threadIdx.x == 0) out[blockIdx.x] = acc[0] * step * coef;
+        return;
+    }
+    const int numPoints = n - 1;
+    int cnt = 0;
+    for (int m = numPoints; m; m >>= 1) ++cnt;
+    for (int i = 1; i < cnt; ++i) {
+        const int oldStep = numPoints >> (i - 1), m = numPoints >> i;
+        double acc[1] = { 0. };
+        if (m > 0)
+            for (long long j = m + (long long)threadIdx.x * oldStep; j < numPoints; j += (long long)blockDim.x * oldStep) acc[0] += row[j];
+        block_sum_n<1>(acc, sm);
+        if (threadIdx.x == 0) lsum[i] = acc[0];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double Rprev[24], Rcur[24];
+        for (int q = 0; q < 24; ++q) { Rprev[q] = 0.; Rcur[q] = 0.; }
+        double h = step * numPoints;
+        Rprev[0] = 0.5 * h * (row[0] + row[numPoints]);
+        double result = 0.;
+        bool done = false;
+        for (int i = 1; i < cnt && !done; ++i) {
+            h *= 0.5;
+            Rcur[0] = 0.5 * Rprev[0] + h * lsum[i];
+            double nk = 1.;
+            for (int q = 1; q <= i; ++q) {
+                nk *= 4.;
+                Rcur[q] = Rcur[q - 1] + (Rcur[q - 1] - Rprev[q - 1]) / (nk - 1.);
+            }
+            if (i >= 3 && fabs(Rcur[i] - Rprev[i - 1]) < 1e-18) { result = Rcur[i]; done = true; break; }
+            for (int q = 0; q < 24; ++q) { const double t = Rcur[q]; Rcur[q] = Rprev[q]; Rprev[q] = t; }
+        }
+        out[blockIdx.x] = done ? result : Rprev[cnt - 1];
+    }
+}
+
+void launch_integrate(int rule, double step, const double* v, int n, int n_rows, double* out, cudaStream_t st)
+{
+    if (rule == 2) simpson38_kernel<<<n_rows, 512, 0, st>>>(step, v, n, out);
+    else integrate_kernel<<<n_rows, 512, 0, st>>>(rule, step, v, n, out);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // SCF kernels, one CTA per atom
 // ---------------------------------------------------------------------------------------------------------

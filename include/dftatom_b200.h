@@ -183,6 +183,11 @@ int dftatom_vwn(dftatom_ctx* ctx, int n, const double* rho_a, const double* rho_
 /* Integral::Simpson38 (Integral.h:50-73) of n_rows rows of length n */
 int dftatom_simpson38(dftatom_ctx* ctx, double step, const double* v, int n, int n_rows, double* out);
 
+/* The whole quadrature family of Integral.h as block reductions: rule 0 Trapezoid (Integral.h:11-23), 1 SimpsonOneThird (:25-48),
+ * 2 Simpson38 (:50-73, the only one the reference's SCF calls), 3 Boole (:75-104), 4 Romberg (:106-155, err 1e-18, minSteps 3).
+ * n must satisfy the reference's assertions for the rule (odd / 4k+1 ...), else DFTATOM_E_ARG. */
+int dftatom_integrate(dftatom_ctx* ctx, int rule, double step, const double* v, int n, int n_rows, double* out);
+
 /* ---- microbenches on DEVICE-resident data (bench.py `value` legs); pointers are CUDA device addresses ---- */
 /* Stream-mode V-cycles (config C5a: many densities on a grid that does not fit on chip; levels >= 15).  n_cycles V-cycles
  * (PoissonSolver.h:155-159: 3 + 3 Gauss-Seidel sweeps per level, injection of the residual, linear prolongation) in place on

@@ -314,6 +314,68 @@ double orc_simpson38(double step, const double* v, int n)
     return ends * step * (3. / 8.);
 }
 
+/* The other quadratures of Integral.h (no call site in the reference; north_star names Romberg).  rule: 0 Trapezoid :11-23,
+ * 1 SimpsonOneThird :25-48, 2 Simpson38 :50-73, 3 Boole :75-104, 4 Romberg :106-155 (err 1e-18, minSteps 3). */
+double orc_integrate(int rule, double step, const double* v, int n)
+{
+    const int szm1 = n - 1;
+    if (rule == 0) {                                               /* :15-22 */
+        double sum = 0.5 * (v[0] + v[n - 1]);
+        for (int i = 1; i < szm1; ++i) sum += v[i];
+        return sum * step;
+    }
+    if (rule == 1) {                                               /* :30-47 */
+        double sum = v[0] + v[n - 1], sum4 = 0, sum2 = 0;
+        for (int i = 1; i < szm1; ++i) {
+            sum4 += v[i++];
+            if (i < szm1) sum2 += v[i];
+        }
+        sum += 4. * sum4 + 2. * sum2;
+        return sum * step * (1. / 3.);
+    }
+    if (rule == 2) return orc_simpson38(step, v, n);
+    if (rule == 3) {                                               /* :80-103 */
+        double sum = 7. * (v[0] + v[n - 1]), sum32 = 0, sum12 = 0, sum14 = 0;
+        for (int i = 1; i < szm1; ++i) {
+            sum32 += v[i++];
+            if (i < szm1) {
+                if (i % 4 == 0) sum14 += v[i]; else sum12 += v[i];
+            }
+        }
+        sum += 32. * sum32 + 12. * sum12 + 14. * sum14;
+        return sum * step * (2. / 45.);
+    }
+    {                                                              /* Romberg :108-154 */
+        const double err = 1E-18;
+        const int minSteps = 3;
+        const int numPoints = n - 1;
+        int m = numPoints, cnt = 0;
+        while (m) { ++cnt; m >>= 1; }
+        double Rprev[64], Rcur[64];
+        for (int i = 0; i < 64; ++i) Rprev[i] = Rcur[i] = 0;
+        double h = step * numPoints;
+        Rprev[0] = 0.5 * h * (v[0] + v[numPoints]);
+        m = numPoints;
+        for (int i = 1; i < cnt; ++i) {
+            const int oldStep = m;
+            m >>= 1;
+            double sum = 0;
+            for (int j = m; j < numPoints; j += oldStep) sum += v[j];
+            h *= 0.5;
+            Rcur[0] = 0.5 * Rprev[0] + h * sum;
+            double nk = 1;
+            for (int q = 1; q <= i; ++q) {
+                nk *= 4;
+                Rcur[q] = Rcur[q - 1] + (Rcur[q - 1] - Rprev[q - 1]) / (nk - 1);
+            }
+            if (i >= minSteps && fabs(Rcur[i] - Rprev[i - 1]) < err) return Rcur[i];
+            for (int q = 0; q < 64; ++q) { const double t = Rcur[q]; Rcur[q] = Rprev[q]; Rprev[q] = t; }     /* Rcur.swap(Rprev) */
+        }
+        return Rprev[cnt - 1];                                     /* Rprev.back() */
+    }
+}
+
+
 void orc_normalize(double* psi, int n_nodes, double rp, double delta)
 {   /* DFTAtom.cpp:36-56: y -> u = y e^{i delta/2}; integral of u^2 dr with dr = rp delta e^{delta i} di */
     double* sq = (double*)malloc(sizeof(double) * (size_t)n_nodes);

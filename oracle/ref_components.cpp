@@ -106,6 +106,19 @@ double ref_simpson38(double delta, const double* v, int n)
     return DFT::Integral::Simpson38(delta, d);
 }
 
+// Integral.h:11-155: 0 Trapezoid, 1 SimpsonOneThird, 2 Simpson38, 3 Boole, 4 Romberg
+double ref_integrate(int rule, double delta, const double* v, int n)
+{
+    std::vector<double> d(v, v + n);
+    switch (rule) {
+        case 0: return DFT::Integral::Trapezoid(delta, d);
+        case 1: return DFT::Integral::SimpsonOneThird(delta, d);
+        case 2: return DFT::Integral::Simpson38(delta, d);
+        case 3: return DFT::Integral::Boole(delta, d);
+        default: return DFT::Integral::Romberg(delta, d);
+    }
+}
+
 // AufbauPrinciple.h:36-75 + the driver's sort (DFTAtom.cpp:367); out = triples (N0, L, occ); returns count
 int ref_aufbau(int Z, int* out, int max_levels)
 {

@@ -66,6 +66,8 @@ def oracle():
         L.orc_level_search.argtypes = [_dp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, _dp, _ip]
         L.orc_simpson38.restype = C.c_double
         L.orc_simpson38.argtypes = [C.c_double, _dp, C.c_int]
+        L.orc_integrate.restype = C.c_double
+        L.orc_integrate.argtypes = [C.c_int, C.c_double, _dp, C.c_int]
         L.orc_vwn_lda.argtypes = [_dp, C.c_int, _dp, _dp]
         L.orc_vwn_lsda.argtypes = [_dp, _dp, C.c_int, _dp, _dp, _dp, _dp]
         L.orc_poisson.argtypes = [C.c_int, C.c_double, C.c_int, C.c_double, _dp, _dp, C.c_int, _dp, _ip]
@@ -95,6 +97,9 @@ def ref_components():
         L.ref_vwn_lsda.argtypes = [_dp, _dp, C.c_int, _dp, _dp, _dp, _dp]
         L.ref_simpson38.restype = C.c_double
         L.ref_simpson38.argtypes = [C.c_double, _dp, C.c_int]
+        if hasattr(L, "ref_integrate"):
+            L.ref_integrate.restype = C.c_double
+            L.ref_integrate.argtypes = [C.c_int, C.c_double, _dp, C.c_int]
         L.ref_aufbau.argtypes = [C.c_int, _ip, C.c_int]
         _ref = L
     return _ref
@@ -194,6 +199,15 @@ def vwn_lsda(ra, rb):
     va = np.zeros_like(ra); vb = np.zeros_like(ra); v = np.zeros_like(ra); e = np.zeros_like(ra)
     oracle().orc_vwn_lsda(d(ra), d(rb), len(ra), d(va), d(vb), d(v), d(e))
     return va, vb, v, e
+
+
+RULES = ("Trapezoid", "SimpsonOneThird", "Simpson38", "Boole", "Romberg")
+
+
+def integrate(rule, step, v):
+    """Integral.h:11-155 by rule index (see RULES)."""
+    v = np.ascontiguousarray(v, np.float64)
+    return oracle().orc_integrate(int(rule), float(step), d(v), len(v))
 
 
 def simpson38(step, v):

@@ -226,3 +226,19 @@ def test_simpson38_matches_oracle(ctx):
         out = ctx.simpson38(0.7, v)
         ref = np.array([O.simpson38(0.7, row) for row in v])
         np.testing.assert_allclose(out, ref, rtol=0, atol=1e-12 * np.sqrt(n))
+
+
+def test_quadrature_family_matches_oracle(ctx):
+    """dftatom_integrate: every rule of Integral.h as a block reduction against the oracle (summation order differs: 1e-13)."""
+    rng = np.random.default_rng(2)
+    for n in (5, 17, 129, 1025, 16385, 131073):
+        v = rng.standard_normal((3, n))
+        for rule in range(5):
+            out = ctx.integrate(rule, 0.7, v)
+            ref = np.array([O.integrate(rule, 0.7, row) for row in v])
+            np.testing.assert_allclose(out, ref, rtol=0, atol=2e-13 * np.sqrt(n) * 32)
+    x = np.linspace(0.0, 5.0, 16385)
+    assert abs(ctx.integrate(4, x[1] - x[0], np.exp(-x))[0] - (1 - np.exp(-5.0))) < 1e-14
+    with pytest.raises(Exception):
+        ctx.integrate(3, 0.1, np.zeros(7))          # Boole needs 4k + 1 samples (Integral.h:78)
+
