@@ -269,7 +269,16 @@ def run_cuda_arm(a):
         )
         if strong:
             line["strong_c3"] = strong
-        if world == 1 and not a.no_batch:
+        # The legs below are extras beside the headline line: a failure in one of them (e.g. the 50 GiB of the C5a leg not being
+        # available) is recorded under its key and must not cost the line itself.
+        def leg(key, fn):
+            try:
+                line[key] = fn()
+            except Exception as e:          # noqa: BLE001
+                line[key] = dict(error=f"{type(e).__name__}: {e}")
+                torch.cuda.empty_cache()
+
+        def leg_batch():
             # the same sweep replicated 8x in ONE batch (736 atoms): C3 as given is bounded by the SCF chain of its slowest atoms
             # (from step ~35 on fewer than 30 atoms are left), a larger batch shows what the kernels sustain when the GPU is full
             big = opts * 8
@@ -278,9 +287,10 @@ def run_cuda_arm(a):
             t1 = time.perf_counter()
             ctx.solve_batch(big, keep_steps=False)
             tb = time.perf_counter() - t1
-            line["batch_8xC3"] = dict(value=len(big) / tb, unit="atoms/s", atoms=len(big), seconds=tb, device_ms=ctx.last_timing()[0],
-                                      note="8 copies of the Z=1-92 sweep in one dftatom_solve_batch call, host options in, host results out")
-        if world == 1 and not a.no_rn:
+            return dict(value=len(big) / tb, unit="atoms/s", atoms=len(big), seconds=tb, device_ms=ctx.last_timing()[0],
+                        note="8 copies of the Z=1-92 sweep in one dftatom_solve_batch call, host options in, host results out")
+
+        def leg_rn():
             # second half of BASELINE.json's metric: wall-ms of one Radon SCF (C2: Z=86 LSDA, 17 levels = 131073 nodes, delta 1e-4,
             # mixing 0.5, Rmax 50) through the same public call, host options in, host results out; warm-up run first
             rn = [D.Options(86, 17, 50.0, 0.0001, 0.5, 1)]
@@ -289,16 +299,24 @@ def run_cuda_arm(a):
             t1 = time.perf_counter()
             r_rn = ctx.solve_batch(rn, keep_steps=False)[0]
             rn_ms = (time.perf_counter() - t1) * 1e3
-            line["rn_scf"] = dict(metric="Rn SCF ms", value=rn_ms, unit="ms", device_ms=ctx.last_timing()[0], scf_steps=r_rn.n_steps, finished=bool(r_rn.finished),
-                                  Etotal=r_rn.Etotal, workload="C2 Radon Z=86 LSDA, 17 levels (131073 nodes), delta 0.0001, mixing 0.5, Rmax 50",
-                                  reference_cpu_seconds_1core=518.0, reference_source="SURVEY.md section 6 (unmodified reference, g++ -O2, one core)")
+            return dict(metric="Rn SCF ms", value=rn_ms, unit="ms", device_ms=ctx.last_timing()[0], scf_steps=r_rn.n_steps, finished=bool(r_rn.finished),
+                        Etotal=r_rn.Etotal, workload="C2 Radon Z=86 LSDA, 17 levels (131073 nodes), delta 0.0001, mixing 0.5, Rmax 50",
+                        reference_cpu_seconds_1core=518.0, reference_source="SURVEY.md section 6 (unmodified reference, g++ -O2, one core)")
+
+        def leg_cpu():
+            cb = cpu_reference_sample(30.0)
+            return {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+        if world == 1 and not a.no_batch:
+            leg("batch_8xC3", leg_batch)
+        if world == 1 and not a.no_rn:
+            leg("rn_scf", leg_rn)
         if world == 1 and not a.no_micro:
             # BASELINE.json configs[4]: the two kernels at scale, each against its own roofline
-            line["c5b_numerov_lanes"] = micro_c5b(ctx, peak, cpu_baseline=not a.no_cpu_baseline)
-            line["c5a_poisson_vcycle"] = micro_c5a(ctx, torch, _hbm_peak(), n_dens=a.micro_densities, cpu_baseline=not a.no_cpu_baseline)
+            leg("c5b_numerov_lanes", lambda: micro_c5b(ctx, peak, cpu_baseline=not a.no_cpu_baseline))
+            leg("c5a_poisson_vcycle", lambda: micro_c5a(ctx, torch, _hbm_peak(), n_dens=a.micro_densities, cpu_baseline=not a.no_cpu_baseline))
         if world == 1 and not a.no_cpu_baseline:
-            cb = cpu_reference_sample(30.0)
-            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            leg("cpu_baseline", leg_cpu)
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
