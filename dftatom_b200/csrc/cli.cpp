@@ -5,6 +5,7 @@
 //
 //   dftatom [--Z 18 | --Z 1-92 | --Z 21,22,57] [--levels 14] [--delta 0.0005] [--mixing 0.5] [--rmax 25]
 //           [--method 0|1|lda|lsda] [--precision 6] [--json] [--quiet-steps] [--device 0] [--ini DFTAtom.ini]
+// --json: one record per atom (final energies, levels, and - unless --quiet-steps - every step at 17 digits)
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -115,7 +116,21 @@ int main(int argc, char** argv)
                     std::printf("%s{\"spin\":%d,\"n\":%d,\"l\":%d,\"occ\":%d,\"nodes\":%d,\"E\":%.17g}", first ? "" : ",", s, L.n, L.l, L.occ, L.nodes, L.E);
                     first = false;
                 }
-            std::printf("]}");
+            std::printf("]");
+            if (!quiet) {       // every "Step:" block of the reference's log, full precision
+                std::printf(",\"steps\":[");
+                for (int sp = 0; sp < R.n_steps; ++sp) {
+                    const dftatom_step& S = steps[(size_t)a * stride + sp];
+                    std::printf("%s{\"Etotal\":%.17g,\"Ekin\":%.17g,\"Ecoul\":%.17g,\"Eenuc\":%.17g,\"Exc\":%.17g,\"E\":[", sp ? "," : "", S.Etotal, S.Ekin, S.Ecoul,
+                                S.Eenuc, S.Exc);
+                    bool f1 = true;
+                    for (int s2 = 0; s2 < R.n_spin; ++s2)
+                        for (int k = 0; k < R.n_levels[s2]; ++k) { std::printf("%s%.17g", f1 ? "" : ",", S.E[s2][k]); f1 = false; }
+                    std::printf("]}");
+                }
+                std::printf("]");
+            }
+            std::printf("}");
             continue;
         }
         std::printf("Computing atom with Z=%d using %s with non-uniform grid\n", opts[a].Z, opts[a].method ? "LSDA" : "LSD");   // DFTAtom.cpp:358,857

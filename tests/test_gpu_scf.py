@@ -233,6 +233,8 @@ def test_cli_text_matches_reference(tmp_path):
     assert subprocess.run([exe, "--ini", str(ini)], capture_output=True, text=True, check=True).stdout == out
     js = json.loads(subprocess.run([exe, "--ini", str(ini), "--json"], capture_output=True, text=True, check=True).stdout)
     assert js[0]["Z"] == 10 and js[0]["status"] == 0 and abs(js[0]["Etotal"] - ref["steps"][-1]["Etotal"]) < 1e-9
+    assert len(js[0]["steps"]) == js[0]["n_steps"] and abs(js[0]["steps"][3]["Ecoul"] - ref["steps"][3]["Ecoul"]) < 1e-9
+    assert len(js[0]["steps"][0]["E"]) == 3
     bad = subprocess.run([exe, "--Z", "10", "--levels", "30"], capture_output=True, text=True)
     assert bad.returncode == 1 and "levels" in bad.stderr
 
