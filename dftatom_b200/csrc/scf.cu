@@ -275,8 +275,9 @@ __global__ void __launch_bounds__(256) orbital_norm_kernel(GridDev g, ScfBuffers
 
 // New density and mixing (DFTAtom.cpp:558-559, :332-342).  grid = (atoms, node_chunks(N)): every CTA owns a contiguous range of
 // nodes of one atom (the nodes are independent), so a handful of atoms still fills the GPU.
-// node ranges per atom: 8 up to 16385 nodes, one per 2048 nodes above (gridDim.y)
-__host__ __device__ inline int node_chunks(int N) { const int c = (N + 2047) / 2048; return c < 8 ? 8 : (c > 64 ? 64 : c); }
+// node ranges per atom (gridDim.y): one per 512 nodes, 8..64 - both kernels are latency chains of loads per thread, and from the
+// middle of a batch on only a few atoms are left, so short ranges on many SMs beat long ones on few
+__host__ __device__ inline int node_chunks(int N) { const int c = (N + 511) / 512; return c < 8 ? 8 : (c > 64 ? 64 : c); }
 constexpr int kDT = 256;
 __global__ void __launch_bounds__(kDT) density_update_kernel(GridDev g, ScfBuffers b)
 {
