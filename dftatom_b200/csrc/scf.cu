@@ -416,14 +416,17 @@ __global__ void __launch_bounds__(kPT2) potential_energy_kernel(GridDev g, Poiss
     }
     __syncthreads();
     if (!is_last) return;
-    if (threadIdx.x == 0) {
+    // the CTA that finished last adds the partial sums in range order (deterministic): one thread per integral, loads from L2
+    if (threadIdx.x < 5) {
         __threadfence();
-        const volatile double* part = b.epart + (size_t)a * kPotChunks * 5;
-        for (int q = 0; q < 5; ++q) {
-            double t = 0.;
-            for (int c = 0; c < kPotChunks; ++c) t += part[c * 5 + q];
-            e[q] = t;
-        }
+        const double* part = b.epart + (size_t)a * kPotChunks * 5 + threadIdx.x;
+        double t = 0.;
+        for (int c = 0; c < kPotChunks; ++c) t += __ldcg(part + c * 5);
+        sm[threadIdx.x] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int q = 0; q < 5; ++q) e[q] = sm[q];
         dftatom_step* rec = b.steps + (size_t)a * b.steps_stride + as.n_steps;
         const double eel = rec->Ekin;                      // parked by density_update_kernel
         const double e_nuc = -kFourPi * e[0];              // DFTAtom.cpp:459-470
