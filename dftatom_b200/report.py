@@ -12,7 +12,7 @@ SEP = "*" * 80
 
 _E_RE = re.compile(r"^Energy (?:alpha |beta )?(\d+)([spdf]): (\S+) Num nodes: (-?\d+)$")
 _T_RE = re.compile(r"^Etotal = (\S+) Ekin = (\S+) Ecoul = (\S+) Eenuc = (\S+) Exc = (\S+)$")
-_H_RE = re.compile(r"^Computing atom with Z=(\d+) using (LSDA|LSD) with non-uniform grid$")
+_H_RE = re.compile(r"^Computing atom with Z=(\d+) using (LSDA|LSD|LDA) with (non-uniform|uniform) grid$")
 _C_RE = re.compile(r"(\d+)([spdf])(\d+)")
 
 
@@ -26,6 +26,7 @@ def parse_report(text):
         if m:
             rec["Z"] = int(m.group(1))
             rec["method"] = 1 if m.group(2) == "LSDA" else 0
+            rec["grid"] = m.group(3)          # "uniform": the CalculateUniform* pair (DFTAtom.cpp:69, :655), levels tagged alpha / beta
             continue
         if line.startswith("Step: "):
             cur = dict(step=int(line[6:]), levels=[])

@@ -3,7 +3,8 @@
 // they lie (never copied into this repo).  Output: oracle/_ref/dftatom_ref (git-ignored).
 // Replaces the wx worker-thread lambda of DFTAtomFrame.cpp:185-198 (the only caller of the solver).
 //
-// usage: dftatom_ref Z levels mixing rmax delta method(0=LDA,1=LSDA)
+// usage: dftatom_ref Z levels mixing rmax delta method(0=LDA,1=LSDA on the logarithmic grid - the product's only path,
+//        DFTAtomFrame.cpp:190-195; 2=LDA, 3=LSDA on the uniform grid, DFTAtom.h:15,18: public but without a live caller, delta unused)
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -24,7 +25,9 @@ int main(int argc, char** argv)
     const double rmax = std::atof(argv[4]);
     const double delta = std::atof(argv[5]);
     const int method = std::atoi(argv[6]);
-    if (method) DFT::DFTAtom::CalculateNonUniformLSDA(Z, levels, mixing, rmax, delta);
+    if (method == 3) DFT::DFTAtom::CalculateUniformLSDA(Z, levels, mixing, rmax);
+    else if (method == 2) DFT::DFTAtom::CalculateUniformLDA(Z, levels, mixing, rmax);
+    else if (method) DFT::DFTAtom::CalculateNonUniformLSDA(Z, levels, mixing, rmax, delta);
     else DFT::DFTAtom::CalculateNonUniformLDA(Z, levels, mixing, rmax, delta);
     std::printf("\n");
     return 0;

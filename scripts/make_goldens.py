@@ -3,7 +3,7 @@
 oracle/Makefile from /root/reference) and parsing its stdout.  Test infrastructure only.
 
 usage: python scripts/make_goldens.py NAME [--jobs J]
-  NAME in: small, argon, radon, sweep, lsda_batch
+  NAME in: small, argon, radon, sweep, lsda_batch, uniform
 Writes tests/golden/<NAME>.json.  Each atom record holds every SCF step the reference printed
 (eigenvalues + five energies, 17 significant digits) unless --final-only semantics apply (sweep,
 lsda_batch keep per-step Etotal and eigenvalues of the last step only, to keep fixtures small).
@@ -35,6 +35,9 @@ CONFIGS = {
     "sweep": [dict(Z=z, **C1) for z in range(1, 93)],
     "lsda_batch": [dict(Z=z, levels=16, mixing=0.5, rmax=50.0, delta=0.0002, method=1)
                    for z in list(range(21, 31)) + list(range(57, 72))],
+    # the uniform-grid pair (DFTAtom.h:15,18; no live caller): method 2 = LDA, 3 = LSDA in dftatom_ref; delta unused
+    "uniform": [dict(Z=z, levels=lv, mixing=0.5, rmax=15.0, delta=0.0, method=m)
+                for z, lv, m in [(1, 12, 3), (2, 12, 2), (2, 14, 2), (7, 12, 3), (10, 12, 2), (10, 12, 3), (18, 13, 2)]],
 }
 FINAL_ONLY = {"sweep", "lsda_batch"}
 
