@@ -872,6 +872,324 @@ int orc_scf_ex(const orc_options* opt, orc_result* res, orc_step_cb cb, void* us
     return 0;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * The uniform-grid pair: CalculateUniformLDA DFTAtom.cpp:60-210, CalculateUniformLSDA :646-844,
+ * LoopOverLevels :213-284, LocateInterval :287-325, NormalizeUniform :21-32, Numerov<NumerovFunctionRegularGrid>
+ * (Numerov.h:16-70 function object, :272-504 sweeps, IsUniform() branches), SolvePoissonUniform PoissonSolver.h:20-49.
+ * Public API of the reference without a live caller; restated here ahead of its kernels and pinned digit for digit on
+ * tests/golden/uniform.json (generated by the unmodified reference, oracle/_ref/dftatom_ref methods 2 / 3).
+ * ---------------------------------------------------------------------------------------------- */
+
+static double uf_veff(const double* V, int l, double pos, long i) { return V[i] + l * (l + 1.) / (pos * pos) * 0.5; }   /* Numerov.h:21-24 */
+static double uf_f(const double* V, int l, double E, double pos, long i) { return 2. * (uf_veff(V, l, pos, i) - E); }   /* :26-31 */
+static double uf_far(double pos, double E) { return exp(-pos * sqrt(2. * fabs(E))); }                                   /* :33-36 */
+static double uf_near(double pos, int l) { return pow(pos, (double)l + 1.); }                                           /* :38-41 */
+static double uf_maxr(double E) { return 200. / sqrt(2. * fabs(E)); }                                                   /* :53-56 */
+
+int orc_u_count_nodes(const double* V, double start_point, int l, double E, long steps, int limit)
+{   /* Numerov.h:272-349, IsUniform() branch */
+    const double h = start_point / steps, h2 = h * h, h2p12 = h2 / 12.;
+    start_point = fmin(start_point, uf_maxr(E));
+    steps = (long)(start_point / h);
+    double position = start_point;
+    double solution = uf_far(position, E);
+    double prev = solution;
+    double f = uf_f(V, l, E, position, steps);
+    double wprev = (1 - h2p12 * f) * solution;
+    position -= h;
+    solution = uf_far(position, E);
+    f = uf_f(V, l, E, position, steps - 1);
+    double w = (1 - h2p12 * f) * solution;
+    int old_sign = solution > 0, count = 0, seen_allowed = 0;
+    for (long i = steps - 2; i > 0; --i) {
+        const double wnext = 2. * w - wprev + h2 * solution * f;
+        position = h * i;
+        wprev = w; w = wnext;
+        f = uf_f(V, l, E, position, i);
+        prev = solution;
+        solution = w / (1. - h2p12 * f);
+        if (fabs(solution) == INFINITY) return count;
+        if ((solution > 0) != old_sign) {
+            if (++count > limit) return count;
+            old_sign = !old_sign;
+        }
+        const double veff = uf_veff(V, l, position, i);
+        if (veff <= E) seen_allowed = 1;
+        else if (seen_allowed) return count;
+    }
+    if (count <= limit) {
+        solution = solution * (2 + h2 * f) - prev;
+        if ((solution > 0) != old_sign) ++count;
+    }
+    return count;
+}
+
+double orc_u_y0(const double* V, double start_point, int l, double E, long steps)
+{   /* Numerov.h:351-401, IsUniform() branch */
+    const double h = start_point / steps, h2 = h * h, h2p12 = h2 / 12.;
+    start_point = fmin(start_point, uf_maxr(E));
+    steps = (long)(start_point / h);
+    double position = start_point;
+    double solution = uf_far(position, E);
+    double prev = solution;
+    double f = uf_f(V, l, E, position, steps);
+    double wprev = (1 - h2p12 * f) * solution;
+    position -= h;
+    solution = uf_far(position, E);
+    f = uf_f(V, l, E, position, steps - 1);
+    double w = (1 - h2p12 * f) * solution;
+    for (long i = steps - 2; i > 0; --i) {
+        const double wnext = 2. * w - wprev + h2 * solution * f;
+        position = h * i;
+        wprev = w; w = wnext;
+        f = uf_f(V, l, E, position, i);
+        prev = solution;
+        solution = w / (1. - h2p12 * f);
+    }
+    return solution * (2 + h2 * f) - prev;
+}
+
+long orc_u_match(const double* V, double start_point, int l, double E, long steps, double* psi)
+{   /* Numerov.h:403-504, IsUniform() branch, including the re-computation of h from the truncated range (:430-432) */
+    const long high = steps + 1;
+    double h = start_point / steps, h2, h2p12;
+    start_point = fmin(start_point, uf_maxr(E));
+    steps = (long)(start_point / h);
+    for (long i = steps + 1; i < high; ++i) psi[i] = 0;
+    h = start_point / steps;
+    h2 = h * h;
+    h2p12 = h2 / 12.;
+    const long size = steps + 1;
+    double position = start_point;
+    double solution = uf_far(position, E);
+    psi[steps] = solution;
+    double f = uf_f(V, l, E, position, steps);
+    double wprev = (1 - h2p12 * f) * solution;
+    position -= h;
+    psi[steps - 1] = solution = uf_far(position, E);
+    f = uf_f(V, l, E, position, steps - 1);
+    double w = (1 - h2p12 * f) * solution;
+    long match = 2;
+    for (long i = steps - 2; i > 0; --i) {
+        const double wnext = 2. * w - wprev + h2 * solution * f;
+        position = h * i;
+        wprev = w; w = wnext;
+        f = uf_f(V, l, E, position, i);
+        psi[i] = solution = w / (1. - h2p12 * f);
+        if (solution < psi[i + 1] || fabs(solution) > 1E15) { match = i; break; }
+    }
+    position = 0;
+    psi[0] = solution = 0;
+    wprev = 0;
+    position += h;
+    psi[1] = solution = uf_near(position, l);
+    f = uf_f(V, l, E, position, 1);
+    w = (1 - h2p12 * f) * solution;
+    for (long i = 2; i < match; ++i) {
+        const double wnext = 2. * w - wprev + h2 * solution * f;
+        position = h * i;
+        wprev = w; w = wnext;
+        f = uf_f(V, l, E, position, i);
+        psi[i] = solution = w / (1. - h2p12 * f);
+    }
+    w = 2. * w - wprev + h2 * solution * f;
+    position = h * match;
+    f = uf_f(V, l, E, position, match);
+    solution = w / (1. - h2p12 * f);
+    const double factor = solution / psi[match];
+    psi[match] = solution;
+    for (long i = match + 1; i < size; ++i) psi[i] *= factor;
+    return match;
+}
+
+void orc_poisson_uniform(int levels, int Z, double max_r, const double* rho, double* U, int max_vcycles)
+{   /* SolvePoissonUniform, PoissonSolver.h:20-49 (constructor with dGrid = 0: no first-derivative term) */
+    mgrid* m = mg_new(levels, 0.);
+    const int n = m->size[0];
+    double* S = m->src[0];
+    const size_t N = (size_t)n - 1;
+    for (size_t i = 0; i < (size_t)n; ++i) S[i] = (0. * (N - i) + max_r * i) / N;      /* FillR, PoissonSolver.cpp:199-209 */
+    const double delta = S[1] - S[0];
+    const double c = (delta * delta) * FOUR_PI;
+    for (int i = 0; i < n; ++i) S[i] *= c * rho[i];
+    m->lo_bc = 0; m->hi_bc = Z;
+    mg_full_cycle(m, 1E-3, 1E-14, max_vcycles, NULL);
+    memcpy(U, m->phi[0], sizeof(double) * (size_t)n);
+    mg_free(m);
+}
+
+/* LoopOverLevels :213-284 (with LocateInterval :287-325 and NormalizeUniform :21-32) + the mixing loop of the drivers */
+static void spin_channel_density_uniform(const double* V, int n, double max_r, double h, double mixing, orc_level* lv, int n_lv, double Z,
+                                         double* rho, double* acc, double* psi, double* sq, double* e_el, int* all_converged)
+{
+    const double tol = 1E-12;
+    const long n_steps = n - 1;
+    double bottom = -Z * Z - 1.;
+    memset(acc, 0, sizeof(double) * (size_t)n);
+    for (int k = 0; k < n_lv; ++k) {
+        const int l = lv[k].l, want = lv[k].n0 - l;
+        double top = 50;
+        double hi = top, lo = bottom;                               /* LocateInterval */
+        while (hi - lo > tol) {
+            const double E = (hi + lo) / 2;
+            if (orc_u_count_nodes(V, max_r, l, E, n_steps, want) > want) hi = E; else lo = E;
+        }
+        top = hi;
+        lo = bottom;
+        while (hi - lo > tol) {
+            const double E = (hi + lo) / 2;
+            if (orc_u_count_nodes(V, max_r, l, E, n_steps, want) < want) lo = E; else hi = E;
+        }
+        bottom = hi;
+        double y0 = orc_u_y0(V, max_r, l, bottom, n_steps);         /* :234-254 */
+        const int sign_bottom = y0 > 0;
+        int ok = 0;
+        double E = bottom;
+        for (int it = 0; it < 500; ++it) {
+            E = (top + bottom) / 2;
+            y0 = orc_u_y0(V, max_r, l, E, n_steps);
+            if ((y0 > 0) == sign_bottom) bottom = E; else top = E;
+            const double a = fabs(y0);
+            if (top - bottom < tol && !isnan(a) && a < 1E15) { ok = 1; break; }
+        }
+        lv[k].E = bottom;                                           /* :255 */
+        if (!ok) *all_converged = 0;
+        bottom = lv[k].E - 3;                                       /* :262 */
+        orc_u_match(V, max_r, l, lv[k].E, n_steps, psi);            /* :266 */
+        for (int i = 0; i < n; ++i) sq[i] = psi[i] * psi[i];        /* NormalizeUniform */
+        const double unorm = 1. / sqrt(orc_simpson38(h, sq, n));
+        for (int i = 0; i < n; ++i) psi[i] *= unorm;
+        for (int i = 0; i < n - 1; ++i) acc[i] += lv[k].occ * psi[i] * psi[i];    /* :279-280 */
+        *e_el += lv[k].occ * lv[k].E;
+    }
+    const double keep = mixing, take = 1. - mixing;
+    for (int i = 1; i < n; ++i) {                                   /* :127-137 / :713-718 */
+        const double position = i * h;
+        acc[i] /= FOUR_PI * position * position;
+        rho[i] = keep * rho[i] + take * acc[i];
+    }
+}
+
+/* opt->method: 2 = CalculateUniformLDA, 3 = CalculateUniformLSDA; opt->delta is not used */
+int orc_scf_uniform(const orc_options* opt, orc_result* res, orc_step_cb cb, void* user, int max_vcycles)
+{
+    const int Z = opt->Z, lsda = opt->method == 3;
+    const int n = orc_n_nodes(opt->levels);
+    const double max_r = opt->max_r;
+    const double h = max_r / (n - 1);
+
+    orc_level all[ORC_MAX_LEVELS];
+    const int n_all = orc_aufbau(Z, all);
+    orc_level lv[2][ORC_MAX_LEVELS];
+    int n_lv[2] = { n_all, 0 };
+    int n_el[2] = { Z, 0 };
+    if (lsda) orc_split_spin(Z, all, n_all, lv[0], &n_lv[0], lv[1], &n_lv[1], &n_el[0], &n_el[1]);
+    else memcpy(lv[0], all, sizeof(orc_level) * (size_t)n_all);
+    const int n_spin = lsda ? 2 : 1;
+
+    const size_t bytes = sizeof(double) * (size_t)n;
+    double* rho_s[2] = { (double*)calloc(1, bytes), (double*)calloc(1, bytes) };
+    double* rho = lsda ? (double*)calloc(1, bytes) : rho_s[0];
+    double* V[2] = { (double*)calloc(1, bytes), (double*)calloc(1, bytes) };
+    double* vxc_s[2] = { (double*)calloc(1, bytes), (double*)calloc(1, bytes) };
+    double* U = (double*)calloc(1, bytes), *vexc = (double*)calloc(1, bytes), *edif = (double*)calloc(1, bytes);
+    double* acc = (double*)calloc(1, bytes), *psi = (double*)calloc(1, bytes), *sq = (double*)calloc(1, bytes);
+    double* g_nuc = (double*)calloc(1, bytes), *g_xc = (double*)calloc(1, bytes), *g_dif = (double*)calloc(1, bytes);
+    double* g_har = (double*)calloc(1, bytes), *g_pot = (double*)calloc(1, bytes);
+
+    const double volume = 4. / 3. * M_PI * max_r * max_r * max_r;   /* :83 / :671 */
+    if (lsda) {
+        const double ca = n_el[0] / volume, cbeta = n_el[1] / volume;
+        for (int i = 1; i < n; ++i) { rho_s[0][i] = ca; rho_s[1][i] = cbeta; rho[i] = ca + cbeta; }
+    } else {
+        const double c = Z / volume;
+        for (int i = 1; i < n; ++i) rho[i] = c;
+    }
+    orc_poisson_uniform(opt->levels, Z, max_r, rho, U, max_vcycles);
+    if (lsda) orc_vwn_lsda(rho_s[0], rho_s[1], n, vxc_s[0], vxc_s[1], vexc, edif);
+    else orc_vwn_lda(rho, n, vexc, edif);
+    for (int i = 1; i < n; ++i) {                                   /* :97-102 / :688-695 */
+        const double pos = h * i;
+        if (lsda) { const double uc = (-Z + U[i]) / pos; V[0][i] = uc + vxc_s[0][i]; V[1][i] = uc + vxc_s[1][i]; }
+        else V[0][i] = (-Z + U[i]) / pos + vexc[i];
+    }
+
+    const int max_steps = lsda ? 150 : 100;                         /* :106 / :699 */
+    double e_old = 0;
+    int prev_ok = 0;
+    memset(res, 0, sizeof(*res));
+    orc_step st;
+    for (int sp = 0; sp < max_steps; ++sp) {
+        memset(&st, 0, sizeof(st));
+        st.step = sp;
+        double e_el = 0;
+        int ok = 1;
+        for (int s = 0; s < n_spin; ++s)
+            spin_channel_density_uniform(V[s], n, max_r, h, opt->mixing, lv[s], n_lv[s], (double)Z, rho_s[s], acc, psi, sq, &e_el, &ok);
+        if (lsda) for (int i = 1; i < n; ++i) rho[i] = rho_s[0][i] + rho_s[1][i];
+
+        orc_poisson_uniform(opt->levels, Z, max_r, rho, U, max_vcycles);
+        if (lsda) orc_vwn_lsda(rho_s[0], rho_s[1], n, vxc_s[0], vxc_s[1], vexc, edif);
+        else orc_vwn_lda(rho, n, vexc, edif);
+
+        g_nuc[0] = g_xc[0] = g_dif[0] = g_har[0] = g_pot[0] = 0;
+        V[0][0] = V[1][0] = 0;
+        for (int i = 1; i < n; ++i) {
+            const double position = i * h;
+            if (!lsda) {                                            /* :160-180 */
+                V[0][i] = (-Z + U[i]) / position + vexc[i];
+                const double pd = position * rho[i];
+                g_nuc[i] = Z * pd;
+                const double p2d = position * position * rho[i];
+                g_xc[i] = p2d * vexc[i];
+                g_dif[i] = p2d * edif[i];
+                g_har[i] = pd * U[i];
+                g_pot[i] = p2d * V[0][i];
+            } else {                                                /* :786-806 */
+                const double uc = (-Z + U[i]) / position;
+                V[0][i] = uc + vxc_s[0][i];
+                V[1][i] = uc + vxc_s[1][i];
+                const double pd = position * rho[i];
+                g_nuc[i] = Z * pd;
+                const double p2 = position * position;
+                const double p2d = p2 * rho[i];
+                g_xc[i] = p2d * vexc[i];
+                g_dif[i] = p2d * edif[i];
+                g_har[i] = pd * U[i];
+                g_pot[i] = p2 * (rho_s[0][i] * V[0][i] + rho_s[1][i] * V[1][i]);
+            }
+        }
+        const double e_nuc = -FOUR_PI * orc_simpson38(h, g_nuc, n);     /* :182-194 */
+        double e_xc = 4 * M_PI * orc_simpson38(h, g_xc, n);
+        const double e_dif = FOUR_PI * orc_simpson38(h, g_dif, n);
+        e_xc += e_dif;
+        const double e_har = -2 * M_PI * orc_simpson38(h, g_har, n);
+        const double e_pot = FOUR_PI * orc_simpson38(h, g_pot, n);
+        st.Ekin = e_el - e_pot;
+        st.Etotal = e_el + e_har + e_dif;
+        st.Ecoul = -e_har;
+        st.Eenuc = e_nuc;
+        st.Exc = e_xc;
+        st.level_search_converged = ok;
+        for (int s = 0; s < n_spin; ++s) { st.n_levels[s] = n_lv[s]; memcpy(st.lv[s], lv[s], sizeof(orc_level) * (size_t)n_lv[s]); }
+        if (cb) cb(&st, user);
+        res->n_steps = sp + 1;
+        if (fabs((e_old - st.Etotal) / st.Etotal) < 1E-11 && ok && prev_ok) { res->finished = 1; break; }   /* :198-203 */
+        e_old = st.Etotal;
+        prev_ok = ok;
+    }
+    res->last = st;
+    for (int s = 0; s < n_spin; ++s) {
+        res->n_sorted[s] = n_lv[s];
+        memcpy(res->sorted[s], lv[s], sizeof(orc_level) * (size_t)n_lv[s]);
+        sort_levels_by_energy(res->sorted[s], n_lv[s]);
+    }
+    free(rho_s[0]); free(rho_s[1]); if (lsda) free(rho);
+    free(V[0]); free(V[1]); free(vxc_s[0]); free(vxc_s[1]); free(U); free(vexc); free(edif); free(acc); free(psi); free(sq);
+    free(g_nuc); free(g_xc); free(g_dif); free(g_har); free(g_pot);
+    return 0;
+}
+
 /* ---- text report, same line formats as the reference (DFTAtom.cpp:358,398,548-556,472,476,483,487-490) ---- */
 
 typedef struct { int precision; int last_step_printed; int pending_sep; } print_ctx;

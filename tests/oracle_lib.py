@@ -74,6 +74,7 @@ def oracle():
         L.orc_poisson_vcycles.restype = C.c_double
         L.orc_poisson_vcycles.argtypes = [C.c_int, C.c_double, _dp, _dp, C.c_int]
         L.orc_scf.argtypes = [C.POINTER(OrcOptions), C.POINTER(OrcResult), STEP_CB, C.c_void_p, C.c_int]
+        L.orc_scf_uniform.argtypes = [C.POINTER(OrcOptions), C.POINTER(OrcResult), STEP_CB, C.c_void_p, C.c_int]
         _orc = L
     return _orc
 
@@ -228,7 +229,10 @@ def scf(Z, levels, mixing, max_r, delta, method, max_vcycles=100):
 
     o = OrcOptions(Z, levels, max_r, delta, mixing, method)
     r = OrcResult()
-    oracle().orc_scf(C.byref(o), C.byref(r), STEP_CB(cb), None, max_vcycles)
-    nsp = 2 if method else 1
+    if method in (2, 3):        # the uniform-grid pair (CalculateUniformLDA / LSDA)
+        oracle().orc_scf_uniform(C.byref(o), C.byref(r), STEP_CB(cb), None, max_vcycles)
+    else:
+        oracle().orc_scf(C.byref(o), C.byref(r), STEP_CB(cb), None, max_vcycles)
+    nsp = 2 if method in (1, 3) else 1
     return dict(steps=steps, finished=bool(r.finished), n_steps=r.n_steps,
                 sorted=[[(r.sorted[sp][k].n0 + 1, r.sorted[sp][k].l, r.sorted[sp][k].occ) for k in range(r.n_sorted[sp])] for sp in range(nsp)])
