@@ -88,6 +88,7 @@ def load_library():
     lib.dftatom_poisson_vcycles.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, _dp, _dp, C.c_int, _dp]
     lib.dftatom_vwn.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp]
     lib.dftatom_simpson38.argtypes = [C.c_void_p, C.c_double, _dp, C.c_int, C.c_int, _dp]
+    lib.dftatom_xc_lda.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp]
     lib.dftatom_integrate.argtypes = [C.c_void_p, C.c_int, C.c_double, _dp, C.c_int, C.c_int, _dp]
     lib.dftatom_poisson_scratch_bytes.argtypes = [C.c_int, C.c_int]
     lib.dftatom_poisson_scratch_bytes.restype = C.c_longlong
@@ -343,6 +344,13 @@ class Context:
         rb = _f64(rho_b); va = np.zeros(n); vb = np.zeros(n)
         _check(self._lib.dftatom_vwn(self._h, n, _d(ra), _d(rb), _d(va), _d(vb), _d(vexc), _d(edif)))
         return va, vb, vexc, edif
+
+    def xc_lda(self, functional, rho):
+        """(Vexc, eps_xc - Vexc) by functional: 0 VWN, 1 Chachiyo, 2 Chachiyo improved (ExcCor.h:27-95)."""
+        r = _f64(rho); n = len(r)
+        vexc = np.zeros(n); edif = np.zeros(n)
+        _check(self._lib.dftatom_xc_lda(self._h, int(functional), n, _d(r), _d(vexc), _d(edif)))
+        return vexc, edif
 
     def integrate(self, rule, step, v):
         """Integral.h quadratures by rule: 0 Trapezoid, 1 SimpsonOneThird, 2 Simpson38, 3 Boole, 4 Romberg; one result per row of v."""

@@ -940,6 +940,25 @@ int dftatom_simpson38(dftatom_ctx* c, double step, const double* v, int n, int n
     return 0;
 }
 
+int dftatom_xc_lda(dftatom_ctx* c, int functional, int n, const double* rho, double* vexc, double* eexcdif)
+{
+    if (!c || !rho || !vexc || !eexcdif || n <= 0 || functional < 0 || functional > 2) return DFTATOM_E_ARG;
+    if (functional == 0) return dftatom_vwn(c, n, rho, nullptr, nullptr, nullptr, vexc, eexcdif);
+    DFT_CHECK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    int rc;
+    DevBuf& d = c->scratch[0];
+    if ((rc = d.ensure(sizeof(double) * (size_t)n * 3))) return rc;
+    double* p = d.as<double>();
+    DFT_CHECK(cudaMemcpyAsync(p, rho, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    launch_chachiyo(n, p, functional == 2, p + n, p + 2 * (size_t)n, st);
+    DFT_CHECK(cudaMemcpyAsync(vexc, p + n, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    DFT_CHECK(cudaMemcpyAsync(eexcdif, p + 2 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    DFT_CHECK(cudaStreamSynchronize(st));
+    DFT_CHECK(cudaGetLastError());
+    return 0;
+}
+
 int dftatom_integrate(dftatom_ctx* c, int rule, double step, const double* v, int n, int n_rows, double* out)
 {
     if (!c || !v || !out || n_rows <= 0 || rule < 0 || rule > 4) return DFTATOM_E_ARG;

@@ -199,6 +199,7 @@ void launch_poisson_stream_solve(const StreamPlan& sp, double delta, const Strea
 
 // XC
 void launch_vwn(int n, const double* ra, const double* rb, double* va, double* vb, double* vexc, double* edif, cudaStream_t st);
+void launch_chachiyo(int n, const double* rho, int improved, double* vexc, double* edif, cudaStream_t st);
 void launch_simpson38(double step, const double* v, int n, int n_rows, double* out, cudaStream_t st);
 void launch_integrate(int rule, double step, const double* v, int n, int n_rows, double* out, cudaStream_t st);
 

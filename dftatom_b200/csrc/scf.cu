@@ -105,6 +105,32 @@ void launch_vwn(int n, const double* ra, const double* rb, double* va, double* v
     vwn_kernel<<<std::min((n + 255) / 256, 148 * 8), 256, 0, st>>>(n, ra, rb, va, vb, vexc, edif);
 }
 
+// Chachiyo's correlation with Dirac exchange (ExcCor.h:27-95; improved = the parameters of :20-25).  The reference reaches it from
+// no option (comments only, DFTAtom.cpp:383,412,421): a component entry point, not part of the SCF path.
+__global__ void chachiyo_kernel(int n, const double* rho, int improved, double* vexc, double* edif)
+{
+    const double a = (0.69314718055994530942 - 1.) / (2. * 3.14159265358979323846 * 3.14159265358979323846);      // (ln 2 - 1) / (2 pi^2)
+    const double b = improved ? 21.7392245 : 20.4562557;
+    const double X1 = pow(3. / (2. * 3.14159265358979323846), 2. / 3.);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double ro = rho[i];
+        double v = 0., e = 0.;
+        if (!(ro < 1E-18)) {
+            const double rs = pow(3. / (kFourPi * ro), 1. / 3.);
+            const double bprs = b / rs, bprs2 = bprs / rs;
+            const double corr = a / (1. + bprs + bprs2) * (bprs + 2. * bprs2) * rs / 3.;
+            v = -X1 / rs + a * log(1. + bprs + bprs / rs) - corr;
+            e = 0.25 * X1 / rs + corr;
+        }
+        vexc[i] = v; edif[i] = e;
+    }
+}
+
+void launch_chachiyo(int n, const double* rho, int improved, double* vexc, double* edif, cudaStream_t st)
+{
+    chachiyo_kernel<<<std::min((n + 255) / 256, 148 * 8), 256, 0, st>>>(n, rho, improved, vexc, edif);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // block reductions
 // ---------------------------------------------------------------------------------------------------------

@@ -180,6 +180,9 @@ int dftatom_poisson_vcycles(dftatom_ctx* ctx, int levels, double delta, int n_de
 /* VWNExchCor::Vexc / eexcDif, LDA (VWNExcCor.h:73-128) and LSDA (:134-312; pass rho_b != NULL) */
 int dftatom_vwn(dftatom_ctx* ctx, int n, const double* rho_a, const double* rho_b, double* va, double* vb,
                 double* vexc, double* eexcdif);
+/* LDA exchange-correlation by functional: 0 = VWN (= dftatom_vwn, the one the reference's SCF uses), 1 = Chachiyo (ExcCor.h:27-95 with
+ * the parameters of :12-17), 2 = Chachiyo improved (:20-25).  The Chachiyo functionals are reachable from no option of the reference. */
+int dftatom_xc_lda(dftatom_ctx* ctx, int functional, int n, const double* rho, double* vexc, double* eexcdif);
 /* Integral::Simpson38 (Integral.h:50-73) of n_rows rows of length n */
 int dftatom_simpson38(dftatom_ctx* ctx, double step, const double* v, int n, int n_rows, double* out);
 

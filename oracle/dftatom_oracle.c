@@ -465,6 +465,26 @@ void orc_vwn_lda(const double* rho, int n, double* vexc, double* eexcdif)
     }
 }
 
+/* Chachiyo's correlation with Dirac exchange (ExcCor.h:27-95): reachable from no option of the reference (only from comments,
+ * DFTAtom.cpp:383,412,421); restated for completeness of the XC family.  improved: 0 = parameters of ExcCor.h:12-17
+ * (b = 20.4562557), 1 = :20-25 (b = 21.7392245). */
+void orc_xc_chachiyo(const double* rho, int n, int improved, double* vexc, double* eexcdif)
+{
+    const double a = (M_LN2 - 1.) / (2. * M_PI * M_PI);            /* :30 */
+    const double b = improved ? 21.7392245 : 20.4562557;
+    const double X1v = pow(3. / (2. * M_PI), 2. / 3.);             /* :43 */
+    const double X1e = 0.25 * pow(3. / (2. * M_PI), 2. / 3.);      /* :73 */
+    for (int i = 0; i < n; ++i) {
+        const double ro = rho[i];
+        if (ro < 1E-18) { vexc[i] = 0.; eexcdif[i] = 0.; continue; }
+        const double rs = pow(3. / (FOUR_PI * ro), 1. / 3.);
+        const double bprs = b / rs;
+        const double bprs2 = bprs / rs;
+        vexc[i] = -X1v / rs + a * log(1. + bprs + bprs / rs) - a / (1. + bprs + bprs2) * (bprs + 2. * bprs2) * rs / 3.;   /* :59-62 */
+        eexcdif[i] = X1e / rs + a / (1. + bprs + bprs2) * (bprs + 2. * bprs2) * rs / 3.;                                  /* :89-91 */
+    }
+}
+
 static double spin_f(double z)
 {   /* ExcCorBase.h:14-19 */
     const double third = 1. / 3.;

@@ -12,6 +12,7 @@
 #include "AufbauPrinciple.h"
 #include "PoissonSolver.h"
 #include "Integral.h"
+#include "ExcCor.h"
 #include "VWNExcCor.h"
 
 using NumerovNU = DFT::Numerov<DFT::NumerovFunctionNonUniformGrid>;
@@ -83,6 +84,16 @@ void ref_vwn_lda(const double* rho, int n, double* vexc, double* eexcdif)
     std::vector<double> d(rho, rho + n);
     std::vector<double> v = DFT::VWNExchCor::Vexc(d);
     std::vector<double> e = DFT::VWNExchCor::eexcDif(d);
+    std::memcpy(vexc, v.data(), sizeof(double) * n);
+    std::memcpy(eexcdif, e.data(), sizeof(double) * n);
+}
+
+// ExcCor.h:27-95 (improved: 0 = ChachiyoExchCorParam, 1 = ChachiyoExchCorImprovedParam)
+void ref_xc_chachiyo(const double* rho, int n, int improved, double* vexc, double* eexcdif)
+{
+    std::vector<double> d(rho, rho + n);
+    std::vector<double> v = improved ? DFT::ChachiyoExchCor<DFT::ChachiyoExchCorImprovedParam>::Vexc(d) : DFT::ChachiyoExchCor<DFT::ChachiyoExchCorParam>::Vexc(d);
+    std::vector<double> e = improved ? DFT::ChachiyoExchCor<DFT::ChachiyoExchCorImprovedParam>::eexcDif(d) : DFT::ChachiyoExchCor<DFT::ChachiyoExchCorParam>::eexcDif(d);
     std::memcpy(vexc, v.data(), sizeof(double) * n);
     std::memcpy(eexcdif, e.data(), sizeof(double) * n);
 }

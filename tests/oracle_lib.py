@@ -69,6 +69,7 @@ def oracle():
         L.orc_integrate.restype = C.c_double
         L.orc_integrate.argtypes = [C.c_int, C.c_double, _dp, C.c_int]
         L.orc_vwn_lda.argtypes = [_dp, C.c_int, _dp, _dp]
+        L.orc_xc_chachiyo.argtypes = [_dp, C.c_int, C.c_int, _dp, _dp]
         L.orc_vwn_lsda.argtypes = [_dp, _dp, C.c_int, _dp, _dp, _dp, _dp]
         L.orc_poisson.argtypes = [C.c_int, C.c_double, C.c_int, C.c_double, _dp, _dp, C.c_int, _dp, _ip]
         L.orc_poisson_vcycles.restype = C.c_double
@@ -95,6 +96,8 @@ def ref_components():
         L.ref_numerov_match.argtypes = [_dp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, _dp]
         L.ref_poisson_nonuniform.argtypes = [C.c_int, C.c_double, C.c_int, C.c_double, _dp, _dp]
         L.ref_vwn_lda.argtypes = [_dp, C.c_int, _dp, _dp]
+        if hasattr(L, "ref_xc_chachiyo"):
+            L.ref_xc_chachiyo.argtypes = [_dp, C.c_int, C.c_int, _dp, _dp]
         L.ref_vwn_lsda.argtypes = [_dp, _dp, C.c_int, _dp, _dp, _dp, _dp]
         L.ref_simpson38.restype = C.c_double
         L.ref_simpson38.argtypes = [C.c_double, _dp, C.c_int]
@@ -192,6 +195,13 @@ def vwn_lda(rho):
     rho = np.ascontiguousarray(rho, np.float64)
     v = np.zeros_like(rho); e = np.zeros_like(rho)
     oracle().orc_vwn_lda(d(rho), len(rho), d(v), d(e))
+    return v, e
+
+
+def xc_chachiyo(rho, improved=0):
+    rho = np.ascontiguousarray(rho, np.float64)
+    v = np.zeros_like(rho); e = np.zeros_like(rho)
+    oracle().orc_xc_chachiyo(d(rho), len(rho), int(improved), d(v), d(e))
     return v, e
 
 

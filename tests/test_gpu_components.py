@@ -242,3 +242,17 @@ def test_quadrature_family_matches_oracle(ctx):
     with pytest.raises(Exception):
         ctx.integrate(3, 0.1, np.zeros(7))          # Boole needs 4k + 1 samples (Integral.h:78)
 
+
+def test_chachiyo_matches_oracle(ctx):
+    """dftatom_xc_lda: the Chachiyo functionals (ExcCor.h:27-95) against the oracle; functional 0 is the VWN path."""
+    rng = np.random.default_rng(4)
+    rho = np.concatenate([10.0 ** rng.uniform(-20, 5, 4000), [0.0, 1e-19, 1e-18, 0.999e-18]])
+    for functional in (1, 2):
+        v, e = ctx.xc_lda(functional, rho)
+        v_o, e_o = O.xc_chachiyo(rho, functional - 1)
+        np.testing.assert_allclose(v, v_o, rtol=2e-11, atol=1e-300)
+        np.testing.assert_allclose(e, e_o, rtol=2e-11, atol=1e-300)
+    v, e = ctx.xc_lda(0, rho)
+    v_o, e_o = O.vwn_lda(rho)
+    np.testing.assert_allclose(v, v_o, rtol=2e-11, atol=1e-300)
+
