@@ -98,18 +98,23 @@ static int get_grid(dftatom_ctx* c, int L, double delta, double max_r, GridDev**
     double* r = &h[0]; double* ex = &h[(size_t)N]; double* sqex = &h[(size_t)2 * N]; double* b12 = &h[(size_t)3 * N];
     double* c6 = &h[(size_t)4 * N]; double* k2 = &h[(size_t)5 * N]; double* wjac = &h[(size_t)6 * N];
     double* psrc = &h[(size_t)7 * N]; double* inv4pr2 = &h[(size_t)8 * N];
-    const double rp = max_r / (std::exp((double)(N - 1) * delta) - 1.);      // DFTAtom.cpp:356
+    // delta == 0 selects the UNIFORM grid of the CalculateUniform* pair (DFTAtom.cpp:65-67: h = MaxR / (N - 1), r_i = i h): the same
+    // tables with e^{delta i} = 1 and K_i = h^2 (Numerov.h:26-31 times h^2; PoissonSolver.h:22-43).  Only the component entry points
+    // accept it so far (dftatom_poisson_solve); dftatom_solve_batch validates delta in (0, 1].
+    const bool uniform = delta == 0.;
+    const double h_uni = max_r / (double)(N - 1);
+    const double rp = uniform ? 0. : max_r / (std::exp((double)(N - 1) * delta) - 1.);      // DFTAtom.cpp:356
     const double rp2d2 = rp * rp * (delta * delta);
     for (int i = 0; i < N; ++i) {
         ex[i] = std::exp((double)i * delta);
-        r[i] = rp * (ex[i] - 1.);                                            // Numerov.h:181-184
+        r[i] = uniform ? (0. * (double)(N - 1 - i) + max_r * (double)i) / (double)(N - 1) : rp * (ex[i] - 1.);   // PoissonSolver.cpp:199-209 / Numerov.h:181-184
         sqex[i] = std::exp((double)i * delta * 0.5);                         // DFTAtom.cpp:42
-        const double K = rp2d2 * std::exp((double)i * (2. * delta));        // Numerov.h:100
+        const double K = uniform ? h_uni * h_uni : rp2d2 * std::exp((double)i * (2. * delta));        // Numerov.h:100
         b12[i] = i ? K / (12. * r[i] * r[i]) : 0.;
         c6[i] = K / 6.;
         k2[i] = 2. * K;
         const double w = (i == 0 || i == N - 1) ? 1. : ((i % 3 == 0) ? 2. : 3.);   // Integral.h:50-73
-        wjac[i] = 0.375 * w * (rp * delta * ex[i]);                          // jacobian DFTAtom.cpp:47,442
+        wjac[i] = 0.375 * w * (uniform ? h_uni : rp * delta * ex[i]);        // jacobian DFTAtom.cpp:47,442 (uniform: the step h, :182)
         psrc[i] = (i == 0 || i == N - 1) ? 0. : r[i] * (kFourPi * K);        // PoissonSolver.h:55-74
         inv4pr2[i] = i ? 1. / (kFourPi * r[i] * r[i]) : 0.;                  // DFTAtom.cpp:340
     }

@@ -72,6 +72,7 @@ def oracle():
         L.orc_xc_chachiyo.argtypes = [_dp, C.c_int, C.c_int, _dp, _dp]
         L.orc_vwn_lsda.argtypes = [_dp, _dp, C.c_int, _dp, _dp, _dp, _dp]
         L.orc_poisson.argtypes = [C.c_int, C.c_double, C.c_int, C.c_double, _dp, _dp, C.c_int, _dp, _ip]
+        L.orc_poisson_uniform.argtypes = [C.c_int, C.c_int, C.c_double, _dp, _dp, C.c_int]
         L.orc_poisson_vcycles.restype = C.c_double
         L.orc_poisson_vcycles.argtypes = [C.c_int, C.c_double, _dp, _dp, C.c_int]
         L.orc_scf.argtypes = [C.POINTER(OrcOptions), C.POINTER(OrcResult), STEP_CB, C.c_void_p, C.c_int]
@@ -183,6 +184,14 @@ def poisson(levels, delta, max_r, Z, rho, max_vcycles=100):
     errs = np.zeros(max(1, max_vcycles)); k = C.c_int()
     oracle().orc_poisson(levels, delta, int(Z), max_r, d(rho), d(U), max_vcycles, d(errs), C.byref(k))
     return U, errs[:k.value]
+
+
+def poisson_uniform(levels, max_r, Z, rho, max_vcycles=100):
+    """SolvePoissonUniform (PoissonSolver.h:20-49) on the uniform grid r_i = i MaxR / (N - 1)."""
+    rho = np.ascontiguousarray(rho, np.float64)
+    U = np.zeros_like(rho)
+    oracle().orc_poisson_uniform(int(levels), int(Z), float(max_r), d(rho), d(U), int(max_vcycles))
+    return U
 
 
 def poisson_vcycles(levels, delta, phi, src, n_cycles):

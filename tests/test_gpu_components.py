@@ -256,3 +256,26 @@ def test_chachiyo_matches_oracle(ctx):
     v_o, e_o = O.vwn_lda(rho)
     np.testing.assert_allclose(v, v_o, rtol=2e-11, atol=1e-300)
 
+
+@pytest.mark.parametrize("L,rmax", [(12, 15.0), (14, 25.0), (15, 25.0)])
+def test_poisson_uniform_grid_matches_oracle(ctx, L, rmax):
+    """First kernel-level piece of the uniform-grid pair: dftatom_poisson_solve with delta = 0 is
+    SolvePoissonUniform (PoissonSolver.h:20-49: r_i = i h, no first-derivative term, source r h^2 4 pi rho) against the oracle
+    and the analytic Hartree potential of an exponential density."""
+    N = (1 << L) + 1
+    r = np.arange(N) * (rmax / (N - 1))
+    Zs = [1, 18, 86]
+    a = [0.8, 1.7, 3.1]
+    rho = np.stack([Z * k ** 3 / np.pi * np.exp(-2 * k * r) for Z, k in zip(Zs, a)])
+    ctx.set_option("stream_min_dens", 1)
+    try:
+        U, used = ctx.poisson_solve(L, 0.0, rmax, Zs, rho)
+    finally:
+        ctx.set_option("stream_min_dens", 4)
+    for j, (Z, k) in enumerate(zip(Zs, a)):
+        U_o = O.poisson_uniform(L, rmax, Z, rho[j], max_vcycles=100 if L <= 14 else 12)
+        U_x = Z * (1 - np.exp(-2 * k * r) * (1 + k * r))
+        assert np.max(np.abs(U[j] - U_o)) < 2e-9 * max(1, Z) * (4 if L > 14 else 1)
+        assert abs(np.max(np.abs(U[j] - U_x)) - np.max(np.abs(U_o - U_x))) < 1e-8 * Z
+        assert U[j][0] == 0.0 and U[j][-1] == Z
+
