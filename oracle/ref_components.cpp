@@ -68,6 +68,45 @@ long ref_numerov_match(const double* V, int n_nodes, double delta, double rmax, 
     return matchPoint;
 }
 
+// The same three sweeps on the UNIFORM grid (Numerov<NumerovFunctionRegularGrid>, called as DFTAtom.cpp:234,242,266,299 do:
+// startPoint = MaxR, steps = N - 1), one object, many (l, E) lanes
+void ref_numerov_uniform_lanes(const double* V, int n_nodes, double rmax, int n_lanes, const int* l, const double* E,
+                               const int* nodes_limit, double* y0, int* count)
+{
+    DFT::Potential pot;
+    pot.m_potentialValues.assign(V, V + n_nodes);
+    DFT::Numerov<DFT::NumerovFunctionRegularGrid> num(pot, 0, rmax, n_nodes);
+    for (int k = 0; k < n_lanes; ++k) {
+        if (y0) y0[k] = num.SolveSchrodingerSolutionInZero(rmax, l[k], E[k], n_nodes - 1);
+        if (count) {
+            int cnt = 0;
+            num.SolveSchrodingerCountNodes(rmax, l[k], E[k], n_nodes - 1, nodes_limit[k], cnt);
+            count[k] = cnt;
+        }
+    }
+}
+
+long ref_numerov_uniform_match(const double* V, int n_nodes, double rmax, int l, double E, double* psi)
+{
+    DFT::Potential pot;
+    pot.m_potentialValues.assign(V, V + n_nodes);
+    DFT::Numerov<DFT::NumerovFunctionRegularGrid> num(pot, 0, rmax, n_nodes);
+    long int matchPoint = 0;
+    std::vector<double> r = num.SolveSchrodingerMatchSolutionCompletely(rmax, l, E, n_nodes - 1, matchPoint);
+    std::memcpy(psi, r.data(), sizeof(double) * n_nodes);
+    return matchPoint;
+}
+
+// PoissonSolver.h:20-49
+void ref_poisson_uniform(int levels, int Z, double rmax, const double* density, double* U)
+{
+    DFT::PoissonSolver ps(levels);
+    const int n = DFT::PoissonSolver::GetNumberOfNodes(levels);
+    std::vector<double> d(density, density + n);
+    std::vector<double> u = ps.SolvePoissonUniform(Z, rmax, d);
+    std::memcpy(U, u.data(), sizeof(double) * n);
+}
+
 // PoissonSolver.h:51-81
 void ref_poisson_nonuniform(int levels, double delta, int Z, double rmax, const double* density, double* U)
 {

@@ -73,6 +73,11 @@ def oracle():
         L.orc_vwn_lsda.argtypes = [_dp, _dp, C.c_int, _dp, _dp, _dp, _dp]
         L.orc_poisson.argtypes = [C.c_int, C.c_double, C.c_int, C.c_double, _dp, _dp, C.c_int, _dp, _ip]
         L.orc_poisson_uniform.argtypes = [C.c_int, C.c_int, C.c_double, _dp, _dp, C.c_int]
+        L.orc_u_count_nodes.argtypes = [_dp, C.c_double, C.c_int, C.c_double, C.c_long, C.c_int]
+        L.orc_u_y0.restype = C.c_double
+        L.orc_u_y0.argtypes = [_dp, C.c_double, C.c_int, C.c_double, C.c_long]
+        L.orc_u_match.restype = C.c_long
+        L.orc_u_match.argtypes = [_dp, C.c_double, C.c_int, C.c_double, C.c_long, _dp]
         L.orc_poisson_vcycles.restype = C.c_double
         L.orc_poisson_vcycles.argtypes = [C.c_int, C.c_double, _dp, _dp, C.c_int]
         L.orc_scf.argtypes = [C.POINTER(OrcOptions), C.POINTER(OrcResult), STEP_CB, C.c_void_p, C.c_int]
@@ -97,6 +102,11 @@ def ref_components():
         L.ref_numerov_match.argtypes = [_dp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, _dp]
         L.ref_poisson_nonuniform.argtypes = [C.c_int, C.c_double, C.c_int, C.c_double, _dp, _dp]
         L.ref_vwn_lda.argtypes = [_dp, C.c_int, _dp, _dp]
+        if hasattr(L, "ref_numerov_uniform_lanes"):
+            L.ref_numerov_uniform_lanes.argtypes = [_dp, C.c_int, C.c_double, C.c_int, _ip, _dp, _ip, _dp, _ip]
+            L.ref_numerov_uniform_match.restype = C.c_long
+            L.ref_numerov_uniform_match.argtypes = [_dp, C.c_int, C.c_double, C.c_int, C.c_double, _dp]
+            L.ref_poisson_uniform.argtypes = [C.c_int, C.c_int, C.c_double, _dp, _dp]
         if hasattr(L, "ref_xc_chachiyo"):
             L.ref_xc_chachiyo.argtypes = [_dp, C.c_int, C.c_int, _dp, _dp]
         L.ref_vwn_lsda.argtypes = [_dp, _dp, C.c_int, _dp, _dp, _dp, _dp]
@@ -184,6 +194,22 @@ def poisson(levels, delta, max_r, Z, rho, max_vcycles=100):
     errs = np.zeros(max(1, max_vcycles)); k = C.c_int()
     oracle().orc_poisson(levels, delta, int(Z), max_r, d(rho), d(U), max_vcycles, d(errs), C.byref(k))
     return U, errs[:k.value]
+
+
+def uniform_lanes(V, max_r, l, E, limit):
+    """(y0, CountNodes) of the uniform-grid sweeps (Numerov.h:272-401, IsUniform() branch) for lanes (l, E, limit)."""
+    V = np.ascontiguousarray(V, np.float64)
+    n = len(V)
+    y0 = np.array([oracle().orc_u_y0(d(V), float(max_r), int(a), float(b), n - 1) for a, b in zip(l, E)])
+    cnt = np.array([oracle().orc_u_count_nodes(d(V), float(max_r), int(a), float(b), n - 1, int(c)) for a, b, c in zip(l, E, limit)], np.int32)
+    return y0, cnt
+
+
+def uniform_orbital(V, max_r, l, E):
+    V = np.ascontiguousarray(V, np.float64)
+    psi = np.zeros_like(V)
+    mp = oracle().orc_u_match(d(V), float(max_r), int(l), float(E), len(V) - 1, d(psi))
+    return psi, mp
 
 
 def poisson_uniform(levels, max_r, Z, rho, max_vcycles=100):
