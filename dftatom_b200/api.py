@@ -35,7 +35,7 @@ class _CLevel(C.Structure):
 
 class _CStep(C.Structure):
     _fields_ = [("E", (C.c_double * MAX_LEVELS) * 2), ("Etotal", C.c_double), ("Ekin", C.c_double), ("Ecoul", C.c_double),
-                ("Eenuc", C.c_double), ("Exc", C.c_double), ("levels_converged", C.c_int), ("reserved", C.c_int)]
+                ("Eenuc", C.c_double), ("Exc", C.c_double), ("levels_converged", C.c_int), ("stop_criterion_met", C.c_int)]
 
 
 class _CResult(C.Structure):
@@ -77,6 +77,7 @@ def load_library():
     lib.dftatom_n_nodes.argtypes = [C.c_int]
     lib.dftatom_solve_batch.argtypes = [C.c_void_p, C.POINTER(_COptions), C.c_int, C.POINTER(_CResult), C.POINTER(_CStep), C.c_int]
     lib.dftatom_last_timing.argtypes = [C.c_void_p, _dp, C.POINTER(C.c_longlong)]
+    lib.dftatom_last_transfer.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     lib.dftatom_last_profile.argtypes = [C.c_void_p, C.POINTER(_CProfile)]
     lib.dftatom_measure_fp64_peak.argtypes = [C.c_void_p, _dp]
     lib.dftatom_numerov_lanes.argtypes = [C.c_void_p, _dp, C.c_int, C.c_double, C.c_double, C.c_int, _ip, _dp, _ip, C.c_int, _ip, _dp, _ip]
@@ -154,6 +155,7 @@ class Step:
     Eenuc: float
     Exc: float
     levels_converged: bool
+    stop_criterion_met: bool = False
 
 
 @dataclass
@@ -259,7 +261,7 @@ class Context:
                 for k in range(r.n_steps):
                     cs = csteps[a * stride + k]
                     steps.append(Step([[cs.E[s][j] for j in range(r.n_levels[s])] for s in range(r.n_spin)], cs.Etotal, cs.Ekin,
-                                      cs.Ecoul, cs.Eenuc, cs.Exc, bool(cs.levels_converged)))
+                                      cs.Ecoul, cs.Eenuc, cs.Exc, bool(cs.levels_converged), bool(cs.stop_criterion_met)))
             out.append(Result(options[a], r.status, r.n_steps, lv, sl, r.Etotal, r.Ekin, r.Ecoul, r.Eenuc, r.Exc, steps))
         return out
 
@@ -267,6 +269,12 @@ class Context:
         ms, n = C.c_double(), C.c_longlong()
         _check(self._lib.dftatom_last_timing(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def last_transfer(self):
+        """(host->device bytes, device->host bytes) of the last solve_batch."""
+        a, b = C.c_longlong(), C.c_longlong()
+        _check(self._lib.dftatom_last_transfer(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def last_profile(self):
         """Per-kernel-class {ms, launches, work} of the last solve_batch (needs set_option('profile', 1))."""

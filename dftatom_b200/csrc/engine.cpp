@@ -40,15 +40,27 @@ struct GridKey {
 
 struct GridEntry { GridDev dev; DevBuf mem; };
 
+// CUDA events of one call, destroyed on every return path
+struct EventPool {
+    std::vector<cudaEvent_t> all;
+    bool ok = true;
+    cudaEvent_t make(bool timing)
+    {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreateWithFlags(&e, timing ? cudaEventDefault : cudaEventDisableTiming) != cudaSuccess) { ok = false; return nullptr; }
+        all.push_back(e);
+        return e;
+    }
+    ~EventPool() { for (cudaEvent_t e : all) cudaEventDestroy(e); }
+};
+
 }  // namespace dft
 
 using namespace dft;
 
-struct dftatom_ctx {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    std::map<GridKey, GridEntry> grids;
-    // options
+// Tuning knobs of a context, set through dftatom_set_option (documented in include/dftatom_b200.h).  One struct so that the
+// child context of stream_groups = 2 inherits ALL of them by assignment.
+struct Knobs {
     int max_vcycles = 8;
     int floor_stop = 0;
     int refine_vcycles = 0;
@@ -63,16 +75,30 @@ struct dftatom_ctx {
     int profile = 0;
     int search_mode = 0;
     int match_mode = 0;
-    int energies_per_lane = 1;
     int warm_start = 1;
-    int stream_groups = 1;     // 2: a batch of >= 32 atoms is split into two groups that run their SCF chains concurrently on separate streams
-    dftatom_ctx* child = nullptr;   // context (stream + buffers) of the second group
     int stream_variant = 0;    // window shape of the stream-mode Poisson visits (poisson_stream.cu)
     int stream_poisson = 1;    // grids above 16385 nodes: level visits streamed over all densities (poisson_stream.cu) instead of one CTA / team per density
     int stream_min_dens = 4;   // ... when the batch has at least this many densities (below, the team of CTAs per density is faster)
     int stream_mid_levels = 11; // stream mode: levels of up to 2^this nodes are run by one CTA per density, the larger ones by slab windows
     int stream_min_levels = 15; // stream mode from this many levels on (at 14 levels one CTA per density is as fast: measured 57.6 against 58.5 ms on C3)
-    DevBuf stream_src0, stream_scratch;
+    int poisson_exact = 0;     // 1: bit-reproducible Poisson solve (poisson_exact.cu): the reference's FullCycle in its own operation order, 100 V-cycles
+    int run_to_cap = 0;        // 1: the stop test (DFTAtom.cpp:474) is evaluated and recorded but never ends the SCF (trajectory parity beyond the stop step)
+    int cluster_poisson = 1;   // warm-started solves on 2049 .. 16385 nodes: one cluster of 8 CTAs per density (poisson_cluster.cu); 0 = one CTA per density
+    int cluster_max_dens = 40; // ... while at most this many atoms are still iterating (8 CTAs per density: above ~37 densities the clusters need more than one wave of the 148 SMs and one CTA per density has the higher throughput)
+    int use_graph = 1;         // SCF steps are replayed from a captured CUDA graph (one graph launch per step) instead of 5+ kernel launches
+};
+
+struct dftatom_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::map<GridKey, GridEntry> grids;
+    Knobs k;                        // tuning knobs (dftatom_set_option); copied as a whole to the child context
+    int segments(int N) const { return k.segments(N); }
+    int stream_groups = 1;     // 2: a batch of >= 32 atoms is split into two groups that run their SCF chains concurrently on separate streams
+    dftatom_ctx* child = nullptr;   // context (stream + buffers) of the second group
+    int n_sm = 148;
+    DevBuf stream_src0, stream_scratch, exact_work, last_steps;
+    dftatom_step* h_last = nullptr; size_t h_last_cap = 0;      // pinned staging of the result records
     DevBuf stream_G; int stream_G_levels = 0; double stream_G_delta = 0.;   // dense coarse operator of the stream-mode V-cycle
     dftatom_kernel_profile prof[DFTATOM_K_COUNT] = {};
     // reusable buffers
@@ -82,22 +108,29 @@ struct dftatom_ctx {
     // timing of the last solve
     double last_ms = 0.;
     long long last_launches = 0;
+    long long last_d2h_bytes = 0, last_h2d_bytes = 0;      // bytes the last solve_batch moved between host and device
 };
 
 namespace dft {
 
 static int get_grid(dftatom_ctx* c, int L, double delta, double max_r, GridDev** out)
 {
+    // one place for the grid arguments of every entry point: 1 <= levels <= 22 (PoissonLevels holds 24, shifts stay defined), finite
+    // delta >= 0 (0 = uniform grid) and finite max_r > 0 (a NaN would also break the ordering of the grid cache)
+    if (L < 1 || L > 22 || !(delta >= 0.) || !std::isfinite(delta) || !(max_r > 0.) || !std::isfinite(max_r)) {
+        set_error("bad grid: need 1 <= levels <= 22, finite delta >= 0, finite max_r > 0");
+        return DFTATOM_E_BAD_OPTION;
+    }
     const GridKey key{ L, delta, max_r };
     auto it = c->grids.find(key);
     if (it != c->grids.end()) { *out = &it->second.dev; return 0; }
     const int N = (1 << L) + 1;
     // host tables with the same libm the CPU reference uses (exp), uploaded once per grid
-    const int n_tab = 9;
+    const int n_tab = 10;
     std::vector<double> h((size_t)n_tab * N);
     double* r = &h[0]; double* ex = &h[(size_t)N]; double* sqex = &h[(size_t)2 * N]; double* b12 = &h[(size_t)3 * N];
     double* c6 = &h[(size_t)4 * N]; double* k2 = &h[(size_t)5 * N]; double* wjac = &h[(size_t)6 * N];
-    double* psrc = &h[(size_t)7 * N]; double* inv4pr2 = &h[(size_t)8 * N];
+    double* psrc = &h[(size_t)7 * N]; double* inv4pr2 = &h[(size_t)8 * N]; double* pex = &h[(size_t)9 * N];
     // delta == 0 selects the UNIFORM grid of the CalculateUniform* pair (DFTAtom.cpp:65-67: h = MaxR / (N - 1), r_i = i h): the same
     // tables with e^{delta i} = 1 and K_i = h^2 (Numerov.h:26-31 times h^2; PoissonSolver.h:22-43).  Only the component entry points
     // accept it so far (dftatom_poisson_solve); dftatom_solve_batch validates delta in (0, 1].
@@ -118,6 +151,19 @@ static int get_grid(dftatom_ctx* c, int L, double delta, double max_r, GridDev**
         psrc[i] = (i == 0 || i == N - 1) ? 0. : r[i] * (kFourPi * K);        // PoissonSolver.h:55-74
         inv4pr2[i] = i ? 1. / (kFourPi * r[i] * r[i]) : 0.;                  // DFTAtom.cpp:340
     }
+    {   // the source factor of the bit-reproducible Poisson mode, in the reference's own product order
+        const double four_pi = 4. * M_PI;                                   // fourM_PI, PoissonSolver.h:12
+        if (uniform) {
+            const double dlt = r[1] - r[0];                                 // PoissonSolver.h:26-27
+            const double d2f = (dlt * dlt) * four_pi;                       // :39
+            for (int i = 0; i < N; ++i) pex[i] = d2f;
+        } else {
+            const double rp_p = max_r / (std::exp(((double)N - 1.) * delta) - 1.);      // PoissonSolver.h:65
+            const double f = four_pi * (rp_p * rp_p * (delta * delta));     // :66-70
+            const double twodelta = 2. * delta;
+            for (int i = 0; i < N; ++i) pex[i] = f * std::exp(i * twodelta);            // :74
+        }
+    }
     GridEntry& e = c->grids[key];
     int rc = e.mem.ensure((h.size() + 32 * 32) * sizeof(double));
     if (rc) { c->grids.erase(key); return rc; }
@@ -127,10 +173,10 @@ static int get_grid(dftatom_ctx* c, int L, double delta, double max_r, GridDev**
     e.dev.N = N; e.dev.L = L; e.dev.delta = delta; e.dev.rp = rp; e.dev.max_r = max_r;
     e.dev.r = d; e.dev.ex = d + (size_t)N; e.dev.sqex = d + (size_t)2 * N; e.dev.b12 = d + (size_t)3 * N;
     e.dev.c6 = d + (size_t)4 * N; e.dev.k2 = d + (size_t)5 * N; e.dev.wjac = d + (size_t)6 * N;
-    e.dev.psrc = d + (size_t)7 * N; e.dev.inv4pr2 = d + (size_t)8 * N;
+    e.dev.psrc = d + (size_t)7 * N; e.dev.inv4pr2 = d + (size_t)8 * N; e.dev.pex = d + (size_t)9 * N;
     e.dev.coarse_op = nullptr;
     if (L >= 6) {
-        e.dev.coarse_op = d + (size_t)9 * N;
+        e.dev.coarse_op = d + (size_t)n_tab * N;
         launch_coarse_op(L, delta, e.dev.coarse_op, c->stream);
         DFT_CHECK(cudaStreamSynchronize(c->stream));
     }
@@ -178,6 +224,10 @@ int dftatom_create(dftatom_ctx** out, int device)
     DFT_CHECK(cudaSetDevice(device));
     dftatom_ctx* c = new dftatom_ctx;
     c->device = device;
+    DFT_CHECK(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device));
+    // opt-in dynamic shared memory is per-device state: set it here, for this context's device (not cached process-wide)
+    int rc_attr;
+    if ((rc_attr = poisson_init_device()) || (rc_attr = stream_init_device()) || (rc_attr = match_init_device()) || (rc_attr = poisson_cluster_init_device())) { delete c; return rc_attr; }
     DFT_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     DFT_CHECK(cudaMallocHost((void**)&c->h_active, sizeof(int) * 256));
     *out = c;
@@ -195,8 +245,9 @@ void dftatom_destroy(dftatom_ctx* c)
                       &c->phi, &c->src, &c->u0, &c->ubuf, &c->zbc, &c->tab_of, &c->steps, &c->n_active };
     for (DevBuf* b : all) b->release();
     for (DevBuf& b : c->scratch) b.release();
-    c->stream_G.release(); c->stream_src0.release(); c->stream_scratch.release();
+    c->stream_G.release(); c->stream_src0.release(); c->stream_scratch.release(); c->exact_work.release(); c->last_steps.release();
     if (c->h_active) cudaFreeHost(c->h_active);
+    if (c->h_last) cudaFreeHost(c->h_last);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -205,25 +256,29 @@ int dftatom_set_option(dftatom_ctx* c, const char* key, double value)
 {
     if (!c || !key) return DFTATOM_E_ARG;
     const std::string k(key);
-    if (k == "max_vcycles") c->max_vcycles = std::max(1, (int)value);
-    else if (k == "vcycle_floor_stop") c->floor_stop = value != 0.;
-    else if (k == "refine_vcycles") c->refine_vcycles = std::max(0, (int)value);
-    else if (k == "warm_vcycles") c->warm_vcycles = std::max(0, (int)value);
-    else if (k == "warm_after") c->warm_after = std::max(0, (int)value);
-    else if (k == "team_poisson") c->team_poisson = value != 0.;
-    else if (k == "r_segments") c->r_segments = (int)value;
-    else if (k == "seg_threshold") c->seg_threshold = (int)value;
-    else if (k == "profile") c->profile = value != 0.;
-    else if (k == "search_mode") c->search_mode = (int)value;
-    else if (k == "match_mode") c->match_mode = (int)value;
-    else if (k == "warm_start") c->warm_start = value != 0.;
+    if (k == "max_vcycles") c->k.max_vcycles = std::max(1, (int)value);
+    else if (k == "vcycle_floor_stop") c->k.floor_stop = value != 0.;
+    else if (k == "refine_vcycles") c->k.refine_vcycles = std::max(0, (int)value);
+    else if (k == "warm_vcycles") c->k.warm_vcycles = std::max(0, (int)value);
+    else if (k == "warm_after") c->k.warm_after = std::max(0, (int)value);
+    else if (k == "team_poisson") c->k.team_poisson = value != 0.;
+    else if (k == "r_segments") c->k.r_segments = (int)value;
+    else if (k == "seg_threshold") c->k.seg_threshold = (int)value;
+    else if (k == "profile") c->k.profile = value != 0.;
+    else if (k == "search_mode") c->k.search_mode = (int)value;
+    else if (k == "match_mode") c->k.match_mode = (int)value;
+    else if (k == "warm_start") c->k.warm_start = value != 0.;
     else if (k == "stream_groups") c->stream_groups = std::min(2, std::max(1, (int)value));
-    else if (k == "stream_poisson") c->stream_poisson = value != 0.;
-    else if (k == "stream_min_dens") c->stream_min_dens = std::max(1, (int)value);
-    else if (k == "stream_mid_levels") c->stream_mid_levels = std::min(14, std::max(11, (int)value));
-    else if (k == "stream_min_levels") c->stream_min_levels = std::min(23, std::max(13, (int)value));
-    else if (k == "stream_variant") c->stream_variant = std::min(2, std::max(0, (int)value));
-    else if (k == "energies_per_lane") c->energies_per_lane = ((int)value == 2) ? 2 : 1;
+    else if (k == "stream_poisson") c->k.stream_poisson = value != 0.;
+    else if (k == "stream_min_dens") c->k.stream_min_dens = std::max(1, (int)value);
+    else if (k == "stream_mid_levels") c->k.stream_mid_levels = std::min(14, std::max(11, (int)value));
+    else if (k == "stream_min_levels") c->k.stream_min_levels = std::min(23, std::max(13, (int)value));
+    else if (k == "stream_variant") c->k.stream_variant = std::min(2, std::max(0, (int)value));
+    else if (k == "poisson_exact") c->k.poisson_exact = value != 0.;
+    else if (k == "cluster_poisson") c->k.cluster_poisson = value != 0.;
+    else if (k == "cluster_max_dens") c->k.cluster_max_dens = std::max(0, (int)value);
+    else if (k == "run_to_cap") c->k.run_to_cap = value != 0.;
+    else if (k == "use_graph") c->k.use_graph = value != 0.;
     else { set_error("unknown option " + k); return DFTATOM_E_ARG; }
     return 0;
 }
@@ -240,6 +295,14 @@ int dftatom_last_timing(dftatom_ctx* c, double* ms, long long* launches)
     if (!c) return DFTATOM_E_ARG;
     if (ms) *ms = c->last_ms;
     if (launches) *launches = c->last_launches;
+    return 0;
+}
+
+int dftatom_last_transfer(dftatom_ctx* c, long long* h2d_bytes, long long* d2h_bytes)
+{
+    if (!c) return DFTATOM_E_ARG;
+    if (h2d_bytes) *h2d_bytes = c->last_h2d_bytes;
+    if (d2h_bytes) *d2h_bytes = c->last_d2h_bytes;
     return 0;
 }
 
@@ -335,6 +398,8 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
     }
     const int n_orbs = (int)orbs.size();
     const int stride = max_steps;
+    c->last_h2d_bytes = (long long)(sizeof(AtomDev) * atoms.size() + sizeof(AtomState) * astate.size() + sizeof(OrbitalDev) * orbs.size()
+                                    + sizeof(int) * (tab_of.size() + zbc.size() + 2));
 
     // ---- device buffers ----
     if ((rc = upload(c, c->atoms, atoms))) return rc;
@@ -355,12 +420,16 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
     if ((rc = c->phi.ensure(sizeof(double) * (size_t)n_atoms * lv.total))) return rc;
     if ((rc = c->src.ensure(sizeof(double) * (size_t)n_atoms * lv.total))) return rc;
     if ((rc = c->u0.ensure(sizeof(double) * (size_t)n_atoms * N))) return rc;
-    const bool stream = c->stream_poisson && n_atoms >= c->stream_min_dens && g.L >= c->stream_min_levels && g.L > c->stream_mid_levels && g.L <= 22 && c->refine_vcycles == 0 && !c->floor_stop;
+    if (n_atoms > 65535) { set_error("at most 65535 atoms per batch"); return DFTATOM_E_ARG; }      // gridDim.y of the per-density launches
+    const bool exact = c->k.poisson_exact != 0;
+    const bool stream = !exact && c->k.stream_poisson && n_atoms >= c->k.stream_min_dens && g.L >= c->k.stream_min_levels && g.L > c->k.stream_mid_levels && g.L <= 22 && c->k.refine_vcycles == 0 && !c->k.floor_stop;
     const int ldU = stream ? ((N + 3) & ~3) : N;
-    const StreamPlan splan = stream ? make_stream_plan(g.L, n_atoms, c->stream_mid_levels) : StreamPlan{};
+    const StreamPlan splan = stream ? make_stream_plan(g.L, n_atoms, c->k.stream_mid_levels) : StreamPlan{};
     if ((rc = c->ubuf.ensure(sizeof(double) * (size_t)n_atoms * ldU))) return rc;
     if (stream && ((rc = c->stream_src0.ensure(sizeof(double) * (size_t)n_atoms * ldU)) || (rc = c->stream_scratch.ensure(sizeof(double) * (size_t)splan.total)))) return rc;
+    if (exact && (rc = c->exact_work.ensure(sizeof(double) * (size_t)n_atoms * (size_t)exact_poisson_work_doubles(g.L)))) return rc;
     if ((rc = c->steps.ensure(sizeof(dftatom_step) * (size_t)n_atoms * stride))) return rc;
+    if ((rc = c->last_steps.ensure(sizeof(dftatom_step) * (size_t)n_atoms))) return rc;
     if ((rc = c->n_active.ensure(sizeof(int) * 2))) return rc;
     DFT_CHECK(cudaMemsetAsync(c->steps.p, 0, sizeof(dftatom_step) * (size_t)n_atoms * stride, st));
     DFT_CHECK(cudaMemsetAsync(c->ss.p, 0, sizeof(SearchState) * (size_t)n_orbs, st));
@@ -374,26 +443,60 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
     b.atab = c->atab.as<double>(); b.psi = c->psi.as<double>(); b.match_pt = c->match_pt.as<int>(); b.inv_norm = c->inv_norm.as<double>(); b.epart = c->epart.as<double>(); b.eticket = c->eticket.as<int>();
     b.phi = c->phi.as<double>(); b.src = c->src.as<double>(); b.U = c->ubuf.as<double>(); b.ldU = ldU; b.Zbc = c->zbc.as<int>(); b.tab_of = c->tab_of.as<int>();
     b.steps = c->steps.as<dftatom_step>(); b.steps_stride = stride; b.n_active = c->n_active.as<int>();
+    b.run_to_cap = c->k.run_to_cap;
 
     PoissonArgs pa{};
     pa.n_dens = n_atoms; pa.rho = b.rhot; pa.Zbc = b.Zbc; pa.phi = b.phi; pa.src = b.src; pa.u_out = b.U; pa.coarse_op = g.coarse_op;
     pa.skip = &b.astate[0].done; pa.skip_stride_bytes = (int)sizeof(AtomState);
-    pa.max_vcycles = c->max_vcycles; pa.floor_stop = c->floor_stop;
-    pa.refine_vcycles = c->refine_vcycles; pa.u0 = c->u0.as<double>();
+    pa.max_vcycles = c->k.max_vcycles; pa.floor_stop = c->k.floor_stop;
+    pa.refine_vcycles = c->k.refine_vcycles; pa.u0 = c->u0.as<double>();
     if ((rc = c->team_bar.ensure(sizeof(unsigned) * (size_t)n_atoms))) return rc;
-    pa.team_bar = c->team_poisson ? c->team_bar.as<unsigned>() : nullptr;
-    pa.nat_stride = 0;
+    pa.team_bar = c->k.team_poisson ? c->team_bar.as<unsigned>() : nullptr;
+    pa.nat_stride = 0; pa.n_sm = c->n_sm;
+    ExactPoissonArgs xa{};
+    xa.n_dens = n_atoms; xa.L = g.L; xa.delta = g.delta; xa.rho = b.rhot; xa.rho_stride = N; xa.r = g.r; xa.pex = g.pex; xa.Zbc = b.Zbc;
+    xa.U = b.U; xa.ldU = ldU; xa.work = c->exact_work.as<double>(); xa.skip = &b.astate[0].done; xa.skip_stride_bytes = (int)sizeof(AtomState);
+    xa.max_vcycles = 100;                                       // PoissonSolver.h:117
+    const bool cluster_ok = c->k.cluster_poisson && !exact && !stream && poisson_cluster_supported(g.L, g.delta) && g.coarse_op && c->k.refine_vcycles == 0 && !c->k.floor_stop;
+    ClusterPoissonArgs ca{};
+    ca.n_dens = n_atoms; ca.rho = b.rhot; ca.rho_stride = N; ca.U = b.U; ca.ldU = ldU; ca.Zbc = b.Zbc; ca.coarse_op = g.coarse_op;
+    ca.skip = &b.astate[0].done; ca.skip_stride_bytes = (int)sizeof(AtomState);
     StreamSolveArgs sa{};
     sa.n_dens = n_atoms; sa.rho = b.rhot; sa.rho_stride = N; sa.psrc = g.psrc; sa.src0 = c->stream_src0.as<double>(); sa.U = b.U; sa.ld0 = ldU;
-    sa.Zbc = b.Zbc; sa.scratch = c->stream_scratch.as<double>(); sa.coarse_op = g.coarse_op; sa.variant = c->stream_variant;
+    sa.Zbc = b.Zbc; sa.scratch = c->stream_scratch.as<double>(); sa.coarse_op = g.coarse_op; sa.variant = c->k.stream_variant;
     sa.skip = &b.astate[0].done; sa.skip_stride_bytes = (int)sizeof(AtomState);
     // the Poisson solve of one SCF step: FullCycle (ramp + max_vcycles V-cycles), or warm_vcycles V-cycles from the previous U
+    int act_est = n_atoms;          // atoms still iterating, as of `lag` steps ago (host-side estimate; only selects between two equivalent kernels)
     auto poisson_solve = [&](int warm_vcycles, long long& n_launch) {
-        if (stream) {
-            sa.warm = warm_vcycles > 0; sa.n_v = warm_vcycles > 0 ? warm_vcycles : c->max_vcycles;
+        if (exact) {
+            launch_poisson_exact(xa, st);
+            ++n_launch;
+        } else if (stream) {
+            sa.warm = warm_vcycles > 0; sa.n_v = warm_vcycles > 0 ? warm_vcycles : c->k.max_vcycles;
             long long nl = 0;
             launch_poisson_stream_solve(splan, g.delta, sa, st, &nl);
             n_launch += nl;
+        } else if (cluster_ok && warm_vcycles > 0 && act_est <= c->k.cluster_max_dens) {
+            ca.n_vcycles = warm_vcycles; ca.work = pa.work;
+            if (getenv("DFTATOM_DEBUG_CLUSTER") && n_launch > 40 && !ca.dbg) {       // development aid: cycle counters of one solve
+                if (c->scratch[5].ensure(sizeof(long long) * 256)) return;
+                cudaMemsetAsync(c->scratch[5].p, 0, sizeof(long long) * 256, st);
+                ca.dbg = c->scratch[5].as<long long>();
+                launch_poisson_cluster(g, ca, st);
+                long long h[256];
+                cudaMemcpyAsync(h, ca.dbg, sizeof(h), cudaMemcpyDeviceToHost, st);
+                cudaStreamSynchronize(st);
+                for (int r = 0; r < 8; ++r) {
+                    fprintf(stderr, "cluster rank %d: total %lld local %lld wait1 %lld wait2 %lld waitL %lld load %lld sweeps %lld store %lld | levels", r, h[r * 32], h[r * 32 + 1], h[r * 32 + 2], h[r * 32 + 3], h[r * 32 + 7], h[r * 32 + 4], h[r * 32 + 5], h[r * 32 + 6]);
+                    for (int l = 0; l < 4; ++l) fprintf(stderr, " %lld", h[r * 32 + 8 + l]);
+                    fprintf(stderr, "\n");
+                }
+                ca.dbg = reinterpret_cast<long long*>(1);       // once
+                ++n_launch;
+                return;
+            }
+            { long long* keep = ca.dbg; ca.dbg = nullptr; launch_poisson_cluster(g, ca, st); ca.dbg = keep; }
+            ++n_launch;
         } else {
             pa.warm_vcycles = warm_vcycles;
             launch_poisson_full(g, lv, pa, st);
@@ -401,24 +504,28 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
         }
     };
 
-    cudaEvent_t ev0, ev1;
-    DFT_CHECK(cudaEventCreate(&ev0));
-    DFT_CHECK(cudaEventCreate(&ev1));
-    std::vector<cudaEvent_t> step_ev(max_steps);
-    for (auto& e : step_ev) DFT_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     if (max_steps > 256) { set_error("internal: step cap"); return DFTATOM_E_ARG; }
+    EventPool events;                       // destroyed on every return path
+    cudaEvent_t ev0 = events.make(true), ev1 = events.make(true);
+    std::vector<cudaEvent_t> step_ev(max_steps);
+    for (auto& e : step_ev) e = events.make(false);
+    if (!events.ok) { set_error("cudaEventCreate failed"); return DFTATOM_E_CUDA; }
 
     long long launches = 0;
     // optional per-class kernel timing: one event pair per launch group, resolved after the final sync
     struct Span { int cls; cudaEvent_t a, b; };
     std::vector<Span> spans;
-    const bool prof = c->profile != 0;
+    const bool prof = c->k.profile != 0;
     unsigned long long* d_work = nullptr;
     if ((rc = c->scratch[7].ensure(sizeof(unsigned long long) * 32))) return rc;
     d_work = c->scratch[7].as<unsigned long long>();
     DFT_CHECK(cudaMemsetAsync(d_work, 0, sizeof(unsigned long long) * 32, st));
     pa.work = d_work + DFTATOM_K_POISSON;
-    auto begin_span = [&](int cls) { if (prof) { Span s{ cls, nullptr, nullptr }; cudaEventCreate(&s.a); cudaEventCreate(&s.b); cudaEventRecord(s.a, st); spans.push_back(s); } };
+    // the event pairs of the per-class timing are created BEFORE the timed loop (profile = 1 must not put cudaEventCreate into it)
+    std::vector<cudaEvent_t> span_ev;
+    if (prof) { span_ev.resize((size_t)max_steps * DFTATOM_K_COUNT * 2); for (auto& e : span_ev) e = events.make(true); if (!events.ok) { set_error("cudaEventCreate failed"); return DFTATOM_E_CUDA; } }
+    size_t span_next = 0;
+    auto begin_span = [&](int cls) { if (prof) { Span s{ cls, span_ev[span_next], span_ev[span_next + 1] }; span_next += 2; cudaEventRecord(s.a, st); spans.push_back(s); } };
     auto end_span = [&]() { if (prof) cudaEventRecord(spans.back().b, st); };
     DFT_CHECK(cudaEventRecord(ev0, st));
     // initial guess -> U -> V   (DFTAtom.cpp:371-392)
@@ -431,30 +538,30 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
     const int lag = 2;
     for (int sp = 0; sp < max_steps; ++sp) {
         begin_span(DFTATOM_K_SEARCH);
-        if (c->search_mode == 0) {
+        if (c->k.search_mode == 0) {
             // two shapes of the same search: serial-in-r (one warp per orbital) while many orbitals are active, parallel-in-r
             // (one cluster per orbital) once few are left.  Both are enqueued; the device-side count of active orbitals
             // decides which one runs (the other returns at once), so the host never has to know.
             const int segs = c->segments(N);
-            const int thr = segs > 1 ? c->seg_threshold : -1;
-            const bool serial_too = !(segs > 1 && c->seg_threshold >= n_orbs);      // the serial-in-r kernel can never be selected: do not launch it
+            const int thr = segs > 1 ? c->k.seg_threshold : -1;
+            const bool serial_too = !(segs > 1 && c->k.seg_threshold >= n_orbs);      // the serial-in-r kernel can never be selected: do not launch it
             if (serial_too) {
-                launch_search_fused(g, b.atab, b.atoms, b.orbs, b.astate, b.ss, n_orbs, d_work + DFTATOM_K_SEARCH, b.n_active + 1, thr, c->warm_start, st);
+                launch_search_fused(g, b.atab, b.atoms, b.orbs, b.astate, b.ss, n_orbs, d_work + DFTATOM_K_SEARCH, b.n_active + 1, thr, c->k.warm_start, st);
                 ++launches;
             }
             if (segs > 1) {
-                launch_search_seg(g, b.atab, b.atoms, b.orbs, b.astate, b.ss, n_orbs, d_work + DFTATOM_K_SEARCH, segs, b.n_active + 1, thr, c->warm_start, st);
+                launch_search_seg(g, b.atab, b.atoms, b.orbs, b.astate, b.ss, n_orbs, d_work + DFTATOM_K_SEARCH, segs, b.n_active + 1, thr, c->k.warm_start, st);
                 ++launches;
             }
         } else {
             launch_search_init(g, b.atoms, b.astate, b.orbs, b.ss, n_orbs, st); ++launches;
         }
-        if (c->search_mode != 0) for (int r = 0; r < rounds; ++r) { launch_search_round(g, b.atab, b.orbs, b.astate, b.ss, n_orbs, d_work + DFTATOM_K_SEARCH, st); ++launches; }
+        if (c->k.search_mode != 0) for (int r = 0; r < rounds; ++r) { launch_search_round(g, b.atab, b.orbs, b.astate, b.ss, n_orbs, d_work + DFTATOM_K_SEARCH, st); ++launches; }
         end_span();
         begin_span(DFTATOM_K_MATCH);
-        if (c->match_mode == 0) launch_match_cta(g, b.atab, b.orbs, b.astate, b.ss, b.psi, b.match_pt, b.inv_norm, n_orbs, st);
+        if (c->k.match_mode == 0) launch_match_cta(g, b.atab, b.orbs, b.astate, b.ss, b.psi, b.match_pt, b.inv_norm, n_orbs, st);
         else {                                              // validation paths: warp-per-orbital / reference-shaped serial solution
-            if (c->match_mode == 2) launch_match_seg(g, b.atab, b.orbs, b.astate, b.ss, b.psi, b.match_pt, n_orbs, st);
+            if (c->k.match_mode == 2) launch_match_seg(g, b.atab, b.orbs, b.astate, b.ss, b.psi, b.match_pt, n_orbs, st);
             else launch_match(g, b.atab, b.orbs, b.astate, b.ss, b.psi, b.match_pt, n_orbs, st);
             launch_orbital_norms(g, b, st); ++launches;
         }
@@ -464,7 +571,7 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
         launch_density_update(g, b, st); ++launches;
         end_span();
         begin_span(DFTATOM_K_POISSON);
-        poisson_solve((sp >= c->warm_after) ? c->warm_vcycles : 0, launches);
+        poisson_solve((sp >= c->k.warm_after) ? c->k.warm_vcycles : 0, launches);
         end_span();
         begin_span(DFTATOM_K_POTENTIAL);
         launch_potential_energy(g, lv, b, 0, st); ++launches;
@@ -476,6 +583,7 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
             // the host stays `lag` steps ahead of the device: it never idles the GPU, it only stops enqueueing
             DFT_CHECK(cudaEventSynchronize(step_ev[sp - lag]));
             if (c->h_active[sp - lag] == 0) break;
+            act_est = c->h_active[sp - lag];
         }
     }
     DFT_CHECK(cudaEventRecord(ev1, st));
@@ -498,24 +606,32 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
             float t = 0.f;
             cudaEventElapsedTime(&t, s.a, s.b);
             c->prof[s.cls].ms += t;
-            c->prof[s.cls].launches += (s.cls == DFTATOM_K_SEARCH) ? (c->search_mode == 0 ? ((c->segments(N) > 1 && c->seg_threshold < n_orbs) ? 2 : 1) : rounds + 1) : 1;
-            cudaEventDestroy(s.a); cudaEventDestroy(s.b);
+            c->prof[s.cls].launches += (s.cls == DFTATOM_K_SEARCH) ? (c->k.search_mode == 0 ? ((c->segments(N) > 1 && c->k.seg_threshold < n_orbs) ? 2 : 1) : rounds + 1) : 1;
         }
     }
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
-    for (auto& e : step_ev) cudaEventDestroy(e);
 
     // ---- results ----
-    std::vector<dftatom_step> hsteps((size_t)n_atoms * stride);
-    DFT_CHECK(cudaMemcpy(astate.data(), b.astate, sizeof(AtomState) * n_atoms, cudaMemcpyDeviceToHost));
-    DFT_CHECK(cudaMemcpy(hsteps.data(), b.steps, sizeof(dftatom_step) * hsteps.size(), cudaMemcpyDeviceToHost));
+    // Download what the caller asked for: with steps == NULL only the last record of every atom (gathered on the device,
+    // n_atoms records) instead of the whole [n_atoms][stride] step array.
+    const size_t n_rec = steps ? (size_t)n_atoms * stride : (size_t)n_atoms;
+    if (n_rec > c->h_last_cap) {
+        if (c->h_last) cudaFreeHost(c->h_last);
+        c->h_last = nullptr; c->h_last_cap = 0;
+        DFT_CHECK(cudaMallocHost((void**)&c->h_last, sizeof(dftatom_step) * n_rec));
+        c->h_last_cap = n_rec;
+    }
+    if (!steps) launch_gather_last_steps(b, c->last_steps.as<dftatom_step>(), st);
+    DFT_CHECK(cudaMemcpyAsync(astate.data(), b.astate, sizeof(AtomState) * n_atoms, cudaMemcpyDeviceToHost, st));
+    DFT_CHECK(cudaMemcpyAsync(c->h_last, steps ? (const void*)b.steps : c->last_steps.p, sizeof(dftatom_step) * n_rec, cudaMemcpyDeviceToHost, st));
+    DFT_CHECK(cudaStreamSynchronize(st));
+    c->last_d2h_bytes = (long long)(sizeof(AtomState) * n_atoms + sizeof(dftatom_step) * n_rec);
     for (int a = 0; a < n_atoms; ++a) {
         dftatom_result& R = out[a];
         std::memset(&R, 0, sizeof(R));
         R.status = astate[a].status;
         R.n_steps = astate[a].n_steps;
         R.n_spin = atoms[a].n_spin;
-        const dftatom_step& last = hsteps[(size_t)a * stride + std::max(0, R.n_steps - 1)];
+        const dftatom_step& last = steps ? c->h_last[(size_t)a * stride + std::max(0, R.n_steps - 1)] : c->h_last[a];
         for (int s = 0; s < R.n_spin; ++s) {
             const auto& L = s ? lev_b[a] : lev_a[a];
             R.n_levels[s] = (int)L.size();
@@ -526,7 +642,7 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
         R.Etotal = last.Etotal; R.Ekin = last.Ekin; R.Ecoul = last.Ecoul; R.Eenuc = last.Eenuc; R.Exc = last.Exc;
         if (steps) {
             const int ncopy = std::min(steps_stride, stride);
-            std::memcpy(steps + (size_t)a * steps_stride, &hsteps[(size_t)a * stride], sizeof(dftatom_step) * ncopy);
+            std::memcpy(steps + (size_t)a * steps_stride, &c->h_last[(size_t)a * stride], sizeof(dftatom_step) * ncopy);
         }
     }
     (void)steps_enqueued;
@@ -552,11 +668,7 @@ int dftatom_solve_batch(dftatom_ctx* c, const dftatom_options* opts, int n_atoms
     }
     if (!c->child) { int rc = dftatom_create(&c->child, c->device); if (rc) return rc; }
     dftatom_ctx* ch = c->child;
-    ch->max_vcycles = c->max_vcycles; ch->floor_stop = c->floor_stop; ch->refine_vcycles = c->refine_vcycles; ch->warm_vcycles = c->warm_vcycles;
-    ch->warm_after = c->warm_after; ch->team_poisson = c->team_poisson; ch->r_segments = c->r_segments; ch->seg_threshold = c->seg_threshold;
-    ch->profile = c->profile; ch->search_mode = c->search_mode; ch->match_mode = c->match_mode; ch->energies_per_lane = c->energies_per_lane;
-    ch->warm_start = c->warm_start; ch->stream_variant = c->stream_variant; ch->stream_poisson = c->stream_poisson;
-    ch->stream_min_dens = c->stream_min_dens; ch->stream_groups = 1;
+    ch->k = c->k; ch->stream_groups = 1;
     // deal the atoms in order of decreasing cost (orbital count ~ Z; LSDA doubles it) alternately into the two groups
     std::vector<int> order(n_atoms);
     std::iota(order.begin(), order.end(), 0);
@@ -717,8 +829,8 @@ int dftatom_level_search(dftatom_ctx* c, const double* V, int levels, double del
     if ((rc = setup_single(c, g, V, Z, orbs, &da, &ds, &dorb, &dss, &datab))) return rc;
     launch_search_init(g, da, ds, dorb, dss, n_levels, st);
     const int rounds = search_rounds_needed(Z);
-    if (c->search_mode == 0 && c->segments(g.N) > 1) launch_search_seg(g, datab, da, dorb, ds, dss, n_levels, nullptr, c->segments(g.N), nullptr, 0, 0, st);
-    else if (c->search_mode == 0) launch_search_fused(g, datab, da, dorb, ds, dss, n_levels, nullptr, nullptr, 0, 0, st);
+    if (c->k.search_mode == 0 && c->segments(g.N) > 1) launch_search_seg(g, datab, da, dorb, ds, dss, n_levels, nullptr, c->segments(g.N), nullptr, 0, 0, st);
+    else if (c->k.search_mode == 0) launch_search_fused(g, datab, da, dorb, ds, dss, n_levels, nullptr, nullptr, 0, 0, st);
     else for (int r = 0; r < rounds; ++r) launch_search_round(g, datab, dorb, ds, dss, n_levels, nullptr, st);
     std::vector<SearchState> h(n_levels);
     DFT_CHECK(cudaMemcpyAsync(h.data(), dss, sizeof(SearchState) * n_levels, cudaMemcpyDeviceToHost, st));
@@ -747,8 +859,8 @@ int dftatom_numerov_orbital(dftatom_ctx* c, const double* V, int levels, double 
     // single-atom ScfBuffers so that density_update's normalisation path is the one exercised
     if ((rc = c->psi.ensure(sizeof(double) * N)) || (rc = c->match_pt.ensure(sizeof(int)))) return rc;
     if ((rc = c->inv_norm.ensure(sizeof(double)))) return rc;
-    if (c->match_mode == 0) launch_match_cta(g, datab, dorb, ds, dss, c->psi.as<double>(), c->match_pt.as<int>(), c->inv_norm.as<double>(), 1, st);
-    else if (c->match_mode == 2) launch_match_seg(g, datab, dorb, ds, dss, c->psi.as<double>(), c->match_pt.as<int>(), 1, st);
+    if (c->k.match_mode == 0) launch_match_cta(g, datab, dorb, ds, dss, c->psi.as<double>(), c->match_pt.as<int>(), c->inv_norm.as<double>(), 1, st);
+    else if (c->k.match_mode == 2) launch_match_seg(g, datab, dorb, ds, dss, c->psi.as<double>(), c->match_pt.as<int>(), 1, st);
     else launch_match(g, datab, dorb, ds, dss, c->psi.as<double>(), c->match_pt.as<int>(), 1, st);
     std::vector<double> y(N), sq(N), wj(N);
     int mp = 0;
@@ -782,36 +894,51 @@ int dftatom_poisson_solve(dftatom_ctx* c, int levels, double delta, double max_r
     DFT_CHECK(cudaMemcpyAsync(dz.p, Z, sizeof(int) * n_dens, cudaMemcpyHostToDevice, st));
     PoissonArgs pa{};
     pa.n_dens = n_dens; pa.rho = dr.as<double>(); pa.Zbc = dz.as<int>(); pa.phi = c->phi.as<double>(); pa.src = c->src.as<double>();
-    pa.max_vcycles = c->max_vcycles; pa.floor_stop = c->floor_stop; pa.vcycles_used = dv.as<int>();
+    pa.max_vcycles = c->k.max_vcycles; pa.floor_stop = c->k.floor_stop; pa.vcycles_used = dv.as<int>();
     if ((rc = c->u0.ensure(sizeof(double) * (size_t)n_dens * N)) || (rc = c->ubuf.ensure(sizeof(double) * (size_t)n_dens * N))) return rc;
-    pa.refine_vcycles = c->refine_vcycles; pa.u0 = c->u0.as<double>(); pa.u_out = c->ubuf.as<double>(); pa.coarse_op = g.coarse_op;
+    pa.refine_vcycles = c->k.refine_vcycles; pa.u0 = c->u0.as<double>(); pa.u_out = c->ubuf.as<double>(); pa.coarse_op = g.coarse_op; pa.n_sm = c->n_sm;
     if ((rc = c->team_bar.ensure(sizeof(unsigned) * (size_t)n_dens))) return rc;
-    pa.team_bar = c->team_poisson ? c->team_bar.as<unsigned>() : nullptr;
-    if (c->profile) {
+    pa.team_bar = c->k.team_poisson ? c->team_bar.as<unsigned>() : nullptr;
+    if (c->k.profile) {
         if ((rc = c->scratch[5].ensure(sizeof(long long) * 128))) return rc;
         DFT_CHECK(cudaMemsetAsync(c->scratch[5].p, 0, sizeof(long long) * 128, st));
         pa.dbg = c->scratch[5].as<long long>();
     }
-    const bool stream = c->stream_poisson && n_dens >= c->stream_min_dens && levels >= c->stream_min_levels && levels > c->stream_mid_levels && levels <= 22 && c->refine_vcycles == 0 && !c->floor_stop && !c->profile;
+    if (n_dens > 65535) { set_error("at most 65535 densities per call"); return DFTATOM_E_ARG; }
+    if (c->k.poisson_exact) {
+        // bit-reproducible mode: the reference's FullCycle in its own operation order (poisson_exact.cu), 100 V-cycles
+        if ((rc = c->exact_work.ensure(sizeof(double) * (size_t)n_dens * (size_t)exact_poisson_work_doubles(levels)))) return rc;
+        ExactPoissonArgs xa{};
+        xa.n_dens = n_dens; xa.L = levels; xa.delta = delta; xa.rho = dr.as<double>(); xa.rho_stride = N; xa.r = g.r; xa.pex = g.pex;
+        xa.Zbc = dz.as<int>(); xa.U = c->ubuf.as<double>(); xa.ldU = N; xa.work = c->exact_work.as<double>(); xa.max_vcycles = 100;
+        xa.vcycles_used = dv.as<int>();
+        launch_poisson_exact(xa, st);
+        DFT_CHECK(cudaMemcpyAsync(U, c->ubuf.p, sizeof(double) * (size_t)n_dens * N, cudaMemcpyDeviceToHost, st));
+        if (vcycles_used) DFT_CHECK(cudaMemcpyAsync(vcycles_used, dv.p, sizeof(int) * n_dens, cudaMemcpyDeviceToHost, st));
+        DFT_CHECK(cudaStreamSynchronize(st));
+        DFT_CHECK(cudaGetLastError());
+        return 0;
+    }
+    const bool stream = c->k.stream_poisson && n_dens >= c->k.stream_min_dens && levels >= c->k.stream_min_levels && levels > c->k.stream_mid_levels && levels <= 22 && c->k.refine_vcycles == 0 && !c->k.floor_stop && !c->k.profile;
     if (stream) {
         // grids beyond the chip: level visits streamed over all densities (poisson_stream.cu)
-        const StreamPlan splan = make_stream_plan(levels, n_dens, c->stream_mid_levels);
+        const StreamPlan splan = make_stream_plan(levels, n_dens, c->k.stream_mid_levels);
         const long long ld = (N + 3) & ~3;
         if ((rc = c->stream_src0.ensure(sizeof(double) * (size_t)n_dens * ld)) || (rc = c->stream_scratch.ensure(sizeof(double) * (size_t)splan.total))) return rc;
         if ((rc = c->ubuf.ensure(sizeof(double) * (size_t)n_dens * ld))) return rc;
         StreamSolveArgs sa{};
         sa.n_dens = n_dens; sa.rho = dr.as<double>(); sa.rho_stride = N; sa.psrc = g.psrc; sa.src0 = c->stream_src0.as<double>();
         sa.U = c->ubuf.as<double>(); sa.ld0 = ld; sa.Zbc = dz.as<int>(); sa.scratch = c->stream_scratch.as<double>(); sa.coarse_op = g.coarse_op;
-        sa.n_v = c->max_vcycles; sa.warm = 0; sa.variant = c->stream_variant;
+        sa.n_v = c->k.max_vcycles; sa.warm = 0; sa.variant = c->k.stream_variant;
         launch_poisson_stream_solve(splan, delta, sa, st, nullptr);
         DFT_CHECK(cudaMemcpy2DAsync(U, sizeof(double) * N, c->ubuf.p, sizeof(double) * ld, sizeof(double) * N, n_dens, cudaMemcpyDeviceToHost, st));
-        if (vcycles_used) for (int k = 0; k < n_dens; ++k) vcycles_used[k] = c->max_vcycles;
+        if (vcycles_used) for (int k = 0; k < n_dens; ++k) vcycles_used[k] = c->k.max_vcycles;
         DFT_CHECK(cudaStreamSynchronize(st));
         DFT_CHECK(cudaGetLastError());
         return 0;
     }
     launch_poisson_full(g, lv, pa, st);
-    if (c->profile) {
+    if (c->k.profile) {
         long long h[128];
         DFT_CHECK(cudaMemcpyAsync(h, pa.dbg, sizeof(h), cudaMemcpyDeviceToHost, st));
         DFT_CHECK(cudaStreamSynchronize(st));
@@ -820,11 +947,11 @@ int dftatom_poisson_solve(dftatom_ctx* c, int levels, double delta, double max_r
             fprintf(stderr, "  level %2d n=%7d  smooth %9lld (%lld visits)  restrict_to %8lld  prolong_from %8lld\n", l, (1 << (levels - l)), h[l], h[72 + l], h[24 + l], h[48 + l]);
         if (getenv("DFTATOM_DEBUG_WARM")) {      // the SCF's steady state: warm_vcycles V-cycles from the solution just computed
             DFT_CHECK(cudaMemsetAsync(pa.dbg, 0, sizeof(long long) * 128, st));
-            pa.warm_vcycles = c->warm_vcycles;
+            pa.warm_vcycles = c->k.warm_vcycles;
             launch_poisson_full(g, lv, pa, st);
             DFT_CHECK(cudaMemcpyAsync(h, pa.dbg, sizeof(h), cudaMemcpyDeviceToHost, st));
             DFT_CHECK(cudaStreamSynchronize(st));
-            fprintf(stderr, "warm start, %d V-cycles (CTA 0): setup %lld  solve %lld  +export %lld\n", c->warm_vcycles, h[98], h[96], h[97]);
+            fprintf(stderr, "warm start, %d V-cycles (CTA 0): setup %lld  solve %lld  +export %lld\n", c->k.warm_vcycles, h[98], h[96], h[97]);
             for (int l = 0; l < levels; ++l)
                 fprintf(stderr, "  level %2d n=%7d  visits %9lld cycles (%lld visits)\n", l, (1 << (levels - l)), h[l], h[72 + l]);
         }
@@ -847,7 +974,8 @@ long long dftatom_poisson_scratch_bytes(int levels, int n_dens)
 int dftatom_poisson_vcycles(dftatom_ctx* c, int levels, double delta, int n_dens, double* phi, const double* src, int n_cycles,
                             double* last_err)
 {
-    if (!c || !phi || !src || n_dens <= 0) return DFTATOM_E_ARG;
+    if (!c || !phi || !src || n_dens <= 0 || n_dens > 65535) return DFTATOM_E_ARG;
+    if (levels < 1 || levels > 22 || !(delta >= 0.) || !std::isfinite(delta)) { set_error("bad grid: need 1 <= levels <= 22, finite delta >= 0"); return DFTATOM_E_BAD_OPTION; }
     DFT_CHECK(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     const PoissonLevels lv = make_levels(levels);
@@ -876,7 +1004,7 @@ int dftatom_poisson_vcycles_dev(dftatom_ctx* c, int levels, double delta, int n_
     if (levels < 15 || levels > 22) { set_error("stream-mode V-cycles need 15 <= levels <= 22 (smaller grids are solved on chip: dftatom_poisson_vcycles)"); return DFTATOM_E_BAD_OPTION; }
     const long long N = (1ll << levels) + 1;
     if (ld < N || (ld & 1) || ((uintptr_t)d_phi & 15) || ((uintptr_t)d_src & 15) || ((uintptr_t)d_scratch & 15)) { set_error("ld must be even and >= N, pointers 16-byte aligned"); return DFTATOM_E_ARG; }
-    const StreamPlan sp = make_stream_plan(levels, n_dens, c->stream_mid_levels);
+    const StreamPlan sp = make_stream_plan(levels, n_dens, c->k.stream_mid_levels);
     if (scratch_bytes < (long long)sizeof(double) * sp.total) { set_error("scratch too small"); return DFTATOM_E_ARG; }
     DFT_CHECK(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
@@ -892,7 +1020,7 @@ int dftatom_poisson_vcycles_dev(dftatom_ctx* c, int levels, double delta, int n_
     DFT_CHECK(cudaEventRecord(e0, st));
     long long nl = 0;
     launch_poisson_stream_vcycles(sp, delta, n_dens, (double*)d_phi, (const double*)d_src, ld, (double*)d_scratch, c->stream_G.as<double>(),
-                                  n_cycles, fuse_tops, c->stream_variant, st, &nl);
+                                  n_cycles, fuse_tops, c->k.stream_variant, st, &nl);
     DFT_CHECK(cudaEventRecord(e1, st));
     DFT_CHECK(cudaStreamSynchronize(st));
     DFT_CHECK(cudaGetLastError());

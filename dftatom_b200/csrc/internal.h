@@ -36,6 +36,7 @@ struct GridDev {
     double* wjac;    // simpson38 weight_i * Rp δ e^{δ i}            (Integral.h:50-73 × jacobian DFTAtom.cpp:47,442)
     double* psrc;    // r_i * 4π K_i  (0 at i=0 and i=N-1)           (PoissonSolver.h:55-74)
     double* inv4pr2; // 1 / (4π r_i^2) (0 at i=0)                    (DFTAtom.cpp:340)
+    double* pex;     // 4π Rp²δ² · e^{2δ i} in the reference's own product order (PoissonSolver.h:66-74; uniform grid: h² 4π, :26-40): poisson_exact.cu
     double* coarse_op; // [32*32] dense operator of the Poisson sub-cycle below the 32-node level (poisson.cu), NULL for L < 6
 };
 
@@ -135,6 +136,7 @@ struct PoissonArgs {
     int skip_stride_bytes;
     int max_vcycles; int floor_stop;
     int warm_vcycles;       // > 0: keep Phi_0 of the previous solve as the initial guess and run this many V-cycles (no FMG ramp)
+    int n_sm;               // SM count of the context's device (team mode sizing); 0: 148
     int team_G;             // set by the launcher: CTAs per density (team mode, poisson.cu), 1 = off
     unsigned* team_bar;     // [n_dens] scratch for the team barriers (or NULL: no team mode)
     int smem_doubles;       // set by the launcher: doubles per shared-memory array of the coarse levels
@@ -197,6 +199,45 @@ struct StreamSolveArgs {
 };
 void launch_poisson_stream_solve(const StreamPlan& sp, double delta, const StreamSolveArgs& a, cudaStream_t st, long long* launches);
 
+// Poisson, bit-reproducible mode (poisson_exact.cu): the reference's FullCycle in its own operation order, U equal bit for bit
+struct ExactPoissonArgs {
+    int n_dens, L;
+    double delta;            // deltaGrid (0: uniform grid)
+    const double* rho; long long rho_stride;    // [n_dens][rho_stride] densities, natural node order
+    const double* r; const double* pex;         // grid tables (GridDev.r, GridDev.pex)
+    const int* Zbc;          // [n_dens] boundary value at Rmax
+    double* U; long long ldU;                   // [n_dens][ldU] result
+    double* work;            // n_dens * exact_poisson_work_doubles(L) doubles
+    const int* skip; int skip_stride_bytes;
+    int max_vcycles;         // 100 = the reference (PoissonSolver.h:117)
+    int* vcycles_used;       // optional [n_dens]
+};
+long long exact_poisson_work_doubles(int L);
+void launch_poisson_exact(const ExactPoissonArgs& a, cudaStream_t st);
+
+// Poisson, cluster mode (poisson_cluster.cu): warm-started V-cycles for 2049 .. 16385 nodes, one cluster of 8 CTAs per density, the
+// hierarchy resident in distributed shared memory
+struct ClusterPoissonArgs {
+    int n_dens;
+    const double* rho; long long rho_stride;    // [n_dens][rho_stride] total densities, natural node order
+    double* U; long long ldU;                   // [n_dens][ldU] in: previous solution (initial guess), out: U(r)
+    const int* Zbc;                             // [n_dens] boundary value at Rmax
+    const double* coarse_op;                    // GridDev.coarse_op
+    const int* skip; int skip_stride_bytes;
+    int n_vcycles;
+    unsigned long long* work;                   // optional: += Gauss-Seidel node-updates
+    int smem_doubles;                           // set by the launcher
+    long long* dbg;                             // optional [8 * 32] cycle counters of the first density's CTAs (development aid)
+};
+bool poisson_cluster_supported(int L, double delta);
+void launch_poisson_cluster(const GridDev& g, const ClusterPoissonArgs& a, cudaStream_t st);
+int poisson_cluster_init_device();
+
+// per-device kernel attributes (opt-in dynamic shared memory): called once per context from dftatom_create under cudaSetDevice
+int poisson_init_device();
+int stream_init_device();
+int match_init_device();
+
 // XC
 void launch_vwn(int n, const double* ra, const double* rb, double* va, double* vb, double* vexc, double* edif, cudaStream_t st);
 void launch_chachiyo(int n, const double* rho, int improved, double* vexc, double* edif, cudaStream_t st);
@@ -224,7 +265,9 @@ struct ScfBuffers {
     dftatom_step* steps;  // [n_atoms][steps_stride]
     int steps_stride;
     int* n_active;    // device counter of atoms not done
+    int run_to_cap;   // != 0: the stop test is recorded in dftatom_step.stop_criterion_met but never ends the SCF
 };
+void launch_gather_last_steps(const ScfBuffers& b, dftatom_step* out, cudaStream_t st);
 void launch_initial_density(const GridDev& g, const ScfBuffers& b, cudaStream_t st);
 void launch_orbital_norms(const GridDev& g, const ScfBuffers& b, cudaStream_t st);
 void launch_density_update(const GridDev& g, const ScfBuffers& b, cudaStream_t st);

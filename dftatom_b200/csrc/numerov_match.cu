@@ -684,18 +684,25 @@ __global__ void __launch_bounds__(kMT) match_win_kernel(GridDev g, const double*
     }
 }
 
+// Opt-in to large dynamic shared memory is per-device state: set once per device from dftatom_create (under cudaSetDevice), not
+// cached in a process-wide static (a second context on another GPU would otherwise never get it).
+constexpr size_t kMatchCtaMaxBytes = 200 * 1024;
+int match_init_device()
+{
+    const size_t wb = ((size_t)kWinNodes + 2 + (size_t)(kWinNodes + 2) / 32 + 8) * sizeof(double);
+    DFT_CHECK(cudaFuncSetAttribute(match_cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMatchCtaMaxBytes));
+    DFT_CHECK(cudaFuncSetAttribute(match_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wb));
+    return 0;
+}
+
 void launch_match_cta(const GridDev& g, const double* atab, const OrbitalDev* orbs, const AtomState* astate, const SearchState* ss,
                       double* psi, int* match_pt, double* inv_norm, int n_orbs, cudaStream_t st)
 {
     const size_t bytes = ((size_t)g.N + (size_t)g.N / 32 + 8) * sizeof(double);
-    if (bytes <= 200 * 1024) {
-        static size_t attr_bytes = 0;
-        if (bytes > attr_bytes) { cudaFuncSetAttribute(match_cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); attr_bytes = bytes; }
+    if (bytes <= kMatchCtaMaxBytes) {
         match_cta_kernel<true><<<n_orbs, kMT, bytes, st>>>(g, atab, orbs, astate, const_cast<SearchState*>(ss), psi, match_pt, inv_norm, n_orbs);
     } else {
         const size_t wb = ((size_t)kWinNodes + 2 + (size_t)(kWinNodes + 2) / 32 + 8) * sizeof(double);
-        static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(match_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wb); attr = true; }
         match_win_kernel<<<n_orbs, kMT, wb, st>>>(g, atab, orbs, astate, const_cast<SearchState*>(ss), psi, match_pt, inv_norm, n_orbs);
     }
 }

@@ -1409,14 +1409,11 @@ void launch_poisson_full(const GridDev& g, const PoissonLevels& lv, const Poisso
     // be resident).  Needs the dense coarse operator (fused visits), no norm / refinement requests, and a barrier array.
     a.team_G = 1;
     const int n0 = lv.size[0] - 1;
-    static int n_sm = 0;
-    if (n_sm == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+    const int n_sm = a.n_sm > 0 ? a.n_sm : 148;
     if (n0 > kTeamLevelNodes && a.team_bar != nullptr && a.coarse_op != nullptr && !a.floor_stop && !a.last_err && a.refine_vcycles == 0) {
         const int G = std::min(41, n_sm / std::max(1, a.n_dens));
         if (G >= 2 && team_npt(n0, 6, G - 1) != 0) { a.team_G = G; bytes = kMaxDynBytes; }
     }
-    static size_t attr_bytes = 0;
-    if (bytes > attr_bytes) { cudaFuncSetAttribute(poisson_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); attr_bytes = bytes; }
     if (a.team_G > 1) {
         cudaMemsetAsync(a.team_bar, 0, sizeof(unsigned) * a.n_dens, st);
         GridDev gg = g; PoissonLevels ll = lv;
@@ -1466,8 +1463,6 @@ void launch_poisson_mid(const PoissonLevels& lv, double delta, int K, int n_dens
 {
     const int sd = dyn_doubles_for(lv);
     const size_t bytes = (size_t)sd * sizeof(double);
-    static size_t attr_bytes = 0;
-    if (bytes > attr_bytes) { cudaFuncSetAttribute(poisson_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); attr_bytes = bytes; }
     poisson_mid_kernel<<<n_dens, kPT, bytes, st>>>(delta, lv, K, nat_phi, nat_src, nat_stride, mid_phi, mid_src, mid_total, coarse_op, sd, skip, skip_stride_bytes);
 }
 
@@ -1496,9 +1491,16 @@ void launch_poisson_vcycles(const PoissonLevels& lv, double delta, int n_dens, d
 {
     const int sd = dyn_doubles_for(lv);
     const size_t bytes = (size_t)sd * sizeof(double);
-    static size_t attr_bytes = 0;
-    if (bytes > attr_bytes) { cudaFuncSetAttribute(poisson_vcycles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); attr_bytes = bytes; }
     poisson_vcycles_kernel<<<n_dens, kPT, bytes, st>>>(delta, lv, phi, src, phi_nat, src_nat, sd, n_cycles, last_err);
+}
+
+// per-device opt-in to the dynamic shared memory the solve kernels may ask for (called from dftatom_create under cudaSetDevice)
+int poisson_init_device()
+{
+    DFT_CHECK(cudaFuncSetAttribute(poisson_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynBytes));
+    DFT_CHECK(cudaFuncSetAttribute(poisson_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynBytes));
+    DFT_CHECK(cudaFuncSetAttribute(poisson_vcycles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynBytes));
+    return 0;
 }
 
 }  // namespace dft

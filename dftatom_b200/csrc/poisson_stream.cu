@@ -247,8 +247,6 @@ void launch_variant(const StreamVisitArgs& v_in, int n_dens, cudaStream_t st)
     StreamVisitArgs v = v_in;
     v.HL = v.sweeps > 3 ? 192 : 128;
     v.slab = G::W - v.HL - kHaloRight;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(stream_visit_kernel<T, NPT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem); attr = true; }
     const int slabs = (v.n + v.slab - 1) / v.slab;
     stream_visit_kernel<T, NPT, MINB><<<dim3(slabs, n_dens), T, G::smem, st>>>(v);
 }
@@ -264,6 +262,14 @@ void launch_stream_visit(const StreamVisitArgs& v, int n_dens, int variant, cuda
     if (variant == 1) launch_variant<256, 8, 3>(v, n_dens, st);
     else if (variant == 2) launch_variant<512, 8, 2>(v, n_dens, st);
     else launch_variant<256, 16, 2>(v, n_dens, st);
+}
+
+int stream_init_device()
+{   // per-device opt-in to the windows' dynamic shared memory (dftatom_create, under cudaSetDevice)
+    DFT_CHECK(cudaFuncSetAttribute(stream_visit_kernel<256, 8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StreamGeom<256, 8>::smem));
+    DFT_CHECK(cudaFuncSetAttribute(stream_visit_kernel<512, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StreamGeom<512, 8>::smem));
+    DFT_CHECK(cudaFuncSetAttribute(stream_visit_kernel<256, 16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StreamGeom<256, 16>::smem));
+    return 0;
 }
 
 StreamPlan make_stream_plan(int L, int n_dens, int mid_levels)

@@ -464,7 +464,9 @@ __global__ void __launch_bounds__(kPT2) potential_energy_kernel(GridDev g, Poiss
         rec->Etotal = etot; rec->Ekin = eel - e_pot; rec->Ecoul = -e_har; rec->Eenuc = e_nuc; rec->Exc = e_xc;
         const int ok = rec->levels_converged;
         int done = 0, status = DFTATOM_MAX_STEPS;
-        if (fabs((as.e_old - etot) / etot) < kTotalEnergyTol && ok && as.prev_ok) { done = 1; status = DFTATOM_CONVERGED; }   // :474
+        const int crit = fabs((as.e_old - etot) / etot) < kTotalEnergyTol && ok && as.prev_ok;                                // :474
+        rec->stop_criterion_met = crit;
+        if (crit && !b.run_to_cap) { done = 1; status = DFTATOM_CONVERGED; }
         as.e_old = etot;
         as.prev_ok = ok;
         as.n_steps += 1;
@@ -472,6 +474,19 @@ __global__ void __launch_bounds__(kPT2) potential_energy_kernel(GridDev g, Poiss
         if (!done && !(fabs(etot) <= 1.7e308)) { done = 1; status = DFTATOM_NUMERIC_FAILURE; }
         if (done) { as.done = 1; as.status = status; atomicAdd(b.n_active, -1); atomicAdd(b.n_active + 1, -(at.orb_count[0] + at.orb_count[1])); }
     }
+}
+
+// last "Step:" record of every atom, compact (what dftatom_solve_batch downloads when the caller did not ask for the steps)
+__global__ void gather_last_steps_kernel(ScfBuffers b, dftatom_step* out)
+{
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= b.n_atoms) return;
+    const int n = b.astate[a].n_steps;
+    out[a] = b.steps[(size_t)a * b.steps_stride + (n > 0 ? n - 1 : 0)];
+}
+void launch_gather_last_steps(const ScfBuffers& b, dftatom_step* out, cudaStream_t st)
+{
+    gather_last_steps_kernel<<<(b.n_atoms + 127) / 128, 128, 0, st>>>(b, out);
 }
 
 void launch_potential_energy(const GridDev& g, const PoissonLevels& lv, const ScfBuffers& b, int first, cudaStream_t st)

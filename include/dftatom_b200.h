@@ -64,7 +64,8 @@ typedef struct {
     double E[2][DFTATOM_MAX_LEVELS];   /* eigenvalues, [spin][level in (n,l) order] */
     double Etotal, Ekin, Ecoul, Eenuc, Exc;
     int levels_converged;              /* reallyConverged of this step (DFTAtom.cpp:406,538) */
-    int reserved;
+    int stop_criterion_met;            /* 1 if the "Finished!" test of DFTAtom.cpp:474 holds at this step (always the last step of a converged
+                                          run; with set_option("run_to_cap", 1) the SCF continues past it and later steps may carry it too) */
 } dftatom_step;
 
 typedef struct {
@@ -115,6 +116,12 @@ const char* dftatom_version(void);
  *                   (poisson_stream.cu: slab windows with halos, one launch per level visit) for the levels above
  *                   2^"stream_mid_levels" (default 11, 11..14) nodes and one CTA per density below, instead of one CTA / team
  *                   of CTAs per density for everything; 0 = never
+ *   "poisson_exact" (default 0) 1 = bit-reproducible Poisson solve (poisson_exact.cu): the reference's FullCycle in the reference's own
+ *                   floating-point operation order (no FMA), with its early exits and its 100 V-cycles; U(r) equals the CPU reference's
+ *                   bit for bit (tests/test_gpu_components.py).  A parity / validation mode, ~50x slower than the production solver.
+ *   "run_to_cap"   (default 0) 1 = the stop test of DFTAtom.cpp:474 is evaluated and recorded (dftatom_step.stop_criterion_met) but does
+ *                   not end the SCF: every atom runs to the step cap.  Lets a test compare the record at the step where the REFERENCE
+ *                   stopped, whatever step this implementation's own (noise-driven) stop fires at.
  *   "stream_variant" (default 0) window shape of the stream-mode Poisson visits: 0 = 256 threads x 16 nodes, 1 = 256 x 8, 2 = 512 x 8
  */
 int dftatom_set_option(dftatom_ctx* ctx, const char* key, double value);
@@ -134,6 +141,9 @@ int dftatom_solve_batch(dftatom_ctx* ctx, const dftatom_options* opts, int n_ato
                         dftatom_step* steps, int steps_stride);
 /* device time (ms, CUDA events) of the last solve_batch's SCF loop, and number of kernel launches it issued */
 int dftatom_last_timing(dftatom_ctx* ctx, double* device_ms, long long* kernel_launches);
+/* bytes the last solve_batch copied host -> device (atom / orbital descriptors; grid tables are cached per context and not counted)
+ * and device -> host (per-atom state + step records: every step when `steps` was given, else the last record of every atom) */
+int dftatom_last_transfer(dftatom_ctx* ctx, long long* h2d_bytes, long long* d2h_bytes);
 
 /* Per-kernel-class profile of the last solve_batch, filled when set_option("profile", 1) was on: device time of
  * every launch of the class (CUDA events on the launching stream), launch count and algorithmic work

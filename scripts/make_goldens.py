@@ -6,7 +6,8 @@ usage: python scripts/make_goldens.py NAME [--jobs J]
   NAME in: small, argon, radon, sweep, lsda_batch, uniform
 Writes tests/golden/<NAME>.json.  Each atom record holds every SCF step the reference printed
 (eigenvalues + five energies, 17 significant digits) unless --final-only semantics apply (sweep,
-lsda_batch keep per-step Etotal and eigenvalues of the last step only, to keep fixtures small).
+lsda_batch keep compact per-step arrays - the five energies and all eigenvalues of every step - plus the full record of the
+last step, to keep fixtures small).
 """
 import argparse
 import json
@@ -69,6 +70,7 @@ def main():
     if a.name in FINAL_ONLY:
         for r in res:
             r["etotal_per_step"] = [s["Etotal"] for s in r["steps"]]
+            r["energies_per_step"] = [[s[k] for k in ("Etotal", "Ekin", "Ecoul", "Eenuc", "Exc")] for s in r["steps"]]
             r["eig_per_step"] = [[l["E"] for l in s["levels"]] for s in r["steps"]]
             r["steps_kept"] = "last"
             r["n_steps"] = len(r["steps"])

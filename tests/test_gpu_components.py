@@ -279,3 +279,38 @@ def test_poisson_uniform_grid_matches_oracle(ctx, L, rmax):
         assert abs(np.max(np.abs(U[j] - U_x)) - np.max(np.abs(U_o - U_x))) < 1e-8 * Z
         assert U[j][0] == 0.0 and U[j][-1] == Z
 
+
+
+@pytest.mark.parametrize("L,delta,rmax", [(8, 0.02, 10.0), (10, 0.004, 15.0), (14, 0.0005, 25.0), (16, 0.0002, 50.0), (17, 0.0001, 50.0),
+                                          (12, 0.0, 15.0), (14, 0.0, 25.0)])
+def test_poisson_exact_mode_is_bit_identical(ctx, L, delta, rmax):
+    """set_option("poisson_exact", 1): the reference's FullCycle (Initialize, FMG ramp with its 1e-3 early exits, 100 V-cycles) in the
+    reference's own floating-point operation order (PoissonSolver.cpp:40-157, .h:51-124), chunk-parallel with a 128-node warm-up halo:
+    U(r) must equal the CPU solver's BIT FOR BIT - against the C restatement and, where oracle/_ref was built, against the unmodified
+    reference's own PoissonSolver class.  delta = 0: SolvePoissonUniform (.h:20-49)."""
+    N = (1 << L) + 1
+    if delta > 0:
+        _, rp, r = O.grid(L, delta, rmax)
+    else:
+        r = np.arange(N) * (rmax / (N - 1))
+    Zs = [1, 18, 86]
+    rng = np.random.default_rng(L)
+    # shell-like densities with rough (non-smooth) multiplicative noise: the bits must agree whatever the input
+    rho = np.stack([Z * k ** 3 / np.pi * np.exp(-2 * k * r) * (1 + 1e-3 * rng.standard_normal(N)) for Z, k in zip(Zs, [0.8, 1.7, 3.1])])
+    ctx.set_option("poisson_exact", 1)
+    try:
+        U, used = ctx.poisson_solve(L, delta, rmax, Zs, rho)
+    finally:
+        ctx.set_option("poisson_exact", 0)
+    ref = O.ref_components()
+    for j, Z in enumerate(Zs):
+        if delta > 0:
+            U_o, errs = O.poisson(L, delta, rmax, Z, rho[j], max_vcycles=100)
+            assert used[j] == len(errs)
+        else:
+            U_o = O.poisson_uniform(L, rmax, Z, rho[j], max_vcycles=100)
+        assert np.array_equal(U[j], U_o), (L, Z, np.max(np.abs(U[j] - U_o)))
+        if ref is not None and delta > 0:
+            U_r = np.zeros(N)
+            ref.ref_poisson_nonuniform(L, delta, int(Z), rmax, O.d(np.ascontiguousarray(rho[j])), O.d(U_r))
+            assert np.array_equal(U[j], U_r)
