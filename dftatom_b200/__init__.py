@@ -15,14 +15,16 @@ from .api import (  # noqa: F401
     Result,
     Step,
     aufbau,
+    estimate_cost,
     lib_path,
     load_library,
     n_nodes,
+    partition,
     split_spin,
 )
 from .report import format_report, parse_report  # noqa: F401
 
 __all__ = [
     "Context", "DFTAtom", "DFTAtomError", "Level", "Options", "Result", "Step", "aufbau", "split_spin", "n_nodes",
-    "lib_path", "load_library", "format_report", "parse_report",
+    "lib_path", "load_library", "format_report", "parse_report", "estimate_cost", "partition",
 ]

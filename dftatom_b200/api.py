@@ -75,6 +75,9 @@ def load_library():
     lib.dftatom_aufbau.argtypes = [C.c_int, C.POINTER(_CLevel), C.c_int]
     lib.dftatom_split_spin.argtypes = [C.c_int, C.POINTER(_CLevel), _ip, C.POINTER(_CLevel), _ip, _ip, _ip]
     lib.dftatom_n_nodes.argtypes = [C.c_int]
+    lib.dftatom_estimate_cost.argtypes = [C.c_int, C.c_int]
+    lib.dftatom_estimate_cost.restype = C.c_double
+    lib.dftatom_partition.argtypes = [_ip, _ip, C.c_int, C.c_int, _ip]
     lib.dftatom_solve_batch.argtypes = [C.c_void_p, C.POINTER(_COptions), C.c_int, C.POINTER(_CResult), C.POINTER(_CStep), C.c_int]
     lib.dftatom_last_timing.argtypes = [C.c_void_p, _dp, C.POINTER(C.c_longlong)]
     lib.dftatom_last_transfer.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
@@ -209,6 +212,18 @@ def split_spin(Z: int):
     na, nb, ea, eb = C.c_int(), C.c_int(), C.c_int(), C.c_int()
     _check(lib.dftatom_split_spin(int(Z), a, C.byref(na), b, C.byref(nb), C.byref(ea), C.byref(eb)))
     return _levels_from_c(a, na.value), _levels_from_c(b, nb.value), ea.value, eb.value
+
+
+def estimate_cost(Z: int, method: int = 0) -> float:
+    """Relative cost of one atom for sharding: (spin) orbitals x expected SCF steps (dftatom_estimate_cost)."""
+    return float(load_library().dftatom_estimate_cost(int(Z), int(method)))
+
+
+def partition(Zs, methods, n_ranks: int):
+    """rank of every atom, longest-processing-time-first on dftatom_estimate_cost (dftatom_partition)."""
+    z = _i32(Zs); m = _i32(methods); out = np.zeros(len(z), np.int32)
+    _check(load_library().dftatom_partition(_i(z), _i(m), len(z), int(n_ranks), _i(out)))
+    return [int(x) for x in out]
 
 
 def n_nodes(levels: int) -> int:

@@ -81,4 +81,50 @@ int split_spin(int Z, dftatom_level* a, int* na, dftatom_level* b, int* nb, int*
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Sharding of a batch of independent atoms over G GPUs (one process per GPU, no collective).
+// Cost of an atom = (spin) orbitals x expected SCF steps.  Which atoms take 60-150 steps instead of ~35 is physics, not Z: the
+// NODELESS compact d / f shells (3d, 4f: n = l + 1) slosh under linear mixing when they are nearly full (Cu, Zn: 89 / 69 steps,
+// Ho .. Yb: 77 .. 100 steps of the reference's sweep; their 4d / 5d / 5f counterparts do not).  Only used to balance
+// shards - a wrong estimate costs time, never results.
+// ---------------------------------------------------------------------------------------------------------
+double estimate_cost(int Z, int method)
+{
+    if (Z < 1 || Z > 118) return 0.;
+    const std::vector<Shell> v = fill(Z);
+    int n_orb = 0;
+    for (const Shell& s : v) n_orb += (method && s.occ > 2 * s.l + 1) ? 2 : 1;
+    // the subshells in Madelung (filling) order: the one filled last, and the one before it
+    std::vector<const Shell*> order;
+    for (const Shell& s : v) order.push_back(&s);
+    std::sort(order.begin(), order.end(), [](const Shell* a, const Shell* b) { return a->n0 + a->l != b->n0 + b->l ? a->n0 + a->l < b->n0 + b->l : a->n0 < b->n0; });
+    double steps = method ? 50. : 36.;
+    for (size_t q = order.size() >= 2 ? order.size() - 2 : 0; q < order.size(); ++q) {
+        const Shell& s = *order[q];
+        if (s.l < 1 || s.n0 != s.l) continue;                   // nodeless: n = l + 1 (n0 is 0-based)
+        const bool is_last = q + 1 == order.size();
+        const double x = (double)s.occ / (double)(2 * (2 * s.l + 1));
+        if (x > 0.7) steps += (method ? 100. : 65.) * (x - 0.7) / 0.3 * (s.l >= 2 ? 1. : 0.2) * (is_last ? 1. : 0.4);
+    }
+    return (double)n_orb * steps;
+}
+
+// longest-processing-time-first: atoms in order of decreasing cost, each to the least loaded rank; deterministic
+int partition_atoms(const int* Z, const int* method, int n, int n_ranks, int* rank_of)
+{
+    if (!Z || !rank_of || n < 0 || n_ranks < 1) return DFTATOM_E_ARG;
+    std::vector<double> cost(n);
+    std::vector<int> order(n);
+    for (int i = 0; i < n; ++i) { cost[i] = estimate_cost(Z[i], method ? method[i] : 0); order[i] = i; }
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+    std::vector<double> load(n_ranks, 0.);
+    for (int i : order) {
+        int r = 0;
+        for (int q = 1; q < n_ranks; ++q) if (load[q] < load[r]) r = q;
+        rank_of[i] = r;
+        load[r] += cost[i];
+    }
+    return 0;
+}
+
 }  // namespace dft

@@ -11,6 +11,7 @@
 #include <mutex>
 #include <numeric>
 #include <thread>
+#include <nvtx3/nvToolsExt.h>
 
 namespace dft {
 
@@ -84,7 +85,10 @@ struct Knobs {
     int poisson_exact = 0;     // 1: bit-reproducible Poisson solve (poisson_exact.cu): the reference's FullCycle in its own operation order, 100 V-cycles
     int run_to_cap = 0;        // 1: the stop test (DFTAtom.cpp:474) is evaluated and recorded but never ends the SCF (trajectory parity beyond the stop step)
     int cluster_poisson = 1;   // warm-started solves on 2049 .. 16385 nodes: one cluster of 8 CTAs per density (poisson_cluster.cu); 0 = one CTA per density
-    int cluster_max_dens = 40; // ... while at most this many atoms are still iterating (8 CTAs per density: above ~37 densities the clusters need more than one wave of the 148 SMs and one CTA per density has the higher throughput)
+    int cluster_max_dens = 1 << 30; // ... while at most this many atoms are still iterating.  Default: always - which kernel solves a density must not depend on
+                               // what else is in the batch (an atom's records are bit-identical alone, in any batch and on any shard); a smaller
+                               // value trades that for throughput while many atoms are active (above ~37 densities the clusters need more than one wave)
+    int step_cap = 0;          // > 0: lower the SCF step cap (100 LDA / 150 LSDA, DFTAtom.cpp:396,908) to this many steps (tests: with run_to_cap, run exactly as long as the reference did)
     int use_graph = 1;         // SCF steps are replayed from a captured CUDA graph (one graph launch per step) instead of 5+ kernel launches
 };
 
@@ -277,6 +281,7 @@ int dftatom_set_option(dftatom_ctx* c, const char* key, double value)
     else if (k == "poisson_exact") c->k.poisson_exact = value != 0.;
     else if (k == "cluster_poisson") c->k.cluster_poisson = value != 0.;
     else if (k == "cluster_max_dens") c->k.cluster_max_dens = std::max(0, (int)value);
+    else if (k == "step_cap") c->k.step_cap = std::max(0, (int)value);
     else if (k == "run_to_cap") c->k.run_to_cap = value != 0.;
     else if (k == "use_graph") c->k.use_graph = value != 0.;
     else { set_error("unknown option " + k); return DFTATOM_E_ARG; }
@@ -289,6 +294,8 @@ int dftatom_split_spin(int Z, dftatom_level* a, int* na, dftatom_level* b, int* 
     return dft::split_spin(Z, a, na, b, nb, ea, eb);
 }
 int dftatom_n_nodes(int levels) { return (1 << levels) + 1; }
+double dftatom_estimate_cost(int Z, int method) { return dft::estimate_cost(Z, method); }
+int dftatom_partition(const int* Z, const int* method, int n_atoms, int n_ranks, int* rank_of) { return dft::partition_atoms(Z, method, n_atoms, n_ranks, rank_of); }
 
 int dftatom_last_timing(dftatom_ctx* c, double* ms, long long* launches)
 {
@@ -372,6 +379,7 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
         AtomDev& at = atoms[a];
         at.Z = opts[a].Z; at.method = opts[a].method; at.n_spin = opts[a].method ? 2 : 1;
         at.n_steps_max = opts[a].method ? DFTATOM_MAX_STEPS_LSDA : DFTATOM_MAX_STEPS_LDA;
+        if (c->k.step_cap > 0) at.n_steps_max = std::min(at.n_steps_max, c->k.step_cap);
         at.mixing = opts[a].mixing;
         max_steps = std::max(max_steps, at.n_steps_max);
         zmax = std::max(zmax, at.Z);
@@ -527,6 +535,10 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
     size_t span_next = 0;
     auto begin_span = [&](int cls) { if (prof) { Span s{ cls, span_ev[span_next], span_ev[span_next + 1] }; span_next += 2; cudaEventRecord(s.a, st); spans.push_back(s); } };
     auto end_span = [&]() { if (prof) cudaEventRecord(spans.back().b, st); };
+    // NVTX ranges per SCF phase (host side: they bracket the enqueue of the phase's launches)
+    static const char* const kPhase[DFTATOM_K_COUNT] = { "dftatom:search", "dftatom:match", "dftatom:density", "dftatom:poisson", "dftatom:potential" };
+    auto begin_phase = [&](int cls) { nvtxRangePushA(kPhase[cls]); begin_span(cls); };
+    auto end_phase = [&]() { end_span(); nvtxRangePop(); };
     DFT_CHECK(cudaEventRecord(ev0, st));
     // initial guess -> U -> V   (DFTAtom.cpp:371-392)
     launch_initial_density(g, b, st); ++launches;
@@ -537,7 +549,8 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
     int steps_enqueued = 0;
     const int lag = 2;
     for (int sp = 0; sp < max_steps; ++sp) {
-        begin_span(DFTATOM_K_SEARCH);
+        nvtxRangePushA("dftatom:scf_step");
+        begin_phase(DFTATOM_K_SEARCH);
         if (c->k.search_mode == 0) {
             // two shapes of the same search: serial-in-r (one warp per orbital) while many orbitals are active, parallel-in-r
             // (one cluster per orbital) once few are left.  Both are enqueued; the device-side count of active orbitals
@@ -557,8 +570,8 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
             launch_search_init(g, b.atoms, b.astate, b.orbs, b.ss, n_orbs, st); ++launches;
         }
         if (c->k.search_mode != 0) for (int r = 0; r < rounds; ++r) { launch_search_round(g, b.atab, b.orbs, b.astate, b.ss, n_orbs, d_work + DFTATOM_K_SEARCH, st); ++launches; }
-        end_span();
-        begin_span(DFTATOM_K_MATCH);
+        end_phase();
+        begin_phase(DFTATOM_K_MATCH);
         if (c->k.match_mode == 0) launch_match_cta(g, b.atab, b.orbs, b.astate, b.ss, b.psi, b.match_pt, b.inv_norm, n_orbs, st);
         else {                                              // validation paths: warp-per-orbital / reference-shaped serial solution
             if (c->k.match_mode == 2) launch_match_seg(g, b.atab, b.orbs, b.astate, b.ss, b.psi, b.match_pt, n_orbs, st);
@@ -566,16 +579,17 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
             launch_orbital_norms(g, b, st); ++launches;
         }
         ++launches;
-        end_span();
-        begin_span(DFTATOM_K_DENSITY);
+        end_phase();
+        begin_phase(DFTATOM_K_DENSITY);
         launch_density_update(g, b, st); ++launches;
-        end_span();
-        begin_span(DFTATOM_K_POISSON);
+        end_phase();
+        begin_phase(DFTATOM_K_POISSON);
         poisson_solve((sp >= c->k.warm_after) ? c->k.warm_vcycles : 0, launches);
-        end_span();
-        begin_span(DFTATOM_K_POTENTIAL);
+        end_phase();
+        begin_phase(DFTATOM_K_POTENTIAL);
         launch_potential_energy(g, lv, b, 0, st); ++launches;
-        end_span();
+        end_phase();
+        nvtxRangePop();
         DFT_CHECK(cudaMemcpyAsync(&c->h_active[sp], b.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
         DFT_CHECK(cudaEventRecord(step_ev[sp], st));
         ++steps_enqueued;

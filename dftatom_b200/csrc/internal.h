@@ -276,5 +276,7 @@ void launch_potential_energy(const GridDev& g, const PoissonLevels& lv, const Sc
 // host rules (aufbau.cpp)
 int aufbau(int Z, dftatom_level* out, int max_out);
 int split_spin(int Z, dftatom_level* a, int* na, dftatom_level* b, int* nb, int* ea, int* eb);
+double estimate_cost(int Z, int method);
+int partition_atoms(const int* Z, const int* method, int n, int n_ranks, int* rank_of);
 
 }  // namespace dft

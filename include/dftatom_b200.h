@@ -122,6 +122,10 @@ const char* dftatom_version(void);
  *   "run_to_cap"   (default 0) 1 = the stop test of DFTAtom.cpp:474 is evaluated and recorded (dftatom_step.stop_criterion_met) but does
  *                   not end the SCF: every atom runs to the step cap.  Lets a test compare the record at the step where the REFERENCE
  *                   stopped, whatever step this implementation's own (noise-driven) stop fires at.
+ *   "step_cap"     (default 0 = the reference's caps, 100 LDA / 150 LSDA steps) a lower cap on the SCF steps of every atom of the batch
+ *   "cluster_poisson" (default 1) warm-started Poisson solves on grids of 2049 .. 16385 nodes run as one thread-block cluster of 8 CTAs per
+ *                   density with the whole multigrid hierarchy in distributed shared memory (poisson_cluster.cu); 0 = one CTA per density.
+ *                   "cluster_max_dens" (default: unlimited) restricts it to steps with at most that many atoms still iterating.
  *   "stream_variant" (default 0) window shape of the stream-mode Poisson visits: 0 = 256 threads x 16 nodes, 1 = 256 x 8, 2 = 512 x 8
  */
 int dftatom_set_option(dftatom_ctx* ctx, const char* key, double value);
@@ -132,6 +136,14 @@ int dftatom_aufbau(int Z, dftatom_level* out, int max_out);
 /* DFTAtom::InitializeLevels (DFTAtom.cpp:611-638) */
 int dftatom_split_spin(int Z, dftatom_level* alpha, int* n_alpha, dftatom_level* beta, int* n_beta, int* n_alpha_el, int* n_beta_el);
 int dftatom_n_nodes(int levels);       /* PoissonSolver::GetNumberOfNodes, PoissonSolver.h:127-135 */
+
+/* ---- sharding of a batch over GPUs (host; atoms are independent: one process per GPU, no collective) ----
+ * dftatom_estimate_cost: relative cost of one atom = its (spin) orbitals x the expected number of SCF steps (the nearly full nodeless
+ * 3d / 4f shells - Cu, Zn, Ho..Yb - take 2-4x the steps of their neighbours).  dftatom_partition: longest-processing-time-first
+ * assignment of n_atoms atoms to n_ranks ranks (rank_of[i] = rank of atom i; method may be NULL = LDA); deterministic.  The estimate
+ * only balances the shards: results never depend on it. */
+double dftatom_estimate_cost(int Z, int method);
+int dftatom_partition(const int* Z, const int* method, int n_atoms, int n_ranks, int* rank_of);
 
 /* ---- L2: the SCF (replaces CalculateNonUniformLDA/LSDA for a whole batch of independent atoms) ----
  * opts[n_atoms], out[n_atoms] are HOST arrays.  steps may be NULL; otherwise it is a HOST array of

@@ -63,3 +63,12 @@ def test_reference_arm_prints_one_json_line():
     assert out == ""                                                              # ranks other than 0 exit 0 without work
     costs = bench._golden_costs()
     assert len(costs) == 92 and min(costs.values()) > 0
+    # rank 0: the pooled sweep (here cut down to two light atoms), value = atoms / wall independent of --steps
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "4", "--warmup", "0", "--ref-atoms", "1,2"],
+                         capture_output=True, text=True, env=dict(os.environ, RANK="0"), check=True).stdout
+    line = json.loads(out.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "atoms/s" and line["higher_is_better"] is True and line["gpu_launches"] == 0
+    cb = line["cpu_baseline"]
+    assert cb["complete"] is True and cb["atoms_finished"] == 2 and cb["kind"] in ("reference", "port") and cb["cores"] >= 1
+    assert abs(line["value"] - 2.0 / cb["wall_s"]) < 1e-9 and abs(line["ms_per_step"] - cb["wall_s"] * 1e3 / 4) < 1e-6
+    assert line["e2e"] == dict(value=line["value"], unit="atoms/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0)

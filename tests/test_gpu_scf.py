@@ -8,62 +8,100 @@ import pytest
 import dftatom_b200 as D
 import oracle_lib as O
 from conftest import golden
+from parity_util import EIG_TOL, ENERGY_TOL, KEYS, fine_grid_energy_tol as _fine_grid_energy_tol, ref_tables as _ref_tables
 
 pytestmark = pytest.mark.gpu
 
-EIG_TOL = 1e-6
-ENERGY_TOL = 1e-5
-# On the 65537- and 131073-node grids (C4, C2) the reference's own energies are only defined to ~1e-5 Ha: its FP64
-# multigrid sits on a rounding floor that is 3.4e-4 Ha (Rn, Etotal) away from the exact discrete solution, two runs of
-# the reference's own arithmetic with 8 and 100 V-cycles differ by 2.8e-6 Ha in a single Coulomb integral, and its
-# MSVC and glibc builds differ by 4e-6.  Any implementation that is not bit-identical lands on a different
-# point of that floor; measured here: <= 2e-5 Ha at every step for 8, 16 and 100 V-cycles alike (eigenvalues <= 5e-7).
-ENERGY_TOL_FINE_GRID = 3e-5
-KEYS = ("Etotal", "Ekin", "Ecoul", "Eenuc", "Exc")
+# The stop test of the reference (DFTAtom.cpp:474: |dE/E| < 1e-11 on two consecutive steps) fires on the ROUNDING NOISE of its own
+# Poisson solve: tests/test_oracle.py::test_reference_poisson_floor_is_chaotic shows that a 1-ulp change of a few density values
+# moves the reference's own Hartree energy by 5e-7 Ha at 16385 nodes (2e-11 of Etotal, twice the stop threshold) and by 1e-5 Ha at
+# 131073 nodes, and tests/golden/self_repro.json holds runs of the UNMODIFIED reference with mixing = 0.5 (1 + 2^-52): they stop at
+# other steps than the reference itself (Rn: 33 steps vs > 80).  The stop step is therefore no parity target.  What is asserted:
+#  (a) EVERY step the reference printed, at north_star tolerances, whatever step this implementation's own stop fires at
+#      (set_option("run_to_cap", 1): the stop test is recorded but does not end the SCF), including the reference's FINAL record
+#      (= the record at the reference's stop index) and the configuration line sorted by that record's eigenvalues;
+#  (b) in normal operation the stop only fires in the reference's own stop window: at the step where this implementation stops,
+#      the reference's own |dE/E| is within 10x of its threshold.
+STOP_WINDOW = 1e-10
 
 
 def _opt(o):
     return D.Options(o["Z"], o["levels"], o["rmax"], o["delta"], o["mixing"], o["method"])
 
 
-def _check_against_golden(res, atom):
-    """res: D.Result, atom: golden record.  Parity is judged step by step at equal step index (north_star tolerances).
+def _worst(res, atom, upto=None):
+    """max |eigenvalue| and |energy| deviation over the first `upto` common steps (default: all common steps)."""
+    n_ref, eigs, en = _ref_tables(atom)
+    n = min(res.n_steps, n_ref, upto or n_ref)
+    de = dE = 0.0
+    for k in range(n):
+        s = res.steps[k]
+        de = max(de, float(np.max(np.abs(np.array([x for chan in s.E for x in chan]) - np.array(eigs[k])))))
+        dE = max(dE, max(abs(getattr(s, key) - en[k][j]) for j, key in enumerate(KEYS)))
+    return n, de, dE
 
-    The step at which "Finished!" fires is NOT a parity target: near convergence the reference's own |dE/E| sits on a
-    rounding-noise floor of 2e-11..1e-10 (from the ill-conditioned Poisson solve) and dips below 1e-11 at a random
-    step (Ar: 33 steps with MSVC, 35 with glibc; Cu: 89).  What is asserted about the stop: this
-    implementation never stops while the reference's energy is still moving by more than its noise floor."""
-    n_ref = atom.get("n_steps", len(atom["steps"]))
+
+def _check_every_step(res, atom, energy_tol=ENERGY_TOL):
+    """Shell structure and node counts bit-exact; every common step: eigenvalues 1e-6, all five energies 1e-5 (north_star)."""
     flat = [L for chan in res.levels for L in chan]
     ref_levels = atom["steps"][-1]["levels"]
     assert [(L.n, L.l, L.nodes) for L in flat] == [(l["n"], l["l"], l["nodes"]) for l in ref_levels]        # bit-exact
-    all_steps = len(atom["steps"]) == n_ref
-    traj = atom.get("etotal_per_step") or [s["Etotal"] for s in atom["steps"]]
-    eigs = atom.get("eig_per_step") or ([[l["E"] for l in s["levels"]] for s in atom["steps"]] if all_steps else None)
+    n_ref, eigs, en = _ref_tables(atom)
     n = min(res.n_steps, n_ref)
     assert n >= 1
-    etol = ENERGY_TOL if atom["options"]["levels"] <= 15 else ENERGY_TOL_FINE_GRID
     for k in range(n):
         s = res.steps[k]
-        assert abs(s.Etotal - traj[k]) <= etol, (k, s.Etotal, traj[k])
-        if eigs is not None:
-            np.testing.assert_allclose([x for chan in s.E for x in chan], eigs[k], rtol=0, atol=EIG_TOL, err_msg=f"step {k}")
-        if all_steps:
-            for key in KEYS:
-                assert abs(getattr(s, key) - atom["steps"][k][key]) <= etol, (k, key, getattr(s, key), atom["steps"][k][key])
-    if res.n_steps == n_ref:        # same stop step: the final records and the configuration line must agree outright
+        np.testing.assert_allclose([x for chan in s.E for x in chan], eigs[k], rtol=0, atol=EIG_TOL, err_msg=f"Z={res.options.Z} step {k}")
+        for j, key in enumerate(KEYS):
+            assert abs(getattr(s, key) - en[k][j]) <= energy_tol, (res.options.Z, k, key, getattr(s, key), en[k][j])
+    return n
+
+
+def _check_final_record_at_reference_stop(res, atom, energy_tol=ENERGY_TOL):
+    """res was run with run_to_cap: its record at the reference's stop index against the reference's FINAL record (eigenvalues, five
+    energies) and the configuration line the reference prints from it (levels sorted by that record's eigenvalues, DFTAtom.cpp:487)."""
+    n_ref, eigs, en = _ref_tables(atom)
+    assert res.n_steps >= n_ref
+    s = res.steps[n_ref - 1]
+    g = atom["steps"][-1]
+    np.testing.assert_allclose([x for chan in s.E for x in chan], [l["E"] for l in g["levels"]], rtol=0, atol=EIG_TOL)
+    for key in KEYS:
+        assert abs(getattr(s, key) - g[key]) <= energy_tol, (res.options.Z, key, getattr(s, key), g[key])
+    conf = [[(L.n, L.l, L.occ) for _, L in sorted(zip(s.E[sp], chan), key=lambda t: t[0])] for sp, chan in enumerate(res.levels)]
+    assert conf[0] == [tuple(x) for x in atom["final"]["alpha"]], res.options.Z
+    if len(conf) > 1:
+        assert conf[1] == [tuple(x) for x in atom["final"]["beta"]], res.options.Z
+
+
+def _check_stop(res, atom):
+    """Normal operation (own stop test active): the stop fires inside the reference's own stop window, the status agrees with the
+    reference wherever the reference's own trajectory leaves no doubt, and a run that stopped at the reference's step reproduces its
+    final record and configuration outright."""
+    n_ref, eigs, en = _ref_tables(atom)
+    et = [e[0] for e in en]
+    if res.finished:
+        k = res.n_steps - 1
+        if k < n_ref and atom["finished"]:
+            # stopped before the reference did: by then the reference's own |dE/E| has already been within 10x of its threshold, i.e. the
+            # reference is on its rounding-noise floor and its own stop is a matter of which step the noise dips at.  (Atoms the reference
+            # never finishes - Er, Tm, Yb, LSDA Cu - slosh at |dE/E| ~ 2e-10..1e-9 for all their steps: no window to compare with.)
+            window = min(abs((et[j] - et[j - 1]) / et[j]) for j in range(1, k + 1))
+            assert k >= 2 and window < STOP_WINDOW, ("stopped outside the reference's stop window", res.options.Z, k, n_ref, window)
+    else:
+        assert res.status == 1 and res.n_steps == len(res.steps)
+    if res.n_steps == n_ref:
         g = atom["steps"][-1]
         for key in KEYS:
-            assert abs(getattr(res, key) - g[key]) <= etol, (key, getattr(res, key), g[key])
+            assert abs(getattr(res, key) - g[key]) <= ENERGY_TOL
         conf = [[(L.n, L.l, L.occ) for L in chan] for chan in res.sorted_levels]
         assert conf[0] == [tuple(x) for x in atom["final"]["alpha"]]
         if len(conf) > 1:
             assert conf[1] == [tuple(x) for x in atom["final"]["beta"]]
-    if res.finished and res.n_steps < n_ref:
-        k = res.n_steps - 1
-        assert abs(traj[k] - traj[k - 1]) / abs(traj[k]) < 2e-9, ("stopped while the reference was still converging", k, n_ref)
-    if not res.finished:
-        assert res.n_steps == len(res.steps) and res.status == 1
+
+
+def _check_against_golden(res, atom):
+    _check_every_step(res, atom)
+    _check_stop(res, atom)
 
 
 def test_small_batch_every_step(ctx):
@@ -239,35 +277,93 @@ def test_cli_text_matches_reference(tmp_path):
     assert bad.returncode == 1 and "levels" in bad.stderr
 
 
-def test_sweep_c3_final_records(ctx):
-    """C3: Z = 1..92, LDA, 14 levels: every atom's last step vs the reference; Etotal trajectory at every step."""
+def test_sweep_c3_every_step_and_final_records(ctx):
+    """C3: Z = 1..92, LDA, 14 levels.  (a) run_to_cap: every step of every atom the reference printed - eigenvalues 1e-6, all five
+    energies 1e-5 - and the reference's FINAL record + configuration line at the reference's own stop index, for all 92 atoms whatever
+    step this implementation's stop test fires at; (b) normal operation: stop inside the reference's stop window, same set of atoms
+    that never converge."""
     atoms = golden("sweep")["atoms"]
-    res = ctx.solve_batch([_opt(a["options"]) for a in atoms])
+    opts = [_opt(a["options"]) for a in atoms]
     assert sum(a["finished"] for a in atoms) == 89                      # reference: Z = 68, 69, 70 never stop (SURVEY fact 5)
-    for r, a in zip(res, atoms):
-        _check_against_golden(r, a)
-    # the slow convergers (Cu, Zn, Er, Tm, Yb ...) stop at a noise-driven step in the reference itself; all others must stop
-    n_fin = sum(r.finished for r in res)
-    assert n_fin >= 84, n_fin
+    ctx.set_option("run_to_cap", 1)
+    try:
+        capped = ctx.solve_batch(opts)
+    finally:
+        ctx.set_option("run_to_cap", 0)
+    for r, a in zip(capped, atoms):
+        assert r.n_steps == 100 and not r.finished
+        assert _check_every_step(r, a) == a["n_steps"]
+        _check_final_record_at_reference_stop(r, a)
+    res = ctx.solve_batch(opts)
+    for r, c, a in zip(res, capped, atoms):
+        # the stop test only ends the run: every record up to the stop is bit-identical to the capped run's, and the stop is the
+        # first step whose record carries the criterion
+        assert [s.Etotal for s in r.steps] == [s.Etotal for s in c.steps[:r.n_steps]]
+        first = next((k for k, s in enumerate(c.steps) if s.stop_criterion_met), None)
+        assert (r.finished and first == r.n_steps - 1) or (not r.finished and first is None)
+        _check_stop(r, a)
+    # Z = 68, 69, 70 slosh for 100 steps in the reference; |dE/E| of Er (Z = 68) sits at 2e-10..3e-10 there, inside the noise window
+    assert all(not res[z - 1].finished for z in (69, 70))
+    assert sum(r.finished for r, a in zip(res, atoms) if a["finished"]) >= 87        # of the reference's 89
 
 
 def test_radon_c2_every_step(ctx):
-    """C2: Rn, LSDA, 17 levels (131073 nodes), delta 1e-4, mixing 0.5, Rmax 50: every step vs the unmodified reference.
-    The finest three Poisson levels exceed the register-resident size and take the streaming sweep."""
+    """C2: Rn, LSDA, 17 levels (131073 nodes), delta 1e-4, mixing 0.5, Rmax 50, bit-reproducible Poisson mode (the reference's own
+    floating-point floor): every step vs the unmodified reference.  Eigenvalues at 1e-6 Ha; energies at 1e-5 Ha unless the fixture
+    proves that the reference itself does not reproduce them to 1e-5 Ha (then: twice its own deviation from itself)."""
     a = golden("radon")["atoms"][0]
-    res = ctx.solve_batch([_opt(a["options"])])[0]
-    _check_against_golden(res, a)
-    # README.md:32-47 (the published run used "LSD"; LSDA gives "basically the same", README.md:58)
+    ctx.set_option("poisson_exact", 1)
+    ctx.set_option("run_to_cap", 1)
+    ctx.set_option("step_cap", len(a["steps"]))             # exactly as many steps as the reference ran
+    try:
+        res = ctx.solve_batch([_opt(a["options"])])[0]
+    finally:
+        ctx.set_option("poisson_exact", 0)
+        ctx.set_option("run_to_cap", 0)
+        ctx.set_option("step_cap", 0)
+    tol = _fine_grid_energy_tol(a)
+    _check_every_step(res, a, energy_tol=tol)
+    _check_final_record_at_reference_stop(res, a, energy_tol=tol)
+    # README.md:32-47, printed to 6 decimals (the published run used "LSD"; LSDA gives "basically the same", README.md:58)
     readme = [-3204.756288, -546.577961, -527.533025, -133.369145, -124.172863, -106.945007, -31.230804, -27.108985,
               -19.449995, -8.953318, -5.889683, -4.408703, -1.911330, -0.626571, -0.293180]
-    np.testing.assert_allclose(res.steps[-1].E[0], readme, rtol=0, atol=2e-6)
-    assert abs(res.Etotal - -21861.346900) < 4e-5
+    n_ref = len(a["steps"])
+    np.testing.assert_allclose(res.steps[n_ref - 1].E[0], readme, rtol=0, atol=EIG_TOL + 5e-7)
+
+
+def test_radon_c2_default_path(ctx):
+    """C2 on the production path (8 V-cycles, FMA, warm start): eigenvalues at 1e-6 Ha at every step, shell structure exact; the
+    energies are reported (bench.py `parity`) and must stay within the reference's own reproducibility (fixture-derived)."""
+    a = golden("radon")["atoms"][0]
+    res = ctx.solve_batch([_opt(a["options"])])[0]
+    _check_every_step(res, a, energy_tol=_fine_grid_energy_tol(a))
 
 
 def test_lsda_batch_c4(ctx):
-    """C4: spin-polarised open-shell batch, Z = 21-30 and 57-71, LSDA, 16 levels (65537 nodes), delta 2e-4, Rmax 50."""
+    """C4: spin-polarised open-shell batch, Z = 21-30 and 57-71, LSDA, 16 levels (65537 nodes), delta 2e-4, Rmax 50, bit-reproducible
+    Poisson mode: EVERY step of all 25 atoms at north_star tolerances (1e-6 / 1e-5 Ha) - for Yb (Z = 70: sloshes for 150 steps in the
+    reference) the energy bar is the reference's own reproducibility, see _fine_grid_energy_tol - and the reference's final record +
+    configuration at the reference's stop index."""
+    atoms = golden("lsda_batch")["atoms"]
+    ctx.set_option("poisson_exact", 1)
+    ctx.set_option("run_to_cap", 1)
+    try:
+        res = ctx.solve_batch([_opt(a["options"]) for a in atoms])
+    finally:
+        ctx.set_option("poisson_exact", 0)
+        ctx.set_option("run_to_cap", 0)
+    for r, a in zip(res, atoms):
+        tol = _fine_grid_energy_tol(a)
+        assert _check_every_step(r, a, energy_tol=tol) == a["n_steps"]
+        _check_final_record_at_reference_stop(r, a, energy_tol=tol)
+
+
+def test_lsda_batch_c4_default_path(ctx):
+    """C4 on the production path (stream-mode Poisson, 8 V-cycles, warm start): eigenvalues 1e-6 Ha at every step of every atom; energies
+    1e-5 Ha for the atoms the reference converges, the reference's own reproducibility for those it does not (Z = 29, 68 - 70: fixtures)."""
     atoms = golden("lsda_batch")["atoms"]
     res = ctx.solve_batch([_opt(a["options"]) for a in atoms])
     for r, a in zip(res, atoms):
-        _check_against_golden(r, a)
+        _check_every_step(r, a, energy_tol=_fine_grid_energy_tol(a))
+        _check_stop(r, a)
     assert sum(r.finished for r in res) >= 19          # reference: 22 of 25 (Z = 29, 69, 70 hit the 150-step cap)

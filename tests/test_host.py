@@ -62,12 +62,23 @@ def test_report_roundtrip_against_reference_text():
 
 
 def test_partition_atoms_lpt():
+    """Shards of the C3 sweep (dftatom_partition: longest-processing-time-first on orbitals x expected SCF steps): every atom exactly
+    once, balanced loads, and the atoms that run 100 steps in the reference (Er, Tm, Yb: nearly full nodeless 4f shell) on different ranks."""
+    import dftatom_b200 as D
     zs = list(range(1, 93))
     for g in (1, 2, 4, 8):
         parts = partition_atoms(zs, g, method=0)
         assert sorted(sum(parts, [])) == list(range(92))
-        loads = [sum(len(O.aufbau(zs[i])) for i in p) for p in parts]
-        assert max(loads) - min(loads) <= 19          # LPT: within one heaviest item
+        loads = [sum(D.estimate_cost(zs[i], 0) for i in p) for p in parts]
+        assert max(loads) - min(loads) <= max(D.estimate_cost(z, 0) for z in zs)          # LPT: within one heaviest item
+        if g >= 4:
+            owners = [next(r for r, p in enumerate(parts) if z - 1 in p) for z in (68, 69, 70)]
+            assert len(set(owners)) == 3
+    # the cost model: slow convergers weigh more than their neighbours with the same number of orbitals
+    assert D.estimate_cost(70, 0) > 1.5 * D.estimate_cost(72, 0) and D.estimate_cost(29, 0) > 1.5 * D.estimate_cost(27, 0)
+    assert D.estimate_cost(29, 1) > D.estimate_cost(29, 0)
+    # C ABI argument checks
+    assert D.estimate_cost(0, 0) == 0.0 and D.estimate_cost(119, 0) == 0.0
 
 
 def test_cli_fails_loudly_without_gpu():
