@@ -88,6 +88,8 @@ struct Knobs {
     int cluster_max_dens = 1 << 30; // ... while at most this many atoms are still iterating.  Default: always - which kernel solves a density must not depend on
                                // what else is in the batch (an atom's records are bit-identical alone, in any batch and on any shard); a smaller
                                // value trades that for throughput while many atoms are active (above ~37 densities the clusters need more than one wave)
+    int delta_poisson = 1;     // warm-started Poisson solves in increment form (A dU = -dS, U += dU: scf.cu) - keeps consecutive SCF steps free of the
+                               // rounding-floor noise of a plain FP64 multigrid solve; 0 = iterate on U itself
     int step_cap = 0;          // > 0: lower the SCF step cap (100 LDA / 150 LSDA, DFTAtom.cpp:396,908) to this many steps (tests: with run_to_cap, run exactly as long as the reference did)
     int use_graph = 1;         // SCF steps are replayed from a captured CUDA graph (one graph launch per step) instead of 5+ kernel launches
 };
@@ -101,7 +103,7 @@ struct dftatom_ctx {
     int stream_groups = 1;     // 2: a batch of >= 32 atoms is split into two groups that run their SCF chains concurrently on separate streams
     dftatom_ctx* child = nullptr;   // context (stream + buffers) of the second group
     int n_sm = 148;
-    DevBuf stream_src0, stream_scratch, exact_work, last_steps;
+    DevBuf stream_src0, stream_scratch, exact_work, last_steps, rho_prev, d_src, d_u;
     dftatom_step* h_last = nullptr; size_t h_last_cap = 0;      // pinned staging of the result records
     DevBuf stream_G; int stream_G_levels = 0; double stream_G_delta = 0.;   // dense coarse operator of the stream-mode V-cycle
     dftatom_kernel_profile prof[DFTATOM_K_COUNT] = {};
@@ -249,7 +251,7 @@ void dftatom_destroy(dftatom_ctx* c)
                       &c->phi, &c->src, &c->u0, &c->ubuf, &c->zbc, &c->tab_of, &c->steps, &c->n_active };
     for (DevBuf* b : all) b->release();
     for (DevBuf& b : c->scratch) b.release();
-    c->stream_G.release(); c->stream_src0.release(); c->stream_scratch.release(); c->exact_work.release(); c->last_steps.release();
+    c->stream_G.release(); c->stream_src0.release(); c->stream_scratch.release(); c->exact_work.release(); c->last_steps.release(); c->rho_prev.release(); c->d_src.release(); c->d_u.release();
     if (c->h_active) cudaFreeHost(c->h_active);
     if (c->h_last) cudaFreeHost(c->h_last);
     cudaStreamDestroy(c->stream);
@@ -281,6 +283,7 @@ int dftatom_set_option(dftatom_ctx* c, const char* key, double value)
     else if (k == "poisson_exact") c->k.poisson_exact = value != 0.;
     else if (k == "cluster_poisson") c->k.cluster_poisson = value != 0.;
     else if (k == "cluster_max_dens") c->k.cluster_max_dens = std::max(0, (int)value);
+    else if (k == "delta_poisson") c->k.delta_poisson = value != 0.;
     else if (k == "step_cap") c->k.step_cap = std::max(0, (int)value);
     else if (k == "run_to_cap") c->k.run_to_cap = value != 0.;
     else if (k == "use_graph") c->k.use_graph = value != 0.;
@@ -436,6 +439,9 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
     if ((rc = c->ubuf.ensure(sizeof(double) * (size_t)n_atoms * ldU))) return rc;
     if (stream && ((rc = c->stream_src0.ensure(sizeof(double) * (size_t)n_atoms * ldU)) || (rc = c->stream_scratch.ensure(sizeof(double) * (size_t)splan.total)))) return rc;
     if (exact && (rc = c->exact_work.ensure(sizeof(double) * (size_t)n_atoms * (size_t)exact_poisson_work_doubles(g.L)))) return rc;
+    const bool delta = c->k.delta_poisson && !exact && c->k.warm_vcycles > 0 && c->k.refine_vcycles == 0 && !c->k.floor_stop;
+    if (delta && ((rc = c->rho_prev.ensure(sizeof(double) * (size_t)n_atoms * N)) || (rc = c->d_src.ensure(sizeof(double) * (size_t)n_atoms * ldU))
+                  || (rc = c->d_u.ensure(sizeof(double) * (size_t)n_atoms * ldU)))) return rc;
     if ((rc = c->steps.ensure(sizeof(dftatom_step) * (size_t)n_atoms * stride))) return rc;
     if ((rc = c->last_steps.ensure(sizeof(dftatom_step) * (size_t)n_atoms))) return rc;
     if ((rc = c->n_active.ensure(sizeof(int) * 2))) return rc;
@@ -475,17 +481,17 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
     sa.skip = &b.astate[0].done; sa.skip_stride_bytes = (int)sizeof(AtomState);
     // the Poisson solve of one SCF step: FullCycle (ramp + max_vcycles V-cycles), or warm_vcycles V-cycles from the previous U
     int act_est = n_atoms;          // atoms still iterating, as of `lag` steps ago (host-side estimate; only selects between two equivalent kernels)
+    double* rho_prev = c->rho_prev.as<double>();
+    double* d_src = c->d_src.as<double>();
+    double* d_u = c->d_u.as<double>();
+    const int* skip_p = &b.astate[0].done; const int skip_stride = (int)sizeof(AtomState);
     auto poisson_solve = [&](int warm_vcycles, long long& n_launch) {
+        const bool warm = warm_vcycles > 0;
         if (exact) {
             launch_poisson_exact(xa, st);
             ++n_launch;
-        } else if (stream) {
-            sa.warm = warm_vcycles > 0; sa.n_v = warm_vcycles > 0 ? warm_vcycles : c->k.max_vcycles;
-            long long nl = 0;
-            launch_poisson_stream_solve(splan, g.delta, sa, st, &nl);
-            n_launch += nl;
-        } else if (cluster_ok && warm_vcycles > 0 && act_est <= c->k.cluster_max_dens) {
-            ca.n_vcycles = warm_vcycles; ca.work = pa.work;
+        } else if (warm && cluster_ok && act_est <= c->k.cluster_max_dens) {
+            ca.n_vcycles = warm_vcycles; ca.work = pa.work; ca.rho_prev = delta ? rho_prev : nullptr;
             if (getenv("DFTATOM_DEBUG_CLUSTER") && n_launch > 40 && !ca.dbg) {       // development aid: cycle counters of one solve
                 if (c->scratch[5].ensure(sizeof(long long) * 256)) return;
                 cudaMemsetAsync(c->scratch[5].p, 0, sizeof(long long) * 256, st);
@@ -505,9 +511,37 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
             }
             { long long* keep = ca.dbg; ca.dbg = nullptr; launch_poisson_cluster(g, ca, st); ca.dbg = keep; }
             ++n_launch;
+        } else if (warm && delta) {
+            // increment form around the existing solvers: dS, dU = 0 -> V-cycles on (dS, dU) with zero boundary values -> U += dU
+            launch_poisson_delta_prepare(g, n_atoms, ldU, b.rhot, rho_prev, d_src, d_u, skip_p, skip_stride, st);
+            if (stream) {
+                StreamSolveArgs sd = sa;
+                sd.rho = nullptr; sd.src0 = d_src; sd.U = d_u; sd.Zbc = nullptr; sd.warm = 1; sd.n_v = warm_vcycles;
+                long long nl = 0;
+                launch_poisson_stream_solve(splan, g.delta, sd, st, &nl);
+                n_launch += nl;
+            } else {
+                PoissonArgs pd = pa;
+                pd.rho = nullptr; pd.src_nat = d_src; pd.u_out = d_u; pd.nat_stride = ldU == N ? 0 : ldU; pd.Zbc = nullptr; pd.warm_vcycles = warm_vcycles;
+                // (team mode keeps Phi_0 in place in the hierarchy between warm solves: it must start from the zero increment too)
+                cudaMemsetAsync(pa.phi, 0, sizeof(double) * (size_t)n_atoms * lv.total, st);
+                launch_poisson_full(g, lv, pd, st);
+                ++n_launch;
+            }
+            launch_poisson_delta_apply(g, n_atoms, ldU, b.U, d_u, skip_p, skip_stride, st);
+            n_launch += 2;
+        } else if (stream) {
+            sa.warm = warm; sa.n_v = warm ? warm_vcycles : c->k.max_vcycles;
+            long long nl = 0;
+            launch_poisson_stream_solve(splan, g.delta, sa, st, &nl);
+            n_launch += nl;
         } else {
             pa.warm_vcycles = warm_vcycles;
             launch_poisson_full(g, lv, pa, st);
+            ++n_launch;
+        }
+        if (delta && !warm) {       // a cold solve: remember its density for the first increment
+            launch_poisson_delta_prepare(g, n_atoms, ldU, b.rhot, rho_prev, nullptr, nullptr, skip_p, skip_stride, st);
             ++n_launch;
         }
     };

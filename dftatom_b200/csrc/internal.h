@@ -220,6 +220,8 @@ void launch_poisson_exact(const ExactPoissonArgs& a, cudaStream_t st);
 struct ClusterPoissonArgs {
     int n_dens;
     const double* rho; long long rho_stride;    // [n_dens][rho_stride] total densities, natural node order
+    double* rho_prev;                           // optional [n_dens][rho_stride], in / out: the density of the previous solve.  Given: increment form - the
+                                                // V-cycles solve A dU = -r 4 pi K (rho - rho_prev) from dU = 0 and U += dU (see scf.cu); NULL: they iterate on U
     double* U; long long ldU;                   // [n_dens][ldU] in: previous solution (initial guess), out: U(r)
     const int* Zbc;                             // [n_dens] boundary value at Rmax
     const double* coarse_op;                    // GridDev.coarse_op
@@ -268,6 +270,12 @@ struct ScfBuffers {
     int run_to_cap;   // != 0: the stop test is recorded in dftatom_step.stop_criterion_met but never ends the SCF
 };
 void launch_gather_last_steps(const ScfBuffers& b, dftatom_step* out, cudaStream_t st);
+// increment form of the warm-started Poisson solves (scf.cu): dS = r 4 pi K (rho - rho_prev), dU = 0, rho_prev = rho (dS == NULL: only
+// the last); U += dU
+void launch_poisson_delta_prepare(const GridDev& g, int n_dens, long long ld, const double* rho, double* rho_prev, double* dS, double* dU,
+                                  const int* skip, int skip_stride_bytes, cudaStream_t st);
+void launch_poisson_delta_apply(const GridDev& g, int n_dens, long long ld, double* U, const double* dU, const int* skip, int skip_stride_bytes,
+                                cudaStream_t st);
 void launch_initial_density(const GridDev& g, const ScfBuffers& b, cudaStream_t st);
 void launch_orbital_norms(const GridDev& g, const ScfBuffers& b, cudaStream_t st);
 void launch_density_update(const GridDev& g, const ScfBuffers& b, cudaStream_t st);

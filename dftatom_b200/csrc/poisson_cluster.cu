@@ -501,7 +501,7 @@ __global__ void __cluster_dims__(kCL, 1, 1) __launch_bounds__(kCT, 2) poisson_cl
         int nd = 0;
         for (int l = 0; l < L; ++l) if ((1 << (L - l)) >= kCL * kCT) ++nd;
         cs.L = L; cs.n_dist = nd; cs.lb = L - 10; cs.md = L - 5;
-        cs.right_bc = a.Zbc ? (double)a.Zbc[k] : 0.;
+        cs.right_bc = (a.Zbc && !a.rho_prev) ? (double)a.Zbc[k] : 0.;      // increment form: dU vanishes on both boundaries
         cs.updates = 0;
         cs.dbg_on = a.dbg != nullptr && k == 0;
         for (int q = 0; q < 32; ++q) cs.dbg[q] = 0;
@@ -517,6 +517,16 @@ __global__ void __cluster_dims__(kCL, 1, 1) __launch_bounds__(kCT, 2) poisson_cl
         const double* u = a.U + (size_t)k * a.ldU;
         const double* rho = a.rho + (size_t)k * a.rho_stride;
         double* P = c_dyn + c0.offP; double* S = c_dyn + c0.offS;
+        if (a.rho_prev) {           // increment form: Phi_0 = dU = 0, Source_0 = r 4 pi K (rho - rho_prev)
+            double* rp = a.rho_prev + (size_t)k * a.rho_stride;
+            for (int q = t; q < c0.m; q += kCT) {
+                const int i = s + q;
+                const double r = rho[i];
+                P[q] = 0.; S[q] = (i >= 1 && i < N - 1) ? g.psrc[i] * (r - rp[i]) : 0.;
+                rp[i] = r;
+            }
+            if (rank == kCL - 1 && t == 0) rp[N - 1] = rho[N - 1];
+        } else
         for (int q = t; q < c0.m; q += kCT) { const int i = s + q; P[q] = u[i]; S[q] = (i >= 1 && i < N - 1) ? g.psrc[i] * rho[i] : 0.; }
     }
     __syncthreads();
@@ -545,8 +555,11 @@ __global__ void __cluster_dims__(kCL, 1, 1) __launch_bounds__(kCT, 2) poisson_cl
         const int s = rank * c0.m;
         double* u = a.U + (size_t)k * a.ldU;
         const double* P = c_dyn + c0.offP;
-        for (int q = t; q < c0.m; q += kCT) u[s + q] = P[q];
-        if (rank == kCL - 1 && t == 0) u[N - 1] = cs.right_bc;
+        if (a.rho_prev) { for (int q = t; q < c0.m; q += kCT) u[s + q] += P[q]; }
+        else {
+            for (int q = t; q < c0.m; q += kCT) u[s + q] = P[q];
+            if (rank == kCL - 1 && t == 0) u[N - 1] = cs.right_bc;
+        }
     }
     if (rank == 0 && t == 0 && a.work) atomicAdd(a.work, cs.updates);
     if (t == 0 && cs.dbg_on) { cs.dbg[0] = clock64() - t_begin; for (int q = 0; q < 32; ++q) a.dbg[rank * 32 + q] = cs.dbg[q]; }

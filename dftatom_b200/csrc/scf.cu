@@ -476,6 +476,48 @@ __global__ void __launch_bounds__(kPT2) potential_energy_kernel(GridDev g, Poiss
     }
 }
 
+// Increment form of the warm-started Poisson solves.  A = the discrete operator is linear, so with U_prev the previous step's solution
+//     U = U_prev + dU,   A dU = -(S - S_prev) = -r 4 pi K (rho - rho_prev),   dU = 0 on both boundaries.
+// The plain warm start iterates on the residual S - A U_prev, whose three U terms cancel to ~1e-8 of their size: that cancellation is
+// what puts every FP64 multigrid solve of U itself (the reference's included) on a rounding floor of ~1e-9 |U| that is a chaotic
+// function of the input (tests/test_oracle.py::test_reference_poisson_floor_is_chaotic) and makes |dE/E| of consecutive SCF steps wander
+// at 2e-11..1e-10.  Solved for the INCREMENT, every quantity in the solve is as small as the density change itself, its rounding is
+// relative to dU, and the rounding-floor error of U stays frozen at what the last cold solve left: consecutive steps differ smoothly,
+// and the stop test |dE/E| < 1e-11 (DFTAtom.cpp:474) fires when the energy has really stopped moving, not when the noise dips.
+__global__ void __launch_bounds__(256) poisson_delta_prepare_kernel(int N, long long ld, const double* __restrict__ psrc, const double* __restrict__ rho,
+                                                                    double* __restrict__ rho_prev, double* __restrict__ dS, double* __restrict__ dU,
+                                                                    const int* skip, int skip_stride_bytes)
+{
+    const int k = blockIdx.y;
+    if (skip && *reinterpret_cast<const int*>(reinterpret_cast<const char*>(skip) + (size_t)k * skip_stride_bytes)) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const double r = rho[(size_t)k * N + i];
+    if (dS) {
+        dS[(size_t)k * ld + i] = psrc[i] * (r - rho_prev[(size_t)k * N + i]);
+        dU[(size_t)k * ld + i] = 0.;
+    }
+    rho_prev[(size_t)k * N + i] = r;
+}
+__global__ void __launch_bounds__(256) poisson_delta_apply_kernel(int N, long long ld, double* __restrict__ U, const double* __restrict__ dU,
+                                                                  const int* skip, int skip_stride_bytes)
+{
+    const int k = blockIdx.y;
+    if (skip && *reinterpret_cast<const int*>(reinterpret_cast<const char*>(skip) + (size_t)k * skip_stride_bytes)) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) U[(size_t)k * ld + i] += dU[(size_t)k * ld + i];
+}
+void launch_poisson_delta_prepare(const GridDev& g, int n_dens, long long ld, const double* rho, double* rho_prev, double* dS, double* dU,
+                                  const int* skip, int skip_stride_bytes, cudaStream_t st)
+{
+    poisson_delta_prepare_kernel<<<dim3((g.N + 255) / 256, n_dens), 256, 0, st>>>(g.N, ld, g.psrc, rho, rho_prev, dS, dU, skip, skip_stride_bytes);
+}
+void launch_poisson_delta_apply(const GridDev& g, int n_dens, long long ld, double* U, const double* dU, const int* skip, int skip_stride_bytes,
+                                cudaStream_t st)
+{
+    poisson_delta_apply_kernel<<<dim3((g.N + 255) / 256, n_dens), 256, 0, st>>>(g.N, ld, U, dU, skip, skip_stride_bytes);
+}
+
 // last "Step:" record of every atom, compact (what dftatom_solve_batch downloads when the caller did not ask for the steps)
 __global__ void gather_last_steps_kernel(ScfBuffers b, dftatom_step* out)
 {

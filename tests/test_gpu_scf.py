@@ -8,7 +8,7 @@ import pytest
 import dftatom_b200 as D
 import oracle_lib as O
 from conftest import golden
-from parity_util import EIG_TOL, ENERGY_TOL, KEYS, fine_grid_energy_tol as _fine_grid_energy_tol, ref_tables as _ref_tables
+from parity_util import EIG_TOL, ENERGY_TOL, KEYS, fine_grid_energy_tol as _fine_grid_energy_tol, ref_tables
 
 pytestmark = pytest.mark.gpu
 
@@ -20,9 +20,8 @@ pytestmark = pytest.mark.gpu
 #  (a) EVERY step the reference printed, at north_star tolerances, whatever step this implementation's own stop fires at
 #      (set_option("run_to_cap", 1): the stop test is recorded but does not end the SCF), including the reference's FINAL record
 #      (= the record at the reference's stop index) and the configuration line sorted by that record's eigenvalues;
-#  (b) in normal operation the stop only fires in the reference's own stop window: at the step where this implementation stops,
-#      the reference's own |dE/E| is within 10x of its threshold.
-STOP_WINDOW = 1e-10
+#  (b) in normal operation (own stop test active) the FINAL records agree in everything the reference's own final record has converged:
+#      eigenvalues 1e-6 Ha, Etotal 1e-5 Ha, configuration line - for every atom the reference finishes, whatever the two stop steps are.
 
 
 def _opt(o):
@@ -31,7 +30,7 @@ def _opt(o):
 
 def _worst(res, atom, upto=None):
     """max |eigenvalue| and |energy| deviation over the first `upto` common steps (default: all common steps)."""
-    n_ref, eigs, en = _ref_tables(atom)
+    n_ref, eigs, en = ref_tables(atom)
     n = min(res.n_steps, n_ref, upto or n_ref)
     de = dE = 0.0
     for k in range(n):
@@ -46,7 +45,7 @@ def _check_every_step(res, atom, energy_tol=ENERGY_TOL):
     flat = [L for chan in res.levels for L in chan]
     ref_levels = atom["steps"][-1]["levels"]
     assert [(L.n, L.l, L.nodes) for L in flat] == [(l["n"], l["l"], l["nodes"]) for l in ref_levels]        # bit-exact
-    n_ref, eigs, en = _ref_tables(atom)
+    n_ref, eigs, en = ref_tables(atom)
     n = min(res.n_steps, n_ref)
     assert n >= 1
     for k in range(n):
@@ -60,7 +59,7 @@ def _check_every_step(res, atom, energy_tol=ENERGY_TOL):
 def _check_final_record_at_reference_stop(res, atom, energy_tol=ENERGY_TOL):
     """res was run with run_to_cap: its record at the reference's stop index against the reference's FINAL record (eigenvalues, five
     energies) and the configuration line the reference prints from it (levels sorted by that record's eigenvalues, DFTAtom.cpp:487)."""
-    n_ref, eigs, en = _ref_tables(atom)
+    n_ref, eigs, en = ref_tables(atom)
     assert res.n_steps >= n_ref
     s = res.steps[n_ref - 1]
     g = atom["steps"][-1]
@@ -73,30 +72,28 @@ def _check_final_record_at_reference_stop(res, atom, energy_tol=ENERGY_TOL):
         assert conf[1] == [tuple(x) for x in atom["final"]["beta"]], res.options.Z
 
 
-def _check_stop(res, atom):
-    """Normal operation (own stop test active): the stop fires inside the reference's own stop window, the status agrees with the
-    reference wherever the reference's own trajectory leaves no doubt, and a run that stopped at the reference's step reproduces its
-    final record and configuration outright."""
-    n_ref, eigs, en = _ref_tables(atom)
-    et = [e[0] for e in en]
-    if res.finished:
-        k = res.n_steps - 1
-        if k < n_ref and atom["finished"]:
-            # stopped before the reference did: by then the reference's own |dE/E| has already been within 10x of its threshold, i.e. the
-            # reference is on its rounding-noise floor and its own stop is a matter of which step the noise dips at.  (Atoms the reference
-            # never finishes - Er, Tm, Yb, LSDA Cu - slosh at |dE/E| ~ 2e-10..1e-9 for all their steps: no window to compare with.)
-            window = min(abs((et[j] - et[j - 1]) / et[j]) for j in range(1, k + 1))
-            assert k >= 2 and window < STOP_WINDOW, ("stopped outside the reference's stop window", res.options.Z, k, n_ref, window)
-    else:
+def _check_stop(res, atom, energy_tol=ENERGY_TOL):
+    """Normal operation (own stop test active).  The warm Poisson solves run in increment form (scf.cu: poisson_delta_*), so this
+    implementation's |dE/E| decays smoothly and its stop fires when the energy has really stopped moving; the reference's fires when
+    its rounding noise dips (earlier or later by up to tens of steps, see the header).  Whatever the two stop steps are, the FINAL
+    records must agree wherever the reference's own final record is converged: eigenvalues (1e-6 Ha), Etotal (1e-5 Ha) and the
+    configuration line; the four partial energies too when both stopped at the same step (they still drift by ~1e-5 Ha per step when
+    Etotal has converged - the reference's criterion only looks at Etotal)."""
+    n_ref, eigs, en = ref_tables(atom)
+    if not res.finished:
         assert res.status == 1 and res.n_steps == len(res.steps)
-    if res.n_steps == n_ref:
+    if res.finished and atom["finished"]:
         g = atom["steps"][-1]
-        for key in KEYS:
-            assert abs(getattr(res, key) - g[key]) <= ENERGY_TOL
+        np.testing.assert_allclose([x for chan in res.steps[-1].E for x in chan], [l["E"] for l in g["levels"]], rtol=0, atol=EIG_TOL,
+                                   err_msg=f"final eigenvalues, Z={res.options.Z}, stop {res.n_steps} vs {n_ref}")
+        assert abs(res.Etotal - g["Etotal"]) <= energy_tol, (res.options.Z, res.n_steps, n_ref, res.Etotal, g["Etotal"])
         conf = [[(L.n, L.l, L.occ) for L in chan] for chan in res.sorted_levels]
         assert conf[0] == [tuple(x) for x in atom["final"]["alpha"]]
         if len(conf) > 1:
             assert conf[1] == [tuple(x) for x in atom["final"]["beta"]]
+        if res.n_steps == n_ref:
+            for key in KEYS:
+                assert abs(getattr(res, key) - g[key]) <= energy_tol, (res.options.Z, key)
 
 
 def _check_against_golden(res, atom):
@@ -302,9 +299,8 @@ def test_sweep_c3_every_step_and_final_records(ctx):
         first = next((k for k, s in enumerate(c.steps) if s.stop_criterion_met), None)
         assert (r.finished and first == r.n_steps - 1) or (not r.finished and first is None)
         _check_stop(r, a)
-    # Z = 68, 69, 70 slosh for 100 steps in the reference; |dE/E| of Er (Z = 68) sits at 2e-10..3e-10 there, inside the noise window
-    assert all(not res[z - 1].finished for z in (69, 70))
-    assert sum(r.finished for r, a in zip(res, atoms) if a["finished"]) >= 87        # of the reference's 89
+    # the same 89 atoms finish; Er, Tm, Yb (Z = 68, 69, 70) slosh for all 100 steps like in the reference
+    assert [bool(r.finished) for r in res] == [bool(a["finished"]) for a in atoms]
 
 
 def test_radon_c2_every_step(ctx):
@@ -337,6 +333,8 @@ def test_radon_c2_default_path(ctx):
     a = golden("radon")["atoms"][0]
     res = ctx.solve_batch([_opt(a["options"])])[0]
     _check_every_step(res, a, energy_tol=_fine_grid_energy_tol(a))
+    _check_stop(res, a, energy_tol=_fine_grid_energy_tol(a))
+    assert res.finished
 
 
 def test_lsda_batch_c4(ctx):
@@ -365,5 +363,5 @@ def test_lsda_batch_c4_default_path(ctx):
     res = ctx.solve_batch([_opt(a["options"]) for a in atoms])
     for r, a in zip(res, atoms):
         _check_every_step(r, a, energy_tol=_fine_grid_energy_tol(a))
-        _check_stop(r, a)
-    assert sum(r.finished for r in res) >= 19          # reference: 22 of 25 (Z = 29, 69, 70 hit the 150-step cap)
+        _check_stop(r, a, energy_tol=_fine_grid_energy_tol(a))
+    assert sum(r.finished for r, a in zip(res, atoms) if a["finished"]) >= 21          # reference: 22 of 25 (Z = 29, 69, 70 hit the 150-step cap)
