@@ -134,7 +134,7 @@ class Options:
     MaxR: float = 10.0
     deltaGrid: float = 0.001
     alpha: float = 0.5
-    method: int = 0          # 0 = LDA ("LSD" in the banner), 1 = LSDA
+    method: int = 0          # 0 = LDA ("LSD" in the banner), 1 = LSDA; 2 / 3 = the same on the uniform grid (CalculateUniformLDA / LSDA)
 
     def _c(self):
         return _COptions(int(self.Z), int(self.MultigridLevels), float(self.MaxR), float(self.deltaGrid), float(self.alpha), int(self.method))
@@ -189,7 +189,7 @@ class Result:
             st.append(dict(levels=lv, Etotal=s.Etotal, Ekin=s.Ekin, Ecoul=s.Ecoul, Eenuc=s.Eenuc, Exc=s.Exc))
         conf = [[(L.n, L.l, L.occ) for L in chan] for chan in self.sorted_levels]
         return format_report(self.options.Z, self.options.method, st, self.finished, conf[0], conf[1] if len(conf) > 1 else None,
-                             precision)
+                             precision, n_alpha=len(self.levels[0]))
 
 
 def _levels_from_c(arr, n):
@@ -410,6 +410,16 @@ class DFTAtom:
     @staticmethod
     def CalculateNonUniformLSDA(Z, MultigridLevels, alpha, MaxR, deltaGrid, out=None) -> Result:
         return DFTAtom._run(Options(Z, MultigridLevels, MaxR, deltaGrid, alpha, 1), out)
+
+    @staticmethod
+    def CalculateUniformLDA(Z, MultigridLevels, alpha, MaxR, out=None) -> Result:
+        """DFTAtom.h:15 (DFTAtom.cpp:60-210): the uniform grid r_i = i MaxR / (N - 1)."""
+        return DFTAtom._run(Options(Z, MultigridLevels, MaxR, 0.0, alpha, 2), out)
+
+    @staticmethod
+    def CalculateUniformLSDA(Z, MultigridLevels, alpha, MaxR, out=None) -> Result:
+        """DFTAtom.h:18 (DFTAtom.cpp:646-844)."""
+        return DFTAtom._run(Options(Z, MultigridLevels, MaxR, 0.0, alpha, 3), out)
 
     @staticmethod
     def _run(opt, out):

@@ -151,7 +151,11 @@ int main(int argc, char** argv)
         else if (a == "--delta") base.delta = std::atof(next());
         else if (a == "--mixing" || a == "--alpha") base.mixing = std::atof(next());
         else if (a == "--rmax") base.max_r = std::atof(next());
-        else if (a == "--method") { std::string m = next(); base.method = (m == "1" || m == "lsda" || m == "LSDA") ? 1 : 0; }
+        else if (a == "--method") {         // 0 | lda, 1 | lsda; 2, 3: the same on the uniform grid (CalculateUniformLDA / LSDA, DFTAtom.h:15,18)
+            std::string m = next();
+            base.method = (m == "1" || m == "lsda" || m == "LSDA") ? 1 : (m == "2" ? 2 : (m == "3" ? 3 : 0));
+        }
+        else if (a == "--uniform") base.method |= 2;
         else if (a == "--precision") precision = std::atoi(next());
         else if (a == "--device") device = std::atoi(next());
         else if (a == "--ini") read_ini(next(), base);
@@ -220,19 +224,22 @@ int main(int argc, char** argv)
             std::printf("}");
             continue;
         }
-        std::printf("Computing atom with Z=%d using %s with non-uniform grid\n", opts[a].Z, opts[a].method ? "LSDA" : "LSD");   // DFTAtom.cpp:358,857
+        const bool uni = opts[a].method >= 2, lsda = (opts[a].method & 1) != 0;
+        std::printf("Computing atom with Z=%d using %s with %s grid\n", opts[a].Z, lsda ? "LSDA" : (uni ? "LDA" : "LSD"),
+                    uni ? "uniform" : "non-uniform");                                                                       // DFTAtom.cpp:358,857,69,656
         for (int sp = quiet ? R.n_steps - 1 : 0; sp < R.n_steps; ++sp) {
             const dftatom_step& S = steps[(size_t)a * stride + sp];
             std::printf("Step: %d\n", sp);
             for (int s = 0; s < R.n_spin; ++s)
                 for (int k = 0; k < R.n_levels[s]; ++k)
-                    std::printf("Energy %d%c: %.*f Num nodes: %d\n", R.levels[s][k].n, kOrb[R.levels[s][k].l], precision, S.E[s][k], R.levels[s][k].nodes);
+                    std::printf("Energy %s%d%c: %.*f Num nodes: %d\n", (uni && lsda) ? (s ? "beta " : "alpha ") : "", R.levels[s][k].n, kOrb[R.levels[s][k].l],
+                                precision, S.E[s][k], R.levels[s][k].nodes);                                                 // tags: DFTAtom.cpp:269-277
             std::printf("Etotal = %.*f Ekin = %.*f Ecoul = %.*f Eenuc = %.*f Exc = %.*f\n", precision, S.Etotal, precision, S.Ekin, precision, S.Ecoul,
                         precision, S.Eenuc, precision, S.Exc);
             if (sp == R.n_steps - 1 && R.status == DFTATOM_CONVERGED) std::printf("\nFinished!\n\n");
             else std::printf("********************************************************************************\n");
         }
-        if (opts[a].method) {
+        if (opts[a].method & 1) {
             std::printf("Alpha: "); print_conf(R.sorted[0], R.n_levels[0]);
             std::printf("\nBeta: "); print_conf(R.sorted[1], R.n_levels[1]);
         } else print_conf(R.sorted[0], R.n_levels[0]);

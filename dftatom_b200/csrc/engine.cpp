@@ -177,6 +177,7 @@ static int get_grid(dftatom_ctx* c, int L, double delta, double max_r, GridDev**
     DFT_CHECK(cudaStreamSynchronize(c->stream));
     double* d = e.mem.as<double>();
     e.dev.N = N; e.dev.L = L; e.dev.delta = delta; e.dev.rp = rp; e.dev.max_r = max_r;
+    e.dev.uniform = uniform ? 1 : 0; e.dev.h = uniform ? h_uni : 0.;
     e.dev.r = d; e.dev.ex = d + (size_t)N; e.dev.sqex = d + (size_t)2 * N; e.dev.b12 = d + (size_t)3 * N;
     e.dev.c6 = d + (size_t)4 * N; e.dev.k2 = d + (size_t)5 * N; e.dev.wjac = d + (size_t)6 * N;
     e.dev.psrc = d + (size_t)7 * N; e.dev.inv4pr2 = d + (size_t)8 * N; e.dev.pex = d + (size_t)9 * N;
@@ -197,9 +198,9 @@ static int validate(const dftatom_options& o)
     // sweeps stop meaning anything (measured: Ne at 65 nodes, 42 Ha between two evaluation orders of the same recurrence)
     if (o.levels < 8 || o.levels > 20) { set_error("levels must be in 8..20"); return DFTATOM_E_BAD_OPTION; }
     if (!(o.max_r >= 1. && o.max_r <= 90.)) { set_error("max_r must be in 1..90"); return DFTATOM_E_BAD_OPTION; }
-    if (!(o.delta > 0. && o.delta <= 1.)) { set_error("delta must be in (0,1]"); return DFTATOM_E_BAD_OPTION; }
+    if (o.method < 0 || o.method > 3) { set_error("method must be 0 (LDA), 1 (LSDA), 2 (LDA, uniform grid) or 3 (LSDA, uniform grid)"); return DFTATOM_E_BAD_OPTION; }
+    if (o.method < 2 && !(o.delta > 0. && o.delta <= 1.)) { set_error("delta must be in (0,1]"); return DFTATOM_E_BAD_OPTION; }      // unused on the uniform grid
     if (!(o.mixing >= 0. && o.mixing <= 1.)) { set_error("mixing must be in [0,1]"); return DFTATOM_E_BAD_OPTION; }
-    if (o.method != 0 && o.method != 1) { set_error("method must be 0 (LDA) or 1 (LSDA)"); return DFTATOM_E_BAD_OPTION; }
     return 0;
 }
 
@@ -358,13 +359,15 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
     for (int a = 0; a < n_atoms; ++a) {
         int rc = validate(opts[a]);
         if (rc) return rc;
-        if (opts[a].levels != opts[0].levels || opts[a].delta != opts[0].delta || opts[a].max_r != opts[0].max_r) {
-            set_error("all atoms of one batch must share (levels, delta, max_r)");
+        // methods 2 / 3 (CalculateUniformLDA / LSDA, DFTAtom.h:15,18) run on the uniform grid: delta is not used (grid key: delta = 0)
+        const bool uni_a = opts[a].method >= 2, uni_0 = opts[0].method >= 2;
+        if (opts[a].levels != opts[0].levels || uni_a != uni_0 || (!uni_a && opts[a].delta != opts[0].delta) || opts[a].max_r != opts[0].max_r) {
+            set_error("all atoms of one batch must share (levels, delta, max_r) and the kind of grid");
             return DFTATOM_E_MIXED_GRID;
         }
     }
     GridDev* gp = nullptr;
-    int rc = get_grid(c, opts[0].levels, opts[0].delta, opts[0].max_r, &gp);
+    int rc = get_grid(c, opts[0].levels, opts[0].method >= 2 ? 0. : opts[0].delta, opts[0].max_r, &gp);
     if (rc) return rc;
     const GridDev g = *gp;
     const int N = g.N;
@@ -380,8 +383,8 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
     int n_tabs = 0, max_steps = 0, zmax = 1;
     for (int a = 0; a < n_atoms; ++a) {
         AtomDev& at = atoms[a];
-        at.Z = opts[a].Z; at.method = opts[a].method; at.n_spin = opts[a].method ? 2 : 1;
-        at.n_steps_max = opts[a].method ? DFTATOM_MAX_STEPS_LSDA : DFTATOM_MAX_STEPS_LDA;
+        at.Z = opts[a].Z; at.method = opts[a].method & 1; at.n_spin = at.method ? 2 : 1;       // 0 / 2: LDA, 1 / 3: LSDA
+        at.n_steps_max = at.method ? DFTATOM_MAX_STEPS_LSDA : DFTATOM_MAX_STEPS_LDA;            // DFTAtom.cpp:106 / :699 (same caps as :396 / :908)
         if (c->k.step_cap > 0) at.n_steps_max = std::min(at.n_steps_max, c->k.step_cap);
         at.mixing = opts[a].mixing;
         max_steps = std::max(max_steps, at.n_steps_max);
@@ -709,8 +712,8 @@ int dftatom_solve_batch(dftatom_ctx* c, const dftatom_options* opts, int n_atoms
     for (int a = 0; a < n_atoms; ++a) {
         int rc = validate(opts[a]);
         if (rc) return rc;
-        if (opts[a].levels != opts[0].levels || opts[a].delta != opts[0].delta || opts[a].max_r != opts[0].max_r) {
-            set_error("all atoms of one batch must share (levels, delta, max_r)");
+        if (opts[a].levels != opts[0].levels || (opts[a].method >= 2) != (opts[0].method >= 2) || (opts[a].method < 2 && opts[a].delta != opts[0].delta) || opts[a].max_r != opts[0].max_r) {
+            set_error("all atoms of one batch must share (levels, delta, max_r) and the kind of grid");
             return DFTATOM_E_MIXED_GRID;
         }
     }
@@ -720,7 +723,7 @@ int dftatom_solve_batch(dftatom_ctx* c, const dftatom_options* opts, int n_atoms
     // deal the atoms in order of decreasing cost (orbital count ~ Z; LSDA doubles it) alternately into the two groups
     std::vector<int> order(n_atoms);
     std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return opts[x].Z * (1 + opts[x].method) > opts[y].Z * (1 + opts[y].method); });
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return opts[x].Z * (1 + (opts[x].method & 1)) > opts[y].Z * (1 + (opts[y].method & 1)); });
     std::vector<int> idx[2];
     for (int q = 0; q < n_atoms; ++q) idx[q & 1].push_back(order[q]);
     for (auto& v : idx) std::sort(v.begin(), v.end());

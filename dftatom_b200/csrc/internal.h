@@ -26,7 +26,9 @@ constexpr double kFourPi = 12.566370614359172;
 // Grid-only tables (device pointers).  K_i = Rp^2 δ^2 e^{2δ i}  (Numerov.h:85,100; PoissonSolver.h:66-74)
 struct GridDev {
     int N, L;
+    int uniform;     // 1: the uniform grid of the CalculateUniform* pair (delta == 0): r_i = i h, h = MaxR / (N - 1)   (DFTAtom.cpp:65-67)
     double delta, rp, max_r;
+    double h;        // uniform grid: its step (0 on the logarithmic grid)
     double* r;       // r_i = Rp (e^{δ i} - 1)                      (Numerov.h:181-184)
     double* ex;      // e^{δ i}
     double* sqex;    // e^{δ i / 2}                                  (DFTAtom.cpp:42)

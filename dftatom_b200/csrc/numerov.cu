@@ -213,15 +213,16 @@ __global__ void match_kernel(GridDev g, const double* __restrict__ atab_all, con
     const int start = start_index(g, kappa);
     const int n_steps = g.N - 1;
 
+    const MatchScale msc = match_scale(g, kappa, start, ob.l);
     double f12 = 0.;      // f_i of the node last evaluated by dval
-    auto dval = [&](int i) { const double gq = fma(-E, __ldg(g.c6 + i), fma(ll1, __ldg(g.b12 + i), __ldg(atab + i))); f12 = 12. * gq; return 1. - gq; };
+    auto dval = [&](int i) { const double gq = match_g(g, atab, ll1, E, msc.rho2, i); f12 = 12. * gq; return 1. - gq; };
 
     for (int i = start + 1; i <= n_steps; ++i) psi[i] = 0.;
-    double y = far_value(g, kappa, start);
+    double y = msc.y_s0;
     psi[start] = y;
     double d = dval(start);
     double wprev = d * y;
-    y = far_value(g, kappa, start - 1);
+    y = msc.y_s1;
     psi[start - 1] = y;
     d = dval(start - 1);
     double w = d * y;
@@ -241,7 +242,7 @@ __global__ void match_kernel(GridDev g, const double* __restrict__ atab_all, con
     const double y_in_match = psi[match];
     // outward
     psi[0] = 0.;
-    y = pow(__ldg(g.r + 1), (double)ob.l + 1.) * exp(-0.5 * g.delta);     // Numerov.h:110-116
+    y = msc.y1;
     psi[1] = y;
     d = dval(1);
     f = f12;

@@ -8,8 +8,15 @@ namespace dft {
 __device__ __forceinline__ int hi32(double x) { return __double2hiint(x); }
 
 // Numerov.h:119-136: bisection on the index for far(idx) = exp(-r_idx sqrt(2|E|) - idx δ/2) < 1e-200
+// Uniform grid (NumerovFunctionRegularGrid, Numerov.h:16-70): the sweeps start at startPoint = min(MaxR, 200 / sqrt(2|E|)) (:53-56,
+// :278-282), steps = (long)(startPoint / h).  The two far seeds sit at the POSITIONS startPoint, startPoint - h - which are not grid
+// nodes when the start point was clipped - paired with the potential of the nodes steps, steps - 1 (:285-296); every later node i is
+// at position h i.
+__device__ __forceinline__ double uniform_start_point(const GridDev& g, double kappa) { return fmin(g.max_r, 200. / kappa); }
+
 __device__ __forceinline__ int start_index(const GridDev& g, double kappa)
 {
+    if (g.uniform) return (int)(uniform_start_point(g, kappa) / g.h);
     // r_i = Rp (e^{δ i} - 1) evaluated in place of the table: 14 dependent table loads would cost ~5000 cycles per call
     // (L2 latency) on kernels whose whole round is ~50000; a last-ulp difference can move the index by one node, where the
     // solution is 1e-200
@@ -23,9 +30,48 @@ __device__ __forceinline__ int start_index(const GridDev& g, double kappa)
     return hi;
 }
 
-__device__ __forceinline__ double far_value(const GridDev& g, double kappa, int idx)
-{   // Numerov.h:103-108
-    return exp(-__ldg(g.r + idx) * kappa - (double)idx * (0.5 * g.delta));
+// far boundary value of seed node idx (= start or start - 1)
+__device__ __forceinline__ double far_value(const GridDev& g, double kappa, int idx, int start)
+{
+    if (g.uniform) return exp(-(uniform_start_point(g, kappa) - (double)(start - idx) * g.h) * kappa);      // Numerov.h:33-36
+    return exp(-__ldg(g.r + idx) * kappa - (double)idx * (0.5 * g.delta));                                   // Numerov.h:103-108
+}
+// what a seed node's f/12 differs by from the table value: on the uniform grid its centrifugal term is taken at the seed's own
+// position, not at the node's (0 on the logarithmic grid, for l = 0, and when the start point is a node)
+__device__ __forceinline__ double seed_g_shift(const GridDev& g, double ll1, double kappa, int idx, int start)
+{
+    if (!g.uniform || ll1 == 0.) return 0.;
+    const double pos = uniform_start_point(g, kappa) - (double)(start - idx) * g.h;
+    const double ri = g.h * (double)idx;
+    return ll1 * (g.h * g.h * (1. / 12.)) * (1. / (pos * pos) - 1. / (ri * ri));
+}
+
+// The two-sided matched solution (Numerov.h:403-504) on either grid: far seeds, near-nucleus start value, and - uniform grid only - the
+// reference's re-computation of the step from the truncated range, h' = startPoint / steps (:430-432): every position becomes h' i,
+// i.e. the potential and energy parts of f_i h'^2 / 12 carry the factor (h'/h)^2 while the centrifugal part l(l+1) / (12 i^2) does not.
+struct MatchScale { double rho2, y_s0, y_s1, y1; };
+__device__ __forceinline__ MatchScale match_scale(const GridDev& g, double kappa, int start, int l)
+{
+    MatchScale m;
+    if (g.uniform) {
+        const double sp = uniform_start_point(g, kappa);
+        const double hp = sp / (double)start;
+        m.rho2 = (hp / g.h) * (hp / g.h);
+        m.y_s0 = exp(-sp * kappa);                                   // GetBoundaryValueFar at startPoint, startPoint - h'  (:434-446)
+        m.y_s1 = exp(-(sp - hp) * kappa);
+        m.y1 = pow(hp, (double)l + 1.);                              // GetBoundaryValueZero at h'  (Numerov.h:38-41, :470-477)
+    } else {
+        m.rho2 = 1.;
+        m.y_s0 = far_value(g, kappa, start, start);
+        m.y_s1 = far_value(g, kappa, start - 1, start);
+        m.y1 = pow(__ldg(g.r + 1), (double)l + 1.) * exp(-0.5 * g.delta);                                   // Numerov.h:110-116
+    }
+    return m;
+}
+__device__ __forceinline__ double match_g(const GridDev& g, const double* __restrict__ atab, double ll1, double E, double rho2, int i)
+{   // f_i / 12 of the matched solve
+    const double a = __ldg(atab + i), b = __ldg(g.b12 + i), c = __ldg(g.c6 + i);
+    return g.uniform ? fma(rho2, fma(-E, c, a), ll1 * b) : fma(-E, c, fma(ll1, b, a));
 }
 
 struct LaneOut { int count; int count_full; int y0_pos; int seen; int steps; double y0_log2; double d_first; };
@@ -42,7 +88,7 @@ static __device__ __noinline__ LaneOut sweep_lane(const GridDev& g, const double
     for (int o = 16; o; o >>= 1) imax = max(imax, __shfl_xor_sync(0xffffffffu, imax, o));
 
     const double ll1 = (double)(l * (l + 1));
-    const double thr = 1. - g.delta * g.delta * (1. / 48.);   // d_i >= thr  <=>  Veff_i <= E  (Numerov.h:336-337)
+    const double thr = 1. - g.delta * g.delta * (1. / 48.);   // d_i >= thr  <=>  Veff_i <= E  (Numerov.h:336-337; uniform grid: delta = 0)
 
     double W1 = 0., W2 = 0.;      // W_{i+1}, W_{i+2}
     double d1 = 1., d2 = 1.;      // d_{i+1}, d_{i+2}
@@ -54,7 +100,8 @@ static __device__ __noinline__ LaneOut sweep_lane(const GridDev& g, const double
 
     for (int i = imax; i >= 1; --i) {
         const double a = __ldg(atab + i), b = __ldg(g.b12 + i), c = __ldg(g.c6 + i);
-        const double gq = fma(-E, c, fma(ll1, b, a));          // f_i / 12
+        double gq = fma(-E, c, fma(ll1, b, a));                // f_i / 12
+        if (i >= start - 1 && i <= start) gq += seed_g_shift(g, ll1, kappa, i, start);
         const double d = 1. - gq;
         if (i > start) continue;
         P *= d1;                                       // P = P_i = prod_{j>i} d_j  (d1 = 1 at i = start)
@@ -71,9 +118,9 @@ static __device__ __noinline__ LaneOut sweep_lane(const GridDev& g, const double
                 else if (seen) snap = count;          // inner turning point: Numerov.h:339-340
             }
         } else if (i == start) {
-            W = d * far_value(g, kappa, i);           // w_start (P_start = 1)
+            W = d * far_value(g, kappa, i, start);    // w_start (P_start = 1)
         } else {
-            W = d * far_value(g, kappa, i) * d1;      // w_{start-1} d_start
+            W = d * far_value(g, kappa, i, start) * d1;      // w_{start-1} d_start
         }
         W2 = W1; W1 = W; d2 = d1; d1 = d;
     }

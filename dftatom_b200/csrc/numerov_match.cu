@@ -41,11 +41,12 @@ __global__ void __launch_bounds__(128) match_seg_kernel(GridDev g, const double*
     const double kappa = sqrt(2. * fabs(E));
     const int start = start_index(g, kappa);
     const int N = g.N;
-    auto gval = [&](int i) { return fma(-E, __ldg(g.c6 + i), fma(ll1, __ldg(g.b12 + i), __ldg(atab + i))); };   // f_i / 12
+    const MatchScale msc = match_scale(g, kappa, start, ob.l);
+    auto gval = [&](int i) { return match_g(g, atab, ll1, E, msc.rho2, i); };   // f_i / 12
 
     // zero tail, far seeds (Numerov.h:427-447)
     for (int i = start + 1 + lane; i < N; i += 32) psi[i] = 0.;
-    const double y_s0 = far_value(g, kappa, start), y_s1 = far_value(g, kappa, start - 1);
+    const double y_s0 = msc.y_s0, y_s1 = msc.y_s1;
     const double g_s0 = gval(start), g_s1 = gval(start - 1);
     const double d_s0 = 1. - g_s0, d_s1 = 1. - g_s1;
     if (lane == 0) { psi[start] = y_s0; psi[start - 1] = y_s1; }
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(128) match_seg_kernel(GridDev g, const double*
     // ------------------------------------------------------------------------------------------------
     double y_out_match;
     {
-        const double y1 = pow(__ldg(g.r + 1), (double)ob.l + 1.) * exp(-0.5 * g.delta);
+        const double y1 = msc.y1;
         const double gn1 = gval(1);
         const int n_out = match - 1;                       // nodes 2..match
         const int len = (n_out + 31) / 32;
@@ -287,7 +288,8 @@ __global__ void __launch_bounds__(kMT) match_cta_kernel(GridDev g, const double*
     const double kappa = sqrt(2. * fabs(E));
     const int start = start_index(g, kappa);
     const int N = g.N;
-    auto gtab = [&](int i) { return fma(-E, __ldg(g.c6 + i), fma(ll1, __ldg(g.b12 + i), __ldg(atab + i))); };   // f_i / 12
+    const MatchScale msc = match_scale(g, kappa, start, ob.l);
+    auto gtab = [&](int i) { return match_g(g, atab, ll1, E, msc.rho2, i); };   // f_i / 12
     if (SMEM) {
         for (int i = t; i <= start; i += kMT) gy[pslot(i)] = gtab(i);
         __syncthreads();
@@ -296,7 +298,7 @@ __global__ void __launch_bounds__(kMT) match_cta_kernel(GridDev g, const double*
     auto put = [&](int i, double y) { if (SMEM) gy[pslot(i)] = y; else psi[i] = y; };
 
     // far seeds (Numerov.h:427-447)
-    const double y_s0 = far_value(g, kappa, start), y_s1 = far_value(g, kappa, start - 1);
+    const double y_s0 = msc.y_s0, y_s1 = msc.y_s1;
     const double g_s0 = gval(start), g_s1 = gval(start - 1);
     const double d_s0 = 1. - g_s0, d_s1 = 1. - g_s1;
     if (t == 0) { sh.y2 = 0.; sh.ylast = 0.; }
@@ -393,7 +395,7 @@ __global__ void __launch_bounds__(kMT) match_cta_kernel(GridDev g, const double*
     // state entering a segment: (W_{bot-1}, D_{bot-2} = W_{bot-1} - W_{bot-2});  Q_i = prod_{j<i} d_j
     // ------------------------------------------------------------------------------------------------
     double y_out_match;
-    const double y1 = pow(__ldg(g.r + 1), (double)ob.l + 1.) * exp(-0.5 * g.delta);
+    const double y1 = msc.y1;
     {
         const double gn1 = gval(1);
         const int n_out = match - 1;                       // nodes 2..match
@@ -506,10 +508,11 @@ __global__ void __launch_bounds__(kMT) match_win_kernel(GridDev g, const double*
     const double kappa = sqrt(2. * fabs(E));
     const int start = start_index(g, kappa);
     const int N = g.N;
-    auto gtab = [&](int i) { return fma(-E, __ldg(g.c6 + i), fma(ll1, __ldg(g.b12 + i), __ldg(atab + i))); };   // f_i / 12
+    const MatchScale msc = match_scale(g, kappa, start, ob.l);
+    auto gtab = [&](int i) { return match_g(g, atab, ll1, E, msc.rho2, i); };   // f_i / 12
 
     // far seeds (Numerov.h:427-447)
-    const double y_s0 = far_value(g, kappa, start), y_s1 = far_value(g, kappa, start - 1);
+    const double y_s0 = msc.y_s0, y_s1 = msc.y_s1;
     const double d_s0 = 1. - gtab(start), d_s1 = 1. - gtab(start - 1);
     if (t == 0) { sh.y2 = 0.; sh.ylast = 0.; }
 
@@ -602,7 +605,7 @@ __global__ void __launch_bounds__(kMT) match_win_kernel(GridDev g, const double*
     if (!found) y_in_match = (start - 2 >= 2) ? sh.y2 : ((start - 1 == 2) ? y_s1 : y_s0);      // matchPoint stays 2 (Numerov.h:449)
 
     // ---------------- outward windows: nodes 2 ... match ----------------
-    const double y1 = pow(__ldg(g.r + 1), (double)ob.l + 1.) * exp(-0.5 * g.delta);
+    const double y1 = msc.y1;
     double oW = (1. - gtab(1)) * y1, oD = oW, oQ = 1.;          // (W_{lo-1}, W_{lo-1} - W_{lo-2}, Q_{lo-1}); W_0 = 0
     for (int lo = 2; lo <= match; lo += kWinNodes) {
         const int hi = min(lo + kWinNodes - 1, match);

@@ -73,8 +73,8 @@ __device__ __forceinline__ void range_sweep(const GridDev& g, const double* __re
             // the far seed w_start lies just above the range (it depends on the tables only): the range begins with the
             // second seed w_{start-1}
             const int i1 = top + 1;
-            const double ga = fma(-E[e], __ldg(g.c6 + i1), fma(ll1, __ldg(g.b12 + i1), __ldg(atab + i1)));
-            W1[e] = (1. - ga) * far_value(g, kappa[e], i1);
+            const double ga = fma(-E[e], __ldg(g.c6 + i1), fma(ll1, __ldg(g.b12 + i1), __ldg(atab + i1))) + seed_g_shift(g, ll1, kappa[e], i1, in.start[e]);
+            W1[e] = (1. - ga) * far_value(g, kappa[e], i1, in.start[e]);
             g1[e] = ga;
             if (!(i1 & 1)) P[e] = 1. - ga;                 // d_{start+1} := 1
             bad |= !(1. - ga > 0.);
@@ -155,18 +155,19 @@ __device__ __forceinline__ void range_sweep(const GridDev& g, const double* __re
                 const double2 t = tile[k];
 #pragma unroll
                 for (int e = 0; e < EPL; ++e) {
-                    const double gk = fma(-E[e], t.y, t.x);
+                    double gk = fma(-E[e], t.y, t.x);
+                    if (g.uniform && i >= start[e] - 1 && i <= start[e]) gk += seed_g_shift(g, ll1, kappa[e], i, start[e]);
                     const double d = 1. - gk;
                     if (i <= start[e]) {
                         double W, s, Dnew;
                         if (i == start[e]) {                      // w_start = d_start far(start)   (Numerov.h:294-298)
-                            W = d * far_value(g, kappa[e], i);
+                            W = d * far_value(g, kappa[e], i, start[e]);
                             s = gk;                               // d_{start+1} := 1
                             P[e] = 1.; count[e] = 0; prev[e] = 0;
                             Dnew = 0.;                            // overwritten at the next node
                             bad |= !(d > 0.);
                         } else if (i == start[e] - 1) {           // w_{start-1} d_start            (Numerov.h:300-303)
-                            W = d * far_value(g, kappa[e], i) * (1. - g1[e]);
+                            W = d * far_value(g, kappa[e], i, start[e]) * (1. - g1[e]);
                             s = fma(-gk, g1[e], gk + g1[e]);
                             Dnew = W - W1[e];                     // D_start = W_{start-1} - W_start
                             bad |= !(d > 0.);

@@ -33,13 +33,16 @@ namespace {
 constexpr int kCL = 8;          // CTAs per density
 constexpr int kCT = 256;        // threads per CTA
 constexpr int kHR = 8;          // right halo (>= sweeps - 1)
+constexpr int kHB = 96;         // left halo buffer in front of every slab array (the largest left halo: 6-sweep visits)
 constexpr double kTinyC = 1e-19;
 enum { kCLoad = 1, kCProlong = 2, kCRestrict = 4 };
 
 struct CLevel {
     int n;                  // owned nodes; node n is the right boundary (Z on level 0, 0 on the correction levels)
     int m;                  // distributed levels: slab nodes per CTA
-    int offP, offS;         // offsets (doubles) inside the CTA's dynamic shared memory
+    int offP, offS;         // offsets (doubles) inside the CTA's dynamic shared memory.  Distributed levels: [kHB left-halo buffer][m slab][kHR right-halo
+                            // buffer] - the halo buffers are written by the NEIGHBOUR CTAs (remote stores at the end of their visits), so a window is one
+                            // contiguous piece of this CTA's own shared memory
     double d, a, b;         // d_l = delta 2^l; a = (1 + d/2)/2; b = (1 - d/2)/2       (PoissonSolver.cpp:56-57)
     int npt, nsteps;        // nodes per thread of this level's visits; warp-scan steps that still matter
     double Ap[5], B;        // A^(2^j), A = a^npt (one thread's affine map); A^32 (one warp)
@@ -49,6 +52,7 @@ struct CLevel {
 struct CShared {
     CLevel lv[16];
     int L, n_dist, lb, md;              // levels; number of distributed levels; block-local level (1024 nodes); dense level (32 nodes)
+    int offCb;                          // every CTA's copy of its share (+ halos) of Phi of the block-local level, pushed by CTA 0: [kHB][m_last/2][kHR]
     double wtot[2][kCT / 32];           // per-warp scan totals, double buffered by sweep parity
     double ufirst[2][kCT / 32 + 1];     // unpatched first value of every warp
     double uinit[kCT / 32 + 1];         // first value of every warp at the start of a visit
@@ -125,7 +129,7 @@ __device__ __noinline__ void visit_dist(int l, int flags, int sweeps)
     const int rank = (int)cluster.block_rank();
     const CLevel& c = cs.lv[l];
     const int m = c.m, s = rank * m, n = c.n;
-    const int HL = sweeps > 3 ? 96 : 64;
+    const int HL = sweeps > 3 ? kHB : 64;
     const int i0 = max(s - HL, 0);                  // frozen left end of the window (rank 0: the boundary node 0)
     const int iR = min(s + m + kHR, n);             // frozen right end (last rank: the boundary node n)
     const int jR = iR - i0;
@@ -133,72 +137,45 @@ __device__ __noinline__ void visit_dist(int l, int flags, int sweeps)
     const int j0 = t * NPT;
     const int q0 = i0 + j0 - s;                     // slab index of this thread's first node (< 0: left halo, >= m: right halo)
     const double a = c.a, b = c.b;
-    double* Pown = c_dyn + c.offP;
-    double* Sown = c_dyn + c.offS;
+    double* Pa = c_dyn + c.offP + kHB;              // slab node q at Pa[q], halos at negative q / q >= m
+    double* Sa = c_dyn + c.offS + kHB;
     const double rbc = (l == 0) ? cs.right_bc : 0.;
-    const bool inner = q0 >= 0 && q0 + NPT <= m;    // every node of this thread lies in the CTA's own slab: plain shared-memory loads
+    const int qmax = m + kHR - 1;
 
     double phi[NPT], hs[NPT];
     const bool dbg = cs.dbg_on && t == 0;
     long long tq0 = dbg ? clock64() : 0;
-    cluster.barrier_wait();                         // the stores of the previous visit (all CTAs) are visible
+    cluster.barrier_wait();                         // the stores and halo pushes of the previous visit (all CTAs) are visible
     long long tq1 = dbg ? clock64() : 0;
-    // ---- window: Phi, Source / 2
-    if (inner) {
+    // ---- window: Phi, Source / 2 - one contiguous piece of this CTA's own shared memory
 #pragma unroll
-        for (int k = 0; k < NPT; ++k) { phi[k] = (flags & kCLoad) ? Pown[q0 + k] : 0.; hs[k] = 0.5 * Sown[q0 + k]; }
-    } else {
-        // halo threads: the owner of a node is the left / right neighbour CTA (distributed shared memory); branch-free pointer selects
-        const double* Pl = rank > 0 ? cluster.map_shared_rank(Pown, rank - 1) : Pown;
-        const double* Pr = rank < kCL - 1 ? cluster.map_shared_rank(Pown, rank + 1) : Pown;
-        const double* Sl = rank > 0 ? cluster.map_shared_rank(Sown, rank - 1) : Sown;
-        const double* Sr = rank < kCL - 1 ? cluster.map_shared_rank(Sown, rank + 1) : Sown;
-#pragma unroll
-        for (int k = 0; k < NPT; ++k) {
-            const int q = q0 + k, i = s + q;
-            const bool live = i < n && i <= iR;
-            const int qq = live ? q : (q0 < 0 ? 0 : m - 1);                         // a safe address for the padding
-            const double* pp = qq < 0 ? Pl + m : (qq >= m ? Pr - m : Pown);
-            const double* sp = qq < 0 ? Sl + m : (qq >= m ? Sr - m : Sown);
-            const double pv = (flags & kCLoad) ? pp[qq] : 0.;
-            const double sv = sp[qq];
-            phi[k] = live ? pv : (i == n ? rbc : 0.);
-            hs[k] = live ? 0.5 * sv : 0.;
-        }
+    for (int k = 0; k < NPT; ++k) {
+        const int q = q0 + k, i = s + q;
+        const bool live = i < n && i <= iR;
+        const int qq = min(q, qmax);
+        const double pv = (flags & kCLoad) ? Pa[qq] : 0.;
+        const double sv = Sa[qq];
+        phi[k] = live ? pv : (i == n ? rbc : 0.);
+        hs[k] = live ? 0.5 * sv : 0.;
     }
     if (flags & kCProlong) {                        // Phi_l += P Phi_{l+1}   (Prolong, PoissonSolver.cpp:110-123)
         const CLevel& cc = cs.lv[l + 1];
         const bool cdist = (l + 1 < cs.n_dist);
-        const double* Cown = c_dyn + cc.offP;
-        const int mc = cc.m, sc = rank * mc;
+        const int mc = m >> 1, sc = rank * mc;
+        const double* Ca = c_dyn + (cdist ? cc.offP : cs.offCb) + kHB;       // coarse slab node qc at Ca[qc]
         constexpr int NCW = NPT / 2 + 2;            // coarse nodes under this thread's nodes
         const int ifirst = i0 + j0, par = ifirst & 1, icf = ifirst >> 1;
         double cv[NCW];
-        if (cdist && inner && (icf - sc) >= 0 && (icf - sc) + NCW <= mc) {
 #pragma unroll
-            for (int q = 0; q < NCW; ++q) cv[q] = Cown[icf - sc + q];
-        } else {
-            const double* Cl = cdist ? (rank > 0 ? cluster.map_shared_rank(Cown, rank - 1) : Cown) : cluster.map_shared_rank(Cown, 0);
-            const double* Cr = cdist ? (rank < kCL - 1 ? cluster.map_shared_rank(Cown, rank + 1) : Cown) : Cl;
-#pragma unroll
-            for (int q = 0; q < NCW; ++q) {
-                const int ic = icf + q;
-                const bool live = ic < cc.n;                                        // the correction vanishes on the boundary (and beyond)
-                const int icc = live ? ic : 0;
-                double v;
-                if (cdist) {
-                    int qc = icc - sc;
-                    qc = max(qc, -mc); qc = min(qc, 2 * mc - 1);
-                    const double* cp = qc < 0 ? Cl + mc : (qc >= mc ? Cr - mc : Cown);
-                    v = cp[qc];
-                } else v = Cl[slot_local(cc.n, icc)];
-                cv[q] = live ? v : 0.;
-            }
+        for (int q = 0; q < NCW; ++q) {
+            const int ic = icf + q;
+            const int qc = min(ic - sc, mc + kHR - 1);
+            const double v = Ca[qc];
+            cv[q] = ic < cc.n ? v : 0.;             // the correction vanishes on the boundary (and beyond)
         }
 #pragma unroll
         for (int k = 0; k < NPT; ++k) {
             const int i = ifirst + k;
-            constexpr int dummy = 0; (void)dummy;
             const int e0 = k >> 1, e1 = (k + 1) >> 1;
             const double even0 = cv[e0], odd0 = 0.5 * (cv[e0] + cv[e0 + 1]);        // first node even: node k sits on coarse e0 (k even) / between e0, e0+1
             const double even1 = cv[e1], odd1 = 0.5 * (cv[e1] + cv[e1 + 1]);        // first node odd
@@ -206,7 +183,7 @@ __device__ __noinline__ void visit_dist(int l, int flags, int sweeps)
             if (i < n && i <= iR) phi[k] += corr;
         }
     }
-    cluster.barrier_arrive();                       // window loaded: the neighbours may overwrite their slabs once everyone got here
+    cluster.barrier_arrive();                       // window loaded: the neighbours may overwrite their slabs / push into the halo buffers once everyone got here
     long long tq2 = dbg ? clock64() : 0;
 
     // ---- sweeps in registers
@@ -219,9 +196,12 @@ __device__ __noinline__ void visit_dist(int l, int flags, int sweeps)
     // "c" is that value.  Right end (node jR) and the padding behind it: swept like any node (what they hold only flows to the right,
     // out of the window) and the end itself is restored after every sweep.
     const int kR = jR - j0;                         // index of the frozen right end inside this thread (0 <= kR < NPT for one thread)
+    const bool hasR = kR >= 0 && kR < NPT;
     double fixR = 0.;
+    if (hasR) {
 #pragma unroll
-    for (int k = 0; k < NPT; ++k) if (k == kR) fixR = phi[k];
+        for (int k = 0; k < NPT; ++k) if (k == kR) fixR = phi[k];
+    }
     const double fix0 = phi[0];
     // old value of the node after this thread's last one: lane + 1's first node; across warps through shared memory
     if (lane == 0) cs.uinit[w] = phi[0];
@@ -248,7 +228,11 @@ __device__ __noinline__ void visit_dist(int l, int flags, int sweeps)
         double cin = fma(sk.Alane, carry, Pex);
         if (t == 0) cin = 0.;
 #pragma unroll
-        for (int k = 0; k < NPT; ++k) phi[k] = (k == kR) ? fixR : fma(apow[k], cin, phi[k]);
+        for (int k = 0; k < NPT; ++k) phi[k] = fma(apow[k], cin, phi[k]);
+        if (hasR) {
+#pragma unroll
+            for (int k = 0; k < NPT; ++k) if (k == kR) phi[k] = fixR;
+        }
         if (lane == 31 && w + 1 < kCT / 32) {
             // next sweep's "old" right neighbour = the next warp's first node after ITS patch: its carry-in is this warp's total
             const double u = cs.ufirst[pb][w + 1];
@@ -256,31 +240,45 @@ __device__ __noinline__ void visit_dist(int l, int flags, int sweeps)
         }
     }
     long long tq3 = dbg ? clock64() : 0;
-    cluster.barrier_wait();                         // every CTA has loaded its window: slabs may be overwritten
+    cluster.barrier_wait();                         // every CTA has loaded its window: slabs and halo buffers may be overwritten
     long long tq4 = dbg ? clock64() : 0;
-    // ---- store the slab
+    // ---- store the slab; push its two ends into the neighbours' halo buffers (remote stores: nobody waits for them)
+    {
+        double* Pl = rank > 0 ? cluster.map_shared_rank(Pa, rank - 1) : nullptr;
+        double* Pr = rank < kCL - 1 ? cluster.map_shared_rank(Pa, rank + 1) : nullptr;
 #pragma unroll
-    for (int k = 0; k < NPT; ++k) {
-        const int q = q0 + k;
-        if (q >= 0 && q < m) Pown[q] = phi[k];
-        if (q == -1) cs.left_adj = phi[k];
+        for (int k = 0; k < NPT; ++k) {
+            const int q = q0 + k;
+            if (q >= 0 && q < m) {
+                Pa[q] = phi[k];
+                if (Pr && q >= m - kHB) Pr[q - m] = phi[k];        // the right neighbour's left halo: its slab indices -kHB .. -1
+                if (Pl && q < kHR) Pl[m + q] = phi[k];             // the left neighbour's right halo: its slab indices m .. m + kHR - 1
+            }
+            if (q == -1) cs.left_adj = phi[k];
+        }
     }
     if (flags & kCRestrict) {                       // Source_{l+1} = 4 (injected residual) - d_{l+1} (first difference); Phi_{l+1} := 0 implicitly
         __syncthreads();
         const CLevel& cc = cs.lv[l + 1];
         const bool cdist = (l + 1 < cs.n_dist);
-        double* Sc = cdist ? c_dyn + cc.offS : cluster.map_shared_rank(c_dyn + cc.offS, 0);
         const int mc = m >> 1;
         const double dc = cc.d;
+        double* Sc = cdist ? c_dyn + cc.offS + kHB : cluster.map_shared_rank(c_dyn + cc.offS, 0);
+        double* Scl = (cdist && rank > 0) ? cluster.map_shared_rank(Sc, rank - 1) : nullptr;
+        double* Scr = (cdist && rank < kCL - 1) ? cluster.map_shared_rank(Sc, rank + 1) : nullptr;
         for (int q = t; q < mc; q += kCT) {
             const int ic = rank * mc + q;
-            const double lft = (q == 0) ? cs.left_adj : Pown[2 * q - 1], mid = Pown[2 * q], rgt = Pown[2 * q + 1];
-            double v = 4. * (Sown[2 * q] + lft - 2. * mid + rgt) - dc * (rgt - lft);
+            const double lft = (q == 0) ? cs.left_adj : Pa[2 * q - 1], mid = Pa[2 * q], rgt = Pa[2 * q + 1];
+            double v = 4. * (Sa[2 * q] + lft - 2. * mid + rgt) - dc * (rgt - lft);
             if (ic == 0) v = 0.;
-            Sc[cdist ? q : slot_local(cc.n, ic)] = v;
+            if (cdist) {
+                Sc[q] = v;
+                if (Scr && q >= mc - kHB) Scr[q - mc] = v;
+                if (Scl && q < kHR) Scl[mc + q] = v;
+            } else Sc[slot_local(cc.n, ic)] = v;
         }
     }
-    cluster.barrier_arrive();                       // slab (and the restricted source) stored
+    cluster.barrier_arrive();                       // slab, halo pushes (and the restricted source) stored
     if (dbg) {
         const long long tq5 = clock64();
         cs.dbg[2] += tq1 - tq0; cs.dbg[4] += tq2 - tq1; cs.dbg[5] += tq3 - tq2; cs.dbg[3] += tq4 - tq3; cs.dbg[6] += tq5 - tq4; cs.dbg[8 + l] += tq5 - tq0;
@@ -469,6 +467,21 @@ __device__ __noinline__ void local_subcycle(const double* G)
     }
     __syncthreads();
     visit_block_local(lb, kCLoad | kCProlong, 3);
+    // every CTA gets its share (+ halos) of Phi_lb for the prolongation into the last distributed level: remote stores into its copy
+    {
+        cg::cluster_group cluster = cg::this_cluster();
+        const CLevel& c = cs.lv[lb];
+        const double* P = c_dyn + c.offP;
+        const int mc = c.n / kCL;                   // coarse share of a CTA
+        const int span = kHB / 2 + mc + kHR;        // coarse slab indices -kHB/2 .. mc + kHR - 1
+        for (int e = threadIdx.x; e < kCL * span; e += kCT) {
+            const int r = e / span, qc = e % span - kHB / 2;
+            const int ic = r * mc + qc;
+            if (ic < 0 || ic >= c.n) continue;
+            double* dst = cluster.map_shared_rank(c_dyn + cs.offCb + kHB, r);
+            dst[qc] = P[slot_local(c.n, ic)];
+        }
+    }
 }
 
 }  // namespace
@@ -488,7 +501,11 @@ __global__ void __cluster_dims__(kCL, 1, 1) __launch_bounds__(kCT, 2) poisson_cl
         for (int l = 0; l <= t; ++l) {
             c.n = 1 << (L - l);
             c.m = 0; c.offP = c.offS = 0; c.npt = 1;
-            if (c.n >= kCL * kCT) { c.m = c.n / kCL; c.offP = off; off += c.m; c.offS = off; off += c.m; c.npt = c.m == 2048 ? 9 : (c.m == 1024 ? 5 : (c.m == 512 ? 3 : 2)); }
+            if (c.n >= kCL * kCT) {
+                c.m = c.n / kCL;
+                c.offP = off; off += kHB + c.m + kHR; c.offS = off; off += kHB + c.m + kHR;
+                c.npt = c.m == 2048 ? 9 : (c.m == 1024 ? 5 : (c.m == 512 ? 3 : 2));
+            }
             else if (c.n >= 32) { c.offP = off; off += c.n + 4; c.offS = off; off += c.n + 4; c.npt = c.n >= 1024 ? 4 : max(1, c.n >> 5); }
         }
         c.d = g.delta * (double)(1 << t);
@@ -501,6 +518,7 @@ __global__ void __cluster_dims__(kCL, 1, 1) __launch_bounds__(kCT, 2) poisson_cl
         int nd = 0;
         for (int l = 0; l < L; ++l) if ((1 << (L - l)) >= kCL * kCT) ++nd;
         cs.L = L; cs.n_dist = nd; cs.lb = L - 10; cs.md = L - 5;
+        cs.offCb = a.smem_doubles - 32 * 32 - (kHB + 128 + kHR);
         cs.right_bc = (a.Zbc && !a.rho_prev) ? (double)a.Zbc[k] : 0.;      // increment form: dU vanishes on both boundaries
         cs.updates = 0;
         cs.dbg_on = a.dbg != nullptr && k == 0;
@@ -510,24 +528,32 @@ __global__ void __cluster_dims__(kCL, 1, 1) __launch_bounds__(kCT, 2) poisson_cl
     __syncthreads();
     double* G = c_dyn + a.smem_doubles - 32 * 32;
     if (rank == 0) for (int i = t; i < 32 * 32; i += kCT) G[i] = a.coarse_op[i];
-    // import: Phi_0 = previous U, Source_0 = r 4 pi K rho  (PoissonSolver.h:55-74); every CTA its slab, coalesced
+    // import: Source_0 = r 4 pi K rho (PoissonSolver.h:55-74) and Phi_0 (the previous U, or zero in increment form) - every CTA its slab
+    // AND its halos, straight from global memory
     {
         const CLevel c0 = cs.lv[0];
         const int s = rank * c0.m;
         const double* u = a.U + (size_t)k * a.ldU;
         const double* rho = a.rho + (size_t)k * a.rho_stride;
-        double* P = c_dyn + c0.offP; double* S = c_dyn + c0.offS;
-        if (a.rho_prev) {           // increment form: Phi_0 = dU = 0, Source_0 = r 4 pi K (rho - rho_prev)
-            double* rp = a.rho_prev + (size_t)k * a.rho_stride;
-            for (int q = t; q < c0.m; q += kCT) {
-                const int i = s + q;
-                const double r = rho[i];
-                P[q] = 0.; S[q] = (i >= 1 && i < N - 1) ? g.psrc[i] * (r - rp[i]) : 0.;
-                rp[i] = r;
-            }
-            if (rank == kCL - 1 && t == 0) rp[N - 1] = rho[N - 1];
-        } else
-        for (int q = t; q < c0.m; q += kCT) { const int i = s + q; P[q] = u[i]; S[q] = (i >= 1 && i < N - 1) ? g.psrc[i] * rho[i] : 0.; }
+        double* P = c_dyn + c0.offP + kHB; double* S = c_dyn + c0.offS + kHB;
+        double* rp = a.rho_prev ? a.rho_prev + (size_t)k * a.rho_stride : nullptr;
+        for (int q = t - kHB; q < c0.m + kHR; q += kCT) {
+            const int i = s + q;
+            if (i < 0 || i > N - 1) continue;
+            const double r = rho[i];
+            const double base = rp ? rp[i] : 0.;
+            P[q] = rp ? 0. : u[i];
+            S[q] = (i >= 1 && i < N - 1) ? g.psrc[i] * (r - base) : 0.;
+        }
+    }
+    cluster.sync();         // everybody has read rho_prev of its halos before anybody overwrites it
+    if (a.rho_prev) {
+        const CLevel c0 = cs.lv[0];
+        const int s = rank * c0.m;
+        const double* rho = a.rho + (size_t)k * a.rho_stride;
+        double* rp = a.rho_prev + (size_t)k * a.rho_stride;
+        for (int q = t; q < c0.m; q += kCT) rp[s + q] = rho[s + q];
+        if (rank == kCL - 1 && t == 0) rp[N - 1] = rho[N - 1];
     }
     __syncthreads();
     cluster.barrier_arrive();
@@ -554,7 +580,7 @@ __global__ void __cluster_dims__(kCL, 1, 1) __launch_bounds__(kCT, 2) poisson_cl
         const CLevel c0 = cs.lv[0];
         const int s = rank * c0.m;
         double* u = a.U + (size_t)k * a.ldU;
-        const double* P = c_dyn + c0.offP;
+        const double* P = c_dyn + c0.offP + kHB;
         if (a.rho_prev) { for (int q = t; q < c0.m; q += kCT) u[s + q] += P[q]; }
         else {
             for (int q = t; q < c0.m; q += kCT) u[s + q] = P[q];
@@ -571,10 +597,10 @@ static int cluster_smem_doubles(int L)
     int off = 0;
     for (int l = 0; l < L; ++l) {
         const int n = 1 << (L - l);
-        if (n >= kCL * kCT) off += 2 * (n / kCL);
+        if (n >= kCL * kCT) off += 2 * (kHB + n / kCL + kHR);
         else if (n >= 32) off += 2 * (n + 4);
     }
-    return off + 32 * 32;
+    return off + (kHB + 128 + kHR) + 32 * 32;
 }
 
 bool poisson_cluster_supported(int L, double delta)

@@ -59,17 +59,23 @@ def _fmt(x, precision):
     return f"{x:.{precision}f}" if precision <= 6 else f"{x:.{precision}g}"
 
 
-def format_report(Z, method, steps, finished, final_alpha, final_beta=None, precision=6):
+def format_report(Z, method, steps, finished, final_alpha, final_beta=None, precision=6, n_alpha=None):
     """Inverse of parse_report: the exact line sequence the reference prints (DFTAtom.cpp:358-490 / :857-1021).
 
     steps: list of dicts {levels: [(n, l, E, nodes), ...] (alpha first, then beta, untagged as in the reference's
     non-uniform path), Etotal, Ekin, Ecoul, Eenuc, Exc}; final_*: [(n, l, occ), ...] sorted by eigenvalue.
     """
-    out = [f"Computing atom with Z={Z} using {'LSDA' if method else 'LSD'} with non-uniform grid"]
+    # method 2 / 3: the uniform-grid pair (DFTAtom.cpp:69 "LDA", :656 "LSDA"; its LSDA level lines are tagged alpha / beta, :269-277)
+    uniform = method >= 2
+    lsda = method in (1, 3)
+    out = [f"Computing atom with Z={Z} using {('LSDA' if lsda else ('LDA' if uniform else 'LSD'))} with {'uniform' if uniform else 'non-uniform'} grid"]
     for k, st in enumerate(steps):
         out.append(f"Step: {k}")
-        for (n, l, E, nodes) in st["levels"]:
-            out.append(f"Energy {n}{ORB[l]}: {_fmt(E, precision)} Num nodes: {nodes}")
+        for j, (n, l, E, nodes) in enumerate(st["levels"]):
+            tag = ""
+            if uniform and lsda:
+                tag = "alpha " if (n_alpha is None or j < n_alpha) else "beta "
+            out.append(f"Energy {tag}{n}{ORB[l]}: {_fmt(E, precision)} Num nodes: {nodes}")
         out.append("Etotal = {} Ekin = {} Ecoul = {} Eenuc = {} Exc = {}".format(
             *[_fmt(st[key], precision) for key in ("Etotal", "Ekin", "Ecoul", "Eenuc", "Exc")]))
         if finished and k == len(steps) - 1:
@@ -77,7 +83,7 @@ def format_report(Z, method, steps, finished, final_alpha, final_beta=None, prec
         else:
             out.append(SEP)
     conf = lambda lv: "".join(f"{n}{ORB[l]}{occ} " for (n, l, occ) in lv)
-    if method:
+    if lsda:
         out.append("Alpha: " + conf(final_alpha))
         out.append("Beta: " + conf(final_beta or []))
     else:
