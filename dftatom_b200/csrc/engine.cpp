@@ -90,6 +90,7 @@ struct Knobs {
                                // value trades that for throughput while many atoms are active (above ~37 densities the clusters need more than one wave)
     int delta_poisson = 1;     // warm-started Poisson solves in increment form (A dU = -dS, U += dU: scf.cu) - keeps consecutive SCF steps free of the
                                // rounding-floor noise of a plain FP64 multigrid solve; 0 = iterate on U itself
+    int adaptive_mixing = 0;   // opt-in: per-atom damping raised when Etotal sloshes with period 2 (beyond the reference; default: its fixed linear mixing)
     int step_cap = 0;          // > 0: lower the SCF step cap (100 LDA / 150 LSDA, DFTAtom.cpp:396,908) to this many steps (tests: with run_to_cap, run exactly as long as the reference did)
     int use_graph = 1;         // SCF steps are replayed from a captured CUDA graph (one graph launch per step) instead of 5+ kernel launches
 };
@@ -285,6 +286,7 @@ int dftatom_set_option(dftatom_ctx* c, const char* key, double value)
     else if (k == "cluster_poisson") c->k.cluster_poisson = value != 0.;
     else if (k == "cluster_max_dens") c->k.cluster_max_dens = std::max(0, (int)value);
     else if (k == "delta_poisson") c->k.delta_poisson = value != 0.;
+    else if (k == "adaptive_mixing") c->k.adaptive_mixing = value != 0.;
     else if (k == "step_cap") c->k.step_cap = std::max(0, (int)value);
     else if (k == "run_to_cap") c->k.run_to_cap = value != 0.;
     else if (k == "use_graph") c->k.use_graph = value != 0.;
@@ -408,7 +410,7 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
             ++n_tabs;
         }
         if (at.n_spin == 1) { at.orb_begin[1] = 0; at.orb_count[1] = 0; }
-        astate[a] = AtomState{ 0., 0, 0, 0, DFTATOM_MAX_STEPS };
+        astate[a] = AtomState{ 0., 0, 0, 0, DFTATOM_MAX_STEPS, opts[a].mixing, 0., 0., 0, 0 };
     }
     const int n_orbs = (int)orbs.size();
     const int stride = max_steps;
@@ -460,7 +462,7 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
     b.atab = c->atab.as<double>(); b.psi = c->psi.as<double>(); b.match_pt = c->match_pt.as<int>(); b.inv_norm = c->inv_norm.as<double>(); b.epart = c->epart.as<double>(); b.eticket = c->eticket.as<int>();
     b.phi = c->phi.as<double>(); b.src = c->src.as<double>(); b.U = c->ubuf.as<double>(); b.ldU = ldU; b.Zbc = c->zbc.as<int>(); b.tab_of = c->tab_of.as<int>();
     b.steps = c->steps.as<dftatom_step>(); b.steps_stride = stride; b.n_active = c->n_active.as<int>();
-    b.run_to_cap = c->k.run_to_cap;
+    b.run_to_cap = c->k.run_to_cap; b.adaptive_mixing = c->k.adaptive_mixing;
 
     PoissonArgs pa{};
     pa.n_dens = n_atoms; pa.rho = b.rhot; pa.Zbc = b.Zbc; pa.phi = b.phi; pa.src = b.src; pa.u_out = b.U; pa.coarse_op = g.coarse_op;
@@ -792,12 +794,12 @@ static int numerov_lanes_impl(dftatom_ctx* c, const double* V, int levels, doubl
     DFT_CHECK(cudaMemcpyAsync(d_lim, nodes_limit, sizeof(int) * n_lanes, cudaMemcpyHostToDevice, st));
     DFT_CHECK(cudaMemcpyAsync(d_E, E, sizeof(double) * n_lanes, cudaMemcpyHostToDevice, st));
     NumerovLaneArgs a{ dA.as<double>(), n_lanes, d_tab, d_l, d_E, d_lim, d_sign, d_log, d_cnt };
-    if (impl == 0) launch_numerov_lanes_fast(g, a, st); else if (impl == 2) launch_numerov_lanes_seg(g, a, c->segments(N) > 1 ? c->segments(N) : 32, st); else launch_numerov_lanes(g, a, st);
+    if (impl == 0) launch_numerov_lanes_fast(g, a, st); else if (impl == 2) launch_numerov_lanes_seg(g, a, c->segments(N) > 1 ? c->segments(N) : 32, st); else if (impl == 3) launch_numerov_lanes_outward(g, a, st); else launch_numerov_lanes(g, a, st);
     if (reps > 0) {          // microbench: the same launch `reps` more times between CUDA events (tables and lanes resident)
         cudaEvent_t e0, e1;
         DFT_CHECK(cudaEventCreate(&e0)); DFT_CHECK(cudaEventCreate(&e1));
         DFT_CHECK(cudaEventRecord(e0, st));
-        for (int r = 0; r < reps; ++r) { if (impl == 0) launch_numerov_lanes_fast(g, a, st); else if (impl == 2) launch_numerov_lanes_seg(g, a, c->segments(N) > 1 ? c->segments(N) : 32, st); else launch_numerov_lanes(g, a, st); }
+        for (int r = 0; r < reps; ++r) { if (impl == 0) launch_numerov_lanes_fast(g, a, st); else if (impl == 2) launch_numerov_lanes_seg(g, a, c->segments(N) > 1 ? c->segments(N) : 32, st); else if (impl == 3) launch_numerov_lanes_outward(g, a, st); else launch_numerov_lanes(g, a, st); }
         DFT_CHECK(cudaEventRecord(e1, st));
         DFT_CHECK(cudaStreamSynchronize(st));
         float ms = 0.f;

@@ -76,6 +76,10 @@ struct AtomState {
     int done;            // 1 once the stop criterion fired or the cap was reached
     int n_steps;
     int status;
+    // opt-in adaptive damping (set_option "adaptive_mixing"; beyond the reference): the weight of the OLD density this atom
+    // currently mixes with (starts at Options::alpha), the last two changes of Etotal, and a hold-off counter
+    double mix, d1, d2;
+    int hold, n_raised;
 };
 
 struct PoissonLevels {       // offsets of each level inside one density's phi/src block
@@ -94,6 +98,7 @@ struct NumerovLaneArgs {
     int* y0_sign; double* y0_log2; int* count;
 };
 void launch_numerov_lanes(const GridDev& g, const NumerovLaneArgs& a, cudaStream_t st);
+void launch_numerov_lanes_outward(const GridDev& g, const NumerovLaneArgs& a, cudaStream_t st);     // Numerov.h:204-270
 
 void launch_search_init(const GridDev& g, const AtomDev* atoms, const AtomState* astate, const OrbitalDev* orbs, SearchState* ss,
                         int n_orbs, cudaStream_t st);
@@ -270,6 +275,7 @@ struct ScfBuffers {
     int steps_stride;
     int* n_active;    // device counter of atoms not done
     int run_to_cap;   // != 0: the stop test is recorded in dftatom_step.stop_criterion_met but never ends the SCF
+    int adaptive_mixing;  // != 0: per-atom damping is raised when Etotal sloshes with period 2 (scf.cu); 0: the reference's fixed linear mixing
 };
 void launch_gather_last_steps(const ScfBuffers& b, dftatom_step* out, cudaStream_t st);
 // increment form of the warm-started Poisson solves (scf.cu): dS = r 4 pi K (rho - rho_prev), dU = 0, rho_prev = rho (dS == NULL: only

@@ -26,6 +26,50 @@ __global__ void numerov_lanes_kernel(GridDev g, NumerovLaneArgs a)
     }
 }
 
+// SolveSchrodingerCountNodesFromNucleus (Numerov.h:204-270; public in the reference, without a caller - SURVEY 8(f) rank 4): the
+// outward sweep from y_0 = 0, y_1 = r_1^(l+1) e^(-delta/2) (uniform grid: h^(l+1)) to the cut-off index, counting the sign changes
+// of y; returns on overflow, on count > limit, and at the outer classical turning point.  Reference-shaped (one division per node):
+// a component entry point (dftatom_numerov_lanes, impl = 3), not on the SCF path.
+__global__ void numerov_lanes_outward_kernel(GridDev g, NumerovLaneArgs a)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= a.n_lanes) return;
+    const double* __restrict__ atab = a.atab + (size_t)a.tab[k] * g.N;
+    const int l = a.l[k], limit = a.limit[k];
+    const double E = a.E[k];
+    const double ll1 = (double)(l * (l + 1));
+    const double kappa = sqrt(2. * fabs(E));
+    const int steps = start_index(g, kappa);
+    const double thr = 1. - g.delta * g.delta * (1. / 48.);       // d_i >= thr  <=>  Veff_i <= E
+    auto gval = [&](int i) { return fma(-E, __ldg(g.c6 + i), fma(ll1, __ldg(g.b12 + i), __ldg(atab + i))); };
+    double y = g.uniform ? pow(g.h, (double)l + 1.) : pow(__ldg(g.r + 1), (double)l + 1.) * exp(-0.5 * g.delta);
+    double gq = gval(1), d = 1. - gq, f = 12. * gq;
+    double wprev = 0., w = d * y;
+    bool positive = y > 0., seen = d >= thr;
+    int count = 0;
+    for (int i = 2; i <= steps; ++i) {
+        const double wn = 2. * w - wprev + y * f;
+        wprev = w; w = wn;
+        gq = gval(i); d = 1. - gq; f = 12. * gq;
+        y = w / d;
+        if (fabs(y) == INFINITY) break;
+        if ((y > 0.) != positive) {
+            if (++count > limit) break;
+            positive = !positive;
+        }
+        if (d >= thr) seen = true;
+        else if (seen) break;
+    }
+    if (a.count) a.count[k] = count;
+    if (a.y0_sign) a.y0_sign[k] = 0;
+    if (a.y0_log2) a.y0_log2[k] = 0.;
+}
+
+void launch_numerov_lanes_outward(const GridDev& g, const NumerovLaneArgs& a, cudaStream_t st)
+{
+    numerov_lanes_outward_kernel<<<(a.n_lanes + 63) / 64, 64, 0, st>>>(g, a);
+}
+
 void launch_numerov_lanes(const GridDev& g, const NumerovLaneArgs& a, cudaStream_t st)
 {
     const int threads = 32;

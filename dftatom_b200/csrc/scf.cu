@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(kDT) density_update_kernel(GridDev g, ScfBuffe
     __syncthreads();
     const int per = (N + (int)gridDim.y - 1) / (int)gridDim.y;
     const int i0 = blockIdx.y * per, i1 = min(i0 + per, N);
-    const double keep = at.mixing, take = 1. - at.mixing;
+    const double keep = b.adaptive_mixing ? as.mix : at.mixing, take = 1. - keep;
     double* rt = b.rhot + (size_t)a * N;
     for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
         double tot = 0.;
@@ -467,6 +467,19 @@ __global__ void __launch_bounds__(kPT2) potential_energy_kernel(GridDev g, Poiss
         const int crit = fabs((as.e_old - etot) / etot) < kTotalEnergyTol && ok && as.prev_ok;                                // :474
         rec->stop_criterion_met = crit;
         if (crit && !b.run_to_cap) { done = 1; status = DFTATOM_CONVERGED; }
+        if (b.adaptive_mixing) {
+            // Opt-in damping (default off: the reference's fixed linear mixing).  Linear mixing rho <- a rho + (1 - a) F(rho) sloshes with period 2
+            // when the density response has an eigenvalue lambda < -(1 + a)/(1 - a) ~ -3 at a = 0.5 (nearly full nodeless 3d / 4f shells: Cu, Zn,
+            // Ho .. Yb; the reference runs Er, Tm, Yb to its 100-step cap).  Detected as three energy changes of alternating sign
+            // that decay by less than 2x per step; the cure is more of the old density: a <- (1 + a) / 2, at most three times, with a hold-off.
+            const double d0 = etot - as.e_old;
+            if (as.hold > 0) --as.hold;
+            else if (as.n_steps >= 6 && as.n_raised < 3 && d0 * as.d1 < 0. && as.d1 * as.d2 < 0. && fabs(d0) > 0.5 * fabs(as.d1) && fabs(as.d1) > 0.5 * fabs(as.d2)) {
+                as.mix = 0.5 * (1. + as.mix);
+                as.hold = 4; as.n_raised += 1;
+            }
+            as.d2 = as.d1; as.d1 = d0;
+        }
         as.e_old = etot;
         as.prev_ok = ok;
         as.n_steps += 1;

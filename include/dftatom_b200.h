@@ -122,6 +122,10 @@ const char* dftatom_version(void);
  *   "run_to_cap"   (default 0) 1 = the stop test of DFTAtom.cpp:474 is evaluated and recorded (dftatom_step.stop_criterion_met) but does
  *                   not end the SCF: every atom runs to the step cap.  Lets a test compare the record at the step where the REFERENCE
  *                   stopped, whatever step this implementation's own (noise-driven) stop fires at.
+ *   "adaptive_mixing" (default 0 = the reference's fixed linear mixing; results unchanged) 1 = opt-in damping beyond the reference: when an
+ *                   atom's Etotal sloshes with period 2 (three changes of alternating sign decaying by less than 2x per step - the
+ *                   nearly full nodeless 3d / 4f shells: Cu, Zn, Ho..Yb; the reference runs Er, Tm, Yb to its 100-step cap) the weight
+ *                   of its old density is raised, alpha <- (1 + alpha) / 2, at most three times.  Lets all 92 atoms of the sweep converge.
  *   "step_cap"     (default 0 = the reference's caps, 100 LDA / 150 LSDA steps) a lower cap on the SCF steps of every atom of the batch
  *   "cluster_poisson" (default 1) warm-started Poisson solves on grids of 2049 .. 16385 nodes run as one thread-block cluster of 8 CTAs per
  *                   density with the whole multigrid hierarchy in distributed shared memory (poisson_cluster.cu); 0 = one CTA per density.
@@ -177,7 +181,9 @@ int dftatom_measure_fp64_peak(dftatom_ctx* ctx, double* tflops);
  * impl = 0: the production tile-staged sweep, count[k] = number of ALL sign changes of y_start..y_1,y_0 (the Sturm count
  *           the fused search uses; nodes_limit ignored; -1 if the lane hit a non-positive 1 - f/12).
  * impl = 2: the same count through the parallel-in-r sweep (one thread-block cluster per 32 lanes, warp = radial segment,
- *           set_option("r_segments") segments). */
+ *           set_option("r_segments") segments).
+ * impl = 3: count[k] = SolveSchrodingerCountNodesFromNucleus (Numerov.h:204-270: the OUTWARD sweep from the nucleus with its early exits -
+ *           overflow, count > nodes_limit, outer classical turning point; public in the reference but without a caller); y0_* are 0. */
 int dftatom_numerov_lanes(dftatom_ctx* ctx, const double* V, int levels, double delta, double max_r, int n_lanes,
                           const int* l, const double* E, const int* nodes_limit, int impl,
                           int* y0_sign, double* y0_log2, int* count);

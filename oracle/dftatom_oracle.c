@@ -206,6 +206,36 @@ int orc_numerov_count_nodes(const double* V, int n_nodes, double delta, double m
     return count;
 }
 
+int orc_numerov_count_from_nucleus(const double* V, int n_nodes, double delta, double max_r, int l, double E, int limit)
+{   /* SolveSchrodingerCountNodesFromNucleus, Numerov.h:204-270, non-uniform branch (no caller in the reference):
+     * outward from y_0 = 0, y_1 = near value, counting sign changes up to the cut-off index; returns on overflow, on count > limit,
+     * and at the OUTER classical turning point (first forbidden node after the allowed region was seen). */
+    const nfun g = nfun_make(V, n_nodes, delta, max_r);
+    const long steps = nf_start(&g, E, n_nodes - 1);
+    const double twelfth = 1. / 12.;
+    double y = nf_near(&g, 1., l);
+    double wprev = 0;
+    double f = nf_f(&g, l, E, 1);
+    double w = (1 - twelfth * f) * y;
+    int positive = y > 0, count = 0;
+    int seen_allowed = nf_veff(&g, l, 1) <= E;
+    for (long i = 2; i <= steps; ++i) {
+        const double wnext = 2. * w - wprev + y * f;
+        wprev = w; w = wnext;
+        f = nf_f(&g, l, E, i);
+        y = GETU(w, f);
+        if (fabs(y) == INFINITY) return count;
+        if ((y > 0) != positive) {
+            if (++count > limit) return count;
+            positive = !positive;
+        }
+        const double veff = nf_veff(&g, l, i);
+        if (veff <= E) seen_allowed = 1;
+        else if (seen_allowed) return count;
+    }
+    return count;
+}
+
 int orc_numerov_count_all(const double* V, int n_nodes, double delta, double max_r, int l, double E)
 {   /* NOT a reference function: the sweep of Numerov.h:272-349 with its three early exits disabled, i.e. the number
      * of sign changes in y_start-1 .. y_1, y_0 (the Sturm count the CUDA search uses as its predicate). */

@@ -30,6 +30,17 @@ int ref_numerov_count_nodes(const double* V, int n_nodes, double delta, double r
     return cnt;
 }
 
+// Numerov.h:204-270 (public, no caller in the reference)
+int ref_numerov_count_from_nucleus(const double* V, int n_nodes, double delta, double rmax, int l, double E, int nodes_limit)
+{
+    DFT::Potential pot;
+    pot.m_potentialValues.assign(V, V + n_nodes);
+    NumerovNU num(pot, delta, rmax, n_nodes);
+    int cnt = 0;
+    num.SolveSchrodingerCountNodesFromNucleus(n_nodes - 1, l, E, n_nodes - 1, nodes_limit, cnt);
+    return cnt;
+}
+
 // Numerov.h:351-401
 double ref_numerov_solution_in_zero(const double* V, int n_nodes, double delta, double rmax, int l, double E)
 {

@@ -57,6 +57,7 @@ def oracle():
         L.orc_numerov_start_index.argtypes = [C.c_double, C.c_int, C.c_double, C.c_double]
         L.orc_numerov_count_nodes.argtypes = [_dp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_int]
         L.orc_numerov_count_all.argtypes = [_dp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double]
+        L.orc_numerov_count_from_nucleus.argtypes = [_dp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_int]
         L.orc_numerov_y0.restype = C.c_double
         L.orc_numerov_y0.argtypes = [_dp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double]
         L.orc_numerov_match.restype = C.c_long
@@ -95,6 +96,8 @@ def ref_components():
             return None
         L = C.CDLL(path)
         L.ref_numerov_count_nodes.argtypes = [_dp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_int]
+        if hasattr(L, "ref_numerov_count_from_nucleus"):
+            L.ref_numerov_count_from_nucleus.argtypes = [_dp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_int]
         L.ref_numerov_solution_in_zero.restype = C.c_double
         L.ref_numerov_solution_in_zero.argtypes = [_dp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double]
         L.ref_numerov_lanes.argtypes = [_dp, C.c_int, C.c_double, C.c_double, C.c_int, _ip, _dp, _ip, _dp, _ip]
@@ -157,6 +160,12 @@ def numerov_lanes(V, delta, max_r, l, E, limit):
     y0 = np.array([oracle().orc_numerov_y0(d(V), len(V), delta, max_r, int(li), float(Ei)) for li, Ei in zip(l, E)])
     cnt = np.array([oracle().orc_numerov_count_nodes(d(V), len(V), delta, max_r, int(li), float(Ei), int(k)) for li, Ei, k in zip(l, E, limit)], np.int32)
     return y0, cnt
+
+
+def numerov_count_from_nucleus(V, delta, max_r, l, E, limit):
+    """SolveSchrodingerCountNodesFromNucleus (Numerov.h:204-270) for lanes (l, E, limit)."""
+    V = np.ascontiguousarray(V, np.float64)
+    return np.array([oracle().orc_numerov_count_from_nucleus(d(V), len(V), delta, max_r, int(a), float(b), int(c)) for a, b, c in zip(l, E, limit)], np.int32)
 
 
 def numerov_count_all(V, delta, max_r, l, E):

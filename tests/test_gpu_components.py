@@ -314,3 +314,24 @@ def test_poisson_exact_mode_is_bit_identical(ctx, L, delta, rmax):
             U_r = np.zeros(N)
             ref.ref_poisson_nonuniform(L, delta, int(Z), rmax, O.d(np.ascontiguousarray(rho[j])), O.d(U_r))
             assert np.array_equal(U[j], U_r)
+
+
+@pytest.mark.parametrize("kind,L,delta,rmax,Z", [("coulomb", 12, 0.001, 15.0, 18), ("screened", 13, 0.0008, 30.0, 64)])
+def test_outward_node_count_matches_oracle(ctx, kind, L, delta, rmax, Z):
+    """SolveSchrodingerCountNodesFromNucleus (Numerov.h:204-270; public in the reference, no caller) as lanes
+    (impl = 3): the count of the outward sweep with its three early exits, bit-exact against the oracle's restatement (itself pinned on
+    the reference's own class in tests/test_oracle.py) on random (l, E, limit) lanes incl. positive energies."""
+    N, rp, r = O.grid(L, delta, rmax)
+    V = _potential(kind, Z, r)
+    rng = np.random.default_rng(7 * L)
+    n_l = 256
+    ls = rng.integers(0, 4, n_l).astype(np.int32)
+    Es = np.concatenate([-10 ** rng.uniform(-2, np.log10(Z * Z + 1.0), n_l - 32), rng.uniform(0, 50, 32)])
+    lim = rng.integers(0, 7, n_l).astype(np.int32)
+    _, _, cnt = ctx.numerov_lanes(V, L, delta, rmax, ls, Es, lim, impl=3)
+    assert np.array_equal(cnt, O.numerov_count_from_nucleus(V, delta, rmax, ls, Es, lim))
+    # known answer: in a Coulomb well the outward count up to the outer turning point of E just above E_n (l = 0) is n - 1... n
+    if kind == "coulomb":
+        E3 = -Z * Z / 18.0
+        _, _, c3 = ctx.numerov_lanes(V, L, delta, rmax, np.zeros(2, np.int32), np.array([E3 * 1.02, E3 * 0.98]), np.full(2, 10, np.int32), impl=3)
+        assert list(c3) == [2, 2] or list(c3) == [2, 3]

@@ -415,3 +415,23 @@ def test_uniform_grid_pair_every_step(ctx):
     # the two kinds of grid cannot share a batch
     with pytest.raises(D.DFTAtomError):
         ctx.solve_batch([D.Options(2, 12, 15.0, 0.001, 0.5, 0), D.Options(2, 12, 15.0, 0.001, 0.5, 2)])
+
+
+def test_opt_in_adaptive_mixing(ctx):
+    """SURVEY 8(f) rank 4 (beyond the reference, opt-in): with set_option("adaptive_mixing", 1) the atoms the reference's fixed linear
+    mixing leaves sloshing for all 100 steps (Er, Tm, Yb) converge; atoms that never slosh are untouched bit for bit; the default
+    (off) is the reference's behaviour."""
+    opts = [D.Options(Z, 14, 25.0, 0.0005, 0.5, 0) for Z in (18, 68, 69, 70)]
+    base = ctx.solve_batch(opts)
+    ctx.set_option("adaptive_mixing", 1)
+    try:
+        damp = ctx.solve_batch(opts)
+    finally:
+        ctx.set_option("adaptive_mixing", 0)
+    assert [r.finished for r in base] == [True, False, False, False] and [r.n_steps for r in base][1:] == [100, 100, 100]
+    assert all(r.finished for r in damp) and max(r.n_steps for r in damp) <= 70
+    assert [s.Etotal for s in damp[0].steps] == [s.Etotal for s in base[0].steps]           # Ar never sloshes: identical records
+    # Er converges to the value its undamped trajectory is creeping towards (|dE/E| ~ 2e-10 at step 99); Yb's undamped step-99 record is a
+    # snapshot of a +-0.4 Ha oscillation (SURVEY B.1)
+    assert abs(damp[1].Etotal - base[1].Etotal) < 1e-5
+    assert abs(damp[3].Etotal - base[3].Etotal) > 0.1
