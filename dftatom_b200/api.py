@@ -80,6 +80,7 @@ def load_library():
     lib.dftatom_partition.argtypes = [_ip, _ip, C.c_int, C.c_int, _ip]
     lib.dftatom_solve_batch.argtypes = [C.c_void_p, C.POINTER(_COptions), C.c_int, C.POINTER(_CResult), C.POINTER(_CStep), C.c_int]
     lib.dftatom_last_timing.argtypes = [C.c_void_p, _dp, C.POINTER(C.c_longlong)]
+    lib.dftatom_last_graph_iterations.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
     lib.dftatom_last_transfer.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     lib.dftatom_last_profile.argtypes = [C.c_void_p, C.POINTER(_CProfile)]
     lib.dftatom_measure_fp64_peak.argtypes = [C.c_void_p, _dp]
@@ -284,6 +285,12 @@ class Context:
         ms, n = C.c_double(), C.c_longlong()
         _check(self._lib.dftatom_last_timing(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def last_graph_iterations(self) -> int:
+        """SCF steps the last solve_batch ran inside the CUDA-graph while node (0: host-driven loop)."""
+        v = C.c_longlong()
+        _check(self._lib.dftatom_last_graph_iterations(self._h, C.byref(v)))
+        return v.value
 
     def last_transfer(self):
         """(host->device bytes, device->host bytes) of the last solve_batch."""

@@ -115,6 +115,7 @@ struct dftatom_ctx {
     // timing of the last solve
     double last_ms = 0.;
     long long last_launches = 0;
+    long long last_graph_iterations = 0;                    // SCF steps the last solve ran inside the CUDA-graph while node (0: host-driven loop)
     long long last_d2h_bytes = 0, last_h2d_bytes = 0;      // bytes the last solve_batch moved between host and device
 };
 
@@ -311,6 +312,13 @@ int dftatom_last_timing(dftatom_ctx* c, double* ms, long long* launches)
     return 0;
 }
 
+int dftatom_last_graph_iterations(dftatom_ctx* c, long long* iterations)
+{
+    if (!c || !iterations) return DFTATOM_E_ARG;
+    *iterations = c->last_graph_iterations;
+    return 0;
+}
+
 int dftatom_last_transfer(dftatom_ctx* c, long long* h2d_bytes, long long* d2h_bytes)
 {
     if (!c) return DFTATOM_E_ARG;
@@ -414,6 +422,7 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
     }
     const int n_orbs = (int)orbs.size();
     const int stride = max_steps;
+    c->last_graph_iterations = 0;
     c->last_h2d_bytes = (long long)(sizeof(AtomDev) * atoms.size() + sizeof(AtomState) * astate.size() + sizeof(OrbitalDev) * orbs.size()
                                     + sizeof(int) * (tab_of.size() + zbc.size() + 2));
 
@@ -587,7 +596,8 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
     const int rounds = search_rounds_needed(zmax);
     int steps_enqueued = 0;
     const int lag = 2;
-    for (int sp = 0; sp < max_steps; ++sp) {
+    // one SCF step = five kernel classes enqueued on the stream; nothing in it touches the host
+    auto enqueue_step = [&](int sp, long long& nl) {
         nvtxRangePushA("dftatom:scf_step");
         begin_phase(DFTATOM_K_SEARCH);
         if (c->k.search_mode == 0) {
@@ -599,36 +609,86 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
             const bool serial_too = !(segs > 1 && c->k.seg_threshold >= n_orbs);      // the serial-in-r kernel can never be selected: do not launch it
             if (serial_too) {
                 launch_search_fused(g, b.atab, b.atoms, b.orbs, b.astate, b.ss, n_orbs, d_work + DFTATOM_K_SEARCH, b.n_active + 1, thr, c->k.warm_start, st);
-                ++launches;
+                ++nl;
             }
             if (segs > 1) {
                 launch_search_seg(g, b.atab, b.atoms, b.orbs, b.astate, b.ss, n_orbs, d_work + DFTATOM_K_SEARCH, segs, b.n_active + 1, thr, c->k.warm_start, st);
-                ++launches;
+                ++nl;
             }
         } else {
-            launch_search_init(g, b.atoms, b.astate, b.orbs, b.ss, n_orbs, st); ++launches;
+            launch_search_init(g, b.atoms, b.astate, b.orbs, b.ss, n_orbs, st); ++nl;
         }
-        if (c->k.search_mode != 0) for (int r = 0; r < rounds; ++r) { launch_search_round(g, b.atab, b.orbs, b.astate, b.ss, n_orbs, d_work + DFTATOM_K_SEARCH, st); ++launches; }
+        if (c->k.search_mode != 0) for (int r = 0; r < rounds; ++r) { launch_search_round(g, b.atab, b.orbs, b.astate, b.ss, n_orbs, d_work + DFTATOM_K_SEARCH, st); ++nl; }
         end_phase();
         begin_phase(DFTATOM_K_MATCH);
         if (c->k.match_mode == 0) launch_match_cta(g, b.atab, b.orbs, b.astate, b.ss, b.psi, b.match_pt, b.inv_norm, n_orbs, st);
         else {                                              // validation paths: warp-per-orbital / reference-shaped serial solution
             if (c->k.match_mode == 2) launch_match_seg(g, b.atab, b.orbs, b.astate, b.ss, b.psi, b.match_pt, n_orbs, st);
             else launch_match(g, b.atab, b.orbs, b.astate, b.ss, b.psi, b.match_pt, n_orbs, st);
-            launch_orbital_norms(g, b, st); ++launches;
+            launch_orbital_norms(g, b, st); ++nl;
         }
-        ++launches;
+        ++nl;
         end_phase();
         begin_phase(DFTATOM_K_DENSITY);
-        launch_density_update(g, b, st); ++launches;
+        launch_density_update(g, b, st); ++nl;
         end_phase();
         begin_phase(DFTATOM_K_POISSON);
-        poisson_solve((sp >= c->k.warm_after) ? c->k.warm_vcycles : 0, launches);
+        poisson_solve((sp >= c->k.warm_after) ? c->k.warm_vcycles : 0, nl);
         end_phase();
         begin_phase(DFTATOM_K_POTENTIAL);
-        launch_potential_energy(g, lv, b, 0, st); ++launches;
+        launch_potential_energy(g, lv, b, 0, st); ++nl;
         end_phase();
         nvtxRangePop();
+    };
+    // The SCF loop.  Default: the steady-state step (from step warm_after on every step enqueues the same launches) is captured ONCE into
+    // the body of a CUDA-graph WHILE node whose condition - "some atom is still iterating" - is set on the device by the last kernel of the
+    // body (cudaGraphSetConditional): one graph launch runs the rest of the SCF of the whole batch with no host round trip at all.
+    // Not used with per-class event timing (profile), the validation search / match modes, or the cooperative team-mode Poisson kernel.
+    const bool team_possible = g.L >= 15 && !stream && !exact;
+    const bool graph_ok = c->k.use_graph && !prof && c->k.search_mode == 0 && c->k.match_mode == 0 && !team_possible && !getenv("DFTATOM_DEBUG_CLUSTER");
+    bool graph_done = false;
+    if (graph_ok) {
+        const int n_cold = std::min(max_steps, std::max(0, c->k.warm_after));
+        for (int sp = 0; sp < n_cold; ++sp) { enqueue_step(sp, launches); ++steps_enqueued; }
+        if (n_cold < max_steps) {
+            cudaGraph_t graph = nullptr, body = nullptr;
+            cudaGraphExec_t exec = nullptr;
+            cudaGraphConditionalHandle handle;
+            long long per_iter = 0;
+            bool ok = cudaGraphCreate(&graph, 0) == cudaSuccess && cudaGraphConditionalHandleCreate(&handle, graph, 1, cudaGraphCondAssignDefault) == cudaSuccess;
+            if (ok) {
+                cudaGraphNodeParams np = {};
+                np.type = cudaGraphNodeTypeConditional;
+                np.conditional.handle = handle; np.conditional.type = cudaGraphCondTypeWhile; np.conditional.size = 1;
+                cudaGraphNode_t node;
+                ok = cudaGraphAddNode(&node, graph, nullptr, 0, &np) == cudaSuccess;
+                if (ok) body = np.conditional.phGraph_out[0];
+            }
+            if (ok && cudaStreamBeginCaptureToGraph(st, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                enqueue_step(n_cold, per_iter);
+                launch_scf_loop_condition(handle, b.n_active, d_work + 6, st); ++per_iter;
+                ok = cudaStreamEndCapture(st, nullptr) == cudaSuccess;
+            } else ok = false;
+            ok = ok && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+            if (ok) {
+                ok = cudaGraphLaunch(exec, st) == cudaSuccess;
+                graph_done = ok;
+            }
+            if (graph_done) {
+                DFT_CHECK(cudaStreamSynchronize(st));
+                unsigned long long iters = 0;
+                DFT_CHECK(cudaMemcpy(&iters, d_work + 6, sizeof(iters), cudaMemcpyDeviceToHost));
+                launches += per_iter * (long long)iters;
+                steps_enqueued += (int)iters;
+                c->last_graph_iterations = (long long)iters;
+            }
+            if (exec) cudaGraphExecDestroy(exec);
+            if (graph) cudaGraphDestroy(graph);
+            if (!graph_done) { cudaGetLastError(); set_error("CUDA graph construction failed"); return DFTATOM_E_CUDA; }
+        } else graph_done = true;
+    }
+    for (int sp = graph_done ? max_steps : 0; sp < max_steps; ++sp) {
+        enqueue_step(sp, launches);
         DFT_CHECK(cudaMemcpyAsync(&c->h_active[sp], b.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
         DFT_CHECK(cudaEventRecord(step_ev[sp], st));
         ++steps_enqueued;

@@ -277,6 +277,7 @@ struct ScfBuffers {
     int run_to_cap;   // != 0: the stop test is recorded in dftatom_step.stop_criterion_met but never ends the SCF
     int adaptive_mixing;  // != 0: per-atom damping is raised when Etotal sloshes with period 2 (scf.cu); 0: the reference's fixed linear mixing
 };
+void launch_scf_loop_condition(cudaGraphConditionalHandle handle, const int* n_active, unsigned long long* iterations, cudaStream_t st);
 void launch_gather_last_steps(const ScfBuffers& b, dftatom_step* out, cudaStream_t st);
 // increment form of the warm-started Poisson solves (scf.cu): dS = r 4 pi K (rho - rho_prev), dU = 0, rho_prev = rho (dS == NULL: only
 // the last); U += dU

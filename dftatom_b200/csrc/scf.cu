@@ -531,6 +531,18 @@ void launch_poisson_delta_apply(const GridDev& g, int n_dens, long long ld, doub
     poisson_delta_apply_kernel<<<dim3((g.N + 255) / 256, n_dens), 256, 0, st>>>(g.N, ld, U, dU, skip, skip_stride_bytes);
 }
 
+// Last node of the body of the SCF loop's CUDA-graph WHILE node: the loop goes on while some atom is still iterating
+// (n_active is kept up to date by potential_energy_kernel)
+__global__ void scf_loop_condition_kernel(cudaGraphConditionalHandle handle, const int* n_active, unsigned long long* iterations)
+{
+    *iterations += 1ULL;
+    cudaGraphSetConditional(handle, *n_active > 0 ? 1u : 0u);
+}
+void launch_scf_loop_condition(cudaGraphConditionalHandle handle, const int* n_active, unsigned long long* iterations, cudaStream_t st)
+{
+    scf_loop_condition_kernel<<<1, 1, 0, st>>>(handle, n_active, iterations);
+}
+
 // last "Step:" record of every atom, compact (what dftatom_solve_batch downloads when the caller did not ask for the steps)
 __global__ void gather_last_steps_kernel(ScfBuffers b, dftatom_step* out)
 {

@@ -126,6 +126,10 @@ const char* dftatom_version(void);
  *                   atom's Etotal sloshes with period 2 (three changes of alternating sign decaying by less than 2x per step - the
  *                   nearly full nodeless 3d / 4f shells: Cu, Zn, Ho..Yb; the reference runs Er, Tm, Yb to its 100-step cap) the weight
  *                   of its old density is raised, alpha <- (1 + alpha) / 2, at most three times.  Lets all 92 atoms of the sweep converge.
+ *   "use_graph"    (default 1) the steady-state SCF step is captured once into the body of a CUDA-graph WHILE node whose condition ("some
+ *                   atom is still iterating") is set on the device (cudaGraphSetConditional): no host round trip between SCF steps.  Not used
+ *                   with "profile" (per-class event timing needs host-side events between the launches), the validation search / match modes
+ *                   and the cooperative team-mode Poisson kernel (one to three atoms on grids above 16385 nodes); 0 = host-driven loop.
  *   "step_cap"     (default 0 = the reference's caps, 100 LDA / 150 LSDA steps) a lower cap on the SCF steps of every atom of the batch
  *   "cluster_poisson" (default 1) warm-started Poisson solves on grids of 2049 .. 16385 nodes run as one thread-block cluster of 8 CTAs per
  *                   density with the whole multigrid hierarchy in distributed shared memory (poisson_cluster.cu); 0 = one CTA per density.
@@ -160,6 +164,9 @@ int dftatom_last_timing(dftatom_ctx* ctx, double* device_ms, long long* kernel_l
 /* bytes the last solve_batch copied host -> device (atom / orbital descriptors; grid tables are cached per context and not counted)
  * and device -> host (per-atom state + step records: every step when `steps` was given, else the last record of every atom) */
 int dftatom_last_transfer(dftatom_ctx* ctx, long long* h2d_bytes, long long* d2h_bytes);
+/* number of SCF steps the last solve_batch ran inside the CUDA-graph WHILE node (set_option "use_graph", default 1: from step "warm_after" on
+ * the whole SCF loop of the batch is ONE graph launch whose loop condition is evaluated on the device; 0 = the host enqueued every step) */
+int dftatom_last_graph_iterations(dftatom_ctx* ctx, long long* iterations);
 
 /* Per-kernel-class profile of the last solve_batch, filled when set_option("profile", 1) was on: device time of
  * every launch of the class (CUDA events on the launching stream), launch count and algorithmic work
