@@ -11,6 +11,7 @@
 #include <mutex>
 #include <numeric>
 #include <thread>
+#include <chrono>
 #include <nvtx3/nvToolsExt.h>
 
 namespace dft {
@@ -75,6 +76,9 @@ struct Knobs {
     int segments(int N) const { return r_segments < 0 ? (N <= 16385 ? 16 : 32) : r_segments; }
     int profile = 0;
     int search_mode = 0;
+    int search_kernel = 0;     // search_mode 0 on the logarithmic grid: 0 = lanes across the radial grid, 4 trial energies per thread, one CTA per orbital
+                               // (numerov_rows.cu, production); 1 = lanes across 32 trial energies, cluster per orbital (numerov_seg.cu / numerov_fast.cu)
+    int rows_cfg = 0x111;      // numerov_rows.cu: energy groups of 4 per round - first ladder of a warm start (bits 0-3), later ladders (4-7), uniform rounds (8-11)
     int match_mode = 0;
     int warm_start = 1;
     int stream_variant = 0;    // window shape of the stream-mode Poisson visits (poisson_stream.cu)
@@ -236,7 +240,7 @@ int dftatom_create(dftatom_ctx** out, int device)
     DFT_CHECK(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device));
     // opt-in dynamic shared memory is per-device state: set it here, for this context's device (not cached process-wide)
     int rc_attr;
-    if ((rc_attr = poisson_init_device()) || (rc_attr = stream_init_device()) || (rc_attr = match_init_device()) || (rc_attr = poisson_cluster_init_device())) { delete c; return rc_attr; }
+    if ((rc_attr = poisson_init_device()) || (rc_attr = stream_init_device()) || (rc_attr = match_init_device()) || (rc_attr = rows_init_device()) || (rc_attr = poisson_cluster_init_device())) { delete c; return rc_attr; }
     DFT_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     DFT_CHECK(cudaMallocHost((void**)&c->h_active, sizeof(int) * 256));
     *out = c;
@@ -275,6 +279,12 @@ int dftatom_set_option(dftatom_ctx* c, const char* key, double value)
     else if (k == "seg_threshold") c->k.seg_threshold = (int)value;
     else if (k == "profile") c->k.profile = value != 0.;
     else if (k == "search_mode") c->k.search_mode = (int)value;
+    else if (k == "search_kernel") c->k.search_kernel = (int)value != 0;
+    else if (k == "rows_cfg") {
+        const int v = (int)value;
+        for (int sft = 0; sft < 12; sft += 4) { const int ng = (v >> sft) & 15; if (ng != 1 && ng != 2 && ng != 4) { set_error("rows_cfg: every field must be 1, 2 or 4"); return DFTATOM_E_ARG; } }
+        c->k.rows_cfg = v & 0xfff;
+    }
     else if (k == "match_mode") c->k.match_mode = (int)value;
     else if (k == "warm_start") c->k.warm_start = value != 0.;
     else if (k == "stream_groups") c->stream_groups = std::min(2, std::max(1, (int)value));
@@ -365,6 +375,10 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
                        int steps_stride)
 {
     if (!c || !opts || !out || n_atoms <= 0) { set_error("bad argument"); return DFTATOM_E_ARG; }
+    const bool host_dbg = getenv("DFTATOM_DEBUG_HOST") != nullptr;      // development aid: wall-clock of the host-side stages
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double th0 = now();
+    double th1 = 0., th2 = 0., th3 = 0., th4 = 0.;
     DFT_CHECK(cudaSetDevice(c->device));
     for (int a = 0; a < n_atoms; ++a) {
         int rc = validate(opts[a]);
@@ -587,6 +601,7 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
     static const char* const kPhase[DFTATOM_K_COUNT] = { "dftatom:search", "dftatom:match", "dftatom:density", "dftatom:poisson", "dftatom:potential" };
     auto begin_phase = [&](int cls) { nvtxRangePushA(kPhase[cls]); begin_span(cls); };
     auto end_phase = [&]() { end_span(); nvtxRangePop(); };
+    th1 = now();
     DFT_CHECK(cudaEventRecord(ev0, st));
     // initial guess -> U -> V   (DFTAtom.cpp:371-392)
     launch_initial_density(g, b, st); ++launches;
@@ -600,7 +615,10 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
     auto enqueue_step = [&](int sp, long long& nl) {
         nvtxRangePushA("dftatom:scf_step");
         begin_phase(DFTATOM_K_SEARCH);
-        if (c->k.search_mode == 0) {
+        if (c->k.search_mode == 0 && c->k.search_kernel == 0 && !g.uniform) {
+            launch_search_rows(g, b.atab, b.atoms, b.orbs, b.astate, b.ss, n_orbs, d_work + DFTATOM_K_SEARCH, c->k.warm_start, c->k.rows_cfg, st);
+            ++nl;
+        } else if (c->k.search_mode == 0) {
             // two shapes of the same search: serial-in-r (one warp per orbital) while many orbitals are active, parallel-in-r
             // (one cluster per orbital) once few are left.  Both are enqueued; the device-side count of active orbitals
             // decides which one runs (the other returns at once), so the host never has to know.
@@ -670,6 +688,7 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
                 ok = cudaStreamEndCapture(st, nullptr) == cudaSuccess;
             } else ok = false;
             ok = ok && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+            th2 = now();
             if (ok) {
                 ok = cudaGraphLaunch(exec, st) == cudaSuccess;
                 graph_done = ok;
@@ -702,6 +721,7 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
     DFT_CHECK(cudaEventRecord(ev1, st));
     DFT_CHECK(cudaStreamSynchronize(st));
     DFT_CHECK(cudaGetLastError());
+    th3 = now();
     float ms = 0.f;
     DFT_CHECK(cudaEventElapsedTime(&ms, ev0, ev1));
     c->last_ms = ms; c->last_launches = launches;
@@ -715,11 +735,21 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
                     hw[28], hw[29], hw[30], hw[31]);
         }
         for (int k = 0; k < DFTATOM_K_COUNT; ++k) { c->prof[k].ms = 0.; c->prof[k].launches = 0; c->prof[k].work = (double)hw[k]; }
+        const bool step_dbg = prof && getenv("DFTATOM_DEBUG_STEPS");          // development aid: per-step time of every kernel class
+        size_t span_i = 0;
         for (Span& s : spans) {
             float t = 0.f;
             cudaEventElapsedTime(&t, s.a, s.b);
+            if (step_dbg) {
+                const size_t sp = span_i / DFTATOM_K_COUNT;
+                if (span_i % DFTATOM_K_COUNT == 0) fprintf(stderr, "step %3zu active %4d |", sp, sp < 256 ? c->h_active[sp] : -1);
+                fprintf(stderr, " %s %.1f us", kPhase[s.cls] + 8, 1e3 * t);
+                if (span_i % DFTATOM_K_COUNT == DFTATOM_K_COUNT - 1) fprintf(stderr, "\n");
+            }
+            ++span_i;
             c->prof[s.cls].ms += t;
-            c->prof[s.cls].launches += (s.cls == DFTATOM_K_SEARCH) ? (c->k.search_mode == 0 ? ((c->segments(N) > 1 && c->k.seg_threshold < n_orbs) ? 2 : 1) : rounds + 1) : 1;
+            const bool rows = c->k.search_mode == 0 && c->k.search_kernel == 0 && !g.uniform;
+            c->prof[s.cls].launches += (s.cls == DFTATOM_K_SEARCH) ? (rows ? 1 : c->k.search_mode == 0 ? ((c->segments(N) > 1 && c->k.seg_threshold < n_orbs) ? 2 : 1) : rounds + 1) : 1;
         }
     }
 
@@ -759,6 +789,9 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
         }
     }
     (void)steps_enqueued;
+    th4 = now();
+    if (host_dbg) fprintf(stderr, "solve_group host stages: setup+uploads %.3f ms | cold steps + graph build %.3f ms | device loop %.3f ms | results %.3f ms | device time %.3f ms\n",
+                          th1 - th0, (th2 > 0. ? th2 : th1) - th1, th3 - (th2 > 0. ? th2 : th1), th4 - th3, c->last_ms);
     return 0;
 }
 
@@ -854,12 +887,12 @@ static int numerov_lanes_impl(dftatom_ctx* c, const double* V, int levels, doubl
     DFT_CHECK(cudaMemcpyAsync(d_lim, nodes_limit, sizeof(int) * n_lanes, cudaMemcpyHostToDevice, st));
     DFT_CHECK(cudaMemcpyAsync(d_E, E, sizeof(double) * n_lanes, cudaMemcpyHostToDevice, st));
     NumerovLaneArgs a{ dA.as<double>(), n_lanes, d_tab, d_l, d_E, d_lim, d_sign, d_log, d_cnt };
-    if (impl == 0) launch_numerov_lanes_fast(g, a, st); else if (impl == 2) launch_numerov_lanes_seg(g, a, c->segments(N) > 1 ? c->segments(N) : 32, st); else if (impl == 3) launch_numerov_lanes_outward(g, a, st); else launch_numerov_lanes(g, a, st);
+    if (impl >= 4 && impl <= 6) launch_numerov_lanes_rows(g, a, 1 << (impl - 4), st); else if (impl == 0) launch_numerov_lanes_fast(g, a, st); else if (impl == 2) launch_numerov_lanes_seg(g, a, c->segments(N) > 1 ? c->segments(N) : 32, st); else if (impl == 3) launch_numerov_lanes_outward(g, a, st); else launch_numerov_lanes(g, a, st);
     if (reps > 0) {          // microbench: the same launch `reps` more times between CUDA events (tables and lanes resident)
         cudaEvent_t e0, e1;
         DFT_CHECK(cudaEventCreate(&e0)); DFT_CHECK(cudaEventCreate(&e1));
         DFT_CHECK(cudaEventRecord(e0, st));
-        for (int r = 0; r < reps; ++r) { if (impl == 0) launch_numerov_lanes_fast(g, a, st); else if (impl == 2) launch_numerov_lanes_seg(g, a, c->segments(N) > 1 ? c->segments(N) : 32, st); else if (impl == 3) launch_numerov_lanes_outward(g, a, st); else launch_numerov_lanes(g, a, st); }
+        for (int r = 0; r < reps; ++r) { if (impl >= 4 && impl <= 6) launch_numerov_lanes_rows(g, a, 1 << (impl - 4), st); else if (impl == 0) launch_numerov_lanes_fast(g, a, st); else if (impl == 2) launch_numerov_lanes_seg(g, a, c->segments(N) > 1 ? c->segments(N) : 32, st); else if (impl == 3) launch_numerov_lanes_outward(g, a, st); else launch_numerov_lanes(g, a, st); }
         DFT_CHECK(cudaEventRecord(e1, st));
         DFT_CHECK(cudaStreamSynchronize(st));
         float ms = 0.f;
@@ -942,7 +975,8 @@ int dftatom_level_search(dftatom_ctx* c, const double* V, int levels, double del
     if ((rc = setup_single(c, g, V, Z, orbs, &da, &ds, &dorb, &dss, &datab))) return rc;
     launch_search_init(g, da, ds, dorb, dss, n_levels, st);
     const int rounds = search_rounds_needed(Z);
-    if (c->k.search_mode == 0 && c->segments(g.N) > 1) launch_search_seg(g, datab, da, dorb, ds, dss, n_levels, nullptr, c->segments(g.N), nullptr, 0, 0, st);
+    if (c->k.search_mode == 0 && c->k.search_kernel == 0 && !g.uniform) launch_search_rows(g, datab, da, dorb, ds, dss, n_levels, nullptr, 0, c->k.rows_cfg, st);
+    else if (c->k.search_mode == 0 && c->segments(g.N) > 1) launch_search_seg(g, datab, da, dorb, ds, dss, n_levels, nullptr, c->segments(g.N), nullptr, 0, 0, st);
     else if (c->k.search_mode == 0) launch_search_fused(g, datab, da, dorb, ds, dss, n_levels, nullptr, nullptr, 0, 0, st);
     else for (int r = 0; r < rounds; ++r) launch_search_round(g, datab, dorb, ds, dss, n_levels, nullptr, st);
     std::vector<SearchState> h(n_levels);

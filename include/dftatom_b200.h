@@ -190,7 +190,9 @@ int dftatom_measure_fp64_peak(dftatom_ctx* ctx, double* tflops);
  * impl = 2: the same count through the parallel-in-r sweep (one thread-block cluster per 32 lanes, warp = radial segment,
  *           set_option("r_segments") segments).
  * impl = 3: count[k] = SolveSchrodingerCountNodesFromNucleus (Numerov.h:204-270: the OUTWARD sweep from the nucleus with its early exits -
- *           overflow, count > nodes_limit, outer classical turning point; public in the reference but without a caller); y0_* are 0. */
+ *           overflow, count > nodes_limit, outer classical turning point; public in the reference but without a caller); y0_* are 0.
+ * impl = 4, 5, 6: the count of impl 0 through the production sweep of the SCF search (numerov_rows.cu: lanes across the radial grid, every
+ *           thread 4 trial energies x 2 basis chains): 4 energies on 128 radial segments, 8 on 64, 16 on 32 per CTA (logarithmic grid only). */
 int dftatom_numerov_lanes(dftatom_ctx* ctx, const double* V, int levels, double delta, double max_r, int n_lanes,
                           const int* l, const double* E, const int* nodes_limit, int impl,
                           int* y0_sign, double* y0_log2, int* count);

@@ -48,6 +48,12 @@ def test_numerov_lanes_match_oracle(ctx, kind, L, delta, rmax, Z):
             assert np.array_equal(cnt, O.numerov_count_all(V, delta, rmax, ls, Es))
     finally:
         ctx.set_option("r_segments", -1)
+    # the production sweep (numerov_rows.cu): lanes across the radial grid, 4 / 8 / 16 trial energies per round on 128 / 64 / 32 segments
+    for impl in (4, 5, 6):
+        sign, lg, cnt = ctx.numerov_lanes(V, L, delta, rmax, ls, Es, lim, impl=impl)
+        assert np.array_equal(sign, (y0 > 0).astype(np.int32)), impl
+        np.testing.assert_allclose(lg, np.log2(np.abs(y0)), atol=1e-6)
+        assert np.array_equal(cnt, O.numerov_count_all(V, delta, rmax, ls, Es)), impl
 
 
 def test_numerov_known_answer_hydrogenic(ctx):
@@ -79,10 +85,13 @@ def test_level_search_matches_oracle(ctx, kind, L, delta, rmax, Z):
     # search_mode 0: Sturm-count search with interpolated ladders (production) in its two shapes - serial in r (one warp
     # per orbital, r_segments <= 1) and parallel in r (one cluster per orbital, 8 / 32 radial segments);
     # search_mode 1: reference-shaped three-stage search
-    for mode, segs in ((0, 0), (0, 8), (0, 32), (1, 0)):
+    # search_kernel 0 (production): lanes across the radial grid, 4 trial energies per thread (numerov_rows.cu); 1: lanes across 32 energies
+    for kern, mode, segs in ((0, 0, -1), (1, 0, 0), (1, 0, 8), (1, 0, 32), (0, 1, 0)):
+        ctx.set_option("search_kernel", kern)
         ctx.set_option("search_mode", mode)
         ctx.set_option("r_segments", segs)
         E_g, ok_g = ctx.level_search(V, L, delta, rmax, Z, ns, ls)
+        ctx.set_option("search_kernel", 0)
         ctx.set_option("search_mode", 0)
         ctx.set_option("r_segments", -1)
         np.testing.assert_allclose(E_g, E_o, rtol=0, atol=5e-9)
