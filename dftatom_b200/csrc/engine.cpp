@@ -88,6 +88,8 @@ struct Knobs {
     int stream_min_levels = 15; // stream mode from this many levels on (at 14 levels one CTA per density is as fast: measured 57.6 against 58.5 ms on C3)
     int poisson_exact = 0;     // 1: bit-reproducible Poisson solve (poisson_exact.cu): the reference's FullCycle in its own operation order, 100 V-cycles
     int run_to_cap = 0;        // 1: the stop test (DFTAtom.cpp:474) is evaluated and recorded but never ends the SCF (trajectory parity beyond the stop step)
+    int warm_poisson = 1;      // warm-started solves in increment form on 2049 .. 16385 nodes: one CTA per density, visits in registers (poisson_warm.cu); 0 = cluster / one-CTA kernels below
+    int warm_until_step = 32;  // ... up to this SCF step; from it on the cluster kernel (0: the one-CTA kernel at every step)
     int cluster_poisson = 1;   // warm-started solves on 2049 .. 16385 nodes: one cluster of 8 CTAs per density (poisson_cluster.cu); 0 = one CTA per density
     int cluster_max_dens = 1 << 30; // ... while at most this many atoms are still iterating.  Default: always - which kernel solves a density must not depend on
                                // what else is in the batch (an atom's records are bit-identical alone, in any batch and on any shard); a smaller
@@ -240,7 +242,7 @@ int dftatom_create(dftatom_ctx** out, int device)
     DFT_CHECK(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device));
     // opt-in dynamic shared memory is per-device state: set it here, for this context's device (not cached process-wide)
     int rc_attr;
-    if ((rc_attr = poisson_init_device()) || (rc_attr = stream_init_device()) || (rc_attr = match_init_device()) || (rc_attr = rows_init_device()) || (rc_attr = poisson_cluster_init_device())) { delete c; return rc_attr; }
+    if ((rc_attr = poisson_init_device()) || (rc_attr = stream_init_device()) || (rc_attr = match_init_device()) || (rc_attr = rows_init_device()) || (rc_attr = poisson_warm_init_device()) || (rc_attr = poisson_cluster_init_device())) { delete c; return rc_attr; }
     DFT_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     DFT_CHECK(cudaMallocHost((void**)&c->h_active, sizeof(int) * 256));
     *out = c;
@@ -295,6 +297,8 @@ int dftatom_set_option(dftatom_ctx* c, const char* key, double value)
     else if (k == "stream_variant") c->k.stream_variant = std::min(2, std::max(0, (int)value));
     else if (k == "poisson_exact") c->k.poisson_exact = value != 0.;
     else if (k == "cluster_poisson") c->k.cluster_poisson = value != 0.;
+    else if (k == "warm_poisson") c->k.warm_poisson = value != 0.;
+    else if (k == "warm_until_step") c->k.warm_until_step = std::max(0, (int)value);
     else if (k == "cluster_max_dens") c->k.cluster_max_dens = std::max(0, (int)value);
     else if (k == "delta_poisson") c->k.delta_poisson = value != 0.;
     else if (k == "adaptive_mixing") c->k.adaptive_mixing = value != 0.;
@@ -513,11 +517,26 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
     double* d_src = c->d_src.as<double>();
     double* d_u = c->d_u.as<double>();
     const int* skip_p = &b.astate[0].done; const int skip_stride = (int)sizeof(AtomState);
+    const bool warm_ok = c->k.warm_poisson && delta && !stream && poisson_warm_supported(g.L, g.delta) && g.coarse_op && (long long)lv.total >= poisson_warm_scratch_doubles(g.L);
     auto poisson_solve = [&](int warm_vcycles, long long& n_launch) {
         const bool warm = warm_vcycles > 0;
         if (exact) {
             launch_poisson_exact(xa, st);
             ++n_launch;
+        } else if (warm && warm_ok) {
+            // one SM per density while most atoms are still iterating (throughput), the 8-SM cluster per density afterwards (latency): shared by
+            // SCF step index, both launched every step, the density's own step counter decides which one solves it
+            const bool both = cluster_ok && c->k.warm_until_step > 0;
+            ca.n_vcycles = warm_vcycles; ca.work = pa.work; ca.rho_prev = rho_prev;
+            ca.step = both ? &b.astate[0].n_steps : nullptr; ca.step_min = 0; ca.step_max = c->k.warm_until_step;
+            launch_poisson_warm(g, ca, pa.phi, pa.src, lv.total, st);
+            ++n_launch;
+            if (both) {
+                ca.step_min = c->k.warm_until_step; ca.step_max = 1 << 30;
+                { long long* keep = ca.dbg; ca.dbg = nullptr; launch_poisson_cluster(g, ca, st); ca.dbg = keep; }
+                ++n_launch;
+            }
+            ca.step = nullptr;
         } else if (warm && cluster_ok && act_est <= c->k.cluster_max_dens) {
             ca.n_vcycles = warm_vcycles; ca.work = pa.work; ca.rho_prev = delta ? rho_prev : nullptr;
             if (getenv("DFTATOM_DEBUG_CLUSTER") && n_launch > 40 && !ca.dbg) {       // development aid: cycle counters of one solve

@@ -239,6 +239,9 @@ struct ClusterPoissonArgs {
     const int* Zbc;                             // [n_dens] boundary value at Rmax
     const double* coarse_op;                    // GridDev.coarse_op
     const int* skip; int skip_stride_bytes;
+    const int* step; int step_min, step_max;    // optional: the density's SCF step counter (AtomState.n_steps, stride = skip_stride_bytes): it is solved by this launch
+                                                // only while step_min <= *step < step_max - two kernels that share the warm solves of one SCF by step index
+                                                // (a property of the atom alone: the records stay independent of what else is in the batch)
     int n_vcycles;
     unsigned long long* work;                   // optional: += Gauss-Seidel node-updates
     int smem_doubles;                           // set by the launcher
@@ -247,6 +250,13 @@ struct ClusterPoissonArgs {
 bool poisson_cluster_supported(int L, double delta);
 void launch_poisson_cluster(const GridDev& g, const ClusterPoissonArgs& a, cudaStream_t st);
 int poisson_cluster_init_device();
+
+// Poisson, warm solves in increment form on one SM per density (poisson_warm.cu): the arguments of the cluster mode with rho_prev given;
+// gphi / gsrc: scratch of n_dens x gstride doubles each (gstride >= poisson_warm_scratch_doubles(L)), contents irrelevant before and after
+bool poisson_warm_supported(int L, double delta);
+long long poisson_warm_scratch_doubles(int L);
+void launch_poisson_warm(const GridDev& g, const ClusterPoissonArgs& a, double* gphi, double* gsrc, long long gstride, cudaStream_t st);
+int poisson_warm_init_device();
 
 // per-device kernel attributes (opt-in dynamic shared memory): called once per context from dftatom_create under cudaSetDevice
 int poisson_init_device();

@@ -492,6 +492,10 @@ __global__ void __cluster_dims__(kCL, 1, 1) __launch_bounds__(kCT, 2) poisson_cl
     const int rank = (int)cluster.block_rank();
     const int k = blockIdx.x / kCL;
     if (a.skip && *reinterpret_cast<const int*>(reinterpret_cast<const char*>(a.skip) + (size_t)k * a.skip_stride_bytes)) return;   // uniform over the cluster
+    if (a.step) {
+        const int sc = *reinterpret_cast<const int*>(reinterpret_cast<const char*>(a.step) + (size_t)k * a.skip_stride_bytes);
+        if (sc < a.step_min || sc >= a.step_max) return;
+    }
     const int L = g.L, N = g.N, t = threadIdx.x;
     if (t < L && t < 16) {
         // level table (thread l fills level l): distributed levels (>= 2048 nodes), then CTA 0's local ones; every thread walks the
