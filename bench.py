@@ -24,6 +24,7 @@ sys.path.insert(0, ROOT)
 C3 = dict(levels=14, delta=0.0005, mixing=0.5, rmax=25.0, method=0)
 WORKLOAD = "C3 periodic-table sweep Z=1-92 LDA, 14 levels (16385 nodes), delta 0.0005, mixing 0.5, Rmax 25"
 FLOP_PER_NODE_STEP = 11.0          # SURVEY §8(d) accounting convention for the Numerov shooting kernel
+SEARCH_TRAFFIC_BYTES = None        # DRAM bytes of one search_rows_kernel launch at full load, from the ncu capture under profiles/ (None: not captured yet)
 REF_EXE = os.path.join(ROOT, "oracle", "_ref", "dftatom_ref")
 ORACLE_EXE = os.path.join(ROOT, "oracle", "dftatom_oracle")
 
@@ -355,17 +356,18 @@ def run_cuda_arm(a):
             scf_loop=dict(mode="CUDA-graph while node, loop condition set on the device (cudaGraphSetConditional)" if graph_iters else "host-driven loop",
                           scf_steps_inside_graph=int(graph_iters), device_ms_per_sweep=dev_ms / a.steps,
                           device_ms_per_sweep_profiled_host_loop=prof_dev_ms / a.steps),
-            roofline=dict(kernel="search_seg_kernel (Numerov shooting: Sturm-count search, parallel in r: cluster of 4 CTAs per orbital, warp = radial segment, lane = trial energy)",
+            roofline=dict(kernel="search_rows_kernel (Numerov shooting: Sturm-count search; one CTA per orbital, lane = radial segment (128 per orbital), every thread "
+                                 "4 trial energies x 2 basis chains: 11 FP64 instructions per credited (trial energy, node) = 11 FLOP -> ceiling 0.5 of the FMA peak)",
                           bound="fp64", achieved=achieved, peak=peak, unit="TFLOP/s",
-                          frac=achieved / peak if peak else None, traffic=12.52e6,
-                          traffic_source="dram__bytes_read + write of one search_seg_kernel launch with all 916 orbitals active, ncu --set full "
-                                         "(profiles/r01_ncu_search_seg.txt): the kernel is FP64-bound, its tables stay in L2",
+                          frac=achieved / peak if peak else None, traffic=SEARCH_TRAFFIC_BYTES,
+                          traffic_source="dram__bytes_read + write of one search_rows_kernel launch with all 916 orbitals active, ncu --set full "
+                                         "(profiles/r02_ncu_search_rows.txt): the kernel is FP64-bound, its tables stay in L2",
                           peak_source="measured live: DFMA microbench in libdftatom_b200 (MEASURED_PEAKS.json has no FP64 entry)",
                           flop_per_lane_node_step=FLOP_PER_NODE_STEP, lane_node_steps=s["work"], kernel_ms=s["ms"], share_of_step=shares,
                           timing="CUDA events around every kernel class over `steps` profiled sweeps run back to back with the timed ones (see scf_loop)"),
             kernels={k: dict(ms=v["ms"], launches=int(v["launches"]), work=v["work"]) for k, v in prof.items()},
             search=dict(orbital_solves=prof["match"]["work"], rounds_per_solve=prof["density"]["work"] / max(1.0, prof["match"]["work"]),
-                        inward_sweeps_per_solve_reference=140, note="one round = 32 concurrent inward sweeps"),
+                        inward_sweeps_per_solve_reference=140, note="one round = 4 concurrent inward sweeps (trial energies), 128 radial segments each"),
             poisson=dict(poisson_record(prof, len(opts), a.steps), share_of_step=shares["poisson"]),
             clocks=clocks,
         )
@@ -495,13 +497,15 @@ def poisson_record(prof, n_atoms, steps):
     p = prof["poisson"]
     N = (1 << C3["levels"]) + 1
     ups = p["work"] / (p["ms"] * 1e-3) if p["ms"] else None
-    return dict(kernel="poisson_cluster_kernel (warm V-cycles: one cluster of 8 CTAs per density, hierarchy in distributed shared memory) + "
+    return dict(kernel="poisson_warm_kernel (warm V-cycles in increment form, SCF steps 4-31: one CTA per density, level visits in registers) + "
+                       "poisson_cluster_kernel (the same from step 32 on: one cluster of 8 CTAs per density, hierarchy in distributed shared memory) + "
                        "poisson_full_kernel (cold full-multigrid solves of the first 4 SCF steps)",
                 launches=int(p["launches"]), gs_node_updates=p["work"], ms=p["ms"], gs_updates_per_s=ups,
                 vcycles_per_s=(ups / (12.0 * N)) if ups else None, share_of_step=None,
-                bound="shared-memory / DSMEM latency and the FP64 pipes of the SMs that hold the hierarchy (compulsory HBM traffic 24 N B per warm solve)",
+                bound="latency of ~380 dependent Gauss-Seidel sweeps per solve (shared memory, shuffles, one block / cluster barrier per sweep) on the SMs that "
+                      "hold the hierarchy (compulsory HBM traffic 24 N B per warm solve)",
                 fp64_flops_per_update=3 * 2, achieved_tflops=(ups * 6 / 1e12) if ups else None,
-                ncu="profiles/r02_ncu_poisson_cluster.txt (shared-memory wavefronts, FP64 pipe, DRAM bytes per launch)")
+                ncu="profiles/r02_ncu_poisson_warm.txt, profiles/r02_ncu_poisson_cluster.txt (shared-memory wavefronts, FP64 pipe, issue slots, DRAM bytes per launch)")
 
 
 def parity_block(ctx, D):
@@ -681,7 +685,8 @@ def micro_c5b(ctx, fp64_peak_tflops, reps=20, cpu_baseline=True):
     # two shapes of the same sweep: serial in r (one warp = 32 energies walks the whole grid) and parallel in r (one cluster
     # of 4 CTAs per 32 energies, warp = one of 16 radial segments; the Sturm count comes from the segments' transfer matrices alone)
     kernels = {}
-    for name, impl in (("serial_in_r", 0), ("parallel_in_r", 2)):
+    # rows (production search sweep): lanes across the radial grid, 4 / 16 energies per CTA on 128 / 32 segments
+    for name, impl in (("serial_in_r", 0), ("parallel_in_r", 2), ("rows_4x128", 4), ("rows_16x32", 6)):
         ctx.set_option("r_segments", 16 if impl == 2 else -1)          # 16 segments (clusters of 4 CTAs) measured best for these lanes
         try:
             sign, lg, cnt, ms, steps = ctx.numerov_lanes_timed(V, levels, delta, rmax, ls, Es, lim, impl=impl, reps=reps)
@@ -701,11 +706,13 @@ def micro_c5b(ctx, fp64_peak_tflops, reps=20, cpu_baseline=True):
     tf = kernels[best]["achieved_tflops"]
     out = dict(workload="C5b Numerov shooting, 4096 (orbital, trial-energy) lanes, Z=86 Coulomb well, 131073 nodes",
                lane_node_steps=steps, kernels=kernels, known_answer_ok=all(k_["known_answer_ok"] for k_ in kernels.values()),
-               roofline=dict(kernel={"serial_in_r": "numerov_lanes_fast_kernel", "parallel_in_r": "numerov_lanes_seg_kernel"}[best] + f" ({best})",
+               roofline=dict(kernel={"serial_in_r": "numerov_lanes_fast_kernel", "parallel_in_r": "numerov_lanes_seg_kernel", "rows_4x128": "numerov_lanes_rows_kernel",
+                                     "rows_16x32": "numerov_lanes_rows_kernel"}[best] + f" ({best})",
                              bound="fp64", achieved=tf, peak=fp64_peak_tflops, unit="TFLOP/s",
                              frac=tf / fp64_peak_tflops if fp64_peak_tflops else None, traffic=None, flop_per_lane_node_step=11.0,
                              note="credited 11 FLOP per (lane, node-step) whatever the kernel executes (SURVEY 8d); 4096 lanes are 128 warps "
-                                  "for 148 SMs x 4 FP64 pipes, so the serial sweep cannot fill the machine; the parallel-in-r one executes 11 FP64 instructions per (lane, node) for the two basis chains"))
+                                  "for 148 SMs x 4 FP64 pipes, so the serial sweep cannot fill the machine; the parallel-in-r and rows kernels execute 11 FP64 "
+                                  "instructions per (lane, node) for the two basis chains of a segment's transfer matrix: their ceiling is 0.5 of the FMA peak"))
     if cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_lib as O

@@ -89,6 +89,8 @@ struct Knobs {
     int poisson_exact = 0;     // 1: bit-reproducible Poisson solve (poisson_exact.cu): the reference's FullCycle in its own operation order, 100 V-cycles
     int run_to_cap = 0;        // 1: the stop test (DFTAtom.cpp:474) is evaluated and recorded but never ends the SCF (trajectory parity beyond the stop step)
     int warm_poisson = 1;      // warm-started solves in increment form on 2049 .. 16385 nodes: one CTA per density, visits in registers (poisson_warm.cu); 0 = cluster / one-CTA kernels below
+    int coarse_exact = 1;      // warm solves: the levels below 2048 nodes are replaced by the exact solve of the 1024-node level (poisson_tri.cuh); 0 = visited
+                               // with 3 + 3 sweeps each like the reference does
     int warm_until_step = 32;  // ... up to this SCF step; from it on the cluster kernel (0: the one-CTA kernel at every step)
     int cluster_poisson = 1;   // warm-started solves on 2049 .. 16385 nodes: one cluster of 8 CTAs per density (poisson_cluster.cu); 0 = one CTA per density
     int cluster_max_dens = 1 << 30; // ... while at most this many atoms are still iterating.  Default: always - which kernel solves a density must not depend on
@@ -179,7 +181,7 @@ static int get_grid(dftatom_ctx* c, int L, double delta, double max_r, GridDev**
         }
     }
     GridEntry& e = c->grids[key];
-    int rc = e.mem.ensure((h.size() + 32 * 32) * sizeof(double));
+    int rc = e.mem.ensure((h.size() + 32 * 32 + 3 * 1024) * sizeof(double));
     if (rc) { c->grids.erase(key); return rc; }
     DFT_CHECK(cudaMemcpyAsync(e.mem.p, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     DFT_CHECK(cudaStreamSynchronize(c->stream));
@@ -189,10 +191,14 @@ static int get_grid(dftatom_ctx* c, int L, double delta, double max_r, GridDev**
     e.dev.r = d; e.dev.ex = d + (size_t)N; e.dev.sqex = d + (size_t)2 * N; e.dev.b12 = d + (size_t)3 * N;
     e.dev.c6 = d + (size_t)4 * N; e.dev.k2 = d + (size_t)5 * N; e.dev.wjac = d + (size_t)6 * N;
     e.dev.psrc = d + (size_t)7 * N; e.dev.inv4pr2 = d + (size_t)8 * N; e.dev.pex = d + (size_t)9 * N;
-    e.dev.coarse_op = nullptr;
+    e.dev.coarse_op = nullptr; e.dev.coarse_tri = nullptr;
     if (L >= 6) {
         e.dev.coarse_op = d + (size_t)n_tab * N;
         launch_coarse_op(L, delta, e.dev.coarse_op, c->stream);
+        if (L >= 11 && L <= 14) {
+            e.dev.coarse_tri = d + (size_t)n_tab * N + 32 * 32;
+            launch_coarse_tri(L, delta, e.dev.coarse_tri, c->stream);
+        }
         DFT_CHECK(cudaStreamSynchronize(c->stream));
     }
     *out = &e.dev;
@@ -298,6 +304,7 @@ int dftatom_set_option(dftatom_ctx* c, const char* key, double value)
     else if (k == "poisson_exact") c->k.poisson_exact = value != 0.;
     else if (k == "cluster_poisson") c->k.cluster_poisson = value != 0.;
     else if (k == "warm_poisson") c->k.warm_poisson = value != 0.;
+    else if (k == "coarse_exact") c->k.coarse_exact = value != 0.;
     else if (k == "warm_until_step") c->k.warm_until_step = std::max(0, (int)value);
     else if (k == "cluster_max_dens") c->k.cluster_max_dens = std::max(0, (int)value);
     else if (k == "delta_poisson") c->k.delta_poisson = value != 0.;
@@ -506,6 +513,7 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
     const bool cluster_ok = c->k.cluster_poisson && !exact && !stream && poisson_cluster_supported(g.L, g.delta) && g.coarse_op && c->k.refine_vcycles == 0 && !c->k.floor_stop;
     ClusterPoissonArgs ca{};
     ca.n_dens = n_atoms; ca.rho = b.rhot; ca.rho_stride = N; ca.U = b.U; ca.ldU = ldU; ca.Zbc = b.Zbc; ca.coarse_op = g.coarse_op;
+    ca.coarse_tri = c->k.coarse_exact ? g.coarse_tri : nullptr;
     ca.skip = &b.astate[0].done; ca.skip_stride_bytes = (int)sizeof(AtomState);
     StreamSolveArgs sa{};
     sa.n_dens = n_atoms; sa.rho = b.rhot; sa.rho_stride = N; sa.psrc = g.psrc; sa.src0 = c->stream_src0.as<double>(); sa.U = b.U; sa.ld0 = ldU;

@@ -40,6 +40,7 @@ struct GridDev {
     double* inv4pr2; // 1 / (4π r_i^2) (0 at i=0)                    (DFTAtom.cpp:340)
     double* pex;     // 4π Rp²δ² · e^{2δ i} in the reference's own product order (PoissonSolver.h:66-74; uniform grid: h² 4π, :26-40): poisson_exact.cu
     double* coarse_op; // [32*32] dense operator of the Poisson sub-cycle below the 32-node level (poisson.cu), NULL for L < 6
+    double* coarse_tri; // table of the exact solve of the 1024-node level (poisson_tri.cuh), NULL unless 11 <= L <= 14
 };
 
 // One orbital = one (atom, spin, n, l) level; also the unit of the batched energy search.
@@ -238,6 +239,8 @@ struct ClusterPoissonArgs {
     double* U; long long ldU;                   // [n_dens][ldU] in: previous solution (initial guess), out: U(r)
     const int* Zbc;                             // [n_dens] boundary value at Rmax
     const double* coarse_op;                    // GridDev.coarse_op
+    const double* coarse_tri;                   // GridDev.coarse_tri or NULL.  Given: the levels below 2048 nodes are replaced by the exact solve of the
+                                                // 1024-node level (poisson_tri.cuh); NULL: they are visited like the reference does, down to the dense operator
     const int* skip; int skip_stride_bytes;
     const int* step; int step_min, step_max;    // optional: the density's SCF step counter (AtomState.n_steps, stride = skip_stride_bytes): it is solved by this launch
                                                 // only while step_min <= *step < step_max - two kernels that share the warm solves of one SCF by step index
@@ -257,6 +260,7 @@ bool poisson_warm_supported(int L, double delta);
 long long poisson_warm_scratch_doubles(int L);
 void launch_poisson_warm(const GridDev& g, const ClusterPoissonArgs& a, double* gphi, double* gsrc, long long gstride, cudaStream_t st);
 int poisson_warm_init_device();
+void launch_coarse_tri(int L, double delta, double* T, cudaStream_t st);
 
 // per-device kernel attributes (opt-in dynamic shared memory): called once per context from dftatom_create under cudaSetDevice
 int poisson_init_device();

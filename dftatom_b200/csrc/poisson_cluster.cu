@@ -21,6 +21,7 @@
 //  * the levels with <= 1024 nodes belong to CTA 0: 1024 nodes by the whole CTA, 512 .. 64 by warp 0 alone (no block barrier),
 //    the sub-cycle below the 32-node level is the precomputed dense operator of the grid (coarse_op_kernel).
 #include "internal.h"
+#include "poisson_tri.cuh"
 #include <cooperative_groups.h>
 #include <algorithm>
 #include <cmath>
@@ -456,17 +457,28 @@ __device__ __forceinline__ void warp_visit(int l, int flags, int sweeps)
 }
 
 // the levels of CTA 0 between the last distributed down-visit and the first distributed up-visit
-__device__ __noinline__ void local_subcycle(const double* G)
+__device__ __noinline__ void local_subcycle(const double* G, bool tri)
 {
     const int lb = cs.lb, md = cs.md;
-    visit_block_local(lb, kCRestrict, 3);
-    if (threadIdx.x < 32) {
-        for (int l = lb + 1; l < md; ++l) warp_visit(l, kCRestrict, 3);
-        dense_apply(G);
-        for (int l = md - 1; l > lb; --l) warp_visit(l, kCLoad | kCProlong, 3);
+    if (tri) {
+        // exact solve of the 1024-node level by warp 0 (poisson_tri.cuh; G = its table) in place of the sub-cycle below
+        if (threadIdx.x < 32) {
+            const CLevel& c = cs.lv[lb];
+            const double* S = c_dyn + c.offS;
+            double* P = c_dyn + c.offP;
+            tri_solve_warp(G, c.a, c.b, [&](int i) { return 0.5 * S[slot_local(kTriN, i)]; }, [&](int i, double v) { P[slot_local(kTriN, i)] = v; });
+        }
+        __syncthreads();
+    } else {
+        visit_block_local(lb, kCRestrict, 3);
+        if (threadIdx.x < 32) {
+            for (int l = lb + 1; l < md; ++l) warp_visit(l, kCRestrict, 3);
+            dense_apply(G);
+            for (int l = md - 1; l > lb; --l) warp_visit(l, kCLoad | kCProlong, 3);
+        }
+        __syncthreads();
+        visit_block_local(lb, kCLoad | kCProlong, 3);
     }
-    __syncthreads();
-    visit_block_local(lb, kCLoad | kCProlong, 3);
     // every CTA gets its share (+ halos) of Phi_lb for the prolongation into the last distributed level: remote stores into its copy
     {
         cg::cluster_group cluster = cg::this_cluster();
@@ -522,7 +534,7 @@ __global__ void __cluster_dims__(kCL, 1, 1) __launch_bounds__(kCT, 2) poisson_cl
         int nd = 0;
         for (int l = 0; l < L; ++l) if ((1 << (L - l)) >= kCL * kCT) ++nd;
         cs.L = L; cs.n_dist = nd; cs.lb = L - 10; cs.md = L - 5;
-        cs.offCb = a.smem_doubles - 32 * 32 - (kHB + 128 + kHR);
+        cs.offCb = a.smem_doubles - kTriTableDoubles - (kHB + 128 + kHR);
         cs.right_bc = (a.Zbc && !a.rho_prev) ? (double)a.Zbc[k] : 0.;      // increment form: dU vanishes on both boundaries
         cs.updates = 0;
         cs.dbg_on = a.dbg != nullptr && k == 0;
@@ -530,8 +542,12 @@ __global__ void __cluster_dims__(kCL, 1, 1) __launch_bounds__(kCT, 2) poisson_cl
     }
     const long long t_begin = clock64();
     __syncthreads();
-    double* G = c_dyn + a.smem_doubles - 32 * 32;
-    if (rank == 0) for (int i = t; i < 32 * 32; i += kCT) G[i] = a.coarse_op[i];
+    double* G = c_dyn + a.smem_doubles - kTriTableDoubles;      // the dense operator (32 x 32) or the table of the exact solve
+    const bool tri = a.coarse_tri != nullptr;
+    if (rank == 0) {
+        if (tri) { for (int i = t; i < kTriTableDoubles; i += kCT) G[i] = a.coarse_tri[i]; }
+        else { for (int i = t; i < 32 * 32; i += kCT) G[i] = a.coarse_op[i]; }
+    }
     // import: Source_0 = r 4 pi K rho (PoissonSolver.h:55-74) and Phi_0 (the previous U, or zero in increment form) - every CTA its slab
     // AND its halos, straight from global memory
     {
@@ -571,7 +587,7 @@ __global__ void __cluster_dims__(kCL, 1, 1) __launch_bounds__(kCT, 2) poisson_cl
         const long long tl0 = clock64();
         cluster.barrier_wait();
         const long long tl1 = clock64();
-        if (rank == 0) local_subcycle(G);
+        if (rank == 0) local_subcycle(G, tri);
         cluster.barrier_arrive();
         if (t == 0 && cs.dbg_on) { cs.dbg[1] += clock64() - tl1; cs.dbg[7] += tl1 - tl0; }
         // up-leg
@@ -604,7 +620,7 @@ static int cluster_smem_doubles(int L)
         if (n >= kCL * kCT) off += 2 * (kHB + n / kCL + kHR);
         else if (n >= 32) off += 2 * (n + 4);
     }
-    return off + (kHB + 128 + kHR) + 32 * 32;
+    return off + (kHB + 128 + kHR) + kTriTableDoubles;
 }
 
 bool poisson_cluster_supported(int L, double delta)

@@ -20,6 +20,7 @@
 //    for the owner and for the coalesced import / export), Phi_0 and the two levels of 8192 / 4096 nodes in this density's block of the
 //    L2-resident hierarchy buffers (owner-major, coalesced): ~0.9 MB of L2 traffic per V-cycle and density.
 #include "internal.h"
+#include "poisson_tri.cuh"
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -47,7 +48,9 @@ struct WLevel {
 
 struct WShared {
     WLevel lv[12];
-    int m;                  // the dense level (32 owned nodes)
+    int m;                  // the dense level (32 owned nodes), or - exact coarse solve - the 1024-node level
+    int tri;                // 1: the levels below 2048 nodes are replaced by the exact solve of the 1024-node level (poisson_tri.cuh)
+    int offT;               // its table in w_dyn
     double* gphi; double* gsrc;     // this density's blocks of the global hierarchy buffers
     double* U;
     double edge[2][kWT / 32 + 1];   // old first node of every warp, by sweep parity
@@ -163,7 +166,9 @@ __device__ __forceinline__ void w_sweeps(double (&phi)[NPT], const double (&hs)[
 // One level visit.  Template: nodes per owner; PG / SG: Phi / Source of THIS level in the global blocks (else shared memory); CG: both arrays
 // of the NEXT (coarser) level in the global blocks.  NPT >= 2: the coarse nodes of an owner's fine nodes are its own (same owner index);
 // NPT == 1: coarse node i is owned by thread i, the transfers go through shared memory.
-template <int NPT, bool PG, bool SG, bool CG>
+__device__ __forceinline__ int w_tri_addr(int i) { return (i >> 5) * 33 + (i & 31); }       // layout of the exactly solved level: lane-major rows of 33
+
+template <int NPT, bool PG, bool SG, bool CG, bool CT = false>
 __device__ __noinline__ void w_visit(int l, int flags, int sweeps)
 {
     const unsigned full = 0xffffffffu;
@@ -203,11 +208,12 @@ __device__ __noinline__ void w_visit(int l, int flags, int sweeps)
         if (NPT >= 2) {
             // coarse nodes o NC .. o NC + NC: the owner's own and the first one of the next owner (the right boundary, 0, behind the last owner)
             const int strideC = cc.strideP;
-            double cprev = Cb[o];
+            double cprev = CT ? Cb[w_tri_addr(o * NC)] : Cb[o];
             phi[0] += cprev;
 #pragma unroll
             for (int j = 1; j <= NC; ++j) {
-                const double cj = j < NC ? Cb[j * strideC + o] : ((o + 1 < owners) ? Cb[o + 1] : 0.);
+                const double cj = CT ? ((j < NC || o + 1 < owners) ? Cb[w_tri_addr(o * NC + j)] : 0.)
+                                     : (j < NC ? Cb[j * strideC + o] : ((o + 1 < owners) ? Cb[o + 1] : 0.));
                 phi[2 * j - 1] += 0.5 * (cprev + cj);
                 if (2 * j < NPT) phi[2 * j < NPT ? 2 * j : 0] += cj;
                 cprev = cj;
@@ -252,7 +258,7 @@ __device__ __noinline__ void w_visit(int l, int flags, int sweeps)
                     const double lft = j ? phi[2 * j - 1 >= 0 ? 2 * j - 1 : 0] : prev, mid = phi[2 * j < NPT ? 2 * j : 0], rgt = phi[2 * j + 1 < NPT ? 2 * j + 1 : 0];
                     const double S = 2. * (SREG ? hs[(SREG && 2 * j < NPT) ? 2 * j : 0] : Sp[2 * j * strideS]);
                     const double v = 4. * (S + lft - 2. * mid + rgt) - dc * (rgt - lft);
-                    CS[j * cc.strideS + o] = (o == 0 && j == 0) ? 0. : 0.5 * v;
+                    CS[CT ? w_tri_addr(o * NC + j) : j * cc.strideS + o] = (o == 0 && j == 0) ? 0. : 0.5 * v;
                 }
             }
         } else {
@@ -274,12 +280,13 @@ __device__ __forceinline__ void w_visit_level_impl(int l, int flags, int sweeps)
 {
     const WLevel& c = ws.lv[l];
     const bool cg = ws.lv[l + 1].gl != 0;
+    const bool ct = ws.tri && l + 1 == ws.m;      // the next level is the exactly solved one
     if (l == 0) {               // Phi_0 in the global block, Source_0 / 2 in shared memory
         switch (c.npt) {
             case 32: w_visit<32, true, false, true>(l, flags, sweeps); break;
             case 16: w_visit<16, true, false, true>(l, flags, sweeps); break;
             case 8: w_visit<8, true, false, false>(l, flags, sweeps); break;
-            default: w_visit<4, true, false, false>(l, flags, sweeps); break;
+            default: if (ct) w_visit<4, true, false, false, true>(l, flags, sweeps); else w_visit<4, true, false, false>(l, flags, sweeps); break;
         }
     } else if (c.gl) {          // 8192 / 4096 nodes below level 0
         if (c.npt == 16) w_visit<16, true, true, true>(l, flags, sweeps);
@@ -287,7 +294,7 @@ __device__ __forceinline__ void w_visit_level_impl(int l, int flags, int sweeps)
         else w_visit<8, true, true, false>(l, flags, sweeps);
     } else {
         switch (c.npt) {
-            case 4: w_visit<4, false, false, false>(l, flags, sweeps); break;
+            case 4: if (ct) w_visit<4, false, false, false, true>(l, flags, sweeps); else w_visit<4, false, false, false>(l, flags, sweeps); break;
             case 2: w_visit<2, false, false, false>(l, flags, sweeps); break;
             default: w_visit<1, false, false, false>(l, flags, sweeps); break;
         }
@@ -323,13 +330,33 @@ __device__ __forceinline__ void w_dense()
     }
 }
 
+// exact solve of the 1024-node level (warp 0), in place of everything below the 2048-node level
+__device__ __forceinline__ void w_tri()
+{
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const WLevel& c = ws.lv[ws.m];
+        const double* hS = w_dyn + c.offS;
+        double* P = w_dyn + c.offP;
+        tri_solve_warp(w_dyn + ws.offT, c.a, c.b, [&](int i) { return hS[w_tri_addr(i)]; }, [&](int i, double v) { P[w_tri_addr(i)] = v; });
+    }
+}
+
 // placement of the levels 0 .. L-5.  Phi_0 and both arrays of the levels of >= 4096 nodes below it live in the global blocks (stride 512),
 // everything else in shared memory (stride 513 with 512 owners; natural order below)
-__host__ __device__ inline void w_place_all(int L, WLevel* out, int& dyn, int& gph, int& gsr)
+__host__ __device__ inline void w_place_all(int L, bool tri, WLevel* out, int& dyn, int& gph, int& gsr, int& offT)
 {
-    dyn = 0; gph = 0; gsr = 0;
-    for (int q = 0; q <= L - 5; ++q) {
+    dyn = 0; gph = 0; gsr = 0; offT = 0;
+    const int last = tri ? L - 10 : L - 5;
+    for (int q = 0; q <= last; ++q) {
         const int n = 1 << (L - q);
+        if (tri && q == last) {         // the exactly solved level: lane-major rows of 33, and its table
+            const int offP = dyn, offS = dyn + 32 * 33 + 1;
+            dyn += 2 * (32 * 33 + 1);
+            offT = dyn; dyn += kTriTableDoubles;
+            if (out) { WLevel& c = out[q]; c.n = n; c.npt = 2; c.gl = 0; c.offP = offP; c.offS = offS; c.strideP = 0; c.strideS = 0; }
+            break;
+        }
         const int npt = n >= kWT ? n / kWT : 1;
         const int owners = n / npt;
         const int gl = (q == 0 || n >= 4096) ? 1 : 0;
@@ -354,12 +381,13 @@ __global__ void __launch_bounds__(kWT, 1) poisson_warm_kernel(GridDev g, Cluster
         if (sc < a.step_min || sc >= a.step_max) return;
     }
     const int L = g.L, N = g.N, t = threadIdx.x;
-    const int m = L - 5;
+    const bool tri = a.coarse_tri != nullptr;
+    const int m = tri ? L - 10 : L - 5;
     if (t == 0) {
-        int dyn, gph, gsr;
-        w_place_all(L, ws.lv, dyn, gph, gsr);
+        int dyn, gph, gsr, offT;
+        w_place_all(L, tri, ws.lv, dyn, gph, gsr, offT);
         ws.lv[m + 1].gl = 0;
-        ws.m = m;
+        ws.m = m; ws.tri = tri; ws.offT = offT;
         ws.gphi = gphi_all + (size_t)k * gstride; ws.gsrc = gsrc_all + (size_t)k * gstride;
         ws.U = a.U + (size_t)k * a.ldU;
         ws.updates = 0;
@@ -386,7 +414,8 @@ __global__ void __launch_bounds__(kWT, 1) poisson_warm_kernel(GridDev g, Cluster
             c.alane[ln] = al;
         }
     }
-    for (int i = t; i < 32 * 32; i += kWT) ws.G[i] = a.coarse_op[i];
+    if (tri) { for (int i = t; i < kTriTableDoubles; i += kWT) w_dyn[ws.offT + i] = a.coarse_tri[i]; }
+    else { for (int i = t; i < 32 * 32; i += kWT) ws.G[i] = a.coarse_op[i]; }
     __syncthreads();
     // import: Source_0 / 2 = r 4 pi K (rho - rho_prev) / 2 into its owner-major rows; rho_prev = rho
     {
@@ -405,7 +434,7 @@ __global__ void __launch_bounds__(kWT, 1) poisson_warm_kernel(GridDev g, Cluster
     for (int cyc = 0; cyc < nv; ++cyc) {
         // down-leg (the level-0 down-visit of every cycle but the first was fused into the previous top); dU starts from 0
         for (int l = (cyc == 0 ? 0 : 1); l < m; ++l) w_visit_level(l, kWRestrict, 3);
-        w_dense();
+        if (tri) w_tri(); else w_dense();
         // up-leg
         for (int l = m - 1; l >= 1; --l) w_visit_level(l, kWLoad | kWProlong, 3);
         if (cyc == nv - 1) w_visit_level(0, kWLoad | kWProlong | kWExport, 3);
@@ -421,32 +450,39 @@ __global__ void __launch_bounds__(kWT, 1) poisson_warm_kernel(GridDev g, Cluster
 #endif
 }
 
-static int warm_smem_doubles(int L)
+static int warm_smem_doubles(int L, bool tri)
 {
-    int dyn, gph, gsr;
-    w_place_all(L, nullptr, dyn, gph, gsr);
+    int dyn, gph, gsr, offT;
+    w_place_all(L, tri, nullptr, dyn, gph, gsr, offT);
     return dyn;
+}
+
+__global__ void coarse_tri_kernel(double d, double* T) { tri_build_table(d, T); }
+// table of the exact solve of the 1024-node level of an L-level grid (poisson_tri.cuh), kTriTableDoubles doubles
+void launch_coarse_tri(int L, double delta, double* T, cudaStream_t st)
+{
+    coarse_tri_kernel<<<1, 1, 0, st>>>(delta * (double)(1 << (L - 10)), T);
 }
 
 bool poisson_warm_supported(int L, double delta) { return L >= 11 && L <= 14 && delta > 0.; }
 
 long long poisson_warm_scratch_doubles(int L)
 {
-    int dyn, gph, gsr;
-    w_place_all(L, nullptr, dyn, gph, gsr);
+    int dyn, gph, gsr, offT;
+    w_place_all(L, false, nullptr, dyn, gph, gsr, offT);
     return std::max(gph, gsr);
 }
 
 int poisson_warm_init_device()
 {
-    DFT_CHECK(cudaFuncSetAttribute(poisson_warm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, warm_smem_doubles(14) * (int)sizeof(double)));
+    DFT_CHECK(cudaFuncSetAttribute(poisson_warm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(warm_smem_doubles(14, false), warm_smem_doubles(14, true)) * (int)sizeof(double)));
     return 0;
 }
 
 // a: the arguments of poisson_cluster.cu (rho_prev required); gphi / gsrc: two scratch buffers of n_dens x gstride doubles, gstride >= poisson_warm_scratch_doubles(L)
 void launch_poisson_warm(const GridDev& g, const ClusterPoissonArgs& a, double* gphi, double* gsrc, long long gstride, cudaStream_t st)
 {
-    poisson_warm_kernel<<<a.n_dens, kWT, (size_t)warm_smem_doubles(g.L) * sizeof(double), st>>>(g, a, gphi, gsrc, gstride);
+    poisson_warm_kernel<<<a.n_dens, kWT, (size_t)warm_smem_doubles(g.L, a.coarse_tri != nullptr) * sizeof(double), st>>>(g, a, gphi, gsrc, gstride);
 }
 
 }  // namespace dft

@@ -128,7 +128,12 @@ def test_argon_c1_every_step(ctx):
 def test_batch_independence_and_determinism(ctx):
     """Atoms never interact: an atom solved alone and inside a batch gives bit-identical records (what makes the
     multi-GPU sharding exact); repeated runs are bit-identical."""
-    opts = [D.Options(Z, 10, 15.0, 0.004, 0.5, m) for Z, m in [(2, 0), (13, 0), (7, 1), (29, 0)]]
+    # (12 levels: the warm Poisson solves are shared between two kernels by the atom's own step index - still independent of the batch)
+    _check_batch_independence(ctx, [D.Options(Z, 10, 15.0, 0.004, 0.5, m) for Z, m in [(2, 0), (13, 0), (7, 1), (29, 0)]])
+    _check_batch_independence(ctx, [D.Options(Z, 12, 20.0, 0.001, 0.5, m) for Z, m in [(3, 1), (30, 0), (10, 0)]])
+
+
+def _check_batch_independence(ctx, opts):
     batch = ctx.solve_batch(opts)
     again = ctx.solve_batch(opts)
     for k, o in enumerate(opts):
@@ -144,9 +149,15 @@ def test_kernel_shapes_agree(ctx):
     full cycle vs warm start, CTA-wide vs warp-wide matched solution.  Same trajectories to far below the parity bars."""
     opts = [D.Options(Z, 12, 20.0, 0.001, 0.5, m) for Z, m in [(4, 0), (18, 0), (26, 1), (47, 0)]]
     base = ctx.solve_batch(opts)
-    variants = [{"r_segments": 0}, {"seg_threshold": 30}, {"r_segments": 32}, {"r_segments": 8}, {"warm_vcycles": 0},
-                {"match_mode": 2}]
-    defaults = {"r_segments": -1, "seg_threshold": 2400, "warm_vcycles": 7, "match_mode": 0}
+    # search: lanes across the radial grid (numerov_rows.cu, production; 4 / 8 / 16 trial energies per round) vs lanes across 32 trial
+    # energies (numerov_seg.cu / numerov_fast.cu); Poisson warm solves: one CTA per density / cluster per density / both shared by step index,
+    # exact solve of the 1024-node level vs its swept sub-cycle; host-driven SCF loop vs CUDA-graph while node
+    variants = [{"search_kernel": 1}, {"search_kernel": 1, "r_segments": 0}, {"search_kernel": 1, "seg_threshold": 30}, {"search_kernel": 1, "r_segments": 32},
+                {"search_kernel": 1, "r_segments": 8}, {"rows_cfg": 0x412}, {"rows_cfg": 0x222}, {"warm_vcycles": 0}, {"match_mode": 2},
+                {"warm_poisson": 0}, {"coarse_exact": 0}, {"warm_poisson": 0, "coarse_exact": 0}, {"warm_until_step": 0}, {"warm_until_step": 12},
+                {"use_graph": 0}]
+    defaults = {"r_segments": -1, "seg_threshold": 2400, "warm_vcycles": 7, "match_mode": 0, "search_kernel": 0, "rows_cfg": 0x111, "warm_poisson": 1,
+                "coarse_exact": 1, "warm_until_step": 32, "use_graph": 1}
     for v in variants:
         for k_, x in v.items():
             ctx.set_option(k_, x)
