@@ -23,6 +23,7 @@ sys.path.insert(0, ROOT)
 
 C3 = dict(levels=14, delta=0.0005, mixing=0.5, rmax=25.0, method=0)
 WORKLOAD = "C3 periodic-table sweep Z=1-92 LDA, 14 levels (16385 nodes), delta 0.0005, mixing 0.5, Rmax 25"
+STREAM_GROUPS_DEFAULT = 3          # libdftatom_b200's default (engine.cpp: stream_groups)
 FLOP_PER_NODE_STEP = 11.0          # SURVEY §8(d) accounting convention for the Numerov shooting kernel
 SEARCH_TRAFFIC_BYTES = None        # DRAM bytes of one search_rows_kernel launch at full load, from the ncu capture under profiles/ (None: not captured yet)
 REF_EXE = os.path.join(ROOT, "oracle", "_ref", "dftatom_ref")
@@ -293,6 +294,7 @@ def run_cuda_arm(a):
     prof = {k: dict(ms=0.0, launches=0, work=0.0) for k in D.api.KERNEL_CLASSES}
     prof_dev_ms = 0.0
     ctx.set_option("profile", 1)
+    ctx.set_option("stream_groups", 1)      # one chain: the class times add up to the sweep (the production default overlaps 3 groups of atoms on 3 streams)
     for _ in range(a.steps):
         flush_l2()
         ctx.solve_batch(opts, keep_steps=False)
@@ -301,6 +303,7 @@ def run_cuda_arm(a):
             for f in ("ms", "launches", "work"):
                 prof[k][f] += v[f]
     ctx.set_option("profile", 0)
+    ctx.set_option("stream_groups", STREAM_GROUPS_DEFAULT)
 
     wall = max_over_ranks(wall)
     dev_s = max_over_ranks(dev_ms * 1e-3)
@@ -323,9 +326,9 @@ def run_cuda_arm(a):
             tws.append(max_over_ranks(time.perf_counter() - t1))
             tds.append(max_over_ranks(ctx.last_timing()[0] * 1e-3))
         tw, td = min(tws), min(tds)
-        ctx.set_option("profile", 1)
+        ctx.set_option("profile", 1); ctx.set_option("stream_groups", 1)
         ctx.solve_batch(my_opts, keep_steps=False)
-        ctx.set_option("profile", 0)
+        ctx.set_option("profile", 0); ctx.set_option("stream_groups", STREAM_GROUPS_DEFAULT)
         pr_s = ctx.last_profile()
         tot = sum(v["ms"] for v in pr_s.values()) or 1.0
         longest = max(r.n_steps for r in r_mine) if r_mine else 0
@@ -355,7 +358,9 @@ def run_cuda_arm(a):
             gpu_launches=int(launches),
             scf_loop=dict(mode="CUDA-graph while node, loop condition set on the device (cudaGraphSetConditional)" if graph_iters else "host-driven loop",
                           scf_steps_inside_graph=int(graph_iters), device_ms_per_sweep=dev_ms / a.steps,
-                          device_ms_per_sweep_profiled_host_loop=prof_dev_ms / a.steps),
+                          device_ms_per_sweep_profiled_host_loop=prof_dev_ms / a.steps, stream_groups=STREAM_GROUPS_DEFAULT,
+                          note="timed sweeps: the library's defaults - the 92 atoms dealt into 3 groups whose SCF chains run concurrently on 3 streams, each group's loop "
+                               "one CUDA-graph launch; profiled sweeps: one group, host-driven loop, CUDA events around every kernel class"),
             roofline=dict(kernel="search_rows_kernel (Numerov shooting: Sturm-count search; one CTA per orbital, lane = radial segment (128 per orbital), every thread "
                                  "4 trial energies x 2 basis chains: 11 FP64 instructions per credited (trial energy, node) = 11 FLOP -> ceiling 0.5 of the FMA peak)",
                           bound="fp64", achieved=achieved, peak=peak, unit="TFLOP/s",
@@ -395,9 +400,9 @@ def run_cuda_arm(a):
             ctx.solve_batch(big, keep_steps=False)
             tb = time.perf_counter() - t1
             dev_b = ctx.last_timing()[0]
-            ctx.set_option("profile", 1)
+            ctx.set_option("profile", 1); ctx.set_option("stream_groups", 1)
             ctx.solve_batch(big, keep_steps=False)
-            ctx.set_option("profile", 0)
+            ctx.set_option("profile", 0); ctx.set_option("stream_groups", STREAM_GROUPS_DEFAULT)
             prb = ctx.last_profile()
             sb_ = prb["search"]
             ach = FLOP_PER_NODE_STEP * sb_["work"] / (sb_["ms"] * 1e-3) / 1e12 if sb_["ms"] > 0 else 0.0
@@ -443,9 +448,9 @@ def run_cuda_arm(a):
             r4 = ctx.solve_batch(c4, keep_steps=False)
             w_ms = (time.perf_counter() - t1) * 1e3
             dev4 = ctx.last_timing()[0]
-            ctx.set_option("profile", 1)
+            ctx.set_option("profile", 1); ctx.set_option("stream_groups", 1)
             ctx.solve_batch(c4, keep_steps=False)
-            ctx.set_option("profile", 0)
+            ctx.set_option("profile", 0); ctx.set_option("stream_groups", STREAM_GROUPS_DEFAULT)
             pr4 = ctx.last_profile()
             return dict(metric="C4 batch ms", value=w_ms, unit="ms", device_ms=dev4, atoms=len(c4), atoms_per_s=len(c4) / (w_ms * 1e-3),
                         atoms_converged=sum(r.finished for r in r4), kernels={k_: round(v["ms"], 2) for k_, v in pr4.items()},

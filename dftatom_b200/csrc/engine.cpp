@@ -80,6 +80,8 @@ struct Knobs {
                                // (numerov_rows.cu, production); 1 = lanes across 32 trial energies, cluster per orbital (numerov_seg.cu / numerov_fast.cu)
     int rows_cfg = 0x111;      // numerov_rows.cu: energy groups of 4 per round - first ladder of a warm start (bits 0-3), later ladders (4-7), uniform rounds (8-11)
     int match_mode = 0;
+    int match_win_until_step = 32;  // > 0 (grids that fit one window of the matched-solution kernel): up to this SCF step the orbitals are solved in windows of
+    int match_win_nodes = 8192;     // match_win_nodes nodes (several CTAs per SM), afterwards in one window (numerov_match.cu)
     int warm_start = 1;
     int stream_variant = 0;    // window shape of the stream-mode Poisson visits (poisson_stream.cu)
     int stream_poisson = 1;    // grids above 16385 nodes: level visits streamed over all densities (poisson_stream.cu) instead of one CTA / team per density
@@ -109,7 +111,8 @@ struct dftatom_ctx {
     std::map<GridKey, GridEntry> grids;
     Knobs k;                        // tuning knobs (dftatom_set_option); copied as a whole to the child context
     int segments(int N) const { return k.segments(N); }
-    int stream_groups = 1;     // 2: a batch of >= 32 atoms is split into two groups that run their SCF chains concurrently on separate streams
+    int stream_groups = 3;     // a batch of >= 32 atoms (grids up to 16385 nodes) is dealt into this many groups that run their SCF chains concurrently on
+                               // separate streams: one group's Poisson solves (one SM per density) overlap another's search; per-atom records are unchanged
     dftatom_ctx* child = nullptr;   // context (stream + buffers) of the second group
     int n_sm = 148;
     DevBuf stream_src0, stream_scratch, exact_work, last_steps, rho_prev, d_src, d_u;
@@ -294,8 +297,10 @@ int dftatom_set_option(dftatom_ctx* c, const char* key, double value)
         c->k.rows_cfg = v & 0xfff;
     }
     else if (k == "match_mode") c->k.match_mode = (int)value;
+    else if (k == "match_win_until_step") c->k.match_win_until_step = std::max(0, (int)value);
+    else if (k == "match_win_nodes") c->k.match_win_nodes = std::max(1024, (int)value);
     else if (k == "warm_start") c->k.warm_start = value != 0.;
-    else if (k == "stream_groups") c->stream_groups = std::min(2, std::max(1, (int)value));
+    else if (k == "stream_groups") c->stream_groups = std::min(8, std::max(1, (int)value));
     else if (k == "stream_poisson") c->k.stream_poisson = value != 0.;
     else if (k == "stream_min_dens") c->k.stream_min_dens = std::max(1, (int)value);
     else if (k == "stream_mid_levels") c->k.stream_mid_levels = std::min(14, std::max(11, (int)value));
@@ -666,7 +671,7 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
         if (c->k.search_mode != 0) for (int r = 0; r < rounds; ++r) { launch_search_round(g, b.atab, b.orbs, b.astate, b.ss, n_orbs, d_work + DFTATOM_K_SEARCH, st); ++nl; }
         end_phase();
         begin_phase(DFTATOM_K_MATCH);
-        if (c->k.match_mode == 0) launch_match_cta(g, b.atab, b.orbs, b.astate, b.ss, b.psi, b.match_pt, b.inv_norm, n_orbs, st);
+        if (c->k.match_mode == 0) launch_match_cta(g, b.atab, b.orbs, b.astate, b.ss, b.psi, b.match_pt, b.inv_norm, n_orbs, c->k.match_win_until_step, c->k.match_win_nodes, st);
         else {                                              // validation paths: warp-per-orbital / reference-shaped serial solution
             if (c->k.match_mode == 2) launch_match_seg(g, b.atab, b.orbs, b.astate, b.ss, b.psi, b.match_pt, n_orbs, st);
             else launch_match(g, b.atab, b.orbs, b.astate, b.ss, b.psi, b.match_pt, n_orbs, st);
@@ -831,6 +836,7 @@ int dftatom_solve_batch(dftatom_ctx* c, const dftatom_options* opts, int n_atoms
 {
     if (!c || !opts || !out || n_atoms <= 0) { set_error("bad argument"); return DFTATOM_E_ARG; }
     if (c->stream_groups < 2 || n_atoms < 32) return solve_group(c, opts, n_atoms, out, steps, steps_stride);
+    if (opts[0].levels > 14) return solve_group(c, opts, n_atoms, out, steps, steps_stride);      // (large grids: one group - the stream-mode Poisson solver wants all densities in one launch)
     for (int a = 0; a < n_atoms; ++a) {
         int rc = validate(opts[a]);
         if (rc) return rc;
@@ -839,42 +845,54 @@ int dftatom_solve_batch(dftatom_ctx* c, const dftatom_options* opts, int n_atoms
             return DFTATOM_E_MIXED_GRID;
         }
     }
-    if (!c->child) { int rc = dftatom_create(&c->child, c->device); if (rc) return rc; }
-    dftatom_ctx* ch = c->child;
-    ch->k = c->k; ch->stream_groups = 1;
-    // deal the atoms in order of decreasing cost (orbital count ~ Z; LSDA doubles it) alternately into the two groups
+    // G groups: this context and a chain of G - 1 child contexts (each its own stream and buffers)
+    const int G = std::min(c->stream_groups, std::max(1, n_atoms / 16));
+    std::vector<dftatom_ctx*> ctxs(1, c);
+    for (dftatom_ctx* p = c; (int)ctxs.size() < G; p = p->child) {
+        if (!p->child) { int rc = dftatom_create(&p->child, c->device); if (rc) return rc; }
+        p->child->k = c->k; p->child->stream_groups = 1;
+        ctxs.push_back(p->child);
+    }
+    // deal the atoms in order of decreasing cost (orbital count ~ Z; LSDA doubles it) round-robin into the groups
     std::vector<int> order(n_atoms);
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return opts[x].Z * (1 + (opts[x].method & 1)) > opts[y].Z * (1 + (opts[y].method & 1)); });
-    std::vector<int> idx[2];
-    for (int q = 0; q < n_atoms; ++q) idx[q & 1].push_back(order[q]);
+    std::vector<std::vector<int>> idx(G);
+    for (int q = 0; q < n_atoms; ++q) idx[q % G].push_back(order[q]);
     for (auto& v : idx) std::sort(v.begin(), v.end());
-    std::vector<dftatom_options> gopts[2];
-    std::vector<dftatom_result> gout[2];
-    std::vector<dftatom_step> gsteps[2];
-    for (int gI = 0; gI < 2; ++gI) {
+    std::vector<std::vector<dftatom_options>> gopts(G);
+    std::vector<std::vector<dftatom_result>> gout(G);
+    std::vector<std::vector<dftatom_step>> gsteps(G);
+    for (int gI = 0; gI < G; ++gI) {
         for (int a : idx[gI]) gopts[gI].push_back(opts[a]);
         gout[gI].resize(idx[gI].size());
         if (steps) gsteps[gI].resize(idx[gI].size() * (size_t)steps_stride);
     }
-    int rc1 = 0;
-    std::string err1;
-    std::thread th([&]() {
-        rc1 = solve_group(ch, gopts[1].data(), (int)gopts[1].size(), gout[1].data(), steps ? gsteps[1].data() : nullptr, steps_stride);
-        if (rc1) err1 = g_err;
-    });
-    const int rc0 = solve_group(c, gopts[0].data(), (int)gopts[0].size(), gout[0].data(), steps ? gsteps[0].data() : nullptr, steps_stride);
-    th.join();
-    if (rc0) return rc0;
-    if (rc1) { set_error(err1); return rc1; }
-    for (int gI = 0; gI < 2; ++gI)
+    std::vector<int> rcs(G, 0);
+    std::vector<std::string> errs(G);
+    std::vector<std::thread> th;
+    for (int gI = 1; gI < G; ++gI)
+        th.emplace_back([&, gI]() {
+            rcs[gI] = solve_group(ctxs[gI], gopts[gI].data(), (int)gopts[gI].size(), gout[gI].data(), steps ? gsteps[gI].data() : nullptr, steps_stride);
+            if (rcs[gI]) errs[gI] = g_err;
+        });
+    rcs[0] = solve_group(c, gopts[0].data(), (int)gopts[0].size(), gout[0].data(), steps ? gsteps[0].data() : nullptr, steps_stride);
+    for (auto& t : th) t.join();
+    if (rcs[0]) return rcs[0];
+    for (int gI = 1; gI < G; ++gI) if (rcs[gI]) { set_error(errs[gI]); return rcs[gI]; }
+    for (int gI = 0; gI < G; ++gI)
         for (size_t q = 0; q < idx[gI].size(); ++q) {
             out[idx[gI][q]] = gout[gI][q];
             if (steps) std::memcpy(steps + (size_t)idx[gI][q] * steps_stride, &gsteps[gI][q * (size_t)steps_stride], sizeof(dftatom_step) * (size_t)steps_stride);
         }
-    c->last_ms = std::max(c->last_ms, ch->last_ms);
-    c->last_launches += ch->last_launches;
-    for (int k = 0; k < DFTATOM_K_COUNT; ++k) { c->prof[k].ms += ch->prof[k].ms; c->prof[k].launches += ch->prof[k].launches; c->prof[k].work += ch->prof[k].work; }
+    for (int gI = 1; gI < G; ++gI) {
+        dftatom_ctx* ch = ctxs[gI];
+        c->last_ms = std::max(c->last_ms, ch->last_ms);
+        c->last_launches += ch->last_launches;
+        c->last_graph_iterations += ch->last_graph_iterations;
+        c->last_h2d_bytes += ch->last_h2d_bytes; c->last_d2h_bytes += ch->last_d2h_bytes;
+        for (int k = 0; k < DFTATOM_K_COUNT; ++k) { c->prof[k].ms += ch->prof[k].ms; c->prof[k].launches += ch->prof[k].launches; c->prof[k].work += ch->prof[k].work; }
+    }
     return 0;
 }
 
@@ -1033,7 +1051,7 @@ int dftatom_numerov_orbital(dftatom_ctx* c, const double* V, int levels, double 
     // single-atom ScfBuffers so that density_update's normalisation path is the one exercised
     if ((rc = c->psi.ensure(sizeof(double) * N)) || (rc = c->match_pt.ensure(sizeof(int)))) return rc;
     if ((rc = c->inv_norm.ensure(sizeof(double)))) return rc;
-    if (c->k.match_mode == 0) launch_match_cta(g, datab, dorb, ds, dss, c->psi.as<double>(), c->match_pt.as<int>(), c->inv_norm.as<double>(), 1, st);
+    if (c->k.match_mode == 0) launch_match_cta(g, datab, dorb, ds, dss, c->psi.as<double>(), c->match_pt.as<int>(), c->inv_norm.as<double>(), 1, 0, 0, st);
     else if (c->k.match_mode == 2) launch_match_seg(g, datab, dorb, ds, dss, c->psi.as<double>(), c->match_pt.as<int>(), 1, st);
     else launch_match(g, datab, dorb, ds, dss, c->psi.as<double>(), c->match_pt.as<int>(), 1, st);
     std::vector<double> y(N), sq(N), wj(N);

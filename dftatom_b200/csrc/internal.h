@@ -132,7 +132,7 @@ void launch_match_seg(const GridDev& g, const double* atab, const OrbitalDev* or
                       double* psi, int* match_pt, int n_orbs, cudaStream_t st);
 
 void launch_match_cta(const GridDev& g, const double* atab, const OrbitalDev* orbs, const AtomState* astate, const SearchState* ss,
-                      double* psi, int* match_pt, double* inv_norm, int n_orbs, cudaStream_t st);
+                      double* psi, int* match_pt, double* inv_norm, int n_orbs, int win_until_step, int win_nodes, cudaStream_t st);
 
 // potential -> a-table (a_i = 1 - (2K_i V_i + δ²/4)/12), n_tabs rows
 void launch_build_atab(const GridDev& g, const double* vpot, double* atab, int n_tabs, cudaStream_t st);

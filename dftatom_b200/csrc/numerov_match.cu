@@ -264,7 +264,7 @@ __device__ __forceinline__ int pslot(int i) { return i + (i >> 5); }
 template <bool SMEM>
 __global__ void __launch_bounds__(kMT) match_cta_kernel(GridDev g, const double* __restrict__ atab_all, const OrbitalDev* orbs,
                                                         const AtomState* astate, SearchState* ss, double* psi_all, int* match_pt,
-                                                        double* inv_norm, int n_orbs)
+                                                        double* inv_norm, int n_orbs, int step_min, int step_max)
 {
     __shared__ MatchShared sh;
     extern __shared__ double gy[];                       // SMEM: g_i, later y_i, slot pslot(i)
@@ -274,6 +274,7 @@ __global__ void __launch_bounds__(kMT) match_cta_kernel(GridDev g, const double*
     if (k >= n_orbs) return;
     const OrbitalDev ob = orbs[k];
     if (astate[ob.atom].done) return;
+    { const int sc = astate[ob.atom].n_steps; if (sc < step_min || sc >= step_max) return; }     // (the two shapes of the kernel share an SCF by step index)
     SearchState s = ss[k];
     if (s.stage != 3) {                 // search budget exhausted: didNotConverge (DFTAtom.cpp:516,538)
         s.converged = 0;
@@ -484,7 +485,7 @@ constexpr int kWinNodes = 24576;
 
 __global__ void __launch_bounds__(kMT) match_win_kernel(GridDev g, const double* __restrict__ atab_all, const OrbitalDev* orbs,
                                                         const AtomState* astate, SearchState* ss, double* psi_all, int* match_pt,
-                                                        double* inv_norm, int n_orbs)
+                                                        double* inv_norm, int n_orbs, int win_nodes, int step_min, int step_max)
 {
     __shared__ MatchShared sh;
     extern __shared__ double gy[];                       // g_i of the window, later y_i; node i at pslot(i - base)
@@ -494,6 +495,7 @@ __global__ void __launch_bounds__(kMT) match_win_kernel(GridDev g, const double*
     if (k >= n_orbs) return;
     const OrbitalDev ob = orbs[k];
     if (astate[ob.atom].done) return;
+    { const int sc = astate[ob.atom].n_steps; if (sc < step_min || sc >= step_max) return; }
     SearchState s = ss[k];
     if (s.stage != 3) {                 // search budget exhausted: didNotConverge (DFTAtom.cpp:516,538)
         s.converged = 0;
@@ -521,8 +523,8 @@ __global__ void __launch_bounds__(kMT) match_win_kernel(GridDev g, const double*
     double y_in_match = 0.;
     bool found = false;
     double eW = d_s1 * y_s1 * d_s0, eD = d_s1 * y_s1 * d_s0 - d_s0 * y_s0, eP = d_s0;      // (W_{hi+1}, W_{hi+1} - W_{hi+2}, P_{hi+1})
-    for (int hi = start - 2; hi >= 1 && !found; hi -= kWinNodes) {
-        const int lo = max(hi - kWinNodes + 1, 1);
+    for (int hi = start - 2; hi >= 1 && !found; hi -= win_nodes) {
+        const int lo = max(hi - win_nodes + 1, 1);
         const int base = lo;
         const int sth = min(hi + 2, start);
         __syncthreads();
@@ -607,8 +609,8 @@ __global__ void __launch_bounds__(kMT) match_win_kernel(GridDev g, const double*
     // ---------------- outward windows: nodes 2 ... match ----------------
     const double y1 = msc.y1;
     double oW = (1. - gtab(1)) * y1, oD = oW, oQ = 1.;          // (W_{lo-1}, W_{lo-1} - W_{lo-2}, Q_{lo-1}); W_0 = 0
-    for (int lo = 2; lo <= match; lo += kWinNodes) {
-        const int hi = min(lo + kWinNodes - 1, match);
+    for (int lo = 2; lo <= match; lo += win_nodes) {
+        const int hi = min(lo + win_nodes - 1, match);
         const int base = lo - 2;
         __syncthreads();
         for (int i = max(lo - 2, 1) + t; i <= hi; i += kMT) gy[pslot(i - base)] = gtab(i);
@@ -698,15 +700,26 @@ int match_init_device()
     return 0;
 }
 
+static size_t match_win_bytes(int win_nodes) { return ((size_t)win_nodes + 2 + (size_t)(win_nodes + 2) / 32 + 8) * sizeof(double); }
+
+// win_until_step > 0 (grids that fit one window): while an atom's SCF step counter is below it, its orbitals are solved by the windowed kernel
+// with small windows (several CTAs per SM: throughput while most atoms are still iterating), afterwards by the one-window kernel (latency);
+// both are launched, the atom's own step counter decides - its records do not depend on what else is in the batch
 void launch_match_cta(const GridDev& g, const double* atab, const OrbitalDev* orbs, const AtomState* astate, const SearchState* ss,
-                      double* psi, int* match_pt, double* inv_norm, int n_orbs, cudaStream_t st)
+                      double* psi, int* match_pt, double* inv_norm, int n_orbs, int win_until_step, int win_nodes, cudaStream_t st)
 {
     const size_t bytes = ((size_t)g.N + (size_t)g.N / 32 + 8) * sizeof(double);
     if (bytes <= kMatchCtaMaxBytes) {
-        match_cta_kernel<true><<<n_orbs, kMT, bytes, st>>>(g, atab, orbs, astate, const_cast<SearchState*>(ss), psi, match_pt, inv_norm, n_orbs);
+        int lo = 0;
+        if (win_until_step > 0 && win_nodes >= 1024 && win_nodes < g.N) {
+            match_win_kernel<<<n_orbs, kMT, match_win_bytes(win_nodes), st>>>(g, atab, orbs, astate, const_cast<SearchState*>(ss), psi, match_pt, inv_norm, n_orbs,
+                                                                          win_nodes, 0, win_until_step);
+            lo = win_until_step;
+        }
+        match_cta_kernel<true><<<n_orbs, kMT, bytes, st>>>(g, atab, orbs, astate, const_cast<SearchState*>(ss), psi, match_pt, inv_norm, n_orbs, lo, 1 << 30);
     } else {
-        const size_t wb = ((size_t)kWinNodes + 2 + (size_t)(kWinNodes + 2) / 32 + 8) * sizeof(double);
-        match_win_kernel<<<n_orbs, kMT, wb, st>>>(g, atab, orbs, astate, const_cast<SearchState*>(ss), psi, match_pt, inv_norm, n_orbs);
+        match_win_kernel<<<n_orbs, kMT, match_win_bytes(kWinNodes), st>>>(g, atab, orbs, astate, const_cast<SearchState*>(ss), psi, match_pt, inv_norm, n_orbs,
+                                                                      kWinNodes, 0, 1 << 30);
     }
 }
 
