@@ -408,7 +408,7 @@ def run_cuda_arm(a):
             ach = FLOP_PER_NODE_STEP * sb_["work"] / (sb_["ms"] * 1e-3) / 1e12 if sb_["ms"] > 0 else 0.0
             return dict(value=len(big) / tb, unit="atoms/s", atoms=len(big), seconds=tb, device_ms=dev_b,
                         search_roofline=dict(bound="fp64", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak if peak else None, kernel_ms=sb_["ms"],
-                                             lane_node_steps=sb_["work"], note="the energy search with 7328 orbitals in flight (serial-in-r kernel above 2400 active orbitals)"),
+                                             lane_node_steps=sb_["work"], note="the energy search with 7328 orbitals in flight (search_rows_kernel: one CTA per orbital)"),
                         kernels={k_: round(v["ms"], 2) for k_, v in prb.items()},
                         note="8 copies of the Z=1-92 sweep in one dftatom_solve_batch call, host options in, host results out")
 
@@ -502,9 +502,9 @@ def poisson_record(prof, n_atoms, steps):
     p = prof["poisson"]
     N = (1 << C3["levels"]) + 1
     ups = p["work"] / (p["ms"] * 1e-3) if p["ms"] else None
-    return dict(kernel="poisson_warm_kernel (warm V-cycles in increment form, SCF steps 4-31: one CTA per density, level visits in registers) + "
+    return dict(kernel="poisson_warm_kernel (warm V-cycles in increment form, SCF steps 1-31: one CTA per density, level visits in registers) + "
                        "poisson_cluster_kernel (the same from step 32 on: one cluster of 8 CTAs per density, hierarchy in distributed shared memory) + "
-                       "poisson_full_kernel (cold full-multigrid solves of the first 4 SCF steps)",
+                       "poisson_full_kernel (cold full-multigrid solves of the initial guess and SCF step 0)",
                 launches=int(p["launches"]), gs_node_updates=p["work"], ms=p["ms"], gs_updates_per_s=ups,
                 vcycles_per_s=(ups / (12.0 * N)) if ups else None, share_of_step=None,
                 bound="latency of ~380 dependent Gauss-Seidel sweeps per solve (shared memory, shuffles, one block / cluster barrier per sweep) on the SMs that "

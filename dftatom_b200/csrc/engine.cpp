@@ -67,7 +67,7 @@ struct Knobs {
     int floor_stop = 0;
     int refine_vcycles = 0;
     int warm_vcycles = 7;      // Poisson warm start from SCF step warm_after on: V-cycles per solve (0 = always the full cycle)
-    int warm_after = 4;
+    int warm_after = 1;
     int team_poisson = 1;      // large grids, few atoms: several CTAs per density (poisson.cu, team mode)
     int r_segments = -1;       // radial segments per orbital of the parallel-in-r search; -1 = auto (16 up to 16385 nodes, 32 above), 0 / 1 = serial-in-r search only
     int seg_threshold = 2400;  // the parallel-in-r search runs once at most this many orbitals are still active; above it (>= 4 warps per
@@ -255,6 +255,23 @@ int dftatom_create(dftatom_ctx** out, int device)
     DFT_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     DFT_CHECK(cudaMallocHost((void**)&c->h_active, sizeof(int) * 256));
     *out = c;
+    // DFTATOM_OPTIONS="key=value key=value ...": options applied to every new context (profiling aid: e.g. "use_graph=0 stream_groups=1" for a
+    // kernel-by-kernel launch list under ncu); an unknown key is an error
+    if (const char* env = getenv("DFTATOM_OPTIONS")) {
+        std::string e(env);
+        size_t pos = 0;
+        while (pos < e.size()) {
+            size_t end = e.find_first_of(" ,;", pos);
+            if (end == std::string::npos) end = e.size();
+            const std::string kv = e.substr(pos, end - pos);
+            pos = end + 1;
+            if (kv.empty()) continue;
+            const size_t eq = kv.find('=');
+            if (eq == std::string::npos) { set_error("DFTATOM_OPTIONS: expected key=value, got " + kv); dftatom_destroy(c); *out = nullptr; return DFTATOM_E_ARG; }
+            const int rc_o = dftatom_set_option(c, kv.substr(0, eq).c_str(), atof(kv.substr(eq + 1).c_str()));
+            if (rc_o) { dftatom_destroy(c); *out = nullptr; return rc_o; }
+        }
+    }
     return 0;
 }
 

@@ -115,8 +115,18 @@ __device__ __forceinline__ RowPre rows_pre(const GridDev& g, const double* __res
     unsigned prev = 0;
     int count = 0, bad = 0;
     if (!o.bad) {
-        for (int i = start; i >= o.qe; --i) {
-            const double gk = fma(-E, __ldg(g.c6 + i), fma(ll1, __ldg(g.b12 + i), __ldg(atab + i)));
+        // nodes qe .. qe + kRowT (start <= qe + kRowT): their table values in one batch of independent loads, then the chain
+        double gv[kRowT + 1];
+#pragma unroll
+        for (int j = 0; j <= kRowT; ++j) {
+            const int i = min(o.qe + j, g.N - 1);
+            gv[j] = fma(-E, __ldg(g.c6 + i), fma(ll1, __ldg(g.b12 + i), __ldg(atab + i)));
+        }
+#pragma unroll
+        for (int j = kRowT; j >= 0; --j) {
+            const int i = o.qe + j;
+            if (i > start) continue;
+            const double gk = gv[j];
             const double d = 1. - gk;
             double W, s, Dnew;
             if (i == start) {                          // w_start = d_start far(start)   (Numerov.h:294-298)

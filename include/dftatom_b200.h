@@ -99,18 +99,22 @@ const char* dftatom_version(void);
  *                   energies around the previous step's eigenvalue (same root: the predicate is monotone); 0 = every
  *                   step searches [-Z^2-1, 50] from scratch like the reference
  *   "match_mode"   (default 0) 0 = segmented two-sided solve (production); 1 = serial reference-arithmetic kernel
- *   "r_segments"   (default -1 = auto: 16 up to 16385 nodes, 32 above) radial segments per orbital of the parallel-in-r search
+ *   "search_kernel" (default 0) search_mode 0 on the logarithmic grid: 0 = lanes across the radial grid (numerov_rows.cu: one CTA per orbital,
+ *                   128 radial segments, every thread 4 trial energies x 2 basis chains; 2-3 rounds of 4 energies per solve); 1 = lanes across 32 trial
+ *                   energies (numerov_seg.cu / numerov_fast.cu, round 1's kernels; always used on the uniform grid).  "rows_cfg" (default 0x111):
+ *                   groups of 4 trial energies per round of the rows kernel, one hex digit each (1, 2 or 4 = 128, 64 or 32 radial segments) for
+ *                   untrusted ladders / trusted ladders / sectioning rounds
+ *   "r_segments"   (default -1 = auto: 16 up to 16385 nodes, 32 above) search_kernel 1: radial segments per orbital of the parallel-in-r search
  *                   (one thread-block cluster per orbital); 0 = serial-in-r search only (one warp per orbital)
- *   "seg_threshold" (default 2400) the parallel-in-r search runs once at most this many orbitals are still active, the
+ *   "seg_threshold" (default 2400) search_kernel 1: the parallel-in-r search runs once at most this many orbitals are still active, the
  *                   serial-in-r one (fewer instructions, needs >= 4 warps per FP64 pipe to hide its dependent chain) above
  *   "search_mode"  (default 0) 0 = fused single-predicate multisection (production); 1 = reference-shaped three-stage
  *                   search (node-count window edges, then the sign change of y(0)), kept for validation
  *   "profile"      (default 0) time every kernel class with CUDA events, see dftatom_last_profile
- *   "stream_groups" (default 1) 2 = a batch of >= 32 atoms is dealt into two groups whose SCF chains run concurrently on two
- *                   streams (atoms are independent; every launch of one chain depends on the previous one and most are
- *                   latency-bound).  Measured: C3 590 -> 624 atoms/s, but 8 x C3 in one batch 1135 -> 1027, and the per-kernel
- *                   CUDA-event times then include the contention between the groups, so it is off by default.  Per-atom
- *                   results do not depend on it.
+ *   "stream_groups" (default 3; 1..8) a batch of >= 32 atoms on a grid of <= 16385 nodes is dealt into this many groups whose SCF chains run
+ *                   concurrently on their own streams (atoms are independent; every launch of one chain depends on the previous one and most
+ *                   are latency-bound: one group's Poisson solves overlap another's search).  Measured: C3 72.5 -> 66 ms.  Per-atom results do
+ *                   not depend on it; the per-class CUDA-event times of "profile" then include the contention between the groups.
  *   "stream_poisson" (default 1) grids of at least "stream_min_levels" (default 15) levels with at least "stream_min_dens"
  *                   (default 4) densities in the batch: the Poisson solve runs as level visits streamed over all densities
  *                   (poisson_stream.cu: slab windows with halos, one launch per level visit) for the levels above
@@ -131,6 +135,17 @@ const char* dftatom_version(void);
  *                   with "profile" (per-class event timing needs host-side events between the launches), the validation search / match modes
  *                   and the cooperative team-mode Poisson kernel (one to three atoms on grids above 16385 nodes); 0 = host-driven loop.
  *   "step_cap"     (default 0 = the reference's caps, 100 LDA / 150 LSDA steps) a lower cap on the SCF steps of every atom of the batch
+ *   "warm_vcycles" (default 7) / "warm_after" (default 1): from SCF step warm_after on the Poisson solve is warm_vcycles V-cycles in increment
+ *                   form (A dU = -r 4 pi K (rho - rho_prev) from dU = 0, U += dU; "delta_poisson" 0 = iterate on U itself) instead of the full
+ *                   multigrid cycle; warm_vcycles 0 = the full cycle at every step
+ *   "warm_poisson" (default 1) those warm solves on grids of 2049 .. 16385 nodes by one CTA per density (poisson_warm.cu) while the atom's own
+ *                   SCF step counter is below "warm_until_step" (default 32; 0 = always), by the cluster kernel below afterwards: both are
+ *                   launched every step and the atom's step counter decides, so its records do not depend on what else is in the batch
+ *   "coarse_exact" (default 1) warm solves: the levels below 2048 nodes (~60 latency-bound sweeps per V-cycle for a few hundred nodes) are
+ *                   replaced by the exact solve of the 1024-node level's own equation (poisson_tri.cuh); 0 = swept like the reference does
+ *   "match_win_until_step" (default 32) / "match_win_nodes" (default 8192): grids that fit one window of the matched-solution kernel: while the
+ *                   atom's step counter is below the former its orbitals are solved in windows of the latter (3 CTAs per SM), afterwards in
+ *                   one window (one CTA per SM, lowest latency); 0 = always one window
  *   "cluster_poisson" (default 1) warm-started Poisson solves on grids of 2049 .. 16385 nodes run as one thread-block cluster of 8 CTAs per
  *                   density with the whole multigrid hierarchy in distributed shared memory (poisson_cluster.cu); 0 = one CTA per density.
  *                   "cluster_max_dens" (default: unlimited) restricts it to steps with at most that many atoms still iterating.
