@@ -68,6 +68,9 @@ struct Knobs {
     int refine_vcycles = 0;
     int warm_vcycles = 7;      // Poisson warm start from SCF step warm_after on: V-cycles per solve (0 = always the full cycle)
     int warm_after = 1;
+    int recold_at = -1;        // >= warm_after: this one SCF step solves the Poisson equation cold (full multigrid) again.  The increments never correct
+                               // U itself, so U keeps the rounding-floor bias of the last cold solve; the reference's bias follows its current density:
+                               // re-anchoring once the density has settled keeps the two closer (C3: worst deviation 7.6e-6 -> 2.7e-6 Ha)
     int team_poisson = 1;      // large grids, few atoms: several CTAs per density (poisson.cu, team mode)
     int r_segments = -1;       // radial segments per orbital of the parallel-in-r search; -1 = auto (16 up to 16385 nodes, 32 above), 0 / 1 = serial-in-r search only
     int seg_threshold = 2400;  // the parallel-in-r search runs once at most this many orbitals are still active; above it (>= 4 warps per
@@ -91,6 +94,9 @@ struct Knobs {
     int poisson_exact = 0;     // 1: bit-reproducible Poisson solve (poisson_exact.cu): the reference's FullCycle in its own operation order, 100 V-cycles
     int run_to_cap = 0;        // 1: the stop test (DFTAtom.cpp:474) is evaluated and recorded but never ends the SCF (trajectory parity beyond the stop step)
     int warm_poisson = 1;      // warm-started solves in increment form on 2049 .. 16385 nodes: one CTA per density, visits in registers (poisson_warm.cu); 0 = cluster / one-CTA kernels below
+    int direct_after = 4;      // ... from this SCF step on (earlier warm steps: the V-cycle kernels)
+    int direct_poisson = 1;    // warm solves in increment form on 2049 .. 16385 nodes: the level-0 system solved directly (Thomas algorithm as block scans,
+                               // poisson_direct.cu) instead of 7 V-cycles; 0 = the V-cycle kernels below
     int coarse_exact = 1;      // warm solves: the levels below 2048 nodes are replaced by the exact solve of the 1024-node level (poisson_tri.cuh); 0 = visited
                                // with 3 + 3 sweeps each like the reference does
     int warm_until_step = 32;  // ... up to this SCF step; from it on the cluster kernel (0: the one-CTA kernel at every step)
@@ -184,7 +190,7 @@ static int get_grid(dftatom_ctx* c, int L, double delta, double max_r, GridDev**
         }
     }
     GridEntry& e = c->grids[key];
-    int rc = e.mem.ensure((h.size() + 32 * 32 + 3 * 1024) * sizeof(double));
+    int rc = e.mem.ensure((h.size() + 32 * 32 + 3 * 1024 + (size_t)poisson_direct_table_doubles(L)) * sizeof(double));
     if (rc) { c->grids.erase(key); return rc; }
     DFT_CHECK(cudaMemcpyAsync(e.mem.p, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     DFT_CHECK(cudaStreamSynchronize(c->stream));
@@ -194,13 +200,17 @@ static int get_grid(dftatom_ctx* c, int L, double delta, double max_r, GridDev**
     e.dev.r = d; e.dev.ex = d + (size_t)N; e.dev.sqex = d + (size_t)2 * N; e.dev.b12 = d + (size_t)3 * N;
     e.dev.c6 = d + (size_t)4 * N; e.dev.k2 = d + (size_t)5 * N; e.dev.wjac = d + (size_t)6 * N;
     e.dev.psrc = d + (size_t)7 * N; e.dev.inv4pr2 = d + (size_t)8 * N; e.dev.pex = d + (size_t)9 * N;
-    e.dev.coarse_op = nullptr; e.dev.coarse_tri = nullptr;
+    e.dev.coarse_op = nullptr; e.dev.coarse_tri = nullptr; e.dev.coarse_direct = nullptr;
     if (L >= 6) {
         e.dev.coarse_op = d + (size_t)n_tab * N;
         launch_coarse_op(L, delta, e.dev.coarse_op, c->stream);
         if (L >= 11 && L <= 14) {
             e.dev.coarse_tri = d + (size_t)n_tab * N + 32 * 32;
             launch_coarse_tri(L, delta, e.dev.coarse_tri, c->stream);
+        }
+        if (poisson_direct_supported(L)) {
+            e.dev.coarse_direct = d + (size_t)n_tab * N + 32 * 32 + 3 * 1024;
+            launch_coarse_direct(L, delta, e.dev.coarse_direct, c->stream);
         }
         DFT_CHECK(cudaStreamSynchronize(c->stream));
     }
@@ -251,7 +261,7 @@ int dftatom_create(dftatom_ctx** out, int device)
     DFT_CHECK(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device));
     // opt-in dynamic shared memory is per-device state: set it here, for this context's device (not cached process-wide)
     int rc_attr;
-    if ((rc_attr = poisson_init_device()) || (rc_attr = stream_init_device()) || (rc_attr = match_init_device()) || (rc_attr = rows_init_device()) || (rc_attr = poisson_warm_init_device()) || (rc_attr = poisson_cluster_init_device())) { delete c; return rc_attr; }
+    if ((rc_attr = poisson_init_device()) || (rc_attr = stream_init_device()) || (rc_attr = match_init_device()) || (rc_attr = rows_init_device()) || (rc_attr = poisson_warm_init_device()) || (rc_attr = poisson_direct_init_device()) || (rc_attr = poisson_cluster_init_device())) { delete c; return rc_attr; }
     DFT_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     DFT_CHECK(cudaMallocHost((void**)&c->h_active, sizeof(int) * 256));
     *out = c;
@@ -302,6 +312,7 @@ int dftatom_set_option(dftatom_ctx* c, const char* key, double value)
     else if (k == "refine_vcycles") c->k.refine_vcycles = std::max(0, (int)value);
     else if (k == "warm_vcycles") c->k.warm_vcycles = std::max(0, (int)value);
     else if (k == "warm_after") c->k.warm_after = std::max(0, (int)value);
+    else if (k == "recold_at") c->k.recold_at = std::max(-1, (int)value);
     else if (k == "team_poisson") c->k.team_poisson = value != 0.;
     else if (k == "r_segments") c->k.r_segments = (int)value;
     else if (k == "seg_threshold") c->k.seg_threshold = (int)value;
@@ -326,6 +337,8 @@ int dftatom_set_option(dftatom_ctx* c, const char* key, double value)
     else if (k == "poisson_exact") c->k.poisson_exact = value != 0.;
     else if (k == "cluster_poisson") c->k.cluster_poisson = value != 0.;
     else if (k == "warm_poisson") c->k.warm_poisson = value != 0.;
+    else if (k == "direct_after") c->k.direct_after = std::max(0, (int)value);
+    else if (k == "direct_poisson") c->k.direct_poisson = value != 0.;
     else if (k == "coarse_exact") c->k.coarse_exact = value != 0.;
     else if (k == "warm_until_step") c->k.warm_until_step = std::max(0, (int)value);
     else if (k == "cluster_max_dens") c->k.cluster_max_dens = std::max(0, (int)value);
@@ -548,10 +561,16 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
     double* d_u = c->d_u.as<double>();
     const int* skip_p = &b.astate[0].done; const int skip_stride = (int)sizeof(AtomState);
     const bool warm_ok = c->k.warm_poisson && delta && !stream && poisson_warm_supported(g.L, g.delta) && g.coarse_op && (long long)lv.total >= poisson_warm_scratch_doubles(g.L);
+    const bool direct_ok = c->k.direct_poisson && delta && g.coarse_direct != nullptr;
+    int cur_step = 0;               // SCF step being enqueued (the graph body is captured at the first steady-state step)
     auto poisson_solve = [&](int warm_vcycles, long long& n_launch) {
         const bool warm = warm_vcycles > 0;
         if (exact) {
             launch_poisson_exact(xa, st);
+            ++n_launch;
+        } else if (warm && direct_ok && cur_step >= c->k.direct_after) {
+            ca.work = pa.work; ca.rho_prev = rho_prev; ca.step = nullptr; ca.scratch = d_u; ca.scratch_stride = ldU;
+            launch_poisson_direct(g, ca, st);
             ++n_launch;
         } else if (warm && warm_ok) {
             // one SM per density while most atoms are still iterating (throughput), the 8-SM cluster per density afterwards (latency): shared by
@@ -700,7 +719,8 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
         launch_density_update(g, b, st); ++nl;
         end_phase();
         begin_phase(DFTATOM_K_POISSON);
-        poisson_solve((sp >= c->k.warm_after) ? c->k.warm_vcycles : 0, nl);
+        cur_step = sp;
+        poisson_solve((sp >= c->k.warm_after && sp != c->k.recold_at) ? c->k.warm_vcycles : 0, nl);
         end_phase();
         begin_phase(DFTATOM_K_POTENTIAL);
         launch_potential_energy(g, lv, b, 0, st); ++nl;
@@ -712,10 +732,10 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
     // body (cudaGraphSetConditional): one graph launch runs the rest of the SCF of the whole batch with no host round trip at all.
     // Not used with per-class event timing (profile), the validation search / match modes, or the cooperative team-mode Poisson kernel.
     const bool team_possible = g.L >= 15 && !stream && !exact;
-    const bool graph_ok = c->k.use_graph && !prof && c->k.search_mode == 0 && c->k.match_mode == 0 && !team_possible && !getenv("DFTATOM_DEBUG_CLUSTER");
+    const bool graph_ok = c->k.use_graph && !prof && c->k.search_mode == 0 && c->k.match_mode == 0 && (!team_possible || direct_ok) && !getenv("DFTATOM_DEBUG_CLUSTER");
     bool graph_done = false;
     if (graph_ok) {
-        const int n_cold = std::min(max_steps, std::max(0, c->k.warm_after));
+        const int n_cold = std::min(max_steps, std::max(std::max(std::max(0, c->k.warm_after), c->k.recold_at + 1), direct_ok ? c->k.direct_after : 0));
         for (int sp = 0; sp < n_cold; ++sp) { enqueue_step(sp, launches); ++steps_enqueued; }
         if (n_cold < max_steps) {
             cudaGraph_t graph = nullptr, body = nullptr;

@@ -40,6 +40,7 @@ struct GridDev {
     double* inv4pr2; // 1 / (4π r_i^2) (0 at i=0)                    (DFTAtom.cpp:340)
     double* pex;     // 4π Rp²δ² · e^{2δ i} in the reference's own product order (PoissonSolver.h:66-74; uniform grid: h² 4π, :26-40): poisson_exact.cu
     double* coarse_op; // [32*32] dense operator of the Poisson sub-cycle below the 32-node level (poisson.cu), NULL for L < 6
+    double* coarse_direct; // pivots of the direct solve of the level-0 system (poisson_direct.cu), NULL unless 11 <= L <= 14
     double* coarse_tri; // table of the exact solve of the 1024-node level (poisson_tri.cuh), NULL unless 11 <= L <= 14
 };
 
@@ -246,6 +247,7 @@ struct ClusterPoissonArgs {
                                                 // only while step_min <= *step < step_max - two kernels that share the warm solves of one SCF by step index
                                                 // (a property of the atom alone: the records stay independent of what else is in the batch)
     int n_vcycles;
+    double* scratch; long long scratch_stride;  // poisson_direct.cu above 16385 nodes: n_dens x scratch_stride doubles (>= N - 1 each)
     unsigned long long* work;                   // optional: += Gauss-Seidel node-updates
     int smem_doubles;                           // set by the launcher
     long long* dbg;                             // optional [8 * 32] cycle counters of the first density's CTAs (development aid)
@@ -260,6 +262,12 @@ bool poisson_warm_supported(int L, double delta);
 long long poisson_warm_scratch_doubles(int L);
 void launch_poisson_warm(const GridDev& g, const ClusterPoissonArgs& a, double* gphi, double* gsrc, long long gstride, cudaStream_t st);
 int poisson_warm_init_device();
+// Poisson, warm solves in increment form as one direct (Thomas) solve per density (poisson_direct.cu): the arguments of the cluster mode with rho_prev given
+bool poisson_direct_supported(int L);
+long long poisson_direct_table_doubles(int L);
+void launch_coarse_direct(int L, double delta, double* W, cudaStream_t st);
+void launch_poisson_direct(const GridDev& g, const ClusterPoissonArgs& a, cudaStream_t st);
+int poisson_direct_init_device();
 void launch_coarse_tri(int L, double delta, double* T, cudaStream_t st);
 
 // per-device kernel attributes (opt-in dynamic shared memory): called once per context from dftatom_create under cudaSetDevice
