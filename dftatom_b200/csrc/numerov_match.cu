@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(128) match_seg_kernel(GridDev g, const double*
     double* __restrict__ psi = psi_all + (size_t)k * g.N;
     const double ll1 = (double)(ob.l * (ob.l + 1));
     const double kappa = sqrt(2. * fabs(E));
-    const int start = start_index(g, kappa);
+    const int start = start_index_fast(g, kappa);
     const int N = g.N;
     const MatchScale msc = match_scale(g, kappa, start, ob.l);
     auto gval = [&](int i) { return match_g(g, atab, ll1, E, msc.rho2, i); };   // f_i / 12
@@ -252,6 +252,18 @@ __device__ __forceinline__ void segment_entries(const MatP& mine, double A0, dou
     __syncthreads();                                 // wtot may be reused
 }
 
+// 1 / x for the normalisation denominators P_i d_i of the hot loops (O(1) numbers: products of 1 - f/12): hardware reciprocal estimate
+// (rcp.approx.ftz.f64, ~20 bits) + two Newton steps = ~1 ulp in 5 FP64 instructions, where the IEEE division is a ~30-instruction call that
+// ptxas evaluates on every node.  The wave functions are compared at 1e-10; the match point is decided by sign tests that do not divide.
+__device__ __forceinline__ double fast_rcp(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.), r, r);
+    r = fma(fma(-x, r, 1.), r, r);
+    return r;
+}
+
 // Node i of the staged arrays lives at slot i + i / 32: a thread walking its own contiguous chunk and a warp reading 32
 // consecutive nodes are both free of bank conflicts as long as the chunk length is a multiple of 32 (or the chunk stride
 // in slots is odd); the launcher rounds the chunk length accordingly.
@@ -275,6 +287,13 @@ __global__ void __launch_bounds__(kMT) match_cta_kernel(GridDev g, const double*
     const OrbitalDev ob = orbs[k];
     if (astate[ob.atom].done) return;
     { const int sc = astate[ob.atom].n_steps; if (sc < step_min || sc >= step_max) return; }     // (the two shapes of the kernel share an SCF by step index)
+#ifdef DFT_MATCH_DEBUG
+    long long tclk[8]; int nclk = 0;
+#define MCLK() do { if (t == 0 && nclk < 8) tclk[nclk++] = clock64(); } while (0)
+    MCLK();
+#else
+#define MCLK() do { } while (0)
+#endif
     SearchState s = ss[k];
     if (s.stage != 3) {                 // search budget exhausted: didNotConverge (DFTAtom.cpp:516,538)
         s.converged = 0;
@@ -287,17 +306,26 @@ __global__ void __launch_bounds__(kMT) match_cta_kernel(GridDev g, const double*
     double* __restrict__ psi = psi_all + (size_t)k * g.N;
     const double ll1 = (double)(ob.l * (ob.l + 1));
     const double kappa = sqrt(2. * fabs(E));
-    const int start = start_index(g, kappa);
+    const int start = start_index_fast(g, kappa);
     const int N = g.N;
     const MatchScale msc = match_scale(g, kappa, start, ob.l);
     auto gtab = [&](int i) { return match_g(g, atab, ll1, E, msc.rho2, i); };   // f_i / 12
     if (SMEM) {
-        for (int i = t; i <= start; i += kMT) gy[pslot(i)] = gtab(i);
+        // batches of 16 nodes per thread: 48 independent table loads (~100 KB per CTA) in flight instead of one L2 round trip per node
+        // (one CTA of 256 threads per SM: the register file is free)
+        for (int i0 = t; i0 <= start; i0 += 16 * kMT) {
+            double gv[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) { const int i = i0 + u * kMT; gv[u] = gtab(min(i, start)); }
+#pragma unroll
+            for (int u = 0; u < 16; ++u) { const int i = i0 + u * kMT; if (i <= start) gy[pslot(i)] = gv[u]; }
+        }
         __syncthreads();
     }
     auto gval = [&](int i) { return SMEM ? gy[pslot(i)] : gtab(i); };
     auto put = [&](int i, double y) { if (SMEM) gy[pslot(i)] = y; else psi[i] = y; };
 
+    MCLK();
     // far seeds (Numerov.h:427-447)
     const double y_s0 = msc.y_s0, y_s1 = msc.y_s1;
     const double g_s0 = gval(start), g_s1 = gval(start - 1);
@@ -336,7 +364,9 @@ __global__ void __launch_bounds__(kMT) match_cta_kernel(GridDev g, const double*
         // entry of segment 0: W_{start-1} = d_{s1} y_{s1} d_{s0}, W_start = d_{s0} y_{s0}; P_{start-1} = d_{s0}
         const double Ws1 = d_s1 * y_s1 * d_s0, Ws0 = d_s0 * y_s0;
         double A, B, Pin;
+        MCLK();
         segment_entries(M, Ws1, Ws1 - Ws0, d_s0, sh, A, B, Pin);
+        MCLK();
         // pass 2a: y_i = W_i / (P_i d_i), P_i = P_{i+1} d_{i+1}; first node (descending) with y_i < y_{i+1} or |y_i| > 1e15.
         // Nothing is stored yet: the nodes below the match point still need their g for the outward solution.
         int cand = 0;
@@ -344,20 +374,24 @@ __global__ void __launch_bounds__(kMT) match_cta_kernel(GridDev g, const double*
         if (have) {
             double g1 = g1e, g2 = g2e;
             double W1 = A, W2 = A - B, D = B, P = Pin;     // P = P_{top+1}
-            double ynext = W1 / (P * (1. - g1));
+            double Wc = 0., denc = 1., Wy2 = 0., deny2 = 1.;
+            bool has2 = false;
             for (int i = top; i >= bot; --i) {
                 const double s1 = fma(-g1, g2, g1 + g2), t1 = 10. * g1;
                 const double Dn = fma(t1, W1, fma(s1, W2, D));
                 const double W = W1 + Dn;
-                P *= (1. - g1);
+                P *= (1. - g1);                              // P_i = P_{i+1} d_{i+1}
                 const double gi = gval(i);
-                const double y = W / (P * (1. - gi));
-                if (!cand && (y < ynext || fabs(y) > 1e15)) { cand = i; ycand = y; }
-                if (i == 2) sh.y2 = y;
-                ynext = y;
+                const double den = P * (1. - gi);            // y_i = W_i / den,  y_{i+1} = W_{i+1} / P_i
+                // y_i < y_{i+1}  <=>  (W_i P_i - W_{i+1} den) sign(den P_i) < 0: no division inside the loop
+                const bool drop = (W * P - W1 * den) * (den * P) < 0.;
+                const bool big = fabs(W) > 1e15 * fabs(den);
+                if (i == 2) { Wy2 = W; deny2 = den; has2 = true; }
                 W2 = W1; W1 = W; D = Dn; g2 = g1; g1 = gi;
-                if (cand) break;                             // everything below belongs to the outward solution
+                if (drop || big) { cand = i; Wc = W; denc = den; break; }       // everything below belongs to the outward solution
             }
+            if (cand) ycand = Wc / denc;
+            if (has2) sh.y2 = Wy2 / deny2;
         }
         // the first candidate from the top = the candidate of the lowest thread index that has one
         const unsigned mc = __ballot_sync(full, cand != 0);
@@ -375,21 +409,24 @@ __global__ void __launch_bounds__(kMT) match_cta_kernel(GridDev g, const double*
         // pass 2b: the inward solution above the match point, stored (in place of g: every thread only overwrites nodes
         // whose g it has already consumed; the entry values g1e, g2e of the neighbours are in registers)
         __syncthreads();
+        MCLK();
         if (have && top > match) {
             double g1 = g1e, g2 = g2e;
-            double W1 = A, W2 = A - B, D = B, P = Pin;
+            double W1 = A, W2 = A - B, D = B;
+            double P = Pin;
             for (int i = top; i >= bot && i > match; --i) {
                 const double s1 = fma(-g1, g2, g1 + g2), t1 = 10. * g1;
                 const double Dn = fma(t1, W1, fma(s1, W2, D));
                 const double W = W1 + Dn;
                 P *= (1. - g1);
                 const double gi = gval(i);
-                put(i, W / (P * (1. - gi)));
+                put(i, W * fast_rcp(P * (1. - gi)));
                 W2 = W1; W1 = W; D = Dn; g2 = g1; g1 = gi;
             }
         }
     }
     __syncthreads();
+    MCLK();
 
     // ------------------------------------------------------------------------------------------------
     // outward: y_0 = 0, y_1 = r_1^{l+1} e^{-δ/2} (Numerov.h:110-116, :470-477); nodes i = 2 ... match
@@ -426,7 +463,8 @@ __global__ void __launch_bounds__(kMT) match_cta_kernel(GridDev g, const double*
         segment_entries(M, Wn1, Wn1, 1., sh, A, B, Qin);      // (its barriers also order the entry reads before the stores below)
         if (have) {
             double g1 = g1e, g2 = g2e;
-            double W1 = A, W2 = A - B, D = B, Q = Qin;     // Q = Q_{bot-1}
+            double W1 = A, W2 = A - B, D = B;
+            double Q = Qin;                                // Q = Q_{bot-1}
             double ylast = 0.;
             for (int i = bot; i <= top; ++i) {
                 const double s1 = fma(-g1, g2, g1 + g2), t1 = 10. * g1;
@@ -434,7 +472,7 @@ __global__ void __launch_bounds__(kMT) match_cta_kernel(GridDev g, const double*
                 const double W = W1 + Dn;
                 Q *= (1. - g1);                            // Q_i = Q_{i-1} d_{i-1}
                 const double gi = gval(i);
-                const double y = W / (Q * (1. - gi));
+                const double y = W * fast_rcp(Q * (1. - gi));
                 put(i, y);                                 // includes node `match` = outward value (Numerov.h:499)
                 ylast = y;
                 W2 = W1; W1 = W; D = Dn; g2 = g1; g1 = gi;
@@ -449,17 +487,27 @@ __global__ void __launch_bounds__(kMT) match_cta_kernel(GridDev g, const double*
     // (DFTAtom.cpp:36-56)
     if (t == 0) { put(start, y_s0); put(start - 1, y_s1); put(0, 0.); put(1, y1); }
     __syncthreads();
+    MCLK();
     const double factor = y_out_match / y_in_match;
     double acc = 0.;
-    for (int i = t; i < N; i += kMT) {
-        double y = 0.;
-        if (i <= start) {
-            y = SMEM ? gy[pslot(i)] : psi[i];
-            if (i > match) y *= factor;
-            const double u = y * __ldg(g.sqex + i);
-            acc = fma(__ldg(g.wjac + i), u * u, acc);
+    for (int i0 = t; i0 < N; i0 += 16 * kMT) {              // batches of 16 nodes per thread: the table loads of a batch are independent
+        double sq[16], wj[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) { const int i = min(i0 + u * kMT, N - 1); sq[u] = __ldg(g.sqex + i); wj[u] = __ldg(g.wjac + i); }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int i = i0 + u * kMT;
+            if (i < N) {
+                double y = 0.;
+                if (i <= start) {
+                    y = SMEM ? gy[pslot(i)] : psi[i];
+                    if (i > match) y *= factor;
+                    const double uu = y * sq[u];
+                    acc = fma(wj[u], uu * uu, acc);
+                }
+                if (SMEM || i > match) psi[i] = y;
+            }
         }
-        if (SMEM || i > match) psi[i] = y;
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(full, acc, o);
@@ -471,6 +519,11 @@ __global__ void __launch_bounds__(kMT) match_cta_kernel(GridDev g, const double*
         inv_norm[k] = 1. / tot;
         match_pt[k] = match;
     }
+#ifdef DFT_MATCH_DEBUG
+    MCLK();
+    if (t == 0 && k == 0 && SMEM) printf("match clk (orb 0, start %d match %d): stage %lld in-pass1 %lld scan %lld 2a+cand %lld 2b %lld outward %lld final %lld\n", start, match,
+                                  tclk[1] - tclk[0], tclk[2] - tclk[1], tclk[3] - tclk[2], tclk[4] - tclk[3], tclk[5] - tclk[4], tclk[6] - tclk[5], tclk[7] - tclk[6]);
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -508,7 +561,7 @@ __global__ void __launch_bounds__(kMT) match_win_kernel(GridDev g, const double*
     double* __restrict__ psi = psi_all + (size_t)k * g.N;
     const double ll1 = (double)(ob.l * (ob.l + 1));
     const double kappa = sqrt(2. * fabs(E));
-    const int start = start_index(g, kappa);
+    const int start = start_index_fast(g, kappa);
     const int N = g.N;
     const MatchScale msc = match_scale(g, kappa, start, ob.l);
     auto gtab = [&](int i) { return match_g(g, atab, ll1, E, msc.rho2, i); };   // f_i / 12

@@ -67,36 +67,6 @@ __device__ __forceinline__ double lds_f64(unsigned addr)
     return v;
 }
 
-// far cut-off index, Numerov.h:119-136: the result of start_index() (numerov_common.cuh) - the smallest idx in [2, N-1] whose far value
-// is below 1e-200, N-1 if there is none - found from the closed-form estimate and confirmed with the same predicate (2-4 evaluations
-// instead of 14 dependent ones); anything unexpected falls back to the bisection
-__device__ __forceinline__ bool far_below(const GridDev& g, double kappa, int idx)
-{
-    return -(g.rp * expm1(g.delta * (double)idx)) * kappa - (double)idx * (0.5 * g.delta) < kFarLog;
-}
-__device__ __forceinline__ int start_index_fast(const GridDev& g, double kappa)
-{
-    const int nmax = g.N - 1;
-    // r* kappa + idx delta/2 = 460.5 with r = Rp (e^{delta idx} - 1): two fixed-point steps on idx
-    double x = (double)nmax;
-#pragma unroll
-    for (int it = 0; it < 2; ++it) {
-        const double rr = (-kFarLog - x * (0.5 * g.delta)) / kappa;
-        x = rr > 0. ? log1p(rr / g.rp) / g.delta : 1.;
-        x = fmin(fmax(x, 1.), (double)nmax);
-    }
-    int idx = min(max((int)x + 1, 2), nmax);
-    // walk to the boundary: want far_below(idx) && !far_below(idx - 1)   (idx == nmax is never tested by the bisection: it is its initial hi)
-    for (int it = 0; it < 6; ++it) {
-        const bool b1 = idx >= nmax ? true : far_below(g, kappa, idx);
-        if (!b1) { ++idx; continue; }
-        const bool b0 = idx <= 2 ? false : far_below(g, kappa, idx - 1);
-        if (b0) { --idx; continue; }
-        return idx;
-    }
-    return start_index(g, kappa);
-}
-
 struct RowPre {            // pre phase of one energy (lanes = energies)
     int start, qe, count, bad;
     unsigned prev;

@@ -143,9 +143,13 @@ const char* dftatom_version(void);
  *                   launched every step and the atom's step counter decides, so its records do not depend on what else is in the batch
  *   "coarse_exact" (default 1) warm solves: the levels below 2048 nodes (~60 latency-bound sweeps per V-cycle for a few hundred nodes) are
  *                   replaced by the exact solve of the 1024-node level's own equation (poisson_tri.cuh); 0 = swept like the reference does
- *   "match_win_until_step" (default 32) / "match_win_nodes" (default 8192): grids that fit one window of the matched-solution kernel: while the
- *                   atom's step counter is below the former its orbitals are solved in windows of the latter (3 CTAs per SM), afterwards in
- *                   one window (one CTA per SM, lowest latency); 0 = always one window
+ *   "direct_poisson" (default 1) warm solves in increment form from SCF step "direct_after" (default 4) on: the level-0 system of the increment
+ *                   is solved directly (Thomas algorithm as block scans of affine maps, poisson_direct.cu; every grid of >= 2049 nodes) instead
+ *                   of by V-cycles; the warm steps before it (large increments) and "direct_poisson" 0 use the V-cycle kernels above
+ *   "recold_at"    (default -1 = never) this one SCF step solves the Poisson equation cold (full multigrid) again
+ *   "match_win_until_step" (default 0 = always one window) / "match_win_nodes" (default 8192): grids that fit one window of the matched-solution
+ *                   kernel: while the atom's step counter is below the former its orbitals are solved in windows of the latter (3 CTAs per SM),
+ *                   afterwards in one window (one CTA per SM, lowest latency)
  *   "cluster_poisson" (default 1) warm-started Poisson solves on grids of 2049 .. 16385 nodes run as one thread-block cluster of 8 CTAs per
  *                   density with the whole multigrid hierarchy in distributed shared memory (poisson_cluster.cu); 0 = one CTA per density.
  *                   "cluster_max_dens" (default: unlimited) restricts it to steps with at most that many atoms still iterating.
