@@ -81,6 +81,7 @@ struct Knobs {
     int search_mode = 0;
     int search_kernel = 0;     // search_mode 0 on the logarithmic grid: 0 = lanes across the radial grid, 4 trial energies per thread, one CTA per orbital
                                // (numerov_rows.cu, production); 1 = lanes across 32 trial energies, cluster per orbital (numerov_seg.cu / numerov_fast.cu)
+    int rows_wide_from_step = 32;   // numerov_rows.cu: from this SCF step on an atom's orbitals are searched by the 8-warp shape (0 = never)
     int rows_cfg = 0x111;      // numerov_rows.cu: energy groups of 4 per round - first ladder of a warm start (bits 0-3), later ladders (4-7), uniform rounds (8-11)
     int match_mode = 0;
     int match_win_until_step = 0;   // > 0 (grids that fit one window of the matched-solution kernel): up to this SCF step the orbitals are solved in windows of
@@ -319,6 +320,7 @@ int dftatom_set_option(dftatom_ctx* c, const char* key, double value)
     else if (k == "profile") c->k.profile = value != 0.;
     else if (k == "search_mode") c->k.search_mode = (int)value;
     else if (k == "search_kernel") c->k.search_kernel = (int)value != 0;
+    else if (k == "rows_wide_from_step") c->k.rows_wide_from_step = std::max(0, (int)value);
     else if (k == "rows_cfg") {
         const int v = (int)value;
         for (int sft = 0; sft < 12; sft += 4) { const int ng = (v >> sft) & 15; if (ng != 1 && ng != 2 && ng != 4) { set_error("rows_cfg: every field must be 1, 2 or 4"); return DFTATOM_E_ARG; } }
@@ -684,7 +686,7 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
         nvtxRangePushA("dftatom:scf_step");
         begin_phase(DFTATOM_K_SEARCH);
         if (c->k.search_mode == 0 && c->k.search_kernel == 0 && !g.uniform) {
-            launch_search_rows(g, b.atab, b.atoms, b.orbs, b.astate, b.ss, n_orbs, d_work + DFTATOM_K_SEARCH, c->k.warm_start, c->k.rows_cfg, st);
+            launch_search_rows(g, b.atab, b.atoms, b.orbs, b.astate, b.ss, n_orbs, d_work + DFTATOM_K_SEARCH, c->k.warm_start, c->k.rows_cfg, c->k.rows_wide_from_step, st);
             ++nl;
         } else if (c->k.search_mode == 0) {
             // two shapes of the same search: serial-in-r (one warp per orbital) while many orbitals are active, parallel-in-r
@@ -1057,7 +1059,7 @@ int dftatom_level_search(dftatom_ctx* c, const double* V, int levels, double del
     if ((rc = setup_single(c, g, V, Z, orbs, &da, &ds, &dorb, &dss, &datab))) return rc;
     launch_search_init(g, da, ds, dorb, dss, n_levels, st);
     const int rounds = search_rounds_needed(Z);
-    if (c->k.search_mode == 0 && c->k.search_kernel == 0 && !g.uniform) launch_search_rows(g, datab, da, dorb, ds, dss, n_levels, nullptr, 0, c->k.rows_cfg, st);
+    if (c->k.search_mode == 0 && c->k.search_kernel == 0 && !g.uniform) launch_search_rows(g, datab, da, dorb, ds, dss, n_levels, nullptr, 0, c->k.rows_cfg, 0, st);
     else if (c->k.search_mode == 0 && c->segments(g.N) > 1) launch_search_seg(g, datab, da, dorb, ds, dss, n_levels, nullptr, c->segments(g.N), nullptr, 0, 0, st);
     else if (c->k.search_mode == 0) launch_search_fused(g, datab, da, dorb, ds, dss, n_levels, nullptr, nullptr, 0, 0, st);
     else for (int r = 0; r < rounds; ++r) launch_search_round(g, datab, dorb, ds, dss, n_levels, nullptr, st);

@@ -119,7 +119,7 @@ void launch_search_seg(const GridDev& g, const double* atab, const AtomDev* atom
 void launch_numerov_lanes_seg(const GridDev& g, const NumerovLaneArgs& a, int segments, cudaStream_t st);
 // production search (numerov_rows.cu): lanes across the radial grid, 4 trial energies per thread, one CTA of 4 warps per orbital
 void launch_search_rows(const GridDev& g, const double* atab, const AtomDev* atoms, const OrbitalDev* orbs, const AtomState* astate,
-                        SearchState* ss, int n_orbs, unsigned long long* work, int warm_start, int cfg, cudaStream_t st);
+                        SearchState* ss, int n_orbs, unsigned long long* work, int warm_start, int cfg, int wide_from_step, cudaStream_t st);
 // lanes through the same sweep: one CTA per 4 n_groups consecutive lanes (n_groups = 1, 2, 4)
 void launch_numerov_lanes_rows(const GridDev& g, const NumerovLaneArgs& a, int n_groups, cudaStream_t st);
 int rows_init_device();

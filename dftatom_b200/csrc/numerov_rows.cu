@@ -34,21 +34,24 @@ namespace dft {
 
 constexpr int kRowT = 8;                          // nodes per staged tile
 constexpr int kRowE = 4;                          // trial energies per thread
-constexpr int kRowWarps = 4;                      // warps per CTA (= per orbital)
-constexpr int kRowMaxE = kRowE * kRowWarps;       // trial energies per round in the widest mode
+constexpr int kRowWarps = 4;                      // warps per CTA (= per orbital): the throughput shape; kRowWarpsWide = 8: the latency shape (few orbitals left)
+constexpr int kRowWarpsWide = 8;
+constexpr int kRowMaxW = 8;
+constexpr int kRowMaxE = 16;                      // trial energies per round in the widest mode (4 groups of 4)
 constexpr int kRowStride = kRowT + 1;             // doubles per staged row (odd: LDS.64 of 32 rows is conflict-free)
 constexpr int kRowArr = 32 * kRowStride;          // one table of one stage
 constexpr int kRowStage = 3 * kRowArr;            // a, b12, c6
-constexpr int kRowSmemBytes = kRowWarps * 2 * kRowStage * (int)sizeof(double);
+constexpr int rows_smem_bytes(int nw) { return nw * 2 * kRowStage * (int)sizeof(double); }
+constexpr int kRowSmemBytes = rows_smem_bytes(kRowWarps);
 
 struct RowShared {
     double E[kRowMaxE];                           // trial energies of the round, ascending
     int n_groups;                                 // NG: energy groups of the round (1, 2 or 4); SW = kRowWarps / NG sub-warps each
     int go;                                       // 1: another round follows
-    double tot[kRowWarps][kRowE][4];              // the composed map of a warp's 32 lanes (ww, wd, dw, dd)
-    double ptot[kRowWarps][kRowE];                // product of d over the warp's lanes
-    int cnt[kRowWarps][kRowE];                    // sign changes of the real solution inside the warp's lanes
-    int bad[kRowWarps][kRowE];
+    double tot[kRowMaxW][kRowE][4];              // the composed map of a warp's 32 lanes (ww, wd, dw, dd)
+    double ptot[kRowMaxW][kRowE];                // product of d over the warp's lanes
+    int cnt[kRowMaxW][kRowE];                    // sign changes of the real solution inside the warp's lanes
+    int bad[kRowMaxW][kRowE];
     // per energy of the round: what the pre phase found (written by the first sub-warp of the group) and the state entering node 7
     double preP[kRowMaxE], botW[kRowMaxE], botD[kRowMaxE];
     int preCnt[kRowMaxE], preBad[kRowMaxE], start[kRowMaxE];
@@ -175,10 +178,10 @@ __device__ __forceinline__ RowOut rows_post(const GridDev& g, const double* __re
 // One round of n = 4 NG trial energies (sh.E, ascending) by the whole CTA.  On return lane e < n of warp 0 holds the result of energy e
 // (other threads: undefined).  Contains block barriers: every thread of the CTA must call it.
 __device__ __forceinline__ RowOut rows_round(const GridDev& g, const double* __restrict__ atab, double ll1, int l, int want, RowShared& sh,
-                                             unsigned tiles_smem, int warp, int lane)
+                                             unsigned tiles_smem, int warp, int lane, int n_warps = kRowWarps)
 {
     const unsigned full = 0xffffffffu;
-    const int NG = sh.n_groups, SW = kRowWarps / NG;
+    const int NG = sh.n_groups, SW = n_warps / NG;
     const int gi = warp / SW, si = warp - gi * SW;
     const int S = 32 * SW;
     const int nmax = g.N - 1;
@@ -520,9 +523,10 @@ __device__ __forceinline__ void rows_update(RowBracket& b, int n, double E, bool
 }
 
 // cfg: energy groups per round (1, 2 or 4) for [bits 0-3] the first ladder of a warm start, [4-7] later ladders, [8-11] uniform rounds
-__global__ void __launch_bounds__(32 * kRowWarps, 3) search_rows_kernel(GridDev g, const double* __restrict__ atab_all, const AtomDev* atoms,
+template <int NW>
+__global__ void __launch_bounds__(32 * NW, NW == kRowWarps ? 3 : 1) search_rows_kernel(GridDev g, const double* __restrict__ atab_all, const AtomDev* atoms,
                                                                       const OrbitalDev* orbs, const AtomState* astate, SearchState* ss, int n_orbs,
-                                                                      unsigned long long* work, int warm_start, int cfg)
+                                                                      unsigned long long* work, int warm_start, int cfg, int step_min, int step_max)
 {
     extern __shared__ __align__(16) unsigned char rows_smem[];
     __shared__ RowShared sh;
@@ -532,6 +536,7 @@ __global__ void __launch_bounds__(32 * kRowWarps, 3) search_rows_kernel(GridDev 
     if (k >= n_orbs) return;
     const OrbitalDev ob = orbs[k];
     if (astate[ob.atom].done) return;
+    { const int sc = astate[ob.atom].n_steps; if (sc < step_min || sc >= step_max) return; }      // (the two shapes of the kernel share an SCF by step index)
     const double* __restrict__ atab = atab_all + (size_t)ob.tab * g.N;
     const double ll1 = (double)(ob.l * (ob.l + 1));
     const double Z = (double)atoms[ob.atom].Z;
@@ -564,7 +569,7 @@ __global__ void __launch_bounds__(32 * kRowWarps, 3) search_rows_kernel(GridDev 
                 dbg_hist[round][4] = b.inner; dbg_hist[round][5] = (double)(b.mode * 10 + (b.mode == kOneSide ? b.side + 1 : (int)b.trusted)); dbg_hist[round][6] = 0.;
             }
 #endif
-            const int NG = b.mode != kLadder ? ((cfg >> 8) & 15) : (b.trusted ? ((cfg >> 4) & 15) : (cfg & 15));
+            const int NG = b.mode != kLadder ? ((cfg >> 8) & 15) : (b.trusted ? ((cfg >> 4) & 15) : (cfg & 15));      // (NG divides NW: 1, 2 or 4)
             if (lane == 0) { sh.go = go; sh.n_groups = NG; }
             const int n = NG * kRowE;
             if (lane < n) sh.E[lane] = rows_sample(b, lane, n);
@@ -572,7 +577,7 @@ __global__ void __launch_bounds__(32 * kRowWarps, 3) search_rows_kernel(GridDev 
         __syncthreads();
         if (!sh.go) break;
         const int n = sh.n_groups * kRowE;
-        const RowOut r = rows_round(g, atab, ll1, ob.l, ob.want, sh, tiles_smem, warp, lane);
+        const RowOut r = rows_round(g, atab, ll1, ob.l, ob.want, sh, tiles_smem, warp, lane, NW);
         if (warp == 0) {
             const double E = sh.E[min(lane, n - 1)];
             if (lane < n) steps += r.start - 1;
@@ -673,16 +678,24 @@ void launch_numerov_lanes_rows(const GridDev& g, const NumerovLaneArgs& a, int n
 
 int rows_init_device()
 {
-    cudaError_t e = cudaFuncSetAttribute(search_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(search_rows_kernel<kRowWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, rows_smem_bytes(kRowWarps));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(search_rows_kernel<kRowWarpsWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, rows_smem_bytes(kRowWarpsWide));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(numerov_lanes_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmemBytes);
     if (e != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute(search_rows_kernel): ") + cudaGetErrorString(e)); return DFTATOM_E_CUDA; }
     return 0;
 }
 
+// wide_from_step > 0: an atom whose SCF step counter has reached it is searched by the 8-warp shape (256 radial segments per orbital: half the
+// depth of a round - the latency shape for the steps where few atoms are left), before that by the 4-warp shape (3 CTAs per SM: throughput); both are
+// launched, the atom's own step counter decides (its records do not depend on what else is in the batch).  0: the 4-warp shape at every step.
 void launch_search_rows(const GridDev& g, const double* atab, const AtomDev* atoms, const OrbitalDev* orbs, const AtomState* astate,
-                        SearchState* ss, int n_orbs, unsigned long long* work, int warm_start, int cfg, cudaStream_t st)
+                        SearchState* ss, int n_orbs, unsigned long long* work, int warm_start, int cfg, int wide_from_step, cudaStream_t st)
 {
-    search_rows_kernel<<<n_orbs, 32 * kRowWarps, kRowSmemBytes, st>>>(g, atab, atoms, orbs, astate, ss, n_orbs, work, warm_start, cfg);
+    const int split = wide_from_step > 0 ? wide_from_step : (1 << 30);
+    search_rows_kernel<kRowWarps><<<n_orbs, 32 * kRowWarps, rows_smem_bytes(kRowWarps), st>>>(g, atab, atoms, orbs, astate, ss, n_orbs, work, warm_start, cfg, 0, split);
+    if (wide_from_step > 0)
+        search_rows_kernel<kRowWarpsWide><<<n_orbs, 32 * kRowWarpsWide, rows_smem_bytes(kRowWarpsWide), st>>>(g, atab, atoms, orbs, astate, ss, n_orbs, work, warm_start,
+                                                                                                           cfg, split, 1 << 30);
 }
 
 }  // namespace dft

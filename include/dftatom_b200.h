@@ -104,6 +104,8 @@ const char* dftatom_version(void);
  *                   energies (numerov_seg.cu / numerov_fast.cu, round 1's kernels; always used on the uniform grid).  "rows_cfg" (default 0x111):
  *                   groups of 4 trial energies per round of the rows kernel, one hex digit each (1, 2 or 4 = 128, 64 or 32 radial segments) for
  *                   untrusted ladders / trusted ladders / sectioning rounds
+ *                   "rows_wide_from_step" (default 32; 0 = never): from this SCF step on an atom's orbitals are searched by the 8-warp shape of the
+ *                   rows kernel (256 radial segments per orbital: half the depth of a round, for the steps where few atoms are left)
  *   "r_segments"   (default -1 = auto: 16 up to 16385 nodes, 32 above) search_kernel 1: radial segments per orbital of the parallel-in-r search
  *                   (one thread-block cluster per orbital); 0 = serial-in-r search only (one warp per orbital)
  *   "seg_threshold" (default 2400) search_kernel 1: the parallel-in-r search runs once at most this many orbitals are still active, the
