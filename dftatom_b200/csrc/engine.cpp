@@ -84,7 +84,7 @@ struct Knobs {
     int rows_wide_from_step = 32;   // numerov_rows.cu: from this SCF step on an atom's orbitals are searched by the 8-warp shape (0 = never)
     int rows_cfg = 0x111;      // numerov_rows.cu: energy groups of 4 per round - first ladder of a warm start (bits 0-3), later ladders (4-7), uniform rounds (8-11)
     int match_mode = 0;
-    int match_win_until_step = 0;   // > 0 (grids that fit one window of the matched-solution kernel): up to this SCF step the orbitals are solved in windows of
+    int match_win_until_step = 32;  // > 0 (grids that fit one window of the matched-solution kernel): up to this SCF step the orbitals are solved in windows of
     int match_win_nodes = 8192;     // match_win_nodes nodes (several CTAs per SM), afterwards in one window (numerov_match.cu)
     int warm_start = 1;
     int stream_variant = 0;    // window shape of the stream-mode Poisson visits (poisson_stream.cu)

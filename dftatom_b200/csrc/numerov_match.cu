@@ -581,7 +581,13 @@ __global__ void __launch_bounds__(kMT) match_win_kernel(GridDev g, const double*
         const int base = lo;
         const int sth = min(hi + 2, start);
         __syncthreads();
-        for (int i = lo + t; i <= sth; i += kMT) gy[pslot(i - base)] = gtab(i);
+        for (int i0 = lo + t; i0 <= sth; i0 += 16 * kMT) {     // 16 nodes per thread in flight (see match_cta_kernel)
+            double gv[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) gv[u] = gtab(min(i0 + u * kMT, sth));
+#pragma unroll
+            for (int u = 0; u < 16; ++u) { const int i = i0 + u * kMT; if (i <= sth) gy[pslot(i - base)] = gv[u]; }
+        }
         __syncthreads();
         auto gval = [&](int i) { return gy[pslot(i - base)]; };
         const int n_in = hi - lo + 1;
@@ -613,20 +619,23 @@ __global__ void __launch_bounds__(kMT) match_win_kernel(GridDev g, const double*
         if (have) {
             double g1 = g1e, g2 = g2e;
             double W1 = A, W2 = A - B, D = B, P = Pin;
-            double ynext = W1 / (P * (1. - g1));
+            double Wc = 0., denc = 1., Wy2 = 0., deny2 = 1.;
+            bool has2 = false;
             for (int i = top; i >= bot; --i) {
                 const double s1 = fma(-g1, g2, g1 + g2), t1 = 10. * g1;
                 const double Dn = fma(t1, W1, fma(s1, W2, D));
                 const double W = W1 + Dn;
                 P *= (1. - g1);
                 const double gi = gval(i);
-                const double y = W / (P * (1. - gi));
-                if (!cand && (y < ynext || fabs(y) > 1e15)) { cand = i; ycand = y; }
-                if (i == 2) sh.y2 = y;
-                ynext = y;
+                const double den = P * (1. - gi);            // y_i = W_i / den, y_{i+1} = W_{i+1} / P_i: compared without a division (match_cta_kernel)
+                const bool drop = (W * P - W1 * den) * (den * P) < 0.;
+                const bool big = fabs(W) > 1e15 * fabs(den);
+                if (i == 2) { Wy2 = W; deny2 = den; has2 = true; }
                 W2 = W1; W1 = W; D = Dn; g2 = g1; g1 = gi;
-                if (cand) break;
+                if (drop || big) { cand = i; Wc = W; denc = den; break; }
             }
+            if (cand) ycand = Wc / denc;
+            if (has2) sh.y2 = Wy2 / deny2;
         }
         const unsigned mc = __ballot_sync(full, cand != 0);
         const int srcl = mc ? __ffs(mc) - 1 : 0;
@@ -648,7 +657,7 @@ __global__ void __launch_bounds__(kMT) match_win_kernel(GridDev g, const double*
                 const double W = W1 + Dn;
                 P *= (1. - g1);
                 const double gi = gval(i);
-                gy[pslot(i - base)] = W / (P * (1. - gi));
+                gy[pslot(i - base)] = W * fast_rcp(P * (1. - gi));
                 W2 = W1; W1 = W; D = Dn; g2 = g1; g1 = gi;
             }
             if (bot == lo && !found) { sh.xW = W1; sh.xD = D; sh.xP = P; }
@@ -666,7 +675,13 @@ __global__ void __launch_bounds__(kMT) match_win_kernel(GridDev g, const double*
         const int hi = min(lo + win_nodes - 1, match);
         const int base = lo - 2;
         __syncthreads();
-        for (int i = max(lo - 2, 1) + t; i <= hi; i += kMT) gy[pslot(i - base)] = gtab(i);
+        for (int i0 = max(lo - 2, 1) + t; i0 <= hi; i0 += 16 * kMT) {
+            double gv[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) gv[u] = gtab(min(i0 + u * kMT, hi));
+#pragma unroll
+            for (int u = 0; u < 16; ++u) { const int i = i0 + u * kMT; if (i <= hi) gy[pslot(i - base)] = gv[u]; }
+        }
         __syncthreads();
         auto gval = [&](int i) { return gy[pslot(i - base)]; };
         const int n_out = hi - lo + 1;
@@ -702,7 +717,7 @@ __global__ void __launch_bounds__(kMT) match_win_kernel(GridDev g, const double*
                 const double W = W1 + Dn;
                 Q *= (1. - g1);
                 const double gi = gval(i);
-                const double y = W / (Q * (1. - gi));
+                const double y = W * fast_rcp(Q * (1. - gi));
                 gy[pslot(i - base)] = y;
                 ylast = y;
                 W2 = W1; W1 = W; D = Dn; g2 = g1; g1 = gi;
@@ -720,15 +735,24 @@ __global__ void __launch_bounds__(kMT) match_win_kernel(GridDev g, const double*
     // scale the outer part so that both pieces meet at the match point (Numerov.h:497-501), zero the tail, norm integral
     const double factor = y_out_match / y_in_match;
     double acc = 0.;
-    for (int i = t; i < N; i += kMT) {
-        double y = 0.;
-        if (i <= start) {
-            y = psi[i];
-            if (i > match) y *= factor;
-            const double u = y * __ldg(g.sqex + i);
-            acc = fma(__ldg(g.wjac + i), u * u, acc);
+    for (int i0 = t; i0 < N; i0 += 16 * kMT) {               // 16 nodes per thread in flight
+        double sq[16], wj[16], yv[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) { const int i = min(i0 + u * kMT, N - 1); sq[u] = __ldg(g.sqex + i); wj[u] = __ldg(g.wjac + i); yv[u] = (i <= start) ? psi[i] : 0.; }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int i = i0 + u * kMT;
+            if (i < N) {
+                double y = 0.;
+                if (i <= start) {
+                    y = yv[u];
+                    if (i > match) y *= factor;
+                    const double uu = y * sq[u];
+                    acc = fma(wj[u], uu * uu, acc);
+                }
+                if (i > match) psi[i] = y;
+            }
         }
-        if (i > match) psi[i] = y;
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(full, acc, o);

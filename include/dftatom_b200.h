@@ -149,7 +149,7 @@ const char* dftatom_version(void);
  *                   is solved directly (Thomas algorithm as block scans of affine maps, poisson_direct.cu; every grid of >= 2049 nodes) instead
  *                   of by V-cycles; the warm steps before it (large increments) and "direct_poisson" 0 use the V-cycle kernels above
  *   "recold_at"    (default -1 = never) this one SCF step solves the Poisson equation cold (full multigrid) again
- *   "match_win_until_step" (default 0 = always one window) / "match_win_nodes" (default 8192): grids that fit one window of the matched-solution
+ *   "match_win_until_step" (default 32; 0 = always one window) / "match_win_nodes" (default 8192): grids that fit one window of the matched-solution
  *                   kernel: while the atom's step counter is below the former its orbitals are solved in windows of the latter (3 CTAs per SM),
  *                   afterwards in one window (one CTA per SM, lowest latency)
  *   "cluster_poisson" (default 1) warm-started Poisson solves on grids of 2049 .. 16385 nodes run as one thread-block cluster of 8 CTAs per

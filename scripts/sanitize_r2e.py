@@ -9,7 +9,12 @@ import dftatom_b200 as D
 ctx = D.Context(0)
 ctx.set_option("use_graph", int(os.environ.get("SAN_GRAPH", "0")))
 ctx.set_option("step_cap", int(os.environ.get("SAN_STEPS", "8")))
-ctx.set_option("warm_until_step", 6)            # steps 4, 5: poisson_warm_kernel; 6, 7: poisson_cluster_kernel
+ctx.set_option("step_cap", int(os.environ.get("SAN_STEPS", "10")))
+ctx.set_option("warm_until_step", 3)            # steps 1, 2: poisson_warm_kernel; 3, 4: poisson_cluster_kernel; 5 .. 9: poisson_direct_kernel
+ctx.set_option("direct_after", 5)
+ctx.set_option("rows_wide_from_step", 5)        # steps 0 .. 4: 4-warp search; 5 .. 9: 8-warp search
+ctx.set_option("match_win_until_step", 5)       # steps 0 .. 4: windowed matched solution (windows of 1024 nodes); 5 .. 9: one window
+ctx.set_option("match_win_nodes", 1024)
 for cfg in (0x111, 0x412):
     ctx.set_option("rows_cfg", cfg)
     r = ctx.solve_batch([D.Options(4, 11, 15.0, 0.002, 0.5, 0), D.Options(3, 11, 15.0, 0.002, 0.5, 1)], keep_steps=False)
@@ -21,6 +26,9 @@ ctx.set_option("coarse_exact", 0)
 r = ctx.solve_batch([D.Options(6, 12, 20.0, 0.001, 0.5, 0)], keep_steps=False)
 print("scf L12 swept coarse levels", [x.n_steps for x in r], r[0].Etotal, flush=True)
 ctx.set_option("coarse_exact", 1)
+ctx.set_option("direct_after", 2); ctx.set_option("step_cap", 5)
+r = ctx.solve_batch([D.Options(3, 15, 20.0, 0.0003, 0.5, 0)], keep_steps=False)
+print("scf L15 (chunked direct Poisson solve, windowed match)", [x.n_steps for x in r], r[0].Etotal, flush=True)
 r = ctx.solve_batch([D.Options(10, 9, 15.0, 0.008, 0.5, 0)], keep_steps=False)
 print("scf L9 (rows search on a coarse grid)", [x.n_steps for x in r], r[0].Etotal, flush=True)
 L, delta, rmax = 10, 0.004, 15.0
