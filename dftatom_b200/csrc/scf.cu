@@ -44,7 +44,7 @@ __device__ __forceinline__ XcLda xc_lda(double rho)
     XcLda o; o.vexc = 0.; o.edif = 0.;
     if (rho < 1e-18) return o;
     const double third = 1. / 3.;
-    const double rs = pow(3. / (kFourPi * rho), third);
+    const double rs = cbrt(3. / (kFourPi * rho));            // (the reference: pow(., 1/3) - equal to ~1e-16 relative, a fifth of the instructions)
     const VwnVal p = vwn_eval(sqrt(rs), kVwnP);
     o.vexc = -DFT_X1 / rs + p.eps - third * p.deps;
     o.edif = 0.25 * DFT_X1 / rs + third * p.deps;
@@ -58,16 +58,17 @@ __device__ __forceinline__ XcLsda xc_lsda(double roa, double rob)
     const double n = roa + rob;
     if (n < 1e-18) return o;
     const double third = 1. / 3.;
-    const double rs = pow(3. / (kFourPi * n), third);
-    const double rsa = pow(3. / (kFourPi * roa), third);
-    const double rsb = pow(3. / (kFourPi * rob), third);
+    const double rs = cbrt(3. / (kFourPi * n));
+    const double rsa = cbrt(3. / (kFourPi * roa));
+    const double rsb = cbrt(3. / (kFourPi * rob));
     const double exp_ = -DFT_X1 / rs;
     const double exdif = DFT_CBRT2 * exp_ - exp_;
     const double zeta = (roa - rob) / n;
     const double z3 = zeta * zeta * zeta, z4 = z3 * zeta;
     const double fdd = 4. / (9. * (DFT_CBRT2 - 1.));
-    const double fv = (pow(1. + zeta, 4. * third) + pow(1. - zeta, 4. * third) - 2.) / (2. * (DFT_CBRT2 - 1.));
-    const double dfv = 2. / (3. * (DFT_CBRT2 - 1.)) * (pow(1. + zeta, third) - pow(1. - zeta, third));
+    const double cp = cbrt(1. + zeta), cm = cbrt(1. - zeta);     // (1 +- zeta)^(1/3); ^(4/3) = x cbrt(x)
+    const double fv = ((1. + zeta) * cp + (1. - zeta) * cm - 2.) / (2. * (DFT_CBRT2 - 1.));
+    const double dfv = 2. / (3. * (DFT_CBRT2 - 1.)) * (cp - cm);
     const double y = sqrt(rs);
     const VwnVal P = vwn_eval(y, kVwnP), F = vwn_eval(y, kVwnF), A = vwn_eval(y, kVwnA);
     const double dfp = F.eps - P.eps;
