@@ -205,14 +205,16 @@ static int get_grid(dftatom_ctx* c, int L, double delta, double max_r, GridDev**
     if (L >= 6) {
         e.dev.coarse_op = d + (size_t)n_tab * N;
         launch_coarse_op(L, delta, e.dev.coarse_op, c->stream);
+        std::vector<double> tab(3 * 1024 + (size_t)poisson_direct_table_doubles(L));      // pivot tables of the exact solves: dependent chains, built here
         if (L >= 11 && L <= 14) {
             e.dev.coarse_tri = d + (size_t)n_tab * N + 32 * 32;
-            launch_coarse_tri(L, delta, e.dev.coarse_tri, c->stream);
+            coarse_tri_host(L, delta, tab.data());
         }
         if (poisson_direct_supported(L)) {
             e.dev.coarse_direct = d + (size_t)n_tab * N + 32 * 32 + 3 * 1024;
-            launch_coarse_direct(L, delta, e.dev.coarse_direct, c->stream);
+            coarse_direct_host(L, delta, tab.data() + 3 * 1024);
         }
+        DFT_CHECK(cudaMemcpyAsync(d + (size_t)n_tab * N + 32 * 32, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         DFT_CHECK(cudaStreamSynchronize(c->stream));
     }
     *out = &e.dev;

@@ -265,10 +265,10 @@ int poisson_warm_init_device();
 // Poisson, warm solves in increment form as one direct (Thomas) solve per density (poisson_direct.cu): the arguments of the cluster mode with rho_prev given
 bool poisson_direct_supported(int L);
 long long poisson_direct_table_doubles(int L);
-void launch_coarse_direct(int L, double delta, double* W, cudaStream_t st);
+void coarse_direct_host(int L, double delta, double* W);      // host-side table builders (once per grid)
 void launch_poisson_direct(const GridDev& g, const ClusterPoissonArgs& a, cudaStream_t st);
 int poisson_direct_init_device();
-void launch_coarse_tri(int L, double delta, double* T, cudaStream_t st);
+void coarse_tri_host(int L, double delta, double* T);
 
 // per-device kernel attributes (opt-in dynamic shared memory): called once per context from dftatom_create under cudaSetDevice
 int poisson_init_device();

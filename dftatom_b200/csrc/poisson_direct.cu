@@ -226,15 +226,16 @@ __global__ void __launch_bounds__(kDT, 1) poisson_direct_kernel(GridDev g, Clust
     if (threadIdx.x == 0 && a.work) atomicAdd(a.work, (unsigned long long)(2 * (g.N - 1)));      // (two elimination passes over the grid)
 }
 
-// pivots of the level-0 system of an L-level grid, owner-major for 512 owners (per chunk of 16384 nodes above 14 levels): one thread
-__global__ void coarse_direct_kernel(int L, double delta, double* W)
+// pivots of the level-0 system of an L-level grid, owner-major for 512 owners (per chunk of 16384 nodes above 14 levels); built on the host once per
+// grid (a dependent chain of n divisions: microseconds on a CPU core, milliseconds on one GPU thread); fma as the device code contracts it
+void coarse_direct_host(int L, double delta, double* W)
 {
     const int n = 1 << L;
     const int npt = n / kDT > 32 ? 32 : n / kDT, ch = kDT * npt;
     const double a = 0.5 * (1. + 0.5 * delta), b = 0.5 * (1. - 0.5 * delta);
     double gamma = 0.;
     for (int i = 0; i < n; ++i) {
-        const double w = i ? 1. / (1. - a * gamma) : 0.;     // node 0: the left boundary (delta_0 = 0, gamma_0 = 0)
+        const double w = i ? 1. / std::fma(-a, gamma, 1.) : 0.;     // node 0: the left boundary (delta_0 = 0, gamma_0 = 0)
         gamma = b * w;
         const int c = i / ch, r = i % ch;
         W[(size_t)c * ch + (r % npt) * kDT + r / npt] = w;
@@ -243,7 +244,6 @@ __global__ void coarse_direct_kernel(int L, double delta, double* W)
 
 bool poisson_direct_supported(int L) { return L >= 11 && L <= 20; }
 long long poisson_direct_table_doubles(int L) { return poisson_direct_supported(L) ? (1ll << L) : 0; }
-void launch_coarse_direct(int L, double delta, double* W, cudaStream_t st) { coarse_direct_kernel<<<1, 1, 0, st>>>(L, delta, W); }
 
 static size_t direct_smem_bytes(int L) { return (size_t)std::min(32, (1 << L) / kDT) * kDStride * sizeof(double); }
 

@@ -21,13 +21,13 @@ constexpr int kTriTableDoubles = 3 * kTriN;     // W, ML, GL, each in the layout
 // table for level spacing d (= delta 2^l of that level): one thread
 //   w_0 = 0, w_i = 1 / (1 - a gamma_{i-1}), gamma_i = b w_i                               (pivots of the forward elimination)
 //   ML_i = prod_{j = 32 lane .. i} a w_j,  GL_i = prod_{j = i .. 32 lane + 31} b w_j      (local prefix / suffix products of the multipliers)
-inline __device__ void tri_build_table(double d, double* T)
+inline __host__ __device__ void tri_build_table(double d, double* T)
 {
     const double a = 0.5 * (1. + 0.5 * d), b = 0.5 * (1. - 0.5 * d);
     double* W = T; double* ML = T + kTriN; double* GL = T + 2 * kTriN;
     double gamma = 0.;
     for (int i = 0; i < kTriN; ++i) {
-        const double w = i ? 1. / (1. - a * gamma) : 0.;
+        const double w = i ? 1. / fma(-a, gamma, 1.) : 0.;
         gamma = b * w;
         W[(i & 31) * 32 + (i >> 5)] = w;
     }

@@ -457,12 +457,8 @@ static int warm_smem_doubles(int L, bool tri)
     return dyn;
 }
 
-__global__ void coarse_tri_kernel(double d, double* T) { tri_build_table(d, T); }
-// table of the exact solve of the 1024-node level of an L-level grid (poisson_tri.cuh), kTriTableDoubles doubles
-void launch_coarse_tri(int L, double delta, double* T, cudaStream_t st)
-{
-    coarse_tri_kernel<<<1, 1, 0, st>>>(delta * (double)(1 << (L - 10)), T);
-}
+// table of the exact solve of the 1024-node level of an L-level grid (poisson_tri.cuh), kTriTableDoubles doubles; built on the host once per grid
+void coarse_tri_host(int L, double delta, double* T) { tri_build_table(delta * (double)(1 << (L - 10)), T); }
 
 bool poisson_warm_supported(int L, double delta) { return L >= 11 && L <= 14 && delta > 0.; }
 
