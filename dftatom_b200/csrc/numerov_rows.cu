@@ -48,6 +48,7 @@ struct RowShared {
     double E[kRowMaxE];                           // trial energies of the round, ascending
     int n_groups;                                 // NG: energy groups of the round (1, 2 or 4); SW = kRowWarps / NG sub-warps each
     int go;                                       // 1: another round follows
+    int use_hint;                                 // 1: the bracket is narrow, the cut-off index of the last round is a good first estimate
     double tot[kRowMaxW][kRowE][4];              // the composed map of a warp's 32 lanes (ww, wd, dw, dd)
     double ptot[kRowMaxW][kRowE];                // product of d over the warp's lanes
     int cnt[kRowMaxW][kRowE];                    // sign changes of the real solution inside the warp's lanes
@@ -76,11 +77,41 @@ struct RowPre {            // pre phase of one energy (lanes = energies)
     double W, D, P;        // state at node qe: (W_qe, W_qe - W_{qe+1}); P = product of d_i d_{i+1} over the even nodes qe .. start
 };
 
-__device__ __forceinline__ RowPre rows_pre(const GridDev& g, const double* __restrict__ atab, double ll1, double E)
+// far cut-off index of the inward sweep = start_index(g, kappa) (numerov_common.cuh; Numerov.h:119-136), warp-collective: lane = 4 j + e
+// evaluates the far-value predicate of energy e (= lane & 3, every lane passes its own kappa) at candidate j of a window of 8 indices around
+// the closed-form estimate; one evaluation per lane instead of a serial walk.  hint: a cut-off index found earlier for a nearby energy
+// (one fixed-point step is then enough), or < 0.  The result is defined by the predicate alone, so it does not depend on the hint.
+__device__ __forceinline__ int rows_start(const GridDev& g, double kappa, int hint, int lane)
+{
+    const unsigned full = 0xffffffffu;
+    if (g.uniform) return start_index(g, kappa);
+    const int nmax = g.N - 1;
+    double x = hint > 0 ? (double)hint : (double)nmax;
+    const int iters = hint > 0 ? 1 : 2;
+    for (int it = 0; it < iters; ++it) {           // r* kappa + idx delta/2 = 460.5 with r = Rp (e^{delta idx} - 1)
+        const double rr = (-kFarLog - x * (0.5 * g.delta)) / kappa;
+        x = rr > 0. ? log1p(rr / g.rp) / g.delta : 1.;
+        x = fmin(fmax(x, 1.), (double)nmax);
+    }
+    const int j = lane >> 2;
+    const int c = min(max((int)x - 2 + j, 2), nmax);
+    const bool below = c >= nmax ? true : far_below(g, kappa, c);
+    const unsigned m = (__ballot_sync(full, below) >> (lane & 3)) & 0x11111111u;        // bit 4 j: candidate j of this lane's energy
+    const int c0 = min(max((int)x - 2, 2), nmax);
+    int res = -1;
+    if (m) {
+        const int jf = (__ffs((int)m) - 1) >> 2;    // first candidate below the threshold; the one before it (if any) is above
+        if (jf > 0 || c0 == 2) res = min(max((int)x - 2 + jf, 2), nmax);
+    }
+    if (__any_sync(full, res < 0)) { const int r2 = start_index(g, kappa); if (res < 0) res = r2; }      // (estimate off by more than the window)
+    return res;
+}
+
+__device__ __forceinline__ RowPre rows_pre(const GridDev& g, const double* __restrict__ atab, double ll1, double E, int hint, int lane)
 {
     RowPre o;
     const double kappa = sqrt(2. * fabs(E));
-    const int start = start_index_fast(g, kappa);
+    const int start = rows_start(g, kappa, hint, lane);
     o.start = start;
     o.qe = ((start - 1) / kRowT) * kRowT;
     o.bad = o.qe < 2 * kRowT;                      // no main tile below the seeds: the generic serial sweep takes the round
@@ -88,40 +119,45 @@ __device__ __forceinline__ RowPre rows_pre(const GridDev& g, const double* __res
     unsigned prev = 0;
     int count = 0, bad = 0;
     if (!o.bad) {
-        // nodes qe .. qe + kRowT (start <= qe + kRowT): their table values in one batch of independent loads, then the chain
+        // nodes qe .. qe + kRowT (qe < start <= qe + kRowT) and the two seed nodes again by their own index: one batch of independent loads
         double gv[kRowT + 1];
 #pragma unroll
         for (int j = 0; j <= kRowT; ++j) {
             const int i = min(o.qe + j, g.N - 1);
             gv[j] = fma(-E, __ldg(g.c6 + i), fma(ll1, __ldg(g.b12 + i), __ldg(atab + i)));
         }
+        const double gs = fma(-E, __ldg(g.c6 + start), fma(ll1, __ldg(g.b12 + start), __ldg(atab + start)));
+        const double gt = fma(-E, __ldg(g.c6 + start - 1), fma(ll1, __ldg(g.b12 + start - 1), __ldg(atab + start - 1)));
+        const double fs = far_value(g, kappa, start, start), ft = far_value(g, kappa, start - 1, start);
+        {   // w_start = d_start far(start), d_{start+1} := 1   (Numerov.h:294-298)
+            const double d = 1. - gs;
+            W2 = d * fs;
+            bad |= !(d > 0.);
+            if (!(start & 1)) P *= (1. - gs);
+        }
+        {   // w_{start-1} d_start   (Numerov.h:300-303)
+            const double d = 1. - gt;
+            W1 = d * ft * (1. - gs);
+            s1 = fma(-gt, gs, gt + gs);
+            D = W1 - W2;
+            bad |= !(d > 0.);
+            if (!((start - 1) & 1)) P *= (1. - s1);
+            g1 = gt; t1 = 10. * gt;
+        }
+        const int js = start - o.qe;               // 1 .. kRowT: the seeds are rows js, js - 1 of the batch
 #pragma unroll
-        for (int j = kRowT; j >= 0; --j) {
-            const int i = o.qe + j;
-            if (i > start) continue;
+        for (int j = kRowT - 2; j >= 0; --j) {
+            if (j >= js - 1) continue;
             const double gk = gv[j];
             const double d = 1. - gk;
-            double W, s, Dnew;
-            if (i == start) {                          // w_start = d_start far(start)   (Numerov.h:294-298)
-                W = d * far_value(g, kappa, i, start);
-                s = gk;                                // d_{start+1} := 1
-                Dnew = 0.;
-                bad |= !(d > 0.);
-            } else if (i == start - 1) {               // w_{start-1} d_start            (Numerov.h:300-303)
-                W = d * far_value(g, kappa, i, start) * (1. - g1);
-                s = fma(-gk, g1, gk + g1);
-                Dnew = W - W1;
-                bad |= !(d > 0.);
-            } else {
-                Dnew = fma(t1, W1, fma(s1, W2, D));
-                W = W1 + Dnew;
-                s = fma(-gk, g1, gk + g1);
-                const unsigned sy = ((unsigned)hi32(W) ^ (unsigned)hi32(d)) >> 31;
-                count += (sy != prev);
-                prev = sy;
-                bad |= !(d > 0.);
-            }
-            if (!(i & 1)) P *= (1. - s);
+            const double Dnew = fma(t1, W1, fma(s1, W2, D));
+            const double W = W1 + Dnew;
+            const double s = fma(-gk, g1, gk + g1);
+            const unsigned sy = ((unsigned)hi32(W) ^ (unsigned)hi32(d)) >> 31;
+            count += (sy != prev);
+            prev = sy;
+            bad |= !(d > 0.);
+            if (!((o.qe + j) & 1)) P *= (1. - s);
             D = Dnew; W2 = W1; W1 = W; g1 = gk; s1 = s; t1 = 10. * gk;
         }
     }
@@ -130,9 +166,10 @@ __device__ __forceinline__ RowPre rows_pre(const GridDev& g, const double* __res
     return o;
 }
 
-struct RowOut { int cfull, y0_pos, start, bad; double d_first, y0_log2; };
+struct RowOut { int cfull, y0_pos, start, bad; double d_first, y0s, P; };      // y_0 = y0s / P (P > 0); its log2: rows_ylog
+__device__ __forceinline__ double rows_ylog(double y0s, double P) { return (fabs(y0s) <= 1.7e308) ? log2(fabs(y0s)) - log2(fabs(P)) : INFINITY; }
 #ifdef DFT_ROWS_DEBUG
-__device__ long long g_rows_clk[8];
+__device__ long long g_rows_clk[12];
 __device__ __forceinline__ bool getenv_dbg_clk(unsigned long long* work) { return work != nullptr && (atomicAdd(work + 5, 0ULL) % 50) == 0; }
 #define ROWS_CLK(i) do { if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd((unsigned long long*)&g_rows_clk[i], (unsigned long long)(t_ - t_last)); t_last = t_; } } while (0)
 #else
@@ -167,7 +204,7 @@ __device__ __forceinline__ RowOut rows_post(const GridDev& g, const double* __re
     const double d1 = 1. - g1;
     const double Y0s = W1 * fma(12., g1, 2.) / d1 - W2;
     o.y0_pos = Y0s > 0.;
-    o.y0_log2 = (fabs(Y0s) <= 1.7e308) ? log2(fabs(Y0s)) - log2(fabs(P)) : INFINITY;
+    o.y0s = Y0s; o.P = P;
     o.cfull = count + (((o.y0_pos ? 0u : 1u) != prev) ? 1 : 0);
     o.bad = bad | !(P > 0.);
     o.d_first = d1;
@@ -178,7 +215,7 @@ __device__ __forceinline__ RowOut rows_post(const GridDev& g, const double* __re
 // One round of n = 4 NG trial energies (sh.E, ascending) by the whole CTA.  On return lane e < n of warp 0 holds the result of energy e
 // (other threads: undefined).  Contains block barriers: every thread of the CTA must call it.
 __device__ __forceinline__ RowOut rows_round(const GridDev& g, const double* __restrict__ atab, double ll1, int l, int want, RowShared& sh,
-                                             unsigned tiles_smem, int warp, int lane, int n_warps = kRowWarps)
+                                             unsigned tiles_smem, int warp, int lane, int n_warps = kRowWarps, int* hint_io = nullptr)
 {
     const unsigned full = 0xffffffffu;
     const int NG = sh.n_groups, SW = n_warps / NG;
@@ -191,7 +228,8 @@ __device__ __forceinline__ RowOut rows_round(const GridDev& g, const double* __r
 #endif
     // ---------------- pre: seeds (lane = energy lane & 3 of the group, replicated over the warp) ----------------
     const int eg = gi * kRowE + (lane & 3);
-    const RowPre pre = rows_pre(g, atab, ll1, sh.E[eg]);
+    const RowPre pre = rows_pre(g, atab, ll1, sh.E[eg], hint_io ? *hint_io : -1, lane);
+    if (hint_io) *hint_io = pre.start;
     if (si == 0 && lane < kRowE) { sh.preP[eg] = pre.P; sh.preCnt[eg] = pre.count; sh.preBad[eg] = pre.bad; sh.start[eg] = pre.start; }
     double E[kRowE], seedW[kRowE], seedD[kRowE];
     int mf[kRowE];                                 // first (highest) main tile of the energy
@@ -370,7 +408,7 @@ __device__ __forceinline__ RowOut rows_round(const GridDev& g, const double* __r
     ROWS_CLK(3);
     // ---------------- post: nodes 7 .. 1 and y_0, lane = energy (warp 0) ----------------
     RowOut r;
-    r.cfull = 0; r.y0_pos = 0; r.start = 0; r.bad = 0; r.d_first = 1.; r.y0_log2 = 0.;
+    r.cfull = 0; r.y0_pos = 0; r.start = 0; r.bad = 0; r.d_first = 1.; r.y0s = 1.; r.P = 1.;
     if (warp == 0) {
         const int n = NG * kRowE;
         const int e = min(lane, n - 1);
@@ -383,9 +421,13 @@ __device__ __forceinline__ RowOut rows_round(const GridDev& g, const double* __r
         if (__any_sync(full, r.bad)) {
             // a non-positive 1 - f/12 inside the sweep, or a sweep too short to cut (grid far too coarse for this energy): generic serial path
             const LaneOut so = sweep_lane(g, atab, l, sh.E[e], want);
-            r.cfull = so.count_full; r.d_first = so.d_first; r.y0_log2 = so.y0_log2; r.y0_pos = so.y0_pos;
+            r.cfull = so.count_full; r.d_first = so.d_first; r.y0_pos = so.y0_pos; r.P = 1.;
+            r.y0s = (so.y0_log2 > -1e300 && so.y0_log2 < 1e300) ? (so.y0_pos ? 1. : -1.) * exp2(fmin(fmax(so.y0_log2, -1000.), 1000.)) : INFINITY;
         }
     }
+#ifdef DFT_ROWS_DEBUG
+    if (r.y0s == 1.2345e-300 && r.P == 7. && r.cfull == 12345) sh.go = 2;       // (the clock below must wait for the results)
+#endif
     ROWS_CLK(4);
     return r;
 }
@@ -403,7 +445,7 @@ struct RowBracket {
     double lo, hi;          // the root is in (lo, hi]
     double c_est, radius;   // kLadder: centre and outermost offset;  kOneSide: anchor and first offset
     double inner;           // kLadder: innermost offset
-    double ylog;
+    double y_lm, P_lm;      // y_0 = y_lm / P_lm of the last virtual-bisection midpoint (1e15 guard, DFTAtom.cpp:528)
     int mode;
     int side;               // kOneSide: -1 = the root lies below the anchor, +1 = above
     bool trusted;           // kLadder: the estimate comes from a checked interpolation (4 energies are enough for the round)
@@ -414,24 +456,34 @@ __device__ __forceinline__ double rows_sample(const RowBracket& b, int e, int n)
     if (b.mode == kLadder) {
         const int h = n >> 1;
         const double inner = fmin(b.inner, b.radius);
-        const double lg = h > 1 ? log2(fmax(b.radius, inner) / inner) / (double)(h - 1) : 0.;
         const int mstep = (e < h) ? (h - 1 - e) : (e - h);                  // 0 = closest to the estimate
-        const double off = inner * exp2((double)mstep * lg);
+        double off;
+        if (h == 2) off = mstep ? fmax(b.radius, inner) : inner;            // (the production shape: 4 energies per round)
+        else {
+            const double lg = h > 1 ? log2(fmax(b.radius, inner) / inner) / (double)(h - 1) : 0.;
+            off = inner * exp2((double)mstep * lg);
+        }
         return fmin(fmax((e < h) ? b.c_est - off : b.c_est + off, b.lo), b.hi);
     }
     if (b.mode == kOneSide) {
         const double far = b.side < 0 ? b.c_est - b.lo : b.hi - b.c_est;
         const double d0 = fmin(b.radius, far);
-        const double lg = log2(fmax(far / d0, 1.)) / (double)n;             // the n-th step would land on the bracket end
         const int mstep = b.side < 0 ? (n - 1 - e) : e;
-        const double off = d0 * exp2((double)mstep * lg);
+        double off;
+        if (n == 4) {                                                       // ratio^(mstep / 4) from two square roots
+            const double q = sqrt(sqrt(fmax(far / d0, 1.)));
+            off = d0 * (mstep & 1 ? q : 1.) * (mstep & 2 ? q * q : 1.);
+        } else {
+            const double lg = log2(fmax(far / d0, 1.)) / (double)n;         // the n-th step would land on the bracket end
+            off = d0 * exp2((double)mstep * lg);
+        }
         return fmin(fmax(b.side < 0 ? b.c_est - off : b.c_est + off, b.lo), b.hi);
     }
     return b.lo + (b.hi - b.lo) * ((double)(e + 1) / (double)(n + 1));
 }
 
 // warp-collective (warp 0): lanes >= n pass copies of lane n-1; all lanes end with the same bracket
-__device__ __forceinline__ void rows_update(RowBracket& b, int n, double E, bool high, int y0_pos, double y0_log2)
+__device__ __forceinline__ void rows_update(RowBracket& b, int n, double E, bool high, double y0s, double P)
 {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -442,7 +494,7 @@ __device__ __forceinline__ void rows_update(RowBracket& b, int n, double E, bool
     const double E_last = __shfl_sync(full, E, n - 1), E_prev = __shfl_sync(full, E, n - 2);
     const double a_lo = __shfl_sync(full, E, max(lo_i, 0)), a_hi = __shfl_sync(full, E, min(hi_i, n - 1));
     const double e_lo = lo_i >= 0 ? a_lo : b.lo, e_hi = hi_i < n ? a_hi : b.hi;
-    b.ylog = __shfl_sync(full, y0_log2, lm);
+    b.y_lm = __shfl_sync(full, y0s, lm); b.P_lm = __shfl_sync(full, P, lm);
     b.mode = kSection; b.trusted = false;
     // every sample on one side of the root: one-sided ladder towards the bracket end - unless that end is closer than the samples' own span
     // (it is then a sample of an earlier round: equal sections of what is left)
@@ -455,9 +507,9 @@ __device__ __forceinline__ void rows_update(RowBracket& b, int n, double E, bool
     // must be WELL SEPARATED from the bracketing pair (>= 5 % of its width): after a round whose innermost pair (+-0.45 energyErr) missed
     // the root, that pair is 1e-12 apart and its divided difference is rounding noise
     if (lo_i >= 0 && hi_i < n && e_lo < e_hi) {
-        double Ek[4], yk[4], lgv[4];
+        double Ek[4], yk[4], Pk[4];
         bool ok[4];
-        double ref = -INFINITY;
+        double ref = 0.;
         const double thr = 0.05 * (e_hi - e_lo);
         const unsigned mL = __ballot_sync(full, lane < lo_i && (e_lo - E) >= thr);
         const unsigned mR = __ballot_sync(full, lane > hi_i && lane < n && (E - e_hi) >= thr);
@@ -467,17 +519,25 @@ __device__ __forceinline__ void rows_update(RowBracket& b, int n, double E, bool
             const int idx = pick[q];
             const int src_lane = min(max(idx, 0), n - 1);
             Ek[q] = __shfl_sync(full, E, src_lane);
-            lgv[q] = __shfl_sync(full, y0_log2, src_lane);
-            yk[q] = __shfl_sync(full, y0_pos, src_lane) ? 1. : -1.;
-            ok[q] = idx >= 0 && idx < n && lgv[q] > -1e300 && lgv[q] < 1e300;
-            if (ok[q]) ref = fmax(ref, lgv[q]);
+            yk[q] = __shfl_sync(full, y0s, src_lane);
+            Pk[q] = __shfl_sync(full, P, src_lane);
+            ok[q] = idx >= 0 && idx < n && fabs(yk[q]) <= 1.7e308 && yk[q] != 0. && Pk[q] > 0.;
+            if (ok[q]) ref = fmax(ref, fabs(yk[q]));
         }
+        // y_0 = y0s / P of the usable samples up to one common positive factor (no division, no logarithm): y0s relative to the largest
+        // one, times the P of the OTHER usable samples
+        const double inv = 1. / ref;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) yk[q] = ok[q] ? yk[q] * exp2(lgv[q] - ref) : 0.;      // relative to the largest sample
+        for (int q = 0; q < 4; ++q) {
+            double v = ok[q] ? yk[q] * inv : 0.;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) if (r != q && ok[r]) v *= Pk[r];
+            yk[q] = v;
+        }
         // the bracket ends must be proper samples with opposite signs and distinct energies
         if (ok[1] && ok[2] && yk[1] * yk[2] < 0. && Ek[1] < Ek[2]) {
-            const double slope = (yk[2] - yk[1]) / (Ek[2] - Ek[1]);
-            const double E2 = Ek[1] - yk[1] / slope;                                      // secant
+            const double dE = Ek[2] - Ek[1], dy = yk[2] - yk[1];
+            const double E2 = Ek[1] - yk[1] * (dE / dy);                                  // secant
             // An outer point is usable when it extends the table monotonically in E and in y (inverse interpolation) AND the line through
             // the bracketing pair predicts it within a factor 4: y0(E) = (E - E*) x (a factor that varies exponentially with E) - over a
             // bracket that is still wide the pair's smaller value is ~0 next to the larger one, every interpolant passes through that end
@@ -485,27 +545,27 @@ __device__ __forceinline__ void rows_update(RowBracket& b, int n, double E, bool
             bool lin[4];
 #pragma unroll
             for (int q = 0; q < 4; q += 3) {
-                const double pred = yk[1] + (Ek[q] - Ek[1]) * slope;
-                const double rat = yk[q] / pred;
-                lin[q] = rat > 0.25 && rat < 4.;
+                const double pd = fma(Ek[q] - Ek[1], dy, yk[1] * dE);                     // (the line's prediction) x dE, dE > 0
+                const double yd = yk[q] * dE;
+                lin[q] = (pd > 0.) == (yd > 0.) && fabs(yd) > 0.25 * fabs(pd) && fabs(yd) < 4. * fabs(pd);
             }
             const bool use0 = ok[0] && Ek[0] < Ek[1] && (yk[0] - yk[1]) * (yk[1] - yk[2]) > 0. && lin[0];
             const bool use3 = ok[3] && Ek[3] > Ek[2] && (yk[2] - yk[3]) * (yk[1] - yk[2]) > 0. && lin[3];
             double Eh = E2;
-            if (use0 || use3) {
+            if (use0 || use3) {                                                           // inverse Lagrange interpolation at y = 0: one division per point
                 double num = 0.;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const bool uq = (q == 0) ? use0 : (q == 3 ? use3 : true);
                     if (!uq) continue;
-                    double wgt = Ek[q];
+                    double top = Ek[q], bot = 1.;
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
                         const bool ur = (r == 0) ? use0 : (r == 3 ? use3 : true);
                         if (r == q || !ur) continue;
-                        wgt *= (0. - yk[r]) / (yk[q] - yk[r]);
+                        top *= -yk[r]; bot *= yk[q] - yk[r];
                     }
-                    num += wgt;
+                    num += top / bot;
                 }
                 Eh = num;
             }
@@ -530,6 +590,9 @@ __global__ void __launch_bounds__(32 * NW, NW == kRowWarps ? 3 : 1) search_rows_
 {
     extern __shared__ __align__(16) unsigned char rows_smem[];
     __shared__ RowShared sh;
+#ifdef DFT_ROWS_DEBUG
+    long long t_mark = clock64();
+#endif
     const unsigned full = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int k = blockIdx.x;
@@ -543,7 +606,7 @@ __global__ void __launch_bounds__(32 * NW, NW == kRowWarps ? 3 : 1) search_rows_
     const unsigned tiles_smem = (unsigned)__cvta_generic_to_shared(rows_smem);
     RowBracket b;
     b.lo = -Z * Z - 1.; b.hi = kTopEnergy;                // DFTAtom.cpp:407,499
-    b.ylog = 0.; b.side = 0; b.trusted = false;
+    b.y_lm = 1.; b.P_lm = 1.; b.side = 0; b.trusted = false;
     const SearchState s0 = ss[k];
     b.mode = (warm_start && s0.pad == 1) ? kLadder : kSection;
     // first ladder: the levels move geometrically from one SCF step to the next (linear mixing); centre = previous eigenvalue + last
@@ -555,11 +618,18 @@ __global__ void __launch_bounds__(32 * NW, NW == kRowWarps ? 3 : 1) search_rows_
     b.inner = (s0.dn_lo > 0.) ? fmin(fmax(2. * s0.dn_lo, 0.45 * kEnergyTol), 0.25 * b.radius) : 0.125 * b.radius;
     const double c_first = b.c_est;
     long long steps = 0;
-    int rounds = 0, sweeps = 0;
+    int rounds = 0, sweeps = 0, hint = -1;
 
 #ifdef DFT_ROWS_DEBUG
     __shared__ double dbg_hist[16][8];
+    const long long t_kernel0 = clock64();
 #endif
+#ifdef DFT_ROWS_DEBUG
+#define ROWS_KCLK(i) do { if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd((unsigned long long*)&g_rows_clk[i], (unsigned long long)(t_ - t_mark)); t_mark = t_; } } while (0)
+#else
+#define ROWS_KCLK(i) do { } while (0)
+#endif
+    ROWS_KCLK(10);                                      // prologue
     for (int round = 0; round < 96; ++round) {
         if (warp == 0) {
             const bool go = bracket_open(b.lo, b.hi);
@@ -570,24 +640,37 @@ __global__ void __launch_bounds__(32 * NW, NW == kRowWarps ? 3 : 1) search_rows_
             }
 #endif
             const int NG = b.mode != kLadder ? ((cfg >> 8) & 15) : (b.trusted ? ((cfg >> 4) & 15) : (cfg & 15));      // (NG divides NW: 1, 2 or 4)
-            if (lane == 0) { sh.go = go; sh.n_groups = NG; }
+            if (lane == 0) { sh.go = go; sh.n_groups = NG; sh.use_hint = round > 0 && (b.hi - b.lo) < 0.02 * fabs(b.lo); }
             const int n = NG * kRowE;
             if (lane < n) sh.E[lane] = rows_sample(b, lane, n);
         }
         __syncthreads();
         if (!sh.go) break;
         const int n = sh.n_groups * kRowE;
-        const RowOut r = rows_round(g, atab, ll1, ob.l, ob.want, sh, tiles_smem, warp, lane, NW);
+        if (!sh.use_hint) hint = -1;
+        ROWS_KCLK(9);                                   // sample + barrier
+        const RowOut r = rows_round(g, atab, ll1, ob.l, ob.want, sh, tiles_smem, warp, lane, NW, &hint);
+        ++rounds; sweeps += n;
+#ifdef DFT_ROWS_DEBUG
+        if (threadIdx.x == 0) t_mark = clock64();
+#endif
         if (warp == 0) {
             const double E = sh.E[min(lane, n - 1)];
             if (lane < n) steps += r.start - 1;
-            rows_update(b, n, E, r.cfull > ob.want + (r.d_first < 0. ? 1 : 0), r.y0_pos, r.y0_log2);
+            rows_update(b, n, E, r.cfull > ob.want + (r.d_first < 0. ? 1 : 0), r.y0s, r.P);
         }
-        ++rounds; sweeps += n;
+#ifdef DFT_ROWS_DEBUG
+        if (b.c_est == 1.2345e-300 && b.lo == 7. && b.hi == 8. && b.radius == 9.) sh.go = 2;
+#endif
+        ROWS_KCLK(8);                                   // bracket update
         __syncthreads();                               // sh.E / sh.go are rewritten at the top
+#ifdef DFT_ROWS_DEBUG
+        if (threadIdx.x == 0) t_mark = clock64();
+#endif
     }
 #ifdef DFT_ROWS_DEBUG
-    if (threadIdx.x == 0 && k == 0 && getenv_dbg_clk(work)) printf("rows clk: pre %lld prefetch+carry %lld main %lld scan %lld post %lld (sum over CTAs so far)\n", g_rows_clk[0], g_rows_clk[1], g_rows_clk[2], g_rows_clk[3], g_rows_clk[4]);
+    if (threadIdx.x == 0) { atomicAdd((unsigned long long*)&g_rows_clk[5], (unsigned long long)(clock64() - t_kernel0)); atomicAdd((unsigned long long*)&g_rows_clk[6], (unsigned long long)rounds); atomicAdd((unsigned long long*)&g_rows_clk[7], 1ULL); }
+    if (threadIdx.x == 0 && k == 0 && getenv_dbg_clk(work)) printf("rows clk: pre %lld prefetch+carry %lld main %lld scan %lld post %lld | update %lld sample+barrier %lld prologue %lld | loop total %lld rounds %lld solves %lld (sum over CTAs so far)\n", g_rows_clk[0], g_rows_clk[1], g_rows_clk[2], g_rows_clk[3], g_rows_clk[4], g_rows_clk[8], g_rows_clk[9], g_rows_clk[10], g_rows_clk[5], g_rows_clk[6], g_rows_clk[7]);
     if (warp == 0 && lane == 0 && rounds >= 6 && s0.pad == 1 && work && atomicAdd(work + 5, 1ULL) % 97 == 0) {
         printf("orb %d l %d want %d e_prev %.12g shifts %.3e %.3e miss_prev %.3e -> E %.12g in %d rounds\n", k, ob.l, ob.want, e_prev, sh1, sh2, s0.dn_lo, b.lo, rounds);
         for (int r = 0; r < min(rounds, 16); ++r)
@@ -599,8 +682,9 @@ __global__ void __launch_bounds__(32 * NW, NW == kRowWarps ? 3 : 1) search_rows_
         if (lane == 0) {
             SearchState s = s0;
             s.bot = b.lo; s.top = b.hi; s.E = b.lo;                              // level.E = BottomEnergy, DFTAtom.cpp:534
-            s.y0_log2 = b.ylog;
-            s.converged = (b.hi - b.lo < kEnergyTol) && (b.ylog < 49.828921423310435); // DFTAtom.cpp:528
+            const double ylog = rows_ylog(b.y_lm, b.P_lm);
+            s.y0_log2 = ylog;
+            s.converged = (b.hi - b.lo < kEnergyTol) && (ylog < 49.828921423310435);   // DFTAtom.cpp:528
             s.stage = 3;
             s.up_hi = s0.pad == 1 ? s0.up_lo : 0.;                               // the last two shifts of the level
             s.up_lo = s0.pad == 1 ? b.lo - e_prev : 0.5 * fabs(b.lo) + 1.;         // (no shift yet: the scale the level may move by)
@@ -661,7 +745,7 @@ __global__ void __launch_bounds__(32 * kRowWarps, 3) numerov_lanes_rows_kernel(G
             const bool mine = s_same ? (lane < n) : (lane == 0);
             if (mine && k < a.n_lanes) {
                 if (a.y0_sign) a.y0_sign[k] = r.y0_pos;
-                if (a.y0_log2) a.y0_log2[k] = r.y0_log2;
+                if (a.y0_log2) a.y0_log2[k] = rows_ylog(r.y0s, r.P);
                 if (a.count) a.count[k] = r.cfull;
             }
         }
