@@ -110,6 +110,8 @@ struct Knobs {
     int adaptive_mixing = 0;   // opt-in: per-atom damping raised when Etotal sloshes with period 2 (beyond the reference; default: its fixed linear mixing)
     int step_cap = 0;          // > 0: lower the SCF step cap (100 LDA / 150 LSDA, DFTAtom.cpp:396,908) to this many steps (tests: with run_to_cap, run exactly as long as the reference did)
     int use_graph = 1;         // SCF steps are replayed from a captured CUDA graph (one graph launch per step) instead of 5+ kernel launches
+    int graph_phases = 1;      // the graph loop is a chain of WHILE nodes, one per range of SCF steps between the step indices at which a kernel shape changes
+                               // (rows_wide_from_step, match_win_until_step): each body holds only the shapes of its range.  0: one WHILE node, every shape in it
 };
 
 struct dftatom_ctx {
@@ -351,6 +353,7 @@ int dftatom_set_option(dftatom_ctx* c, const char* key, double value)
     else if (k == "step_cap") c->k.step_cap = std::max(0, (int)value);
     else if (k == "run_to_cap") c->k.run_to_cap = value != 0.;
     else if (k == "use_graph") c->k.use_graph = value != 0.;
+    else if (k == "graph_phases") c->k.graph_phases = value != 0.;
     else { set_error("unknown option " + k); return DFTATOM_E_ARG; }
     return 0;
 }
@@ -684,12 +687,12 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
     int steps_enqueued = 0;
     const int lag = 2;
     // one SCF step = five kernel classes enqueued on the stream; nothing in it touches the host
-    auto enqueue_step = [&](int sp, long long& nl) {
+    // sp: the SCF step being enqueued; [sp, sp_end): the steps these launches may be executed at (a graph body is replayed for a range of steps)
+    auto enqueue_step = [&](int sp, int sp_end, long long& nl) {
         nvtxRangePushA("dftatom:scf_step");
         begin_phase(DFTATOM_K_SEARCH);
         if (c->k.search_mode == 0 && c->k.search_kernel == 0 && !g.uniform) {
-            launch_search_rows(g, b.atab, b.atoms, b.orbs, b.astate, b.ss, n_orbs, d_work + DFTATOM_K_SEARCH, c->k.warm_start, c->k.rows_cfg, c->k.rows_wide_from_step, st);
-            ++nl;
+            nl += launch_search_rows(g, b.atab, b.atoms, b.orbs, b.astate, b.ss, n_orbs, d_work + DFTATOM_K_SEARCH, c->k.warm_start, c->k.rows_cfg, c->k.rows_wide_from_step, sp, sp_end, st);
         } else if (c->k.search_mode == 0) {
             // two shapes of the same search: serial-in-r (one warp per orbital) while many orbitals are active, parallel-in-r
             // (one cluster per orbital) once few are left.  Both are enqueued; the device-side count of active orbitals
@@ -711,13 +714,12 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
         if (c->k.search_mode != 0) for (int r = 0; r < rounds; ++r) { launch_search_round(g, b.atab, b.orbs, b.astate, b.ss, n_orbs, d_work + DFTATOM_K_SEARCH, st); ++nl; }
         end_phase();
         begin_phase(DFTATOM_K_MATCH);
-        if (c->k.match_mode == 0) launch_match_cta(g, b.atab, b.orbs, b.astate, b.ss, b.psi, b.match_pt, b.inv_norm, n_orbs, c->k.match_win_until_step, c->k.match_win_nodes, st);
+        if (c->k.match_mode == 0) nl += launch_match_cta(g, b.atab, b.orbs, b.astate, b.ss, b.psi, b.match_pt, b.inv_norm, n_orbs, c->k.match_win_until_step, c->k.match_win_nodes, sp, sp_end, st);
         else {                                              // validation paths: warp-per-orbital / reference-shaped serial solution
             if (c->k.match_mode == 2) launch_match_seg(g, b.atab, b.orbs, b.astate, b.ss, b.psi, b.match_pt, n_orbs, st);
             else launch_match(g, b.atab, b.orbs, b.astate, b.ss, b.psi, b.match_pt, n_orbs, st);
-            launch_orbital_norms(g, b, st); ++nl;
+            launch_orbital_norms(g, b, st); nl += 2;
         }
-        ++nl;
         end_phase();
         begin_phase(DFTATOM_K_DENSITY);
         launch_density_update(g, b, st); ++nl;
@@ -740,26 +742,41 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
     bool graph_done = false;
     if (graph_ok) {
         const int n_cold = std::min(max_steps, std::max(std::max(std::max(0, c->k.warm_after), c->k.recold_at + 1), direct_ok ? c->k.direct_after : 0));
-        for (int sp = 0; sp < n_cold; ++sp) { enqueue_step(sp, launches); ++steps_enqueued; }
+        for (int sp = 0; sp < n_cold; ++sp) { enqueue_step(sp, sp + 1, launches); ++steps_enqueued; }
         if (n_cold < max_steps) {
-            cudaGraph_t graph = nullptr, body = nullptr;
+            // phases: the ranges of SCF steps between the step indices at which a kernel shape hands over to another one
+            std::vector<int> cut{ n_cold };
+            if (c->k.graph_phases && c->k.search_kernel == 0 && !g.uniform) {
+                for (int s_ : { c->k.rows_wide_from_step, c->k.match_win_until_step })
+                    if (s_ > n_cold && s_ < max_steps && std::find(cut.begin(), cut.end(), s_) == cut.end()) cut.push_back(s_);
+                std::sort(cut.begin(), cut.end());
+            }
+            cut.push_back(1 << 30);
+            ScfLoopPhases ph{};
+            ph.n = (int)cut.size() - 1;                 // <= 3
+            cudaGraph_t graph = nullptr;
             cudaGraphExec_t exec = nullptr;
-            cudaGraphConditionalHandle handle;
-            long long per_iter = 0;
-            bool ok = cudaGraphCreate(&graph, 0) == cudaSuccess && cudaGraphConditionalHandleCreate(&handle, graph, 1, cudaGraphCondAssignDefault) == cudaSuccess;
-            if (ok) {
+            long long per_iter[4] = {};
+            bool ok = cudaGraphCreate(&graph, 0) == cudaSuccess;
+            // every handle first: the condition kernel of a phase also switches the later phases off
+            for (int p_ = 0; ok && p_ < ph.n; ++p_) ok = cudaGraphConditionalHandleCreate(&ph.handle[p_], graph, 1, cudaGraphCondAssignDefault) == cudaSuccess;
+            cudaGraphNode_t prev_node = nullptr;
+            for (int p_ = 0; ok && p_ < ph.n; ++p_) {
                 cudaGraphNodeParams np = {};
                 np.type = cudaGraphNodeTypeConditional;
-                np.conditional.handle = handle; np.conditional.type = cudaGraphCondTypeWhile; np.conditional.size = 1;
+                np.conditional.handle = ph.handle[p_]; np.conditional.type = cudaGraphCondTypeWhile; np.conditional.size = 1;
                 cudaGraphNode_t node;
-                ok = cudaGraphAddNode(&node, graph, nullptr, 0, &np) == cudaSuccess;
-                if (ok) body = np.conditional.phGraph_out[0];
+                ok = cudaGraphAddNode(&node, graph, prev_node ? &prev_node : nullptr, prev_node ? 1 : 0, &np) == cudaSuccess;
+                if (!ok) break;
+                prev_node = node;
+                cudaGraph_t body = np.conditional.phGraph_out[0];
+                ok = cudaStreamBeginCaptureToGraph(st, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+                if (ok) {
+                    enqueue_step(cut[p_], cut[p_ + 1], per_iter[p_]);
+                    launch_scf_loop_condition(ph, p_, n_cold, cut[p_ + 1], b.n_active, d_work + 6, st); ++per_iter[p_];
+                    ok = cudaStreamEndCapture(st, nullptr) == cudaSuccess;
+                }
             }
-            if (ok && cudaStreamBeginCaptureToGraph(st, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-                enqueue_step(n_cold, per_iter);
-                launch_scf_loop_condition(handle, b.n_active, d_work + 6, st); ++per_iter;
-                ok = cudaStreamEndCapture(st, nullptr) == cudaSuccess;
-            } else ok = false;
             ok = ok && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
             th2 = now();
             if (ok) {
@@ -770,7 +787,10 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
                 DFT_CHECK(cudaStreamSynchronize(st));
                 unsigned long long iters = 0;
                 DFT_CHECK(cudaMemcpy(&iters, d_work + 6, sizeof(iters), cudaMemcpyDeviceToHost));
-                launches += per_iter * (long long)iters;
+                for (int p_ = 0; p_ < ph.n; ++p_) {        // iterations of phase p: the steps of [cut[p], cut[p + 1]) that were executed
+                    const long long first = cut[p_] - n_cold, last = std::min<long long>((long long)iters, (long long)cut[p_ + 1] - n_cold);
+                    if (last > first) launches += per_iter[p_] * (last - first);
+                }
                 steps_enqueued += (int)iters;
                 c->last_graph_iterations = (long long)iters;
             }
@@ -780,7 +800,7 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
         } else graph_done = true;
     }
     for (int sp = graph_done ? max_steps : 0; sp < max_steps; ++sp) {
-        enqueue_step(sp, launches);
+        enqueue_step(sp, sp + 1, launches);
         DFT_CHECK(cudaMemcpyAsync(&c->h_active[sp], b.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
         DFT_CHECK(cudaEventRecord(step_ev[sp], st));
         ++steps_enqueued;
@@ -1061,7 +1081,7 @@ int dftatom_level_search(dftatom_ctx* c, const double* V, int levels, double del
     if ((rc = setup_single(c, g, V, Z, orbs, &da, &ds, &dorb, &dss, &datab))) return rc;
     launch_search_init(g, da, ds, dorb, dss, n_levels, st);
     const int rounds = search_rounds_needed(Z);
-    if (c->k.search_mode == 0 && c->k.search_kernel == 0 && !g.uniform) launch_search_rows(g, datab, da, dorb, ds, dss, n_levels, nullptr, 0, c->k.rows_cfg, 0, st);
+    if (c->k.search_mode == 0 && c->k.search_kernel == 0 && !g.uniform) launch_search_rows(g, datab, da, dorb, ds, dss, n_levels, nullptr, 0, c->k.rows_cfg, 0, 0, 1 << 30, st);
     else if (c->k.search_mode == 0 && c->segments(g.N) > 1) launch_search_seg(g, datab, da, dorb, ds, dss, n_levels, nullptr, c->segments(g.N), nullptr, 0, 0, st);
     else if (c->k.search_mode == 0) launch_search_fused(g, datab, da, dorb, ds, dss, n_levels, nullptr, nullptr, 0, 0, st);
     else for (int r = 0; r < rounds; ++r) launch_search_round(g, datab, dorb, ds, dss, n_levels, nullptr, st);
@@ -1092,7 +1112,7 @@ int dftatom_numerov_orbital(dftatom_ctx* c, const double* V, int levels, double 
     // single-atom ScfBuffers so that density_update's normalisation path is the one exercised
     if ((rc = c->psi.ensure(sizeof(double) * N)) || (rc = c->match_pt.ensure(sizeof(int)))) return rc;
     if ((rc = c->inv_norm.ensure(sizeof(double)))) return rc;
-    if (c->k.match_mode == 0) launch_match_cta(g, datab, dorb, ds, dss, c->psi.as<double>(), c->match_pt.as<int>(), c->inv_norm.as<double>(), 1, 0, 0, st);
+    if (c->k.match_mode == 0) launch_match_cta(g, datab, dorb, ds, dss, c->psi.as<double>(), c->match_pt.as<int>(), c->inv_norm.as<double>(), 1, 0, 0, 0, 1 << 30, st);
     else if (c->k.match_mode == 2) launch_match_seg(g, datab, dorb, ds, dss, c->psi.as<double>(), c->match_pt.as<int>(), 1, st);
     else launch_match(g, datab, dorb, ds, dss, c->psi.as<double>(), c->match_pt.as<int>(), 1, st);
     std::vector<double> y(N), sq(N), wj(N);

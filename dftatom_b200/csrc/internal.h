@@ -118,8 +118,8 @@ void launch_search_seg(const GridDev& g, const double* atab, const AtomDev* atom
 // lanes through the parallel-in-r sweep: one cluster per 32 lanes sharing (tab, l); segments = 4 x cluster size (<= 32)
 void launch_numerov_lanes_seg(const GridDev& g, const NumerovLaneArgs& a, int segments, cudaStream_t st);
 // production search (numerov_rows.cu): lanes across the radial grid, 4 trial energies per thread, one CTA of 4 warps per orbital
-void launch_search_rows(const GridDev& g, const double* atab, const AtomDev* atoms, const OrbitalDev* orbs, const AtomState* astate,
-                        SearchState* ss, int n_orbs, unsigned long long* work, int warm_start, int cfg, int wide_from_step, cudaStream_t st);
+int launch_search_rows(const GridDev& g, const double* atab, const AtomDev* atoms, const OrbitalDev* orbs, const AtomState* astate,
+                        SearchState* ss, int n_orbs, unsigned long long* work, int warm_start, int cfg, int wide_from_step, int step_lo, int step_hi, cudaStream_t st);
 // lanes through the same sweep: one CTA per 4 n_groups consecutive lanes (n_groups = 1, 2, 4)
 void launch_numerov_lanes_rows(const GridDev& g, const NumerovLaneArgs& a, int n_groups, cudaStream_t st);
 int rows_init_device();
@@ -132,8 +132,8 @@ void launch_match(const GridDev& g, const double* atab, const OrbitalDev* orbs, 
 void launch_match_seg(const GridDev& g, const double* atab, const OrbitalDev* orbs, const AtomState* astate, const SearchState* ss,
                       double* psi, int* match_pt, int n_orbs, cudaStream_t st);
 
-void launch_match_cta(const GridDev& g, const double* atab, const OrbitalDev* orbs, const AtomState* astate, const SearchState* ss,
-                      double* psi, int* match_pt, double* inv_norm, int n_orbs, int win_until_step, int win_nodes, cudaStream_t st);
+int launch_match_cta(const GridDev& g, const double* atab, const OrbitalDev* orbs, const AtomState* astate, const SearchState* ss,
+                      double* psi, int* match_pt, double* inv_norm, int n_orbs, int win_until_step, int win_nodes, int step_lo, int step_hi, cudaStream_t st);
 
 // potential -> a-table (a_i = 1 - (2K_i V_i + δ²/4)/12), n_tabs rows
 void launch_build_atab(const GridDev& g, const double* vpot, double* atab, int n_tabs, cudaStream_t st);
@@ -305,7 +305,8 @@ struct ScfBuffers {
     int run_to_cap;   // != 0: the stop test is recorded in dftatom_step.stop_criterion_met but never ends the SCF
     int adaptive_mixing;  // != 0: per-atom damping is raised when Etotal sloshes with period 2 (scf.cu); 0: the reference's fixed linear mixing
 };
-void launch_scf_loop_condition(cudaGraphConditionalHandle handle, const int* n_active, unsigned long long* iterations, cudaStream_t st);
+struct ScfLoopPhases { cudaGraphConditionalHandle handle[4]; int n; };      // the WHILE nodes of the SCF loop, one per phase (a range of SCF steps), in order
+void launch_scf_loop_condition(const ScfLoopPhases& ph, int phase, int step_first, int step_end, const int* n_active, unsigned long long* iterations, cudaStream_t st);
 void launch_gather_last_steps(const ScfBuffers& b, dftatom_step* out, cudaStream_t st);
 // increment form of the warm-started Poisson solves (scf.cu): dS = r 4 pi K (rho - rho_prev), dU = 0, rho_prev = rho (dS == NULL: only
 // the last); U += dU

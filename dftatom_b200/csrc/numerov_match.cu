@@ -782,22 +782,32 @@ static size_t match_win_bytes(int win_nodes) { return ((size_t)win_nodes + 2 + (
 // win_until_step > 0 (grids that fit one window): while an atom's SCF step counter is below it, its orbitals are solved by the windowed kernel
 // with small windows (several CTAs per SM: throughput while most atoms are still iterating), afterwards by the one-window kernel (latency);
 // both are launched, the atom's own step counter decides - its records do not depend on what else is in the batch
-void launch_match_cta(const GridDev& g, const double* atab, const OrbitalDev* orbs, const AtomState* astate, const SearchState* ss,
-                      double* psi, int* match_pt, double* inv_norm, int n_orbs, int win_until_step, int win_nodes, cudaStream_t st)
+int launch_match_cta(const GridDev& g, const double* atab, const OrbitalDev* orbs, const AtomState* astate, const SearchState* ss,
+                     double* psi, int* match_pt, double* inv_norm, int n_orbs, int win_until_step, int win_nodes, int step_lo, int step_hi, cudaStream_t st)
 {
+    int n_launch = 0;
+    // [step_lo, step_hi): the SCF steps this launch can be executed at; a shape whose step window misses it is not launched
     const size_t bytes = ((size_t)g.N + (size_t)g.N / 32 + 8) * sizeof(double);
     if (bytes <= kMatchCtaMaxBytes) {
         int lo = 0;
         if (win_until_step > 0 && win_nodes >= 1024 && win_nodes < g.N) {
-            match_win_kernel<<<n_orbs, kMT, match_win_bytes(win_nodes), st>>>(g, atab, orbs, astate, const_cast<SearchState*>(ss), psi, match_pt, inv_norm, n_orbs,
-                                                                          win_nodes, 0, win_until_step);
+            if (step_lo < win_until_step) {
+                match_win_kernel<<<n_orbs, kMT, match_win_bytes(win_nodes), st>>>(g, atab, orbs, astate, const_cast<SearchState*>(ss), psi, match_pt, inv_norm, n_orbs,
+                                                                              win_nodes, 0, win_until_step);
+                ++n_launch;
+            }
             lo = win_until_step;
         }
-        match_cta_kernel<true><<<n_orbs, kMT, bytes, st>>>(g, atab, orbs, astate, const_cast<SearchState*>(ss), psi, match_pt, inv_norm, n_orbs, lo, 1 << 30);
+        if (step_hi > lo) {
+            match_cta_kernel<true><<<n_orbs, kMT, bytes, st>>>(g, atab, orbs, astate, const_cast<SearchState*>(ss), psi, match_pt, inv_norm, n_orbs, lo, 1 << 30);
+            ++n_launch;
+        }
     } else {
         match_win_kernel<<<n_orbs, kMT, match_win_bytes(kWinNodes), st>>>(g, atab, orbs, astate, const_cast<SearchState*>(ss), psi, match_pt, inv_norm, n_orbs,
                                                                       kWinNodes, 0, 1 << 30);
+        ++n_launch;
     }
+    return n_launch;
 }
 
 void launch_match_seg(const GridDev& g, const double* atab, const OrbitalDev* orbs, const AtomState* astate, const SearchState* ss,

@@ -772,14 +772,22 @@ int rows_init_device()
 // wide_from_step > 0: an atom whose SCF step counter has reached it is searched by the 8-warp shape (256 radial segments per orbital: half the
 // depth of a round - the latency shape for the steps where few atoms are left), before that by the 4-warp shape (3 CTAs per SM: throughput); both are
 // launched, the atom's own step counter decides (its records do not depend on what else is in the batch).  0: the 4-warp shape at every step.
-void launch_search_rows(const GridDev& g, const double* atab, const AtomDev* atoms, const OrbitalDev* orbs, const AtomState* astate,
-                        SearchState* ss, int n_orbs, unsigned long long* work, int warm_start, int cfg, int wide_from_step, cudaStream_t st)
+int launch_search_rows(const GridDev& g, const double* atab, const AtomDev* atoms, const OrbitalDev* orbs, const AtomState* astate,
+                       SearchState* ss, int n_orbs, unsigned long long* work, int warm_start, int cfg, int wide_from_step, int step_lo, int step_hi, cudaStream_t st)
 {
+    int n_launch = 0;
+    // [step_lo, step_hi): the SCF steps this launch can be executed at (all atoms of a batch step together); a shape whose window misses it is not launched
     const int split = wide_from_step > 0 ? wide_from_step : (1 << 30);
-    search_rows_kernel<kRowWarps><<<n_orbs, 32 * kRowWarps, rows_smem_bytes(kRowWarps), st>>>(g, atab, atoms, orbs, astate, ss, n_orbs, work, warm_start, cfg, 0, split);
-    if (wide_from_step > 0)
+    if (step_lo < split) {
+        search_rows_kernel<kRowWarps><<<n_orbs, 32 * kRowWarps, rows_smem_bytes(kRowWarps), st>>>(g, atab, atoms, orbs, astate, ss, n_orbs, work, warm_start, cfg, 0, split);
+        ++n_launch;
+    }
+    if (wide_from_step > 0 && step_hi > split) {
         search_rows_kernel<kRowWarpsWide><<<n_orbs, 32 * kRowWarpsWide, rows_smem_bytes(kRowWarpsWide), st>>>(g, atab, atoms, orbs, astate, ss, n_orbs, work, warm_start,
                                                                                                            cfg, split, 1 << 30);
+        ++n_launch;
+    }
+    return n_launch;
 }
 
 }  // namespace dft

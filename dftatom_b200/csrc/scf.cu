@@ -532,16 +532,19 @@ void launch_poisson_delta_apply(const GridDev& g, int n_dens, long long ld, doub
     poisson_delta_apply_kernel<<<dim3((g.N + 255) / 256, n_dens), 256, 0, st>>>(g.N, ld, U, dU, skip, skip_stride_bytes);
 }
 
-// Last node of the body of the SCF loop's CUDA-graph WHILE node: the loop goes on while some atom is still iterating
-// (n_active is kept up to date by potential_energy_kernel)
-__global__ void scf_loop_condition_kernel(cudaGraphConditionalHandle handle, const int* n_active, unsigned long long* iterations)
+// Last node of the body of a phase of the SCF loop (one CUDA-graph WHILE node per phase = range of SCF steps [.., step_end), executed in
+// order): the phase goes on while some atom is still iterating (n_active is kept up to date by potential_energy_kernel) and the next step
+// is still its own; once no atom is left the later phases are switched off too.  step_first: the SCF step of the first graph iteration.
+__global__ void scf_loop_condition_kernel(ScfLoopPhases ph, int phase, int step_first, int step_end, const int* n_active, unsigned long long* iterations)
 {
-    *iterations += 1ULL;
-    cudaGraphSetConditional(handle, *n_active > 0 ? 1u : 0u);
+    const unsigned long long it = (*iterations += 1ULL);
+    const bool active = *n_active > 0;
+    cudaGraphSetConditional(ph.handle[phase], (active && (long long)step_first + (long long)it < (long long)step_end) ? 1u : 0u);
+    if (!active) for (int q = phase + 1; q < ph.n; ++q) cudaGraphSetConditional(ph.handle[q], 0u);
 }
-void launch_scf_loop_condition(cudaGraphConditionalHandle handle, const int* n_active, unsigned long long* iterations, cudaStream_t st)
+void launch_scf_loop_condition(const ScfLoopPhases& ph, int phase, int step_first, int step_end, const int* n_active, unsigned long long* iterations, cudaStream_t st)
 {
-    scf_loop_condition_kernel<<<1, 1, 0, st>>>(handle, n_active, iterations);
+    scf_loop_condition_kernel<<<1, 1, 0, st>>>(ph, phase, step_first, step_end, n_active, iterations);
 }
 
 // last "Step:" record of every atom, compact (what dftatom_solve_batch downloads when the caller did not ask for the steps)

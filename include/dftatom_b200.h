@@ -136,6 +136,10 @@ const char* dftatom_version(void);
  *                   atom is still iterating") is set on the device (cudaGraphSetConditional): no host round trip between SCF steps.  Not used
  *                   with "profile" (per-class event timing needs host-side events between the launches), the validation search / match modes
  *                   and the cooperative team-mode Poisson kernel (one to three atoms on grids above 16385 nodes); 0 = host-driven loop.
+ *   "graph_phases" (default 1) the graph loop is a chain of WHILE nodes, one per range of SCF steps between the step indices at which a
+ *                   kernel shape hands over to another one ("rows_wide_from_step", "match_win_until_step"; all atoms of a batch step
+ *                   together): every body holds only the shapes of its own range, no launch that returns at once.  0 = one WHILE node
+ *                   whose body launches every shape at every step.  Same records either way.
  *   "step_cap"     (default 0 = the reference's caps, 100 LDA / 150 LSDA steps) a lower cap on the SCF steps of every atom of the batch
  *   "warm_vcycles" (default 7) / "warm_after" (default 1): from SCF step warm_after on the Poisson solve is warm_vcycles V-cycles in increment
  *                   form (A dU = -r 4 pi K (rho - rho_prev) from dU = 0, U += dU; "delta_poisson" 0 = iterate on U itself) instead of the full

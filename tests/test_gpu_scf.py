@@ -155,8 +155,9 @@ def test_kernel_shapes_agree(ctx):
     variants = [{"search_kernel": 1}, {"search_kernel": 1, "r_segments": 0}, {"search_kernel": 1, "seg_threshold": 30}, {"search_kernel": 1, "r_segments": 32},
                 {"search_kernel": 1, "r_segments": 8}, {"rows_cfg": 0x412}, {"rows_cfg": 0x222}, {"warm_vcycles": 0}, {"match_mode": 2},
                 {"warm_poisson": 0}, {"coarse_exact": 0}, {"warm_poisson": 0, "coarse_exact": 0}, {"warm_until_step": 0}, {"warm_until_step": 12},
-                {"use_graph": 0}, {"match_win_until_step": 0}, {"match_win_until_step": 100, "match_win_nodes": 2048}, {"direct_poisson": 0}, {"direct_after": 1}, {"rows_wide_from_step": 0}, {"rows_wide_from_step": 1}, {"stream_groups": 1}]
-    defaults = {"r_segments": -1, "seg_threshold": 2400, "warm_vcycles": 7, "match_mode": 0, "search_kernel": 0, "rows_cfg": 0x111, "warm_poisson": 1,
+                {"use_graph": 0}, {"match_win_until_step": 0}, {"match_win_until_step": 100, "match_win_nodes": 2048}, {"direct_poisson": 0}, {"direct_after": 1}, {"rows_wide_from_step": 0}, {"rows_wide_from_step": 1}, {"stream_groups": 1},
+                {"graph_phases": 0}, {"rows_wide_from_step": 10, "match_win_until_step": 20}]
+    defaults = {"graph_phases": 1, "r_segments": -1, "seg_threshold": 2400, "warm_vcycles": 7, "match_mode": 0, "search_kernel": 0, "rows_cfg": 0x111, "warm_poisson": 1,
                 "coarse_exact": 1, "warm_until_step": 32, "use_graph": 1, "match_win_until_step": 32, "match_win_nodes": 8192, "stream_groups": 3, "direct_poisson": 1, "direct_after": 4, "rows_wide_from_step": 32}
     for v in variants:
         for k_, x in v.items():
@@ -172,6 +173,36 @@ def test_kernel_shapes_agree(ctx):
             for k in range(n):
                 assert abs(r.steps[k].Etotal - b.steps[k].Etotal) < 2e-6, (v, k)
                 np.testing.assert_allclose([x for ch in r.steps[k].E for x in ch], [x for ch in b.steps[k].E for x in ch], rtol=0, atol=2e-7)
+
+
+def test_scf_loop_forms_are_bit_identical(ctx):
+    """The SCF loop as a chain of CUDA-graph WHILE nodes (one per range of steps between two kernel-shape hand-overs: the default), as ONE
+    WHILE node whose body launches every shape at every step, and as the host-driven loop: the same kernels on the same data in the same
+    order - every step record identical to the last bit.  The batch crosses both hand-over steps (10, 20 here; Cu runs 50+ steps)."""
+    opts = [D.Options(Z, 12, 20.0, 0.001, 0.5, 0) for Z in (3, 10, 29, 47)]
+    for k_, x in (("rows_wide_from_step", 10), ("match_win_until_step", 20)):
+        ctx.set_option(k_, x)
+    try:
+        runs = []
+        for v in ({}, {"graph_phases": 0}, {"use_graph": 0}):
+            for k_, x in v.items():
+                ctx.set_option(k_, x)
+            try:
+                runs.append(ctx.solve_batch(opts))
+                if v.get("use_graph", 1):
+                    assert ctx.last_graph_iterations() > 15
+            finally:
+                for k_ in v:
+                    ctx.set_option(k_, 1)
+    finally:
+        ctx.set_option("rows_wide_from_step", 32)
+        ctx.set_option("match_win_until_step", 32)
+    assert max(r.n_steps for r in runs[0]) > 21          # (both hand-overs were crossed)
+    for other in runs[1:]:
+        for r, b in zip(other, runs[0]):
+            assert r.n_steps == b.n_steps and r.finished == b.finished
+            assert [s.Etotal for s in r.steps] == [s.Etotal for s in b.steps]
+            assert [list(ch) for s in r.steps for ch in s.E] == [list(ch) for s in b.steps for ch in s.E]
 
 
 def test_stream_poisson_agrees(ctx):
