@@ -110,6 +110,8 @@ struct Knobs {
     int adaptive_mixing = 0;   // opt-in: per-atom damping raised when Etotal sloshes with period 2 (beyond the reference; default: its fixed linear mixing)
     int step_cap = 0;          // > 0: lower the SCF step cap (100 LDA / 150 LSDA, DFTAtom.cpp:396,908) to this many steps (tests: with run_to_cap, run exactly as long as the reference did)
     int use_graph = 1;         // SCF steps are replayed from a captured CUDA graph (one graph launch per step) instead of 5+ kernel launches
+    int search_predict = 1;    // rows search: first ladders from what the first SCF steps are known to do (hydrogenic levels of the initial uniform-sphere
+                               // potential at step 0, one-sided ladder at step 1, default decay ratio at step 2, miss scaled with the shifts later)
     int graph_phases = 1;      // the graph loop is a chain of WHILE nodes, one per range of SCF steps between the step indices at which a kernel shape changes
                                // (rows_wide_from_step, match_win_until_step): each body holds only the shapes of its range.  0: one WHILE node, every shape in it
 };
@@ -354,6 +356,7 @@ int dftatom_set_option(dftatom_ctx* c, const char* key, double value)
     else if (k == "run_to_cap") c->k.run_to_cap = value != 0.;
     else if (k == "use_graph") c->k.use_graph = value != 0.;
     else if (k == "graph_phases") c->k.graph_phases = value != 0.;
+    else if (k == "search_predict") c->k.search_predict = value != 0.;
     else { set_error("unknown option " + k); return DFTATOM_E_ARG; }
     return 0;
 }
@@ -692,7 +695,7 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
         nvtxRangePushA("dftatom:scf_step");
         begin_phase(DFTATOM_K_SEARCH);
         if (c->k.search_mode == 0 && c->k.search_kernel == 0 && !g.uniform) {
-            nl += launch_search_rows(g, b.atab, b.atoms, b.orbs, b.astate, b.ss, n_orbs, d_work + DFTATOM_K_SEARCH, c->k.warm_start, c->k.rows_cfg, c->k.rows_wide_from_step, sp, sp_end, st);
+            nl += launch_search_rows(g, b.atab, b.atoms, b.orbs, b.astate, b.ss, n_orbs, d_work + DFTATOM_K_SEARCH, (c->k.warm_start ? 1 : 0) | (c->k.search_predict ? 2 : 0), c->k.rows_cfg, c->k.rows_wide_from_step, sp, sp_end, st);
         } else if (c->k.search_mode == 0) {
             // two shapes of the same search: serial-in-r (one warp per orbital) while many orbitals are active, parallel-in-r
             // (one cluster per orbital) once few are left.  Both are enqueued; the device-side count of active orbitals

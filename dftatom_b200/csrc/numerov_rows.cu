@@ -608,7 +608,8 @@ __global__ void __launch_bounds__(32 * NW, NW == kRowWarps ? 3 : 1) search_rows_
     b.lo = -Z * Z - 1.; b.hi = kTopEnergy;                // DFTAtom.cpp:407,499
     b.y_lm = 1.; b.P_lm = 1.; b.side = 0; b.trusted = false;
     const SearchState s0 = ss[k];
-    b.mode = (warm_start && s0.pad == 1) ? kLadder : kSection;
+    const bool warm = (warm_start & 1) && s0.pad == 1;
+    b.mode = warm ? kLadder : kSection;
     // first ladder: the levels move geometrically from one SCF step to the next (linear mixing); centre = previous eigenvalue + last
     // shift x (ratio of the last two shifts), radius = 1.5 x last shift, innermost offset = twice what the last step's prediction missed by
     const double e_prev = s0.E, sh1 = s0.up_lo, sh2 = s0.up_hi;
@@ -616,6 +617,37 @@ __global__ void __launch_bounds__(32 * NW, NW == kRowWarps ? 3 : 1) search_rows_
     b.c_est = fmin(fmax(e_prev + sh1 * ratio, b.lo), b.hi);
     b.radius = fmin(fmax(1.5 * fabs(sh1), 1e-7), Z * Z + 51.);
     b.inner = (s0.dn_lo > 0.) ? fmin(fmax(2. * s0.dn_lo, 0.45 * kEnergyTol), 0.25 * b.radius) : 0.125 * b.radius;
+    if (warm_start & 2) {
+        // Inside an SCF (the step counter of the atom says where): what the first steps of the reference's SCF are known to do.  Only the
+        // first ladder changes - a wrong guess costs rounds, never the result (the bracket logic certifies every bracket it keeps).
+        const int sc = astate[ob.atom].n_steps;
+        const double mix = atoms[ob.atom].mixing;
+        if (sc == 0 && !warm) {
+            // step 0: the initial density is a uniform sphere of radius MaxR (DFTAtom.cpp:371-376): V = -Z/r + 3Z/(2 MaxR) - Z r^2/(2 MaxR^3) + v_xc
+            // of a density of ~1e-3: hydrogenic levels shifted by 3Z/(2 MaxR) - ~0.1
+            const double nq = (double)(ob.want + ob.l + 1);
+            const double hyd = Z * Z / (2. * nq * nq);
+            b.mode = kLadder;
+            b.c_est = fmin(fmax(-hyd + 1.5 * Z / g.max_r - 0.1, b.lo), b.hi);
+            b.inner = 0.1; b.radius = 0.4 + 0.002 * hyd;
+        } else if (warm && sc == 1) {
+            // step 1: the first real density screens the nucleus: every level rises by about (1 - mixing) x (|E| + 2); samples on that side only
+            const double up = 2. * (1. - mix) * sh1;           // (sh1 = 0.5 |E| + 1 after a cold search)
+            b.c_est = fmin(fmax(e_prev + 1.025 * up, b.lo), b.hi);
+            b.inner = 0.125 * up; b.radius = 0.5 * up;
+            if (!(up > 1e-7)) { b.c_est = e_prev; b.inner = 0.125 * b.radius; }
+        } else if (warm && sc >= 2) {
+            // step 2: one real shift so far - the shifts of a linearly mixed SCF decay by ~1 - 1.28 (1 - mixing) per step (0.36 at mixing 0.5);
+            // later: the miss of the extrapolation scales with the shifts
+            const bool real2 = sc >= 3;
+            const double q = real2 ? ratio : fmax(0., 1. - 1.28 * (1. - mix));
+            b.c_est = fmin(fmax(e_prev + sh1 * q, b.lo), b.hi);
+            b.radius = fmin(fmax(0.75 * fabs(sh1), 1e-7), Z * Z + 51.);
+            const double decay = (real2 && sh2 != 0.) ? fmin(fabs(sh1 / sh2), 1.) : 1.;
+            b.inner = real2 ? ((s0.dn_lo > 0.) ? fmin(fmax(2. * s0.dn_lo * decay, 0.45 * kEnergyTol), 0.25 * b.radius) : 0.125 * b.radius)
+                            : 0.16 * b.radius;
+        }
+    }
     const double c_first = b.c_est;
     long long steps = 0;
     int rounds = 0, sweeps = 0, hint = -1;
@@ -686,9 +718,9 @@ __global__ void __launch_bounds__(32 * NW, NW == kRowWarps ? 3 : 1) search_rows_
             s.y0_log2 = ylog;
             s.converged = (b.hi - b.lo < kEnergyTol) && (ylog < 49.828921423310435);   // DFTAtom.cpp:528
             s.stage = 3;
-            s.up_hi = s0.pad == 1 ? s0.up_lo : 0.;                               // the last two shifts of the level
-            s.up_lo = s0.pad == 1 ? b.lo - e_prev : 0.5 * fabs(b.lo) + 1.;         // (no shift yet: the scale the level may move by)
-            s.dn_lo = s0.pad == 1 ? fabs(b.lo - c_first) : 0.;                   // what this step's prediction missed by
+            s.up_hi = warm ? s0.up_lo : 0.;                                      // the last two shifts of the level
+            s.up_lo = warm ? b.lo - e_prev : 0.5 * fabs(b.lo) + 1.;                // (no shift yet: the scale the level may move by)
+            s.dn_lo = warm ? fabs(b.lo - c_first) : 0.;                          // what this step's prediction missed by
             s.pad = 1;
             ss[k] = s;
         }

@@ -136,6 +136,12 @@ const char* dftatom_version(void);
  *                   atom is still iterating") is set on the device (cudaGraphSetConditional): no host round trip between SCF steps.  Not used
  *                   with "profile" (per-class event timing needs host-side events between the launches), the validation search / match modes
  *                   and the cooperative team-mode Poisson kernel (one to three atoms on grids above 16385 nodes); 0 = host-driven loop.
+ *   "search_predict" (default 1) the production search starts every level of an SCF step from a ladder of 4 trial energies placed by what the
+ *                   first steps of the reference's SCF are known to do: step 0 - hydrogenic levels of the initial potential (uniform sphere of
+ *                   radius MaxR, DFTAtom.cpp:371-376: -Z^2/2n^2 + 3Z/(2 MaxR)); step 1 - one-sided (every level rises when the first real
+ *                   density screens the nucleus); step 2 - default decay ratio of the shifts; later - extrapolated shift, offsets scaled
+ *                   with the shifts.  0 = cold section of [-Z^2-1, 50] at step 0 and the plain previous-eigenvalue ladder.  Same results
+ *                   (every bracket is certified by the Sturm count), fewer rounds.
  *   "graph_phases" (default 1) the graph loop is a chain of WHILE nodes, one per range of SCF steps between the step indices at which a
  *                   kernel shape hands over to another one ("rows_wide_from_step", "match_win_until_step"; all atoms of a batch step
  *                   together): every body holds only the shapes of its own range, no launch that returns at once.  0 = one WHILE node
