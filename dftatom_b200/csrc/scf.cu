@@ -377,7 +377,12 @@ void launch_density_update(const GridDev& g, const ScfBuffers& b, cudaStream_t s
 // grid = (atoms, node_chunks(N)): every CTA owns a contiguous range of nodes; the partial sums of the five integrals go to
 // b.epart, and the CTA that finishes last (per-atom ticket) adds them in chunk order - deterministic - and runs the stop test.
 constexpr int kPT2 = 256;
-__global__ void __launch_bounds__(kPT2) potential_energy_kernel(GridDev g, PoissonLevels lv, ScfBuffers b, int first)
+// 3 CTAs per SM (80 registers, 256 B of spills): the kernel waits on the latency of log / atan / divisions of 2 nodes per thread - measured on the
+// C3 sweep: 4.36 ms at 2 CTAs per SM (128 registers), 3.82 at 3, 3.60 at 4 (64 registers, 320 B of spills; no faster end to end)
+#ifndef DFT_POT_MINB
+#define DFT_POT_MINB 3
+#endif
+__global__ void __launch_bounds__(kPT2, DFT_POT_MINB) potential_energy_kernel(GridDev g, PoissonLevels lv, ScfBuffers b, int first)
 {
     __shared__ double sm[5 * 32];
     __shared__ int is_last;
