@@ -18,6 +18,7 @@ namespace dft {
 
 static thread_local std::string g_err;
 void set_error(const std::string& s) { g_err = s; }
+int g_dft_pdl = 0;         // internal.h: launch_step_kernel (set from the option "use_pdl" when a solve starts)
 
 struct DevBuf {
     void* p = nullptr; size_t cap = 0;
@@ -112,6 +113,7 @@ struct Knobs {
     int use_graph = 1;         // SCF steps are replayed from a captured CUDA graph (one graph launch per step) instead of 5+ kernel launches
     int search_predict = 1;    // rows search: first ladders from what the first SCF steps are known to do (hydrogenic levels of the initial uniform-sphere
                                // potential at step 0, one-sided ladder at step 1, default decay ratio at step 2, miss scaled with the shifts later)
+    int use_pdl = 1;           // the kernels of an SCF step are launched with programmatic stream serialization (internal.h: launch_step_kernel)
     int graph_phases = 1;      // the graph loop is a chain of WHILE nodes, one per range of SCF steps between the step indices at which a kernel shape changes
                                // (rows_wide_from_step, match_win_until_step): each body holds only the shapes of its range.  0: one WHILE node, every shape in it
 };
@@ -356,6 +358,7 @@ int dftatom_set_option(dftatom_ctx* c, const char* key, double value)
     else if (k == "run_to_cap") c->k.run_to_cap = value != 0.;
     else if (k == "use_graph") c->k.use_graph = value != 0.;
     else if (k == "graph_phases") c->k.graph_phases = value != 0.;
+    else if (k == "use_pdl") c->k.use_pdl = value != 0.;
     else if (k == "search_predict") c->k.search_predict = value != 0.;
     else { set_error("unknown option " + k); return DFTATOM_E_ARG; }
     return 0;
@@ -680,6 +683,7 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
     auto begin_phase = [&](int cls) { nvtxRangePushA(kPhase[cls]); begin_span(cls); };
     auto end_phase = [&]() { end_span(); nvtxRangePop(); };
     th1 = now();
+    g_dft_pdl = c->k.use_pdl;
     DFT_CHECK(cudaEventRecord(ev0, st));
     // initial guess -> U -> V   (DFTAtom.cpp:371-392)
     launch_initial_density(g, b, st); ++launches;

@@ -305,6 +305,23 @@ struct ScfBuffers {
     int run_to_cap;   // != 0: the stop test is recorded in dftatom_step.stop_criterion_met but never ends the SCF
     int adaptive_mixing;  // != 0: per-atom damping is raised when Etotal sloshes with period 2 (scf.cu); 0: the reference's fixed linear mixing
 };
+// Programmatic dependent launch of the kernels of an SCF step: with g_dft_pdl != 0 (option "use_pdl") a step kernel may be scheduled while
+// the kernel before it on the stream drains; every such kernel starts with DFT_PDL_WAIT() - before its first global read and before any
+// early exit - which returns once the preceding grid has completed and its writes are visible (a no-op for a normal launch).
+extern int g_dft_pdl;
+#define DFT_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+template <class... KA, class... A>
+inline void launch_step_kernel(void (*k)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = g_dft_pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, k, static_cast<KA>(args)...);
+}
+
 struct ScfLoopPhases { cudaGraphConditionalHandle handle[4]; int n; };      // the WHILE nodes of the SCF loop, one per phase (a range of SCF steps), in order
 void launch_scf_loop_condition(const ScfLoopPhases& ph, int phase, int step_first, int step_end, const int* n_active, unsigned long long* iterations, cudaStream_t st);
 void launch_gather_last_steps(const ScfBuffers& b, dftatom_step* out, cudaStream_t st);

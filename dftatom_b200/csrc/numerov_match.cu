@@ -278,6 +278,7 @@ __global__ void __launch_bounds__(kMT) match_cta_kernel(GridDev g, const double*
                                                         const AtomState* astate, SearchState* ss, double* psi_all, int* match_pt,
                                                         double* inv_norm, int n_orbs, int step_min, int step_max)
 {
+    DFT_PDL_WAIT();
     __shared__ MatchShared sh;
     extern __shared__ double gy[];                       // SMEM: g_i, later y_i, slot pslot(i)
     const unsigned full = 0xffffffffu;
@@ -540,6 +541,7 @@ __global__ void __launch_bounds__(kMT) match_win_kernel(GridDev g, const double*
                                                         const AtomState* astate, SearchState* ss, double* psi_all, int* match_pt,
                                                         double* inv_norm, int n_orbs, int win_nodes, int step_min, int step_max)
 {
+    DFT_PDL_WAIT();
     __shared__ MatchShared sh;
     extern __shared__ double gy[];                       // g_i of the window, later y_i; node i at pslot(i - base)
     const unsigned full = 0xffffffffu;
@@ -792,19 +794,19 @@ int launch_match_cta(const GridDev& g, const double* atab, const OrbitalDev* orb
         int lo = 0;
         if (win_until_step > 0 && win_nodes >= 1024 && win_nodes < g.N) {
             if (step_lo < win_until_step) {
-                match_win_kernel<<<n_orbs, kMT, match_win_bytes(win_nodes), st>>>(g, atab, orbs, astate, const_cast<SearchState*>(ss), psi, match_pt, inv_norm, n_orbs,
-                                                                              win_nodes, 0, win_until_step);
+                launch_step_kernel(match_win_kernel, dim3(n_orbs), dim3(kMT), match_win_bytes(win_nodes), st, g, atab, orbs, astate, const_cast<SearchState*>(ss), psi, match_pt,
+                                   inv_norm, n_orbs, win_nodes, 0, win_until_step);
                 ++n_launch;
             }
             lo = win_until_step;
         }
         if (step_hi > lo) {
-            match_cta_kernel<true><<<n_orbs, kMT, bytes, st>>>(g, atab, orbs, astate, const_cast<SearchState*>(ss), psi, match_pt, inv_norm, n_orbs, lo, 1 << 30);
+            launch_step_kernel(match_cta_kernel<true>, dim3(n_orbs), dim3(kMT), bytes, st, g, atab, orbs, astate, const_cast<SearchState*>(ss), psi, match_pt, inv_norm, n_orbs, lo, 1 << 30);
             ++n_launch;
         }
     } else {
-        match_win_kernel<<<n_orbs, kMT, match_win_bytes(kWinNodes), st>>>(g, atab, orbs, astate, const_cast<SearchState*>(ss), psi, match_pt, inv_norm, n_orbs,
-                                                                      kWinNodes, 0, 1 << 30);
+        launch_step_kernel(match_win_kernel, dim3(n_orbs), dim3(kMT), match_win_bytes(kWinNodes), st, g, atab, orbs, astate, const_cast<SearchState*>(ss), psi, match_pt, inv_norm,
+                           n_orbs, kWinNodes, 0, 1 << 30);
         ++n_launch;
     }
     return n_launch;

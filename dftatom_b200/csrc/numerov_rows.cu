@@ -588,6 +588,7 @@ __global__ void __launch_bounds__(32 * NW, NW == kRowWarps ? 3 : 1) search_rows_
                                                                       const OrbitalDev* orbs, const AtomState* astate, SearchState* ss, int n_orbs,
                                                                       unsigned long long* work, int warm_start, int cfg, int step_min, int step_max)
 {
+    DFT_PDL_WAIT();
     extern __shared__ __align__(16) unsigned char rows_smem[];
     __shared__ RowShared sh;
 #ifdef DFT_ROWS_DEBUG
@@ -811,12 +812,12 @@ int launch_search_rows(const GridDev& g, const double* atab, const AtomDev* atom
     // [step_lo, step_hi): the SCF steps this launch can be executed at (all atoms of a batch step together); a shape whose window misses it is not launched
     const int split = wide_from_step > 0 ? wide_from_step : (1 << 30);
     if (step_lo < split) {
-        search_rows_kernel<kRowWarps><<<n_orbs, 32 * kRowWarps, rows_smem_bytes(kRowWarps), st>>>(g, atab, atoms, orbs, astate, ss, n_orbs, work, warm_start, cfg, 0, split);
+        launch_step_kernel(search_rows_kernel<kRowWarps>, dim3(n_orbs), dim3(32 * kRowWarps), rows_smem_bytes(kRowWarps), st, g, atab, atoms, orbs, astate, ss, n_orbs, work, warm_start, cfg, 0, split);
         ++n_launch;
     }
     if (wide_from_step > 0 && step_hi > split) {
-        search_rows_kernel<kRowWarpsWide><<<n_orbs, 32 * kRowWarpsWide, rows_smem_bytes(kRowWarpsWide), st>>>(g, atab, atoms, orbs, astate, ss, n_orbs, work, warm_start,
-                                                                                                           cfg, split, 1 << 30);
+        launch_step_kernel(search_rows_kernel<kRowWarpsWide>, dim3(n_orbs), dim3(32 * kRowWarpsWide), rows_smem_bytes(kRowWarpsWide), st, g, atab, atoms, orbs, astate, ss, n_orbs,
+                           work, warm_start, cfg, split, 1 << 30);
         ++n_launch;
     }
     return n_launch;

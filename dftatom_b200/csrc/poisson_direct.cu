@@ -214,6 +214,7 @@ __device__ __forceinline__ void direct_solve_chunked(const GridDev& g, const Clu
 
 __global__ void __launch_bounds__(kDT, 1) poisson_direct_kernel(GridDev g, ClusterPoissonArgs a)
 {
+    DFT_PDL_WAIT();
     const int k = blockIdx.x;
     if (a.skip && *reinterpret_cast<const int*>(reinterpret_cast<const char*>(a.skip) + (size_t)k * a.skip_stride_bytes)) return;
     switch (g.L) {
@@ -257,7 +258,7 @@ int poisson_direct_init_device()
 // levels a.scratch (n_dens x scratch_stride doubles, scratch_stride >= N - 1) is required
 void launch_poisson_direct(const GridDev& g, const ClusterPoissonArgs& a, cudaStream_t st)
 {
-    poisson_direct_kernel<<<a.n_dens, kDT, direct_smem_bytes(g.L), st>>>(g, a);
+    launch_step_kernel(poisson_direct_kernel, dim3(a.n_dens), dim3(kDT), direct_smem_bytes(g.L), st, g, a);
 }
 
 }  // namespace dft

@@ -308,6 +308,7 @@ __host__ __device__ inline int node_chunks(int N) { const int c = (N + 511) / 51
 constexpr int kDT = 256;
 __global__ void __launch_bounds__(kDT) density_update_kernel(GridDev g, ScfBuffers b)
 {
+    DFT_PDL_WAIT();
     __shared__ double wgt[2 * DFTATOM_MAX_LEVELS];          // occupation / norm of every orbital
     const int a = blockIdx.x;
     AtomState& as = b.astate[a];
@@ -370,7 +371,7 @@ void launch_orbital_norms(const GridDev& g, const ScfBuffers& b, cudaStream_t st
 
 void launch_density_update(const GridDev& g, const ScfBuffers& b, cudaStream_t st)
 {
-    density_update_kernel<<<dim3(b.n_atoms, node_chunks(g.N)), kDT, 0, st>>>(g, b);
+    launch_step_kernel(density_update_kernel, dim3(b.n_atoms, node_chunks(g.N)), dim3(kDT), 0, st, g, b);
 }
 
 // Potential from (U, rho), the five integrals, energies, stop test.  first != 0: only the initial potential.
@@ -384,6 +385,7 @@ constexpr int kPT2 = 256;
 #endif
 __global__ void __launch_bounds__(kPT2, DFT_POT_MINB) potential_energy_kernel(GridDev g, PoissonLevels lv, ScfBuffers b, int first)
 {
+    DFT_PDL_WAIT();
     __shared__ double sm[5 * 32];
     __shared__ int is_last;
     const int a = blockIdx.x;
@@ -542,6 +544,7 @@ void launch_poisson_delta_apply(const GridDev& g, int n_dens, long long ld, doub
 // is still its own; once no atom is left the later phases are switched off too.  step_first: the SCF step of the first graph iteration.
 __global__ void scf_loop_condition_kernel(ScfLoopPhases ph, int phase, int step_first, int step_end, const int* n_active, unsigned long long* iterations)
 {
+    DFT_PDL_WAIT();
     const unsigned long long it = (*iterations += 1ULL);
     const bool active = *n_active > 0;
     cudaGraphSetConditional(ph.handle[phase], (active && (long long)step_first + (long long)it < (long long)step_end) ? 1u : 0u);
@@ -549,7 +552,7 @@ __global__ void scf_loop_condition_kernel(ScfLoopPhases ph, int phase, int step_
 }
 void launch_scf_loop_condition(const ScfLoopPhases& ph, int phase, int step_first, int step_end, const int* n_active, unsigned long long* iterations, cudaStream_t st)
 {
-    scf_loop_condition_kernel<<<1, 1, 0, st>>>(ph, phase, step_first, step_end, n_active, iterations);
+    launch_step_kernel(scf_loop_condition_kernel, dim3(1), dim3(1), 0, st, ph, phase, step_first, step_end, n_active, iterations);
 }
 
 // last "Step:" record of every atom, compact (what dftatom_solve_batch downloads when the caller did not ask for the steps)
@@ -567,7 +570,7 @@ void launch_gather_last_steps(const ScfBuffers& b, dftatom_step* out, cudaStream
 
 void launch_potential_energy(const GridDev& g, const PoissonLevels& lv, const ScfBuffers& b, int first, cudaStream_t st)
 {
-    potential_energy_kernel<<<dim3(b.n_atoms, node_chunks(g.N)), kPT2, 0, st>>>(g, lv, b, first);
+    launch_step_kernel(potential_energy_kernel, dim3(b.n_atoms, node_chunks(g.N)), dim3(kPT2), 0, st, g, lv, b, first);
 }
 
 }  // namespace dft

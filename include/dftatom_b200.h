@@ -136,6 +136,9 @@ const char* dftatom_version(void);
  *                   atom is still iterating") is set on the device (cudaGraphSetConditional): no host round trip between SCF steps.  Not used
  *                   with "profile" (per-class event timing needs host-side events between the launches), the validation search / match modes
  *                   and the cooperative team-mode Poisson kernel (one to three atoms on grids above 16385 nodes); 0 = host-driven loop.
+ *   "use_pdl"      (default 1) the kernels of an SCF step are launched with programmatic stream serialization (each starts with
+ *                   griddepcontrol.wait before its first global read): the next kernel's blocks are scheduled while the previous one drains.
+ *                   Same records; 0 = plain stream order.
  *   "search_predict" (default 1) the production search starts every level of an SCF step from a ladder of 4 trial energies placed by what the
  *                   first steps of the reference's SCF are known to do: step 0 - hydrogenic levels of the initial potential (uniform sphere of
  *                   radius MaxR, DFTAtom.cpp:371-376: -Z^2/2n^2 + 3Z/(2 MaxR)); step 1 - one-sided (every level rises when the first real
