@@ -23,7 +23,7 @@ sys.path.insert(0, ROOT)
 
 C3 = dict(levels=14, delta=0.0005, mixing=0.5, rmax=25.0, method=0)
 WORKLOAD = "C3 periodic-table sweep Z=1-92 LDA, 14 levels (16385 nodes), delta 0.0005, mixing 0.5, Rmax 25"
-STREAM_GROUPS_DEFAULT = 3          # libdftatom_b200's default (engine.cpp: stream_groups)
+STREAM_GROUPS_DEFAULT = 4          # libdftatom_b200's default (engine.cpp: stream_groups)
 FLOP_PER_NODE_STEP = 11.0          # SURVEY §8(d) accounting convention for the Numerov shooting kernel
 SEARCH_TRAFFIC_BYTES = 12553728    # DRAM bytes (read 12 551 424 + write 2 304) of one search_rows_kernel launch at full load, ncu --set full (profiles/r02_ncu_search_rows.txt)
 REF_EXE = os.path.join(ROOT, "oracle", "_ref", "dftatom_ref")
@@ -294,7 +294,7 @@ def run_cuda_arm(a):
     prof = {k: dict(ms=0.0, launches=0, work=0.0) for k in D.api.KERNEL_CLASSES}
     prof_dev_ms = 0.0
     ctx.set_option("profile", 1)
-    ctx.set_option("stream_groups", 1)      # one chain: the class times add up to the sweep (the production default overlaps 3 groups of atoms on 3 streams)
+    ctx.set_option("stream_groups", 1)      # one chain: the class times add up to the sweep (the production default overlaps 4 groups of atoms on 4 streams)
     for _ in range(a.steps):
         flush_l2()
         ctx.solve_batch(opts, keep_steps=False)
@@ -374,7 +374,7 @@ def run_cuda_arm(a):
             scf_loop=dict(mode="CUDA-graph while node, loop condition set on the device (cudaGraphSetConditional)" if graph_iters else "host-driven loop",
                           scf_steps_inside_graph=int(graph_iters), device_ms_per_sweep=dev_ms / a.steps,
                           device_ms_per_sweep_profiled_host_loop=prof_dev_ms / a.steps, stream_groups=STREAM_GROUPS_DEFAULT,
-                          note="timed sweeps: the library's defaults - the 92 atoms dealt into 3 groups whose SCF chains run concurrently on 3 streams, each group's loop "
+                          note="timed sweeps: the library's defaults - the 92 atoms dealt into 4 groups whose SCF chains run concurrently on 4 streams, each group's loop "
                                "one CUDA-graph launch; profiled sweeps: one group, host-driven loop, CUDA events around every kernel class"),
             roofline=dict(kernel="search_rows_kernel (Numerov shooting: Sturm-count search; one CTA per orbital, lane = radial segment (128 per orbital), every thread "
                                  "4 trial energies x 2 basis chains: 11 FP64 instructions per credited (trial energy, node) = 11 FLOP -> ceiling 0.5 of the FMA peak)",

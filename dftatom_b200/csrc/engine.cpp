@@ -124,7 +124,7 @@ struct dftatom_ctx {
     std::map<GridKey, GridEntry> grids;
     Knobs k;                        // tuning knobs (dftatom_set_option); copied as a whole to the child context
     int segments(int N) const { return k.segments(N); }
-    int stream_groups = 3;     // a batch of >= 32 atoms (grids up to 16385 nodes) is dealt into this many groups that run their SCF chains concurrently on
+    int stream_groups = 4;     // a batch of >= 32 atoms (grids up to 16385 nodes) is dealt into this many groups that run their SCF chains concurrently on
                                // separate streams: one group's Poisson solves (one SM per density) overlap another's search; per-atom records are unchanged
     dftatom_ctx* child = nullptr;   // context (stream + buffers) of the second group
     int n_sm = 148;

@@ -113,7 +113,7 @@ const char* dftatom_version(void);
  *   "search_mode"  (default 0) 0 = fused single-predicate multisection (production); 1 = reference-shaped three-stage
  *                   search (node-count window edges, then the sign change of y(0)), kept for validation
  *   "profile"      (default 0) time every kernel class with CUDA events, see dftatom_last_profile
- *   "stream_groups" (default 3; 1..8) a batch of >= 32 atoms on a grid of <= 16385 nodes is dealt into this many groups whose SCF chains run
+ *   "stream_groups" (default 4; 1..8) a batch of >= 32 atoms on a grid of <= 16385 nodes is dealt into this many groups whose SCF chains run
  *                   concurrently on their own streams (atoms are independent; every launch of one chain depends on the previous one and most
  *                   are latency-bound: one group's Poisson solves overlap another's search).  Measured: C3 72.5 -> 66 ms.  Per-atom results do
  *                   not depend on it; the per-class CUDA-event times of "profile" then include the contention between the groups.

@@ -158,7 +158,7 @@ def test_kernel_shapes_agree(ctx):
                 {"use_graph": 0}, {"match_win_until_step": 0}, {"match_win_until_step": 100, "match_win_nodes": 2048}, {"direct_poisson": 0}, {"direct_after": 1}, {"rows_wide_from_step": 0}, {"rows_wide_from_step": 1}, {"stream_groups": 1},
                 {"graph_phases": 0}, {"rows_wide_from_step": 10, "match_win_until_step": 20}, {"search_predict": 0}, {"use_pdl": 0}]
     defaults = {"graph_phases": 1, "search_predict": 1, "use_pdl": 1, "r_segments": -1, "seg_threshold": 2400, "warm_vcycles": 7, "match_mode": 0, "search_kernel": 0, "rows_cfg": 0x111, "warm_poisson": 1,
-                "coarse_exact": 1, "warm_until_step": 32, "use_graph": 1, "match_win_until_step": 32, "match_win_nodes": 8192, "stream_groups": 3, "direct_poisson": 1, "direct_after": 4, "rows_wide_from_step": 32}
+                "coarse_exact": 1, "warm_until_step": 32, "use_graph": 1, "match_win_until_step": 32, "match_win_nodes": 8192, "stream_groups": 4, "direct_poisson": 1, "direct_after": 4, "rows_wide_from_step": 32}
     for v in variants:
         for k_, x in v.items():
             ctx.set_option(k_, x)
@@ -228,20 +228,22 @@ def test_stream_poisson_agrees(ctx):
 
 
 def test_stream_groups_same_results(ctx):
-    """Two groups of atoms on two streams (stream_groups = 2, batches of >= 32 atoms): every atom's trajectory is bit-identical
-    to the single-group run - no atom sees another."""
+    """Groups of atoms on their own streams (stream_groups = 2 and the default 4, batches of >= 32 atoms): every atom's trajectory is
+    bit-identical to the single-group run - no atom sees another."""
     opts = [D.Options(Z, 10, 15.0, 0.004, 0.5, Z % 2) for Z in range(1, 41)]
-    base = ctx.solve_batch(opts)
-    ctx.set_option("stream_groups", 2)
     try:
-        res = ctx.solve_batch(opts)
-    finally:
         ctx.set_option("stream_groups", 1)
-    for r, b in zip(res, base):
-        assert r.n_steps == b.n_steps and r.status == b.status
-        assert [s.Etotal for s in r.steps] == [s.Etotal for s in b.steps]
-        assert [s.E for s in r.steps] == [s.E for s in b.steps]
-        assert [[(L.n, L.l, L.occ) for L in ch] for ch in r.sorted_levels] == [[(L.n, L.l, L.occ) for L in ch] for ch in b.sorted_levels]
+        base = ctx.solve_batch(opts)
+        for groups in (2, 4):
+            ctx.set_option("stream_groups", groups)
+            res = ctx.solve_batch(opts)
+            for r, b in zip(res, base):
+                assert r.n_steps == b.n_steps and r.status == b.status
+                assert [s.Etotal for s in r.steps] == [s.Etotal for s in b.steps]
+                assert [s.E for s in r.steps] == [s.E for s in b.steps]
+                assert [[(L.n, L.l, L.occ) for L in ch] for ch in r.sorted_levels] == [[(L.n, L.l, L.occ) for L in ch] for ch in b.sorted_levels]
+    finally:
+        ctx.set_option("stream_groups", 4)
 
 
 def test_edge_options_match_oracle(ctx):
