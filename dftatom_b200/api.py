@@ -44,6 +44,12 @@ class _CResult(C.Structure):
                 ("Etotal", C.c_double), ("Ekin", C.c_double), ("Ecoul", C.c_double), ("Eenuc", C.c_double), ("Exc", C.c_double)]
 
 
+_RESULT_DTYPE = np.dtype(_CResult)      # numpy views of the C structs (same layout: built from the ctypes definitions)
+_STEP_DTYPE = np.dtype(_CStep)
+_LEVEL_IDX = np.arange(MAX_LEVELS)[None, None, :]
+_SPIN_IDX = np.arange(2)[None, :, None]
+
+
 class _CProfile(C.Structure):
     _fields_ = [("ms", C.c_double), ("launches", C.c_longlong), ("work", C.c_double)]
 
@@ -162,19 +168,34 @@ class Step:
     stop_criterion_met: bool = False
 
 
-@dataclass
 class Result:
-    options: Options
-    status: int
-    n_steps: int
-    levels: List[List[Level]]           # [spin][level] in (n,l) order, eigenvalues of the last step
-    sorted_levels: List[List[Level]]    # sorted by eigenvalue (the reference's last line)
-    Etotal: float
-    Ekin: float
-    Ecoul: float
-    Eenuc: float
-    Exc: float
-    steps: List[Step] = field(default_factory=list)
+    """One atom of a solve_batch call.  `levels` ([spin][level] in (n, l) order, eigenvalues of the last step) and `sorted_levels` (sorted by
+    eigenvalue: the reference's last line) are lists of Level objects, built on first use from the (n, l, occ, nodes, E) records the library
+    returned (a sweep that only reads the energies does not pay for 2000 Python objects)."""
+    __slots__ = ("options", "status", "n_steps", "Etotal", "Ekin", "Ecoul", "Eenuc", "Exc", "steps", "_lv", "_sl")
+
+    def __init__(self, options, status, n_steps, levels, sorted_levels, Etotal, Ekin, Ecoul, Eenuc, Exc, steps=None):
+        self.options, self.status, self.n_steps = options, status, n_steps
+        self._lv, self._sl = levels, sorted_levels            # [spin][k]: Level objects or raw tuples
+        self.Etotal, self.Ekin, self.Ecoul, self.Eenuc, self.Exc = Etotal, Ekin, Ecoul, Eenuc, Exc
+        self.steps = steps if steps is not None else []
+
+    @staticmethod
+    def _as_levels(chans):
+        return [[x if isinstance(x, Level) else Level(*x) for x in ch] for ch in chans]
+
+    @property
+    def levels(self) -> List[List[Level]]:
+        self._lv = self._as_levels(self._lv)
+        return self._lv
+
+    @property
+    def sorted_levels(self) -> List[List[Level]]:
+        self._sl = self._as_levels(self._sl)
+        return self._sl
+
+    def __repr__(self):
+        return f"Result(Z={self.options.Z}, status={self.status}, n_steps={self.n_steps}, Etotal={self.Etotal!r})"
 
     @property
     def finished(self) -> bool:
@@ -267,18 +288,34 @@ class Context:
         stride = MAX_STEPS_LSDA if any(o.method for o in options) else MAX_STEPS_LDA
         csteps = (_CStep * (n * stride))() if keep_steps else None
         _check(self._lib.dftatom_solve_batch(self._h, copts, n, cres, csteps, stride if keep_steps else 0))
+        # host structs -> Python objects in bulk (numpy structured views of the ctypes arrays: one pass in C instead of a ctypes
+        # attribute access per field)
+        ra = np.frombuffer(cres, dtype=_RESULT_DTYPE, count=n)
+        head = ra[["status", "n_steps", "n_spin", "Etotal", "Ekin", "Ecoul", "Eenuc", "Exc"]].tolist()
+        nlv = ra["n_levels"]
+        used = (_LEVEL_IDX < nlv[:, :, None]) & (_SPIN_IDX < ra["n_spin"][:, None, None])        # [atom][spin][k]
+        lev, sor = ra["levels"][used].tolist(), ra["sorted"][used].tolist()                        # flat, (n, l, occ, nodes, E) each
+        n_levels = nlv.tolist()
+        sa = np.frombuffer(csteps, dtype=_STEP_DTYPE, count=n * stride) if keep_steps else None
         out = []
+        p = 0
         for a in range(n):
-            r = cres[a]
-            lv = [_levels_from_c(r.levels[s], r.n_levels[s]) for s in range(r.n_spin)]
-            sl = [_levels_from_c(r.sorted[s], r.n_levels[s]) for s in range(r.n_spin)]
+            status, n_steps, n_spin, etot, ekin, ecoul, eenuc, exc = head[a]
+            nl = n_levels[a]
+            lv, sl = [], []
+            for s in range(n_spin):
+                q = p + nl[s]
+                lv.append(lev[p:q]); sl.append(sor[p:q])
+                p = q
             steps = []
-            if keep_steps:
-                for k in range(r.n_steps):
-                    cs = csteps[a * stride + k]
-                    steps.append(Step([[cs.E[s][j] for j in range(r.n_levels[s])] for s in range(r.n_spin)], cs.Etotal, cs.Ekin,
-                                      cs.Ecoul, cs.Eenuc, cs.Exc, bool(cs.levels_converged), bool(cs.stop_criterion_met)))
-            out.append(Result(options[a], r.status, r.n_steps, lv, sl, r.Etotal, r.Ekin, r.Ecoul, r.Eenuc, r.Exc, steps))
+            if keep_steps and n_steps:
+                blk = sa[a * stride:a * stride + n_steps]
+                E = blk["E"].tolist()
+                rest = blk[["Etotal", "Ekin", "Ecoul", "Eenuc", "Exc", "levels_converged", "stop_criterion_met"]].tolist()
+                for k in range(n_steps):
+                    r_ = rest[k]
+                    steps.append(Step([E[k][s][:nl[s]] for s in range(n_spin)], r_[0], r_[1], r_[2], r_[3], r_[4], bool(r_[5]), bool(r_[6])))
+            out.append(Result(options[a], status, n_steps, lv, sl, etot, ekin, ecoul, eenuc, exc, steps))
         return out
 
     def last_timing(self):
