@@ -136,6 +136,7 @@ struct dftatom_ctx {
     DevBuf atoms, astate, orbs, ss, rho, rhot, vpot, atab, psi, match_pt, inv_norm, epart, eticket, team_bar, phi, src, u0, ubuf, zbc, tab_of, steps, n_active;
     DevBuf scratch[8];
     int* h_active = nullptr;       // pinned
+    char* h_up = nullptr; size_t h_up_cap = 0, h_up_used = 0;      // pinned staging of the descriptor uploads of one solve (reset at its start)
     // timing of the last solve
     double last_ms = 0.;
     long long last_launches = 0;
@@ -240,11 +241,34 @@ static int validate(const dftatom_options& o)
     return 0;
 }
 
+// descriptor upload through the context's pinned arena: truly asynchronous (a copy from pageable memory is staged and synchronised by the
+// driver - five of those per group, from four host threads, were ~1 ms of every sweep)
 template <class T> static int upload(dftatom_ctx* c, DevBuf& b, const std::vector<T>& h)
 {
     int rc = b.ensure(std::max<size_t>(h.size(), 1) * sizeof(T));
     if (rc) return rc;
-    if (!h.empty()) DFT_CHECK(cudaMemcpyAsync(b.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    if (h.empty()) return 0;
+    const size_t bytes = h.size() * sizeof(T), at = (c->h_up_used + 63) & ~(size_t)63;
+    if (at + bytes <= c->h_up_cap) {
+        std::memcpy(c->h_up + at, h.data(), bytes);
+        c->h_up_used = at + bytes;
+        DFT_CHECK(cudaMemcpyAsync(b.p, c->h_up + at, bytes, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        DFT_CHECK(cudaMemcpyAsync(b.p, h.data(), bytes, cudaMemcpyHostToDevice, c->stream));        // (arena too small for this batch: staged copy)
+    }
+    return 0;
+}
+// called at the start of a solve: the arena is free again (the previous solve has synchronised its stream); grown to what that solve needed
+static int upload_arena_reset(dftatom_ctx* c, size_t want_bytes)
+{
+    c->h_up_used = 0;
+    if (want_bytes > c->h_up_cap) {
+        if (c->h_up) cudaFreeHost(c->h_up);
+        c->h_up = nullptr; c->h_up_cap = 0;
+        const size_t cap = std::max<size_t>(want_bytes * 2, (size_t)1 << 16);
+        DFT_CHECK(cudaMallocHost((void**)&c->h_up, cap));
+        c->h_up_cap = cap;
+    }
     return 0;
 }
 
@@ -307,6 +331,7 @@ void dftatom_destroy(dftatom_ctx* c)
     for (DevBuf& b : c->scratch) b.release();
     c->stream_G.release(); c->stream_src0.release(); c->stream_scratch.release(); c->exact_work.release(); c->last_steps.release(); c->rho_prev.release(); c->d_src.release(); c->d_u.release();
     if (c->h_active) cudaFreeHost(c->h_active);
+    if (c->h_up) cudaFreeHost(c->h_up);
     if (c->h_last) cudaFreeHost(c->h_last);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -500,6 +525,7 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
                                     + sizeof(int) * (tab_of.size() + zbc.size() + 2));
 
     // ---- device buffers ----
+    if ((rc = upload_arena_reset(c, (size_t)c->last_h2d_bytes + 64 * 8))) return rc;
     if ((rc = upload(c, c->atoms, atoms))) return rc;
     if ((rc = upload(c, c->astate, astate))) return rc;
     if ((rc = upload(c, c->orbs, orbs))) return rc;
