@@ -182,7 +182,9 @@ class Result:
 
     @staticmethod
     def _as_levels(chans):
-        return [[x if isinstance(x, Level) else Level(*x) for x in ch] for ch in chans]
+        if any(ch and not isinstance(ch[0], Level) for ch in chans):
+            return [[x if isinstance(x, Level) else Level(*x) for x in ch] for ch in chans]
+        return chans
 
     @property
     def levels(self) -> List[List[Level]]:

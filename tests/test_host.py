@@ -94,3 +94,39 @@ def test_cli_fails_loudly_without_gpu():
     assert r.returncode == 1 and "no CUDA device" in r.stderr and r.stdout == ""
     assert subprocess.run([exe, "--bogus"], capture_output=True).returncode == 2
 
+
+
+def test_python_structs_mirror_the_header():
+    """The numpy views solve_batch converts the host structs through (built from the ctypes mirrors of dftatom_result / dftatom_step) have the
+    same size and see the same fields at the same places as ctypes does."""
+    import ctypes as C
+    from dftatom_b200 import api
+    assert api._RESULT_DTYPE.itemsize == C.sizeof(api._CResult) and api._STEP_DTYPE.itemsize == C.sizeof(api._CStep)
+    n = 3
+    cres = (api._CResult * n)()
+    cres[1].status = 1; cres[1].n_steps = 7; cres[1].n_spin = 2
+    cres[1].n_levels[0] = 2; cres[1].n_levels[1] = 1
+    cres[1].levels[0][1].n = 3; cres[1].levels[0][1].l = 1; cres[1].levels[0][1].occ = 4; cres[1].levels[0][1].nodes = 1; cres[1].levels[0][1].E = -1.5
+    cres[1].sorted[1][0].occ = 5
+    cres[1].Etotal = -9.25
+    ra = np.frombuffer(cres, dtype=api._RESULT_DTYPE, count=n)
+    assert ra[["status", "n_steps", "n_spin", "Etotal"]].tolist()[1] == (1, 7, 2, -9.25)
+    assert ra["n_levels"].tolist()[1] == [2, 1]
+    assert ra["levels"].tolist()[1][0][1] == (3, 1, 4, 1, -1.5) and ra["sorted"].tolist()[1][1][0][2] == 5
+    cs = (api._CStep * 4)()
+    cs[2].E[1][3] = 2.5; cs[2].Etotal = -3.0; cs[2].stop_criterion_met = 1
+    sa = np.frombuffer(cs, dtype=api._STEP_DTYPE, count=4)
+    assert sa["E"].tolist()[2][1][3] == 2.5 and sa[["Etotal", "stop_criterion_met"]].tolist()[2] == (-3.0, 1)
+
+
+def test_result_builds_levels_on_first_use():
+    """Result keeps the (n, l, occ, nodes, E) records the library returned and turns them into Level objects when asked; it pickles (the
+    torch.distributed gather of dftatom_b200/distributed.py sends Results between ranks)."""
+    import pickle
+    r = D.Result(D.Options(3, 10, 10.0, 0.01, 0.5, 0), 0, 5, [[(1, 0, 2, 0, -1.9), (2, 0, 1, 1, -0.1)]], [[(2, 0, 1, 1, -0.1), (1, 0, 2, 0, -1.9)]],
+                 -7.0, 1.0, 2.0, 3.0, 4.0)
+    assert r.finished and r.steps == []
+    assert [(L.n, L.l, L.occ, L.nodes, L.E) for L in r.levels[0]] == [(1, 0, 2, 0, -1.9), (2, 0, 1, 1, -0.1)]
+    assert r.levels is r.levels and isinstance(r.sorted_levels[0][0], D.Level) and r.sorted_levels[0][0].E == -0.1
+    q = pickle.loads(pickle.dumps(r))
+    assert q.Etotal == -7.0 and q.levels[0][1].nodes == 1 and q.options.Z == 3
