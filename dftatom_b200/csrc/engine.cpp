@@ -41,7 +41,10 @@ struct GridKey {
     bool operator<(const GridKey& o) const { return std::tie(L, delta, max_r) < std::tie(o.L, o.delta, o.max_r); }
 };
 
-struct GridEntry { GridDev dev; DevBuf mem; };
+struct GridEntry {
+    GridDev dev; DevBuf mem;
+    DevBuf u_unit; bool u_unit_ok = false;      // U of the SCF's start density for Z = 1 (solve_group: unit_guess), [N] doubles + one int (= 1)
+};
 
 // CUDA events of one call, destroyed on every return path
 struct EventPool {
@@ -111,6 +114,8 @@ struct Knobs {
     int adaptive_mixing = 0;   // opt-in: per-atom damping raised when Etotal sloshes with period 2 (beyond the reference; default: its fixed linear mixing)
     int step_cap = 0;          // > 0: lower the SCF step cap (100 LDA / 150 LSDA, DFTAtom.cpp:396,908) to this many steps (tests: with run_to_cap, run exactly as long as the reference did)
     int use_graph = 1;         // SCF steps are replayed from a captured CUDA graph (one graph launch per step) instead of 5+ kernel launches
+    int unit_guess = 1;        // the Poisson solve of the SCF's start density (a uniform sphere of Z electrons: linear in Z) is done once per grid for Z = 1
+                               // and scaled per atom, instead of one cold multigrid solve per atom and call (grids up to 16385 nodes)
     int search_predict = 1;    // rows search: first ladders from what the first SCF steps are known to do (hydrogenic levels of the initial uniform-sphere
                                // potential at step 0, one-sided ladder at step 1, default decay ratio at step 2, miss scaled with the shifts later)
     int use_pdl = 1;           // the kernels of an SCF step are launched with programmatic stream serialization (internal.h: launch_step_kernel)
@@ -146,7 +151,7 @@ struct dftatom_ctx {
 
 namespace dft {
 
-static int get_grid(dftatom_ctx* c, int L, double delta, double max_r, GridDev** out)
+static int get_grid(dftatom_ctx* c, int L, double delta, double max_r, GridDev** out, GridEntry** entry_out = nullptr)
 {
     // one place for the grid arguments of every entry point: 1 <= levels <= 22 (PoissonLevels holds 24, shifts stay defined), finite
     // delta >= 0 (0 = uniform grid) and finite max_r > 0 (a NaN would also break the ordering of the grid cache)
@@ -156,7 +161,7 @@ static int get_grid(dftatom_ctx* c, int L, double delta, double max_r, GridDev**
     }
     const GridKey key{ L, delta, max_r };
     auto it = c->grids.find(key);
-    if (it != c->grids.end()) { *out = &it->second.dev; return 0; }
+    if (it != c->grids.end()) { *out = &it->second.dev; if (entry_out) *entry_out = &it->second; return 0; }
     const int N = (1 << L) + 1;
     // host tables with the same libm the CPU reference uses (exp), uploaded once per grid
     const int n_tab = 10;
@@ -225,6 +230,7 @@ static int get_grid(dftatom_ctx* c, int L, double delta, double max_r, GridDev**
         DFT_CHECK(cudaStreamSynchronize(c->stream));
     }
     *out = &e.dev;
+    if (entry_out) *entry_out = &e;
     return 0;
 }
 
@@ -385,6 +391,7 @@ int dftatom_set_option(dftatom_ctx* c, const char* key, double value)
     else if (k == "graph_phases") c->k.graph_phases = value != 0.;
     else if (k == "use_pdl") c->k.use_pdl = value != 0.;
     else if (k == "search_predict") c->k.search_predict = value != 0.;
+    else if (k == "unit_guess") c->k.unit_guess = value != 0.;
     else { set_error("unknown option " + k); return DFTATOM_E_ARG; }
     return 0;
 }
@@ -475,7 +482,8 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
         }
     }
     GridDev* gp = nullptr;
-    int rc = get_grid(c, opts[0].levels, opts[0].method >= 2 ? 0. : opts[0].delta, opts[0].max_r, &gp);
+    GridEntry* gentry = nullptr;
+    int rc = get_grid(c, opts[0].levels, opts[0].method >= 2 ? 0. : opts[0].delta, opts[0].max_r, &gp, &gentry);
     if (rc) return rc;
     const GridDev g = *gp;
     const int N = g.N;
@@ -713,7 +721,32 @@ static int solve_group(dftatom_ctx* c, const dftatom_options* opts, int n_atoms,
     DFT_CHECK(cudaEventRecord(ev0, st));
     // initial guess -> U -> V   (DFTAtom.cpp:371-392)
     launch_initial_density(g, b, st); ++launches;
-    poisson_solve(0, launches);
+    // The start density is n_el / volume on every node but the first and the boundary value is Z: A U = S is linear in Z.  One cold solve of
+    // the Z = 1 problem per grid (the same kernel, the same cycle), U_atom = Z U_1 afterwards.
+    const bool unit_guess = c->k.unit_guess && !exact && !stream && !g.uniform && g.L <= 14 && gentry != nullptr;
+    if (unit_guess) {
+        if (!gentry->u_unit_ok) {
+            if ((rc = gentry->u_unit.ensure(sizeof(double) * (size_t)(2 * N + 2)))) return rc;
+            double* u1 = gentry->u_unit.as<double>();
+            double* rho1 = u1 + N;
+            int* one = reinterpret_cast<int*>(rho1 + N);
+            std::vector<double> h1((size_t)N, 1. / (4. * M_PI / 3. * g.max_r * g.max_r * g.max_r));
+            h1[0] = 0.;
+            const int h_one = 1;
+            DFT_CHECK(cudaMemcpyAsync(rho1, h1.data(), sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, st));
+            DFT_CHECK(cudaMemcpyAsync(one, &h_one, sizeof(int), cudaMemcpyHostToDevice, st));
+            DFT_CHECK(cudaStreamSynchronize(st));                       // (h1, h_one are pageable locals)
+            PoissonArgs p1 = pa;
+            p1.n_dens = 1; p1.rho = rho1; p1.src_nat = nullptr; p1.u_out = u1; p1.nat_stride = 0; p1.Zbc = one; p1.skip = nullptr; p1.skip_stride_bytes = 0;
+            p1.warm_vcycles = 0; p1.team_bar = nullptr;
+            launch_poisson_full(g, lv, p1, st); ++launches;
+            gentry->u_unit_ok = true;
+        }
+        launch_scale_unit_potential(g.N, n_atoms, ldU, gentry->u_unit.as<double>(), b.Zbc, b.U, st); ++launches;
+        if (delta) { launch_poisson_delta_prepare(g, n_atoms, ldU, b.rhot, rho_prev, nullptr, nullptr, skip_p, skip_stride, st); ++launches; }
+    } else {
+        poisson_solve(0, launches);
+    }
     launch_potential_energy(g, lv, b, 1, st); ++launches;
 
     const int rounds = search_rounds_needed(zmax);

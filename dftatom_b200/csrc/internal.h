@@ -165,6 +165,8 @@ struct PoissonArgs {
 };
 void launch_coarse_op(int L, double delta, double* G, cudaStream_t st);
 void launch_poisson_full(const GridDev& g, const PoissonLevels& lv, const PoissonArgs& a, cudaStream_t st);
+// U[k][i] = Z[k] u1[i]: the Poisson solve of the SCF's start density from the solution of the Z = 1 problem (engine.cpp: unit_guess)
+void launch_scale_unit_potential(int N, int n_dens, int ldU, const double* u1, const int* Z, double* U, cudaStream_t st);
 void launch_poisson_vcycles(const PoissonLevels& lv, double delta, int n_dens, double* phi, double* src, double* phi_nat,
                             const double* src_nat, int n_cycles, double* last_err, cudaStream_t st);
 

@@ -555,6 +555,16 @@ void launch_scf_loop_condition(const ScfLoopPhases& ph, int phase, int step_firs
     launch_step_kernel(scf_loop_condition_kernel, dim3(1), dim3(1), 0, st, ph, phase, step_first, step_end, n_active, iterations);
 }
 
+__global__ void scale_unit_potential_kernel(int N, int ldU, const double* __restrict__ u1, const int* __restrict__ Z, double* __restrict__ U)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) U[(size_t)blockIdx.y * ldU + i] = (double)Z[blockIdx.y] * u1[i];
+}
+void launch_scale_unit_potential(int N, int n_dens, int ldU, const double* u1, const int* Z, double* U, cudaStream_t st)
+{
+    scale_unit_potential_kernel<<<dim3((N + 255) / 256, n_dens), 256, 0, st>>>(N, ldU, u1, Z, U);
+}
+
 // last "Step:" record of every atom, compact (what dftatom_solve_batch downloads when the caller did not ask for the steps)
 __global__ void gather_last_steps_kernel(ScfBuffers b, dftatom_step* out)
 {

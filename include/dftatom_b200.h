@@ -139,6 +139,9 @@ const char* dftatom_version(void);
  *   "use_pdl"      (default 1) the kernels of an SCF step are launched with programmatic stream serialization (each starts with
  *                   griddepcontrol.wait before its first global read): the next kernel's blocks are scheduled while the previous one drains.
  *                   Same records; 0 = plain stream order.
+ *   "unit_guess"   (default 1) the Poisson solve of the SCF's start density (DFTAtom.cpp:371-392: a uniform sphere of Z electrons, boundary value Z -
+ *                   linear in Z) is done once per grid for Z = 1 by the cold multigrid kernel and scaled per atom (grids up to 16385 nodes);
+ *                   0 = one cold solve per atom and call.  Per-step parity with the reference unchanged (C3: 2.70e-6 vs 2.72e-6 Ha).
  *   "search_predict" (default 1) the production search starts every level of an SCF step from a ladder of 4 trial energies placed by what the
  *                   first steps of the reference's SCF are known to do: step 0 - hydrogenic levels of the initial potential (uniform sphere of
  *                   radius MaxR, DFTAtom.cpp:371-376: -Z^2/2n^2 + 3Z/(2 MaxR)); step 1 - one-sided (every level rises when the first real

@@ -4,7 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import dftatom_b200 as D
 DEFAULTS = {"stream_groups": 4, "rows_wide_from_step": 32, "match_win_until_step": 32, "match_win_nodes": 8192, "use_pdl": 1, "graph_phases": 1, "search_predict": 1,
-            "direct_after": 4, "warm_after": 1, "step_cap": 0}
+            "direct_after": 4, "warm_after": 1, "step_cap": 0, "unit_guess": 1}
 ctx = D.Context(0)
 opts = [D.Options(Z, 14, 25.0, 0.0005, 0.5, 0) for Z in range(1, 93)]
 for grp in sys.argv[1:]:

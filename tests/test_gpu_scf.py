@@ -156,8 +156,8 @@ def test_kernel_shapes_agree(ctx):
                 {"search_kernel": 1, "r_segments": 8}, {"rows_cfg": 0x412}, {"rows_cfg": 0x222}, {"warm_vcycles": 0}, {"match_mode": 2},
                 {"warm_poisson": 0}, {"coarse_exact": 0}, {"warm_poisson": 0, "coarse_exact": 0}, {"warm_until_step": 0}, {"warm_until_step": 12},
                 {"use_graph": 0}, {"match_win_until_step": 0}, {"match_win_until_step": 100, "match_win_nodes": 2048}, {"direct_poisson": 0}, {"direct_after": 1}, {"rows_wide_from_step": 0}, {"rows_wide_from_step": 1}, {"stream_groups": 1},
-                {"graph_phases": 0}, {"rows_wide_from_step": 10, "match_win_until_step": 20}, {"search_predict": 0}, {"use_pdl": 0}]
-    defaults = {"graph_phases": 1, "search_predict": 1, "use_pdl": 1, "r_segments": -1, "seg_threshold": 2400, "warm_vcycles": 7, "match_mode": 0, "search_kernel": 0, "rows_cfg": 0x111, "warm_poisson": 1,
+                {"graph_phases": 0}, {"rows_wide_from_step": 10, "match_win_until_step": 20}, {"search_predict": 0}, {"use_pdl": 0}, {"unit_guess": 0}]
+    defaults = {"graph_phases": 1, "search_predict": 1, "use_pdl": 1, "unit_guess": 1, "r_segments": -1, "seg_threshold": 2400, "warm_vcycles": 7, "match_mode": 0, "search_kernel": 0, "rows_cfg": 0x111, "warm_poisson": 1,
                 "coarse_exact": 1, "warm_until_step": 32, "use_graph": 1, "match_win_until_step": 32, "match_win_nodes": 8192, "stream_groups": 4, "direct_poisson": 1, "direct_after": 4, "rows_wide_from_step": 32}
     for v in variants:
         for k_, x in v.items():
